@@ -1,0 +1,157 @@
+/*
+ * nice_slam_b200.h -- C ABI of the B200-native render-and-backprop path for NICE-SLAM.
+ *
+ * This is the drop-in boundary.  The reference (cvg/nice-slam) has no FFI layer:
+ * its operator boundary is the Python object `slam.renderer` (src/NICE_SLAM.py:91) whose methods
+ * Renderer.render_batch_ray / eval_points / render_img (src/utils/Renderer.py:63,23,200) are called by
+ * Tracker.optimize_cam_in_batch (src/Tracker.py:106) and Mapper.optimize_map (src/Mapper.py:482).
+ * The functions below are what a ctypes binding of that object calls; every
+ * pointer is a raw device pointer owned by the caller (torch storage), every size is a plain integer,
+ * no torch types cross this boundary.  All entry points return 0 on success and a negative nsb_status
+ * on failure; nsb_last_error() gives the message (the Python side raises RuntimeError, the reference's
+ * own convention being plain Python exceptions).
+ *
+ * Threading: calls are asynchronous on the given cudaStream_t (pass the caller's current stream); the
+ * library keeps no per-call state and allocates nothing persistent, so the three reference processes
+ * (tracker, mapper, coarse mapper; src/NICE_SLAM.py:288-307) can each dlopen it independently.
+ */
+#ifndef NICE_SLAM_B200_H_
+#define NICE_SLAM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSB_VERSION 100           /* 1.0.0 */
+#define NSB_C_DIM 32              /* feature channels per grid     (configs/nice_slam.yaml:113) */
+#define NSB_HIDDEN 32             /* decoder width                 (src/conv_onet/models/decoder.py:293) */
+#define NSB_EMBED 93              /* Gaussian-Fourier mapping size (src/conv_onet/models/decoder.py:133) */
+#define NSB_MAX_SAMPLES 256       /* N_samples + N_surface per ray supported by the kernels */
+
+typedef enum { NSB_OK = 0, NSB_ERR_ARG = -1, NSB_ERR_CUDA = -2, NSB_ERR_UNSUPPORTED = -3 } nsb_status;
+
+/* stage of NICE.forward (src/conv_onet/models/decoder.py:312-342) */
+typedef enum { NSB_STAGE_COARSE = 0, NSB_STAGE_MIDDLE = 1, NSB_STAGE_FINE = 2, NSB_STAGE_COLOR = 3 } nsb_stage;
+/* decoder / grid slot indices used by every array-of-4 below */
+typedef enum { NSB_COARSE = 0, NSB_MIDDLE = 1, NSB_FINE = 2, NSB_COLOR = 3 } nsb_level;
+
+/* One hierarchical feature grid, logical shape [1, 32, D, H, W] (src/NICE_SLAM.py:192-250; D=z, H=y, W=x).
+ * Strides are in elements.  Fast path: channels-last (stride_c == 1, stride_w == 32), 128 B per voxel.
+ * The reference's contiguous NCDHW layout is accepted too (slow gathers). */
+typedef struct {
+  const float* data;
+  int32_t D, H, W;
+  int64_t stride_c, stride_d, stride_h, stride_w;
+} nsb_grid;
+
+/* Device pointers to one decoder's parameter tensors exactly as the reference's nn.Module holds them
+ * (contiguous fp32).  MLP (middle/fine/color): src/conv_onet/models/decoder.py:117-164;
+ * MLP_no_xyz (coarse): :224-253 (B, Wc, bc are NULL).
+ *   B      embedder._B              [3][93]
+ *   W[i]   pts_linears.i.weight     [32][in_i]   in = 93,32,32,125,32   (coarse: 32,32,32,64,32)
+ *   b[i]   pts_linears.i.bias       [32]
+ *   Wc[i]  fc_c.i.weight            [32][c_dim]  c_dim = 32 (middle,color) / 64 (fine)
+ *   bc[i]  fc_c.i.bias              [32]
+ *   Wo/bo  output_linear            [n_out][32], [n_out]   n_out = 1 (occupancy) / 4 (color)     */
+typedef struct {
+  const float* B;
+  const float* W[5];
+  const float* b[5];
+  const float* Wc[5];
+  const float* bc[5];
+  const float* Wo;
+  const float* bo;
+} nsb_decoder_params;
+
+/* Canonical flat order of one decoder's parameters / parameter gradients:
+ *   [B] [W0 b0 W1 b1 W2 b2 W3 b3 W4 b4] [Wc0 bc0 ... Wc4 bc4] [Wo bo]      (row-major as above) */
+size_t nsb_flat_decoder_floats(int level);
+/* Offset (in floats) of a named block inside the flat order.  kind: 0=B 1=W 2=b 3=Wc 4=bc 5=Wo 6=bo */
+long long nsb_flat_offset(int level, int kind, int layer);
+/* Size (in floats) of the kernel-side packed weight image of one decoder (padded, TMA-stageable). */
+size_t nsb_packed_decoder_floats(int level);
+
+int nsb_version(void);
+const char* nsb_last_error(void);
+
+/* Pack decoders' parameters into the kernels' shared-memory image (one launch for all four).
+ * params[l] == NULL skips level l.  packed[l] must hold nsb_packed_decoder_floats(l) floats.
+ * Must be re-run whenever the parameters changed (the mapper's Adam mutates them in place,
+ * src/Mapper.py:339-341,504; the tracker deep-copies them, src/Tracker.py:138). */
+int nsb_pack_decoders(const nsb_decoder_params* const params[4], float* const packed[4], void* stream);
+
+/* Batch-global depth maxima used by the sampler: out[0] = max(gt_depth), out[1] = max(gt_depth*1.2f)
+ * (src/utils/Renderer.py:109,144).  n may be 0 (out := 0). */
+int nsb_batch_max_depth(const float* gt_depth, int n, float* out2, void* stream);
+
+/* Ray pre-filter (src/Tracker.py:95-104, src/Mapper.py:471-481): keep[i] = (t_exit(ray i) >= gt_depth[i]). */
+int nsb_bbox_prefilter(const float* rays_o, const float* rays_d, const float* gt_depth, int n,
+                       const double bound[6], uint8_t* keep, void* stream);
+
+typedef struct {
+  int32_t stage;                 /* nsb_stage */
+  int32_t n_rays;
+  int32_t n_samples;             /* cfg rendering.N_samples (32) */
+  int32_t n_surface;             /* cfg rendering.N_surface (16); forced 0 when gt_depth==NULL or stage coarse */
+  double bound[6];               /* scene bound x_lo,x_hi,y_lo,y_hi,z_lo,z_hi as float64 (slam.bound) */
+  double coarse_bound[6];        /* bound * coarse_bound_enlarge (src/NICE_SLAM.py:157) */
+  const float* rays_o;           /* [N,3] */
+  const float* rays_d;           /* [N,3] (not normalised) */
+  const float* gt_depth;         /* [N] or NULL */
+  const float* depth_max;        /* device float[2] from nsb_batch_max_depth, NULL iff gt_depth NULL */
+  const float* t_uniform;        /* device f32[n_samples]  = torch.linspace(0,1,n_samples) */
+  const double* t_surface;       /* device f64[n_surface]  = torch.linspace(0,1,n_surface).double() */
+  nsb_grid grid[4];              /* indexed by nsb_level; only the stage's grids are read */
+  const float* packed[4];        /* packed decoders (nsb_pack_decoders) */
+} nsb_render_inputs;
+
+typedef struct {
+  double* depth;                 /* [N]   rendered depth      (float64 like the reference) */
+  double* var;                   /* [N]   depth variance */
+  float* rgb;                    /* [N,3] */
+  double* z_vals;                /* [N,S] sorted sample depths; required if backward will run, else optional */
+  float* raw;                    /* [N,S,4] (r,g,b,occ logit with the out-of-bound override); same rule */
+  int32_t* corner_idx;           /* optional [N,S,3]: (ix0,iy0,iz0) of the stage's finest occupancy grid */
+} nsb_forward_outputs;
+
+/* Forward: sample -> gather -> decode -> composite  (Renderer.render_batch_ray, src/utils/Renderer.py:63-198) */
+int nsb_render_forward(const nsb_render_inputs* in, const nsb_forward_outputs* out, void* stream);
+
+typedef struct {
+  const double* z_vals;          /* [N,S] from forward */
+  const float* raw;              /* [N,S,4] from forward */
+  const double* g_depth;         /* [N]   dL/d depth */
+  const double* g_var;           /* [N]   dL/d var   or NULL (0) */
+  const float* g_rgb;            /* [N,3] dL/d rgb   or NULL (0) */
+  float* d_rays_o;               /* [N,3] or NULL */
+  float* d_rays_d;               /* [N,3] or NULL */
+  float* d_grid[4];              /* dense gradient, same shape+strides as grid[l]; ACCUMULATED (caller zeroes); NULL = skip */
+  float* d_flat[4];              /* decoder parameter gradients, canonical flat order; ACCUMULATED; NULL = skip */
+} nsb_backward_args;
+
+/* Backward of the same path (what loss.backward() does at src/Tracker.py:125 / src/Mapper.py:503). */
+int nsb_render_backward(const nsb_render_inputs* in, const nsb_backward_args* bw, void* stream);
+
+/* Loss seeds.  Tracking (src/Tracker.py:108-123): residual r = |gt-depth|/sqrt(var+1e-10), mask =
+ * (r < 10*median(r)) & (gt>0) when handle_dynamic else gt>0; loss = sum_mask r + w_color*sum_mask|gt_rgb-rgb|.
+ * Mapping (src/Mapper.py:487-493): loss = sum_{gt>0}|gt-depth| (+ w_color*sum|gt_rgb-rgb| in stage color).
+ * gt_rgb is float64 [N,3] for tracking (dataset colour is f64) and float32 for mapping (Mapper.py:462).
+ * Writes g_depth[N] (f64), g_rgb[N,3] (f32) and loss[1] (f64). */
+int nsb_tracking_seeds(const double* depth, const double* var, const float* rgb, const float* gt_depth,
+                       const double* gt_rgb, int n, double w_color, int handle_dynamic, int use_color,
+                       double* g_depth, float* g_rgb, double* loss, void* workspace, size_t workspace_bytes,
+                       void* stream);
+int nsb_mapping_seeds(const double* depth, const float* rgb, const float* gt_depth, const float* gt_rgb, int n,
+                      double w_color, int use_color, double* g_depth, float* g_rgb, double* loss, void* stream);
+size_t nsb_tracking_seeds_workspace(int n);
+
+/* Points-only decode (Renderer.eval_points, src/utils/Renderer.py:23-61): p f64 [P,3] -> raw f32 [P,4]. */
+int nsb_eval_points(const nsb_render_inputs* in, const double* points, int n_points, float* raw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NICE_SLAM_B200_H_ */
