@@ -130,7 +130,11 @@ typedef struct {
   float* d_rays_d;               /* [N,3] or NULL */
   float* d_grid[4];              /* dense gradient, same shape+strides as grid[l]; ACCUMULATED (caller zeroes); NULL = skip */
   float* d_flat[4];              /* decoder parameter gradients, canonical flat order; ACCUMULATED; NULL = skip */
+  void* workspace;               /* device scratch of nsb_backward_workspace_bytes() bytes, 16-byte aligned;
+                                    required iff any d_flat[l] != NULL (the library zeroes and consumes it) */
 } nsb_backward_args;
+
+size_t nsb_backward_workspace_bytes(void);
 
 /* Backward of the same path (what loss.backward() does at src/Tracker.py:125 / src/Mapper.py:503). */
 int nsb_render_backward(const nsb_render_inputs* in, const nsb_backward_args* bw, void* stream);

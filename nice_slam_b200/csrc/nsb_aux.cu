@@ -1,0 +1,251 @@
+// nsb_aux.cu -- small kernels on either side of the render kernels + library plumbing:
+//   decoder packing / gradient unpacking, batch depth maxima, ray pre-filter, loss seeds.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "nsb_common.cuh"
+#include "nsb_geom.cuh"
+
+namespace nsb {
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return NSB_OK;
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return NSB_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------------------------------------ pack / unpack
+// Maps every element of the reference parameter tensors to its slot in the packed image (nsb_common.cuh).
+// DIR = 0: packed[slot] = param[i] ; DIR = 1: flat_grad[flat_i] += packed_grad[slot]
+struct PackArgs { nsb_decoder_params p[4]; float* packed[4]; float* flat[4]; int present[4]; };
+
+template <int LV, int DIR>
+__device__ void pack_level(const PackArgs& A) {
+  using D = Dec<LV>;
+  float* pk = A.packed[LV];
+  const nsb_decoder_params& p = A.p[LV];
+  float* fl = A.flat[LV];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (DIR == 0) {
+    for (int i = tid; i < D::TOTAL; i += nt) pk[i] = 0.0f;         // zero pads
+    __syncthreads();
+  }
+  auto xfer = [&](const float* src, long long flat_off, int n, auto slot) {
+    for (int i = tid; i < n; i += nt) {
+      const int s = slot(i);
+      if (DIR == 0) pk[s] = src[i]; else fl[flat_off + i] += pk[s];
+    }
+  };
+  if (D::XYZ) xfer(p.B, flat_offset(LV, 0, 0), 3 * kEmb, [](int i) { return D::o_B + (i / kEmb) * kEmbPad + i % kEmb; });
+  for (int l = 0; l < 5; l++) {
+    const int nin = dec_in(LV, l);
+    if (l == 0) xfer(p.W[0], flat_offset(LV, 1, 0), 32 * nin, [=](int i) { return D::o_W0 + (i / nin) * D::PF + i % nin; });
+    else if (l == 3) xfer(p.W[3], flat_offset(LV, 1, 3), 32 * nin, [=](int i) {
+      const int o = i / nin, k = i % nin;
+      return k < D::FIRST ? D::o_W3E + o * D::PF + k : D::o_W3H + o * D::PH + (k - D::FIRST); });
+    else {
+      const int ow = l == 1 ? D::o_W1 : l == 2 ? D::o_W2 : D::o_W4;
+      xfer(p.W[l], flat_offset(LV, 1, l), 32 * 32, [=](int i) { return ow + (i / 32) * D::PH + i % 32; });
+    }
+    xfer(p.b[l], flat_offset(LV, 2, l), 32, [=](int i) { return D::o_b + l * 32 + i; });
+    if (D::XYZ) {
+      xfer(p.Wc[l], flat_offset(LV, 3, l), 32 * D::CD, [=](int i) { return D::o_WC + (l * 32 + i / D::CD) * D::PC + i % D::CD; });
+      xfer(p.bc[l], flat_offset(LV, 4, l), 32, [=](int i) { return D::o_bc + l * 32 + i; });
+    }
+  }
+  xfer(p.Wo, flat_offset(LV, 5, 0), D::NO * 32, [](int i) { return D::o_WO + (i / 32) * D::PH + i % 32; });
+  xfer(p.bo, flat_offset(LV, 6, 0), D::NO, [](int i) { return D::o_bo + i; });
+}
+
+template <int DIR>
+__global__ void pack_kernel(const __grid_constant__ PackArgs A) {
+  const int lv = blockIdx.x;
+  if (!A.present[lv]) return;
+  switch (lv) {
+    case 0: pack_level<0, DIR>(A); break;
+    case 1: pack_level<1, DIR>(A); break;
+    case 2: pack_level<2, DIR>(A); break;
+    default: pack_level<3, DIR>(A); break;
+  }
+}
+
+int launch_unpack_grads(float* const d_packed[4], float* const d_flat[4], cudaStream_t st) {
+  PackArgs A; memset(&A, 0, sizeof(A));
+  for (int l = 0; l < 4; l++) { A.packed[l] = d_packed[l]; A.flat[l] = d_flat[l]; A.present[l] = d_packed[l] != nullptr && d_flat[l] != nullptr; }
+  pack_kernel<1><<<4, 256, 0, st>>>(A);
+  return check_cuda(cudaGetLastError(), "unpack_grads launch");
+}
+
+// ------------------------------------------------------------------------------------------------ batch max
+__global__ void batch_max_kernel(const float* __restrict__ gt, int n, float* __restrict__ out2) {
+  __shared__ float red[32];
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, gt[i]);
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY;
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) {
+      if (n <= 0) m = 0.0f;
+      out2[0] = m;                       // torch.max(gt_depth)            (Renderer.py:144)
+      out2[1] = __fmul_rn(m, 1.2f);      // torch.max(gt_depth*1.2): x -> fl(1.2f*x) is monotone, so max commutes (Renderer.py:109)
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ ray pre-filter
+struct Bound6 { double b[6]; };
+__global__ void prefilter_kernel(const float* __restrict__ ro, const float* __restrict__ rd, const float* __restrict__ gt,
+                                 int n, const Bound6 B, uint8_t* __restrict__ keep) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float o[3] = {ro[3 * i], ro[3 * i + 1], ro[3 * i + 2]}, d[3] = {rd[3 * i], rd[3 * i + 1], rd[3 * i + 2]};
+  const double t = ray_far_bb(B.b, o, d);
+  keep[i] = (t >= (double)gt[i]) ? 1 : 0;          // Tracker.py:101 / Mapper.py:478
+}
+
+// ------------------------------------------------------------------------------------------------ loss seeds
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x < 32) {
+    t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  __syncthreads();
+  return t;   // valid in thread 0
+}
+__device__ __forceinline__ double sgn(double x) { return (x > 0.0) - (x < 0.0); }
+
+// Tracker.optimize_cam_in_batch loss (src/Tracker.py:108-123); single CTA, residuals staged in `res`.
+__global__ void tracking_seeds_kernel(const double* __restrict__ depth, const double* __restrict__ var, const float* __restrict__ rgb,
+                                      const float* __restrict__ gt, const double* __restrict__ gt_rgb, int n, double w_color,
+                                      int handle_dynamic, int use_color, double* __restrict__ g_depth, float* __restrict__ g_rgb,
+                                      double* __restrict__ loss, double* __restrict__ res) {
+  __shared__ double red[32];
+  __shared__ double med_s;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    res[i] = fabs((double)gt[i] - depth[i]) / sqrt(var[i] + 1e-10);
+  __syncthreads();
+  if (handle_dynamic) {            // torch.median = lower median = element of rank (n-1)/2 in the stable sorted order
+    const int kth = (n - 1) / 2;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const double ri = res[i]; int rank = 0;
+      for (int j = 0; j < n; j++) { const double rj = res[j]; rank += (z_less(rj, ri) || (!z_less(ri, rj) && j < i)) ? 1 : 0; }
+      if (rank == kth) med_s = ri;
+    }
+    __syncthreads();
+  }
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double r = res[i];
+    bool m = gt[i] > 0.0f;
+    if (handle_dynamic) m = m && (r < 10.0 * med_s);
+    double gd = 0.0; float gc[3] = {0.f, 0.f, 0.f};
+    if (m) {
+      acc += r;
+      gd = -sgn((double)gt[i] - depth[i]) / sqrt(var[i] + 1e-10);
+      if (use_color) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) { const double df = gt_rgb[3 * i + a] - (double)rgb[3 * i + a]; acc += w_color * fabs(df); gc[a] = (float)(-w_color * sgn(df)); }
+      }
+    }
+    g_depth[i] = gd; g_rgb[3 * i] = gc[0]; g_rgb[3 * i + 1] = gc[1]; g_rgb[3 * i + 2] = gc[2];
+  }
+  const double tot = block_sum(acc, red);
+  if (threadIdx.x == 0) loss[0] = tot;
+}
+
+// Mapper.optimize_map loss (src/Mapper.py:487-493); single CTA (deterministic sum)
+__global__ void mapping_seeds_kernel(const double* __restrict__ depth, const float* __restrict__ rgb, const float* __restrict__ gt,
+                                     const float* __restrict__ gt_rgb, int n, double w_color, int use_color,
+                                     double* __restrict__ g_depth, float* __restrict__ g_rgb, double* __restrict__ loss) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double gd = 0.0;
+    if (gt[i] > 0.0f) { const double df = (double)gt[i] - depth[i]; acc += fabs(df); gd = -sgn(df); }
+    g_depth[i] = gd;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      float g = 0.0f;
+      if (use_color) { const float df = gt_rgb[3 * i + a] - rgb[3 * i + a]; acc += w_color * (double)fabsf(df); g = (float)(-w_color * sgn((double)df)); }
+      g_rgb[3 * i + a] = g;
+    }
+  }
+  const double tot = block_sum(acc, red);
+  if (threadIdx.x == 0) loss[0] = tot;
+}
+
+}  // namespace nsb
+
+using namespace nsb;
+
+extern "C" int nsb_version(void) { return NSB_VERSION; }
+extern "C" const char* nsb_last_error(void) { return g_err; }
+extern "C" size_t nsb_flat_decoder_floats(int level) { return level < 0 || level > 3 ? 0 : (size_t)flat_offset(level, 7, 0); }
+extern "C" long long nsb_flat_offset(int level, int kind, int layer) { return level < 0 || level > 3 ? -1 : flat_offset(level, kind, layer); }
+extern "C" size_t nsb_packed_decoder_floats(int level) { return level < 0 || level > 3 ? 0 : (size_t)packed_floats(level); }
+
+extern "C" int nsb_pack_decoders(const nsb_decoder_params* const params[4], float* const packed[4], void* stream) {
+  if (!params || !packed) { set_error("params / packed NULL"); return NSB_ERR_ARG; }
+  PackArgs A; memset(&A, 0, sizeof(A));
+  for (int l = 0; l < 4; l++) {
+    if (!params[l]) continue;
+    if (!packed[l]) { set_error("packed[%d] NULL", l); return NSB_ERR_ARG; }
+    const nsb_decoder_params& p = *params[l];
+    bool ok = p.Wo && p.bo;
+    for (int i = 0; i < 5; i++) ok = ok && p.W[i] && p.b[i] && (l == 0 || (p.Wc[i] && p.bc[i]));
+    if (l != 0) ok = ok && p.B;
+    if (!ok) { set_error("decoder %d has NULL parameter pointers", l); return NSB_ERR_ARG; }
+    A.p[l] = p; A.packed[l] = packed[l]; A.present[l] = 1;
+  }
+  pack_kernel<0><<<4, 256, 0, (cudaStream_t)stream>>>(A);
+  return check_cuda(cudaGetLastError(), "pack_decoders launch");
+}
+
+extern "C" int nsb_batch_max_depth(const float* gt_depth, int n, float* out2, void* stream) {
+  if (!out2 || (n > 0 && !gt_depth) || n < 0) { set_error("batch_max_depth: bad arguments"); return NSB_ERR_ARG; }
+  batch_max_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(gt_depth, n, out2);
+  return check_cuda(cudaGetLastError(), "batch_max launch");
+}
+
+extern "C" int nsb_bbox_prefilter(const float* rays_o, const float* rays_d, const float* gt_depth, int n,
+                                  const double bound[6], uint8_t* keep, void* stream) {
+  if (n < 0 || (n > 0 && (!rays_o || !rays_d || !gt_depth || !keep || !bound))) { set_error("bbox_prefilter: bad arguments"); return NSB_ERR_ARG; }
+  if (n == 0) return NSB_OK;
+  Bound6 B; for (int i = 0; i < 6; i++) B.b[i] = bound[i];
+  prefilter_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, gt_depth, n, B, keep);
+  return check_cuda(cudaGetLastError(), "prefilter launch");
+}
+
+extern "C" size_t nsb_tracking_seeds_workspace(int n) { return (size_t)(n > 0 ? n : 1) * sizeof(double); }
+
+extern "C" int nsb_tracking_seeds(const double* depth, const double* var, const float* rgb, const float* gt_depth,
+                                  const double* gt_rgb, int n, double w_color, int handle_dynamic, int use_color,
+                                  double* g_depth, float* g_rgb, double* loss, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+  if (n < 0 || !loss || (n > 0 && (!depth || !var || !rgb || !gt_depth || !g_depth || !g_rgb || (use_color && !gt_rgb)))) {
+    set_error("tracking_seeds: bad arguments"); return NSB_ERR_ARG; }
+  if (!workspace || workspace_bytes < nsb_tracking_seeds_workspace(n)) { set_error("tracking_seeds: workspace too small"); return NSB_ERR_ARG; }
+  tracking_seeds_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(depth, var, rgb, gt_depth, gt_rgb, n, w_color, handle_dynamic, use_color,
+                                                               g_depth, g_rgb, loss, (double*)workspace);
+  return check_cuda(cudaGetLastError(), "tracking_seeds launch");
+}
+
+extern "C" int nsb_mapping_seeds(const double* depth, const float* rgb, const float* gt_depth, const float* gt_rgb, int n,
+                                 double w_color, int use_color, double* g_depth, float* g_rgb, double* loss, void* stream) {
+  if (n < 0 || !loss || (n > 0 && (!depth || !rgb || !gt_depth || !g_depth || !g_rgb || (use_color && !gt_rgb)))) {
+    set_error("mapping_seeds: bad arguments"); return NSB_ERR_ARG; }
+  mapping_seeds_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(depth, rgb, gt_depth, gt_rgb, n, w_color, use_color, g_depth, g_rgb, loss);
+  return check_cuda(cudaGetLastError(), "mapping_seeds launch");
+}

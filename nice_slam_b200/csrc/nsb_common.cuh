@@ -1,0 +1,128 @@
+// nsb_common.cuh -- shared constants, packed-decoder layout and PTX helpers for the sm_100a kernels.
+//
+// Packed decoder image = what one CTA stages into shared memory with a single TMA bulk copy
+// (cp.async.bulk) before it evaluates that decoder.  Every matrix keeps the reference's [out][in]
+// orientation (nn.Linear.weight, src/conv_onet/models/decoder.py:117-164) with the row pitch padded to
+// pitch == 4 (mod 8) floats, which makes BOTH access patterns of the kernels bank-conflict free:
+//   forward   acc[pt][n] += A[k][pt] * W[n][k]   (lanes stride rows n = og + 8j, float4 along k)
+//   backward  dx[pt][i]  += DU[o][pt] * W[o][i]  (lanes read consecutive float4 along i in row o)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/nice_slam_b200.h"
+
+namespace nsb {
+
+constexpr int kHid = 32;
+constexpr int kEmb = 93;
+constexpr int kEmbPad = 96;
+constexpr int kChunk = 16;          // points per warp work item
+constexpr int kRowF = 16;           // floats per activation row (one value per point of the chunk)
+constexpr int kMaxPtsPerBlock = 384;
+constexpr int kMaxRaysPerBlock = 24;
+
+// ---------------------------------------------------------------------------------------------
+// Per-level decoder shape + packed layout (offsets in floats, every block 16-byte aligned)
+// ---------------------------------------------------------------------------------------------
+template <int LV>
+struct Dec {
+  static constexpr bool XYZ = LV != 0;                 // MLP (xyz + Fourier embedding) vs MLP_no_xyz
+  static constexpr int CD = LV == 2 ? 64 : 32;         // fc_c input width (fine: [fine | middle] concat)
+  static constexpr int NO = LV == 3 ? 4 : 1;           // outputs
+  static constexpr int FIRST = XYZ ? kEmb : 32;        // width of the first-layer / skip input
+  static constexpr int FIRSTP = XYZ ? kEmbPad : 32;    // padded to a multiple of 4
+  static constexpr int PF = FIRSTP + 4;                // row pitch of W0 / W3E
+  static constexpr int PH = kHid + 4;                  // row pitch of the 32-wide matrices
+  static constexpr int PC = CD + 4;                    // row pitch of the fc_c matrices
+  static constexpr int o_B = 0;                        // [3][96]
+  static constexpr int o_W0 = XYZ ? 3 * kEmbPad : 0;   // [32][PF]
+  static constexpr int o_W1 = o_W0 + 32 * PF;          // [32][PH]
+  static constexpr int o_W2 = o_W1 + 32 * PH;
+  static constexpr int o_W3E = o_W2 + 32 * PH;         // [32][PF]  skip part (embedding / coarse feature)
+  static constexpr int o_W3H = o_W3E + 32 * PF;        // [32][PH]  hidden part
+  static constexpr int o_W4 = o_W3H + 32 * PH;
+  static constexpr int o_WC = o_W4 + 32 * PH;          // [5*32][PC]  (XYZ only)
+  static constexpr int o_WO = o_WC + (XYZ ? 160 * PC : 0);   // [4][PH]   rows >= NO are zero
+  static constexpr int o_b = o_WO + 4 * PH;            // [5][32]
+  static constexpr int o_bc = o_b + 160;               // [5][32]    (XYZ only)
+  static constexpr int o_bo = o_bc + (XYZ ? 160 : 0);  // [4]
+  static constexpr int TOTAL = o_bo + 4;
+  static_assert(TOTAL % 4 == 0, "packed image must be a multiple of 16 bytes");
+  // activation rows per warp
+  static constexpr int ROWS_FWD = FIRSTP * (XYZ ? 1 : 0) + 64 + 64;                 // E | C | HA | HB
+  static constexpr int ROWS_BWD = FIRSTP * (XYZ ? 1 : 0) + 64 + 160 + 32 + 32;      // E | C | S1..S5 | DU | DU3
+};
+
+__host__ __device__ constexpr int packed_floats(int lv) {
+  return lv == 0 ? Dec<0>::TOTAL : lv == 1 ? Dec<1>::TOTAL : lv == 2 ? Dec<2>::TOTAL : Dec<3>::TOTAL;
+}
+constexpr int kMaxPacked = Dec<2>::TOTAL;
+constexpr int kRowsFwd = Dec<2>::ROWS_FWD;     // 224
+constexpr int kRowsBwd = Dec<2>::ROWS_BWD;     // 384
+
+// canonical flat layout (include/nice_slam_b200.h): kind 0=B 1=W 2=b 3=Wc 4=bc 5=Wo 6=bo 7=total
+__host__ __device__ inline int dec_in(int lv, int i) {
+  if (lv == 0) return i == 3 ? 64 : 32;
+  return i == 0 ? kEmb : (i == 3 ? kEmb + kHid : kHid);
+}
+__host__ __device__ inline long long flat_offset(int lv, int kind, int layer) {
+  const bool xyz = lv != 0;
+  const int cd = lv == 2 ? 64 : 32, no = lv == 3 ? 4 : 1;
+  long long off = 0;
+  if (xyz) { if (kind == 0) return off; off += 3 * kEmb; }
+  for (int i = 0; i < 5; i++) {
+    if (kind == 1 && layer == i) return off; off += (long long)kHid * dec_in(lv, i);
+    if (kind == 2 && layer == i) return off; off += kHid;
+  }
+  if (xyz) for (int i = 0; i < 5; i++) {
+    if (kind == 3 && layer == i) return off; off += (long long)kHid * cd;
+    if (kind == 4 && layer == i) return off; off += kHid;
+  }
+  if (kind == 5) return off; off += (long long)no * kHid;
+  if (kind == 6) return off; off += no;
+  return off;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA bulk copy (global -> shared), vector reductions
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared::cta, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// 16-byte vector reduction into global memory (sm_90+): one L2 atomic transaction for 4 floats
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// activation-row swizzle: element (row r, point pt) lives at r*16 + ((pt>>2) ^ (r>>1))&3)*4 + (pt&3)
+__device__ __forceinline__ int swz(int r, int q) { return ((q ^ (r >> 1)) & 3) << 2; }
+__device__ __forceinline__ int act_idx(int r, int pt) { return r * kRowF + swz(r, pt >> 2) + (pt & 3); }
+
+// error plumbing shared by the API translation units
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+
+}  // namespace nsb

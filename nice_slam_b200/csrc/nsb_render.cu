@@ -1,0 +1,630 @@
+// nsb_render.cu -- the render-and-backprop kernels and their C-ABI entry points.
+//
+//   render_fwd_kernel : sample -> trilinear gather -> decoders -> alpha-composite      (Renderer.render_batch_ray,
+//                       src/utils/Renderer.py:63-198; eval_points :23-61; raw2outputs_nerf_color, src/common.py:204-245)
+//   render_bwd_kernel : recompute + hand-rolled backward into rays, grid voxels and decoder weights
+//                       (what loss.backward() does at src/Tracker.py:125 / src/Mapper.py:503)
+//
+// Work decomposition: a CTA owns `rays_per_block` consecutive rays (all S samples of each, so compositing and
+// the per-ray scan stay inside the CTA); its points are cut into chunks of 16 that the warps process
+// independently (nsb_mlp.cuh).  Decoders are evaluated one after the other; each decoder's packed weight image
+// is staged into shared memory with one TMA bulk copy that overlaps with the first chunk's feature gather.
+#include <cstdarg>
+#include <cstdio>
+#include "nsb_common.cuh"
+#include "nsb_geom.cuh"
+#include "nsb_mlp.cuh"
+
+namespace nsb {
+
+// ------------------------------------------------------------------------------------------------
+// trilinear gather / scatter of one chunk (8 lanes per point, 16-byte channel quads, 4 points per pass)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool grid_fast(const nsb_grid& g) { return g.stride_c == 1; }
+
+__device__ __forceinline__ float4 grid_load4(const nsb_grid& g, long long off, int c0, bool fast) {
+  if (fast) return ldg_f4(g.data + off + c0);
+  return make_float4(__ldg(g.data + off + (long long)c0 * g.stride_c), __ldg(g.data + off + (long long)(c0 + 1) * g.stride_c),
+                     __ldg(g.data + off + (long long)(c0 + 2) * g.stride_c), __ldg(g.data + off + (long long)(c0 + 3) * g.stride_c));
+}
+
+// rows [row0,row0+32) <- features of the 16 points; xn = normalised coords of point (lane & 15)
+__device__ __forceinline__ void gather_chunk(const nsb_grid& g, float* __restrict__ act, int row0, const float xn[3], int lane) {
+  const bool fast = grid_fast(g);
+  const int q = lane & 7;
+#pragma unroll 2
+  for (int it = 0; it < 4; it++) {
+    const int pt = it * 4 + (lane >> 3);
+    float x[3];
+    x[0] = __shfl_sync(0xffffffffu, xn[0], pt); x[1] = __shfl_sync(0xffffffffu, xn[1], pt); x[2] = __shfl_sync(0xffffffffu, xn[2], pt);
+    const Tri t = make_tri(x, g.W, g.H, g.D);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      int cx, cy, cz;
+      if (tri_corner(t, k, g.W, g.H, g.D, cx, cy, cz)) {
+        const long long off = cz * g.stride_d + cy * g.stride_h + cx * g.stride_w;
+        const float4 v = grid_load4(g, off, 4 * q, fast);
+        const float w = tri_weight(t, k);
+        acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y); acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
+      }
+    }
+    act[act_idx(row0 + 4 * q + 0, pt)] = acc.x; act[act_idx(row0 + 4 * q + 1, pt)] = acc.y;
+    act[act_idx(row0 + 4 * q + 2, pt)] = acc.z; act[act_idx(row0 + 4 * q + 3, pt)] = acc.w;
+  }
+}
+
+// Backward of gather_chunk: rows [row0,row0+32) hold dL/dc.  Scatter-adds w_k * dc into dgrid (if non-null)
+// and returns through gx (valid in lanes with (lane&7)==0, for point it*4 + lane>>3 of pass `it`) the gradient
+// w.r.t. the normalised coordinate (grid_sampler_3d_backward incl. the clip multiplier, GridSampler.h:66-82).
+template <typename F>
+__device__ __forceinline__ void scatter_chunk(const nsb_grid& g, float* __restrict__ dgrid, const float* __restrict__ act,
+                                              int row0, const float xn[3], int lane, F&& emit) {
+  const bool fast = grid_fast(g);
+  const int q = lane & 7;
+#pragma unroll 1
+  for (int it = 0; it < 4; it++) {
+    const int pt = it * 4 + (lane >> 3);
+    float x[3];
+    x[0] = __shfl_sync(0xffffffffu, xn[0], pt); x[1] = __shfl_sync(0xffffffffu, xn[1], pt); x[2] = __shfl_sync(0xffffffffu, xn[2], pt);
+    const Tri t = make_tri(x, g.W, g.H, g.D);
+    float dc[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) dc[c] = act[act_idx(row0 + 4 * q + c, pt)];
+    float gi[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      int cx, cy, cz;
+      if (tri_corner(t, k, g.W, g.H, g.D, cx, cy, cz)) {
+        const long long off = cz * g.stride_d + cy * g.stride_h + cx * g.stride_w;
+        const float4 v = grid_load4(g, off, 4 * q, fast);
+        const float dot = v.x * dc[0] + v.y * dc[1] + v.z * dc[2] + v.w * dc[3];
+        if (dgrid != nullptr) {
+          const float w = tri_weight(t, k);
+          if (fast) red_add_v4(dgrid + off + 4 * q, w * dc[0], w * dc[1], w * dc[2], w * dc[3]);
+          else {
+#pragma unroll
+            for (int c = 0; c < 4; c++) atomicAdd(dgrid + off + (long long)(4 * q + c) * g.stride_c, w * dc[c]);
+          }
+        }
+        const float wx = (k & 1) ? t.w1[0] : t.w0[0], wy = (k & 2) ? t.w1[1] : t.w0[1], wz = (k & 4) ? t.w1[2] : t.w0[2];
+        gi[0] += ((k & 1) ? 1.f : -1.f) * wy * wz * dot;
+        gi[1] += ((k & 2) ? 1.f : -1.f) * wx * wz * dot;
+        gi[2] += ((k & 4) ? 1.f : -1.f) * wx * wy * dot;
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      float v = gi[a];
+      v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
+      gi[a] = v;
+    }
+    if (q == 0) {
+      const int size[3] = {g.W, g.H, g.D};
+      float gx[3];
+#pragma unroll
+      for (int a = 0; a < 3; a++) gx[a] = t.clipg[a] * ((float)(size[a] - 1) * 0.5f) * gi[a];
+      emit(pt, gx);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel parameters
+// ------------------------------------------------------------------------------------------------
+struct KParams {
+  nsb_render_inputs in;
+  nsb_forward_outputs fo;       // forward
+  nsb_backward_args bw;         // backward
+  float* d_packed[4];           // backward: packed-layout weight-gradient images (WGRAD decoders)
+  const double* points;         // points-only mode: f64 [P,3]
+  float* points_raw;            // points-only mode: f32 [P,4]
+  int n_points;
+  int rays_per_block;
+  int S;                        // samples per ray actually used
+  int has_gt;
+  int n_dec;                    // decoders of this stage, in the reference's evaluation order
+  int dec[3];
+  int wbytes;                   // bytes reserved for the weight image in shared memory
+  int max_pts, max_rays;        // per-CTA capacities the shared-memory carve-up was sized for
+};
+
+struct Smem {                   // carve-up of dynamic shared memory (all offsets 16-byte aligned)
+  float* wt; uint64_t* bar; float* rays; double* far; double* zs; float* raw; double* dp; float* gocc; float* wgt;
+  unsigned char* inb; float* act;
+};
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+__host__ __device__ inline size_t smem_layout(int wbytes, int max_pts, int max_rays, int warps, int rows, bool bwd, Smem* s, unsigned char* base) {
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align16(o + bytes); return r; };
+  size_t o_wt = take(wbytes), o_bar = take(16), o_rays = take(sizeof(float) * 8 * max_rays), o_far = take(sizeof(double) * max_rays);
+  size_t o_zs = take(sizeof(double) * max_pts), o_raw = take(sizeof(float) * 4 * max_pts);
+  size_t o_dp = bwd ? take(sizeof(double) * 3 * max_pts) : 0, o_gocc = bwd ? take(sizeof(float) * max_pts) : 0, o_wgt = bwd ? take(sizeof(float) * max_pts) : 0;
+  size_t o_inb = take(max_pts);
+  size_t o_act = take((size_t)warps * rows * kRowF * sizeof(float));
+  if (s) {
+    s->wt = (float*)(base + o_wt); s->bar = (uint64_t*)(base + o_bar); s->rays = (float*)(base + o_rays); s->far = (double*)(base + o_far);
+    s->zs = (double*)(base + o_zs); s->raw = (float*)(base + o_raw); s->dp = (double*)(base + o_dp); s->gocc = (float*)(base + o_gocc);
+    s->wgt = (float*)(base + o_wgt); s->inb = base + o_inb; s->act = (float*)(base + o_act);
+  }
+  return o;
+}
+
+// rays[r*8 + {0,1,2}] = o, {3,4,5} = d, 6 = near(f32), 7 = gt ; far[r] (f64)
+__device__ __forceinline__ void block_setup_rays(const KParams& P, const Smem& sm, int r0, int nr, float gtmax12) {
+  for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+    float o[3], d[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) { o[a] = P.in.rays_o[3 * (r0 + r) + a]; d[a] = P.in.rays_d[3 * (r0 + r) + a]; }
+    const float gt = P.has_gt ? P.in.gt_depth[r0 + r] : 0.0f;
+    const RaySampler rs = make_sampler(P.in.bound, o, d, P.has_gt, gt, gtmax12);
+#pragma unroll
+    for (int a = 0; a < 3; a++) { sm.rays[8 * r + a] = o[a]; sm.rays[8 * r + 3 + a] = d[a]; }
+    sm.rays[8 * r + 6] = rs.near; sm.rays[8 * r + 7] = gt; sm.far[r] = rs.far;
+  }
+}
+
+__device__ __forceinline__ void issue_weights(const KParams& P, const Smem& sm, int lv) {
+  // one elected thread: order prior generic-proxy reads of the buffer before the async-proxy overwrite, then TMA
+  fence_proxy_async();
+  const uint32_t bytes = (uint32_t)packed_floats(lv) * 4u;
+  mbar_expect_tx(sm.bar, bytes);
+  const char* src = reinterpret_cast<const char*>(P.in.packed[lv]);
+  char* dst = reinterpret_cast<char*>(sm.wt);
+  for (uint32_t off = 0; off < bytes; off += 32768u) {
+    const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+    tma_bulk_g2s(dst + off, src + off, n, sm.bar);
+  }
+}
+
+// geometry of this lane's point (lane & 15) of chunk `chunk`
+__device__ __forceinline__ void chunk_point(const KParams& P, const Smem& sm, int chunk, int Pb, int lane, int& lp, PointGeom& G) {
+  lp = chunk * kChunk + (lane & 15);
+  const int lpc = lp < Pb ? lp : Pb - 1;
+  if (P.points != nullptr) {
+    const long long gp = (long long)blockIdx.x * P.rays_per_block + lpc;      // points mode: rays_per_block == points per block
+    const double pin[3] = {P.points[3 * gp], P.points[3 * gp + 1], P.points[3 * gp + 2]};
+    make_point_from_p(P.in.bound, P.in.coarse_bound, pin, G);
+  } else {
+    const int ray = lpc / P.S;
+    const float* rr = sm.rays + 8 * ray;
+    const float o[3] = {rr[0], rr[1], rr[2]}, d[3] = {rr[3], rr[4], rr[5]};
+    make_point(P.in.bound, P.in.coarse_bound, o, d, sm.zs[lpc], G);
+  }
+}
+
+template <int LV>
+__device__ __forceinline__ void chunk_forward(const KParams& P, const Smem& sm, float* act, int chunk, int Pb,
+                                              const LaneId& L, uint32_t parity, bool first_dec) {
+  using D = Dec<LV>;
+  int lp; PointGeom G;
+  chunk_point(P, sm, chunk, Pb, L.lane, lp, G);
+  const float* xn = LV == 0 ? G.xnc : G.xn;
+  gather_chunk(P.in.grid[LV], act, R_C, xn, L.lane);
+  if (LV == 2) gather_chunk(P.in.grid[1], act, R_C + 32, G.xn, L.lane);   // no_grad middle concat (decoder.py:182-187)
+  mbar_wait(sm.bar, parity);
+  if (D::XYZ) embed_chunk(act, sm.wt + D::o_B, G.pf, L.lane);
+  __syncwarp();
+  uint32_t masks[5]; float out[4];
+  mlp_forward<LV, false>(sm.wt, act, L, masks, out);
+  if (L.lane < 16 && lp < Pb) {
+    if (LV == 3) { sm.raw[4 * lp] = out[0]; sm.raw[4 * lp + 1] = out[1]; sm.raw[4 * lp + 2] = out[2]; }
+    else sm.raw[4 * lp + 3] += out[0];
+    if (first_dec) {
+      sm.inb[lp] = (unsigned char)G.inb;
+      if (P.fo.corner_idx != nullptr) {
+        const nsb_grid& g = P.in.grid[LV];
+        const Tri t = make_tri(xn, g.W, g.H, g.D);
+        const long long gp = ((long long)blockIdx.x * P.rays_per_block) * P.S + lp;
+        P.fo.corner_idx[3 * gp] = t.i0[0]; P.fo.corner_idx[3 * gp + 1] = t.i0[1]; P.fo.corner_idx[3 * gp + 2] = t.i0[2];
+      }
+    }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ------------------------------------------------------------------------------------------------
+// forward kernel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1) render_fwd_kernel(const __grid_constant__ KParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5;
+  const LaneId L = make_lane(threadIdx.x & 31);
+  Smem sm;
+  smem_layout(P.wbytes, P.max_pts, P.max_rays, warps, kRowsFwd, false, &sm, smem_raw);
+  float* act = sm.act + (size_t)warp * kRowsFwd * kRowF;
+  const bool points_mode = P.points != nullptr;
+
+  int r0 = 0, nr = 0, Pb;
+  if (points_mode) {
+    const long long p0 = (long long)blockIdx.x * P.rays_per_block;
+    Pb = (int)((P.n_points - p0) < P.rays_per_block ? (P.n_points - p0) : P.rays_per_block);
+  } else {
+    r0 = blockIdx.x * P.rays_per_block;
+    nr = P.in.n_rays - r0 < P.rays_per_block ? P.in.n_rays - r0 : P.rays_per_block;
+    Pb = nr * P.S;
+  }
+  if (threadIdx.x == 0) { mbar_init(sm.bar, 1); mbar_fence_init(); }
+
+  if (!points_mode) {
+    const float gtmax = P.has_gt ? P.in.depth_max[0] : 0.0f, gtmax12 = P.has_gt ? P.in.depth_max[1] : 0.0f;
+    block_setup_rays(P, sm, r0, nr, gtmax12);
+    __syncthreads();
+    double* zu = reinterpret_cast<double*>(sm.raw);              // unsorted samples (raw is not live yet)
+    for (int lp = threadIdx.x; lp < Pb; lp += blockDim.x) {
+      const int ray = lp / P.S, i = lp - ray * P.S;
+      RaySampler rs; rs.near = sm.rays[8 * ray + 6]; rs.gt = sm.rays[8 * ray + 7]; rs.far = sm.far[ray]; rs.has_gt = P.has_gt;
+      zu[lp] = sample_z(rs, i, P.in.n_samples, P.in.t_uniform, P.in.t_surface, gtmax);
+    }
+    __syncthreads();
+    for (int lp = threadIdx.x; lp < Pb; lp += blockDim.x) {      // stable rank sort == torch.sort (Renderer.py:168-170)
+      const int ray = lp / P.S, i = lp - ray * P.S;
+      const double zi = zu[lp];
+      const double* zr = zu + ray * P.S;
+      int rank = 0;
+      for (int j = 0; j < P.S; j++) { const double zj = zr[j]; rank += (z_less(zj, zi) || (!z_less(zi, zj) && j < i)) ? 1 : 0; }
+      sm.zs[ray * P.S + rank] = zi;
+    }
+  }
+  __syncthreads();
+  for (int lp = threadIdx.x; lp < Pb; lp += blockDim.x) { sm.raw[4 * lp] = 0.f; sm.raw[4 * lp + 1] = 0.f; sm.raw[4 * lp + 2] = 0.f; sm.raw[4 * lp + 3] = 0.f; }
+
+  const int nchunks = (Pb + kChunk - 1) / kChunk;
+  uint32_t parity = 0;
+  for (int qd = 0; qd < P.n_dec; qd++) {
+    const int lv = P.dec[qd];
+    __syncthreads();                                             // previous weight image no longer in use
+    if (threadIdx.x == 0) issue_weights(P, sm, lv);
+    for (int chunk = warp; chunk < nchunks; chunk += warps) {
+      switch (lv) {
+        case 0: chunk_forward<0>(P, sm, act, chunk, Pb, L, parity, qd == 0); break;
+        case 1: chunk_forward<1>(P, sm, act, chunk, Pb, L, parity, qd == 0); break;
+        case 2: chunk_forward<2>(P, sm, act, chunk, Pb, L, parity, qd == 0); break;
+        default: chunk_forward<3>(P, sm, act, chunk, Pb, L, parity, qd == 0); break;
+      }
+    }
+    parity ^= 1u;
+  }
+  __syncthreads();
+
+  if (points_mode) {                                             // Renderer.eval_points: raw with the OOB override
+    for (int lp = threadIdx.x; lp < Pb; lp += blockDim.x) {
+      const long long gp = (long long)blockIdx.x * P.rays_per_block + lp;
+      float4 v = *reinterpret_cast<float4*>(sm.raw + 4 * lp);
+      if (!sm.inb[lp]) v.w = 100.0f;
+      *reinterpret_cast<float4*>(P.points_raw + 4 * gp) = v;
+    }
+    return;
+  }
+  // out-of-bound override (Renderer.py:57), then raw2outputs_nerf_color, occupancy branch (common.py:233-244)
+  for (int lp = threadIdx.x; lp < Pb; lp += blockDim.x) if (!sm.inb[lp]) sm.raw[4 * lp + 3] = 100.0f;
+  __syncthreads();
+  for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+    const float* rw = sm.raw + 4 * r * P.S;
+    const double* z = sm.zs + r * P.S;
+    float T = 1.0f, c0 = 0.f, c1 = 0.f, c2 = 0.f; double dsum = 0.0;
+    for (int s = 0; s < P.S; s++) {
+      const float al = sigmoid_f(10.0f * rw[4 * s + 3]);
+      const float w = al * T;
+      T = T * ((1.0f - al) + 1e-10f);
+      c0 = fmaf(w, rw[4 * s], c0); c1 = fmaf(w, rw[4 * s + 1], c1); c2 = fmaf(w, rw[4 * s + 2], c2);
+      dsum += (double)w * z[s];
+    }
+    double v = 0.0; T = 1.0f;
+    for (int s = 0; s < P.S; s++) {
+      const float al = sigmoid_f(10.0f * rw[4 * s + 3]);
+      const float w = al * T;
+      T = T * ((1.0f - al) + 1e-10f);
+      const double t = z[s] - dsum;
+      v += (double)w * t * t;
+    }
+    P.fo.depth[r0 + r] = dsum; P.fo.var[r0 + r] = v;
+    P.fo.rgb[3 * (r0 + r)] = c0; P.fo.rgb[3 * (r0 + r) + 1] = c1; P.fo.rgb[3 * (r0 + r) + 2] = c2;
+  }
+  const long long g0 = (long long)r0 * P.S;
+  if (P.fo.z_vals != nullptr) for (int lp = threadIdx.x; lp < Pb; lp += blockDim.x) P.fo.z_vals[g0 + lp] = sm.zs[lp];
+  if (P.fo.raw != nullptr)
+    for (int lp = threadIdx.x; lp < Pb; lp += blockDim.x)
+      *reinterpret_cast<float4*>(P.fo.raw + 4 * (g0 + lp)) = *reinterpret_cast<float4*>(sm.raw + 4 * lp);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward kernel
+// ------------------------------------------------------------------------------------------------
+template <int LV, bool WGRAD>
+__device__ __forceinline__ void chunk_backward(const KParams& P, const Smem& sm, float* act, int chunk, int Pb,
+                                               const LaneId& L, uint32_t parity, const float* gC /*[R][3] smem*/) {
+  using D = Dec<LV>;
+  int lp; PointGeom G;
+  chunk_point(P, sm, chunk, Pb, L.lane, lp, G);
+  const float* xn = LV == 0 ? G.xnc : G.xn;
+  gather_chunk(P.in.grid[LV], act, R_C, xn, L.lane);
+  if (LV == 2) gather_chunk(P.in.grid[1], act, R_C + 32, G.xn, L.lane);
+  mbar_wait(sm.bar, parity);
+  if (D::XYZ) embed_chunk(act, sm.wt + D::o_B, G.pf, L.lane);
+  __syncwarp();
+  uint32_t masks[5]; float out[4];
+  mlp_forward<LV, true>(sm.wt, act, L, masks, out);
+
+  float g_out[4] = {0.f, 0.f, 0.f, 0.f};
+  if (lp < Pb) {
+    if (LV == 3) { const int ray = lp / P.S; const float w = sm.wgt[lp];
+      g_out[0] = w * gC[3 * ray]; g_out[1] = w * gC[3 * ray + 1]; g_out[2] = w * gC[3 * ray + 2]; }
+    else g_out[0] = sm.gocc[lp];
+  }
+  float pfq[4][3], dpe[4][3];
+#pragma unroll
+  for (int p = 0; p < 4; p++)
+#pragma unroll
+    for (int a = 0; a < 3; a++) pfq[p][a] = __shfl_sync(0xffffffffu, G.pf[a], 4 * L.pg + p);
+  mlp_backward<LV, WGRAD>(sm.wt, act, L, masks, g_out, pfq, dpe, WGRAD ? P.d_packed[LV] : nullptr);
+
+  if (D::XYZ && L.og == 0) {                                      // embedding chain -> dL/dp
+#pragma unroll
+    for (int p = 0; p < 4; p++) { const int l2 = chunk * kChunk + 4 * L.pg + p;
+      if (l2 < Pb) { sm.dp[3 * l2] += (double)dpe[p][0]; sm.dp[3 * l2 + 1] += (double)dpe[p][1]; sm.dp[3 * l2 + 2] += (double)dpe[p][2]; } }
+  }
+  __syncwarp();
+  const double* bb = LV == 0 ? P.in.coarse_bound : P.in.bound;
+  // rows of padding points (lp >= Pb) carry zero gradients because their g_out is zero
+  scatter_chunk(P.in.grid[LV], P.bw.d_grid[LV], act, R_C, xn, L.lane, [&](int pt, const float gx[3]) {
+    const int l2 = chunk * kChunk + pt;
+    if (l2 < Pb) {
+#pragma unroll
+      for (int a = 0; a < 3; a++) sm.dp[3 * l2 + a] += ((double)gx[a] * 2.0) / (bb[2 * a + 1] - bb[2 * a]);   // d normalise / dp, common.py:280-282
+    }
+  });
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(256, 1) render_bwd_kernel(const __grid_constant__ KParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5;
+  const LaneId L = make_lane(threadIdx.x & 31);
+  Smem sm;
+  smem_layout(P.wbytes, P.max_pts, P.max_rays, warps, kRowsBwd, true, &sm, smem_raw);
+  float* act = sm.act + (size_t)warp * kRowsBwd * kRowF;
+  __shared__ float gC[kMaxRaysPerBlock * 3];
+
+  const int r0 = blockIdx.x * P.rays_per_block;
+  const int nr = P.in.n_rays - r0 < P.rays_per_block ? P.in.n_rays - r0 : P.rays_per_block;
+  const int Pb = nr * P.S;
+  const long long g0 = (long long)r0 * P.S;
+  if (threadIdx.x == 0) { mbar_init(sm.bar, 1); mbar_fence_init(); }
+  block_setup_rays(P, sm, r0, nr, 0.0f);                         // only o, d are used below (z comes from forward)
+  for (int lp = threadIdx.x; lp < Pb; lp += blockDim.x) {
+    sm.zs[lp] = P.bw.z_vals[g0 + lp];
+    *reinterpret_cast<float4*>(sm.raw + 4 * lp) = *reinterpret_cast<const float4*>(P.bw.raw + 4 * (g0 + lp));
+    sm.dp[3 * lp] = 0.0; sm.dp[3 * lp + 1] = 0.0; sm.dp[3 * lp + 2] = 0.0;
+  }
+  __syncthreads();
+  for (int lp = threadIdx.x; lp < Pb; lp += blockDim.x) {        // in-bound flags (Renderer.py:43-46)
+    const int ray = lp / P.S; const float* rr = sm.rays + 8 * ray;
+    const float o[3] = {rr[0], rr[1], rr[2]}, d[3] = {rr[3], rr[4], rr[5]};
+    PointGeom G; make_point(P.in.bound, P.in.coarse_bound, o, d, sm.zs[lp], G);
+    sm.inb[lp] = (unsigned char)G.inb;
+  }
+  __syncthreads();
+  // per-ray: compositing weights and dL/d(occupancy logit)   (cumprod backward in division form)
+  for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+    const float* rw = sm.raw + 4 * r * P.S;
+    const double* z = sm.zs + r * P.S;
+    float* wq = sm.wgt + r * P.S; float* go = sm.gocc + r * P.S;
+    const double gD = P.bw.g_depth != nullptr ? P.bw.g_depth[r0 + r] : 0.0;
+    const double gV = P.bw.g_var != nullptr ? P.bw.g_var[r0 + r] : 0.0;
+    float g3[3] = {0.f, 0.f, 0.f};
+    if (P.bw.g_rgb != nullptr) { g3[0] = P.bw.g_rgb[3 * (r0 + r)]; g3[1] = P.bw.g_rgb[3 * (r0 + r) + 1]; g3[2] = P.bw.g_rgb[3 * (r0 + r) + 2]; }
+    gC[3 * r] = g3[0]; gC[3 * r + 1] = g3[1]; gC[3 * r + 2] = g3[2];
+    float T = 1.0f; double Dm = 0.0;
+    for (int s = 0; s < P.S; s++) {                              // forward scan: w_s (go[] temporarily holds T_s)
+      const float al = sigmoid_f(10.0f * rw[4 * s + 3]);
+      wq[s] = al * T; go[s] = T;
+      T = T * ((1.0f - al) + 1e-10f);
+      Dm += (double)wq[s] * z[s];
+    }
+    double swt = 0.0;
+    for (int s = 0; s < P.S; s++) swt += (double)wq[s] * (z[s] - Dm);
+    const double gDe = gD + gV * (-2.0 * swt);                   // var reaches depth through tmp = z - depth
+    float R = 0.0f;
+    for (int s = P.S - 1; s >= 0; s--) {
+      const float al = sigmoid_f(10.0f * rw[4 * s + 3]);
+      const double t = z[s] - Dm;
+      const float gw = (float)(gDe * z[s] + gV * t * t) + g3[0] * rw[4 * s] + g3[1] * rw[4 * s + 1] + g3[2] * rw[4 * s + 2];
+      const float qd = (1.0f - al) + 1e-10f;
+      const float ga = go[s] * gw - R / qd;
+      R += gw * wq[s];
+      go[s] = sm.inb[r * P.S + s] ? 10.0f * al * (1.0f - al) * ga : 0.0f;
+    }
+  }
+
+  const int nchunks = (Pb + kChunk - 1) / kChunk;
+  uint32_t parity = 0;
+  for (int qd = 0; qd < P.n_dec; qd++) {
+    const int lv = P.dec[qd];
+    const bool wg = P.d_packed[lv] != nullptr;
+    __syncthreads();
+    if (threadIdx.x == 0) issue_weights(P, sm, lv);
+    for (int chunk = warp; chunk < nchunks; chunk += warps) {
+      switch (lv * 2 + (wg ? 1 : 0)) {
+        case 0: chunk_backward<0, false>(P, sm, act, chunk, Pb, L, parity, gC); break;
+        case 1: chunk_backward<0, true>(P, sm, act, chunk, Pb, L, parity, gC); break;
+        case 2: chunk_backward<1, false>(P, sm, act, chunk, Pb, L, parity, gC); break;
+        case 3: chunk_backward<1, true>(P, sm, act, chunk, Pb, L, parity, gC); break;
+        case 4: chunk_backward<2, false>(P, sm, act, chunk, Pb, L, parity, gC); break;
+        case 5: chunk_backward<2, true>(P, sm, act, chunk, Pb, L, parity, gC); break;
+        case 6: chunk_backward<3, false>(P, sm, act, chunk, Pb, L, parity, gC); break;
+        default: chunk_backward<3, true>(P, sm, act, chunk, Pb, L, parity, gC); break;
+      }
+    }
+    parity ^= 1u;
+  }
+  __syncthreads();
+  // d rays_o = sum_s dp ; d rays_d = sum_s z_s dp   (pts = o + d*z, Renderer.py:172-174)
+  if (P.bw.d_rays_o != nullptr || P.bw.d_rays_d != nullptr) {
+    for (int t = threadIdx.x; t < nr * 3; t += blockDim.x) {
+      const int r = t / 3, a = t - 3 * r;
+      double so = 0.0, sd = 0.0;
+      for (int s = 0; s < P.S; s++) { const double v = sm.dp[3 * (r * P.S + s) + a]; so += v; sd += v * sm.zs[r * P.S + s]; }
+      if (P.bw.d_rays_o != nullptr) P.bw.d_rays_o[3 * (r0 + r) + a] = (float)so;
+      if (P.bw.d_rays_d != nullptr) P.bw.d_rays_d[3 * (r0 + r) + a] = (float)sd;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int stage_decoders(int stage, int dec[3]) {   // NICE.forward evaluation order, decoder.py:317-342
+  switch (stage) {
+    case NSB_STAGE_COARSE: dec[0] = NSB_COARSE; return 1;
+    case NSB_STAGE_MIDDLE: dec[0] = NSB_MIDDLE; return 1;
+    case NSB_STAGE_FINE: dec[0] = NSB_FINE; dec[1] = NSB_MIDDLE; return 2;
+    default: dec[0] = NSB_FINE; dec[1] = NSB_COLOR; dec[2] = NSB_MIDDLE; return 3;
+  }
+}
+
+static int validate_inputs(const nsb_render_inputs* in, bool need_rays) {
+  if (!in) { set_error("inputs == NULL"); return NSB_ERR_ARG; }
+  if (in->stage < 0 || in->stage > 3) { set_error("bad stage %d", in->stage); return NSB_ERR_ARG; }
+  if (need_rays) {
+    if (in->n_rays < 0) { set_error("n_rays < 0"); return NSB_ERR_ARG; }
+    if (in->n_rays > 0 && (!in->rays_o || !in->rays_d)) { set_error("rays_o / rays_d are NULL"); return NSB_ERR_ARG; }
+    if (in->n_samples < 1 || !in->t_uniform) { set_error("n_samples < 1 or t_uniform NULL"); return NSB_ERR_ARG; }
+    if (in->gt_depth && !in->depth_max) { set_error("gt_depth given without depth_max (call nsb_batch_max_depth)"); return NSB_ERR_ARG; }
+  }
+  int dec[3]; const int nd = stage_decoders(in->stage, dec);
+  for (int i = 0; i < nd; i++) {
+    const nsb_grid& g = in->grid[dec[i]];
+    if (!g.data || g.D < 1 || g.H < 1 || g.W < 1) { set_error("grid %d missing", dec[i]); return NSB_ERR_ARG; }
+    if (g.stride_c == 1 && (g.stride_w % 4 || g.stride_h % 4 || g.stride_d % 4 || ((uintptr_t)g.data & 15))) {
+      set_error("channels-last grid %d must be 16-byte aligned with strides multiple of 4", dec[i]); return NSB_ERR_ARG; }
+    if (!in->packed[dec[i]]) { set_error("packed decoder %d missing (call nsb_pack_decoders)", dec[i]); return NSB_ERR_ARG; }
+    if ((uintptr_t)in->packed[dec[i]] & 15) { set_error("packed decoder %d not 16-byte aligned", dec[i]); return NSB_ERR_ARG; }
+  }
+  return NSB_OK;
+}
+
+static void fill_common(KParams& K, const nsb_render_inputs* in) {
+  K.in = *in;
+  K.has_gt = (in->gt_depth != nullptr && in->stage != NSB_STAGE_COARSE) ? 1 : 0;    // Renderer.py:88-92
+  K.S = in->n_samples + (K.has_gt ? in->n_surface : 0);
+  K.n_dec = stage_decoders(in->stage, K.dec);
+  int wb = 0;
+  for (int i = 0; i < K.n_dec; i++) { const int b = packed_floats(K.dec[i]) * 4; wb = b > wb ? b : wb; }
+  K.wbytes = wb;
+  K.points = nullptr; K.points_raw = nullptr; K.n_points = 0;
+  for (int l = 0; l < 4; l++) K.d_packed[l] = nullptr;
+}
+
+static int g_sm_count = 0;
+static int sm_count() {
+  if (g_sm_count == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev); if (g_sm_count <= 0) g_sm_count = 148; }
+  return g_sm_count;
+}
+
+// choose rays per CTA and warps per CTA: fill all SMs once before growing CTAs (latency-bound small batches),
+// cap CTA size by the shared-memory budget (227 KB per CTA, 1 KB kept for static shared memory)
+constexpr size_t kSmemCap = 226u * 1024u;
+static void choose_config(int n_items, int S, int rows, bool bwd, int wbytes, int max_warps, KParams* K, int* warps, size_t* smem) {
+  const int sms = sm_count();
+  int r_cap = kMaxPtsPerBlock / S; if (r_cap < 1) r_cap = 1; if (r_cap > kMaxRaysPerBlock) r_cap = kMaxRaysPerBlock;
+  int r = (n_items + sms - 1) / sms; if (r < 1) r = 1; if (r > r_cap) r = r_cap;
+  const int max_pts = ((r * S + kChunk - 1) / kChunk) * kChunk;
+  const int chunks = max_pts / kChunk;
+  int w = chunks < max_warps ? chunks : max_warps;
+  while (w > 1 && smem_layout(wbytes, max_pts, r, w, rows, bwd, nullptr, nullptr) > kSmemCap) w--;
+  const int rounds = (chunks + w - 1) / w;
+  w = (chunks + rounds - 1) / rounds;                    // same number of rounds with balanced warps
+  K->rays_per_block = r; K->max_pts = max_pts; K->max_rays = r;
+  *warps = w;
+  *smem = smem_layout(wbytes, max_pts, r, w, rows, bwd, nullptr, nullptr);
+}
+
+static bool g_attr_set = false;
+static int set_attrs() {
+  if (g_attr_set) return NSB_OK;
+  if (check_cuda(cudaFuncSetAttribute(render_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "fwd smem attr")) return NSB_ERR_CUDA;
+  if (check_cuda(cudaFuncSetAttribute(render_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "bwd smem attr")) return NSB_ERR_CUDA;
+  g_attr_set = true;
+  return NSB_OK;
+}
+
+}  // namespace nsb
+
+using namespace nsb;
+
+extern "C" int nsb_render_forward(const nsb_render_inputs* in, const nsb_forward_outputs* out, void* stream) {
+  int rc = validate_inputs(in, true); if (rc) return rc;
+  if (!out || !out->depth || !out->var || !out->rgb) { set_error("forward outputs missing"); return NSB_ERR_ARG; }
+  if (in->n_rays == 0) return NSB_OK;
+  KParams K; fill_common(K, in); K.fo = *out; memset(&K.bw, 0, sizeof(K.bw));
+  if (K.S > NSB_MAX_SAMPLES) { set_error("n_samples+n_surface = %d exceeds %d", K.S, NSB_MAX_SAMPLES); return NSB_ERR_UNSUPPORTED; }
+  if (K.has_gt && in->n_surface > 0 && !in->t_surface) { set_error("t_surface NULL"); return NSB_ERR_ARG; }
+  if ((rc = set_attrs())) return rc;
+  int warps; size_t smem;
+  choose_config(in->n_rays, K.S, kRowsFwd, false, K.wbytes, 8, &K, &warps, &smem);
+  if (smem > kSmemCap) { set_error("shared-memory budget exceeded (%zu bytes)", smem); return NSB_ERR_UNSUPPORTED; }
+  const int grid = (in->n_rays + K.rays_per_block - 1) / K.rays_per_block;
+  render_fwd_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(K);
+  return check_cuda(cudaGetLastError(), "render_fwd_kernel launch");
+}
+
+extern "C" int nsb_eval_points(const nsb_render_inputs* in, const double* points, int n_points, float* raw, void* stream) {
+  int rc = validate_inputs(in, false); if (rc) return rc;
+  if (n_points < 0 || (n_points > 0 && (!points || !raw))) { set_error("points / raw missing"); return NSB_ERR_ARG; }
+  if (n_points == 0) return NSB_OK;
+  KParams K; fill_common(K, in); memset(&K.fo, 0, sizeof(K.fo)); memset(&K.bw, 0, sizeof(K.bw));
+  K.points = points; K.points_raw = raw; K.n_points = n_points; K.S = 1; K.has_gt = 0;
+  if ((rc = set_attrs())) return rc;
+  // points mode: "rays_per_block" = points per CTA
+  const int sms = sm_count();
+  int ppb = (n_points + sms - 1) / sms; ppb = ((ppb + kChunk - 1) / kChunk) * kChunk;
+  if (ppb > kMaxPtsPerBlock) ppb = kMaxPtsPerBlock;
+  if (ppb < kChunk) ppb = kChunk;
+  int warps = ppb / kChunk < 8 ? ppb / kChunk : 8;
+  while (warps > 1 && smem_layout(K.wbytes, ppb, 1, warps, kRowsFwd, false, nullptr, nullptr) > kSmemCap) warps--;
+  const size_t smem = smem_layout(K.wbytes, ppb, 1, warps, kRowsFwd, false, nullptr, nullptr);
+  K.rays_per_block = ppb; K.max_pts = ppb; K.max_rays = 1;
+  const int grid = (n_points + ppb - 1) / ppb;
+  render_fwd_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(K);
+  return check_cuda(cudaGetLastError(), "render_fwd_kernel(points) launch");
+}
+
+namespace nsb { int launch_unpack_grads(float* const d_packed[4], float* const d_flat[4], cudaStream_t st); }
+
+extern "C" size_t nsb_backward_workspace_bytes(void) {
+  size_t t = 0; for (int l = 0; l < 4; l++) t += align16((size_t)packed_floats(l) * 4); return t;
+}
+
+extern "C" int nsb_render_backward(const nsb_render_inputs* in, const nsb_backward_args* bw, void* stream) {
+  int rc = validate_inputs(in, true); if (rc) return rc;
+  if (!bw || !bw->z_vals || !bw->raw) { set_error("backward needs z_vals and raw from the forward pass"); return NSB_ERR_ARG; }
+  if (in->n_rays == 0) return NSB_OK;
+  KParams K; fill_common(K, in); K.bw = *bw; memset(&K.fo, 0, sizeof(K.fo));
+  if (K.S > NSB_MAX_SAMPLES) { set_error("n_samples+n_surface = %d exceeds %d", K.S, NSB_MAX_SAMPLES); return NSB_ERR_UNSUPPORTED; }
+  cudaStream_t st = (cudaStream_t)stream;
+  bool any_w = false;
+  for (int i = 0; i < K.n_dec; i++) {
+    const int l = K.dec[i];
+    if (bw->d_flat[l] != nullptr) {
+      if (!bw->workspace) { set_error("d_flat requested but workspace is NULL (nsb_backward_workspace_bytes)"); return NSB_ERR_ARG; }
+      size_t off = 0; for (int m = 0; m < l; m++) off += align16((size_t)packed_floats(m) * 4);
+      K.d_packed[l] = reinterpret_cast<float*>(reinterpret_cast<char*>(bw->workspace) + off);
+      if (check_cuda(cudaMemsetAsync(K.d_packed[l], 0, (size_t)packed_floats(l) * 4, st), "memset d_packed")) return NSB_ERR_CUDA;
+      any_w = true;
+    }
+  }
+  // grids/weights that are not part of this stage get no gradient
+  for (int l = 0; l < 4; l++) { bool used = false; for (int i = 0; i < K.n_dec; i++) used |= K.dec[i] == l; if (!used) { K.bw.d_grid[l] = nullptr; } }
+  if ((rc = set_attrs())) return rc;
+  int warps; size_t smem;
+  choose_config(in->n_rays, K.S, kRowsBwd, true, K.wbytes, 8, &K, &warps, &smem);
+  if (smem > kSmemCap) { set_error("shared-memory budget exceeded (%zu bytes)", smem); return NSB_ERR_UNSUPPORTED; }
+  const int grid = (in->n_rays + K.rays_per_block - 1) / K.rays_per_block;
+  render_bwd_kernel<<<grid, warps * 32, smem, st>>>(K);
+  if ((rc = check_cuda(cudaGetLastError(), "render_bwd_kernel launch"))) return rc;
+  if (any_w) return launch_unpack_grads(K.d_packed, bw->d_flat, st);
+  return NSB_OK;
+}

@@ -205,6 +205,7 @@ def make_mapper(cfg, slam, renderer, coarse_mapper=False, device="cpu", BA=False
     m.frustum_feature_selection = mp["frustum_feature_selection"]
     m.keyframe_selection_method = "global" if coarse_mapper else mp["keyframe_selection_method"]
     m.save_selected_keyframes_info = False
+    m.no_vis_on_first_frame = mp["no_vis_on_first_frame"]
     m.occupancy = cfg["occupancy"]
     m.keyframe_dict, m.keyframe_list = [], []
     m.H, m.W, m.fx, m.fy, m.cx, m.cy = slam.H, slam.W, slam.fx, slam.fy, slam.cx, slam.cy

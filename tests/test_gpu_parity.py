@@ -1,0 +1,269 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C-ABI library
+(nice_slam_b200/libnsb.so) via FusedRenderer; the checker is the oracle (oracle/torch_port.py, oracle/nsb_oracle.c)
+run live on the host CPU plus the committed reference fixtures (tests/golden).
+
+Bars: bit-exact sample positions (z_vals) and voxel-corner indices; 1e-4 relative (max-norm) on rendered
+depth / variance / RGB and on every gradient (TOL); the saturated-scene occupancy-decoder weight gradients use the
+measured f32 noise floor (TOL_SATURATED, see tests/test_oracle_golden.py)."""
+import glob
+import os
+
+import pytest
+import torch
+
+import glue
+import scene_util as su
+from gpu_util import LV, l2rel, make_renderer, rel
+from oracle import torch_port as tp
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+TOL_SATURATED = 3e-3
+RENDER_CASES = sorted(glob.glob(os.path.join(su.GOLDEN, "render_*.pt")))
+DEV = "cuda"
+
+
+def load_case(path):
+    case = torch.load(path, map_location="cpu", weights_only=False)
+    sc = su.load_scenes()[case["scene"]]
+    return case, sc, su.make_grids(sc, case["variant"]), su.load_decoders(case["variant"])
+
+
+def run_render(renderer, c, dec, case, stage, grads=True):
+    ro = case["rays_o"].to(DEV).requires_grad_(grads)
+    rd = case["rays_d"].to(DEV).requires_grad_(grads)
+    gt = case["gt_depth"].to(DEV) if case["gt_depth"] is not None else None
+    for k in c:
+        c[k] = c[k].detach().requires_grad_(grads and k[5:] in LV[stage])
+    for p in dec.parameters():
+        p.grad = None
+        p.requires_grad_(grads)
+    aux = {}
+    d, u, col = renderer.render_batch_ray(c, dec, rd, ro, DEV, stage, gt_depth=gt, aux=aux)
+    if grads:
+        ((d * case["g_depth"].to(DEV)).sum() + (u * case["g_var"].to(DEV)).sum() + (col * case["g_rgb"].to(DEV)).sum()).backward()
+    return d, u, col, aux, ro, rd
+
+
+@pytest.mark.parametrize("layout", ["channels_last", "ncdhw"])
+@pytest.mark.parametrize("path", RENDER_CASES, ids=[os.path.basename(p)[:-3] for p in RENDER_CASES])
+def test_render_against_reference_fixture(path, layout):
+    case, sc, grids, dec_state = load_case(path)
+    stage, variant = case["stage"], case["variant"]
+    renderer, c, dec = make_renderer(sc, grids, dec_state, DEV, channels_last=(layout == "channels_last"))
+    d, u, col, aux, ro, rd = run_render(renderer, c, dec, case, stage)
+    assert d.dtype == torch.float64 and u.dtype == torch.float64 and col.dtype == torch.float32
+    # bit-exact sampling and voxel indices
+    assert torch.equal(aux["z_vals"].cpu(), case["z_vals"])
+    assert torch.equal(aux["corner_idx"].cpu().to(torch.int16), case["corner_idx"])
+    assert rel(d, case["depth"]) < TOL and rel(u, case["var"]) < TOL
+    if stage == "color":
+        assert rel(col, case["rgb"]) < TOL
+    assert rel(ro.grad, case["d_rays_o"]) < TOL and rel(rd.grad, case["d_rays_d"]) < TOL
+    # dense grid gradients: fingerprints from the reference + the full tensor from the oracle run live
+    bound = su.scene_bound(sc)
+    o_grids = {k: v.clone().requires_grad_(k[5:] in LV[stage]) for k, v in grids.items()}
+    o_ro, o_rd = case["rays_o"].clone().requires_grad_(True), case["rays_d"].clone().requires_grad_(True)
+    od, ou, oc = tp.render_batch_ray(o_grids, dec_state, o_rd, o_ro, stage, case["gt_depth"], bound)
+    ((od * case["g_depth"]).sum() + (ou * case["g_var"]).sum() + (oc * case["g_rgb"]).sum()).backward()
+    for k, summ in case["d_grid"].items():
+        g = c[k].grad
+        assert g is not None, k
+        assert rel(g.reshape(-1).cpu()[summ["idx"]], summ["val"]) < TOL, k
+        assert abs(float(g.double().norm()) - summ["norm"]) < TOL * summ["norm"], k
+        assert rel(g, o_grids[k].grad) < TOL and l2rel(g, o_grids[k].grad) < TOL, k
+    for lvl, gd in case["d_dec"].items():
+        tol = TOL_SATURATED if (variant == "init" and lvl in ("fine", "middle", "coarse")) else TOL
+        mine = dict(getattr(dec, lvl + "_decoder").named_parameters())
+        for k, v in gd.items():
+            assert mine[k].grad is not None, (lvl, k)
+            assert rel(mine[k].grad, v) < tol, (lvl, k, rel(mine[k].grad, v))
+
+
+def test_tracker_iteration_against_real_tracker_capture():
+    """camera_tensor.grad of one Tracker.optimize_cam_in_batch iteration (captured from the real Tracker on CPU)."""
+    case = torch.load(os.path.join(su.GOLDEN, "tracker_color.pt"), map_location="cpu", weights_only=False)
+    sc = su.load_scenes()[case["scene"]]
+    renderer, c, dec = make_renderer(sc, su.make_grids(sc, case["variant"]), su.load_decoders(case["variant"]), DEV)
+    bound = su.scene_bound(sc)
+    out = glue.tracking_iteration(sc, case, lambda rd, ro, stage, gd: renderer.render_batch_ray(c, dec, rd, ro, DEV, stage, gt_depth=gd),
+                                  bound, device=DEV)
+    assert torch.equal(out["rays_o"], case["rays_o"])
+    assert rel(out["depth"], case["depth"]) < TOL
+    assert abs(out["loss"] - case["loss"]) < TOL * abs(case["loss"])
+    assert rel(out["d_camera"], case["d_camera"]) < TOL, (out["d_camera"], case["d_camera"])
+
+
+@pytest.mark.parametrize("stage", ["coarse", "middle", "fine", "color"])
+def test_mapper_iteration_against_real_mapper_capture(stage):
+    """Masked voxel gradients + colour-decoder gradients of real Mapper.optimize_map iterations (captured on CPU)."""
+    case = torch.load(os.path.join(su.GOLDEN, "mapper_%s.pt" % stage), map_location="cpu", weights_only=False)
+    sc = su.load_scenes()[case["scene"]]
+    renderer, c, dec = make_renderer(sc, su.make_grids(sc, case["variant"]), su.load_decoders(case["variant"]), DEV)
+    for k in c:
+        c[k] = c[k].detach().requires_grad_(k[5:] in LV[stage])
+    for n, p in dec.named_parameters():
+        p.requires_grad_(stage == "color" and n.startswith("color_decoder"))
+    gt = case["gt_depth"].to(DEV) if case["gt_depth"] is not None else None
+    d, u, col = renderer.render_batch_ray(c, dec, case["rays_d"].to(DEV), case["rays_o"].to(DEV), DEV, stage, gt_depth=gt)
+    assert rel(d, case["depth"]) < TOL and rel(u, case["var"]) < TOL
+    loss = tp.mapping_loss(d, col, case["gt_depth_loss"].to(DEV), case["gt_color"].to(DEV), stage, sc["mapping"]["w_color_loss"])
+    loss.backward()
+    for k, summ in case["masked_grads"].items():
+        dense = c[k].grad.cpu()
+        m = case["masks"][k]
+        masked = dense[m.unsqueeze(0).unsqueeze(0).expand_as(dense)]
+        assert rel(masked.reshape(-1)[summ["idx"]], summ["val"]) < TOL, k
+        assert abs(float(masked.double().norm()) - summ["norm"]) < TOL * summ["norm"], k
+    mine = dict(dec.color_decoder.named_parameters())
+    for k, v in case["d_color_decoder"].items():
+        assert rel(mine[k].grad, v) < TOL, (k, rel(mine[k].grad, v))
+
+
+def test_eval_points_matches_oracle():
+    sc = su.load_scenes()["room0"]
+    grids, dec_state = su.make_grids(sc, "soft"), su.load_decoders("soft")
+    renderer, c, dec = make_renderer(sc, grids, dec_state, DEV)
+    bound = su.scene_bound(sc)
+    g = torch.Generator().manual_seed(5)
+    lo, hi = bound[:, 0] - 0.3, bound[:, 1] + 0.3
+    p = lo + (hi - lo) * torch.rand(3001, 3, generator=g, dtype=torch.float64)
+    for stage in ("coarse", "middle", "fine", "color"):
+        want = tp.eval_points(p, grids, dec_state, stage, bound)
+        got = renderer.eval_points(p.to(DEV), dec, c, stage, DEV)
+        assert rel(got, want) < TOL, stage
+        assert torch.equal(got[:, 3].cpu() == 100, want[:, 3] == 100)
+
+
+def test_seed_kernels_match_reference_losses():
+    import ctypes as C
+    from nice_slam_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(9)
+    n = 777
+    depth = torch.rand(n, generator=g, dtype=torch.float64) * 3
+    var = torch.rand(n, generator=g, dtype=torch.float64) * 0.1
+    rgb = torch.rand(n, 3, generator=g)
+    gt = torch.rand(n, generator=g) * 3
+    gt[::13] = 0
+    gt_rgb = torch.rand(n, 3, generator=g, dtype=torch.float64)
+    # tracking
+    d1 = depth.clone().requires_grad_(True); c1 = rgb.clone().requires_grad_(True)
+    loss = tp.tracking_loss(d1, var, c1, gt, gt_rgb, 0.5)
+    loss.backward()
+    dev = lambda t: t.to(DEV)
+    gD = torch.empty(n, dtype=torch.float64, device=DEV); gC = torch.empty(n, 3, device=DEV); lo = torch.empty(1, dtype=torch.float64, device=DEV)
+    ws = torch.empty(L.nsb_tracking_seeds_workspace(n), dtype=torch.uint8, device=DEV)
+    t = [dev(depth), dev(var), dev(rgb), dev(gt), dev(gt_rgb)]
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(L.nsb_tracking_seeds(*[C.c_void_p(x.data_ptr()) for x in t], n, 0.5, 1, 1, C.c_void_p(gD.data_ptr()), C.c_void_p(gC.data_ptr()),
+                                    C.c_void_p(lo.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(), st), "tracking_seeds")
+    assert abs(float(lo) - float(loss)) < 1e-9 * abs(float(loss))
+    assert rel(gD, d1.grad) < 1e-12 and rel(gC, c1.grad) < 1e-6
+    # mapping
+    d2 = depth.clone().requires_grad_(True); c2 = rgb.clone().requires_grad_(True)
+    loss2 = tp.mapping_loss(d2, c2, gt, gt_rgb.float(), "color", 0.2)
+    loss2.backward()
+    t2 = [dev(depth), dev(rgb), dev(gt), dev(gt_rgb.float())]
+    _lib.check(L.nsb_mapping_seeds(*[C.c_void_p(x.data_ptr()) for x in t2], n, 0.2, 1, C.c_void_p(gD.data_ptr()), C.c_void_p(gC.data_ptr()),
+                                   C.c_void_p(lo.data_ptr()), st), "mapping_seeds")
+    assert abs(float(lo) - float(loss2)) < 1e-6 * abs(float(loss2))
+    assert rel(gD, d2.grad) < 1e-12 and rel(gC, c2.grad) < 1e-6
+
+
+def test_prefilter_and_batch_max():
+    import ctypes as C
+    from nice_slam_b200 import _lib
+    L = _lib.lib()
+    sc = su.load_scenes()["room0"]
+    bound = su.scene_bound(sc)
+    ro, rd, gd, _ = su.make_rays(sc, 5000, seed=1)
+    keep = tp.bbox_prefilter(ro, rd, gd, bound)
+    k = torch.empty(5000, dtype=torch.uint8, device=DEV)
+    b6 = (C.c_double * 6)(*bound.reshape(6).tolist())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ro_d, rd_d, gd_d = ro.to(DEV), rd.to(DEV), gd.to(DEV)
+    _lib.check(L.nsb_bbox_prefilter(C.c_void_p(ro_d.data_ptr()), C.c_void_p(rd_d.data_ptr()), C.c_void_p(gd_d.data_ptr()), 5000, b6,
+                                    C.c_void_p(k.data_ptr()), st), "prefilter")
+    assert torch.equal(k.cpu().bool(), keep)
+    out = torch.empty(2, device=DEV)
+    _lib.check(L.nsb_batch_max_depth(C.c_void_p(gd_d.data_ptr()), 5000, C.c_void_p(out.data_ptr()), st), "batch_max")
+    assert float(out[0]) == float(torch.max(gd)) and float(out[1]) == float(torch.max(gd * 1.2))
+
+
+# ------------------------------------------------------------------------------------ edge cases & properties
+@pytest.mark.parametrize("n_samples,n_surface,n_rays", [(5, 3, 37), (32, 16, 1), (16, 16, 333), (80, 16, 50), (32, 0, 64)])
+def test_ragged_shapes_against_oracle(n_samples, n_surface, n_rays):
+    sc = su.load_scenes()["room0"]
+    grids, dec_state = su.make_grids(sc, "soft"), su.load_decoders("soft")
+    renderer, c, dec = make_renderer(sc, grids, dec_state, DEV, n_samples=n_samples, n_surface=n_surface)
+    bound = su.scene_bound(sc)
+    ro, rd, gd, gc = su.make_rays(sc, n_rays, seed=n_rays)
+    gd[::5] = 0                                    # zero-depth branch of the surface sampler (Renderer.py:143-150)
+    out = tp.iteration("map", grids, dec_state, ro, rd, gd, gc.float(), "color", bound, n_samples, n_surface,
+                       grad_grids=("grid_fine", "grid_color", "grid_middle"), grad_decoders=("color",))
+    for k in c:
+        c[k] = c[k].detach().requires_grad_(k != "grid_coarse")
+    for n, p in dec.named_parameters():
+        p.requires_grad_(n.startswith("color_decoder"))
+    r1, r2 = ro.to(DEV).requires_grad_(True), rd.to(DEV).requires_grad_(True)
+    aux = {}
+    d, u, col = renderer.render_batch_ray(c, dec, r2, r1, DEV, "color", gt_depth=gd.to(DEV), aux=aux)
+    z = tp.sample_z_vals(ro, rd, gd, bound, n_samples, n_surface, "color")
+    assert torch.equal(aux["z_vals"].cpu(), z)
+    tp.mapping_loss(d, col, gd.to(DEV), gc.float().to(DEV), "color").backward()
+    assert rel(d, out["depth"]) < TOL and rel(col, out["color"]) < TOL and rel(u, out["var"]) < TOL
+    assert rel(r1.grad, out["d_rays_o"]) < TOL and rel(r2.grad, out["d_rays_d"]) < TOL
+    for k in ("grid_fine", "grid_color", "grid_middle"):
+        assert rel(c[k].grad, out["d_" + k]) < TOL, k
+    mine = dict(dec.color_decoder.named_parameters())
+    for k, v in out["d_dec"]["color"].items():
+        assert rel(mine[k].grad, v) < TOL, k
+
+
+def test_all_rays_outside_bound_and_zero_depth():
+    sc = su.load_scenes()["room0"]
+    grids, dec_state = su.make_grids(sc, "soft"), su.load_decoders("soft")
+    renderer, c, dec = make_renderer(sc, grids, dec_state, DEV)
+    bound = su.scene_bound(sc)
+    ro, rd, gd, _ = su.make_rays(sc, 64, seed=2)
+    ro = ro + 100.0                  # every sample out of bound -> occ logit 100 -> alpha 1 at the first sample
+    gd = torch.zeros_like(gd)        # no sensor depth anywhere
+    want = tp.render_batch_ray(grids, dec_state, rd, ro, "color", gd, bound)
+    got = renderer.render_batch_ray(c, dec, rd.to(DEV), ro.to(DEV), DEV, "color", gt_depth=gd.to(DEV))
+    for a, b in zip(got, want):
+        assert torch.allclose(a.cpu().double(), b.double(), rtol=1e-4, atol=1e-7)
+
+
+def test_large_batch_properties():
+    """BASELINE sweep size (65536 rays x 48): size-independent properties instead of an oracle run."""
+    sc = su.load_scenes()["room0"]
+    grids, dec_state = su.make_grids(sc, "soft"), su.load_decoders("soft")
+    renderer, c, dec = make_renderer(sc, grids, dec_state, DEV)
+    n = 65536
+    ro, rd, gd, gc = su.make_rays(sc, n, seed=77)
+    ro, rd, gd = ro.to(DEV), rd.to(DEV), gd.to(DEV)
+    aux = {}
+    d, u, col = renderer.render_batch_ray(c, dec, rd, ro, DEV, "color", gt_depth=gd, aux=aux)
+    z = aux["z_vals"]
+    assert bool((z[:, 1:] >= z[:, :-1]).all())                       # sortedness
+    assert bool(torch.isfinite(d).all() and torch.isfinite(col).all() and (u >= 0).all())
+    # permutation equivariance + split invariance (same batch-global depth max in both halves by construction)
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(1)).to(DEV)
+    imax = int(torch.argmax(gd))
+    d2, u2, col2 = renderer.render_batch_ray(c, dec, rd[perm], ro[perm], DEV, "color", gt_depth=gd[perm])
+    assert torch.equal(d2, d[perm]) and torch.equal(col2, col[perm]) and torch.equal(u2, u[perm])
+    half = torch.cat([torch.arange(0, n // 2, device=DEV), torch.tensor([imax], device=DEV)])
+    d3, _, col3 = renderer.render_batch_ray(c, dec, rd[half], ro[half], DEV, "color", gt_depth=gd[half])
+    assert torch.equal(d3[:-1], d[: n // 2]) and torch.equal(col3[:-1], col[: n // 2])
+    # linearity of the backward pass in the output seeds
+    sub = slice(0, 4096)
+    r1 = ro[sub].clone().requires_grad_(True); r2 = rd[sub].clone().requires_grad_(True)
+    dd, uu, cc = renderer.render_batch_ray(c, dec, r2, r1, DEV, "color", gt_depth=gd[sub])
+    g = torch.Generator(device=DEV).manual_seed(3)
+    s1 = torch.randn(4096, dtype=torch.float64, device=DEV, generator=g); s2 = torch.randn(4096, 3, device=DEV, generator=g)
+    ga = torch.autograd.grad((dd * s1).sum(), (r1, r2), retain_graph=True)
+    gb = torch.autograd.grad((cc * s2).sum(), (r1, r2), retain_graph=True)
+    gab = torch.autograd.grad((dd * s1).sum() + (cc * s2).sum(), (r1, r2))
+    for x, y, zz in zip(ga, gb, gab):
+        assert rel(x + y, zz) < 1e-5

@@ -1,0 +1,118 @@
+"""CPU: both oracles (oracle/torch_port.py, oracle/nsb_oracle.c) against the fixtures produced by the real
+reference (tests/make_golden.py).  This is what pins the oracle wherever /root/reference is absent."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import scene_util as su
+from oracle import c_oracle as co
+from oracle import torch_port as tp
+
+RENDER_CASES = sorted(glob.glob(os.path.join(su.GOLDEN, "render_*.pt")))
+LV = {"coarse": ["coarse"], "middle": ["middle"], "fine": ["fine", "middle"], "color": ["fine", "color", "middle"]}
+TOL = 1e-4      # north_star tolerance (rel) -- the oracles actually agree to ~1e-6
+# Saturated scene ('init': alpha == 1 at the first sample): the occupancy decoders' weight gradients are ~1e-7 and
+# dominated by f32 rounding of (1 - alpha); the reference's own f32 run differs from its f64 evaluation by 8e-4 there
+# (measured, DESIGN.md "tolerances"), so those tensors get a noise-floor tolerance instead of 1e-4.
+TOL_SATURATED = 3e-3
+
+
+def dec_tol(variant, lvl):
+    return TOL_SATURATED if (variant == "init" and lvl in ("fine", "middle", "coarse")) else TOL
+
+
+def rel(a, b):
+    a = torch.as_tensor(np.asarray(a)).double()
+    b = torch.as_tensor(np.asarray(b)).double()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def load_case(path):
+    case = torch.load(path, map_location="cpu", weights_only=False)
+    sc = su.load_scenes()[case["scene"]]
+    grids = su.make_grids(sc, case["variant"])
+    dec = su.load_decoders(case["variant"])
+    return case, sc, grids, dec
+
+
+@pytest.mark.parametrize("path", RENDER_CASES, ids=[os.path.basename(p)[:-3] for p in RENDER_CASES])
+def test_torch_port_matches_reference_fixture(path):
+    case, sc, grids, dec = load_case(path)
+    bound = su.scene_bound(sc)
+    stage = case["stage"]
+    ro = case["rays_o"].clone().requires_grad_(True)
+    rd = case["rays_d"].clone().requires_grad_(True)
+    g = {k: v.clone().requires_grad_(k[5:] in LV[stage]) for k, v in grids.items()}
+    dw = {n: {k: v.clone().requires_grad_(True) for k, v in W.items()} for n, W in dec.items()}
+    d, u, c, aux = tp.render_batch_ray(g, dw, rd, ro, stage, case["gt_depth"], bound, return_aux=True)
+    assert torch.equal(aux["z_vals"], case["z_vals"])                      # bit-exact sample positions
+    assert torch.equal(d.detach(), case["depth"]) and torch.equal(u.detach(), case["var"]) and torch.equal(c.detach(), case["rgb"])
+    ((d * case["g_depth"]).sum() + (u * case["g_var"]).sum() + (c * case["g_rgb"]).sum()).backward()
+    assert torch.equal(ro.grad, case["d_rays_o"]) and torch.equal(rd.grad, case["d_rays_d"])
+    for k, summ in case["d_grid"].items():
+        mine = su.grid_summary(g[k].grad)
+        assert mine["nnz"] == summ["nnz"] and torch.equal(mine["val"], summ["val"])
+    for lvl, gd in case["d_dec"].items():
+        for k, v in gd.items():
+            assert torch.equal(dw[lvl][k].grad, v), (lvl, k)
+
+
+@pytest.mark.parametrize("path", RENDER_CASES, ids=[os.path.basename(p)[:-3] for p in RENDER_CASES])
+def test_c_oracle_matches_reference_fixture(path):
+    case, sc, grids, dec = load_case(path)
+    stage = case["stage"]
+    scene = co.Scene(grids, dec, su.scene_bound(sc), coarse_enlarge=sc["coarse_bound_enlarge"],
+                     n_samples=sc["rendering"]["N_samples"], n_surface=sc["rendering"]["N_surface"])
+    f = scene.forward(stage, case["rays_o"], case["rays_d"], case["gt_depth"])
+    assert np.array_equal(f["z_vals"], case["z_vals"].numpy())               # bit-exact
+    assert np.array_equal(f["corner_idx"], case["corner_idx"].numpy().astype(np.int32))   # bit-exact voxel indices
+    assert rel(f["depth"], case["depth"]) < TOL and rel(f["var"], case["var"]) < TOL
+    if stage == "color":
+        assert rel(f["rgb"], case["rgb"]) < TOL
+    b = scene.backward(stage, case["rays_o"], case["rays_d"], case["gt_depth"], case["g_depth"], case["g_var"], case["g_rgb"],
+                       grad_grids=["grid_" + x for x in LV[stage]], grad_decoders=LV[stage])
+    assert rel(b["d_rays_o"], case["d_rays_o"]) < TOL and rel(b["d_rays_d"], case["d_rays_d"]) < TOL
+    for k, summ in case["d_grid"].items():
+        mine = b["d_" + k].reshape(-1)[summ["idx"]]
+        assert rel(mine, summ["val"]) < TOL, k
+        assert abs(float(b["d_" + k].double().norm()) - summ["norm"]) < TOL * summ["norm"]
+    for lvl, gd in case["d_dec"].items():
+        fl = co.unflatten_decoder(co.LEVELS.index(lvl), b["d_flat_" + lvl], dec[lvl])
+        for k, v in gd.items():
+            assert rel(fl[k], v) < dec_tol(case["variant"], lvl), (lvl, k)
+
+
+def test_tracker_boundary_capture():
+    """Real Tracker.optimize_cam_in_batch (src/Tracker.py:71-128) captured at the renderer boundary: the port, fed the
+    captured rays, reproduces outputs exactly and -- through the restated glue -- the camera gradient."""
+    case = torch.load(os.path.join(su.GOLDEN, "tracker_color.pt"), map_location="cpu", weights_only=False)
+    sc = su.load_scenes()[case["scene"]]
+    grids, dec, bound = su.make_grids(sc, case["variant"]), su.load_decoders(case["variant"]), su.scene_bound(sc)
+    d, u, c = tp.render_batch_ray(grids, dec, case["rays_d"], case["rays_o"], "color", case["gt_depth"], bound)
+    assert torch.equal(d, case["depth"]) and torch.equal(u, case["var"]) and torch.equal(c, case["rgb"])
+    import glue
+    out = glue.tracking_iteration_cpu(sc, case, grids, dec)
+    assert abs(out["loss"] - case["loss"]) < 1e-9 * abs(case["loss"])
+    assert torch.allclose(out["d_camera"], case["d_camera"], rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("stage", ["coarse", "middle", "fine", "color"])
+def test_mapper_boundary_capture(stage):
+    """Real Mapper.optimize_map (src/Mapper.py:230-540) iterations captured at the renderer boundary."""
+    case = torch.load(os.path.join(su.GOLDEN, "mapper_%s.pt" % stage), map_location="cpu", weights_only=False)
+    sc = su.load_scenes()[case["scene"]]
+    grids, dec, bound = su.make_grids(sc, case["variant"]), su.load_decoders(case["variant"]), su.scene_bound(sc)
+    import glue
+    out = glue.mapping_iteration_cpu(sc, case, grids, dec)
+    assert torch.equal(out["depth"], case["depth"]) and torch.equal(out["color"], case["rgb"])
+    for k, summ in case["masked_grads"].items():
+        dense = out["d_" + k]
+        m = case["masks"][k]
+        masked = dense[m.unsqueeze(0).unsqueeze(0).expand_as(dense)]
+        mine = su.grid_summary(masked, n_sample=4096)
+        assert mine["nnz"] == summ["nnz"] and torch.equal(mine["val"], summ["val"]), k
+    for k, v in case["d_color_decoder"].items():
+        assert torch.equal(out["d_dec"]["color"][k], v), k
