@@ -16,6 +16,7 @@ void set_error(const char* fmt, ...) {
 int check_cuda(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return NSB_OK;
   set_error("%s: %s", what, cudaGetErrorString(e));
+  (void)cudaGetLastError();      // non-sticky errors must not leak into the next call's launch check
   return NSB_ERR_CUDA;
 }
 

@@ -545,8 +545,8 @@ static void choose_config(int n_items, int S, int rows, bool bwd, int wbytes, in
 static bool g_attr_set = false;
 static int set_attrs() {
   if (g_attr_set) return NSB_OK;
-  if (check_cuda(cudaFuncSetAttribute(render_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "fwd smem attr")) return NSB_ERR_CUDA;
-  if (check_cuda(cudaFuncSetAttribute(render_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "bwd smem attr")) return NSB_ERR_CUDA;
+  if (check_cuda(cudaFuncSetAttribute(render_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap), "fwd smem attr")) return NSB_ERR_CUDA;
+  if (check_cuda(cudaFuncSetAttribute(render_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap), "bwd smem attr")) return NSB_ERR_CUDA;
   g_attr_set = true;
   return NSB_OK;
 }
