@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- rendered rays/sec of one NICE-SLAM tracking iteration (fwd + loss + bwd) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json metric "rendered rays/sec (200px x 48samp batch) ... ms/tracking-iter"): Replica room0 geometry,
+full coarse/middle/fine/color grids (48.5 MB, channels-last), pretrained middle/fine decoders + seeded colour decoder,
+stage 'color', 200 rays x (32 uniform + 16 near-surface) samples per GPU, one Tracker.optimize_cam_in_batch-style
+iteration = batch depth maxima -> render forward -> tracking loss (median-gated) -> render backward -> pose-gradient
+reduction.  N > 1: the global batch of 200*N rays is ray-sharded (weak scaling) with the exchanges the reference's
+batch-global ops require (depth maxima MAX, residual all-gather for the median, SUM of loss + pose gradient) over NCCL.
+The Adam step on the 7 pose numbers stays in PyTorch and is outside the timed region of both arms.
+
+`value` : rays/s with inputs resident in HBM; `e2e`: same through IterationContext.run_host (pinned host inputs, H2D and D2H
+inside the timed region).  --impl reference times the reference algorithm's CPU path (oracle port, PyTorch CPU, all host
+threads) on the same batch.  Every timed quantity uses CUDA events on the launching stream, max over ranks.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+RAYS_PER_GPU = 200
+STAGE = "color"
+BYTES_PER_RAY = 48 * 3 * 1024            # S x G(stage) x 1024 B gathered per ray (tracking: no scatter) = 147456
+METRIC = "rendered rays/sec"
+WORKLOAD = "room0 tracking iteration (fwd+loss+bwd), 200 rays x 48 samples (32+16) per GPU, stage color, full grids"
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2] or [r for _, r in self.rows]
+        sm, mx, reasons = [], None, set()
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_scene(device):
+    import scene_util as su
+    from gpu_util import make_renderer
+    sc = su.load_scenes()["room0"]
+    renderer, c, dec = make_renderer(sc, su.make_grids(sc, "soft"), su.load_decoders("soft"), device)
+    for p in dec.parameters():
+        p.requires_grad_(False)
+    return sc, renderer, c, dec
+
+
+def make_batch(sc, n, seed):
+    """n rays that pass the bbox pre-filter (host tensors): rays_o, rays_d, camera-frame dirs, gt_depth f32, gt_color f64."""
+    import scene_util as su
+    depth, color = su.make_frame(sc, seed)
+    c2w = su.make_pose(sc, seed)
+    cam = sc["cam"]
+    g = torch.Generator().manual_seed(31000 + seed)
+    idx = torch.randint(cam["H"] * cam["W"], (4 * n,), generator=g)
+    i, j = (idx % cam["W"]).float(), (idx // cam["W"]).float()
+    dirs = torch.stack([(i - cam["cx"]) / cam["fx"], -(j - cam["cy"]) / cam["fy"], -torch.ones_like(i)], -1)
+    rd = torch.sum(dirs.reshape(-1, 1, 3) * c2w[:3, :3], -1)
+    ro = c2w[:3, -1].expand(rd.shape).contiguous()
+    gd, gc = depth.reshape(-1)[idx], color.reshape(-1, 3)[idx]
+    keep = su.prefilter_host(ro, rd, gd, su.scene_bound(sc))
+    sel = torch.nonzero(keep).reshape(-1)[:n]
+    assert sel.numel() == n, "not enough rays survive the pre-filter"
+    return ro[sel].contiguous(), rd[sel].contiguous(), dirs[sel].contiguous(), gd[sel].contiguous(), gc[sel].contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ reference arm (CPU)
+def cpu_iteration_fn(sc, batch):
+    """One tracking iteration of the reference algorithm on the host CPUs (oracle port = same torch ops as the reference)."""
+    import scene_util as su
+    from oracle import torch_port as tp
+    grids, dec, bound = su.make_grids(sc, "soft"), su.load_decoders("soft"), su.scene_bound(sc)
+    ro, rd, dirs, gd, gc = batch
+
+    def step():
+        # the reference's tracker leaves requires_grad on its deep-copied decoders (src/Tracker.py:138), so its backward
+        # also computes their (unused) gradients -- kept here to time what the reference actually does
+        out = tp.iteration("track", grids, dec, ro, rd, gd, gc, STAGE, bound, grad_rays=True, grad_decoders=("fine", "color", "middle"))
+        d_c2w = torch.cat([out["d_rays_d"].double().t() @ dirs.double(), out["d_rays_o"].double().sum(0, keepdim=True).t()], 1)
+        return float(out["loss"]), d_c2w
+    return step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import scene_util as su
+    sc = su.load_scenes()["room0"]
+    batch = make_batch(sc, RAYS_PER_GPU, 0)
+    best = None
+    for threads in sorted({1, os.cpu_count() or 1}):        # CPU grid_sample is single-threaded for batch 1: report the faster setting
+        torch.set_num_threads(threads)
+        step = cpu_iteration_fn(sc, batch)
+        for _ in range(max(1, min(args.warmup, 3))):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(max(1, min(args.steps, 8))):
+            step()
+        dt = (time.perf_counter() - t0) / max(1, min(args.steps, 8))
+        if best is None or dt < best[0]:
+            best = (dt, threads)
+    torch.set_num_threads(best[1])
+    # bounded sample: keep the whole run within ~2.5 minutes whatever --steps is
+    n_rays = RAYS_PER_GPU
+    budget = 150.0
+    if (args.steps + args.warmup) * best[0] > budget:
+        n_rays = max(8, int(RAYS_PER_GPU * budget / ((args.steps + args.warmup) * best[0])))
+    sub = tuple(t[:n_rays] for t in batch)
+    step = cpu_iteration_fn(sc, sub)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    ms = (time.perf_counter() - t0) / args.steps * 1e3
+    value = n_rays / (ms * 1e-3)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": WORKLOAD, "device": "host CPU", "rays_per_step": n_rays},
+            "cpu_baseline": {"value": value, "unit": "rays/s", "cores": best[1], "kind": "port",
+                             "sample": "%d tracking iterations on %d of the 200 rays per step (oracle/torch_port.py, PyTorch CPU, %d threads of %d cores)"
+                                       % (args.steps, n_rays, best[1], os.cpu_count() or 1)},
+            "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ native arm (GPU)
+def run_native(args):
+    import torch.distributed as dist
+    from nice_slam_b200.steps import IterationContext
+    from nice_slam_b200.dist import ShardedTrackingIteration
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, "--gpus must equal the number of launched ranks"
+
+    sc, renderer, c, dec = build_scene(dev)
+    host = make_batch(sc, RAYS_PER_GPU, rank)
+    ro, rd, dirs, gd, gc = [t.to(dev) for t in host]
+    ctx = IterationContext(renderer, RAYS_PER_GPU, STAGE, dev, kind="track")
+    ctx.stage_host_inputs(host[0], host[1], host[3], host[4])
+    sharded = ShardedTrackingIteration(ctx) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+
+    def step_dev():
+        if sharded is not None:
+            sharded.run(c, dec, ro, rd, dirs, gd, gc)
+        else:
+            ctx.run(c, dec, ro, rd, gd, gc)
+            ctx.pose_grad(dirs)
+
+    h_pose = torch.empty(13, dtype=torch.float64).pin_memory()
+
+    def step_e2e():
+        if sharded is not None:          # host inputs -> device -> sharded iteration -> [loss | d_c2w] back to the host
+            n = ctx.n
+            ctx.d_in32.copy_(ctx.h_in32, non_blocking=True); ctx.gt_color.copy_(ctx.h_col, non_blocking=True)
+            packed = sharded.run(c, dec, ctx.d_in32[: 3 * n].view(n, 3), ctx.d_in32[3 * n: 6 * n].view(n, 3), dirs, ctx.d_in32[6 * n:], ctx.gt_color)
+            h_pose.copy_(packed, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        else:
+            ctx.run_host(c, dec)
+
+    def timed(fn, steps, warmup, flush_l2):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        t0 = time.time()
+        for a, b in evs:
+            if flush_l2:
+                flush.zero_()
+            a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t1 = time.time()
+        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        if world > 1:
+            t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t)
+        return total_ms, t0, t1
+
+    # correctness guard of the timed path (cheap): loss finite
+    step_dev(); torch.cuda.synchronize()
+    assert torch.isfinite(ctx.loss).all()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ctx.time_backward(True)
+    total_ms, t0, t1 = timed(step_dev, args.steps, max(args.warmup, 3), True)
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    # dominant kernel (render_bwd_kernel): events recorded by the library around its launch, averaged over a short loop
+    bwd_ms = []
+    if sharded is None:
+        for _ in range(50):
+            flush.zero_(); ctx.run(c, dec, ro, rd, gd, gc); torch.cuda.synchronize()
+            bwd_ms.append(ctx.ev_bwd[0].elapsed_time(ctx.ev_bwd[1]))
+    ctx.time_backward(False)
+    warm_ms, _, _ = timed(step_dev, args.steps, 3, False)                 # L2-warm (production steady state), reported as extra
+    e2e_ms, _, _ = timed(step_e2e, args.steps, 3, True)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms = total_ms / args.steps
+    rays = RAYS_PER_GPU * world
+    value = rays / (ms * 1e-3)
+    peak, peak_src = peaks()
+    line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rays_per_step": rays, "l2": "flushed between steps (256 MiB memset outside the event pair)",
+                       "parallelism": "ray-sharded x%d" % world, "timing": "sum of per-step CUDA-event pairs, max over ranks"},
+            "clocks": clocks,
+            "e2e": {"value": rays / (e2e_ms / args.steps * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": ctx.h2d_bytes,
+                    "d2h_bytes_per_step": ctx.d2h_bytes if sharded is None else 13 * 8, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": (5 if sharded is None else 7) * args.steps,
+            "extra": {"l2_warm_ms_per_step": warm_ms / args.steps, "l2_warm_rays_per_s": rays / (warm_ms / args.steps * 1e-3)}}
+    if bwd_ms:
+        t_bwd = statistics.mean(bwd_ms) * 1e-3
+        ach = BYTES_PER_RAY * RAYS_PER_GPU / t_bwd / 1e9
+        line["roofline"] = {"bound": "hbm", "kernel": "render_bwd_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                            "traffic": None, "peak_source": peak_src, "launch_ms": t_bwd * 1e3,
+                            "algorithmic_bytes_per_launch": BYTES_PER_RAY * RAYS_PER_GPU,
+                            "note": "200-ray tracking batch is latency/FP32-FMA bound, not HBM bound (see DESIGN.md)"}
+    if world == 1:
+        step = cpu_iteration_fn(sc, host)
+        torch.set_num_threads(os.cpu_count() or 1)
+        for _ in range(2):
+            step()
+        t0c, k = time.perf_counter(), 0
+        while k < 10 or time.perf_counter() - t0c < 8.0:
+            step(); k += 1
+        dtc = (time.perf_counter() - t0c) / k
+        line["cpu_baseline"] = {"value": RAYS_PER_GPU / dtc, "unit": "rays/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": "%d iterations of the same 200-ray batch, oracle/torch_port.py on PyTorch CPU" % k,
+                                "ms_per_step": dtc * 1e3}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = 30 if args.steps is None else args.steps
+        args.warmup = 3 if args.warmup is None else args.warmup
+        run_reference(args)
+    else:
+        args.steps = 1000 if args.steps is None else args.steps
+        args.warmup = 20 if args.warmup is None else args.warmup
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -146,14 +146,49 @@ int nsb_render_backward(const nsb_render_inputs* in, const nsb_backward_args* bw
  * Writes g_depth[N] (f64), g_rgb[N,3] (f32) and loss[1] (f64). */
 int nsb_tracking_seeds(const double* depth, const double* var, const float* rgb, const float* gt_depth,
                        const double* gt_rgb, int n, double w_color, int handle_dynamic, int use_color,
+                       const double* median_pool, int n_pool,
                        double* g_depth, float* g_rgb, double* loss, void* workspace, size_t workspace_bytes,
                        void* stream);
+/* r_i = |gt_i - depth_i| / sqrt(var_i + 1e-10) (src/Tracker.py:112).  When a tracking batch is sharded over several
+ * GPUs the median of Tracker.py:113 must be taken over ALL shards: all-gather these residuals and pass them to
+ * nsb_tracking_seeds as median_pool / n_pool (NULL / 0 = use this call's own rays). */
+int nsb_tracking_residuals(const double* depth, const double* var, const float* gt_depth, int n, double* res, void* stream);
 int nsb_mapping_seeds(const double* depth, const float* rgb, const float* gt_depth, const float* gt_rgb, int n,
                       double w_color, int use_color, double* g_depth, float* g_rgb, double* loss, void* stream);
 size_t nsb_tracking_seeds_workspace(int n);
 
 /* Points-only decode (Renderer.eval_points, src/utils/Renderer.py:23-61): p f64 [P,3] -> raw f32 [P,4]. */
 int nsb_eval_points(const nsb_render_inputs* in, const double* points, int n_points, float* raw, void* stream);
+
+/* Pose-gradient reduction: rays_d = sum_j dirs_j * R[:,j], rays_o = t (get_rays_from_uv, src/common.py:74-89) =>
+ * d c2w[i][j] = sum_r d_rays_d[r][i] * dirs[r][j] (j<3), d c2w[i][3] = sum_r d_rays_o[r][i].  dirs: [N,3] camera-frame
+ * directions.  d_c2w: float64 [3][4], OVERWRITTEN.  The quaternion chain (quad2rotation, src/common.py:137-160) stays in
+ * PyTorch on these 12 numbers. */
+int nsb_pose_grad(const float* dirs, const float* d_rays_o, const float* d_rays_d, int n, double* d_c2w, void* stream);
+
+/* ---- one optimisation iteration = batch max -> forward -> loss seeds -> backward, enqueued by ONE call ----
+ * (what Tracker.optimize_cam_in_batch, src/Tracker.py:106-125, and one joint_iter of Mapper.optimize_map,
+ * src/Mapper.py:482-503, do around the optimiser step).  All buffers are caller-owned device memory. */
+typedef struct {
+  double* depth;  double* var;  float* rgb;      /* [N], [N], [N,3]   rendered outputs            */
+  double* z_vals; float* raw;                    /* [N,S], [N,S,4]    forward state kept for backward */
+  double* g_depth; float* g_rgb;                 /* [N], [N,3]        loss seeds                  */
+  double* loss;                                  /* [1]               scalar loss (float64)       */
+  float* depth_max;                              /* [2]               batch depth maxima          */
+  void* workspace; size_t workspace_bytes;       /* >= nsb_iteration_workspace_bytes(N)           */
+  void* event_bwd_begin; void* event_bwd_end;    /* optional cudaEvent_t recorded around the backward launch (profiling hook) */
+} nsb_iteration_buffers;
+
+size_t nsb_iteration_workspace_bytes(int n_rays);
+
+/* `in->depth_max` is ignored (computed into buf->depth_max).  `grads` supplies only the OUTPUT pointers of
+ * nsb_backward_args (d_rays_o, d_rays_d, d_grid, d_flat); its z_vals, raw, seed and workspace fields are ignored. */
+int nsb_tracking_iteration(const nsb_render_inputs* in, const nsb_iteration_buffers* buf, const double* gt_rgb,
+                           double w_color, int handle_dynamic, int use_color, const nsb_backward_args* grads, void* stream);
+/* gt_depth_loss: the depth the loss compares against (the coarse mapper renders with in->gt_depth == NULL but still
+ * supervises with the sensor depth, src/Mapper.py:484-489); NULL = in->gt_depth. */
+int nsb_mapping_iteration(const nsb_render_inputs* in, const nsb_iteration_buffers* buf, const float* gt_depth_loss,
+                          const float* gt_rgb, double w_color, const nsb_backward_args* grads, void* stream);
 
 #ifdef __cplusplus
 }

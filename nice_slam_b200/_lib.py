@@ -45,6 +45,13 @@ class BackwardArgs(C.Structure):
                 ("d_grid", C.c_void_p * 4), ("d_flat", C.c_void_p * 4), ("workspace", C.c_void_p)]
 
 
+class IterationBuffers(C.Structure):
+    _fields_ = [("depth", C.c_void_p), ("var", C.c_void_p), ("rgb", C.c_void_p), ("z_vals", C.c_void_p), ("raw", C.c_void_p),
+                ("g_depth", C.c_void_p), ("g_rgb", C.c_void_p), ("loss", C.c_void_p), ("depth_max", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+                ("event_bwd_begin", C.c_void_p), ("event_bwd_end", C.c_void_p)]
+
+
 # every symbol include/nice_slam_b200.h declares: (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -59,7 +66,12 @@ SYMBOLS = {
     "nsb_render_forward": (C.c_int, [C.POINTER(RenderInputs), C.POINTER(ForwardOutputs), _P]),
     "nsb_backward_workspace_bytes": (C.c_size_t, []),
     "nsb_render_backward": (C.c_int, [C.POINTER(RenderInputs), C.POINTER(BackwardArgs), _P]),
-    "nsb_tracking_seeds": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_double, C.c_int, C.c_int, _P, _P, _P, _P, C.c_size_t, _P]),
+    "nsb_tracking_seeds": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_double, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P, _P, C.c_size_t, _P]),
+    "nsb_tracking_residuals": (C.c_int, [_P, _P, _P, C.c_int, _P, _P]),
+    "nsb_pose_grad": (C.c_int, [_P, _P, _P, C.c_int, _P, _P]),
+    "nsb_iteration_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "nsb_tracking_iteration": (C.c_int, [C.POINTER(RenderInputs), C.POINTER(IterationBuffers), _P, C.c_double, C.c_int, C.c_int, C.POINTER(BackwardArgs), _P]),
+    "nsb_mapping_iteration": (C.c_int, [C.POINTER(RenderInputs), C.POINTER(IterationBuffers), _P, _P, C.c_double, C.POINTER(BackwardArgs), _P]),
     "nsb_mapping_seeds": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_double, C.c_int, _P, _P, _P, _P]),
     "nsb_tracking_seeds_workspace": (C.c_size_t, [C.c_int]),
     "nsb_eval_points": (C.c_int, [C.POINTER(RenderInputs), _P, C.c_int, _P, _P]),

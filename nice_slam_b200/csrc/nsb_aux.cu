@@ -130,7 +130,8 @@ __device__ __forceinline__ double sgn(double x) { return (x > 0.0) - (x < 0.0); 
 // Tracker.optimize_cam_in_batch loss (src/Tracker.py:108-123); single CTA, residuals staged in `res`.
 __global__ void tracking_seeds_kernel(const double* __restrict__ depth, const double* __restrict__ var, const float* __restrict__ rgb,
                                       const float* __restrict__ gt, const double* __restrict__ gt_rgb, int n, double w_color,
-                                      int handle_dynamic, int use_color, double* __restrict__ g_depth, float* __restrict__ g_rgb,
+                                      int handle_dynamic, int use_color, const double* __restrict__ pool, int n_pool,
+                                      double* __restrict__ g_depth, float* __restrict__ g_rgb,
                                       double* __restrict__ loss, double* __restrict__ res) {
   __shared__ double red[32];
   __shared__ double med_s;
@@ -138,10 +139,12 @@ __global__ void tracking_seeds_kernel(const double* __restrict__ depth, const do
     res[i] = fabs((double)gt[i] - depth[i]) / sqrt(var[i] + 1e-10);
   __syncthreads();
   if (handle_dynamic) {            // torch.median = lower median = element of rank (n-1)/2 in the stable sorted order
-    const int kth = (n - 1) / 2;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const double ri = res[i]; int rank = 0;
-      for (int j = 0; j < n; j++) { const double rj = res[j]; rank += (z_less(rj, ri) || (!z_less(ri, rj) && j < i)) ? 1 : 0; }
+    const double* mp = pool != nullptr ? pool : res;       // sharded batches: median over the all-gathered residuals
+    const int np = pool != nullptr ? n_pool : n;
+    const int kth = (np - 1) / 2;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) {
+      const double ri = mp[i]; int rank = 0;
+      for (int j = 0; j < np; j++) { const double rj = mp[j]; rank += (z_less(rj, ri) || (!z_less(ri, rj) && j < i)) ? 1 : 0; }
       if (rank == kth) med_s = ri;
     }
     __syncthreads();
@@ -187,9 +190,34 @@ __global__ void mapping_seeds_kernel(const double* __restrict__ depth, const flo
   if (threadIdx.x == 0) loss[0] = tot;
 }
 
+// d c2w from ray gradients (single CTA, deterministic)
+__global__ void pose_grad_kernel(const float* __restrict__ dirs, const float* __restrict__ dro, const float* __restrict__ drd, int n,
+                                 double* __restrict__ out) {
+  __shared__ double red[32];
+  double acc[12];
+#pragma unroll
+  for (int k = 0; k < 12; k++) acc[k] = 0.0;
+  for (int r = threadIdx.x; r < n; r += blockDim.x) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const double g = (double)drd[3 * r + i];
+#pragma unroll
+      for (int j = 0; j < 3; j++) acc[4 * i + j] += g * (double)dirs[3 * r + j];
+      acc[4 * i + 3] += (double)dro[3 * r + i];
+    }
+  }
+  for (int k = 0; k < 12; k++) { const double t = block_sum(acc[k], red); if (threadIdx.x == 0) out[k] = t; }
+}
+
 }  // namespace nsb
 
 using namespace nsb;
+
+extern "C" int nsb_pose_grad(const float* dirs, const float* d_rays_o, const float* d_rays_d, int n, double* d_c2w, void* stream) {
+  if (n < 0 || !d_c2w || (n > 0 && (!dirs || !d_rays_o || !d_rays_d))) { set_error("pose_grad: bad arguments"); return NSB_ERR_ARG; }
+  pose_grad_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(dirs, d_rays_o, d_rays_d, n, d_c2w);
+  return check_cuda(cudaGetLastError(), "pose_grad launch");
+}
 
 extern "C" int nsb_version(void) { return NSB_VERSION; }
 extern "C" const char* nsb_last_error(void) { return g_err; }
@@ -231,15 +259,29 @@ extern "C" int nsb_bbox_prefilter(const float* rays_o, const float* rays_d, cons
 
 extern "C" size_t nsb_tracking_seeds_workspace(int n) { return (size_t)(n > 0 ? n : 1) * sizeof(double); }
 
+__global__ void residuals_kernel(const double* __restrict__ depth, const double* __restrict__ var, const float* __restrict__ gt,
+                                 int n, double* __restrict__ res) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) res[i] = fabs((double)gt[i] - depth[i]) / sqrt(var[i] + 1e-10);
+}
+extern "C" int nsb_tracking_residuals(const double* depth, const double* var, const float* gt_depth, int n, double* res, void* stream) {
+  if (n < 0 || (n > 0 && (!depth || !var || !gt_depth || !res))) { set_error("tracking_residuals: bad arguments"); return NSB_ERR_ARG; }
+  if (n == 0) return NSB_OK;
+  residuals_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(depth, var, gt_depth, n, res);
+  return check_cuda(cudaGetLastError(), "residuals launch");
+}
+
 extern "C" int nsb_tracking_seeds(const double* depth, const double* var, const float* rgb, const float* gt_depth,
                                   const double* gt_rgb, int n, double w_color, int handle_dynamic, int use_color,
+                                  const double* median_pool, int n_pool,
                                   double* g_depth, float* g_rgb, double* loss, void* workspace, size_t workspace_bytes,
                                   void* stream) {
   if (n < 0 || !loss || (n > 0 && (!depth || !var || !rgb || !gt_depth || !g_depth || !g_rgb || (use_color && !gt_rgb)))) {
     set_error("tracking_seeds: bad arguments"); return NSB_ERR_ARG; }
   if (!workspace || workspace_bytes < nsb_tracking_seeds_workspace(n)) { set_error("tracking_seeds: workspace too small"); return NSB_ERR_ARG; }
+  if (median_pool != nullptr && n_pool < 1) { set_error("tracking_seeds: empty median pool"); return NSB_ERR_ARG; }
   tracking_seeds_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(depth, var, rgb, gt_depth, gt_rgb, n, w_color, handle_dynamic, use_color,
-                                                               g_depth, g_rgb, loss, (double*)workspace);
+                                                               median_pool, n_pool, g_depth, g_rgb, loss, (double*)workspace);
   return check_cuda(cudaGetLastError(), "tracking_seeds launch");
 }
 

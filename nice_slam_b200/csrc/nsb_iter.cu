@@ -1,0 +1,64 @@
+// nsb_iter.cu -- one optimisation iteration enqueued by a single C call:
+//   batch depth maxima -> render forward -> loss seeds -> render backward
+// (Tracker.optimize_cam_in_batch, src/Tracker.py:106-125; one joint_iter of Mapper.optimize_map, src/Mapper.py:482-503).
+#include "nsb_common.cuh"
+
+using namespace nsb;
+
+static size_t a16(size_t x) { return (x + 15) & ~size_t(15); }
+
+extern "C" size_t nsb_iteration_workspace_bytes(int n_rays) {
+  return a16(nsb_tracking_seeds_workspace(n_rays)) + a16(nsb_backward_workspace_bytes());
+}
+
+static int check_buffers(const nsb_render_inputs* in, const nsb_iteration_buffers* b, const nsb_backward_args* g) {
+  if (!in || !b || !g) { set_error("iteration: NULL argument"); return NSB_ERR_ARG; }
+  if (!b->depth || !b->var || !b->rgb || !b->z_vals || !b->raw || !b->g_depth || !b->g_rgb || !b->loss || !b->depth_max || !b->workspace) {
+    set_error("iteration: incomplete nsb_iteration_buffers"); return NSB_ERR_ARG; }
+  if (b->workspace_bytes < nsb_iteration_workspace_bytes(in->n_rays)) { set_error("iteration: workspace too small"); return NSB_ERR_ARG; }
+  return NSB_OK;
+}
+
+static int forward_part(const nsb_render_inputs* in, const nsb_iteration_buffers* b, nsb_render_inputs* in2, void* stream) {
+  *in2 = *in;
+  int rc;
+  if (in->gt_depth) {
+    if ((rc = nsb_batch_max_depth(in->gt_depth, in->n_rays, b->depth_max, stream))) return rc;
+    in2->depth_max = b->depth_max;
+  }
+  nsb_forward_outputs fo = {b->depth, b->var, b->rgb, b->z_vals, b->raw, nullptr};
+  return nsb_render_forward(in2, &fo, stream);
+}
+
+static int backward_part(const nsb_render_inputs* in2, const nsb_iteration_buffers* b, const nsb_backward_args* g, void* stream) {
+  nsb_backward_args bw = *g;
+  bw.z_vals = b->z_vals; bw.raw = b->raw; bw.g_depth = b->g_depth; bw.g_var = nullptr; bw.g_rgb = b->g_rgb;
+  bw.workspace = reinterpret_cast<char*>(b->workspace) + a16(nsb_tracking_seeds_workspace(in2->n_rays));
+  if (b->event_bwd_begin) cudaEventRecord((cudaEvent_t)b->event_bwd_begin, (cudaStream_t)stream);
+  const int rc = nsb_render_backward(in2, &bw, stream);
+  if (b->event_bwd_end) cudaEventRecord((cudaEvent_t)b->event_bwd_end, (cudaStream_t)stream);
+  return rc;
+}
+
+extern "C" int nsb_tracking_iteration(const nsb_render_inputs* in, const nsb_iteration_buffers* buf, const double* gt_rgb,
+                                      double w_color, int handle_dynamic, int use_color, const nsb_backward_args* grads, void* stream) {
+  int rc = check_buffers(in, buf, grads); if (rc) return rc;
+  if (!in->gt_depth) { set_error("tracking iteration needs gt_depth"); return NSB_ERR_ARG; }
+  nsb_render_inputs in2;
+  if ((rc = forward_part(in, buf, &in2, stream))) return rc;
+  if ((rc = nsb_tracking_seeds(buf->depth, buf->var, buf->rgb, in->gt_depth, gt_rgb, in->n_rays, w_color, handle_dynamic, use_color,
+                               nullptr, 0, buf->g_depth, buf->g_rgb, buf->loss, buf->workspace, nsb_tracking_seeds_workspace(in->n_rays), stream))) return rc;
+  return backward_part(&in2, buf, grads, stream);
+}
+
+extern "C" int nsb_mapping_iteration(const nsb_render_inputs* in, const nsb_iteration_buffers* buf, const float* gt_depth_loss,
+                                     const float* gt_rgb, double w_color, const nsb_backward_args* grads, void* stream) {
+  int rc = check_buffers(in, buf, grads); if (rc) return rc;
+  const float* gtl = gt_depth_loss ? gt_depth_loss : in->gt_depth;
+  if (!gtl) { set_error("mapping iteration needs a depth to supervise with"); return NSB_ERR_ARG; }
+  nsb_render_inputs in2;
+  if ((rc = forward_part(in, buf, &in2, stream))) return rc;
+  const int use_color = in->stage == NSB_STAGE_COLOR;                      // Mapper.py:490
+  if ((rc = nsb_mapping_seeds(buf->depth, buf->rgb, gtl, gt_rgb, in->n_rays, w_color, use_color, buf->g_depth, buf->g_rgb, buf->loss, stream))) return rc;
+  return backward_part(&in2, buf, grads, stream);
+}

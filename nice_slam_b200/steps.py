@@ -1,0 +1,143 @@
+"""Fused optimisation iterations (no autograd graph, no per-call allocations).
+
+`IterationContext` owns the device buffers of one (batch size, stage) configuration and enqueues a whole
+Tracker.optimize_cam_in_batch-style or Mapper.optimize_map-style iteration -- batch depth maxima, render forward,
+loss seeds, render backward -- with ONE C call (nsb_tracking_iteration / nsb_mapping_iteration).  The optimiser
+step itself (Adam on the pose / masked voxels / colour decoder) stays in PyTorch, as in the reference.
+
+`run_host()` is the end-to-end entry used by bench.py's `e2e` figure: inputs come from pinned host memory, the loss
+and the ray gradients are read back to pinned host memory, both copies inside the call.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import LEVELS, STAGE_DECODERS
+from .renderer import _VP, _inputs, _linspaces, _stream, _Call, _require_cuda
+
+KERNEL_LAUNCHES_PER_ITERATION = 4       # batch_max, render_fwd, seeds, render_bwd (+1 unpack when decoder grads are requested)
+
+
+class IterationContext:
+    def __init__(self, renderer, n_rays, stage, device, kind="track", grad_grids=(), grad_decoders=(), coarse_mapper=False):
+        L = _lib.lib()
+        self.r, self.n, self.stage, self.kind = renderer, int(n_rays), stage, kind
+        self.dev = torch.device(device)
+        self.levels = STAGE_DECODERS[stage]
+        self.render_with_depth = not (kind == "map" and (stage == "coarse" or coarse_mapper))
+        S = renderer.N_samples + (renderer.N_surface if (self.render_with_depth and stage != "coarse") else 0)
+        self.S = S
+        n, dev = self.n, self.dev
+        f64, f32 = torch.float64, torch.float32
+        self.depth = torch.empty(n, dtype=f64, device=dev)
+        self.var = torch.empty(n, dtype=f64, device=dev)
+        self.rgb = torch.empty(n, 3, dtype=f32, device=dev)
+        self.z_vals = torch.empty(n, S, dtype=f64, device=dev)
+        self.raw = torch.empty(n, S, 4, dtype=f32, device=dev)
+        self.g_depth = torch.empty(n, dtype=f64, device=dev)
+        self.g_rgb = torch.empty(n, 3, dtype=f32, device=dev)
+        self.loss = torch.zeros(1, dtype=f64, device=dev)
+        self.depth_max = torch.zeros(2, dtype=f32, device=dev)
+        self.ws = torch.empty(L.nsb_iteration_workspace_bytes(n), dtype=torch.uint8, device=dev)
+        self.d_out = torch.empty(n * 6, dtype=f32, device=dev)          # [d_rays_o | d_rays_d], one block for the read-back
+        self.d_rays_o = self.d_out[: 3 * n].view(n, 3)
+        self.d_rays_d = self.d_out[3 * n:].view(n, 3)
+        self.d_c2w = torch.zeros(3, 4, dtype=f64, device=dev)
+        # device-side inputs (run_host copies into these; run() can alias caller tensors instead)
+        self.rays_o = torch.empty(n, 3, dtype=f32, device=dev)
+        self.rays_d = torch.empty(n, 3, dtype=f32, device=dev)
+        self.gt_depth = torch.empty(n, dtype=f32, device=dev)
+        self.gt_color = torch.empty(n, 3, dtype=f64 if kind == "track" else f32, device=dev)
+        self.grad_grids = tuple(grad_grids)
+        self.grad_decoders = tuple(grad_decoders)
+        self.d_grid = {}
+        self.d_flat = {lvl: torch.zeros(L.nsb_flat_decoder_floats(LEVELS.index(lvl)), dtype=f32, device=dev) for lvl in self.grad_decoders}
+        self.buf = _lib.IterationBuffers(self.depth.data_ptr(), self.var.data_ptr(), self.rgb.data_ptr(), self.z_vals.data_ptr(),
+                                         self.raw.data_ptr(), self.g_depth.data_ptr(), self.g_rgb.data_ptr(), self.loss.data_ptr(),
+                                         self.depth_max.data_ptr(), self.ws.data_ptr(), self.ws.numel(), None, None)
+        self.ev_bwd = None
+        # pinned host staging for run_host(): [rays_o | rays_d | gt_depth] f32, gt_color, and the read-back block
+        self.h_in32 = torch.empty(n * 7, dtype=f32).pin_memory() if dev.type == "cuda" else None
+        self.h_col = torch.empty(n, 3, dtype=self.gt_color.dtype).pin_memory() if dev.type == "cuda" else None
+        self.d_in32 = torch.empty(n * 7, dtype=f32, device=dev)
+        self.h_out = torch.empty(n * 6, dtype=f32).pin_memory() if dev.type == "cuda" else None
+        self.h_loss = torch.empty(1, dtype=f64).pin_memory() if dev.type == "cuda" else None
+        self.h_pose = torch.empty(3, 4, dtype=f64).pin_memory() if dev.type == "cuda" else None
+        self.h2d_bytes = n * 7 * 4 + self.gt_color.numel() * self.gt_color.element_size()
+        self.d2h_bytes = n * 6 * 4 + 8
+
+    # ------------------------------------------------------------------------------------------
+    def _grads(self, c):
+        bw = _lib.BackwardArgs()
+        bw.d_rays_o, bw.d_rays_d = self.d_rays_o.data_ptr(), self.d_rays_d.data_ptr()
+        for lvl in self.levels:
+            key = "grid_" + lvl
+            if key in self.grad_grids:
+                g = c[key]
+                if key not in self.d_grid or self.d_grid[key].stride() != g.stride():
+                    self.d_grid[key] = torch.empty_strided(g.size(), g.stride(), dtype=g.dtype, device=g.device)
+                self.d_grid[key].zero_()                      # dense voxel-gradient buffer, accumulated by the kernel
+                bw.d_grid[LEVELS.index(lvl)] = self.d_grid[key].data_ptr()
+            if lvl in self.d_flat:
+                self.d_flat[lvl].zero_()
+                bw.d_flat[LEVELS.index(lvl)] = self.d_flat[lvl].data_ptr()
+        return bw
+
+    def run(self, c, decoders, rays_o, rays_d, gt_depth, gt_color, w_color=None, handle_dynamic=True, use_color=True):
+        """Enqueue one iteration on the current stream (inputs already on the device).  Results stay on the device:
+        self.loss, self.depth/var/rgb, self.d_rays_o/d, self.d_grid[key], self.d_flat[level]."""
+        L = _lib.lib()
+        for t, nm in ((rays_o, "rays_o"), (rays_d, "rays_d"), (gt_depth, "gt_depth")):
+            _require_cuda(t, nm)
+        call, grids, _ = self.r._call(c, decoders, self.stage, gt_depth if self.render_with_depth else None, self.dev)
+        t_u, t_s = _linspaces(self.r.N_samples, self.r.N_surface, self.dev)
+        inp = _inputs(call, rays_o, rays_d, self.depth_max, t_u, t_s, [g.detach() for g in grids])
+        bw = self._grads(c)
+        if self.kind == "track":
+            w = 0.5 if w_color is None else w_color
+            _lib.check(L.nsb_tracking_iteration(C.byref(inp), C.byref(self.buf), _VP(gt_color.data_ptr()), w, int(handle_dynamic),
+                                                int(use_color), C.byref(bw), _stream()), "nsb_tracking_iteration")
+        else:
+            w = 0.2 if w_color is None else w_color
+            _lib.check(L.nsb_mapping_iteration(C.byref(inp), C.byref(self.buf), _VP(gt_depth.data_ptr()), _VP(gt_color.data_ptr()), w,
+                                               C.byref(bw), _stream()), "nsb_mapping_iteration")
+        return self.loss
+
+    def time_backward(self, enable=True):
+        """Profiling hook: have the library record CUDA events around the backward launch of every run()."""
+        if enable:
+            self.ev_bwd = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            for e in self.ev_bwd:
+                e.record()                                  # materialise the cudaEvent_t handle
+            self.buf.event_bwd_begin, self.buf.event_bwd_end = self.ev_bwd[0].cuda_event, self.ev_bwd[1].cuda_event
+        else:
+            self.ev_bwd = None
+            self.buf.event_bwd_begin = self.buf.event_bwd_end = None
+
+    def pose_grad(self, dirs):
+        """d c2w [3,4] (f64, device) of the last run() from the ray gradients (nsb_pose_grad)."""
+        _lib.check(_lib.lib().nsb_pose_grad(_VP(dirs.data_ptr()), _VP(self.d_rays_o.data_ptr()), _VP(self.d_rays_d.data_ptr()), self.n,
+                                            _VP(self.d_c2w.data_ptr()), _stream()), "nsb_pose_grad")
+        return self.d_c2w
+
+    def stage_host_inputs(self, rays_o, rays_d, gt_depth, gt_color):
+        """Fill the pinned host block from CPU tensors (outside the timed region of a benchmark)."""
+        n = self.n
+        self.h_in32[: 3 * n].copy_(rays_o.reshape(-1))
+        self.h_in32[3 * n: 6 * n].copy_(rays_d.reshape(-1))
+        self.h_in32[6 * n:].copy_(gt_depth.reshape(-1))
+        self.h_col.copy_(gt_color)
+
+    def run_host(self, c, decoders, **kw):
+        """End-to-end: pinned host inputs -> device -> iteration -> loss + ray gradients back to pinned host memory.
+        Returns (loss float, d_rays [N,6] pinned host view).  Synchronises the current stream."""
+        n = self.n
+        self.d_in32.copy_(self.h_in32, non_blocking=True)
+        self.gt_color.copy_(self.h_col, non_blocking=True)
+        ro, rd, gd = self.d_in32[: 3 * n].view(n, 3), self.d_in32[3 * n: 6 * n].view(n, 3), self.d_in32[6 * n:]
+        self.run(c, decoders, ro, rd, gd, self.gt_color, **kw)
+        self.h_out.copy_(self.d_out, non_blocking=True)
+        self.h_loss.copy_(self.loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self.h_loss[0]), self.h_out.view(2, n, 3)

@@ -107,6 +107,14 @@ def make_rays(scene, n, seed=0, frame_seed=0, pose_seed=0):
     return ro, rd, depth.reshape(-1)[idx], color.reshape(-1, 3)[idx]
 
 
+def prefilter_host(rays_o, rays_d, gt_depth, bound):
+    """Host-side data preparation for synthetic batches: keep rays whose bound exit lies beyond the sensor depth
+    (same rule as src/Tracker.py:95-104; plain torch, used only to BUILD benchmark/test inputs)."""
+    t = (bound.unsqueeze(0) - rays_o.unsqueeze(-1)) / rays_d.unsqueeze(-1)
+    t, _ = torch.min(torch.max(t, dim=2)[0], dim=1)
+    return t >= gt_depth
+
+
 def grid_summary(t, seed=0, n_sample=2048):
     """Compact fingerprint of a dense gradient grid: sum, L2 norm, 3 random projections, sampled entries."""
     flat = t.detach().double().reshape(-1).cpu()
@@ -121,6 +129,3 @@ def grid_summary(t, seed=0, n_sample=2048):
                 idx=pick.clone(), val=flat[pick].float().clone())
 
 
-def logical_flat_index_check(t):
-    """grid_summary indexes the LOGICAL (NCDHW) order: make that explicit for channels-last tensors."""
-    return t.contiguous(memory_format=torch.contiguous_format)

@@ -156,7 +156,7 @@ def test_seed_kernels_match_reference_losses():
     ws = torch.empty(L.nsb_tracking_seeds_workspace(n), dtype=torch.uint8, device=DEV)
     t = [dev(depth), dev(var), dev(rgb), dev(gt), dev(gt_rgb)]
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    _lib.check(L.nsb_tracking_seeds(*[C.c_void_p(x.data_ptr()) for x in t], n, 0.5, 1, 1, C.c_void_p(gD.data_ptr()), C.c_void_p(gC.data_ptr()),
+    _lib.check(L.nsb_tracking_seeds(*[C.c_void_p(x.data_ptr()) for x in t], n, 0.5, 1, 1, None, 0, C.c_void_p(gD.data_ptr()), C.c_void_p(gC.data_ptr()),
                                     C.c_void_p(lo.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(), st), "tracking_seeds")
     assert abs(float(lo) - float(loss)) < 1e-9 * abs(float(loss))
     assert rel(gD, d1.grad) < 1e-12 and rel(gC, c1.grad) < 1e-6
