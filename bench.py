@@ -287,16 +287,23 @@ def run_native(args):
                             "algorithmic_bytes_per_launch": BYTES_PER_RAY * RAYS_PER_GPU,
                             "note": "200-ray tracking batch is latency/FP32-FMA bound, not HBM bound (see DESIGN.md)"}
     if world == 1:
-        step = cpu_iteration_fn(sc, host)
-        torch.set_num_threads(os.cpu_count() or 1)
-        for _ in range(2):
+        best = None
+        for threads in sorted({1, os.cpu_count() or 1}):      # CPU grid_sample is single-threaded for batch 1; oversubscribed MKL is slower
+            torch.set_num_threads(threads)
+            step = cpu_iteration_fn(sc, host)
             step()
+            t0c = time.perf_counter(); step(); dt1 = time.perf_counter() - t0c
+            if best is None or dt1 < best[0]:
+                best = (dt1, threads)
+        torch.set_num_threads(best[1])
+        step = cpu_iteration_fn(sc, host)
         t0c, k = time.perf_counter(), 0
-        while k < 10 or time.perf_counter() - t0c < 8.0:
+        while k < 10 or time.perf_counter() - t0c < 10.0:
             step(); k += 1
         dtc = (time.perf_counter() - t0c) / k
-        line["cpu_baseline"] = {"value": RAYS_PER_GPU / dtc, "unit": "rays/s", "cores": os.cpu_count() or 1, "kind": "port",
-                                "sample": "%d iterations of the same 200-ray batch, oracle/torch_port.py on PyTorch CPU" % k,
+        line["cpu_baseline"] = {"value": RAYS_PER_GPU / dtc, "unit": "rays/s", "cores": best[1], "kind": "port",
+                                "sample": "%d iterations of the same 200-ray batch, oracle/torch_port.py on PyTorch CPU (%d threads of %d cores)"
+                                          % (k, best[1], os.cpu_count() or 1),
                                 "ms_per_step": dtc * 1e3}
     print(json.dumps(line))
     if world > 1:

@@ -193,27 +193,25 @@ __device__ __forceinline__ void chunk_point(const KParams& P, const Smem& sm, in
   }
 }
 
-template <int LV>
 __device__ __forceinline__ void chunk_forward(const KParams& P, const Smem& sm, float* act, int chunk, int Pb,
-                                              const LaneId& L, uint32_t parity, bool first_dec) {
-  using D = Dec<LV>;
+                                              const LaneId& L, uint32_t parity, bool first_dec, const int lv, const DecRT& d) {
   int lp; PointGeom G;
   chunk_point(P, sm, chunk, Pb, L.lane, lp, G);
-  const float* xn = LV == 0 ? G.xnc : G.xn;
-  gather_chunk(P.in.grid[LV], act, R_C, xn, L.lane);
-  if (LV == 2) gather_chunk(P.in.grid[1], act, R_C + 32, G.xn, L.lane);   // no_grad middle concat (decoder.py:182-187)
+  const float* xn = lv == 0 ? G.xnc : G.xn;
+  gather_chunk(P.in.grid[lv], act, R_C, xn, L.lane);
+  if (lv == 2) gather_chunk(P.in.grid[1], act, R_C + 32, G.xn, L.lane);   // no_grad middle concat (decoder.py:182-187)
   mbar_wait(sm.bar, parity);
-  if (D::XYZ) embed_chunk(act, sm.wt + D::o_B, G.pf, L.lane);
+  if (d.xyz) embed_chunk(act, sm.wt + d.o_B, G.pf, L.lane);
   __syncwarp();
-  uint32_t masks[5]; float out[4];
-  mlp_forward<LV, false>(sm.wt, act, L, masks, out);
+  Masks masks; float out[4];
+  mlp_forward<false>(d, sm.wt, act, L, masks, out);
   if (L.lane < 16 && lp < Pb) {
-    if (LV == 3) { sm.raw[4 * lp] = out[0]; sm.raw[4 * lp + 1] = out[1]; sm.raw[4 * lp + 2] = out[2]; }
+    if (lv == 3) { sm.raw[4 * lp] = out[0]; sm.raw[4 * lp + 1] = out[1]; sm.raw[4 * lp + 2] = out[2]; }
     else sm.raw[4 * lp + 3] += out[0];
     if (first_dec) {
       sm.inb[lp] = (unsigned char)G.inb;
       if (P.fo.corner_idx != nullptr) {
-        const nsb_grid& g = P.in.grid[LV];
+        const nsb_grid& g = P.in.grid[lv];
         const Tri t = make_tri(xn, g.W, g.H, g.D);
         const long long gp = ((long long)blockIdx.x * P.rays_per_block) * P.S + lp;
         P.fo.corner_idx[3 * gp] = t.i0[0]; P.fo.corner_idx[3 * gp + 1] = t.i0[1]; P.fo.corner_idx[3 * gp + 2] = t.i0[2];
@@ -277,14 +275,9 @@ __global__ void __launch_bounds__(256, 1) render_fwd_kernel(const __grid_constan
     const int lv = P.dec[qd];
     __syncthreads();                                             // previous weight image no longer in use
     if (threadIdx.x == 0) issue_weights(P, sm, lv);
-    for (int chunk = warp; chunk < nchunks; chunk += warps) {
-      switch (lv) {
-        case 0: chunk_forward<0>(P, sm, act, chunk, Pb, L, parity, qd == 0); break;
-        case 1: chunk_forward<1>(P, sm, act, chunk, Pb, L, parity, qd == 0); break;
-        case 2: chunk_forward<2>(P, sm, act, chunk, Pb, L, parity, qd == 0); break;
-        default: chunk_forward<3>(P, sm, act, chunk, Pb, L, parity, qd == 0); break;
-      }
-    }
+    const DecRT d = make_dec(lv);
+#pragma unroll 1
+    for (int chunk = warp; chunk < nchunks; chunk += warps) chunk_forward(P, sm, act, chunk, Pb, L, parity, qd == 0, lv, d);
     parity ^= 1u;
   }
   __syncthreads();
@@ -333,24 +326,23 @@ __global__ void __launch_bounds__(256, 1) render_fwd_kernel(const __grid_constan
 // ------------------------------------------------------------------------------------------------
 // backward kernel
 // ------------------------------------------------------------------------------------------------
-template <int LV, bool WGRAD>
 __device__ __forceinline__ void chunk_backward(const KParams& P, const Smem& sm, float* act, int chunk, int Pb,
-                                               const LaneId& L, uint32_t parity, const float* gC /*[R][3] smem*/) {
-  using D = Dec<LV>;
+                                               const LaneId& L, uint32_t parity, const float* gC /*[R][3] smem*/,
+                                               const int lv, const DecRT& d) {
   int lp; PointGeom G;
   chunk_point(P, sm, chunk, Pb, L.lane, lp, G);
-  const float* xn = LV == 0 ? G.xnc : G.xn;
-  gather_chunk(P.in.grid[LV], act, R_C, xn, L.lane);
-  if (LV == 2) gather_chunk(P.in.grid[1], act, R_C + 32, G.xn, L.lane);
+  const float* xn = lv == 0 ? G.xnc : G.xn;
+  gather_chunk(P.in.grid[lv], act, R_C, xn, L.lane);
+  if (lv == 2) gather_chunk(P.in.grid[1], act, R_C + 32, G.xn, L.lane);
   mbar_wait(sm.bar, parity);
-  if (D::XYZ) embed_chunk(act, sm.wt + D::o_B, G.pf, L.lane);
+  if (d.xyz) embed_chunk(act, sm.wt + d.o_B, G.pf, L.lane);
   __syncwarp();
-  uint32_t masks[5]; float out[4];
-  mlp_forward<LV, true>(sm.wt, act, L, masks, out);
+  Masks masks; float out[4];
+  mlp_forward<true>(d, sm.wt, act, L, masks, out);
 
   float g_out[4] = {0.f, 0.f, 0.f, 0.f};
   if (lp < Pb) {
-    if (LV == 3) { const int ray = lp / P.S; const float w = sm.wgt[lp];
+    if (lv == 3) { const int ray = lp / P.S; const float w = sm.wgt[lp];
       g_out[0] = w * gC[3 * ray]; g_out[1] = w * gC[3 * ray + 1]; g_out[2] = w * gC[3 * ray + 2]; }
     else g_out[0] = sm.gocc[lp];
   }
@@ -359,17 +351,17 @@ __device__ __forceinline__ void chunk_backward(const KParams& P, const Smem& sm,
   for (int p = 0; p < 4; p++)
 #pragma unroll
     for (int a = 0; a < 3; a++) pfq[p][a] = __shfl_sync(0xffffffffu, G.pf[a], 4 * L.pg + p);
-  mlp_backward<LV, WGRAD>(sm.wt, act, L, masks, g_out, pfq, dpe, WGRAD ? P.d_packed[LV] : nullptr);
+  mlp_backward(d, sm.wt, act, L, masks, g_out, pfq, dpe, P.d_packed[lv]);
 
-  if (D::XYZ && L.og == 0) {                                      // embedding chain -> dL/dp
+  if (d.xyz && L.og == 0) {                                       // embedding chain -> dL/dp
 #pragma unroll
     for (int p = 0; p < 4; p++) { const int l2 = chunk * kChunk + 4 * L.pg + p;
       if (l2 < Pb) { sm.dp[3 * l2] += (double)dpe[p][0]; sm.dp[3 * l2 + 1] += (double)dpe[p][1]; sm.dp[3 * l2 + 2] += (double)dpe[p][2]; } }
   }
   __syncwarp();
-  const double* bb = LV == 0 ? P.in.coarse_bound : P.in.bound;
+  const double* bb = lv == 0 ? P.in.coarse_bound : P.in.bound;
   // rows of padding points (lp >= Pb) carry zero gradients because their g_out is zero
-  scatter_chunk(P.in.grid[LV], P.bw.d_grid[LV], act, R_C, xn, L.lane, [&](int pt, const float gx[3]) {
+  scatter_chunk(P.in.grid[lv], P.bw.d_grid[lv], act, R_C, xn, L.lane, [&](int pt, const float gx[3]) {
     const int l2 = chunk * kChunk + pt;
     if (l2 < Pb) {
 #pragma unroll
@@ -443,21 +435,11 @@ __global__ void __launch_bounds__(256, 1) render_bwd_kernel(const __grid_constan
   uint32_t parity = 0;
   for (int qd = 0; qd < P.n_dec; qd++) {
     const int lv = P.dec[qd];
-    const bool wg = P.d_packed[lv] != nullptr;
+    const DecRT d = make_dec(lv);
     __syncthreads();
     if (threadIdx.x == 0) issue_weights(P, sm, lv);
-    for (int chunk = warp; chunk < nchunks; chunk += warps) {
-      switch (lv * 2 + (wg ? 1 : 0)) {
-        case 0: chunk_backward<0, false>(P, sm, act, chunk, Pb, L, parity, gC); break;
-        case 1: chunk_backward<0, true>(P, sm, act, chunk, Pb, L, parity, gC); break;
-        case 2: chunk_backward<1, false>(P, sm, act, chunk, Pb, L, parity, gC); break;
-        case 3: chunk_backward<1, true>(P, sm, act, chunk, Pb, L, parity, gC); break;
-        case 4: chunk_backward<2, false>(P, sm, act, chunk, Pb, L, parity, gC); break;
-        case 5: chunk_backward<2, true>(P, sm, act, chunk, Pb, L, parity, gC); break;
-        case 6: chunk_backward<3, false>(P, sm, act, chunk, Pb, L, parity, gC); break;
-        default: chunk_backward<3, true>(P, sm, act, chunk, Pb, L, parity, gC); break;
-      }
-    }
+#pragma unroll 1
+    for (int chunk = warp; chunk < nchunks; chunk += warps) chunk_backward(P, sm, act, chunk, Pb, L, parity, gC, lv, d);
     parity ^= 1u;
   }
   __syncthreads();
