@@ -198,24 +198,29 @@ def run_native(args):
     sharded = ShardedTrackingIteration(ctx) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
 
-    def step_dev():
-        if sharded is not None:
-            sharded.run(c, dec, ro, rd, dirs, gd, gc)
-        else:
-            ctx.run(c, dec, ro, rd, gd, gc)
-            ctx.pose_grad(dirs)
-
     h_pose = torch.empty(13, dtype=torch.float64).pin_memory()
+    if sharded is None:
+        # single GPU: the whole iteration (and, for e2e, its host copies) is one CUDA-graph launch
+        ctx.load_device_inputs(ro, rd, gd, gc)
+        g_dev = ctx.build_graph(c, dec, dirs=dirs, host_io=False)
+        g_e2e = ctx.build_graph(c, dec, dirs=dirs, host_io=True)
 
-    def step_e2e():
-        if sharded is not None:          # host inputs -> device -> sharded iteration -> [loss | d_c2w] back to the host
+        def step_dev():
+            g_dev.replay()
+
+        def step_e2e():
+            g_e2e.replay()
+            torch.cuda.current_stream().synchronize()      # the caller reads loss / pose gradient from pinned memory
+    else:
+        def step_dev():
+            sharded.run(c, dec, ro, rd, dirs, gd, gc)
+
+        def step_e2e():      # host inputs -> device -> sharded iteration (NCCL exchanges) -> [loss | d_c2w] back to the host
             n = ctx.n
             ctx.d_in32.copy_(ctx.h_in32, non_blocking=True); ctx.gt_color.copy_(ctx.h_col, non_blocking=True)
             packed = sharded.run(c, dec, ctx.d_in32[: 3 * n].view(n, 3), ctx.d_in32[3 * n: 6 * n].view(n, 3), dirs, ctx.d_in32[6 * n:], ctx.gt_color)
             h_pose.copy_(packed, non_blocking=True)
             torch.cuda.current_stream().synchronize()
-        else:
-            ctx.run_host(c, dec)
 
     def timed(fn, steps, warmup, flush_l2):
         for _ in range(warmup):
@@ -249,12 +254,12 @@ def run_native(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ctx.time_backward(True)
     total_ms, t0, t1 = timed(step_dev, args.steps, max(args.warmup, 3), True)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     # dominant kernel (render_bwd_kernel): events recorded by the library around its launch, averaged over a short loop
     bwd_ms = []
     if sharded is None:
+        ctx.time_backward(True)
         for _ in range(50):
             flush.zero_(); ctx.run(c, dec, ro, rd, gd, gc); torch.cuda.synchronize()
             bwd_ms.append(ctx.ev_bwd[0].elapsed_time(ctx.ev_bwd[1]))
@@ -273,10 +278,11 @@ def run_native(args):
     line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "rays_per_step": rays, "l2": "flushed between steps (256 MiB memset outside the event pair)",
+                       "launch": "CUDA graph replay (one graph per iteration)" if sharded is None else "stream launches + NCCL",
                        "parallelism": "ray-sharded x%d" % world, "timing": "sum of per-step CUDA-event pairs, max over ranks"},
             "clocks": clocks,
             "e2e": {"value": rays / (e2e_ms / args.steps * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": ctx.h2d_bytes,
-                    "d2h_bytes_per_step": ctx.d2h_bytes if sharded is None else 13 * 8, "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": (ctx.d2h_bytes + 96) if sharded is None else 13 * 8, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": (5 if sharded is None else 7) * args.steps,
             "extra": {"l2_warm_ms_per_step": warm_ms / args.steps, "l2_warm_rays_per_s": rays / (warm_ms / args.steps * 1e-3)}}
     if bwd_ms:

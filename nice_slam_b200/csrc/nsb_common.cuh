@@ -49,16 +49,16 @@ struct Dec {
   static constexpr int TOTAL = o_bo + 4;
   static_assert(TOTAL % 4 == 0, "packed image must be a multiple of 16 bytes");
   // activation rows per warp
-  static constexpr int ROWS_FWD = FIRSTP * (XYZ ? 1 : 0) + 64 + 64;                 // E | C | HA | HB
-  static constexpr int ROWS_BWD = FIRSTP * (XYZ ? 1 : 0) + 64 + 160 + 32 + 32;      // E | C | S1..S5 | DU | DU3
+  static constexpr int ROWS_FWD = 32 + 64 + 64;                 // E-scratch | C | HA | HB
+  static constexpr int ROWS_BWD = 32 + 64 + 160 + 32 + 32;      // E-scratch | C | S1..S5 | DU | DU3
 };
 
 __host__ __device__ constexpr int packed_floats(int lv) {
   return lv == 0 ? Dec<0>::TOTAL : lv == 1 ? Dec<1>::TOTAL : lv == 2 ? Dec<2>::TOTAL : Dec<3>::TOTAL;
 }
 constexpr int kMaxPacked = Dec<2>::TOTAL;
-constexpr int kRowsFwd = Dec<2>::ROWS_FWD;     // 224
-constexpr int kRowsBwd = Dec<2>::ROWS_BWD;     // 384
+constexpr int kRowsFwd = Dec<2>::ROWS_FWD;     // 160
+constexpr int kRowsBwd = Dec<2>::ROWS_BWD;     // 320
 
 // canonical flat layout (include/nice_slam_b200.h): kind 0=B 1=W 2=b 3=Wc 4=bc 5=Wo 6=bo 7=total
 __host__ __device__ inline int dec_in(int lv, int i) {

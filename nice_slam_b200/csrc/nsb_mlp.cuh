@@ -21,13 +21,13 @@
 namespace nsb {
 
 // row bases inside a warp's activation area (all multiples of 8, required by the swizzle)
-constexpr int R_E = 0;         // 96 rows: Fourier embedding (rows 93..95 are zero)
-constexpr int R_C = 96;        // 64 rows: sampled grid features (fine: [fine | middle])
-constexpr int R_HA = 160;      // forward-only kernels: ping
-constexpr int R_HB = 192;      //                        pong
-constexpr int R_S = 160;       // backward kernels: S1..S5 (5 x 32 rows): h_{i+1}, later g_{i+1}
-constexpr int R_DU = 320;      // 32 rows
-constexpr int R_DU3 = 352;     // 32 rows
+constexpr int R_E = 0;         // 32 rows: scratch block of the Fourier embedding (recomputed 32 features at a time)
+constexpr int R_C = 32;        // 64 rows: sampled grid features (fine: [fine | middle])
+constexpr int R_HA = 96;       // forward-only kernels: ping
+constexpr int R_HB = 128;      //                        pong          -> 160 rows (10 KB) per warp
+constexpr int R_S = 96;        // backward kernels: S1..S5 (5 x 32 rows): h_{i+1}, later g_{i+1}
+constexpr int R_DU = 256;      // 32 rows
+constexpr int R_DU3 = 288;     // 32 rows                               -> 320 rows (20 KB) per warp
 
 struct LaneId { int lane, pg, og; int q[4]; };
 __device__ __forceinline__ LaneId make_lane(int lane) {
@@ -178,16 +178,32 @@ __device__ __forceinline__ float fourier_arg(const float pf[3], const float* __r
   return fmaf(pf[2], B[2 * kEmbPad + f], x);
 }
 
-// E rows <- sin(p @ B) for the 16 points of the chunk.  pf = this lane's point (lane&15) coordinates.
-__device__ __forceinline__ void embed_chunk(float* __restrict__ act, const float* __restrict__ B, const float pf[3], int lane) {
+// Scratch rows [R_E, R_E+32) <- features [32*blk, 32*blk+32) of sin(p @ B) for the 16 points of the chunk (features
+// >= 93 are zero).  pf = coordinates of this lane's point (lane & 15).  The embedding is recomputed block by block
+// where it is consumed (layers 0 and 3, and their weight gradients) instead of living in 96 rows of shared memory:
+// ~600 extra instructions per chunk buy 4 KB per warp, i.e. more resident warps per SM.
+__device__ __forceinline__ void embed_block(float* __restrict__ act, const float* __restrict__ B, const float pf[3], int lane, int blk) {
   const int pt = lane & 15, half = lane >> 4;
 #pragma unroll 4
-  for (int it = 0; it < kEmbPad / 2; it++) {
-    const int f = 2 * it + half;
+  for (int it = 0; it < 16; it++) {
+    const int fl = 2 * it + half, f = 32 * blk + fl;
     float v = 0.0f;
     if (f < kEmb) v = __sinf(reduce_2pi(fourier_arg(pf, B, f)));
-    act[act_idx(R_E + f, pt)] = v;
+    act[act_idx(R_E + fl, pt)] = v;
   }
+}
+// acc += first-input part of layer 0 / 3:  W[:, first] * first   (first = Fourier embedding, or the grid feature for coarse)
+__device__ __forceinline__ void gemm_first(float (&acc)[4][4], const DecRT& d, float* __restrict__ act, const float* __restrict__ Wt,
+                                           const int o_w, const float pf[3], const LaneId& L) {
+  if (d.xyz) {
+#pragma unroll 1
+    for (int blk = 0; blk < 3; blk++) {
+      embed_block(act, Wt + d.o_B, pf, L.lane, blk);
+      __syncwarp();
+      gemm_t(acc, act + R_E * kRowF, Wt + o_w + 32 * blk, d.pf, 32, L);
+      __syncwarp();
+    }
+  } else gemm_t(acc, act + R_C * kRowF, Wt + o_w, d.pf, 32, L);
 }
 
 // relu masks of the five layers, 16 bits each (bit 4p+j <-> T-own element [p][j]), packed in three registers
@@ -206,8 +222,7 @@ __device__ __forceinline__ uint32_t get_mask(const Masks& M, int i) {
 // ---------------------------------------------------------------------------------------------
 template <bool KEEP>
 __device__ __forceinline__ void mlp_forward(const DecRT& d, const float* __restrict__ Wt, float* __restrict__ act, const LaneId& L,
-                                            Masks& masks, float (&out)[4]) {
-  const float* first = act + (d.xyz ? R_E : R_C) * kRowF;
+                                            const float pf[3], Masks& masks, float (&out)[4]) {
   const float* crow = act + R_C * kRowF;
   masks.m01 = masks.m23 = masks.m4 = 0u;
 #pragma unroll 1
@@ -220,7 +235,7 @@ __device__ __forceinline__ void mlp_forward(const DecRT& d, const float* __restr
     }
     const int rin = KEEP ? (R_S + (i - 1) * 32) : ((i & 1) ? R_HA : R_HB);     // rows of h_i (i >= 1)
     const int rout = KEEP ? (R_S + i * 32) : ((i & 1) ? R_HB : R_HA);         // rows of h_{i+1}
-    if (i == 0 || i == 3) gemm_t(acc, first, Wt + (i == 0 ? d.o_W0 : d.o_W3E), d.pf, d.firstp, L);
+    if (i == 0 || i == 3) gemm_first(acc, d, act, Wt, i == 0 ? d.o_W0 : d.o_W3E, pf, L);
     if (i >= 1) gemm_t(acc, act + rin * kRowF, Wt + dec_wh(d, i), Dec<1>::PH, 32, L);
     uint32_t m = 0;
 #pragma unroll
@@ -310,13 +325,12 @@ __device__ __forceinline__ void bgrad(float* __restrict__ dst, const float* __re
 // memory, or nullptr when this decoder's parameters get no gradient.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mlp_backward(const DecRT& d, const float* __restrict__ Wt, float* __restrict__ act, const LaneId& L,
-                                             const Masks& masks, const float (&g_out)[4],
+                                             const float pf[3], const Masks& masks, const float (&g_out)[4],
                                              const float (&pfq)[4][3], float (&dpe)[4][3], float* __restrict__ dWp) {
   float* S = act + R_S * kRowF;
   float* DU = act + R_DU * kRowF;
   float* DU3 = act + R_DU3 * kRowF;
   float* C = act + R_C * kRowF;
-  const float* first = act + (d.xyz ? R_E : R_C) * kRowF;
   const int pt = L.lane & 15, half = L.lane >> 4;
   const bool wgrad = dWp != nullptr;
   constexpr int PH = Dec<1>::PH;
@@ -385,7 +399,18 @@ __device__ __forceinline__ void mlp_backward(const DecRT& d, const float* __rest
     }
     __syncwarp();
     if (wgrad) {                                     // pts_linears.i : dW = du x_i^T, db = sum du
-      if (i == 0 || i == 3) wgrad_nt(dWp + (i == 0 ? d.o_W0 : d.o_W3E), d.pf, du, first, d.firstp, L);
+      if (i == 0 || i == 3) {
+        float* dst = dWp + (i == 0 ? d.o_W0 : d.o_W3E);
+        if (d.xyz) {
+#pragma unroll 1
+          for (int blk = 0; blk < 3; blk++) {           // recompute the embedding block as the X operand
+            embed_block(act, Wt + d.o_B, pf, L.lane, blk);
+            __syncwarp();
+            wgrad_nt(dst + 32 * blk, d.pf, du, act + R_E * kRowF, 32, L);
+            __syncwarp();
+          }
+        } else wgrad_nt(dst, d.pf, du, C, 32, L);
+      }
       if (i >= 1) wgrad_nt(dWp + dec_wh(d, i), PH, du, S + (i - 1) * 32 * kRowF, 32, L);
       bgrad(dWp + d.o_b + i * 32, du, L.lane);
       __syncwarp();

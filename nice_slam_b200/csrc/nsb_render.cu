@@ -139,7 +139,7 @@ __host__ __device__ inline size_t smem_layout(int wbytes, int max_pts, int max_r
   auto take = [&](size_t bytes) { size_t r = o; o = align16(o + bytes); return r; };
   size_t o_wt = take(wbytes), o_bar = take(16), o_rays = take(sizeof(float) * 8 * max_rays), o_far = take(sizeof(double) * max_rays);
   size_t o_zs = take(sizeof(double) * max_pts), o_raw = take(sizeof(float) * 4 * max_pts);
-  size_t o_dp = bwd ? take(sizeof(double) * 3 * max_pts) : 0, o_gocc = bwd ? take(sizeof(float) * max_pts) : 0, o_wgt = bwd ? take(sizeof(float) * max_pts) : 0;
+  size_t o_dp = bwd ? take(sizeof(double) * 3 * max_pts) : 0, o_gocc = bwd ? take(sizeof(float) * max_pts) : 0, o_wgt = take(sizeof(float) * max_pts);
   size_t o_inb = take(max_pts);
   size_t o_act = take((size_t)warps * rows * kRowF * sizeof(float));
   if (s) {
@@ -201,10 +201,9 @@ __device__ __forceinline__ void chunk_forward(const KParams& P, const Smem& sm, 
   gather_chunk(P.in.grid[lv], act, R_C, xn, L.lane);
   if (lv == 2) gather_chunk(P.in.grid[1], act, R_C + 32, G.xn, L.lane);   // no_grad middle concat (decoder.py:182-187)
   mbar_wait(sm.bar, parity);
-  if (d.xyz) embed_chunk(act, sm.wt + d.o_B, G.pf, L.lane);
   __syncwarp();
   Masks masks; float out[4];
-  mlp_forward<false>(d, sm.wt, act, L, masks, out);
+  mlp_forward<false>(d, sm.wt, act, L, G.pf, masks, out);
   if (L.lane < 16 && lp < Pb) {
     if (lv == 3) { sm.raw[4 * lp] = out[0]; sm.raw[4 * lp + 1] = out[1]; sm.raw[4 * lp + 2] = out[2]; }
     else sm.raw[4 * lp + 3] += out[0];
@@ -222,6 +221,45 @@ __device__ __forceinline__ void chunk_forward(const KParams& P, const Smem& sm, 
 }
 
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// warp-wide helpers for the per-ray compositing scans (one warp per ray, lanes over samples)
+__device__ __forceinline__ float warp_incl_prod(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v *= t; }
+  return v;
+}
+__device__ __forceinline__ float warp_incl_suffix_sum(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_down_sync(0xffffffffu, v, o); if (lane + o < 32) v += t; }
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// alpha_s = sigmoid(10 occ_s), T_s = prod_{j<s} (1 - alpha_j + 1e-10), w_s = alpha_s T_s  (common.py:233-240).
+// Writes w to wq[] and (optionally) T to tq[].  All lanes of one warp call it for one ray.
+__device__ __forceinline__ void ray_weights(const float* __restrict__ rw, int S, int lane, float* __restrict__ wq, float* __restrict__ tq) {
+  float carry = 1.0f;
+  for (int base = 0; base < S; base += 32) {
+    const int s = base + lane;
+    const bool v = s < S;
+    const float al = v ? sigmoid_f(10.0f * rw[4 * s + 3]) : 0.0f;
+    const float q = v ? (1.0f - al) + 1e-10f : 1.0f;
+    const float incl = warp_incl_prod(q, lane);
+    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 1.0f;
+    const float T = carry * excl;
+    if (v) { wq[s] = al * T; if (tq) tq[s] = T; }
+    carry *= __shfl_sync(0xffffffffu, incl, 31);
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // forward kernel
@@ -294,27 +332,26 @@ __global__ void __launch_bounds__(256, 1) render_fwd_kernel(const __grid_constan
   // out-of-bound override (Renderer.py:57), then raw2outputs_nerf_color, occupancy branch (common.py:233-244)
   for (int lp = threadIdx.x; lp < Pb; lp += blockDim.x) if (!sm.inb[lp]) sm.raw[4 * lp + 3] = 100.0f;
   __syncthreads();
-  for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+  for (int r = warp; r < nr; r += warps) {                       // one warp per ray, lanes over samples
     const float* rw = sm.raw + 4 * r * P.S;
     const double* z = sm.zs + r * P.S;
-    float T = 1.0f, c0 = 0.f, c1 = 0.f, c2 = 0.f; double dsum = 0.0;
-    for (int s = 0; s < P.S; s++) {
-      const float al = sigmoid_f(10.0f * rw[4 * s + 3]);
-      const float w = al * T;
-      T = T * ((1.0f - al) + 1e-10f);
+    float* wq = sm.wgt + r * P.S;
+    ray_weights(rw, P.S, L.lane, wq, nullptr);
+    __syncwarp();
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f; double dsum = 0.0;
+    for (int s = L.lane; s < P.S; s += 32) {
+      const float w = wq[s];
       c0 = fmaf(w, rw[4 * s], c0); c1 = fmaf(w, rw[4 * s + 1], c1); c2 = fmaf(w, rw[4 * s + 2], c2);
       dsum += (double)w * z[s];
     }
-    double v = 0.0; T = 1.0f;
-    for (int s = 0; s < P.S; s++) {
-      const float al = sigmoid_f(10.0f * rw[4 * s + 3]);
-      const float w = al * T;
-      T = T * ((1.0f - al) + 1e-10f);
-      const double t = z[s] - dsum;
-      v += (double)w * t * t;
+    c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2); dsum = warp_sum(dsum);
+    double v = 0.0;
+    for (int s = L.lane; s < P.S; s += 32) { const double t = z[s] - dsum; v += (double)wq[s] * t * t; }
+    v = warp_sum(v);
+    if (L.lane == 0) {
+      P.fo.depth[r0 + r] = dsum; P.fo.var[r0 + r] = v;
+      P.fo.rgb[3 * (r0 + r)] = c0; P.fo.rgb[3 * (r0 + r) + 1] = c1; P.fo.rgb[3 * (r0 + r) + 2] = c2;
     }
-    P.fo.depth[r0 + r] = dsum; P.fo.var[r0 + r] = v;
-    P.fo.rgb[3 * (r0 + r)] = c0; P.fo.rgb[3 * (r0 + r) + 1] = c1; P.fo.rgb[3 * (r0 + r) + 2] = c2;
   }
   const long long g0 = (long long)r0 * P.S;
   if (P.fo.z_vals != nullptr) for (int lp = threadIdx.x; lp < Pb; lp += blockDim.x) P.fo.z_vals[g0 + lp] = sm.zs[lp];
@@ -335,10 +372,9 @@ __device__ __forceinline__ void chunk_backward(const KParams& P, const Smem& sm,
   gather_chunk(P.in.grid[lv], act, R_C, xn, L.lane);
   if (lv == 2) gather_chunk(P.in.grid[1], act, R_C + 32, G.xn, L.lane);
   mbar_wait(sm.bar, parity);
-  if (d.xyz) embed_chunk(act, sm.wt + d.o_B, G.pf, L.lane);
   __syncwarp();
   Masks masks; float out[4];
-  mlp_forward<true>(d, sm.wt, act, L, masks, out);
+  mlp_forward<true>(d, sm.wt, act, L, G.pf, masks, out);
 
   float g_out[4] = {0.f, 0.f, 0.f, 0.f};
   if (lp < Pb) {
@@ -351,7 +387,7 @@ __device__ __forceinline__ void chunk_backward(const KParams& P, const Smem& sm,
   for (int p = 0; p < 4; p++)
 #pragma unroll
     for (int a = 0; a < 3; a++) pfq[p][a] = __shfl_sync(0xffffffffu, G.pf[a], 4 * L.pg + p);
-  mlp_backward(d, sm.wt, act, L, masks, g_out, pfq, dpe, P.d_packed[lv]);
+  mlp_backward(d, sm.wt, act, L, G.pf, masks, g_out, pfq, dpe, P.d_packed[lv]);
 
   if (d.xyz && L.og == 0) {                                       // embedding chain -> dL/dp
 #pragma unroll
@@ -400,7 +436,7 @@ __global__ void __launch_bounds__(256, 1) render_bwd_kernel(const __grid_constan
   }
   __syncthreads();
   // per-ray: compositing weights and dL/d(occupancy logit)   (cumprod backward in division form)
-  for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+  for (int r = warp; r < nr; r += warps) {                       // one warp per ray, lanes over samples
     const float* rw = sm.raw + 4 * r * P.S;
     const double* z = sm.zs + r * P.S;
     float* wq = sm.wgt + r * P.S; float* go = sm.gocc + r * P.S;
@@ -408,26 +444,38 @@ __global__ void __launch_bounds__(256, 1) render_bwd_kernel(const __grid_constan
     const double gV = P.bw.g_var != nullptr ? P.bw.g_var[r0 + r] : 0.0;
     float g3[3] = {0.f, 0.f, 0.f};
     if (P.bw.g_rgb != nullptr) { g3[0] = P.bw.g_rgb[3 * (r0 + r)]; g3[1] = P.bw.g_rgb[3 * (r0 + r) + 1]; g3[2] = P.bw.g_rgb[3 * (r0 + r) + 2]; }
-    gC[3 * r] = g3[0]; gC[3 * r + 1] = g3[1]; gC[3 * r + 2] = g3[2];
-    float T = 1.0f; double Dm = 0.0;
-    for (int s = 0; s < P.S; s++) {                              // forward scan: w_s (go[] temporarily holds T_s)
-      const float al = sigmoid_f(10.0f * rw[4 * s + 3]);
-      wq[s] = al * T; go[s] = T;
-      T = T * ((1.0f - al) + 1e-10f);
-      Dm += (double)wq[s] * z[s];
-    }
+    if (L.lane == 0) { gC[3 * r] = g3[0]; gC[3 * r + 1] = g3[1]; gC[3 * r + 2] = g3[2]; }
+    ray_weights(rw, P.S, L.lane, wq, go);                        // go[] temporarily holds T_s
+    __syncwarp();
+    double Dm = 0.0;
+    for (int s = L.lane; s < P.S; s += 32) Dm += (double)wq[s] * z[s];
+    Dm = warp_sum(Dm);
     double swt = 0.0;
-    for (int s = 0; s < P.S; s++) swt += (double)wq[s] * (z[s] - Dm);
+    for (int s = L.lane; s < P.S; s += 32) swt += (double)wq[s] * (z[s] - Dm);
+    swt = warp_sum(swt);
     const double gDe = gD + gV * (-2.0 * swt);                   // var reaches depth through tmp = z - depth
-    float R = 0.0f;
-    for (int s = P.S - 1; s >= 0; s--) {
-      const float al = sigmoid_f(10.0f * rw[4 * s + 3]);
-      const double t = z[s] - Dm;
-      const float gw = (float)(gDe * z[s] + gV * t * t) + g3[0] * rw[4 * s] + g3[1] * rw[4 * s + 1] + g3[2] * rw[4 * s + 2];
-      const float qd = (1.0f - al) + 1e-10f;
-      const float ga = go[s] * gw - R / qd;
-      R += gw * wq[s];
-      go[s] = sm.inb[r * P.S + s] ? 10.0f * al * (1.0f - al) * ga : 0.0f;
+    // dL/dalpha_s = T_s g_w_s - (sum_{k>s} g_w_k w_k) / q_s   (cumprod backward in division form)
+    float carry = 0.0f;
+    const int nblk = (P.S + 31) / 32;
+    for (int b = nblk - 1; b >= 0; b--) {
+      const int s = b * 32 + L.lane;
+      const bool v = s < P.S;
+      float gw = 0.0f, al = 0.0f, T = 0.0f, w = 0.0f;
+      if (v) {
+        al = sigmoid_f(10.0f * rw[4 * s + 3]); T = go[s]; w = wq[s];
+        const double t = z[s] - Dm;
+        gw = (float)(gDe * z[s] + gV * t * t) + g3[0] * rw[4 * s] + g3[1] * rw[4 * s + 1] + g3[2] * rw[4 * s + 2];
+      }
+      const float incl = warp_incl_suffix_sum(gw * w, L.lane);
+      float excl = __shfl_down_sync(0xffffffffu, incl, 1);       // exclusive suffix sum inside the block (no cancellation)
+      if (L.lane == 31) excl = 0.0f;
+      const float R = carry + excl;
+      if (v) {
+        const float qd = (1.0f - al) + 1e-10f;
+        const float ga = T * gw - R / qd;
+        go[s] = sm.inb[r * P.S + s] ? 10.0f * al * (1.0f - al) * ga : 0.0f;
+      }
+      carry += __shfl_sync(0xffffffffu, incl, 0);
     }
   }
 

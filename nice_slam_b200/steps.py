@@ -121,6 +121,47 @@ class IterationContext:
                                             _VP(self.d_c2w.data_ptr()), _stream()), "nsb_pose_grad")
         return self.d_c2w
 
+    # ------------------------------------------------------------------------------------------ CUDA graph
+    def device_views(self):
+        """(rays_o, rays_d, gt_depth, gt_color) views of the context-owned input block (fixed addresses for graphs)."""
+        n = self.n
+        return self.d_in32[: 3 * n].view(n, 3), self.d_in32[3 * n: 6 * n].view(n, 3), self.d_in32[6 * n:], self.gt_color
+
+    def load_device_inputs(self, rays_o, rays_d, gt_depth, gt_color):
+        ro, rd, gd, gc = self.device_views()
+        ro.copy_(rays_o); rd.copy_(rays_d); gd.copy_(gt_depth); gc.copy_(gt_color)
+
+    def build_graph(self, c, decoders, dirs=None, host_io=False, **kw):
+        """Capture one whole iteration into a CUDA graph (launch-bound small batches: one graph launch instead of
+        4-6 kernel launches + Python glue).  Inputs are read from the context-owned block (load_device_inputs) or,
+        with host_io, copied from the pinned staging block inside the graph; results stay in the context's buffers
+        (and, with host_io, are copied to the pinned read-back block inside the graph).
+        Re-capture after anything that changes pointers (grids re-created) or the decoders' packed image."""
+        ro, rd, gd, gc = self.device_views()
+
+        def body():
+            if host_io:
+                self.d_in32.copy_(self.h_in32, non_blocking=True)
+                self.gt_color.copy_(self.h_col, non_blocking=True)
+            self.run(c, decoders, ro, rd, gd, gc, **kw)
+            if dirs is not None:
+                self.pose_grad(dirs)
+            if host_io:
+                self.h_out.copy_(self.d_out, non_blocking=True)
+                self.h_loss.copy_(self.loss, non_blocking=True)
+                self.h_pose.copy_(self.d_c2w, non_blocking=True)
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            body(); body()                       # warm-up outside capture: lazy attribute setup, decoder packing
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            body()
+        return g
+
     def stage_host_inputs(self, rays_o, rays_d, gt_depth, gt_color):
         """Fill the pinned host block from CPU tensors (outside the timed region of a benchmark)."""
         n = self.n
