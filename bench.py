@@ -177,6 +177,44 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def extra_workloads(sc, renderer, c, dec, dev, flush, peak):
+    """Secondary measurements reported under `extra` (same timing rules: CUDA events per step, L2 flushed between steps):
+    BASELINE configs[1] (mapping iteration, 996 rays = 6 frames x 166 px, stage color, voxel + colour-decoder gradients)
+    and the ray-throughput sweep (tracking-style fwd+loss+bwd, 48 samples) at larger batches."""
+    from nice_slam_b200.steps import IterationContext
+
+    def time_steps(fn, steps, warmup=3):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in evs:
+            flush.zero_(); a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs) / steps
+
+    out = {}
+    n = 996
+    ro, rd, dirs, gd, gc = [t.to(dev) for t in make_batch(sc, n, 101)]
+    ctx = IterationContext(renderer, n, "color", dev, kind="map", grad_grids=("grid_middle", "grid_fine", "grid_color"), grad_decoders=("color",))
+    gcf = gc.float()
+    ms = time_steps(lambda: ctx.run(c, dec, ro, rd, gd, gcf), 100)
+    bpr = 48 * 3 * 1024 * 2
+    out["mapping_configs1"] = {"workload": "room0 mapping iteration, 996 rays x 48, stage color, dense voxel grads (middle+fine+color) + colour-decoder grads",
+                               "ms_per_step": ms, "rays_per_s": n / (ms * 1e-3), "algorithmic_bytes_per_ray": bpr,
+                               "hbm_frac": n * bpr / (ms * 1e-3) / 1e9 / peak}
+    sweep = []
+    for nn, steps in ((1024, 100), (8192, 30), (65536, 8)):
+        ro, rd, dirs, gd, gc = [t.to(dev) for t in make_batch(sc, nn, 200 + nn)]
+        cx = IterationContext(renderer, nn, "color", dev, kind="track")
+        ms = time_steps(lambda: cx.run(c, dec, ro, rd, gd, gc), steps)
+        sweep.append({"rays": nn, "samples": 48, "ms_per_step": ms, "rays_per_s": nn / (ms * 1e-3),
+                      "hbm_frac": nn * BYTES_PER_RAY / (ms * 1e-3) / 1e9 / peak})
+        del cx
+    out["sweep_tracking_iteration"] = sweep
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ native arm (GPU)
 def run_native(args):
     import torch.distributed as dist
@@ -293,6 +331,7 @@ def run_native(args):
                             "algorithmic_bytes_per_launch": BYTES_PER_RAY * RAYS_PER_GPU,
                             "note": "200-ray tracking batch is latency/FP32-FMA bound, not HBM bound (see DESIGN.md)"}
     if world == 1:
+        line["extra"].update(extra_workloads(sc, renderer, c, dec, dev, flush, peak))
         best = None
         for threads in sorted({1, os.cpu_count() or 1}):      # CPU grid_sample is single-threaded for batch 1; oversubscribed MKL is slower
             torch.set_num_threads(threads)

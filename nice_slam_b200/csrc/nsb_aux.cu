@@ -134,19 +134,34 @@ __global__ void tracking_seeds_kernel(const double* __restrict__ depth, const do
                                       double* __restrict__ g_depth, float* __restrict__ g_rgb,
                                       double* __restrict__ loss, double* __restrict__ res) {
   __shared__ double red[32];
+  __shared__ int ired[32];
   __shared__ double med_s;
   for (int i = threadIdx.x; i < n; i += blockDim.x)
     res[i] = fabs((double)gt[i] - depth[i]) / sqrt(var[i] + 1e-10);
   __syncthreads();
-  if (handle_dynamic) {            // torch.median = lower median = element of rank (n-1)/2 in the stable sorted order
+  if (handle_dynamic) {
+    // torch.median = lower median = the element of rank (n-1)/2.  Radix select on the IEEE bit pattern (residuals are
+    // non-negative, so the unsigned 64-bit pattern is order preserving; NaN sorts last like torch.sort): 64 counting passes.
     const double* mp = pool != nullptr ? pool : res;       // sharded batches: median over the all-gathered residuals
     const int np = pool != nullptr ? n_pool : n;
-    const int kth = (np - 1) / 2;
-    for (int i = threadIdx.x; i < np; i += blockDim.x) {
-      const double ri = mp[i]; int rank = 0;
-      for (int j = 0; j < np; j++) { const double rj = mp[j]; rank += (z_less(rj, ri) || (!z_less(ri, rj) && j < i)) ? 1 : 0; }
-      if (rank == kth) med_s = ri;
+    int k = (np - 1) / 2;
+    unsigned long long prefix = 0ull;
+    for (int b = 63; b >= 0; --b) {
+      const unsigned long long maskhi = b == 63 ? 0ull : (~0ull << (b + 1));
+      int c = 0;
+      for (int i = threadIdx.x; i < np; i += blockDim.x) {
+        const unsigned long long key = (unsigned long long)__double_as_longlong(mp[i]);
+        c += ((key & maskhi) == prefix && !((key >> b) & 1ull)) ? 1 : 0;
+      }
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      if ((threadIdx.x & 31) == 0) ired[threadIdx.x >> 5] = c;
+      __syncthreads();
+      int tot = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot += ired[w];
+      __syncthreads();
+      if (k >= tot) { k -= tot; prefix |= 1ull << b; }
     }
+    if (threadIdx.x == 0) med_s = __longlong_as_double((long long)prefix);
     __syncthreads();
   }
   double acc = 0.0;
