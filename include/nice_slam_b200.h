@@ -76,6 +76,8 @@ size_t nsb_packed_decoder_floats(int level);
 
 int nsb_version(void);
 const char* nsb_last_error(void);
+/* Process-wide options.  "mlp_backend": 0 = auto (default), 1 = FP32-FMA decoders, 2 = tcgen05 (3xTF32) decoders. */
+int nsb_set_option(const char* key, int value);
 
 /* Pack decoders' parameters into the kernels' shared-memory image (one launch for all four).
  * params[l] == NULL skips level l.  packed[l] must hold nsb_packed_decoder_floats(l) floats.

@@ -57,6 +57,7 @@ _P = C.c_void_p
 SYMBOLS = {
     "nsb_version": (C.c_int, []),
     "nsb_last_error": (C.c_char_p, []),
+    "nsb_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "nsb_flat_decoder_floats": (C.c_size_t, [C.c_int]),
     "nsb_flat_offset": (C.c_longlong, [C.c_int, C.c_int, C.c_int]),
     "nsb_packed_decoder_floats": (C.c_size_t, [C.c_int]),
@@ -92,6 +93,9 @@ def lib():
         for name, (res, args) in SYMBOLS.items():
             f = getattr(h, name)          # AttributeError if the library does not export a declared symbol
             f.restype, f.argtypes = res, args
+        backend = os.environ.get("NSB_MLP_BACKEND")          # 1 = FP32-FMA decoders, 2 = tcgen05 decoders (default: auto)
+        if backend is not None and h.nsb_set_option(b"mlp_backend", int(backend)) != 0:
+            raise RuntimeError("bad NSB_MLP_BACKEND=%r" % backend)
         _LIB = h
     return _LIB
 

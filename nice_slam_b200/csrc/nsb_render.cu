@@ -11,6 +11,7 @@
 // is staged into shared memory with one TMA bulk copy that overlaps with the first chunk's feature gather.
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 #include "nsb_common.cuh"
 #include "nsb_geom.cuh"
 #include "nsb_mlp.cuh"
@@ -264,38 +265,34 @@ __device__ __forceinline__ void ray_weights(const float* __restrict__ rw, int S,
 // ------------------------------------------------------------------------------------------------
 // forward kernel
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1) render_fwd_kernel(const __grid_constant__ KParams P) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5;
-  const LaneId L = make_lane(threadIdx.x & 31);
-  Smem sm;
-  smem_layout(P.wbytes, P.max_pts, P.max_rays, warps, kRowsFwd, false, &sm, smem_raw);
-  float* act = sm.act + (size_t)warp * kRowsFwd * kRowF;
-  const bool points_mode = P.points != nullptr;
-
-  int r0 = 0, nr = 0, Pb;
-  if (points_mode) {
+// shared by the SIMT and the tensor-core forward kernels
+struct BlockRange { int r0, nr, Pb; };
+__device__ __forceinline__ BlockRange block_range(const KParams& P) {
+  BlockRange b; b.r0 = 0; b.nr = 0;
+  if (P.points != nullptr) {
     const long long p0 = (long long)blockIdx.x * P.rays_per_block;
-    Pb = (int)((P.n_points - p0) < P.rays_per_block ? (P.n_points - p0) : P.rays_per_block);
+    b.Pb = (int)((P.n_points - p0) < P.rays_per_block ? (P.n_points - p0) : P.rays_per_block);
   } else {
-    r0 = blockIdx.x * P.rays_per_block;
-    nr = P.in.n_rays - r0 < P.rays_per_block ? P.in.n_rays - r0 : P.rays_per_block;
-    Pb = nr * P.S;
+    b.r0 = blockIdx.x * P.rays_per_block;
+    b.nr = P.in.n_rays - b.r0 < P.rays_per_block ? P.in.n_rays - b.r0 : P.rays_per_block;
+    b.Pb = b.nr * P.S;
   }
-  if (threadIdx.x == 0) { mbar_init(sm.bar, 1); mbar_fence_init(); }
-
-  if (!points_mode) {
+  return b;
+}
+// stratified + near-surface sampling and the stable merge (Renderer.py:82-170); leaves sorted z in sm.zs and zeroes sm.raw
+__device__ __forceinline__ void fwd_sample_sort(const KParams& P, const Smem& sm, const BlockRange& b) {
+  if (P.points == nullptr) {
     const float gtmax = P.has_gt ? P.in.depth_max[0] : 0.0f, gtmax12 = P.has_gt ? P.in.depth_max[1] : 0.0f;
-    block_setup_rays(P, sm, r0, nr, gtmax12);
+    block_setup_rays(P, sm, b.r0, b.nr, gtmax12);
     __syncthreads();
     double* zu = reinterpret_cast<double*>(sm.raw);              // unsorted samples (raw is not live yet)
-    for (int lp = threadIdx.x; lp < Pb; lp += blockDim.x) {
+    for (int lp = threadIdx.x; lp < b.Pb; lp += blockDim.x) {
       const int ray = lp / P.S, i = lp - ray * P.S;
       RaySampler rs; rs.near = sm.rays[8 * ray + 6]; rs.gt = sm.rays[8 * ray + 7]; rs.far = sm.far[ray]; rs.has_gt = P.has_gt;
       zu[lp] = sample_z(rs, i, P.in.n_samples, P.in.t_uniform, P.in.t_surface, gtmax);
     }
     __syncthreads();
-    for (int lp = threadIdx.x; lp < Pb; lp += blockDim.x) {      // stable rank sort == torch.sort (Renderer.py:168-170)
+    for (int lp = threadIdx.x; lp < b.Pb; lp += blockDim.x) {    // stable rank sort == torch.sort (Renderer.py:168-170)
       const int ray = lp / P.S, i = lp - ray * P.S;
       const double zi = zu[lp];
       const double* zr = zu + ray * P.S;
@@ -305,22 +302,12 @@ __global__ void __launch_bounds__(256, 1) render_fwd_kernel(const __grid_constan
     }
   }
   __syncthreads();
-  for (int lp = threadIdx.x; lp < Pb; lp += blockDim.x) { sm.raw[4 * lp] = 0.f; sm.raw[4 * lp + 1] = 0.f; sm.raw[4 * lp + 2] = 0.f; sm.raw[4 * lp + 3] = 0.f; }
-
-  const int nchunks = (Pb + kChunk - 1) / kChunk;
-  uint32_t parity = 0;
-  for (int qd = 0; qd < P.n_dec; qd++) {
-    const int lv = P.dec[qd];
-    __syncthreads();                                             // previous weight image no longer in use
-    if (threadIdx.x == 0) issue_weights(P, sm, lv);
-    const DecRT d = make_dec(lv);
-#pragma unroll 1
-    for (int chunk = warp; chunk < nchunks; chunk += warps) chunk_forward(P, sm, act, chunk, Pb, L, parity, qd == 0, lv, d);
-    parity ^= 1u;
-  }
-  __syncthreads();
-
-  if (points_mode) {                                             // Renderer.eval_points: raw with the OOB override
+  for (int lp = threadIdx.x; lp < b.Pb; lp += blockDim.x) { sm.raw[4 * lp] = 0.f; sm.raw[4 * lp + 1] = 0.f; sm.raw[4 * lp + 2] = 0.f; sm.raw[4 * lp + 3] = 0.f; }
+}
+// out-of-bound override, compositing and the stores of the forward pass (call after a __syncthreads())
+__device__ __forceinline__ void fwd_composite_store(const KParams& P, const Smem& sm, const BlockRange& b, int warp, int warps, int lane) {
+  const int r0 = b.r0, nr = b.nr, Pb = b.Pb;
+  if (P.points != nullptr) {                                     // Renderer.eval_points: raw with the OOB override
     for (int lp = threadIdx.x; lp < Pb; lp += blockDim.x) {
       const long long gp = (long long)blockIdx.x * P.rays_per_block + lp;
       float4 v = *reinterpret_cast<float4*>(sm.raw + 4 * lp);
@@ -336,19 +323,19 @@ __global__ void __launch_bounds__(256, 1) render_fwd_kernel(const __grid_constan
     const float* rw = sm.raw + 4 * r * P.S;
     const double* z = sm.zs + r * P.S;
     float* wq = sm.wgt + r * P.S;
-    ray_weights(rw, P.S, L.lane, wq, nullptr);
+    ray_weights(rw, P.S, lane, wq, nullptr);
     __syncwarp();
     float c0 = 0.f, c1 = 0.f, c2 = 0.f; double dsum = 0.0;
-    for (int s = L.lane; s < P.S; s += 32) {
+    for (int s = lane; s < P.S; s += 32) {
       const float w = wq[s];
       c0 = fmaf(w, rw[4 * s], c0); c1 = fmaf(w, rw[4 * s + 1], c1); c2 = fmaf(w, rw[4 * s + 2], c2);
       dsum += (double)w * z[s];
     }
     c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2); dsum = warp_sum(dsum);
     double v = 0.0;
-    for (int s = L.lane; s < P.S; s += 32) { const double t = z[s] - dsum; v += (double)wq[s] * t * t; }
+    for (int s = lane; s < P.S; s += 32) { const double t = z[s] - dsum; v += (double)wq[s] * t * t; }
     v = warp_sum(v);
-    if (L.lane == 0) {
+    if (lane == 0) {
       P.fo.depth[r0 + r] = dsum; P.fo.var[r0 + r] = v;
       P.fo.rgb[3 * (r0 + r)] = c0; P.fo.rgb[3 * (r0 + r) + 1] = c1; P.fo.rgb[3 * (r0 + r) + 2] = c2;
     }
@@ -358,6 +345,102 @@ __global__ void __launch_bounds__(256, 1) render_fwd_kernel(const __grid_constan
   if (P.fo.raw != nullptr)
     for (int lp = threadIdx.x; lp < Pb; lp += blockDim.x)
       *reinterpret_cast<float4*>(P.fo.raw + 4 * (g0 + lp)) = *reinterpret_cast<float4*>(sm.raw + 4 * lp);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward kernel, FP32-FMA (SIMT) decoders
+__global__ void __launch_bounds__(256, 1) render_fwd_kernel(const __grid_constant__ KParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5;
+  const LaneId L = make_lane(threadIdx.x & 31);
+  Smem sm;
+  smem_layout(P.wbytes, P.max_pts, P.max_rays, warps, kRowsFwd, false, &sm, smem_raw);
+  float* act = sm.act + (size_t)warp * kRowsFwd * kRowF;
+  const BlockRange b = block_range(P);
+  const int Pb = b.Pb;
+  if (threadIdx.x == 0) { mbar_init(sm.bar, 1); mbar_fence_init(); }
+  fwd_sample_sort(P, sm, b);
+
+  const int nchunks = (Pb + kChunk - 1) / kChunk;
+  uint32_t parity = 0;
+  for (int qd = 0; qd < P.n_dec; qd++) {
+    const int lv = P.dec[qd];
+    __syncthreads();                                             // previous weight image no longer in use
+    if (threadIdx.x == 0) issue_weights(P, sm, lv);
+    const DecRT d = make_dec(lv);
+#pragma unroll 1
+    for (int chunk = warp; chunk < nchunks; chunk += warps) chunk_forward(P, sm, act, chunk, Pb, L, parity, qd == 0, lv, d);
+    parity ^= 1u;
+  }
+  __syncthreads();
+  fwd_composite_store(P, sm, b, warp, warps, L.lane);
+}
+
+}  // namespace nsb
+#include "nsb_tc.cuh"
+namespace nsb {
+
+// ------------------------------------------------------------------------------------------------
+// forward kernel, tensor-core (tcgen05, 3xTF32) decoders: 128 threads, one thread per point of a 128-point tile
+__global__ void __launch_bounds__(128, 2) render_fwd_tc_kernel(const __grid_constant__ KParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];       // tiles need 16-byte alignment only (no-swizzle descriptors)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  tc::TcSmem t;
+  tc::tc_carve(smem_raw, t);
+  Smem sm;
+  smem_layout(0, P.max_pts, P.max_rays, 0, 0, false, &sm, smem_raw + ((tc::tc_smem_bytes() + 127) & ~size_t(127)));
+  const BlockRange b = block_range(P);
+  const int Pb = b.Pb;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(t.tmem)), "r"(tc::kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 0) { mbar_init(t.bar, 1); mbar_fence_init(); }
+  fwd_sample_sort(P, sm, b);                                     // contains __syncthreads(): TMEM address + barrier are visible after it
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *t.tmem;
+
+  uint32_t parity = 0;
+  const int ntiles = (Pb + tc::TM - 1) / tc::TM;
+  for (int tile = 0; tile < ntiles; tile++) {
+    const int lp = tile * tc::TM + threadIdx.x;
+    const int lpc = lp < Pb ? lp : Pb - 1;
+    PointGeom G;
+    if (P.points != nullptr) {
+      const long long gp = (long long)blockIdx.x * P.rays_per_block + lpc;
+      const double pin[3] = {P.points[3 * gp], P.points[3 * gp + 1], P.points[3 * gp + 2]};
+      make_point_from_p(P.in.bound, P.in.coarse_bound, pin, G);
+    } else {
+      const int ray = lpc / P.S;
+      const float* rr = sm.rays + 8 * ray;
+      const float o[3] = {rr[0], rr[1], rr[2]}, dd[3] = {rr[3], rr[4], rr[5]};
+      make_point(P.in.bound, P.in.coarse_bound, o, dd, sm.zs[lpc], G);
+    }
+    float occ = 0.0f, c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
+    for (int qd = 0; qd < P.n_dec; qd++) {
+      const int lv = P.dec[qd];
+      const DecRT d = make_dec(lv);
+      float out[4];
+      tc::tile_forward(P, t, d, lv, G, tmem, parity, out);
+      if (lv == 3) { c0 = out[0]; c1 = out[1]; c2 = out[2]; } else occ += out[0];
+      if (qd == 0 && lp < Pb && P.fo.corner_idx != nullptr) {
+        const nsb_grid& g = P.in.grid[lv];
+        const Tri tr = make_tri(lv == 0 ? G.xnc : G.xn, g.W, g.H, g.D);
+        const long long gp = ((long long)blockIdx.x * P.rays_per_block) * P.S + lp;
+        P.fo.corner_idx[3 * gp] = tr.i0[0]; P.fo.corner_idx[3 * gp + 1] = tr.i0[1]; P.fo.corner_idx[3 * gp + 2] = tr.i0[2];
+      }
+    }
+    if (lp < Pb) {
+      *reinterpret_cast<float4*>(sm.raw + 4 * lp) = make_float4(c0, c1, c2, occ);
+      sm.inb[lp] = (unsigned char)G.inb;
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tc::kTmemCols) : "memory");
+  fwd_composite_store(P, sm, b, warp, 4, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -572,9 +655,15 @@ static void choose_config(int n_items, int S, int rows, bool bwd, int wbytes, in
   *smem = smem_layout(wbytes, max_pts, r, w, rows, bwd, nullptr, nullptr);
 }
 
+static int g_mlp_backend = 0;      // 0 = auto (tensor-core forward), 1 = SIMT, 2 = tcgen05
+static size_t tc_total_smem(int max_pts, int max_rays) {
+  return ((tc::tc_smem_bytes() + 127) & ~size_t(127)) + smem_layout(0, max_pts, max_rays, 0, 0, false, nullptr, nullptr);
+}
+
 static bool g_attr_set = false;
 static int set_attrs() {
   if (g_attr_set) return NSB_OK;
+  if (check_cuda(cudaFuncSetAttribute(render_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap), "fwd tc smem attr")) return NSB_ERR_CUDA;
   if (check_cuda(cudaFuncSetAttribute(render_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap), "fwd smem attr")) return NSB_ERR_CUDA;
   if (check_cuda(cudaFuncSetAttribute(render_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap), "bwd smem attr")) return NSB_ERR_CUDA;
   g_attr_set = true;
@@ -584,6 +673,11 @@ static int set_attrs() {
 }  // namespace nsb
 
 using namespace nsb;
+
+extern "C" int nsb_set_option(const char* key, int value) {
+  if (key && !strcmp(key, "mlp_backend")) { if (value < 0 || value > 2) { set_error("mlp_backend must be 0 (auto), 1 (simt) or 2 (tcgen05)"); return NSB_ERR_ARG; } g_mlp_backend = value; return NSB_OK; }
+  set_error("unknown option %s", key ? key : "(null)"); return NSB_ERR_ARG;
+}
 
 extern "C" int nsb_render_forward(const nsb_render_inputs* in, const nsb_forward_outputs* out, void* stream) {
   int rc = validate_inputs(in, true); if (rc) return rc;
@@ -597,6 +691,11 @@ extern "C" int nsb_render_forward(const nsb_render_inputs* in, const nsb_forward
   choose_config(in->n_rays, K.S, kRowsFwd, false, K.wbytes, 8, &K, &warps, &smem);
   if (smem > kSmemCap) { set_error("shared-memory budget exceeded (%zu bytes)", smem); return NSB_ERR_UNSUPPORTED; }
   const int grid = (in->n_rays + K.rays_per_block - 1) / K.rays_per_block;
+  if (g_mlp_backend != 1) {          // tensor-core decoders (same CTA <-> ray mapping, 128 threads)
+    const size_t smem_tc = tc_total_smem(K.max_pts, K.max_rays);
+    render_fwd_tc_kernel<<<grid, 128, smem_tc, (cudaStream_t)stream>>>(K);
+    return check_cuda(cudaGetLastError(), "render_fwd_tc_kernel launch");
+  }
   render_fwd_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(K);
   return check_cuda(cudaGetLastError(), "render_fwd_kernel launch");
 }
@@ -618,6 +717,10 @@ extern "C" int nsb_eval_points(const nsb_render_inputs* in, const double* points
   const size_t smem = smem_layout(K.wbytes, ppb, 1, warps, kRowsFwd, false, nullptr, nullptr);
   K.rays_per_block = ppb; K.max_pts = ppb; K.max_rays = 1;
   const int grid = (n_points + ppb - 1) / ppb;
+  if (g_mlp_backend != 1) {
+    render_fwd_tc_kernel<<<grid, 128, tc_total_smem(K.max_pts, K.max_rays), (cudaStream_t)stream>>>(K);
+    return check_cuda(cudaGetLastError(), "render_fwd_tc_kernel(points) launch");
+  }
   render_fwd_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(K);
   return check_cuda(cudaGetLastError(), "render_fwd_kernel(points) launch");
 }

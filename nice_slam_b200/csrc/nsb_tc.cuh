@@ -1,0 +1,275 @@
+// nsb_tc.cuh -- tensor-core evaluation of the NICE decoders: tcgen05.mma (kind::tf32) with a 3xTF32 operand split,
+// accumulators in TMEM.  Included by nsb_render.cu (it uses that file's KParams / Smem / gather helpers).
+//
+// Why 3xTF32: plain TF32 operands miss the 1e-4 parity bar by an order of magnitude (probe: 3e-4 relative on a single
+// 32-wide GEMM); splitting every operand into hi = tf32(x), lo = tf32(x - hi) and issuing lo*hi + hi*lo + hi*hi gives
+// fp32-level results (probe_tcgen05.cu: 6e-6 abs on |ref| <= 20, same as an FP32 FMA chain).
+//
+// Tile = 128 sample points (one TMEM lane / one thread per point).  Operands live in shared memory in the canonical
+// K-major no-swizzle UMMA layout  [row/8][k/4][row%8][k%4]  (core matrix = 8 rows x 16 B): the epilogue thread of row r
+// writes 16-byte chunks that land conflict-free, and the same tile can later be read as an MN-major operand.
+// Per decoder and tile:
+//   gather -> C tile (hi/lo) -> D2[128 x 160] = C * Wc_i^T for the five layers (TMEM columns 32..191); C is dead after that,
+//   its shared memory is reused for the embedding blocks E (32 features at a time, recomputed) and the hidden state H;
+//   layer i: D1[128 x 32] = x_i * W_i^T ; epilogue (one thread per point): h = relu(D1 + b) + D2_i + bc -> H tile (hi/lo).
+// Weights are converted fp32 -> (hi, lo) canonical tiles on the fly from the packed image (L2 resident), one layer at a time.
+#pragma once
+
+namespace nsb {
+namespace tc {
+
+constexpr int TM = 128;                 // points per tile
+constexpr uint32_t kTmemCols = 256;     // D1: [0,32)  D2: [32,192)
+
+__device__ __forceinline__ float to_tf32(float x) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return __uint_as_float(u); }
+
+// element (row r, k) of a canonical tile of width K floats
+__device__ __forceinline__ int canon_q(int r, int kq, int K) { return ((r >> 3) * (K >> 2) + kq) * 32 + (r & 7) * 4; }
+
+__device__ __forceinline__ void put4(float* __restrict__ hi, float* __restrict__ lo, int r, int kq, int K, float4 v) {
+  const int idx = canon_q(r, kq, K);
+  float4 h, l;
+  h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+  l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+  *reinterpret_cast<float4*>(hi + idx) = h;
+  *reinterpret_cast<float4*>(lo + idx) = l;
+}
+
+__device__ __forceinline__ uint64_t make_desc(const float* smem, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_u32(smem) >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell); layout_type 0 = no swizzle
+  return d;
+}
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {      // D=F32, A=B=TF32, both K-major
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D[128 x N] (+)= A[128 x kcount*8] * B[N x kcount*8]^T with the 3xTF32 split.  A/B tiles have widths KA/KB floats and
+// the product starts at column ka0 / kb0 (multiples of 8).  `acc` is the running accumulate flag of this D.
+__device__ __forceinline__ void mma_3x(uint32_t d_tmem, const float* a_hi, const float* a_lo, int KA, int ka0,
+                                       const float* b_hi, const float* b_lo, int KB, int kb0, int kcount, int N, uint32_t& acc) {
+  const uint32_t idesc = make_idesc(TM, N);
+  const uint32_t sboA = (uint32_t)(KA >> 2) * 128u, sboB = (uint32_t)(KB >> 2) * 128u;
+  for (int ks = 0; ks < kcount; ks++) {
+    const int oa = ((ka0 >> 2) + 2 * ks) * 32, ob = ((kb0 >> 2) + 2 * ks) * 32;
+    const uint64_t ah = make_desc(a_hi + oa, 128u, sboA), al = make_desc(a_lo + oa, 128u, sboA);
+    const uint64_t bh = make_desc(b_hi + ob, 128u, sboB), bl = make_desc(b_lo + ob, 128u, sboB);
+    mma_tf32(d_tmem, al, bh, idesc, acc); acc = 1u;
+    mma_tf32(d_tmem, ah, bl, idesc, 1u);
+    mma_tf32(d_tmem, ah, bh, idesc, 1u);
+  }
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// operands written by this thread (generic proxy) -> visible to the tensor core (async proxy), then CTA barrier
+__device__ __forceinline__ void publish_operands() { fence_proxy_async(); tc_fence_before(); __syncthreads(); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+                 "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+                 "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+}
+
+// shared-memory regions of the tensor-core path (all 1024-byte aligned so that every tile start is 16-byte aligned)
+struct TcSmem {
+  float* x;        // 64 KB: C hi|lo (128 x 64 each)  -- later  E hi|lo (128 x 32) + H hi|lo (128 x 32), or two E blocks
+  float* wa;       // weight stage A: hi|lo, 32 x 96 each (24 KB)
+  float* wb;       // weight stage B: hi|lo, 32 x 32 each (8 KB)
+  float* bias;     // 328 floats: b[5][32] | bc[5][32] | bo[4] | Wo[4][32] is read from global
+  uint64_t* bar;   // MMA completion barrier
+  uint32_t* tmem;  // TMEM base address slot
+};
+constexpr int kXFloats = 2 * TM * 64;            // 16384 floats = 64 KB
+constexpr int kWaFloats = 2 * 32 * 96;           // 24 KB
+constexpr int kWbFloats = 2 * 32 * 32;           // 8 KB
+__host__ __device__ inline size_t tc_smem_bytes() { return (size_t)(kXFloats + kWaFloats + kWbFloats + 336) * 4 + 64; }
+__device__ __forceinline__ void tc_carve(unsigned char* base, TcSmem& t) {
+  float* f = reinterpret_cast<float*>(base);
+  t.x = f; f += kXFloats;
+  t.wa = f; f += kWaFloats;
+  t.wb = f; f += kWbFloats;
+  t.bias = f; f += 336;
+  t.bar = reinterpret_cast<uint64_t*>(f);
+  t.tmem = reinterpret_cast<uint32_t*>(f + 4);
+}
+
+// stage rows [0,32) x columns [c0, c0+K) of a packed fp32 matrix (row pitch `pitch`) as a canonical hi|lo tile pair of width K
+__device__ __forceinline__ void stage_w(float* __restrict__ dst, const float* __restrict__ src, int pitch, int c0, int K) {
+  float* hi = dst; float* lo = dst + 32 * K;
+  const int kq4 = K >> 2;
+  for (int i = threadIdx.x; i < 32 * kq4; i += blockDim.x) {
+    const int n = i / kq4, kq = i - n * kq4;
+    const float4 v = ldg_f4(src + n * pitch + c0 + 4 * kq);
+    put4(hi, lo, n, kq, K, v);
+  }
+}
+
+// 8 lanes per point, 4 points per pass: gather the 32 channels of `g` for the warp's 32 rows into columns [col0, col0+32) of the C tile
+__device__ __forceinline__ void gather_rows(const nsb_grid& g, float* __restrict__ c_hi, float* __restrict__ c_lo, int KC, int col0,
+                                            const float xn[3], int warp, int lane) {
+  const bool fast = grid_fast(g);
+  const int q = lane & 7;
+#pragma unroll 2
+  for (int it = 0; it < 8; it++) {
+    const int src_lane = it * 4 + (lane >> 3);
+    float x[3];
+    x[0] = __shfl_sync(0xffffffffu, xn[0], src_lane); x[1] = __shfl_sync(0xffffffffu, xn[1], src_lane); x[2] = __shfl_sync(0xffffffffu, xn[2], src_lane);
+    const Tri t = make_tri(x, g.W, g.H, g.D);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      int cx, cy, cz;
+      if (tri_corner(t, k, g.W, g.H, g.D, cx, cy, cz)) {
+        const long long off = cz * g.stride_d + cy * g.stride_h + cx * g.stride_w;
+        const float4 v = grid_load4(g, off, 4 * q, fast);
+        const float w = tri_weight(t, k);
+        acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y); acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
+      }
+    }
+    put4(c_hi, c_lo, warp * 32 + src_lane, (col0 >> 2) + q, KC, acc);
+  }
+}
+
+// E block `blk` (features 32*blk .. +31, zero beyond 93) of this thread's point -> canonical hi|lo tile of width 32
+__device__ __forceinline__ void embed_row(float* __restrict__ e_hi, float* __restrict__ e_lo, const float* __restrict__ B /*global packed [3][96]*/,
+                                          const float pf[3], int row, int blk) {
+#pragma unroll 2
+  for (int kq = 0; kq < 8; kq++) {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int f = 32 * blk + 4 * kq + j;
+      float x = pf[0] * __ldg(B + f); x = fmaf(pf[1], __ldg(B + kEmbPad + f), x); x = fmaf(pf[2], __ldg(B + 2 * kEmbPad + f), x);
+      v[j] = f < kEmb ? __sinf(reduce_2pi(x)) : 0.0f;
+    }
+    put4(e_hi, e_lo, row, kq, 32, make_float4(v[0], v[1], v[2], v[3]));
+  }
+}
+
+// Forward of decoder `lv` for one 128-point tile.  Every thread = one point (row == threadIdx.x).  On return out[o] holds the
+// decoder outputs of this thread's point.  `parity` is the running phase of t.bar.
+__device__ __forceinline__ void tile_forward(const KParams& P, const TcSmem& t, const DecRT& d, int lv, const PointGeom& G,
+                                             uint32_t tmem, uint32_t& parity, float (&out)[4]) {
+  const int row = threadIdx.x, warp = row >> 5, lane = row & 31;
+  const float* Wg = P.in.packed[lv];                       // packed fp32 image in global memory (L2 resident)
+  float* c_hi = t.x; float* c_lo = t.x + TM * d.cd;
+  const uint32_t d1 = tmem, d2 = tmem + 32u;
+  const uint32_t my_lane = (uint32_t)(warp * 32) << 16;
+
+  __syncthreads();                       // previous decoder / tile: all reads of the bias block and of the tiles are done
+  // biases -> shared (b[5][32] | bc[5][32] | bo[4])
+  for (int i = threadIdx.x; i < 324; i += blockDim.x) {
+    float v = 0.0f;
+    if (i < 160) v = __ldg(Wg + d.o_b + i);
+    else if (i < 320) v = d.xyz ? __ldg(Wg + d.o_bc + (i - 160)) : 0.0f;
+    else v = __ldg(Wg + d.o_bo + (i - 320));
+    t.bias[i] = v;
+  }
+  // ---- gather -> C tile
+  const float* xn = lv == 0 ? G.xnc : G.xn;
+  gather_rows(P.in.grid[lv], c_hi, c_lo, d.cd, 0, xn, warp, lane);
+  if (lv == 2) gather_rows(P.in.grid[1], c_hi, c_lo, d.cd, 32, G.xn, warp, lane);
+
+  // ---- D2[:, 32i..32i+32) = C * Wc_i^T  (xyz decoders only)
+  if (d.xyz) {
+    for (int i = 0; i < 5; i++) {
+      stage_w(t.wa, Wg + d.o_WC + i * 32 * d.pc, d.pc, 0, d.cd);
+      publish_operands();
+      if (threadIdx.x == 0) {
+        tc_fence_after();
+        uint32_t acc = 0;
+        mma_3x(d2 + 32u * i, c_hi, c_lo, d.cd, 0, t.wa, t.wa + 32 * d.cd, d.cd, 0, d.cd >> 3, 32, acc);
+        mma_commit(t.bar);
+      }
+      __syncwarp();
+      mbar_wait(t.bar, parity); parity ^= 1u;              // the stage buffer is reused by the next layer
+      tc_fence_after();
+    }
+  }
+  // (for the coarse decoder the first input is C itself: keep the C tile alive, the E/H tiles use the upper half of x)
+  float* e_hi = d.xyz ? t.x : c_hi;
+  float* e_lo = d.xyz ? t.x + TM * 32 : c_lo;
+  float* h_hi = t.x + 2 * TM * 32;
+  float* h_lo = t.x + 3 * TM * 32;
+  float h[32];
+#pragma unroll 1
+  for (int i = 0; i < 5; i++) {
+    uint32_t acc = 0;
+    if (i == 0 || i == 3) {
+      const int ow = i == 0 ? d.o_W0 : d.o_W3E;
+      stage_w(t.wa, Wg + ow, d.pf, 0, d.firstp);           // whole first-input weight block (K = 96 or 32)
+      if (i == 3) stage_w(t.wb, Wg + d.o_Wh[3], Dec<1>::PH, 0, 32);
+      const int nblk = d.xyz ? 3 : 1;
+      for (int blk = 0; blk < nblk; blk++) {
+        if (d.xyz) embed_row(e_hi, e_lo, Wg + d.o_B, G.pf, row, blk);
+        publish_operands();
+        if (threadIdx.x == 0) {
+          tc_fence_after();
+          mma_3x(d1, e_hi, e_lo, 32, 0, t.wa, t.wa + 32 * d.firstp, d.firstp, 32 * blk, 4, 32, acc);
+          if (i == 3 && blk == nblk - 1) mma_3x(d1, h_hi, h_lo, 32, 0, t.wb, t.wb + 32 * 32, 32, 0, 4, 32, acc);
+          mma_commit(t.bar);
+        }
+        __syncwarp();
+        mbar_wait(t.bar, parity); parity ^= 1u;            // E buffer / stage buffers free again
+        tc_fence_after();
+      }
+    } else {
+      stage_w(t.wb, Wg + dec_wh(d, i), Dec<1>::PH, 0, 32);
+      publish_operands();
+      if (threadIdx.x == 0) {
+        tc_fence_after();
+        mma_3x(d1, h_hi, h_lo, 32, 0, t.wb, t.wb + 32 * 32, 32, 0, 4, 32, acc);
+        mma_commit(t.bar);
+      }
+      __syncwarp();
+      mbar_wait(t.bar, parity); parity ^= 1u;
+      tc_fence_after();
+    }
+    // ---- epilogue of layer i: h = relu(D1 + b_i) + (D2_i + bc_i)
+    float v1[32];
+    tmem_ld32(d1 + my_lane, v1);
+#pragma unroll
+    for (int j = 0; j < 32; j++) { const float u = v1[j] + t.bias[i * 32 + j]; h[j] = u > 0.0f ? u : 0.0f; }
+    if (d.xyz) {
+      float v2[32];
+      tmem_ld32(d2 + 32u * i + my_lane, v2);
+#pragma unroll
+      for (int j = 0; j < 32; j++) h[j] += v2[j] + t.bias[160 + i * 32 + j];
+    }
+    if (i < 4) {
+#pragma unroll
+      for (int kq = 0; kq < 8; kq++) put4(h_hi, h_lo, row, kq, 32, make_float4(h[4 * kq], h[4 * kq + 1], h[4 * kq + 2], h[4 * kq + 3]));
+    }
+    tc_fence_before();      // TMEM reads of this layer are ordered before the next layer's MMAs (issued after the next barrier)
+  }
+  // ---- output layer in registers
+#pragma unroll
+  for (int o = 0; o < 4; o++) {
+    float s = t.bias[320 + o];
+    if (o < d.no) {
+#pragma unroll
+      for (int j = 0; j < 32; j++) s = fmaf(h[j], __ldg(Wg + d.o_WO + o * Dec<1>::PH + j), s);
+    }
+    out[o] = s;
+  }
+}
+
+}  // namespace tc
+}  // namespace nsb
