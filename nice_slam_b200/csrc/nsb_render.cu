@@ -382,7 +382,7 @@ namespace nsb {
 
 // ------------------------------------------------------------------------------------------------
 // forward kernel, tensor-core (tcgen05, 3xTF32) decoders: 128 threads, one thread per point of a 128-point tile
-__global__ void __launch_bounds__(128, 2) render_fwd_tc_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(128, 1) render_fwd_tc_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];       // tiles need 16-byte alignment only (no-swizzle descriptors)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   tc::TcSmem t;
@@ -395,14 +395,14 @@ __global__ void __launch_bounds__(128, 2) render_fwd_tc_kernel(const __grid_cons
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(t.tmem)), "r"(tc::kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (threadIdx.x == 0) { mbar_init(t.bar, 1); mbar_fence_init(); }
+  if (threadIdx.x == 0) { mbar_init(t.bar, 1); mbar_init(t.wbar, 1); mbar_fence_init(); }
   fwd_sample_sort(P, sm, b);                                     // contains __syncthreads(): TMEM address + barrier are visible after it
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = *t.tmem;
 
-  uint32_t parity = 0;
+  uint32_t parity = 0, wparity = 0;
   const int ntiles = (Pb + tc::TM - 1) / tc::TM;
   for (int tile = 0; tile < ntiles; tile++) {
     const int lp = tile * tc::TM + threadIdx.x;
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(128, 2) render_fwd_tc_kernel(const __grid_cons
       const int lv = P.dec[qd];
       const DecRT d = make_dec(lv);
       float out[4];
-      tc::tile_forward(P, t, d, lv, G, tmem, parity, out);
+      tc::tile_forward<false>(P, t, d, lv, G, tmem, parity, wparity, out);
       if (lv == 3) { c0 = out[0]; c1 = out[1]; c2 = out[2]; } else occ += out[0];
       if (qd == 0 && lp < Pb && P.fo.corner_idx != nullptr) {
         const nsb_grid& g = P.in.grid[lv];
@@ -490,20 +490,9 @@ __device__ __forceinline__ void chunk_backward(const KParams& P, const Smem& sm,
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(256, 1) render_bwd_kernel(const __grid_constant__ KParams P) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5;
-  const LaneId L = make_lane(threadIdx.x & 31);
-  Smem sm;
-  smem_layout(P.wbytes, P.max_pts, P.max_rays, warps, kRowsBwd, true, &sm, smem_raw);
-  float* act = sm.act + (size_t)warp * kRowsBwd * kRowF;
-  __shared__ float gC[kMaxRaysPerBlock * 3];
-
-  const int r0 = blockIdx.x * P.rays_per_block;
-  const int nr = P.in.n_rays - r0 < P.rays_per_block ? P.in.n_rays - r0 : P.rays_per_block;
-  const int Pb = nr * P.S;
+// shared by the SIMT and tensor-core backward kernels: load the forward state, in-bound flags, and the per-ray scans
+__device__ __forceinline__ void bwd_prologue(const KParams& P, const Smem& sm, int r0, int nr, int Pb, int warp, int warps, int lane, float* gC) {
   const long long g0 = (long long)r0 * P.S;
-  if (threadIdx.x == 0) { mbar_init(sm.bar, 1); mbar_fence_init(); }
   block_setup_rays(P, sm, r0, nr, 0.0f);                         // only o, d are used below (z comes from forward)
   for (int lp = threadIdx.x; lp < Pb; lp += blockDim.x) {
     sm.zs[lp] = P.bw.z_vals[g0 + lp];
@@ -527,21 +516,21 @@ __global__ void __launch_bounds__(256, 1) render_bwd_kernel(const __grid_constan
     const double gV = P.bw.g_var != nullptr ? P.bw.g_var[r0 + r] : 0.0;
     float g3[3] = {0.f, 0.f, 0.f};
     if (P.bw.g_rgb != nullptr) { g3[0] = P.bw.g_rgb[3 * (r0 + r)]; g3[1] = P.bw.g_rgb[3 * (r0 + r) + 1]; g3[2] = P.bw.g_rgb[3 * (r0 + r) + 2]; }
-    if (L.lane == 0) { gC[3 * r] = g3[0]; gC[3 * r + 1] = g3[1]; gC[3 * r + 2] = g3[2]; }
-    ray_weights(rw, P.S, L.lane, wq, go);                        // go[] temporarily holds T_s
+    if (lane == 0) { gC[3 * r] = g3[0]; gC[3 * r + 1] = g3[1]; gC[3 * r + 2] = g3[2]; }
+    ray_weights(rw, P.S, lane, wq, go);                        // go[] temporarily holds T_s
     __syncwarp();
     double Dm = 0.0;
-    for (int s = L.lane; s < P.S; s += 32) Dm += (double)wq[s] * z[s];
+    for (int s = lane; s < P.S; s += 32) Dm += (double)wq[s] * z[s];
     Dm = warp_sum(Dm);
     double swt = 0.0;
-    for (int s = L.lane; s < P.S; s += 32) swt += (double)wq[s] * (z[s] - Dm);
+    for (int s = lane; s < P.S; s += 32) swt += (double)wq[s] * (z[s] - Dm);
     swt = warp_sum(swt);
     const double gDe = gD + gV * (-2.0 * swt);                   // var reaches depth through tmp = z - depth
     // dL/dalpha_s = T_s g_w_s - (sum_{k>s} g_w_k w_k) / q_s   (cumprod backward in division form)
     float carry = 0.0f;
     const int nblk = (P.S + 31) / 32;
     for (int b = nblk - 1; b >= 0; b--) {
-      const int s = b * 32 + L.lane;
+      const int s = b * 32 + lane;
       const bool v = s < P.S;
       float gw = 0.0f, al = 0.0f, T = 0.0f, w = 0.0f;
       if (v) {
@@ -549,9 +538,9 @@ __global__ void __launch_bounds__(256, 1) render_bwd_kernel(const __grid_constan
         const double t = z[s] - Dm;
         gw = (float)(gDe * z[s] + gV * t * t) + g3[0] * rw[4 * s] + g3[1] * rw[4 * s + 1] + g3[2] * rw[4 * s + 2];
       }
-      const float incl = warp_incl_suffix_sum(gw * w, L.lane);
+      const float incl = warp_incl_suffix_sum(gw * w, lane);
       float excl = __shfl_down_sync(0xffffffffu, incl, 1);       // exclusive suffix sum inside the block (no cancellation)
-      if (L.lane == 31) excl = 0.0f;
+      if (lane == 31) excl = 0.0f;
       const float R = carry + excl;
       if (v) {
         const float qd = (1.0f - al) + 1e-10f;
@@ -561,6 +550,35 @@ __global__ void __launch_bounds__(256, 1) render_bwd_kernel(const __grid_constan
       carry += __shfl_sync(0xffffffffu, incl, 0);
     }
   }
+
+}
+// d rays_o = sum_s dp ; d rays_d = sum_s z_s dp   (pts = o + d*z, Renderer.py:172-174)
+__device__ __forceinline__ void bwd_ray_reduce(const KParams& P, const Smem& sm, int r0, int nr) {
+  if (P.bw.d_rays_o != nullptr || P.bw.d_rays_d != nullptr) {
+    for (int t = threadIdx.x; t < nr * 3; t += blockDim.x) {
+      const int r = t / 3, a = t - 3 * r;
+      double so = 0.0, sd = 0.0;
+      for (int s = 0; s < P.S; s++) { const double v = sm.dp[3 * (r * P.S + s) + a]; so += v; sd += v * sm.zs[r * P.S + s]; }
+      if (P.bw.d_rays_o != nullptr) P.bw.d_rays_o[3 * (r0 + r) + a] = (float)so;
+      if (P.bw.d_rays_d != nullptr) P.bw.d_rays_d[3 * (r0 + r) + a] = (float)sd;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 1) render_bwd_kernel(const __grid_constant__ KParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5;
+  const LaneId L = make_lane(threadIdx.x & 31);
+  Smem sm;
+  smem_layout(P.wbytes, P.max_pts, P.max_rays, warps, kRowsBwd, true, &sm, smem_raw);
+  float* act = sm.act + (size_t)warp * kRowsBwd * kRowF;
+  __shared__ float gC[kMaxRaysPerBlock * 3];
+
+  const int r0 = blockIdx.x * P.rays_per_block;
+  const int nr = P.in.n_rays - r0 < P.rays_per_block ? P.in.n_rays - r0 : P.rays_per_block;
+  const int Pb = nr * P.S;
+  if (threadIdx.x == 0) { mbar_init(sm.bar, 1); mbar_fence_init(); }
+  bwd_prologue(P, sm, r0, nr, Pb, warp, warps, L.lane, gC);
 
   const int nchunks = (Pb + kChunk - 1) / kChunk;
   uint32_t parity = 0;
@@ -574,16 +592,75 @@ __global__ void __launch_bounds__(256, 1) render_bwd_kernel(const __grid_constan
     parity ^= 1u;
   }
   __syncthreads();
-  // d rays_o = sum_s dp ; d rays_d = sum_s z_s dp   (pts = o + d*z, Renderer.py:172-174)
-  if (P.bw.d_rays_o != nullptr || P.bw.d_rays_d != nullptr) {
-    for (int t = threadIdx.x; t < nr * 3; t += blockDim.x) {
-      const int r = t / 3, a = t - 3 * r;
-      double so = 0.0, sd = 0.0;
-      for (int s = 0; s < P.S; s++) { const double v = sm.dp[3 * (r * P.S + s) + a]; so += v; sd += v * sm.zs[r * P.S + s]; }
-      if (P.bw.d_rays_o != nullptr) P.bw.d_rays_o[3 * (r0 + r) + a] = (float)so;
-      if (P.bw.d_rays_d != nullptr) P.bw.d_rays_d[3 * (r0 + r) + a] = (float)sd;
+  bwd_ray_reduce(P, sm, r0, nr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward kernel, tensor-core decoders (input gradients: rays + grid voxels).  Decoder-weight gradients stay on the
+// SIMT kernel for now (host dispatch).
+__global__ void __launch_bounds__(128, 1) render_bwd_tc_kernel(const __grid_constant__ KParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  tc::TcSmem t;
+  tc::tc_carve(smem_raw, t);
+  Smem sm;
+  smem_layout(0, P.max_pts, P.max_rays, 0, 0, true, &sm, smem_raw + ((tc::tc_smem_bytes() + 127) & ~size_t(127)));
+  __shared__ float gC[kMaxRaysPerBlock * 3];
+  const int r0 = blockIdx.x * P.rays_per_block;
+  const int nr = P.in.n_rays - r0 < P.rays_per_block ? P.in.n_rays - r0 : P.rays_per_block;
+  const int Pb = nr * P.S;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(t.tmem)), "r"(tc::kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 0) { mbar_init(t.bar, 1); mbar_init(t.wbar, 1); mbar_fence_init(); }
+  bwd_prologue(P, sm, r0, nr, Pb, warp, 4, lane, gC);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *t.tmem;
+
+  uint32_t parity = 0, wparity = 0;
+  const int ntiles = (Pb + tc::TM - 1) / tc::TM;
+  for (int tile = 0; tile < ntiles; tile++) {
+    const int lp = tile * tc::TM + threadIdx.x;
+    const int lpc = lp < Pb ? lp : Pb - 1;
+    const int ray = lpc / P.S;
+    PointGeom G;
+    {
+      const float* rr = sm.rays + 8 * ray;
+      const float o[3] = {rr[0], rr[1], rr[2]}, dd[3] = {rr[3], rr[4], rr[5]};
+      make_point(P.in.bound, P.in.coarse_bound, o, dd, sm.zs[lpc], G);
+    }
+    for (int qd = 0; qd < P.n_dec; qd++) {
+      const int lv = P.dec[qd];
+      const DecRT d = make_dec(lv);
+      float out[4];
+      tc::tile_forward<true>(P, t, d, lv, G, tmem, parity, wparity, out);
+      float g_out[4] = {0.f, 0.f, 0.f, 0.f};
+      if (lp < Pb) {
+        if (lv == 3) { const float w = sm.wgt[lp]; g_out[0] = w * gC[3 * ray]; g_out[1] = w * gC[3 * ray + 1]; g_out[2] = w * gC[3 * ray + 2]; }
+        else g_out[0] = sm.gocc[lp];
+      }
+      float dpe[3];
+      tc::tile_backward(P, t, d, lv, G, tmem, parity, g_out, dpe);
+      if (lp < Pb) { sm.dp[3 * lp] += (double)dpe[0]; sm.dp[3 * lp + 1] += (double)dpe[1]; sm.dp[3 * lp + 2] += (double)dpe[2]; }
+      __syncthreads();                                           // dL/dc rows + the dp updates above are visible
+      const double* bb = lv == 0 ? P.in.coarse_bound : P.in.bound;
+      const float* xn = lv == 0 ? G.xnc : G.xn;
+      tc::scatter_rows(P.in.grid[lv], P.bw.d_grid[lv], t.x, d.cd, xn, warp, lane, [&](int row, const float gx[3]) {
+        const int l2 = tile * tc::TM + row;
+        if (l2 < Pb) {
+#pragma unroll
+          for (int a = 0; a < 3; a++) sm.dp[3 * l2 + a] += ((double)gx[a] * 2.0) / (bb[2 * a + 1] - bb[2 * a]);
+        }
+      });
     }
   }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tc::kTmemCols) : "memory");
+  bwd_ray_reduce(P, sm, r0, nr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -656,14 +733,15 @@ static void choose_config(int n_items, int S, int rows, bool bwd, int wbytes, in
 }
 
 static int g_mlp_backend = 0;      // 0 = auto (tensor-core forward), 1 = SIMT, 2 = tcgen05
-static size_t tc_total_smem(int max_pts, int max_rays) {
-  return ((tc::tc_smem_bytes() + 127) & ~size_t(127)) + smem_layout(0, max_pts, max_rays, 0, 0, false, nullptr, nullptr);
+static size_t tc_total_smem(int max_pts, int max_rays, bool bwd = false) {
+  return ((tc::tc_smem_bytes() + 127) & ~size_t(127)) + smem_layout(0, max_pts, max_rays, 0, 0, bwd, nullptr, nullptr);
 }
 
 static bool g_attr_set = false;
 static int set_attrs() {
   if (g_attr_set) return NSB_OK;
   if (check_cuda(cudaFuncSetAttribute(render_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap), "fwd tc smem attr")) return NSB_ERR_CUDA;
+  if (check_cuda(cudaFuncSetAttribute(render_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap), "bwd tc smem attr")) return NSB_ERR_CUDA;
   if (check_cuda(cudaFuncSetAttribute(render_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap), "fwd smem attr")) return NSB_ERR_CUDA;
   if (check_cuda(cudaFuncSetAttribute(render_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap), "bwd smem attr")) return NSB_ERR_CUDA;
   g_attr_set = true;
@@ -756,6 +834,10 @@ extern "C" int nsb_render_backward(const nsb_render_inputs* in, const nsb_backwa
   choose_config(in->n_rays, K.S, kRowsBwd, true, K.wbytes, 8, &K, &warps, &smem);
   if (smem > kSmemCap) { set_error("shared-memory budget exceeded (%zu bytes)", smem); return NSB_ERR_UNSUPPORTED; }
   const int grid = (in->n_rays + K.rays_per_block - 1) / K.rays_per_block;
+  if (g_mlp_backend != 1 && !any_w) {        // tensor-core decoders; decoder-weight gradients are SIMT-only for now
+    render_bwd_tc_kernel<<<grid, 128, tc_total_smem(K.max_pts, K.max_rays, true), st>>>(K);
+    return check_cuda(cudaGetLastError(), "render_bwd_tc_kernel launch");
+  }
   render_bwd_kernel<<<grid, warps * 32, smem, st>>>(K);
   if ((rc = check_cuda(cudaGetLastError(), "render_bwd_kernel launch"))) return rc;
   if (any_w) return launch_unpack_grads(K.d_packed, bw->d_flat, st);

@@ -93,20 +93,26 @@ struct TcSmem {
   float* wa;       // weight stage A: hi|lo, 32 x 96 each (24 KB)
   float* wb;       // weight stage B: hi|lo, 32 x 32 each (8 KB)
   float* bias;     // 328 floats: b[5][32] | bc[5][32] | bo[4] | Wo[4][32] is read from global
+  uint32_t* masks; // [5][128] relu masks of the recomputed forward (backward kernel)
+  float* wraw;     // packed fp32 image of the current decoder (one TMA bulk copy per decoder and tile, overlapped with the gather)
+  uint64_t* wbar;  // TMA completion barrier
   uint64_t* bar;   // MMA completion barrier
   uint32_t* tmem;  // TMEM base address slot
 };
 constexpr int kXFloats = 2 * TM * 64;            // 16384 floats = 64 KB
 constexpr int kWaFloats = 2 * 32 * 96;           // 24 KB
 constexpr int kWbFloats = 2 * 32 * 32;           // 8 KB
-__host__ __device__ inline size_t tc_smem_bytes() { return (size_t)(kXFloats + kWaFloats + kWbFloats + 336) * 4 + 64; }
+__host__ __device__ inline size_t tc_smem_bytes() { return (size_t)(kXFloats + kWaFloats + kWbFloats + 336 + 5 * TM + kMaxPacked) * 4 + 64; }
 __device__ __forceinline__ void tc_carve(unsigned char* base, TcSmem& t) {
   float* f = reinterpret_cast<float*>(base);
   t.x = f; f += kXFloats;
   t.wa = f; f += kWaFloats;
   t.wb = f; f += kWbFloats;
   t.bias = f; f += 336;
+  t.masks = reinterpret_cast<uint32_t*>(f); f += 5 * TM;
+  t.wraw = f; f += kMaxPacked;
   t.bar = reinterpret_cast<uint64_t*>(f);
+  t.wbar = reinterpret_cast<uint64_t*>(f + 2);
   t.tmem = reinterpret_cast<uint32_t*>(f + 4);
 }
 
@@ -116,7 +122,7 @@ __device__ __forceinline__ void stage_w(float* __restrict__ dst, const float* __
   const int kq4 = K >> 2;
   for (int i = threadIdx.x; i < 32 * kq4; i += blockDim.x) {
     const int n = i / kq4, kq = i - n * kq4;
-    const float4 v = ldg_f4(src + n * pitch + c0 + 4 * kq);
+    const float4 v = *reinterpret_cast<const float4*>(src + n * pitch + c0 + 4 * kq);
     put4(hi, lo, n, kq, K, v);
   }
 }
@@ -126,7 +132,7 @@ __device__ __forceinline__ void gather_rows(const nsb_grid& g, float* __restrict
                                             const float xn[3], int warp, int lane) {
   const bool fast = grid_fast(g);
   const int q = lane & 7;
-#pragma unroll 2
+#pragma unroll 4
   for (int it = 0; it < 8; it++) {
     const int src_lane = it * 4 + (lane >> 3);
     float x[3];
@@ -148,7 +154,7 @@ __device__ __forceinline__ void gather_rows(const nsb_grid& g, float* __restrict
 }
 
 // E block `blk` (features 32*blk .. +31, zero beyond 93) of this thread's point -> canonical hi|lo tile of width 32
-__device__ __forceinline__ void embed_row(float* __restrict__ e_hi, float* __restrict__ e_lo, const float* __restrict__ B /*global packed [3][96]*/,
+__device__ __forceinline__ void embed_row(float* __restrict__ e_hi, float* __restrict__ e_lo, const float* __restrict__ B /*packed [3][96]*/,
                                           const float pf[3], int row, int blk) {
 #pragma unroll 2
   for (int kq = 0; kq < 8; kq++) {
@@ -156,7 +162,7 @@ __device__ __forceinline__ void embed_row(float* __restrict__ e_hi, float* __res
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const int f = 32 * blk + 4 * kq + j;
-      float x = pf[0] * __ldg(B + f); x = fmaf(pf[1], __ldg(B + kEmbPad + f), x); x = fmaf(pf[2], __ldg(B + 2 * kEmbPad + f), x);
+      float x = pf[0] * B[f]; x = fmaf(pf[1], B[kEmbPad + f], x); x = fmaf(pf[2], B[2 * kEmbPad + f], x);
       v[j] = f < kEmb ? __sinf(reduce_2pi(x)) : 0.0f;
     }
     put4(e_hi, e_lo, row, kq, 32, make_float4(v[0], v[1], v[2], v[3]));
@@ -165,27 +171,37 @@ __device__ __forceinline__ void embed_row(float* __restrict__ e_hi, float* __res
 
 // Forward of decoder `lv` for one 128-point tile.  Every thread = one point (row == threadIdx.x).  On return out[o] holds the
 // decoder outputs of this thread's point.  `parity` is the running phase of t.bar.
+template <bool KEEP>
 __device__ __forceinline__ void tile_forward(const KParams& P, const TcSmem& t, const DecRT& d, int lv, const PointGeom& G,
-                                             uint32_t tmem, uint32_t& parity, float (&out)[4]) {
+                                             uint32_t tmem, uint32_t& parity, uint32_t& wparity, float (&out)[4]) {
   const int row = threadIdx.x, warp = row >> 5, lane = row & 31;
-  const float* Wg = P.in.packed[lv];                       // packed fp32 image in global memory (L2 resident)
+  const float* Wg = t.wraw;                                // packed fp32 image of this decoder, staged by TMA below
   float* c_hi = t.x; float* c_lo = t.x + TM * d.cd;
   const uint32_t d1 = tmem, d2 = tmem + 32u;
   const uint32_t my_lane = (uint32_t)(warp * 32) << 16;
 
-  __syncthreads();                       // previous decoder / tile: all reads of the bias block and of the tiles are done
-  // biases -> shared (b[5][32] | bc[5][32] | bo[4])
-  for (int i = threadIdx.x; i < 324; i += blockDim.x) {
-    float v = 0.0f;
-    if (i < 160) v = __ldg(Wg + d.o_b + i);
-    else if (i < 320) v = d.xyz ? __ldg(Wg + d.o_bc + (i - 160)) : 0.0f;
-    else v = __ldg(Wg + d.o_bo + (i - 320));
-    t.bias[i] = v;
+  __syncthreads();                       // previous decoder / tile: all reads of the weight image and of the tiles are done
+  if (threadIdx.x == 0) {                // TMA bulk copy of the decoder's packed image; overlaps with the gather below
+    fence_proxy_async();
+    const uint32_t bytes = (uint32_t)packed_floats(lv) * 4u;
+    mbar_expect_tx(t.wbar, bytes);
+    const char* src = reinterpret_cast<const char*>(P.in.packed[lv]);
+    char* dst = reinterpret_cast<char*>(t.wraw);
+    for (uint32_t off = 0; off < bytes; off += 32768u) tma_bulk_g2s(dst + off, src + off, bytes - off < 32768u ? bytes - off : 32768u, t.wbar);
   }
   // ---- gather -> C tile
   const float* xn = lv == 0 ? G.xnc : G.xn;
   gather_rows(P.in.grid[lv], c_hi, c_lo, d.cd, 0, xn, warp, lane);
   if (lv == 2) gather_rows(P.in.grid[1], c_hi, c_lo, d.cd, 32, G.xn, warp, lane);
+  mbar_wait(t.wbar, wparity); wparity ^= 1u;
+  // biases -> shared (b[5][32] | bc[5][32] | bo[4])  (kept separate: they are read with per-thread broadcast indices)
+  for (int i = threadIdx.x; i < 324; i += blockDim.x) {
+    float v = 0.0f;
+    if (i < 160) v = Wg[d.o_b + i];
+    else if (i < 320) v = d.xyz ? Wg[d.o_bc + (i - 160)] : 0.0f;
+    else v = Wg[d.o_bo + (i - 320)];
+    t.bias[i] = v;
+  }
 
   // ---- D2[:, 32i..32i+32) = C * Wc_i^T  (xyz decoders only)
   if (d.xyz) {
@@ -245,8 +261,10 @@ __device__ __forceinline__ void tile_forward(const KParams& P, const TcSmem& t, 
     // ---- epilogue of layer i: h = relu(D1 + b_i) + (D2_i + bc_i)
     float v1[32];
     tmem_ld32(d1 + my_lane, v1);
+    uint32_t m = 0;
 #pragma unroll
-    for (int j = 0; j < 32; j++) { const float u = v1[j] + t.bias[i * 32 + j]; h[j] = u > 0.0f ? u : 0.0f; }
+    for (int j = 0; j < 32; j++) { const float u = v1[j] + t.bias[i * 32 + j]; h[j] = u > 0.0f ? u : 0.0f; m |= u > 0.0f ? (1u << j) : 0u; }
+    if (KEEP) t.masks[i * TM + row] = m;
     if (d.xyz) {
       float v2[32];
       tmem_ld32(d2 + 32u * i + my_lane, v2);
@@ -265,9 +283,173 @@ __device__ __forceinline__ void tile_forward(const KParams& P, const TcSmem& t, 
     float s = t.bias[320 + o];
     if (o < d.no) {
 #pragma unroll
-      for (int j = 0; j < 32; j++) s = fmaf(h[j], __ldg(Wg + d.o_WO + o * Dec<1>::PH + j), s);
+      for (int j = 0; j < 32; j++) s = fmaf(h[j], Wg[d.o_WO + o * Dec<1>::PH + j], s);
     }
     out[o] = s;
+  }
+}
+
+// transposed staging for the backward GEMMs: B[n][k] = W[k][c0 + n] for n < NR, k < 32  (canonical hi|lo tiles of width 32)
+__device__ __forceinline__ void stage_wT(float* __restrict__ dst, const float* __restrict__ src, int pitch, int c0, int NR) {
+  float* hi = dst; float* lo = dst + NR * 32;
+  const int nq4 = NR >> 2;
+  for (int i = threadIdx.x; i < 32 * nq4; i += blockDim.x) {
+    const int k = i / nq4, nq = i - k * nq4;
+    const float4 v = *reinterpret_cast<const float4*>(src + k * pitch + c0 + 4 * nq);
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int n = 4 * nq + j;
+      const int idx = ((n >> 3) * 8 + (k >> 2)) * 32 + (n & 7) * 4 + (k & 3);
+      const float h = to_tf32(vv[j]);
+      hi[idx] = h; lo[idx] = to_tf32(vv[j] - h);
+    }
+  }
+}
+
+// Backward of decoder `lv` for one tile, input gradients only (rays + grid voxels; no decoder-weight gradients).
+// Precondition: tile_forward<true> just ran for the same tile (masks in t.masks).  g_out = dL/d out of this thread's point.
+// Writes dL/dc of every row to `dcs` ([128][cd] fp32, aliasing t.x) and returns dpe = dL/dp through the Fourier embedding.
+__device__ __forceinline__ void tile_backward(const KParams& P, const TcSmem& t, const DecRT& d, int lv, const PointGeom& G,
+                                              uint32_t tmem, uint32_t& parity, const float (&g_out)[4], float (&dpe)[3]) {
+  const int row = threadIdx.x, warp = row >> 5;
+  const float* Wg = t.wraw;                                 // still resident from the recomputed forward of this decoder
+  const uint32_t d1 = tmem, dcc = tmem + 32u, dfc = tmem + 96u;      // DC: cols [32,96)  DF: cols [96,192)  (D2 is dead)
+  const uint32_t my_lane = (uint32_t)(warp * 32) << 16;
+  float* g_hi = t.x; float* g_lo = t.x + TM * 32;
+  float* du_hi = t.x + 2 * TM * 32; float* du_lo = t.x + 3 * TM * 32;
+  constexpr int PH = Dec<1>::PH;
+  float g[32];
+#pragma unroll
+  for (int j = 0; j < 32; j++) {
+    float v = 0.0f;
+#pragma unroll
+    for (int o = 0; o < 4; o++) v = fmaf(Wg[d.o_WO + o * PH + j], g_out[o], v);       // rows >= NO are zero
+    g[j] = v;
+  }
+  uint32_t acc_dc = 0, acc_df = 0;
+#pragma unroll 1
+  for (int i = 4; i >= 0; i--) {
+    const uint32_t m = t.masks[i * TM + row];
+#pragma unroll
+    for (int kq = 0; kq < 8; kq++) {
+      if (d.xyz) put4(g_hi, g_lo, row, kq, 32, make_float4(g[4 * kq], g[4 * kq + 1], g[4 * kq + 2], g[4 * kq + 3]));
+      put4(du_hi, du_lo, row, kq, 32, make_float4((m >> (4 * kq)) & 1u ? g[4 * kq] : 0.0f, (m >> (4 * kq + 1)) & 1u ? g[4 * kq + 1] : 0.0f,
+                                                   (m >> (4 * kq + 2)) & 1u ? g[4 * kq + 2] : 0.0f, (m >> (4 * kq + 3)) & 1u ? g[4 * kq + 3] : 0.0f));
+    }
+    if (d.xyz || i >= 1) {     // batch A: DC += G * Wc_i (dL/dc through fc_c) ; D1 = DU * W_i[:, hidden] (g_i)
+      if (d.xyz) stage_wT(t.wa, Wg + d.o_WC + i * 32 * d.pc, d.pc, 0, d.cd);
+      if (i >= 1) stage_wT(t.wb, Wg + dec_wh(d, i), PH, 0, 32);
+      publish_operands();
+      if (threadIdx.x == 0) {
+        tc_fence_after();
+        if (d.xyz) mma_3x(dcc, g_hi, g_lo, 32, 0, t.wa, t.wa + d.cd * 32, 32, 0, 4, d.cd, acc_dc);
+        if (i >= 1) { uint32_t a1 = 0; mma_3x(d1, du_hi, du_lo, 32, 0, t.wb, t.wb + 32 * 32, 32, 0, 4, 32, a1); }
+        mma_commit(t.bar);
+      }
+      __syncwarp();
+      mbar_wait(t.bar, parity); parity ^= 1u;
+      tc_fence_after();
+    }
+    if (i == 3 || i == 0) {    // batch B: DF += DU * W_i[:, first]  (gradient w.r.t. the embedding / coarse feature)
+      stage_wT(t.wa, Wg + (i == 0 ? d.o_W0 : d.o_W3E), d.pf, 0, d.firstp);
+      publish_operands();
+      if (threadIdx.x == 0) {
+        tc_fence_after();
+        mma_3x(dfc, du_hi, du_lo, 32, 0, t.wa, t.wa + d.firstp * 32, 32, 0, 4, d.firstp, acc_df);
+        mma_commit(t.bar);
+      }
+      __syncwarp();
+      mbar_wait(t.bar, parity); parity ^= 1u;
+      tc_fence_after();
+    }
+    if (i >= 1) tmem_ld32(d1 + my_lane, g);
+    tc_fence_before();
+  }
+  // ---- dL/dc rows -> shared (plain fp32 [128][cd]); all MMAs reading t.x have completed
+  float* dcs = t.x;
+  {
+    float v[32];
+    const int nch = d.xyz ? (d.cd >> 5) : 1;
+    for (int c = 0; c < nch; c++) {
+      tmem_ld32((d.xyz ? dcc : dfc) + 32u * c + my_lane, v);
+#pragma unroll
+      for (int kq = 0; kq < 8; kq++) *reinterpret_cast<float4*>(dcs + row * d.cd + 32 * c + 4 * kq) = make_float4(v[4 * kq], v[4 * kq + 1], v[4 * kq + 2], v[4 * kq + 3]);
+    }
+  }
+  // ---- embedding chain: dp += B (cos(pB) * dfirst)
+  dpe[0] = dpe[1] = dpe[2] = 0.0f;
+  if (d.xyz) {
+    const float* B = Wg + d.o_B;
+    for (int c = 0; c < 3; c++) {
+      float v[32];
+      tmem_ld32(dfc + 32u * c + my_lane, v);
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        const int f = 32 * c + j;
+        if (f < kEmb) {
+          const float b0 = B[f], b1 = B[kEmbPad + f], b2 = B[2 * kEmbPad + f];
+          float x = G.pf[0] * b0; x = fmaf(G.pf[1], b1, x); x = fmaf(G.pf[2], b2, x);
+          const float dx = __cosf(reduce_2pi(x)) * v[j];
+          dpe[0] = fmaf(b0, dx, dpe[0]); dpe[1] = fmaf(b1, dx, dpe[1]); dpe[2] = fmaf(b2, dx, dpe[2]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+}
+
+// Backward of gather_rows for the warp's 32 rows: dc rows come from `dcs` ([128][cd] fp32).  Scatter-adds into dgrid (if non-null)
+// and hands the normalised-coordinate gradient of each point to emit(row, gx).
+template <typename F>
+__device__ __forceinline__ void scatter_rows(const nsb_grid& g, float* __restrict__ dgrid, const float* __restrict__ dcs, int cd,
+                                             const float xn[3], int warp, int lane, F&& emit) {
+  const bool fast = grid_fast(g);
+  const int q = lane & 7;
+#pragma unroll 1
+  for (int it = 0; it < 8; it++) {
+    const int src_lane = it * 4 + (lane >> 3);
+    const int row = warp * 32 + src_lane;
+    float x[3];
+    x[0] = __shfl_sync(0xffffffffu, xn[0], src_lane); x[1] = __shfl_sync(0xffffffffu, xn[1], src_lane); x[2] = __shfl_sync(0xffffffffu, xn[2], src_lane);
+    const Tri t = make_tri(x, g.W, g.H, g.D);
+    const float4 d4 = *reinterpret_cast<const float4*>(dcs + row * cd + 4 * q);
+    const float dc[4] = {d4.x, d4.y, d4.z, d4.w};
+    float gi[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      int cx, cy, cz;
+      if (tri_corner(t, k, g.W, g.H, g.D, cx, cy, cz)) {
+        const long long off = cz * g.stride_d + cy * g.stride_h + cx * g.stride_w;
+        const float4 v = grid_load4(g, off, 4 * q, fast);
+        const float dot = v.x * dc[0] + v.y * dc[1] + v.z * dc[2] + v.w * dc[3];
+        if (dgrid != nullptr) {
+          const float w = tri_weight(t, k);
+          if (fast) red_add_v4(dgrid + off + 4 * q, w * dc[0], w * dc[1], w * dc[2], w * dc[3]);
+          else {
+#pragma unroll
+            for (int c = 0; c < 4; c++) atomicAdd(dgrid + off + (long long)(4 * q + c) * g.stride_c, w * dc[c]);
+          }
+        }
+        const float wx = (k & 1) ? t.w1[0] : t.w0[0], wy = (k & 2) ? t.w1[1] : t.w0[1], wz = (k & 4) ? t.w1[2] : t.w0[2];
+        gi[0] += ((k & 1) ? 1.f : -1.f) * wy * wz * dot;
+        gi[1] += ((k & 2) ? 1.f : -1.f) * wx * wz * dot;
+        gi[2] += ((k & 4) ? 1.f : -1.f) * wx * wy * dot;
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      float v = gi[a];
+      v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
+      gi[a] = v;
+    }
+    if (q == 0) {
+      const int size[3] = {g.W, g.H, g.D};
+      float gx[3];
+#pragma unroll
+      for (int a = 0; a < 3; a++) gx[a] = t.clipg[a] * ((float)(size[a] - 1) * 0.5f) * gi[a];
+      emit(row, gx);
+    }
   }
 }
 
