@@ -117,6 +117,8 @@ typedef struct {
   double* z_vals;                /* [N,S] sorted sample depths; required if backward will run, else optional */
   float* raw;                    /* [N,S,4] (r,g,b,occ logit with the out-of-bound override); same rule */
   int32_t* corner_idx;           /* optional [N,S,3]: (ix0,iy0,iz0) of the stage's finest occupancy grid */
+  uint32_t* masks;               /* optional [N,S,15]: ReLU sign bits of the 5 layers of up to 3 decoders (stage order); when the
+                                    backward pass receives them it does not recompute the forward (tensor-core backend only) */
 } nsb_forward_outputs;
 
 /* Forward: sample -> gather -> decode -> composite  (Renderer.render_batch_ray, src/utils/Renderer.py:63-198) */
@@ -134,6 +136,7 @@ typedef struct {
   float* d_flat[4];              /* decoder parameter gradients, canonical flat order; ACCUMULATED; NULL = skip */
   void* workspace;               /* device scratch of nsb_backward_workspace_bytes() bytes, 16-byte aligned;
                                     required iff any d_flat[l] != NULL (the library zeroes and consumes it) */
+  const uint32_t* masks;         /* [N,S,15] from forward, or NULL (recompute) */
 } nsb_backward_args;
 
 size_t nsb_backward_workspace_bytes(void);
@@ -174,6 +177,7 @@ int nsb_pose_grad(const float* dirs, const float* d_rays_o, const float* d_rays_
 typedef struct {
   double* depth;  double* var;  float* rgb;      /* [N], [N], [N,3]   rendered outputs            */
   double* z_vals; float* raw;                    /* [N,S], [N,S,4]    forward state kept for backward */
+  uint32_t* masks;                               /* [N,S,15] or NULL  ReLU sign bits (see nsb_forward_outputs) */
   double* g_depth; float* g_rgb;                 /* [N], [N,3]        loss seeds                  */
   double* loss;                                  /* [1]               scalar loss (float64)       */
   float* depth_max;                              /* [2]               batch depth maxima          */

@@ -134,6 +134,11 @@ __device__ __forceinline__ float tri_weight(const Tri& t, int k) {   // corner k
   const float wz = (k & 4) ? t.w1[2] : t.w0[2];
   return __fmul_rn(__fmul_rn(wx, wy), wz);
 }
+// Branch-free corner addressing: the upper corner index is clamped to the grid; when the clamp is active the sample sits
+// exactly on the last voxel (u == size-1) so that corner's weight w1 is exactly 0 -- same result as grid_sample skipping it.
+__device__ __forceinline__ void tri_corner_clamped(const Tri& t, int k, int W, int H, int D, int& x, int& y, int& z) {
+  x = min(t.i0[0] + (k & 1), W - 1); y = min(t.i0[1] + ((k >> 1) & 1), H - 1); z = min(t.i0[2] + ((k >> 2) & 1), D - 1);
+}
 __device__ __forceinline__ bool tri_corner(const Tri& t, int k, int W, int H, int D, int& x, int& y, int& z) {
   x = t.i0[0] + (k & 1); y = t.i0[1] + ((k >> 1) & 1); z = t.i0[2] + ((k >> 2) & 1);
   return x < W && y < H && z < D;      // lower bounds hold by construction (border clip)

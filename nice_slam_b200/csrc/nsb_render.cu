@@ -29,7 +29,8 @@ __device__ __forceinline__ float4 grid_load4(const nsb_grid& g, long long off, i
                      __ldg(g.data + off + (long long)(c0 + 2) * g.stride_c), __ldg(g.data + off + (long long)(c0 + 3) * g.stride_c));
 }
 
-// rows [row0,row0+32) <- features of the 16 points; xn = normalised coords of point (lane & 15)
+// rows [row0,row0+32) <- features of the 16 points; xn = normalised coords of point (lane & 15).
+// All eight corner loads of a pass are issued before any of them is consumed (branch-free clamped addressing).
 __device__ __forceinline__ void gather_chunk(const nsb_grid& g, float* __restrict__ act, int row0, const float xn[3], int lane) {
   const bool fast = grid_fast(g);
   const int q = lane & 7;
@@ -39,16 +40,18 @@ __device__ __forceinline__ void gather_chunk(const nsb_grid& g, float* __restric
     float x[3];
     x[0] = __shfl_sync(0xffffffffu, xn[0], pt); x[1] = __shfl_sync(0xffffffffu, xn[1], pt); x[2] = __shfl_sync(0xffffffffu, xn[2], pt);
     const Tri t = make_tri(x, g.W, g.H, g.D);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       int cx, cy, cz;
-      if (tri_corner(t, k, g.W, g.H, g.D, cx, cy, cz)) {
-        const long long off = cz * g.stride_d + cy * g.stride_h + cx * g.stride_w;
-        const float4 v = grid_load4(g, off, 4 * q, fast);
-        const float w = tri_weight(t, k);
-        acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y); acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
-      }
+      tri_corner_clamped(t, k, g.W, g.H, g.D, cx, cy, cz);
+      v[k] = grid_load4(g, cz * g.stride_d + cy * g.stride_h + cx * g.stride_w, 4 * q, fast);
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const float w = tri_weight(t, k);
+      acc.x = fmaf(v[k].x, w, acc.x); acc.y = fmaf(v[k].y, w, acc.y); acc.z = fmaf(v[k].z, w, acc.z); acc.w = fmaf(v[k].w, w, acc.w);
     }
     act[act_idx(row0 + 4 * q + 0, pt)] = acc.x; act[act_idx(row0 + 4 * q + 1, pt)] = acc.y;
     act[act_idx(row0 + 4 * q + 2, pt)] = acc.z; act[act_idx(row0 + 4 * q + 3, pt)] = acc.w;
@@ -73,19 +76,26 @@ __device__ __forceinline__ void scatter_chunk(const nsb_grid& g, float* __restri
 #pragma unroll
     for (int c = 0; c < 4; c++) dc[c] = act[act_idx(row0 + 4 * q + c, pt)];
     float gi[3] = {0.f, 0.f, 0.f};
+    long long offs[8]; float4 vv[8]; bool ins[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {                                // all corner loads first (branch-free clamped addressing)
+      int cx, cy, cz;
+      ins[k] = tri_corner(t, k, g.W, g.H, g.D, cx, cy, cz);
+      tri_corner_clamped(t, k, g.W, g.H, g.D, cx, cy, cz);
+      offs[k] = cz * g.stride_d + cy * g.stride_h + cx * g.stride_w;
+      vv[k] = grid_load4(g, offs[k], 4 * q, fast);
+    }
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      int cx, cy, cz;
-      if (tri_corner(t, k, g.W, g.H, g.D, cx, cy, cz)) {
-        const long long off = cz * g.stride_d + cy * g.stride_h + cx * g.stride_w;
-        const float4 v = grid_load4(g, off, 4 * q, fast);
+      if (ins[k]) {                                              // corners outside the grid get neither gradient nor a dot product
+        const float4 v = vv[k];
         const float dot = v.x * dc[0] + v.y * dc[1] + v.z * dc[2] + v.w * dc[3];
         if (dgrid != nullptr) {
           const float w = tri_weight(t, k);
-          if (fast) red_add_v4(dgrid + off + 4 * q, w * dc[0], w * dc[1], w * dc[2], w * dc[3]);
+          if (fast) red_add_v4(dgrid + offs[k] + 4 * q, w * dc[0], w * dc[1], w * dc[2], w * dc[3]);
           else {
 #pragma unroll
-            for (int c = 0; c < 4; c++) atomicAdd(dgrid + off + (long long)(4 * q + c) * g.stride_c, w * dc[c]);
+            for (int c = 0; c < 4; c++) atomicAdd(dgrid + offs[k] + (long long)(4 * q + c) * g.stride_c, w * dc[c]);
           }
         }
         const float wx = (k & 1) ? t.w1[0] : t.w0[0], wy = (k & 2) ? t.w1[1] : t.w0[1], wz = (k & 4) ? t.w1[2] : t.w0[2];
@@ -423,7 +433,8 @@ __global__ void __launch_bounds__(128, 1) render_fwd_tc_kernel(const __grid_cons
       const int lv = P.dec[qd];
       const DecRT d = make_dec(lv);
       float out[4];
-      tc::tile_forward<false>(P, t, d, lv, G, tmem, parity, wparity, out);
+      uint32_t* gm = (P.fo.masks != nullptr && lp < Pb) ? P.fo.masks + ((((long long)blockIdx.x * P.rays_per_block) * P.S + lp) * 15 + qd * 5) : nullptr;
+      tc::tile_forward<false>(P, t, d, lv, G, tmem, parity, wparity, out, gm);
       if (lv == 3) { c0 = out[0]; c1 = out[1]; c2 = out[2]; } else occ += out[0];
       if (qd == 0 && lp < Pb && P.fo.corner_idx != nullptr) {
         const nsb_grid& g = P.in.grid[lv];
@@ -635,15 +646,15 @@ __global__ void __launch_bounds__(128, 1) render_bwd_tc_kernel(const __grid_cons
     for (int qd = 0; qd < P.n_dec; qd++) {
       const int lv = P.dec[qd];
       const DecRT d = make_dec(lv);
-      float out[4];
-      tc::tile_forward<true>(P, t, d, lv, G, tmem, parity, wparity, out);
+      const uint32_t* gm = P.bw.masks != nullptr ? P.bw.masks + ((((long long)blockIdx.x * P.rays_per_block) * P.S + lpc) * 15 + qd * 5) : nullptr;
+      if (gm == nullptr) { float out[4]; tc::tile_forward<true>(P, t, d, lv, G, tmem, parity, wparity, out, nullptr); }
       float g_out[4] = {0.f, 0.f, 0.f, 0.f};
       if (lp < Pb) {
         if (lv == 3) { const float w = sm.wgt[lp]; g_out[0] = w * gC[3 * ray]; g_out[1] = w * gC[3 * ray + 1]; g_out[2] = w * gC[3 * ray + 2]; }
         else g_out[0] = sm.gocc[lp];
       }
       float dpe[3];
-      tc::tile_backward(P, t, d, lv, G, tmem, parity, g_out, dpe);
+      tc::tile_backward(P, t, d, lv, G, tmem, parity, wparity, g_out, dpe, gm);
       if (lp < Pb) { sm.dp[3 * lp] += (double)dpe[0]; sm.dp[3 * lp + 1] += (double)dpe[1]; sm.dp[3 * lp + 2] += (double)dpe[2]; }
       __syncthreads();                                           // dL/dc rows + the dp updates above are visible
       const double* bb = lv == 0 ? P.in.coarse_bound : P.in.bound;
@@ -717,9 +728,11 @@ static int sm_count() {
 // choose rays per CTA and warps per CTA: fill all SMs once before growing CTAs (latency-bound small batches),
 // cap CTA size by the shared-memory budget (227 KB per CTA, 1 KB kept for static shared memory)
 constexpr size_t kSmemCap = 226u * 1024u;
-static void choose_config(int n_items, int S, int rows, bool bwd, int wbytes, int max_warps, KParams* K, int* warps, size_t* smem) {
+constexpr int kMaxPtsTc = 256;            // points per CTA of the tensor-core kernels (2 tiles)
+static void choose_config(int n_items, int S, int rows, bool bwd, int wbytes, int max_warps, KParams* K, int* warps, size_t* smem,
+                          int max_pts_cap = kMaxPtsPerBlock) {
   const int sms = sm_count();
-  int r_cap = kMaxPtsPerBlock / S; if (r_cap < 1) r_cap = 1; if (r_cap > kMaxRaysPerBlock) r_cap = kMaxRaysPerBlock;
+  int r_cap = max_pts_cap / S; if (r_cap < 1) r_cap = 1; if (r_cap > kMaxRaysPerBlock) r_cap = kMaxRaysPerBlock;
   int r = (n_items + sms - 1) / sms; if (r < 1) r = 1; if (r > r_cap) r = r_cap;
   const int max_pts = ((r * S + kChunk - 1) / kChunk) * kChunk;
   const int chunks = max_pts / kChunk;
@@ -762,6 +775,7 @@ extern "C" int nsb_render_forward(const nsb_render_inputs* in, const nsb_forward
   if (!out || !out->depth || !out->var || !out->rgb) { set_error("forward outputs missing"); return NSB_ERR_ARG; }
   if (in->n_rays == 0) return NSB_OK;
   KParams K; fill_common(K, in); K.fo = *out; memset(&K.bw, 0, sizeof(K.bw));
+  if (g_mlp_backend == 1 || K.S > kMaxPtsTc) K.fo.masks = nullptr;        // only the tensor-core forward produces masks
   if (K.S > NSB_MAX_SAMPLES) { set_error("n_samples+n_surface = %d exceeds %d", K.S, NSB_MAX_SAMPLES); return NSB_ERR_UNSUPPORTED; }
   if (K.has_gt && in->n_surface > 0 && !in->t_surface) { set_error("t_surface NULL"); return NSB_ERR_ARG; }
   if ((rc = set_attrs())) return rc;
@@ -769,9 +783,12 @@ extern "C" int nsb_render_forward(const nsb_render_inputs* in, const nsb_forward
   choose_config(in->n_rays, K.S, kRowsFwd, false, K.wbytes, 8, &K, &warps, &smem);
   if (smem > kSmemCap) { set_error("shared-memory budget exceeded (%zu bytes)", smem); return NSB_ERR_UNSUPPORTED; }
   const int grid = (in->n_rays + K.rays_per_block - 1) / K.rays_per_block;
-  if (g_mlp_backend != 1) {          // tensor-core decoders (same CTA <-> ray mapping, 128 threads)
+  if (g_mlp_backend != 1 && K.S <= kMaxPtsTc) {          // tensor-core decoders, 128 threads, <= 2 tiles of 128 points per CTA
+    choose_config(in->n_rays, K.S, kRowsFwd, false, K.wbytes, 8, &K, &warps, &smem, kMaxPtsTc);
+    const int grid_tc = (in->n_rays + K.rays_per_block - 1) / K.rays_per_block;
     const size_t smem_tc = tc_total_smem(K.max_pts, K.max_rays);
-    render_fwd_tc_kernel<<<grid, 128, smem_tc, (cudaStream_t)stream>>>(K);
+    if (smem_tc > kSmemCap) { set_error("shared-memory budget exceeded (%zu bytes)", smem_tc); return NSB_ERR_UNSUPPORTED; }
+    render_fwd_tc_kernel<<<grid_tc, 128, smem_tc, (cudaStream_t)stream>>>(K);
     return check_cuda(cudaGetLastError(), "render_fwd_tc_kernel launch");
   }
   render_fwd_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(K);
@@ -834,8 +851,12 @@ extern "C" int nsb_render_backward(const nsb_render_inputs* in, const nsb_backwa
   choose_config(in->n_rays, K.S, kRowsBwd, true, K.wbytes, 8, &K, &warps, &smem);
   if (smem > kSmemCap) { set_error("shared-memory budget exceeded (%zu bytes)", smem); return NSB_ERR_UNSUPPORTED; }
   const int grid = (in->n_rays + K.rays_per_block - 1) / K.rays_per_block;
-  if (g_mlp_backend != 1 && !any_w) {        // tensor-core decoders; decoder-weight gradients are SIMT-only for now
-    render_bwd_tc_kernel<<<grid, 128, tc_total_smem(K.max_pts, K.max_rays, true), st>>>(K);
+  if (g_mlp_backend != 1 && !any_w && K.S <= kMaxPtsTc) {        // tensor-core decoders; decoder-weight gradients are SIMT-only for now
+    choose_config(in->n_rays, K.S, kRowsBwd, true, K.wbytes, 8, &K, &warps, &smem, kMaxPtsTc);
+    const int grid_tc = (in->n_rays + K.rays_per_block - 1) / K.rays_per_block;
+    const size_t smem_tc = tc_total_smem(K.max_pts, K.max_rays, true);
+    if (smem_tc > kSmemCap) { set_error("shared-memory budget exceeded (%zu bytes)", smem_tc); return NSB_ERR_UNSUPPORTED; }
+    render_bwd_tc_kernel<<<grid_tc, 128, smem_tc, st>>>(K);
     return check_cuda(cudaGetLastError(), "render_bwd_tc_kernel launch");
   }
   render_bwd_kernel<<<grid, warps * 32, smem, st>>>(K);

@@ -30,7 +30,7 @@ __device__ __forceinline__ void put4(float* __restrict__ hi, float* __restrict__
   const int idx = canon_q(r, kq, K);
   float4 h, l;
   h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-  l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+  l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;   // exact; the MMA ignores the 13 low bits (<= 2^-21 |v|)
   *reinterpret_cast<float4*>(hi + idx) = h;
   *reinterpret_cast<float4*>(lo + idx) = l;
 }
@@ -91,8 +91,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 struct TcSmem {
   float* x;        // 64 KB: C hi|lo (128 x 64 each)  -- later  E hi|lo (128 x 32) + H hi|lo (128 x 32), or two E blocks
   float* wa;       // weight stage A: hi|lo, 32 x 96 each (24 KB)
-  float* wb;       // weight stage B: hi|lo, 32 x 32 each (8 KB)
-  float* bias;     // 328 floats: b[5][32] | bc[5][32] | bo[4] | Wo[4][32] is read from global
+  float* wb;       // weight stage B: 24 KB, contiguous with wa
+  float* bias;     // 464 floats: b[5][32] | bc[5][32] | bo[4] | pad[12] | Wo[4][32]
   uint32_t* masks; // [5][128] relu masks of the recomputed forward (backward kernel)
   float* wraw;     // packed fp32 image of the current decoder (one TMA bulk copy per decoder and tile, overlapped with the gather)
   uint64_t* wbar;  // TMA completion barrier
@@ -101,14 +101,14 @@ struct TcSmem {
 };
 constexpr int kXFloats = 2 * TM * 64;            // 16384 floats = 64 KB
 constexpr int kWaFloats = 2 * 32 * 96;           // 24 KB
-constexpr int kWbFloats = 2 * 32 * 32;           // 8 KB
-__host__ __device__ inline size_t tc_smem_bytes() { return (size_t)(kXFloats + kWaFloats + kWbFloats + 336 + 5 * TM + kMaxPacked) * 4 + 64; }
+constexpr int kWbFloats = 2 * 32 * 96;           // 24 KB (contiguous with wa: 48 KB stage)
+__host__ __device__ inline size_t tc_smem_bytes() { return (size_t)(kXFloats + kWaFloats + kWbFloats + 464 + 5 * TM + kMaxPacked) * 4 + 64; }
 __device__ __forceinline__ void tc_carve(unsigned char* base, TcSmem& t) {
   float* f = reinterpret_cast<float*>(base);
   t.x = f; f += kXFloats;
   t.wa = f; f += kWaFloats;
   t.wb = f; f += kWbFloats;
-  t.bias = f; f += 336;
+  t.bias = f; f += 464;
   t.masks = reinterpret_cast<uint32_t*>(f); f += 5 * TM;
   t.wraw = f; f += kMaxPacked;
   t.bar = reinterpret_cast<uint64_t*>(f);
@@ -132,24 +132,32 @@ __device__ __forceinline__ void gather_rows(const nsb_grid& g, float* __restrict
                                             const float xn[3], int warp, int lane) {
   const bool fast = grid_fast(g);
   const int q = lane & 7;
-#pragma unroll 4
-  for (int it = 0; it < 8; it++) {
-    const int src_lane = it * 4 + (lane >> 3);
-    float x[3];
-    x[0] = __shfl_sync(0xffffffffu, xn[0], src_lane); x[1] = __shfl_sync(0xffffffffu, xn[1], src_lane); x[2] = __shfl_sync(0xffffffffu, xn[2], src_lane);
-    const Tri t = make_tri(x, g.W, g.H, g.D);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+  for (int it0 = 0; it0 < 8; it0 += 2) {                         // two passes (8 points of the warp) per batch: 16 loads in flight per lane
+    Tri t[2]; float4 v[2][8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-      int cx, cy, cz;
-      if (tri_corner(t, k, g.W, g.H, g.D, cx, cy, cz)) {
-        const long long off = cz * g.stride_d + cy * g.stride_h + cx * g.stride_w;
-        const float4 v = grid_load4(g, off, 4 * q, fast);
-        const float w = tri_weight(t, k);
-        acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y); acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
+    for (int u = 0; u < 2; u++) {
+      const int src_lane = (it0 + u) * 4 + (lane >> 3);
+      float x[3];
+      x[0] = __shfl_sync(0xffffffffu, xn[0], src_lane); x[1] = __shfl_sync(0xffffffffu, xn[1], src_lane); x[2] = __shfl_sync(0xffffffffu, xn[2], src_lane);
+      t[u] = make_tri(x, g.W, g.H, g.D);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        int cx, cy, cz;
+        tri_corner_clamped(t[u], k, g.W, g.H, g.D, cx, cy, cz);
+        v[u][k] = grid_load4(g, cz * g.stride_d + cy * g.stride_h + cx * g.stride_w, 4 * q, fast);
       }
     }
-    put4(c_hi, c_lo, warp * 32 + src_lane, (col0 >> 2) + q, KC, acc);
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const float w = tri_weight(t[u], k);
+        acc.x = fmaf(v[u][k].x, w, acc.x); acc.y = fmaf(v[u][k].y, w, acc.y); acc.z = fmaf(v[u][k].z, w, acc.z); acc.w = fmaf(v[u][k].w, w, acc.w);
+      }
+      put4(c_hi, c_lo, warp * 32 + (it0 + u) * 4 + (lane >> 3), (col0 >> 2) + q, KC, acc);
+    }
   }
 }
 
@@ -170,15 +178,20 @@ __device__ __forceinline__ void embed_row(float* __restrict__ e_hi, float* __res
 }
 
 // Forward of decoder `lv` for one 128-point tile.  Every thread = one point (row == threadIdx.x).  On return out[o] holds the
-// decoder outputs of this thread's point.  `parity` is the running phase of t.bar.
+// decoder outputs of this thread's point.  `parity` / `wparity` are the running phases of t.bar / t.wbar.
+// TMEM: D1 = cols [0,32) (layers 0,1,2,4), D2 = [32,192) (fc_c of the five layers), D3 = [192,224) (layer 3; its skip part
+// E * W3E^T is accumulated while the embedding blocks are live for layer 0, so the embedding is computed once).
+// Sequential MMA batches per decoder: fc_c 1-2, layer 0: 3 (one per embedding block), layers 1..4: one each.
 template <bool KEEP>
 __device__ __forceinline__ void tile_forward(const KParams& P, const TcSmem& t, const DecRT& d, int lv, const PointGeom& G,
-                                             uint32_t tmem, uint32_t& parity, uint32_t& wparity, float (&out)[4]) {
+                                             uint32_t tmem, uint32_t& parity, uint32_t& wparity, float (&out)[4],
+                                             uint32_t* __restrict__ gmask /* global [5] slot of this point+decoder, or nullptr */) {
   const int row = threadIdx.x, warp = row >> 5, lane = row & 31;
   const float* Wg = t.wraw;                                // packed fp32 image of this decoder, staged by TMA below
   float* c_hi = t.x; float* c_lo = t.x + TM * d.cd;
-  const uint32_t d1 = tmem, d2 = tmem + 32u;
+  const uint32_t d1 = tmem, d2 = tmem + 32u, d3 = tmem + 192u;
   const uint32_t my_lane = (uint32_t)(warp * 32) << 16;
+  constexpr int PH = Dec<1>::PH;
 
   __syncthreads();                       // previous decoder / tile: all reads of the weight image and of the tiles are done
   if (threadIdx.x == 0) {                // TMA bulk copy of the decoder's packed image; overlaps with the gather below
@@ -194,96 +207,102 @@ __device__ __forceinline__ void tile_forward(const KParams& P, const TcSmem& t, 
   gather_rows(P.in.grid[lv], c_hi, c_lo, d.cd, 0, xn, warp, lane);
   if (lv == 2) gather_rows(P.in.grid[1], c_hi, c_lo, d.cd, 32, G.xn, warp, lane);
   mbar_wait(t.wbar, wparity); wparity ^= 1u;
-  // biases -> shared (b[5][32] | bc[5][32] | bo[4])  (kept separate: they are read with per-thread broadcast indices)
-  for (int i = threadIdx.x; i < 324; i += blockDim.x) {
+  // biases + output weights -> shared (b[5][32] | bc[5][32] | bo[4] | pad | Wo[4][32])
+  for (int i = threadIdx.x; i < 464; i += blockDim.x) {
     float v = 0.0f;
     if (i < 160) v = Wg[d.o_b + i];
     else if (i < 320) v = d.xyz ? Wg[d.o_bc + (i - 160)] : 0.0f;
-    else v = Wg[d.o_bo + (i - 320)];
+    else if (i < 324) v = Wg[d.o_bo + (i - 320)];
+    else if (i >= 336) v = Wg[d.o_WO + ((i - 336) >> 5) * PH + ((i - 336) & 31)];
     t.bias[i] = v;
   }
-
-  // ---- D2[:, 32i..32i+32) = C * Wc_i^T  (xyz decoders only)
+  // ---- D2[:, 32i..32i+32) = C * Wc_i^T  (xyz decoders only); as many layers per batch as the 48 KB stage holds
   if (d.xyz) {
-    for (int i = 0; i < 5; i++) {
-      stage_w(t.wa, Wg + d.o_WC + i * 32 * d.pc, d.pc, 0, d.cd);
+    const int per = d.cd == 64 ? 3 : 5;
+    for (int i0 = 0; i0 < 5; i0 += per) {
+      const int i1 = i0 + per < 5 ? i0 + per : 5;
+      for (int i = i0; i < i1; i++) stage_w(t.wa + (i - i0) * 2 * 32 * d.cd, Wg + d.o_WC + i * 32 * d.pc, d.pc, 0, d.cd);
       publish_operands();
       if (threadIdx.x == 0) {
         tc_fence_after();
-        uint32_t acc = 0;
-        mma_3x(d2 + 32u * i, c_hi, c_lo, d.cd, 0, t.wa, t.wa + 32 * d.cd, d.cd, 0, d.cd >> 3, 32, acc);
-        mma_commit(t.bar);
-      }
-      __syncwarp();
-      mbar_wait(t.bar, parity); parity ^= 1u;              // the stage buffer is reused by the next layer
-      tc_fence_after();
-    }
-  }
-  // (for the coarse decoder the first input is C itself: keep the C tile alive, the E/H tiles use the upper half of x)
-  float* e_hi = d.xyz ? t.x : c_hi;
-  float* e_lo = d.xyz ? t.x + TM * 32 : c_lo;
-  float* h_hi = t.x + 2 * TM * 32;
-  float* h_lo = t.x + 3 * TM * 32;
-  float h[32];
-#pragma unroll 1
-  for (int i = 0; i < 5; i++) {
-    uint32_t acc = 0;
-    if (i == 0 || i == 3) {
-      const int ow = i == 0 ? d.o_W0 : d.o_W3E;
-      stage_w(t.wa, Wg + ow, d.pf, 0, d.firstp);           // whole first-input weight block (K = 96 or 32)
-      if (i == 3) stage_w(t.wb, Wg + d.o_Wh[3], Dec<1>::PH, 0, 32);
-      const int nblk = d.xyz ? 3 : 1;
-      for (int blk = 0; blk < nblk; blk++) {
-        if (d.xyz) embed_row(e_hi, e_lo, Wg + d.o_B, G.pf, row, blk);
-        publish_operands();
-        if (threadIdx.x == 0) {
-          tc_fence_after();
-          mma_3x(d1, e_hi, e_lo, 32, 0, t.wa, t.wa + 32 * d.firstp, d.firstp, 32 * blk, 4, 32, acc);
-          if (i == 3 && blk == nblk - 1) mma_3x(d1, h_hi, h_lo, 32, 0, t.wb, t.wb + 32 * 32, 32, 0, 4, 32, acc);
-          mma_commit(t.bar);
+        for (int i = i0; i < i1; i++) {
+          uint32_t acc = 0;
+          const float* w = t.wa + (i - i0) * 2 * 32 * d.cd;
+          mma_3x(d2 + 32u * i, c_hi, c_lo, d.cd, 0, w, w + 32 * d.cd, d.cd, 0, d.cd >> 3, 32, acc);
         }
-        __syncwarp();
-        mbar_wait(t.bar, parity); parity ^= 1u;            // E buffer / stage buffers free again
-        tc_fence_after();
-      }
-    } else {
-      stage_w(t.wb, Wg + dec_wh(d, i), Dec<1>::PH, 0, 32);
-      publish_operands();
-      if (threadIdx.x == 0) {
-        tc_fence_after();
-        mma_3x(d1, h_hi, h_lo, 32, 0, t.wb, t.wb + 32 * 32, 32, 0, 4, 32, acc);
         mma_commit(t.bar);
       }
       __syncwarp();
       mbar_wait(t.bar, parity); parity ^= 1u;
       tc_fence_after();
     }
-    // ---- epilogue of layer i: h = relu(D1 + b_i) + (D2_i + bc_i)
+  }
+  // ---- layer 0 (and the skip part of layer 3): first input = Fourier embedding (three 32-feature blocks) or, coarse, C itself
+  float* e_hi = d.xyz ? t.x : c_hi;
+  float* e_lo = d.xyz ? t.x + TM * 32 : c_lo;
+  float* h_hi = t.x + 2 * TM * 32;
+  float* h_lo = t.x + 3 * TM * 32;
+  {
+    uint32_t acc1 = 0, acc3 = 0;
+    const int nblk = d.xyz ? 3 : 1;
+    for (int blk = 0; blk < nblk; blk++) {
+      stage_w(t.wa, Wg + d.o_W0, d.pf, 32 * blk, 32);
+      stage_w(t.wa + 2 * 32 * 32, Wg + d.o_W3E, d.pf, 32 * blk, 32);
+      if (d.xyz) embed_row(e_hi, e_lo, Wg + d.o_B, G.pf, row, blk);
+      publish_operands();
+      if (threadIdx.x == 0) {
+        tc_fence_after();
+        mma_3x(d1, e_hi, e_lo, 32, 0, t.wa, t.wa + 32 * 32, 32, 0, 4, 32, acc1);
+        mma_3x(d3, e_hi, e_lo, 32, 0, t.wa + 2 * 32 * 32, t.wa + 3 * 32 * 32, 32, 0, 4, 32, acc3);
+        mma_commit(t.bar);
+      }
+      __syncwarp();
+      mbar_wait(t.bar, parity); parity ^= 1u;              // E buffer / stage buffers free again
+      tc_fence_after();
+    }
+  }
+  // hidden-part weights of layers 1..4, all at once (4 x 8 KB): no staging on the critical path of the remaining layers
+  for (int i = 1; i < 5; i++) stage_w(t.wa + (i - 1) * 2 * 32 * 32, Wg + dec_wh(d, i), PH, 0, 32);
+  float h[32];
+#pragma unroll 1
+  for (int i = 0; i < 5; i++) {
+    // ---- epilogue of layer i: h = relu(D + b_i) + (D2_i + bc_i)
     float v1[32];
-    tmem_ld32(d1 + my_lane, v1);
+    tmem_ld32((i == 3 ? d3 : d1) + my_lane, v1);
     uint32_t m = 0;
 #pragma unroll
     for (int j = 0; j < 32; j++) { const float u = v1[j] + t.bias[i * 32 + j]; h[j] = u > 0.0f ? u : 0.0f; m |= u > 0.0f ? (1u << j) : 0u; }
     if (KEEP) t.masks[i * TM + row] = m;
+    if (gmask != nullptr) gmask[i] = m;
     if (d.xyz) {
       float v2[32];
       tmem_ld32(d2 + 32u * i + my_lane, v2);
 #pragma unroll
       for (int j = 0; j < 32; j++) h[j] += v2[j] + t.bias[160 + i * 32 + j];
     }
-    if (i < 4) {
+    if (i == 4) break;
 #pragma unroll
-      for (int kq = 0; kq < 8; kq++) put4(h_hi, h_lo, row, kq, 32, make_float4(h[4 * kq], h[4 * kq + 1], h[4 * kq + 2], h[4 * kq + 3]));
+    for (int kq = 0; kq < 8; kq++) put4(h_hi, h_lo, row, kq, 32, make_float4(h[4 * kq], h[4 * kq + 1], h[4 * kq + 2], h[4 * kq + 3]));
+    publish_operands();                                      // (also orders this layer's TMEM reads before the next MMAs)
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      const float* w = t.wa + i * 2 * 32 * 32;               // hidden weights of layer i+1
+      uint32_t acc = (i + 1 == 3) ? 1u : 0u;                 // layer 3 accumulates onto E * W3E^T
+      mma_3x((i + 1 == 3) ? d3 : d1, h_hi, h_lo, 32, 0, w, w + 32 * 32, 32, 0, 4, 32, acc);
+      mma_commit(t.bar);
     }
-    tc_fence_before();      // TMEM reads of this layer are ordered before the next layer's MMAs (issued after the next barrier)
+    __syncwarp();
+    mbar_wait(t.bar, parity); parity ^= 1u;
+    tc_fence_after();
   }
+  tc_fence_before();
   // ---- output layer in registers
 #pragma unroll
   for (int o = 0; o < 4; o++) {
     float s = t.bias[320 + o];
     if (o < d.no) {
 #pragma unroll
-      for (int j = 0; j < 32; j++) s = fmaf(h[j], Wg[d.o_WO + o * Dec<1>::PH + j], s);
+      for (int j = 0; j < 32; j++) s = fmaf(h[j], t.bias[336 + o * 32 + j], s);
     }
     out[o] = s;
   }
@@ -302,7 +321,7 @@ __device__ __forceinline__ void stage_wT(float* __restrict__ dst, const float* _
       const int n = 4 * nq + j;
       const int idx = ((n >> 3) * 8 + (k >> 2)) * 32 + (n & 7) * 4 + (k & 3);
       const float h = to_tf32(vv[j]);
-      hi[idx] = h; lo[idx] = to_tf32(vv[j] - h);
+      hi[idx] = h; lo[idx] = vv[j] - h;
     }
   }
 }
@@ -311,9 +330,26 @@ __device__ __forceinline__ void stage_wT(float* __restrict__ dst, const float* _
 // Precondition: tile_forward<true> just ran for the same tile (masks in t.masks).  g_out = dL/d out of this thread's point.
 // Writes dL/dc of every row to `dcs` ([128][cd] fp32, aliasing t.x) and returns dpe = dL/dp through the Fourier embedding.
 __device__ __forceinline__ void tile_backward(const KParams& P, const TcSmem& t, const DecRT& d, int lv, const PointGeom& G,
-                                              uint32_t tmem, uint32_t& parity, const float (&g_out)[4], float (&dpe)[3]) {
+                                              uint32_t tmem, uint32_t& parity, uint32_t& wparity, const float (&g_out)[4], float (&dpe)[3],
+                                              const uint32_t* __restrict__ gmask /* saved masks of this point+decoder or nullptr */) {
   const int row = threadIdx.x, warp = row >> 5;
-  const float* Wg = t.wraw;                                 // still resident from the recomputed forward of this decoder
+  const float* Wg = t.wraw;                                 // resident from the recomputed forward, or loaded below
+  if (gmask != nullptr) {                                   // no forward recompute: bring the decoder image in and the masks
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      fence_proxy_async();
+      const uint32_t bytes = (uint32_t)packed_floats(lv) * 4u;
+      mbar_expect_tx(t.wbar, bytes);
+      const char* src = reinterpret_cast<const char*>(P.in.packed[lv]);
+      char* dst = reinterpret_cast<char*>(t.wraw);
+      for (uint32_t off = 0; off < bytes; off += 32768u) tma_bulk_g2s(dst + off, src + off, bytes - off < 32768u ? bytes - off : 32768u, t.wbar);
+    }
+#pragma unroll
+    for (int i = 0; i < 5; i++) t.masks[i * TM + row] = gmask[i];
+    mbar_wait(t.wbar, wparity); wparity ^= 1u;
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) t.bias[336 + i] = Wg[d.o_WO + (i >> 5) * Dec<1>::PH + (i & 31)];
+    __syncthreads();
+  }
   const uint32_t d1 = tmem, dcc = tmem + 32u, dfc = tmem + 96u;      // DC: cols [32,96)  DF: cols [96,192)  (D2 is dead)
   const uint32_t my_lane = (uint32_t)(warp * 32) << 16;
   float* g_hi = t.x; float* g_lo = t.x + TM * 32;
@@ -324,7 +360,7 @@ __device__ __forceinline__ void tile_backward(const KParams& P, const TcSmem& t,
   for (int j = 0; j < 32; j++) {
     float v = 0.0f;
 #pragma unroll
-    for (int o = 0; o < 4; o++) v = fmaf(Wg[d.o_WO + o * PH + j], g_out[o], v);       // rows >= NO are zero
+    for (int o = 0; o < 4; o++) v = fmaf(t.bias[336 + o * 32 + j], g_out[o], v);       // rows >= NO are zero
     g[j] = v;
   }
   uint32_t acc_dc = 0, acc_df = 0;
@@ -337,26 +373,19 @@ __device__ __forceinline__ void tile_backward(const KParams& P, const TcSmem& t,
       put4(du_hi, du_lo, row, kq, 32, make_float4((m >> (4 * kq)) & 1u ? g[4 * kq] : 0.0f, (m >> (4 * kq + 1)) & 1u ? g[4 * kq + 1] : 0.0f,
                                                    (m >> (4 * kq + 2)) & 1u ? g[4 * kq + 2] : 0.0f, (m >> (4 * kq + 3)) & 1u ? g[4 * kq + 3] : 0.0f));
     }
-    if (d.xyz || i >= 1) {     // batch A: DC += G * Wc_i (dL/dc through fc_c) ; D1 = DU * W_i[:, hidden] (g_i)
-      if (d.xyz) stage_wT(t.wa, Wg + d.o_WC + i * 32 * d.pc, d.pc, 0, d.cd);
-      if (i >= 1) stage_wT(t.wb, Wg + dec_wh(d, i), PH, 0, 32);
+    {   // one batch per layer: DC += G * Wc_i (dL/dc through fc_c) ; D1 = DU * W_i[:, hidden] (g_i) ; DF += DU * W_i[:, first] (i = 3, 0)
+      float* wcT = t.wa;                         // [cd x 32] hi|lo (<= 16 KB)
+      float* whT = t.wa + 2 * 64 * 32;           // [32 x 32] hi|lo (8 KB)
+      float* weT = t.wb;                         // [firstp x 32] hi|lo (<= 24 KB)
+      if (d.xyz) stage_wT(wcT, Wg + d.o_WC + i * 32 * d.pc, d.pc, 0, d.cd);
+      if (i >= 1) stage_wT(whT, Wg + dec_wh(d, i), PH, 0, 32);
+      if (i == 3 || i == 0) stage_wT(weT, Wg + (i == 0 ? d.o_W0 : d.o_W3E), d.pf, 0, d.firstp);
       publish_operands();
       if (threadIdx.x == 0) {
         tc_fence_after();
-        if (d.xyz) mma_3x(dcc, g_hi, g_lo, 32, 0, t.wa, t.wa + d.cd * 32, 32, 0, 4, d.cd, acc_dc);
-        if (i >= 1) { uint32_t a1 = 0; mma_3x(d1, du_hi, du_lo, 32, 0, t.wb, t.wb + 32 * 32, 32, 0, 4, 32, a1); }
-        mma_commit(t.bar);
-      }
-      __syncwarp();
-      mbar_wait(t.bar, parity); parity ^= 1u;
-      tc_fence_after();
-    }
-    if (i == 3 || i == 0) {    // batch B: DF += DU * W_i[:, first]  (gradient w.r.t. the embedding / coarse feature)
-      stage_wT(t.wa, Wg + (i == 0 ? d.o_W0 : d.o_W3E), d.pf, 0, d.firstp);
-      publish_operands();
-      if (threadIdx.x == 0) {
-        tc_fence_after();
-        mma_3x(dfc, du_hi, du_lo, 32, 0, t.wa, t.wa + d.firstp * 32, 32, 0, 4, d.firstp, acc_df);
+        if (d.xyz) mma_3x(dcc, g_hi, g_lo, 32, 0, wcT, wcT + d.cd * 32, 32, 0, 4, d.cd, acc_dc);
+        if (i >= 1) { uint32_t a1 = 0; mma_3x(d1, du_hi, du_lo, 32, 0, whT, whT + 32 * 32, 32, 0, 4, 32, a1); }
+        if (i == 3 || i == 0) mma_3x(dfc, du_hi, du_lo, 32, 0, weT, weT + d.firstp * 32, 32, 0, 4, d.firstp, acc_df);
         mma_commit(t.bar);
       }
       __syncwarp();
@@ -416,19 +445,26 @@ __device__ __forceinline__ void scatter_rows(const nsb_grid& g, float* __restric
     const float4 d4 = *reinterpret_cast<const float4*>(dcs + row * cd + 4 * q);
     const float dc[4] = {d4.x, d4.y, d4.z, d4.w};
     float gi[3] = {0.f, 0.f, 0.f};
+    long long offs[8]; float4 vv[8]; bool ins[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {                                // all corner loads first (branch-free clamped addressing)
+      int cx, cy, cz;
+      ins[k] = tri_corner(t, k, g.W, g.H, g.D, cx, cy, cz);
+      tri_corner_clamped(t, k, g.W, g.H, g.D, cx, cy, cz);
+      offs[k] = cz * g.stride_d + cy * g.stride_h + cx * g.stride_w;
+      vv[k] = grid_load4(g, offs[k], 4 * q, fast);
+    }
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      int cx, cy, cz;
-      if (tri_corner(t, k, g.W, g.H, g.D, cx, cy, cz)) {
-        const long long off = cz * g.stride_d + cy * g.stride_h + cx * g.stride_w;
-        const float4 v = grid_load4(g, off, 4 * q, fast);
+      if (ins[k]) {
+        const float4 v = vv[k];
         const float dot = v.x * dc[0] + v.y * dc[1] + v.z * dc[2] + v.w * dc[3];
         if (dgrid != nullptr) {
           const float w = tri_weight(t, k);
-          if (fast) red_add_v4(dgrid + off + 4 * q, w * dc[0], w * dc[1], w * dc[2], w * dc[3]);
+          if (fast) red_add_v4(dgrid + offs[k] + 4 * q, w * dc[0], w * dc[1], w * dc[2], w * dc[3]);
           else {
 #pragma unroll
-            for (int c = 0; c < 4; c++) atomicAdd(dgrid + off + (long long)(4 * q + c) * g.stride_c, w * dc[c]);
+            for (int c = 0; c < 4; c++) atomicAdd(dgrid + offs[k] + (long long)(4 * q + c) * g.stride_c, w * dc[c]);
           }
         }
         const float wx = (k & 1) ? t.w1[0] : t.w0[0], wy = (k & 2) ? t.w1[1] : t.w0[1], wz = (k & 4) ? t.w1[2] : t.w0[2];

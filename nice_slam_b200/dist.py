@@ -74,7 +74,7 @@ class ShardedTrackingIteration:
         _lib.check(L.nsb_batch_max_depth(_VP(gt_depth.data_ptr()), n, _VP(x.depth_max.data_ptr()), _stream()), "nsb_batch_max_depth")
         exchange_depth_max(x.depth_max)
         inp = _inputs(call, rays_o, rays_d, x.depth_max, t_u, t_s, [g.detach() for g in grids])
-        fo = _lib.ForwardOutputs(x.depth.data_ptr(), x.var.data_ptr(), x.rgb.data_ptr(), x.z_vals.data_ptr(), x.raw.data_ptr(), None)
+        fo = _lib.ForwardOutputs(x.depth.data_ptr(), x.var.data_ptr(), x.rgb.data_ptr(), x.z_vals.data_ptr(), x.raw.data_ptr(), None, x.masks.data_ptr())
         _lib.check(L.nsb_render_forward(C.byref(inp), C.byref(fo), _stream()), "nsb_render_forward")
         pool, n_pool = None, 0
         if handle_dynamic and world()[1] > 1:
@@ -87,7 +87,7 @@ class ShardedTrackingIteration:
                                         _VP(x.g_depth.data_ptr()), _VP(x.g_rgb.data_ptr()), _VP(x.loss.data_ptr()),
                                         _VP(x.ws.data_ptr()), L.nsb_tracking_seeds_workspace(n), _stream()), "nsb_tracking_seeds")
         bw = x._grads(c)
-        bw.z_vals, bw.raw, bw.g_depth, bw.g_rgb = x.z_vals.data_ptr(), x.raw.data_ptr(), x.g_depth.data_ptr(), x.g_rgb.data_ptr()
+        bw.z_vals, bw.raw, bw.g_depth, bw.g_rgb, bw.masks = x.z_vals.data_ptr(), x.raw.data_ptr(), x.g_depth.data_ptr(), x.g_rgb.data_ptr(), x.masks.data_ptr()
         _lib.check(L.nsb_render_backward(C.byref(inp), C.byref(bw), _stream()), "nsb_render_backward")
         _lib.check(L.nsb_pose_grad(_VP(dirs.data_ptr()), _VP(x.d_rays_o.data_ptr()), _VP(x.d_rays_d.data_ptr()), n,
                                    _VP(self.packed.data_ptr() + 8), _stream()), "nsb_pose_grad")

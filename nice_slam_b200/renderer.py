@@ -169,7 +169,8 @@ class _RenderFn(torch.autograd.Function):
         rgb = torch.empty(n, 3, dtype=torch.float32, device=dev)
         z_vals = torch.empty(n, S, dtype=torch.float64, device=dev)
         raw = torch.empty(n, S, 4, dtype=torch.float32, device=dev)
-        out = _lib.ForwardOutputs(depth.data_ptr(), var.data_ptr(), rgb.data_ptr(), z_vals.data_ptr(), raw.data_ptr(), None)
+        masks = torch.empty(n, S, 15, dtype=torch.int32, device=dev)      # ReLU sign bits: lets backward skip the forward recompute
+        out = _lib.ForwardOutputs(depth.data_ptr(), var.data_ptr(), rgb.data_ptr(), z_vals.data_ptr(), raw.data_ptr(), None, masks.data_ptr())
         corner = None
         if call.aux is not None:
             corner = torch.empty(n, S, 3, dtype=torch.int32, device=dev)
@@ -179,7 +180,7 @@ class _RenderFn(torch.autograd.Function):
             call.aux.update(z_vals=z_vals, raw=raw, corner_idx=corner)
         ctx.call = call
         ctx.n_lvl = n_lvl
-        ctx.keep = (ro, rd, depth_max, t_u, t_s, z_vals, raw)
+        ctx.keep = (ro, rd, depth_max, t_u, t_s, z_vals, raw, masks)
         ctx.grids = [g.detach() for g in grids]
         ctx.param_shapes = [tuple(p.shape) for p in params]
         return depth, var, rgb
@@ -188,14 +189,14 @@ class _RenderFn(torch.autograd.Function):
     def backward(ctx, g_depth, g_var, g_rgb):
         L = _lib.lib()
         call = ctx.call
-        ro, rd, depth_max, t_u, t_s, z_vals, raw = ctx.keep
+        ro, rd, depth_max, t_u, t_s, z_vals, raw, masks = ctx.keep
         dev = ro.device
         n = ro.shape[0]
         n_lvl = ctx.n_lvl
         needs = ctx.needs_input_grad          # (call, rays_o, rays_d, *grids, *params)
         inp = _inputs(call, ro, rd, depth_max, t_u, t_s, ctx.grids)
         bw = _lib.BackwardArgs()
-        bw.z_vals, bw.raw = z_vals.data_ptr(), raw.data_ptr()
+        bw.z_vals, bw.raw, bw.masks = z_vals.data_ptr(), raw.data_ptr(), masks.data_ptr()
         gd = g_depth.detach().contiguous().double() if g_depth is not None else torch.zeros(n, dtype=torch.float64, device=dev)
         gv = g_var.detach().contiguous().double() if g_var is not None else None
         gc = g_rgb.detach().contiguous().float() if g_rgb is not None else None

@@ -35,6 +35,7 @@ class IterationContext:
         self.rgb = torch.empty(n, 3, dtype=f32, device=dev)
         self.z_vals = torch.empty(n, S, dtype=f64, device=dev)
         self.raw = torch.empty(n, S, 4, dtype=f32, device=dev)
+        self.masks = torch.empty(n, S, 15, dtype=torch.int32, device=dev)
         self.g_depth = torch.empty(n, dtype=f64, device=dev)
         self.g_rgb = torch.empty(n, 3, dtype=f32, device=dev)
         self.loss = torch.zeros(1, dtype=f64, device=dev)
@@ -54,7 +55,7 @@ class IterationContext:
         self.d_grid = {}
         self.d_flat = {lvl: torch.zeros(L.nsb_flat_decoder_floats(LEVELS.index(lvl)), dtype=f32, device=dev) for lvl in self.grad_decoders}
         self.buf = _lib.IterationBuffers(self.depth.data_ptr(), self.var.data_ptr(), self.rgb.data_ptr(), self.z_vals.data_ptr(),
-                                         self.raw.data_ptr(), self.g_depth.data_ptr(), self.g_rgb.data_ptr(), self.loss.data_ptr(),
+                                         self.raw.data_ptr(), self.masks.data_ptr(), self.g_depth.data_ptr(), self.g_rgb.data_ptr(), self.loss.data_ptr(),
                                          self.depth_max.data_ptr(), self.ws.data_ptr(), self.ws.numel(), None, None)
         self.ev_bwd = None
         # pinned host staging for run_host(): [rays_o | rays_d | gt_depth] f32, gt_color, and the read-back block
