@@ -413,6 +413,7 @@ __global__ void __launch_bounds__(128, 1) render_fwd_tc_kernel(const __grid_cons
   const uint32_t tmem = *t.tmem;
 
   uint32_t parity = 0, wparity = 0;
+  bool prefetched = false;
   const int ntiles = (Pb + tc::TM - 1) / tc::TM;
   for (int tile = 0; tile < ntiles; tile++) {
     const int lp = tile * tc::TM + threadIdx.x;
@@ -434,7 +435,8 @@ __global__ void __launch_bounds__(128, 1) render_fwd_tc_kernel(const __grid_cons
       const DecRT d = make_dec(lv);
       float out[4];
       uint32_t* gm = (P.fo.masks != nullptr && lp < Pb) ? P.fo.masks + ((((long long)blockIdx.x * P.rays_per_block) * P.S + lp) * 15 + qd * 5) : nullptr;
-      tc::tile_forward<false>(P, t, d, lv, G, tmem, parity, wparity, out, gm);
+      const int next_lv = qd + 1 < P.n_dec ? P.dec[qd + 1] : (tile + 1 < ntiles ? P.dec[0] : -1);
+      tc::tile_forward<false>(P, t, d, lv, G, tmem, parity, wparity, out, gm, prefetched, next_lv);
       if (lv == 3) { c0 = out[0]; c1 = out[1]; c2 = out[2]; } else occ += out[0];
       if (qd == 0 && lp < Pb && P.fo.corner_idx != nullptr) {
         const nsb_grid& g = P.in.grid[lv];
@@ -632,6 +634,7 @@ __global__ void __launch_bounds__(128, 1) render_bwd_tc_kernel(const __grid_cons
   const uint32_t tmem = *t.tmem;
 
   uint32_t parity = 0, wparity = 0;
+  bool prefetched = false;
   const int ntiles = (Pb + tc::TM - 1) / tc::TM;
   for (int tile = 0; tile < ntiles; tile++) {
     const int lp = tile * tc::TM + threadIdx.x;
@@ -647,23 +650,28 @@ __global__ void __launch_bounds__(128, 1) render_bwd_tc_kernel(const __grid_cons
       const int lv = P.dec[qd];
       const DecRT d = make_dec(lv);
       const uint32_t* gm = P.bw.masks != nullptr ? P.bw.masks + ((((long long)blockIdx.x * P.rays_per_block) * P.S + lpc) * 15 + qd * 5) : nullptr;
-      if (gm == nullptr) { float out[4]; tc::tile_forward<true>(P, t, d, lv, G, tmem, parity, wparity, out, nullptr); }
+      if (gm == nullptr) { float out[4]; bool pf0 = false; tc::tile_forward<true>(P, t, d, lv, G, tmem, parity, wparity, out, nullptr, pf0, -1); }
       float g_out[4] = {0.f, 0.f, 0.f, 0.f};
       if (lp < Pb) {
         if (lv == 3) { const float w = sm.wgt[lp]; g_out[0] = w * gC[3 * ray]; g_out[1] = w * gC[3 * ray + 1]; g_out[2] = w * gC[3 * ray + 2]; }
         else g_out[0] = sm.gocc[lp];
       }
       float dpe[3];
-      tc::tile_backward(P, t, d, lv, G, tmem, parity, wparity, g_out, dpe, gm);
+      tc::tile_backward(P, t, d, lv, G, tmem, parity, wparity, g_out, dpe, gm, prefetched);
       if (lp < Pb) { sm.dp[3 * lp] += (double)dpe[0]; sm.dp[3 * lp + 1] += (double)dpe[1]; sm.dp[3 * lp + 2] += (double)dpe[2]; }
-      __syncthreads();                                           // dL/dc rows + the dp updates above are visible
+      __syncthreads();                                           // dL/dc rows + the dp updates above are visible; the packed image is dead
+      if (gm != nullptr) {                                       // prefetch the next decoder's image under the scatter below
+        const int next_lv = qd + 1 < P.n_dec ? P.dec[qd + 1] : (tile + 1 < ntiles ? P.dec[0] : -1);
+        if (next_lv >= 0) { if (threadIdx.x == 0) tc::issue_decoder_tma(P, t, next_lv); prefetched = true; }
+      }
       const double* bb = lv == 0 ? P.in.coarse_bound : P.in.bound;
+      const double sc[3] = {2.0 / (bb[1] - bb[0]), 2.0 / (bb[3] - bb[2]), 2.0 / (bb[5] - bb[4])};      // d(normalised)/dp, common.py:280-282
       const float* xn = lv == 0 ? G.xnc : G.xn;
       tc::scatter_rows(P.in.grid[lv], P.bw.d_grid[lv], t.x, d.cd, xn, warp, lane, [&](int row, const float gx[3]) {
         const int l2 = tile * tc::TM + row;
         if (l2 < Pb) {
 #pragma unroll
-          for (int a = 0; a < 3; a++) sm.dp[3 * l2 + a] += ((double)gx[a] * 2.0) / (bb[2 * a + 1] - bb[2 * a]);
+          for (int a = 0; a < 3; a++) sm.dp[3 * l2 + a] += (double)gx[a] * sc[a];
         }
       });
     }

@@ -116,6 +116,16 @@ __device__ __forceinline__ void tc_carve(unsigned char* base, TcSmem& t) {
   t.tmem = reinterpret_cast<uint32_t*>(f + 4);
 }
 
+// one elected thread: TMA bulk copy of decoder `lv`'s packed image into t.wraw, completion on t.wbar
+__device__ __forceinline__ void issue_decoder_tma(const KParams& P, const TcSmem& t, int lv) {
+  fence_proxy_async();
+  const uint32_t bytes = (uint32_t)packed_floats(lv) * 4u;
+  mbar_expect_tx(t.wbar, bytes);
+  const char* src = reinterpret_cast<const char*>(P.in.packed[lv]);
+  char* dst = reinterpret_cast<char*>(t.wraw);
+  for (uint32_t off = 0; off < bytes; off += 32768u) tma_bulk_g2s(dst + off, src + off, bytes - off < 32768u ? bytes - off : 32768u, t.wbar);
+}
+
 // stage rows [0,32) x columns [c0, c0+K) of a packed fp32 matrix (row pitch `pitch`) as a canonical hi|lo tile pair of width K
 __device__ __forceinline__ void stage_w(float* __restrict__ dst, const float* __restrict__ src, int pitch, int c0, int K) {
   float* hi = dst; float* lo = dst + 32 * K;
@@ -185,7 +195,8 @@ __device__ __forceinline__ void embed_row(float* __restrict__ e_hi, float* __res
 template <bool KEEP>
 __device__ __forceinline__ void tile_forward(const KParams& P, const TcSmem& t, const DecRT& d, int lv, const PointGeom& G,
                                              uint32_t tmem, uint32_t& parity, uint32_t& wparity, float (&out)[4],
-                                             uint32_t* __restrict__ gmask /* global [5] slot of this point+decoder, or nullptr */) {
+                                             uint32_t* __restrict__ gmask /* global [5] slot of this point+decoder, or nullptr */,
+                                             bool& prefetched /* this decoder's image is already in flight */, int next_lv /* prefetch after the last use, or -1 */) {
   const int row = threadIdx.x, warp = row >> 5, lane = row & 31;
   const float* Wg = t.wraw;                                // packed fp32 image of this decoder, staged by TMA below
   float* c_hi = t.x; float* c_lo = t.x + TM * d.cd;
@@ -194,14 +205,8 @@ __device__ __forceinline__ void tile_forward(const KParams& P, const TcSmem& t, 
   constexpr int PH = Dec<1>::PH;
 
   __syncthreads();                       // previous decoder / tile: all reads of the weight image and of the tiles are done
-  if (threadIdx.x == 0) {                // TMA bulk copy of the decoder's packed image; overlaps with the gather below
-    fence_proxy_async();
-    const uint32_t bytes = (uint32_t)packed_floats(lv) * 4u;
-    mbar_expect_tx(t.wbar, bytes);
-    const char* src = reinterpret_cast<const char*>(P.in.packed[lv]);
-    char* dst = reinterpret_cast<char*>(t.wraw);
-    for (uint32_t off = 0; off < bytes; off += 32768u) tma_bulk_g2s(dst + off, src + off, bytes - off < 32768u ? bytes - off : 32768u, t.wbar);
-  }
+  if (!prefetched && threadIdx.x == 0) issue_decoder_tma(P, t, lv);      // overlaps with the gather below
+  prefetched = false;
   // ---- gather -> C tile
   const float* xn = lv == 0 ? G.xnc : G.xn;
   gather_rows(P.in.grid[lv], c_hi, c_lo, d.cd, 0, xn, warp, lane);
@@ -284,6 +289,10 @@ __device__ __forceinline__ void tile_forward(const KParams& P, const TcSmem& t, 
 #pragma unroll
     for (int kq = 0; kq < 8; kq++) put4(h_hi, h_lo, row, kq, 32, make_float4(h[4 * kq], h[4 * kq + 1], h[4 * kq + 2], h[4 * kq + 3]));
     publish_operands();                                      // (also orders this layer's TMEM reads before the next MMAs)
+    if (i == 0 && next_lv >= 0 && !KEEP) {                   // the packed image is dead (hidden weights + biases are staged): prefetch the next one
+      if (threadIdx.x == 0) issue_decoder_tma(P, t, next_lv);
+      prefetched = true;
+    }
     if (threadIdx.x == 0) {
       tc_fence_after();
       const float* w = t.wa + i * 2 * 32 * 32;               // hidden weights of layer i+1
@@ -331,19 +340,14 @@ __device__ __forceinline__ void stage_wT(float* __restrict__ dst, const float* _
 // Writes dL/dc of every row to `dcs` ([128][cd] fp32, aliasing t.x) and returns dpe = dL/dp through the Fourier embedding.
 __device__ __forceinline__ void tile_backward(const KParams& P, const TcSmem& t, const DecRT& d, int lv, const PointGeom& G,
                                               uint32_t tmem, uint32_t& parity, uint32_t& wparity, const float (&g_out)[4], float (&dpe)[3],
-                                              const uint32_t* __restrict__ gmask /* saved masks of this point+decoder or nullptr */) {
+                                              const uint32_t* __restrict__ gmask /* saved masks of this point+decoder or nullptr */,
+                                              bool& prefetched) {
   const int row = threadIdx.x, warp = row >> 5;
   const float* Wg = t.wraw;                                 // resident from the recomputed forward, or loaded below
   if (gmask != nullptr) {                                   // no forward recompute: bring the decoder image in and the masks
     __syncthreads();
-    if (threadIdx.x == 0) {
-      fence_proxy_async();
-      const uint32_t bytes = (uint32_t)packed_floats(lv) * 4u;
-      mbar_expect_tx(t.wbar, bytes);
-      const char* src = reinterpret_cast<const char*>(P.in.packed[lv]);
-      char* dst = reinterpret_cast<char*>(t.wraw);
-      for (uint32_t off = 0; off < bytes; off += 32768u) tma_bulk_g2s(dst + off, src + off, bytes - off < 32768u ? bytes - off : 32768u, t.wbar);
-    }
+    if (!prefetched && threadIdx.x == 0) issue_decoder_tma(P, t, lv);
+    prefetched = false;
 #pragma unroll
     for (int i = 0; i < 5; i++) t.masks[i * TM + row] = gmask[i];
     mbar_wait(t.wbar, wparity); wparity ^= 1u;
