@@ -236,7 +236,7 @@ def run_native(args):
     sharded = ShardedTrackingIteration(ctx) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
 
-    h_pose = torch.empty(13, dtype=torch.float64).pin_memory()
+    use_graph = True
     if sharded is None:
         # single GPU: the whole iteration (and, for e2e, its host copies) is one CUDA-graph launch
         ctx.load_device_inputs(ro, rd, gd, gc)
@@ -250,14 +250,29 @@ def run_native(args):
             g_e2e.replay()
             torch.cuda.current_stream().synchronize()      # the caller reads loss / pose gradient from pinned memory
     else:
+        # N > 1: split-phase iteration with the three NCCL exchanges; captured into one CUDA graph per rank when possible
+        ctx.load_device_inputs(ro, rd, gd, gc)
+        sharded.prepare(c, dec, dirs)
+        sharded.enqueue(); torch.cuda.synchronize()
+        g_dev = sharded.build_graph(host_io=False)
+        g_e2e = sharded.build_graph(host_io=True)
+        flag = torch.tensor([1.0 if (g_dev is not None and g_e2e is not None) else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)                # all ranks must agree (collectives inside the graph)
+        use_graph = bool(flag.item() > 0.5)
+
         def step_dev():
-            sharded.run(c, dec, ro, rd, dirs, gd, gc)
+            if use_graph:
+                g_dev.replay()
+            else:
+                sharded.enqueue()
 
         def step_e2e():      # host inputs -> device -> sharded iteration (NCCL exchanges) -> [loss | d_c2w] back to the host
-            n = ctx.n
-            ctx.d_in32.copy_(ctx.h_in32, non_blocking=True); ctx.gt_color.copy_(ctx.h_col, non_blocking=True)
-            packed = sharded.run(c, dec, ctx.d_in32[: 3 * n].view(n, 3), ctx.d_in32[3 * n: 6 * n].view(n, 3), dirs, ctx.d_in32[6 * n:], ctx.gt_color)
-            h_pose.copy_(packed, non_blocking=True)
+            if use_graph:
+                g_e2e.replay()
+            else:
+                ctx.d_in32.copy_(ctx.h_in32, non_blocking=True); ctx.gt_color.copy_(ctx.h_col, non_blocking=True)
+                sharded.enqueue()
+                ctx.h_pose13.copy_(sharded.packed, non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
     def timed(fn, steps, warmup, flush_l2):
@@ -287,7 +302,7 @@ def run_native(args):
 
     # correctness guard of the timed path (cheap): loss finite
     step_dev(); torch.cuda.synchronize()
-    assert torch.isfinite(ctx.loss).all()
+    assert torch.isfinite(ctx.loss if sharded is None else sharded.packed).all()
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -316,7 +331,7 @@ def run_native(args):
     line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "rays_per_step": rays, "l2": "flushed between steps (256 MiB memset outside the event pair)",
-                       "launch": "CUDA graph replay (one graph per iteration)" if sharded is None else "stream launches + NCCL",
+                       "launch": "CUDA graph replay (one graph per iteration)" if (sharded is None or use_graph) else "stream launches + NCCL",
                        "parallelism": "ray-sharded x%d" % world, "timing": "sum of per-step CUDA-event pairs, max over ranks"},
             "clocks": clocks,
             "e2e": {"value": rays / (e2e_ms / args.steps * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": ctx.h2d_bytes,

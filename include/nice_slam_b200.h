@@ -137,6 +137,10 @@ typedef struct {
   void* workspace;               /* device scratch of nsb_backward_workspace_bytes() bytes, 16-byte aligned;
                                     required iff any d_flat[l] != NULL (the library zeroes and consumes it) */
   const uint32_t* masks;         /* [N,S,15] from forward, or NULL (recompute) */
+  const int32_t* slot_map[4];    /* masked (frustum-selected) voxel parameterisation, src/Mapper.py:317-333: when slot_map[l] != NULL
+                                    it is the [D*H*W] voxel -> slot table of nsb_voxel_slots() and d_grid[l] is the COMPACT gradient
+                                    [n_selected][32] (slot-major, 32 channels contiguous) of the selected voxels only; voxels with
+                                    slot -1 are not parameters and receive nothing.  NULL = d_grid[l] is dense. */
 } nsb_backward_args;
 
 size_t nsb_backward_workspace_bytes(void);
@@ -161,6 +165,24 @@ int nsb_tracking_residuals(const double* depth, const double* var, const float* 
 int nsb_mapping_seeds(const double* depth, const float* rgb, const float* gt_depth, const float* gt_rgb, int n,
                       double w_color, int use_color, double* g_depth, float* g_rgb, double* loss, void* stream);
 size_t nsb_tracking_seeds_workspace(int n);
+
+/* ---- masked voxel parameterisation (src/Mapper.py:317-333 val_grad = val[mask]; :393-401 / :511-519 val[mask] = val_grad) ----
+ * voxel_mask: uint8 [D*H*W] (the reference's bool mask is the same for all 32 channels: Mapper.py:319-320 repeats it).
+ * nsb_voxel_slots: slot_map[v] = rank of voxel v among the selected ones (d,h,w order), -1 if not selected; count[0] = n_selected.
+ * The reference orders val[mask] channel-major ([32][n_selected]); the compact buffers here are slot-major ([n_selected][32],
+ * one 128-byte line per voxel = what one red.global.add.v4 quad of the scatter touches): nsb_compact_transpose converts. */
+size_t nsb_voxel_slots_workspace(long long n_voxels);
+int nsb_voxel_slots(const uint8_t* voxel_mask, long long n_voxels, int32_t* slot_map, int32_t* count,
+                    void* workspace, size_t workspace_bytes, void* stream);
+int nsb_masked_gather(const nsb_grid* grid, const int32_t* slot_map, float* compact, void* stream);        /* compact = val[mask] */
+int nsb_masked_scatter(const nsb_grid* grid, const int32_t* slot_map, const float* compact, void* stream); /* val[mask] = compact */
+/* to_reference != 0: [n][32] -> [32][n] (the reference's val[mask] order); 0: the inverse. */
+int nsb_compact_transpose(const float* src, float* dst, long long n_selected, int to_reference, void* stream);
+
+/* d c2w per keyframe of a bundle-adjustment window (src/Mapper.py:437-467 concatenates per-frame ray blocks):
+ * frame f owns rays [frame_offsets[f], frame_offsets[f+1]); out[f][12] (float32, row-major [3][4]) as nsb_pose_grad. */
+int nsb_pose_grad_frames(const float* dirs, const float* d_rays_o, const float* d_rays_d, const int32_t* frame_offsets,
+                         int n_frames, float* out, void* stream);
 
 /* Points-only decode (Renderer.eval_points, src/utils/Renderer.py:23-61): p f64 [P,3] -> raw f32 [P,4]. */
 int nsb_eval_points(const nsb_render_inputs* in, const double* points, int n_points, float* raw, void* stream);

@@ -42,7 +42,8 @@ class ForwardOutputs(C.Structure):
 class BackwardArgs(C.Structure):
     _fields_ = [("z_vals", C.c_void_p), ("raw", C.c_void_p), ("g_depth", C.c_void_p), ("g_var", C.c_void_p),
                 ("g_rgb", C.c_void_p), ("d_rays_o", C.c_void_p), ("d_rays_d", C.c_void_p),
-                ("d_grid", C.c_void_p * 4), ("d_flat", C.c_void_p * 4), ("workspace", C.c_void_p), ("masks", C.c_void_p)]
+                ("d_grid", C.c_void_p * 4), ("d_flat", C.c_void_p * 4), ("workspace", C.c_void_p), ("masks", C.c_void_p),
+                ("slot_map", C.c_void_p * 4)]
 
 
 class IterationBuffers(C.Structure):
@@ -76,6 +77,12 @@ SYMBOLS = {
     "nsb_mapping_seeds": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_double, C.c_int, _P, _P, _P, _P]),
     "nsb_tracking_seeds_workspace": (C.c_size_t, [C.c_int]),
     "nsb_eval_points": (C.c_int, [C.POINTER(RenderInputs), _P, C.c_int, _P, _P]),
+    "nsb_voxel_slots_workspace": (C.c_size_t, [C.c_longlong]),
+    "nsb_voxel_slots": (C.c_int, [_P, C.c_longlong, _P, _P, _P, C.c_size_t, _P]),
+    "nsb_masked_gather": (C.c_int, [C.POINTER(Grid), _P, _P, _P]),
+    "nsb_masked_scatter": (C.c_int, [C.POINTER(Grid), _P, _P, _P]),
+    "nsb_compact_transpose": (C.c_int, [_P, _P, C.c_longlong, C.c_int, _P]),
+    "nsb_pose_grad_frames": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P]),
 }
 
 _LIB = None

@@ -224,6 +224,114 @@ __global__ void pose_grad_kernel(const float* __restrict__ dirs, const float* __
   for (int k = 0; k < 12; k++) { const double t = block_sum(acc[k], red); if (threadIdx.x == 0) out[k] = t; }
 }
 
+// ---- masked voxel parameterisation (Mapper.py:317-333, :393-401, :511-519) --------------------------------------------
+constexpr int kScanBlock = 1024;
+__global__ void slots_count_kernel(const uint8_t* __restrict__ mask, long long n, int* __restrict__ block_count) {
+  __shared__ int red[32];
+  const long long i = (long long)blockIdx.x * kScanBlock + threadIdx.x;
+  int v = (i < n && mask[i]) ? 1 : 0;
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int t = red[threadIdx.x];
+    for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) block_count[blockIdx.x] = t;
+  }
+}
+// single CTA: exclusive scan of the block counts in place, total -> count[0]
+__global__ void slots_scan_kernel(int* __restrict__ block_count, int n_blocks, int* __restrict__ count) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_blocks; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < n_blocks ? block_count[i] : 0;
+    int inc = v;
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if ((threadIdx.x & 31) >= o) inc += t; }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int t = warp_tot[threadIdx.x];
+      for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, t, o); if (threadIdx.x >= o) t += u; }
+      warp_tot[threadIdx.x] = t;                               // inclusive over warps
+    }
+    __syncthreads();
+    const int before = carry + ((threadIdx.x >> 5) ? warp_tot[(threadIdx.x >> 5) - 1] : 0) + inc - v;
+    if (i < n_blocks) block_count[i] = before;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += warp_tot[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) count[0] = carry;
+}
+__global__ void slots_write_kernel(const uint8_t* __restrict__ mask, long long n, const int* __restrict__ block_base, int32_t* __restrict__ slots) {
+  __shared__ int warp_tot[32];
+  const long long i = (long long)blockIdx.x * kScanBlock + threadIdx.x;
+  const int v = (i < n && mask[i]) ? 1 : 0;
+  const unsigned b = __ballot_sync(0xffffffffu, v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) warp_tot[warp] = __popc(b);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int t = warp_tot[threadIdx.x];
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, t, o); if (threadIdx.x >= o) t += u; }
+    warp_tot[threadIdx.x] = t;
+  }
+  __syncthreads();
+  if (i < n) slots[i] = v ? block_base[blockIdx.x] + (warp ? warp_tot[warp - 1] : 0) + __popc(b & ((1u << lane) - 1u)) : -1;
+}
+// one warp per voxel quad-row: lane -> channel; DIR 0: compact = grid[voxel], 1: grid[voxel] = compact
+template <int DIR>
+__global__ void masked_copy_kernel(nsb_grid g, const int32_t* __restrict__ slots, float* __restrict__ compact) {
+  const long long n = (long long)g.D * g.H * g.W;
+  const int lane = threadIdx.x & 31;
+  for (long long v = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); v < n; v += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const int s = __ldg(slots + v);
+    if (s < 0) continue;
+    const int w = (int)(v % g.W), h = (int)((v / g.W) % g.H), d = (int)(v / ((long long)g.W * g.H));
+    float* cell = const_cast<float*>(g.data) + d * g.stride_d + h * g.stride_h + w * g.stride_w + lane * g.stride_c;
+    if (DIR == 0) compact[(long long)s * 32 + lane] = *cell; else *cell = compact[(long long)s * 32 + lane];
+  }
+}
+__global__ void compact_transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n, int to_ref) {
+  __shared__ float tile[32][33];
+  const long long v0 = (long long)blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;                         // 32 x 8 threads
+  for (int r = ty; r < 32; r += 8) {
+    const long long v = v0 + (to_ref ? r : tx);
+    const int c = to_ref ? tx : r;
+    if (v < n) tile[r][tx] = to_ref ? src[v * 32 + c] : src[(long long)c * n + v];
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const long long v = v0 + (to_ref ? tx : r);
+    const int c = to_ref ? r : tx;
+    if (v < n) { if (to_ref) dst[(long long)c * n + v] = tile[tx][r]; else dst[v * 32 + c] = tile[tx][r]; }
+  }
+}
+
+// d c2w of every keyframe block (one CTA per frame)
+__global__ void pose_grad_frames_kernel(const float* __restrict__ dirs, const float* __restrict__ dro, const float* __restrict__ drd,
+                                        const int32_t* __restrict__ offs, float* __restrict__ out) {
+  __shared__ double red[32];
+  const int lo = offs[blockIdx.x], hi = offs[blockIdx.x + 1];
+  double acc[12];
+#pragma unroll
+  for (int k = 0; k < 12; k++) acc[k] = 0.0;
+  for (int r = lo + threadIdx.x; r < hi; r += blockDim.x) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const double g = (double)drd[3 * r + i];
+#pragma unroll
+      for (int j = 0; j < 3; j++) acc[4 * i + j] += g * (double)dirs[3 * r + j];
+      acc[4 * i + 3] += (double)dro[3 * r + i];
+    }
+  }
+  for (int k = 0; k < 12; k++) { const double t = block_sum(acc[k], red); if (threadIdx.x == 0) out[12 * blockIdx.x + k] = (float)t; }
+}
+
 }  // namespace nsb
 
 using namespace nsb;
@@ -232,6 +340,48 @@ extern "C" int nsb_pose_grad(const float* dirs, const float* d_rays_o, const flo
   if (n < 0 || !d_c2w || (n > 0 && (!dirs || !d_rays_o || !d_rays_d))) { set_error("pose_grad: bad arguments"); return NSB_ERR_ARG; }
   pose_grad_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(dirs, d_rays_o, d_rays_d, n, d_c2w);
   return check_cuda(cudaGetLastError(), "pose_grad launch");
+}
+
+extern "C" size_t nsb_voxel_slots_workspace(long long n_voxels) {
+  return n_voxels <= 0 ? 16 : (size_t)((n_voxels + kScanBlock - 1) / kScanBlock) * sizeof(int) + 16;
+}
+extern "C" int nsb_voxel_slots(const uint8_t* voxel_mask, long long n_voxels, int32_t* slot_map, int32_t* count,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  if (n_voxels < 0 || !count || (n_voxels > 0 && (!voxel_mask || !slot_map || !workspace))) { set_error("voxel_slots: bad arguments"); return NSB_ERR_ARG; }
+  if (workspace_bytes < nsb_voxel_slots_workspace(n_voxels)) { set_error("voxel_slots: workspace too small"); return NSB_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_voxels == 0) return check_cuda(cudaMemsetAsync(count, 0, sizeof(int32_t), st), "voxel_slots memset");
+  const int nb = (int)((n_voxels + kScanBlock - 1) / kScanBlock);
+  int* bc = static_cast<int*>(workspace);
+  slots_count_kernel<<<nb, kScanBlock, 0, st>>>(voxel_mask, n_voxels, bc);
+  slots_scan_kernel<<<1, 1024, 0, st>>>(bc, nb, count);
+  slots_write_kernel<<<nb, kScanBlock, 0, st>>>(voxel_mask, n_voxels, bc, slot_map);
+  return check_cuda(cudaGetLastError(), "voxel_slots launch");
+}
+static int masked_copy(const nsb_grid* g, const int32_t* slots, float* compact, int dir, void* stream) {
+  if (!g || !g->data || !slots || !compact || g->D <= 0 || g->H <= 0 || g->W <= 0) { set_error("masked gather/scatter: bad arguments"); return NSB_ERR_ARG; }
+  const long long n = (long long)g->D * g->H * g->W;
+  const int blocks = (int)((n + 7) / 8 < 148 * 16 ? (n + 7) / 8 : 148 * 16);
+  if (dir == 0) masked_copy_kernel<0><<<blocks, 256, 0, (cudaStream_t)stream>>>(*g, slots, compact);
+  else masked_copy_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(*g, slots, compact);
+  return check_cuda(cudaGetLastError(), "masked copy launch");
+}
+extern "C" int nsb_masked_gather(const nsb_grid* grid, const int32_t* slot_map, float* compact, void* stream) { return masked_copy(grid, slot_map, compact, 0, stream); }
+extern "C" int nsb_masked_scatter(const nsb_grid* grid, const int32_t* slot_map, const float* compact, void* stream) {
+  return masked_copy(grid, slot_map, const_cast<float*>(compact), 1, stream);
+}
+extern "C" int nsb_compact_transpose(const float* src, float* dst, long long n_selected, int to_reference, void* stream) {
+  if (n_selected < 0 || (n_selected > 0 && (!src || !dst))) { set_error("compact_transpose: bad arguments"); return NSB_ERR_ARG; }
+  if (n_selected == 0) return NSB_OK;
+  compact_transpose_kernel<<<(unsigned)((n_selected + 31) / 32), 256, 0, (cudaStream_t)stream>>>(src, dst, n_selected, to_reference);
+  return check_cuda(cudaGetLastError(), "compact_transpose launch");
+}
+extern "C" int nsb_pose_grad_frames(const float* dirs, const float* d_rays_o, const float* d_rays_d, const int32_t* frame_offsets,
+                                    int n_frames, float* out, void* stream) {
+  if (n_frames < 0 || (n_frames > 0 && (!dirs || !d_rays_o || !d_rays_d || !frame_offsets || !out))) { set_error("pose_grad_frames: bad arguments"); return NSB_ERR_ARG; }
+  if (n_frames == 0) return NSB_OK;
+  pose_grad_frames_kernel<<<n_frames, 256, 0, (cudaStream_t)stream>>>(dirs, d_rays_o, d_rays_d, frame_offsets, out);
+  return check_cuda(cudaGetLastError(), "pose_grad_frames launch");
 }
 
 extern "C" int nsb_version(void) { return NSB_VERSION; }

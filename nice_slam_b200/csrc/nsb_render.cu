@@ -58,12 +58,27 @@ __device__ __forceinline__ void gather_chunk(const nsb_grid& g, float* __restric
   }
 }
 
+// w * dc -> gradient of voxel (cx,cy,cz), channels [4q,4q+4): dense buffer with the grid's strides, or -- masked voxel
+// parameterisation (Mapper.py:317-333) -- the compact [n_selected][32] buffer through the voxel -> slot table
+__device__ __forceinline__ void voxel_grad_add(const nsb_grid& g, float* __restrict__ dgrid, const int32_t* __restrict__ slots, long long off,
+                                               int cx, int cy, int cz, int q, bool fast, float w, const float dc[4]) {
+  if (slots != nullptr) {
+    const int s = __ldg(slots + ((long long)cz * g.H + cy) * g.W + cx);
+    if (s >= 0) red_add_v4(dgrid + (long long)s * 32 + 4 * q, w * dc[0], w * dc[1], w * dc[2], w * dc[3]);
+  } else if (fast) {
+    red_add_v4(dgrid + off + 4 * q, w * dc[0], w * dc[1], w * dc[2], w * dc[3]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < 4; c++) atomicAdd(dgrid + off + (long long)(4 * q + c) * g.stride_c, w * dc[c]);
+  }
+}
+
 // Backward of gather_chunk: rows [row0,row0+32) hold dL/dc.  Scatter-adds w_k * dc into dgrid (if non-null)
 // and returns through gx (valid in lanes with (lane&7)==0, for point it*4 + lane>>3 of pass `it`) the gradient
 // w.r.t. the normalised coordinate (grid_sampler_3d_backward incl. the clip multiplier, GridSampler.h:66-82).
 template <typename F>
-__device__ __forceinline__ void scatter_chunk(const nsb_grid& g, float* __restrict__ dgrid, const float* __restrict__ act,
-                                              int row0, const float xn[3], int lane, F&& emit) {
+__device__ __forceinline__ void scatter_chunk(const nsb_grid& g, float* __restrict__ dgrid, const int32_t* __restrict__ slots,
+                                              const float* __restrict__ act, int row0, const float xn[3], int lane, F&& emit) {
   const bool fast = grid_fast(g);
   const int q = lane & 7;
 #pragma unroll 1
@@ -91,12 +106,9 @@ __device__ __forceinline__ void scatter_chunk(const nsb_grid& g, float* __restri
         const float4 v = vv[k];
         const float dot = v.x * dc[0] + v.y * dc[1] + v.z * dc[2] + v.w * dc[3];
         if (dgrid != nullptr) {
-          const float w = tri_weight(t, k);
-          if (fast) red_add_v4(dgrid + offs[k] + 4 * q, w * dc[0], w * dc[1], w * dc[2], w * dc[3]);
-          else {
-#pragma unroll
-            for (int c = 0; c < 4; c++) atomicAdd(dgrid + offs[k] + (long long)(4 * q + c) * g.stride_c, w * dc[c]);
-          }
+          int cx, cy, cz;
+          tri_corner(t, k, g.W, g.H, g.D, cx, cy, cz);
+          voxel_grad_add(g, dgrid, slots, offs[k], cx, cy, cz, q, fast, tri_weight(t, k), dc);
         }
         const float wx = (k & 1) ? t.w1[0] : t.w0[0], wy = (k & 2) ? t.w1[1] : t.w0[1], wz = (k & 4) ? t.w1[2] : t.w0[2];
         gi[0] += ((k & 1) ? 1.f : -1.f) * wy * wz * dot;
@@ -493,7 +505,7 @@ __device__ __forceinline__ void chunk_backward(const KParams& P, const Smem& sm,
   __syncwarp();
   const double* bb = lv == 0 ? P.in.coarse_bound : P.in.bound;
   // rows of padding points (lp >= Pb) carry zero gradients because their g_out is zero
-  scatter_chunk(P.in.grid[lv], P.bw.d_grid[lv], act, R_C, xn, L.lane, [&](int pt, const float gx[3]) {
+  scatter_chunk(P.in.grid[lv], P.bw.d_grid[lv], P.bw.slot_map[lv], act, R_C, xn, L.lane, [&](int pt, const float gx[3]) {
     const int l2 = chunk * kChunk + pt;
     if (l2 < Pb) {
 #pragma unroll
@@ -667,7 +679,7 @@ __global__ void __launch_bounds__(128, 1) render_bwd_tc_kernel(const __grid_cons
       const double* bb = lv == 0 ? P.in.coarse_bound : P.in.bound;
       const double sc[3] = {2.0 / (bb[1] - bb[0]), 2.0 / (bb[3] - bb[2]), 2.0 / (bb[5] - bb[4])};      // d(normalised)/dp, common.py:280-282
       const float* xn = lv == 0 ? G.xnc : G.xn;
-      tc::scatter_rows(P.in.grid[lv], P.bw.d_grid[lv], t.x, d.cd, xn, warp, lane, [&](int row, const float gx[3]) {
+      tc::scatter_rows(P.in.grid[lv], P.bw.d_grid[lv], P.bw.slot_map[lv], t.x, d.cd, xn, warp, lane, [&](int row, const float gx[3]) {
         const int l2 = tile * tc::TM + row;
         if (l2 < Pb) {
 #pragma unroll
@@ -842,6 +854,11 @@ extern "C" int nsb_render_backward(const nsb_render_inputs* in, const nsb_backwa
   if (K.S > NSB_MAX_SAMPLES) { set_error("n_samples+n_surface = %d exceeds %d", K.S, NSB_MAX_SAMPLES); return NSB_ERR_UNSUPPORTED; }
   cudaStream_t st = (cudaStream_t)stream;
   bool any_w = false;
+  for (int l = 0; l < 4; l++) {
+    if (bw->slot_map[l] != nullptr && bw->d_grid[l] != nullptr && (reinterpret_cast<uintptr_t>(bw->d_grid[l]) & 15) != 0) {
+      set_error("compact d_grid[%d] must be 16-byte aligned", l); return NSB_ERR_ARG;
+    }
+  }
   for (int i = 0; i < K.n_dec; i++) {
     const int l = K.dec[i];
     if (bw->d_flat[l] != nullptr) {

@@ -435,7 +435,8 @@ __device__ __forceinline__ void tile_backward(const KParams& P, const TcSmem& t,
 // Backward of gather_rows for the warp's 32 rows: dc rows come from `dcs` ([128][cd] fp32).  Scatter-adds into dgrid (if non-null)
 // and hands the normalised-coordinate gradient of each point to emit(row, gx).
 template <typename F>
-__device__ __forceinline__ void scatter_rows(const nsb_grid& g, float* __restrict__ dgrid, const float* __restrict__ dcs, int cd,
+__device__ __forceinline__ void scatter_rows(const nsb_grid& g, float* __restrict__ dgrid, const int32_t* __restrict__ slots,
+                                             const float* __restrict__ dcs, int cd,
                                              const float xn[3], int warp, int lane, F&& emit) {
   const bool fast = grid_fast(g);
   const int q = lane & 7;
@@ -464,12 +465,9 @@ __device__ __forceinline__ void scatter_rows(const nsb_grid& g, float* __restric
         const float4 v = vv[k];
         const float dot = v.x * dc[0] + v.y * dc[1] + v.z * dc[2] + v.w * dc[3];
         if (dgrid != nullptr) {
-          const float w = tri_weight(t, k);
-          if (fast) red_add_v4(dgrid + offs[k] + 4 * q, w * dc[0], w * dc[1], w * dc[2], w * dc[3]);
-          else {
-#pragma unroll
-            for (int c = 0; c < 4; c++) atomicAdd(dgrid + offs[k] + (long long)(4 * q + c) * g.stride_c, w * dc[c]);
-          }
+          int cx, cy, cz;
+          tri_corner(t, k, g.W, g.H, g.D, cx, cy, cz);
+          voxel_grad_add(g, dgrid, slots, offs[k], cx, cy, cz, q, fast, tri_weight(t, k), dc);
         }
         const float wx = (k & 1) ? t.w1[0] : t.w0[0], wy = (k & 2) ? t.w1[1] : t.w0[1], wz = (k & 4) ? t.w1[2] : t.w0[2];
         gi[0] += ((k & 1) ? 1.f : -1.f) * wy * wz * dot;

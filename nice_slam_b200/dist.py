@@ -54,43 +54,92 @@ def reduce_sum(packed):
 
 class ShardedTrackingIteration:
     """One tracking iteration on this rank's shard of a global ray batch (split-phase: the exchanges sit between the
-    kernels).  With world_size == 1 it degenerates to the same kernels without collectives."""
+    kernels).  With world_size == 1 it degenerates to the same kernels without collectives.
+
+    prepare() builds every ctypes structure once (pointers are fixed: the context's own input block); enqueue() then
+    only issues the kernels and the three collectives, so it can be replayed from a CUDA graph (NCCL collectives are
+    graph-capturable) -- build_graph() returns None if capture is not possible and the caller falls back to enqueue()."""
 
     def __init__(self, ctx):
         self.ctx = ctx                      # steps.IterationContext(kind='track')
         dev = ctx.dev
         self.res = torch.empty(ctx.n, dtype=torch.float64, device=dev)
+        self.allres = torch.empty(ctx.n * world()[1], dtype=torch.float64, device=dev)
         self.packed = torch.zeros(13, dtype=torch.float64, device=dev)      # [loss | d_c2w(12)]
+        self._p = None
 
-    def run(self, c, decoders, rays_o, rays_d, dirs, gt_depth, gt_color, w_color=0.5, handle_dynamic=True, use_color=True):
+    def prepare(self, c, decoders, dirs, w_color=0.5, handle_dynamic=True, use_color=True):
+        from . import _lib
+        from .renderer import _inputs, _linspaces
+        x = self.ctx
+        ro, rd, gd, gc = x.device_views()
+        call, grids, _ = x.r._call(c, decoders, x.stage, gd, x.dev)
+        t_u, t_s = _linspaces(x.r.N_samples, x.r.N_surface, x.dev)
+        inp = _inputs(call, ro, rd, x.depth_max, t_u, t_s, [g.detach() for g in grids])
+        fo = _lib.ForwardOutputs(x.depth.data_ptr(), x.var.data_ptr(), x.rgb.data_ptr(), x.z_vals.data_ptr(), x.raw.data_ptr(), None,
+                                 x.masks.data_ptr())
+        bw = x._grads(c)
+        bw.z_vals, bw.raw, bw.g_depth, bw.g_rgb, bw.masks = (x.z_vals.data_ptr(), x.raw.data_ptr(), x.g_depth.data_ptr(),
+                                                              x.g_rgb.data_ptr(), x.masks.data_ptr())
+        self._p = dict(call=call, grids=grids, lin=(t_u, t_s), inp=inp, fo=fo, bw=bw, dirs=dirs, gd=gd, gc=gc,
+                       w_color=w_color, hd=int(handle_dynamic), uc=int(use_color))
+
+    def enqueue(self):
         import ctypes as C
         from . import _lib
-        from .renderer import _VP, _inputs, _linspaces, _stream
+        from .renderer import _VP, _stream
         L = _lib.lib()
-        x = self.ctx
+        x, p = self.ctx, self._p
         n = x.n
-        call, grids, _ = x.r._call(c, decoders, x.stage, gt_depth, x.dev)
-        t_u, t_s = _linspaces(x.r.N_samples, x.r.N_surface, x.dev)
-        _lib.check(L.nsb_batch_max_depth(_VP(gt_depth.data_ptr()), n, _VP(x.depth_max.data_ptr()), _stream()), "nsb_batch_max_depth")
+        st = _stream()
+        _lib.check(L.nsb_batch_max_depth(_VP(p["gd"].data_ptr()), n, _VP(x.depth_max.data_ptr()), st), "nsb_batch_max_depth")
         exchange_depth_max(x.depth_max)
-        inp = _inputs(call, rays_o, rays_d, x.depth_max, t_u, t_s, [g.detach() for g in grids])
-        fo = _lib.ForwardOutputs(x.depth.data_ptr(), x.var.data_ptr(), x.rgb.data_ptr(), x.z_vals.data_ptr(), x.raw.data_ptr(), None, x.masks.data_ptr())
-        _lib.check(L.nsb_render_forward(C.byref(inp), C.byref(fo), _stream()), "nsb_render_forward")
+        _lib.check(L.nsb_render_forward(C.byref(p["inp"]), C.byref(p["fo"]), st), "nsb_render_forward")
         pool, n_pool = None, 0
-        if handle_dynamic and world()[1] > 1:
-            _lib.check(L.nsb_tracking_residuals(_VP(x.depth.data_ptr()), _VP(x.var.data_ptr()), _VP(gt_depth.data_ptr()), n,
-                                                _VP(self.res.data_ptr()), _stream()), "nsb_tracking_residuals")
-            allres = gather_residuals(self.res)
-            pool, n_pool = _VP(allres.data_ptr()), allres.numel()
-        _lib.check(L.nsb_tracking_seeds(_VP(x.depth.data_ptr()), _VP(x.var.data_ptr()), _VP(x.rgb.data_ptr()), _VP(gt_depth.data_ptr()),
-                                        _VP(gt_color.data_ptr()), n, w_color, int(handle_dynamic), int(use_color), pool, n_pool,
-                                        _VP(x.g_depth.data_ptr()), _VP(x.g_rgb.data_ptr()), _VP(x.loss.data_ptr()),
-                                        _VP(x.ws.data_ptr()), L.nsb_tracking_seeds_workspace(n), _stream()), "nsb_tracking_seeds")
-        bw = x._grads(c)
-        bw.z_vals, bw.raw, bw.g_depth, bw.g_rgb, bw.masks = x.z_vals.data_ptr(), x.raw.data_ptr(), x.g_depth.data_ptr(), x.g_rgb.data_ptr(), x.masks.data_ptr()
-        _lib.check(L.nsb_render_backward(C.byref(inp), C.byref(bw), _stream()), "nsb_render_backward")
-        _lib.check(L.nsb_pose_grad(_VP(dirs.data_ptr()), _VP(x.d_rays_o.data_ptr()), _VP(x.d_rays_d.data_ptr()), n,
-                                   _VP(self.packed.data_ptr() + 8), _stream()), "nsb_pose_grad")
-        self.packed[:1].copy_(x.loss)
-        reduce_sum(self.packed)
-        return self.packed                  # [global loss | global d_c2w]
+        if p["hd"] and world()[1] > 1:
+            _lib.check(L.nsb_tracking_residuals(_VP(x.depth.data_ptr()), _VP(x.var.data_ptr()), _VP(p["gd"].data_ptr()), n,
+                                                _VP(self.res.data_ptr()), st), "nsb_tracking_residuals")
+            dist.all_gather_into_tensor(self.allres, self.res)
+            pool, n_pool = _VP(self.allres.data_ptr()), self.allres.numel()
+        _lib.check(L.nsb_tracking_seeds(_VP(x.depth.data_ptr()), _VP(x.var.data_ptr()), _VP(x.rgb.data_ptr()), _VP(p["gd"].data_ptr()),
+                                        _VP(p["gc"].data_ptr()), n, p["w_color"], p["hd"], p["uc"], pool, n_pool,
+                                        _VP(x.g_depth.data_ptr()), _VP(x.g_rgb.data_ptr()), _VP(self.packed.data_ptr()),
+                                        _VP(x.ws.data_ptr()), L.nsb_tracking_seeds_workspace(n), st), "nsb_tracking_seeds")
+        _lib.check(L.nsb_render_backward(C.byref(p["inp"]), C.byref(p["bw"]), st), "nsb_render_backward")
+        _lib.check(L.nsb_pose_grad(_VP(p["dirs"].data_ptr()), _VP(x.d_rays_o.data_ptr()), _VP(x.d_rays_d.data_ptr()), n,
+                                   _VP(self.packed.data_ptr() + 8), st), "nsb_pose_grad")
+        reduce_sum(self.packed)             # [global loss | global d_c2w]  (the seeds kernel wrote the local loss into packed[0])
+        return self.packed
+
+    def build_graph(self, host_io=False):
+        """CUDA graph of enqueue() (and, with host_io, of the pinned-host copies around it); None if capture fails."""
+        x = self.ctx
+
+        def body():
+            if host_io:
+                x.d_in32.copy_(x.h_in32, non_blocking=True)
+                x.gt_color.copy_(x.h_col, non_blocking=True)
+            self.enqueue()
+            if host_io:
+                x.h_pose13.copy_(self.packed, non_blocking=True)
+        try:
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                body(); body()
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
+            return g
+        except Exception:
+            torch.cuda.synchronize()
+            return None
+
+    def run(self, c, decoders, rays_o, rays_d, dirs, gt_depth, gt_color, w_color=0.5, handle_dynamic=True, use_color=True):
+        """Convenience: copy the shard into the context's input block, prepare and enqueue once."""
+        self.ctx.load_device_inputs(rays_o, rays_d, gt_depth, gt_color)
+        self.prepare(c, decoders, dirs, w_color, handle_dynamic, use_color)
+        return self.enqueue()

@@ -65,6 +65,7 @@ class IterationContext:
         self.h_out = torch.empty(n * 6, dtype=f32).pin_memory() if dev.type == "cuda" else None
         self.h_loss = torch.empty(1, dtype=f64).pin_memory() if dev.type == "cuda" else None
         self.h_pose = torch.empty(3, 4, dtype=f64).pin_memory() if dev.type == "cuda" else None
+        self.h_pose13 = torch.empty(13, dtype=f64).pin_memory() if dev.type == "cuda" else None
         self.h2d_bytes = n * 7 * 4 + self.gt_color.numel() * self.gt_color.element_size()
         self.d2h_bytes = n * 6 * 4 + 8
 

@@ -267,3 +267,84 @@ def test_large_batch_properties():
     gab = torch.autograd.grad((dd * s1).sum() + (cc * s2).sum(), (r1, r2))
     for x, y, zz in zip(ga, gb, gab):
         assert rel(x + y, zz) < 1e-5
+
+
+# ------------------------------------------------------------------------------------ fused iterations (what bench.py times)
+def _flat_named(level, flat):
+    from nice_slam_b200 import _lib
+    return {nm: flat[off:off + cnt] for nm, off, cnt in _lib.flat_layout(level)}
+
+
+@pytest.mark.parametrize("n_rays", [200, 37])
+def test_fused_tracking_iteration_matches_oracle(n_rays):
+    """nsb_tracking_iteration (one C call: batch max, forward, median-gated loss seeds, backward) + nsb_pose_grad, eager,
+    replayed from a CUDA graph, and through the split-phase sharded iteration at world size 1."""
+    from nice_slam_b200.dist import ShardedTrackingIteration
+    from nice_slam_b200.steps import IterationContext
+    sc = su.load_scenes()["room0"]
+    grids, dec_state = su.make_grids(sc, "soft"), su.load_decoders("soft")
+    renderer, c, dec = make_renderer(sc, grids, dec_state, DEV)
+    bound = su.scene_bound(sc)
+    ro, rd, gd, gc = su.make_rays(sc, n_rays, seed=5 + n_rays)
+    out = tp.iteration("track", grids, dec_state, ro, rd, gd, gc.double(), "color", bound)
+    dirs = torch.randn(n_rays, 3, generator=torch.Generator().manual_seed(1))
+    want_pose = torch.cat([(out["d_rays_d"].double()[:, :, None] * dirs.double()[:, None, :]).sum(0),
+                           out["d_rays_o"].double().sum(0)[:, None]], 1)             # d c2w[:3,:3] | d c2w[:3,3]
+    ctx = IterationContext(renderer, n_rays, "color", DEV, kind="track")
+    dev_in = [t.to(DEV) for t in (ro, rd, gd, gc.double())]
+    dirs_d = dirs.to(DEV)
+
+    def check(loss, d_o, d_d, pose):
+        assert abs(float(loss) - float(out["loss"])) < TOL * abs(float(out["loss"]))
+        assert rel(d_o, out["d_rays_o"]) < TOL and rel(d_d, out["d_rays_d"]) < TOL
+        assert rel(pose, want_pose) < TOL
+
+    ctx.run(c, dec, *dev_in)
+    check(ctx.loss, ctx.d_rays_o, ctx.d_rays_d, ctx.pose_grad(dirs_d))
+    assert rel(ctx.depth, out["depth"]) < TOL and rel(ctx.rgb, out["color"]) < TOL and rel(ctx.var, out["var"]) < TOL
+    # CUDA graph replay (device inputs, then pinned-host inputs)
+    ctx.load_device_inputs(*dev_in)
+    g = ctx.build_graph(c, dec, dirs=dirs_d)
+    ctx.loss.zero_(); ctx.d_out.zero_(); ctx.d_c2w.zero_()
+    g.replay(); torch.cuda.synchronize()
+    check(ctx.loss, ctx.d_rays_o, ctx.d_rays_d, ctx.d_c2w)
+    ctx.stage_host_inputs(ro, rd, gd, gc.double())
+    loss, d_rays = ctx.run_host(c, dec)
+    check(loss, d_rays[0], d_rays[1], ctx.pose_grad(dirs_d))
+    # split-phase sharded iteration without a process group == the fused one
+    sh = ShardedTrackingIteration(ctx)
+    packed = sh.run(c, dec, *dev_in[:2], dirs_d, *dev_in[2:]).clone()
+    check(packed[0], ctx.d_rays_o, ctx.d_rays_d, packed[1:].view(3, 4))
+    gs = sh.build_graph()
+    assert gs is not None
+    sh.packed.zero_()
+    gs.replay(); torch.cuda.synchronize()
+    check(sh.packed[0], ctx.d_rays_o, ctx.d_rays_d, sh.packed[1:].view(3, 4))
+
+
+@pytest.mark.parametrize("stage", ["middle", "color"])
+def test_fused_mapping_iteration_matches_oracle(stage):
+    """nsb_mapping_iteration: dense voxel gradients of the stage's grids + (stage color) colour-decoder gradients."""
+    from nice_slam_b200.steps import IterationContext
+    sc = su.load_scenes()["room0"]
+    grids, dec_state = su.make_grids(sc, "soft"), su.load_decoders("soft")
+    renderer, c, dec = make_renderer(sc, grids, dec_state, DEV)
+    bound = su.scene_bound(sc)
+    n_rays = 300
+    ro, rd, gd, gc = su.make_rays(sc, n_rays, seed=99)
+    gg = tuple("grid_" + l for l in LV[stage])
+    gdec = ("color",) if stage == "color" else ()
+    out = tp.iteration("map", grids, dec_state, ro, rd, gd, gc.float(), stage, bound, grad_grids=gg, grad_decoders=gdec)
+    ctx = IterationContext(renderer, n_rays, stage, DEV, kind="map", grad_grids=gg, grad_decoders=gdec)
+    for rep in range(2):                            # second run: the accumulation buffers are re-zeroed
+        ctx.run(c, dec, ro.to(DEV), rd.to(DEV), gd.to(DEV), gc.float().to(DEV))
+    assert abs(float(ctx.loss) - float(out["loss"])) < TOL * abs(float(out["loss"]))
+    assert rel(ctx.d_rays_o, out["d_rays_o"]) < TOL and rel(ctx.d_rays_d, out["d_rays_d"]) < TOL
+    for k in gg:
+        assert rel(ctx.d_grid[k], out["d_" + k]) < TOL, k
+    for lvl in gdec:
+        from nice_slam_b200._lib import LEVELS
+        mine = _flat_named(LEVELS.index(lvl), ctx.d_flat[lvl])
+        for k, v in out["d_dec"][lvl].items():
+            if k in mine:
+                assert rel(mine[k], v.reshape(-1)) < TOL, (lvl, k)
