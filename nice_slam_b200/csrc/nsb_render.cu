@@ -403,10 +403,11 @@ __global__ void __launch_bounds__(256, 1) render_fwd_kernel(const __grid_constan
 namespace nsb {
 
 // ------------------------------------------------------------------------------------------------
-// forward kernel, tensor-core (tcgen05, 3xTF32) decoders: 128 threads, one thread per point of a 128-point tile
-__global__ void __launch_bounds__(128, 1) render_fwd_tc_kernel(const __grid_constant__ KParams P) {
+// forward kernel, tensor-core (tcgen05, 3xTF32) decoders: 512 threads = four per point of a 128-point tile (nsb_tc.cuh)
+__global__ void __launch_bounds__(tc::kThreads, 1) render_fwd_tc_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];       // tiles need 16-byte alignment only (no-swizzle descriptors)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = threadIdx.x & (tc::TM - 1), cg = threadIdx.x >> 7;
   tc::TcSmem t;
   tc::tc_carve(smem_raw, t);
   Smem sm;
@@ -428,7 +429,7 @@ __global__ void __launch_bounds__(128, 1) render_fwd_tc_kernel(const __grid_cons
   bool prefetched = false;
   const int ntiles = (Pb + tc::TM - 1) / tc::TM;
   for (int tile = 0; tile < ntiles; tile++) {
-    const int lp = tile * tc::TM + threadIdx.x;
+    const int lp = tile * tc::TM + row;
     const int lpc = lp < Pb ? lp : Pb - 1;
     PointGeom G;
     if (P.points != nullptr) {
@@ -450,14 +451,14 @@ __global__ void __launch_bounds__(128, 1) render_fwd_tc_kernel(const __grid_cons
       const int next_lv = qd + 1 < P.n_dec ? P.dec[qd + 1] : (tile + 1 < ntiles ? P.dec[0] : -1);
       tc::tile_forward<false>(P, t, d, lv, G, tmem, parity, wparity, out, gm, prefetched, next_lv);
       if (lv == 3) { c0 = out[0]; c1 = out[1]; c2 = out[2]; } else occ += out[0];
-      if (qd == 0 && lp < Pb && P.fo.corner_idx != nullptr) {
+      if (qd == 0 && cg == 0 && lp < Pb && P.fo.corner_idx != nullptr) {
         const nsb_grid& g = P.in.grid[lv];
         const Tri tr = make_tri(lv == 0 ? G.xnc : G.xn, g.W, g.H, g.D);
         const long long gp = ((long long)blockIdx.x * P.rays_per_block) * P.S + lp;
         P.fo.corner_idx[3 * gp] = tr.i0[0]; P.fo.corner_idx[3 * gp + 1] = tr.i0[1]; P.fo.corner_idx[3 * gp + 2] = tr.i0[2];
       }
     }
-    if (lp < Pb) {
+    if (cg == 0 && lp < Pb) {
       *reinterpret_cast<float4*>(sm.raw + 4 * lp) = make_float4(c0, c1, c2, occ);
       sm.inb[lp] = (unsigned char)G.inb;
     }
@@ -465,7 +466,7 @@ __global__ void __launch_bounds__(128, 1) render_fwd_tc_kernel(const __grid_cons
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tc::kTmemCols) : "memory");
-  fwd_composite_store(P, sm, b, warp, 4, lane);
+  fwd_composite_store(P, sm, b, warp, tc::kThreads / 32, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -623,9 +624,10 @@ __global__ void __launch_bounds__(256, 1) render_bwd_kernel(const __grid_constan
 // ------------------------------------------------------------------------------------------------
 // backward kernel, tensor-core decoders (input gradients: rays + grid voxels).  Decoder-weight gradients stay on the
 // SIMT kernel for now (host dispatch).
-__global__ void __launch_bounds__(128, 1) render_bwd_tc_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(tc::kThreads, 1) render_bwd_tc_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = threadIdx.x & (tc::TM - 1);
   tc::TcSmem t;
   tc::tc_carve(smem_raw, t);
   Smem sm;
@@ -639,7 +641,7 @@ __global__ void __launch_bounds__(128, 1) render_bwd_tc_kernel(const __grid_cons
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (threadIdx.x == 0) { mbar_init(t.bar, 1); mbar_init(t.wbar, 1); mbar_fence_init(); }
-  bwd_prologue(P, sm, r0, nr, Pb, warp, 4, lane, gC);
+  bwd_prologue(P, sm, r0, nr, Pb, warp, tc::kThreads / 32, lane, gC);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -649,7 +651,7 @@ __global__ void __launch_bounds__(128, 1) render_bwd_tc_kernel(const __grid_cons
   bool prefetched = false;
   const int ntiles = (Pb + tc::TM - 1) / tc::TM;
   for (int tile = 0; tile < ntiles; tile++) {
-    const int lp = tile * tc::TM + threadIdx.x;
+    const int lp = tile * tc::TM + row;
     const int lpc = lp < Pb ? lp : Pb - 1;
     const int ray = lpc / P.S;
     PointGeom G;
@@ -668,10 +670,8 @@ __global__ void __launch_bounds__(128, 1) render_bwd_tc_kernel(const __grid_cons
         if (lv == 3) { const float w = sm.wgt[lp]; g_out[0] = w * gC[3 * ray]; g_out[1] = w * gC[3 * ray + 1]; g_out[2] = w * gC[3 * ray + 2]; }
         else g_out[0] = sm.gocc[lp];
       }
-      float dpe[3];
-      tc::tile_backward(P, t, d, lv, G, tmem, parity, wparity, g_out, dpe, gm, prefetched);
-      if (lp < Pb) { sm.dp[3 * lp] += (double)dpe[0]; sm.dp[3 * lp + 1] += (double)dpe[1]; sm.dp[3 * lp + 2] += (double)dpe[2]; }
-      __syncthreads();                                           // dL/dc rows + the dp updates above are visible; the packed image is dead
+      tc::tile_backward(P, t, d, lv, G, tmem, parity, wparity, g_out, gm, prefetched);
+      __syncthreads();                                           // dL/dc rows + the embedding partials are visible; the packed image is dead
       if (gm != nullptr) {                                       // prefetch the next decoder's image under the scatter below
         const int next_lv = qd + 1 < P.n_dec ? P.dec[qd + 1] : (tile + 1 < ntiles ? P.dec[0] : -1);
         if (next_lv >= 0) { if (threadIdx.x == 0) tc::issue_decoder_tma(P, t, next_lv); prefetched = true; }
@@ -679,11 +679,14 @@ __global__ void __launch_bounds__(128, 1) render_bwd_tc_kernel(const __grid_cons
       const double* bb = lv == 0 ? P.in.coarse_bound : P.in.bound;
       const double sc[3] = {2.0 / (bb[1] - bb[0]), 2.0 / (bb[3] - bb[2]), 2.0 / (bb[5] - bb[4])};      // d(normalised)/dp, common.py:280-282
       const float* xn = lv == 0 ? G.xnc : G.xn;
-      tc::scatter_rows(P.in.grid[lv], P.bw.d_grid[lv], P.bw.slot_map[lv], t.x, d.cd, xn, warp, lane, [&](int row, const float gx[3]) {
-        const int l2 = tile * tc::TM + row;
+      // one writer per point: dL/dp = embedding chain (partials of tile_backward) + trilinear-coordinate chain of this grid
+      tc::scatter_rows(P.in.grid[lv], P.bw.d_grid[lv], P.bw.slot_map[lv], t.x, d.cd, xn, warp, lane, [&](int prow, const float gx[3]) {
+        const int l2 = tile * tc::TM + prow;
         if (l2 < Pb) {
+          float dpe[3];
+          tc::dpe_sum(t, prow, dpe);
 #pragma unroll
-          for (int a = 0; a < 3; a++) sm.dp[3 * l2 + a] += (double)gx[a] * sc[a];
+          for (int a = 0; a < 3; a++) sm.dp[3 * l2 + a] += (double)dpe[a] + (double)gx[a] * sc[a];
         }
       });
     }
@@ -808,7 +811,7 @@ extern "C" int nsb_render_forward(const nsb_render_inputs* in, const nsb_forward
     const int grid_tc = (in->n_rays + K.rays_per_block - 1) / K.rays_per_block;
     const size_t smem_tc = tc_total_smem(K.max_pts, K.max_rays);
     if (smem_tc > kSmemCap) { set_error("shared-memory budget exceeded (%zu bytes)", smem_tc); return NSB_ERR_UNSUPPORTED; }
-    render_fwd_tc_kernel<<<grid_tc, 128, smem_tc, (cudaStream_t)stream>>>(K);
+    render_fwd_tc_kernel<<<grid_tc, tc::kThreads, smem_tc, (cudaStream_t)stream>>>(K);
     return check_cuda(cudaGetLastError(), "render_fwd_tc_kernel launch");
   }
   render_fwd_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(K);
@@ -833,7 +836,7 @@ extern "C" int nsb_eval_points(const nsb_render_inputs* in, const double* points
   K.rays_per_block = ppb; K.max_pts = ppb; K.max_rays = 1;
   const int grid = (n_points + ppb - 1) / ppb;
   if (g_mlp_backend != 1) {
-    render_fwd_tc_kernel<<<grid, 128, tc_total_smem(K.max_pts, K.max_rays), (cudaStream_t)stream>>>(K);
+    render_fwd_tc_kernel<<<grid, tc::kThreads, tc_total_smem(K.max_pts, K.max_rays), (cudaStream_t)stream>>>(K);
     return check_cuda(cudaGetLastError(), "render_fwd_tc_kernel(points) launch");
   }
   render_fwd_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(K);
@@ -881,7 +884,7 @@ extern "C" int nsb_render_backward(const nsb_render_inputs* in, const nsb_backwa
     const int grid_tc = (in->n_rays + K.rays_per_block - 1) / K.rays_per_block;
     const size_t smem_tc = tc_total_smem(K.max_pts, K.max_rays, true);
     if (smem_tc > kSmemCap) { set_error("shared-memory budget exceeded (%zu bytes)", smem_tc); return NSB_ERR_UNSUPPORTED; }
-    render_bwd_tc_kernel<<<grid_tc, 128, smem_tc, st>>>(K);
+    render_bwd_tc_kernel<<<grid_tc, tc::kThreads, smem_tc, st>>>(K);
     return check_cuda(cudaGetLastError(), "render_bwd_tc_kernel launch");
   }
   render_bwd_kernel<<<grid, warps * 32, smem, st>>>(K);

@@ -20,8 +20,17 @@ namespace tc {
 
 constexpr int TM = 128;                 // points per tile
 constexpr uint32_t kTmemCols = 256;     // D1: [0,32)  D2: [32,192)
+// Four threads per point: thread tid owns row (tid & 127) and the 8-column group cg = tid >> 7 of every 32-wide epilogue.
+// Warp w may only touch TMEM lanes [32 (w & 3), +32): with this numbering the row of a thread is exactly such a lane.
+constexpr int kThreads = 512;
+constexpr int kCG = kThreads / TM;      // column groups (threads per point)
+constexpr int kCW = 32 / kCG;           // columns per thread
+constexpr int kKQ = kCW / 4;            // 16-byte operand chunks per thread and 32-wide tile row
 
-__device__ __forceinline__ float to_tf32(float x) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return __uint_as_float(u); }
+// hi part of the 3xTF32 split: the top 19 bits (sign, exponent, 10 mantissa bits) -- exactly what the tensor core reads of
+// an fp32 word.  Truncation instead of cvt.rna keeps x = hi + lo exact (lo has <= 13 significant bits, of which the MMA
+// drops <= 3: 2^-21 |x|) and is one full-rate LOP instead of a quarter-rate conversion.
+__device__ __forceinline__ float to_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 // element (row r, k) of a canonical tile of width K floats
 __device__ __forceinline__ int canon_q(int r, int kq, int K) { return ((r >> 3) * (K >> 2) + kq) * 32 + (r & 7) * 4; }
@@ -87,6 +96,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 8; j++) v[j] = __uint_as_float(r[j]);
+}
+static_assert(kCW == 8, "epilogues use tcgen05.ld.32x32b.x8");
+
 // shared-memory regions of the tensor-core path (all 1024-byte aligned so that every tile start is 16-byte aligned)
 struct TcSmem {
   float* x;        // 64 KB: C hi|lo (128 x 64 each)  -- later  E hi|lo (128 x 32) + H hi|lo (128 x 32), or two E blocks
@@ -137,45 +156,44 @@ __device__ __forceinline__ void stage_w(float* __restrict__ dst, const float* __
   }
 }
 
-// 8 lanes per point, 4 points per pass: gather the 32 channels of `g` for the warp's 32 rows into columns [col0, col0+32) of the C tile
+// 8 lanes per point, 4 points per pass: gather the 32 channels of `g` into columns [col0, col0+32) of the C tile.  Warp w serves
+// the rows of its lane quadrant (w & 3); the eight passes of a quadrant are split over the kCG warps that share it.
 __device__ __forceinline__ void gather_rows(const nsb_grid& g, float* __restrict__ c_hi, float* __restrict__ c_lo, int KC, int col0,
                                             const float xn[3], int warp, int lane) {
   const bool fast = grid_fast(g);
-  const int q = lane & 7;
-#pragma unroll 1
-  for (int it0 = 0; it0 < 8; it0 += 2) {                         // two passes (8 points of the warp) per batch: 16 loads in flight per lane
-    Tri t[2]; float4 v[2][8];
+  const int q = lane & 7, qd = warp & 3, it0 = (warp >> 2) * (8 / kCG);
+  static_assert(8 / kCG == 2, "one batch of two passes per warp");
+  Tri t[2]; float4 v[2][8];                                        // 16 loads in flight per lane
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
-      const int src_lane = (it0 + u) * 4 + (lane >> 3);
-      float x[3];
-      x[0] = __shfl_sync(0xffffffffu, xn[0], src_lane); x[1] = __shfl_sync(0xffffffffu, xn[1], src_lane); x[2] = __shfl_sync(0xffffffffu, xn[2], src_lane);
-      t[u] = make_tri(x, g.W, g.H, g.D);
+  for (int u = 0; u < 2; u++) {
+    const int src_lane = (it0 + u) * 4 + (lane >> 3);
+    float x[3];
+    x[0] = __shfl_sync(0xffffffffu, xn[0], src_lane); x[1] = __shfl_sync(0xffffffffu, xn[1], src_lane); x[2] = __shfl_sync(0xffffffffu, xn[2], src_lane);
+    t[u] = make_tri(x, g.W, g.H, g.D);
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
-        int cx, cy, cz;
-        tri_corner_clamped(t[u], k, g.W, g.H, g.D, cx, cy, cz);
-        v[u][k] = grid_load4(g, cz * g.stride_d + cy * g.stride_h + cx * g.stride_w, 4 * q, fast);
-      }
+    for (int k = 0; k < 8; k++) {
+      int cx, cy, cz;
+      tri_corner_clamped(t[u], k, g.W, g.H, g.D, cx, cy, cz);
+      v[u][k] = grid_load4(g, cz * g.stride_d + cy * g.stride_h + cx * g.stride_w, 4 * q, fast);
     }
+  }
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int u = 0; u < 2; u++) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const float w = tri_weight(t[u], k);
-        acc.x = fmaf(v[u][k].x, w, acc.x); acc.y = fmaf(v[u][k].y, w, acc.y); acc.z = fmaf(v[u][k].z, w, acc.z); acc.w = fmaf(v[u][k].w, w, acc.w);
-      }
-      put4(c_hi, c_lo, warp * 32 + (it0 + u) * 4 + (lane >> 3), (col0 >> 2) + q, KC, acc);
+    for (int k = 0; k < 8; k++) {
+      const float w = tri_weight(t[u], k);
+      acc.x = fmaf(v[u][k].x, w, acc.x); acc.y = fmaf(v[u][k].y, w, acc.y); acc.z = fmaf(v[u][k].z, w, acc.z); acc.w = fmaf(v[u][k].w, w, acc.w);
     }
+    put4(c_hi, c_lo, qd * 32 + (it0 + u) * 4 + (lane >> 3), (col0 >> 2) + q, KC, acc);
   }
 }
 
-// E block `blk` (features 32*blk .. +31, zero beyond 93) of this thread's point -> canonical hi|lo tile of width 32
+// this thread's kCW features of E block `blk` (features 32*blk .. +31, zero beyond 93) of its point -> canonical hi|lo tile of width 32
 __device__ __forceinline__ void embed_row(float* __restrict__ e_hi, float* __restrict__ e_lo, const float* __restrict__ B /*packed [3][96]*/,
-                                          const float pf[3], int row, int blk) {
-#pragma unroll 2
-  for (int kq = 0; kq < 8; kq++) {
+                                          const float pf[3], int row, int cg, int blk) {
+#pragma unroll
+  for (int kq = kKQ * cg; kq < kKQ * cg + kKQ; kq++) {
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -187,8 +205,9 @@ __device__ __forceinline__ void embed_row(float* __restrict__ e_hi, float* __res
   }
 }
 
-// Forward of decoder `lv` for one 128-point tile.  Every thread = one point (row == threadIdx.x).  On return out[o] holds the
-// decoder outputs of this thread's point.  `parity` / `wparity` are the running phases of t.bar / t.wbar.
+// Forward of decoder `lv` for one 128-point tile.  Thread tid = (row = tid & 127, column group cg = tid >> 7).  On return out[o] holds
+// the decoder outputs of this thread's point (identical in the kCG threads of a row).  `parity` / `wparity` are the running phases of
+// t.bar / t.wbar.
 // TMEM: D1 = cols [0,32) (layers 0,1,2,4), D2 = [32,192) (fc_c of the five layers), D3 = [192,224) (layer 3; its skip part
 // E * W3E^T is accumulated while the embedding blocks are live for layer 0, so the embedding is computed once).
 // Sequential MMA batches per decoder: fc_c 1-2, layer 0: 3 (one per embedding block), layers 1..4: one each.
@@ -197,11 +216,11 @@ __device__ __forceinline__ void tile_forward(const KParams& P, const TcSmem& t, 
                                              uint32_t tmem, uint32_t& parity, uint32_t& wparity, float (&out)[4],
                                              uint32_t* __restrict__ gmask /* global [5] slot of this point+decoder, or nullptr */,
                                              bool& prefetched /* this decoder's image is already in flight */, int next_lv /* prefetch after the last use, or -1 */) {
-  const int row = threadIdx.x, warp = row >> 5, lane = row & 31;
+  const int row = threadIdx.x & (TM - 1), cg = threadIdx.x >> 7, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* Wg = t.wraw;                                // packed fp32 image of this decoder, staged by TMA below
   float* c_hi = t.x; float* c_lo = t.x + TM * d.cd;
-  const uint32_t d1 = tmem, d2 = tmem + 32u, d3 = tmem + 192u;
-  const uint32_t my_lane = (uint32_t)(warp * 32) << 16;
+  const uint32_t my = ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kCW * cg);      // TMEM lane quadrant + first column of this thread
+  const uint32_t d1 = tmem + my, d2 = tmem + 32u + my, d3 = tmem + 192u + my;
   constexpr int PH = Dec<1>::PH;
 
   __syncthreads();                       // previous decoder / tile: all reads of the weight image and of the tiles are done
@@ -233,7 +252,7 @@ __device__ __forceinline__ void tile_forward(const KParams& P, const TcSmem& t, 
         for (int i = i0; i < i1; i++) {
           uint32_t acc = 0;
           const float* w = t.wa + (i - i0) * 2 * 32 * d.cd;
-          mma_3x(d2 + 32u * i, c_hi, c_lo, d.cd, 0, w, w + 32 * d.cd, d.cd, 0, d.cd >> 3, 32, acc);
+          mma_3x(tmem + 32u + 32u * i, c_hi, c_lo, d.cd, 0, w, w + 32 * d.cd, d.cd, 0, d.cd >> 3, 32, acc);
         }
         mma_commit(t.bar);
       }
@@ -253,12 +272,12 @@ __device__ __forceinline__ void tile_forward(const KParams& P, const TcSmem& t, 
     for (int blk = 0; blk < nblk; blk++) {
       stage_w(t.wa, Wg + d.o_W0, d.pf, 32 * blk, 32);
       stage_w(t.wa + 2 * 32 * 32, Wg + d.o_W3E, d.pf, 32 * blk, 32);
-      if (d.xyz) embed_row(e_hi, e_lo, Wg + d.o_B, G.pf, row, blk);
+      if (d.xyz) embed_row(e_hi, e_lo, Wg + d.o_B, G.pf, row, cg, blk);
       publish_operands();
       if (threadIdx.x == 0) {
         tc_fence_after();
-        mma_3x(d1, e_hi, e_lo, 32, 0, t.wa, t.wa + 32 * 32, 32, 0, 4, 32, acc1);
-        mma_3x(d3, e_hi, e_lo, 32, 0, t.wa + 2 * 32 * 32, t.wa + 3 * 32 * 32, 32, 0, 4, 32, acc3);
+        mma_3x(tmem, e_hi, e_lo, 32, 0, t.wa, t.wa + 32 * 32, 32, 0, 4, 32, acc1);
+        mma_3x(tmem + 192u, e_hi, e_lo, 32, 0, t.wa + 2 * 32 * 32, t.wa + 3 * 32 * 32, 32, 0, 4, 32, acc3);
         mma_commit(t.bar);
       }
       __syncwarp();
@@ -268,26 +287,27 @@ __device__ __forceinline__ void tile_forward(const KParams& P, const TcSmem& t, 
   }
   // hidden-part weights of layers 1..4, all at once (4 x 8 KB): no staging on the critical path of the remaining layers
   for (int i = 1; i < 5; i++) stage_w(t.wa + (i - 1) * 2 * 32 * 32, Wg + dec_wh(d, i), PH, 0, 32);
-  float h[32];
+  float h[kCW];
+  uint8_t* smask = reinterpret_cast<uint8_t*>(t.masks);
 #pragma unroll 1
   for (int i = 0; i < 5; i++) {
-    // ---- epilogue of layer i: h = relu(D + b_i) + (D2_i + bc_i)
-    float v1[32];
-    tmem_ld32((i == 3 ? d3 : d1) + my_lane, v1);
+    // ---- epilogue of layer i (this thread's kCW columns): h = relu(D + b_i) + (D2_i + bc_i)
+    float v1[kCW];
+    tmem_ld8(i == 3 ? d3 : d1, v1);
     uint32_t m = 0;
 #pragma unroll
-    for (int j = 0; j < 32; j++) { const float u = v1[j] + t.bias[i * 32 + j]; h[j] = u > 0.0f ? u : 0.0f; m |= u > 0.0f ? (1u << j) : 0u; }
-    if (KEEP) t.masks[i * TM + row] = m;
-    if (gmask != nullptr) gmask[i] = m;
+    for (int j = 0; j < kCW; j++) { const float u = v1[j] + t.bias[i * 32 + kCW * cg + j]; h[j] = u > 0.0f ? u : 0.0f; m |= u > 0.0f ? (1u << j) : 0u; }
+    if (KEEP) smask[(i * TM + row) * 4 + cg] = (uint8_t)m;                           // byte cg of the 32-bit ReLU mask word
+    if (gmask != nullptr) reinterpret_cast<uint8_t*>(gmask)[i * 4 + cg] = (uint8_t)m;
     if (d.xyz) {
-      float v2[32];
-      tmem_ld32(d2 + 32u * i + my_lane, v2);
+      float v2[kCW];
+      tmem_ld8(d2 + 32u * i, v2);
 #pragma unroll
-      for (int j = 0; j < 32; j++) h[j] += v2[j] + t.bias[160 + i * 32 + j];
+      for (int j = 0; j < kCW; j++) h[j] += v2[j] + t.bias[160 + i * 32 + kCW * cg + j];
     }
     if (i == 4) break;
 #pragma unroll
-    for (int kq = 0; kq < 8; kq++) put4(h_hi, h_lo, row, kq, 32, make_float4(h[4 * kq], h[4 * kq + 1], h[4 * kq + 2], h[4 * kq + 3]));
+    for (int k = 0; k < kKQ; k++) put4(h_hi, h_lo, row, kKQ * cg + k, 32, make_float4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]));
     publish_operands();                                      // (also orders this layer's TMEM reads before the next MMAs)
     if (i == 0 && next_lv >= 0 && !KEEP) {                   // the packed image is dead (hidden weights + biases are staged): prefetch the next one
       if (threadIdx.x == 0) issue_decoder_tma(P, t, next_lv);
@@ -297,7 +317,7 @@ __device__ __forceinline__ void tile_forward(const KParams& P, const TcSmem& t, 
       tc_fence_after();
       const float* w = t.wa + i * 2 * 32 * 32;               // hidden weights of layer i+1
       uint32_t acc = (i + 1 == 3) ? 1u : 0u;                 // layer 3 accumulates onto E * W3E^T
-      mma_3x((i + 1 == 3) ? d3 : d1, h_hi, h_lo, 32, 0, w, w + 32 * 32, 32, 0, 4, 32, acc);
+      mma_3x((i + 1 == 3) ? tmem + 192u : tmem, h_hi, h_lo, 32, 0, w, w + 32 * 32, 32, 0, 4, 32, acc);
       mma_commit(t.bar);
     }
     __syncwarp();
@@ -305,15 +325,28 @@ __device__ __forceinline__ void tile_forward(const KParams& P, const TcSmem& t, 
     tc_fence_after();
   }
   tc_fence_before();
-  // ---- output layer in registers
+  // ---- output layer: partial dot products over this thread's columns, summed over the kCG threads of the row through shared memory
+  // (the H tile is dead: layer 4 has consumed it)
+  float* part = h_hi;                                        // [kCG][TM][4]
+  {
+    float s[4];
 #pragma unroll
-  for (int o = 0; o < 4; o++) {
-    float s = t.bias[320 + o];
-    if (o < d.no) {
+    for (int o = 0; o < 4; o++) {
+      s[o] = 0.0f;
+      if (o < d.no) {
 #pragma unroll
-      for (int j = 0; j < 32; j++) s = fmaf(h[j], t.bias[336 + o * 32 + j], s);
+        for (int j = 0; j < kCW; j++) s[o] = fmaf(h[j], t.bias[336 + o * 32 + kCW * cg + j], s[o]);
+      }
     }
-    out[o] = s;
+    *reinterpret_cast<float4*>(part + (cg * TM + row) * 4) = make_float4(s[0], s[1], s[2], s[3]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int o = 0; o < 4; o++) out[o] = t.bias[320 + o];
+#pragma unroll
+  for (int c = 0; c < kCG; c++) {
+    const float4 v = *reinterpret_cast<const float4*>(part + (c * TM + row) * 4);
+    out[0] += v.x; out[1] += v.y; out[2] += v.z; out[3] += v.w;
   }
 }
 
@@ -336,46 +369,53 @@ __device__ __forceinline__ void stage_wT(float* __restrict__ dst, const float* _
 }
 
 // Backward of decoder `lv` for one tile, input gradients only (rays + grid voxels; no decoder-weight gradients).
-// Precondition: tile_forward<true> just ran for the same tile (masks in t.masks).  g_out = dL/d out of this thread's point.
-// Writes dL/dc of every row to `dcs` ([128][cd] fp32, aliasing t.x) and returns dpe = dL/dp through the Fourier embedding.
+// Precondition: tile_forward<true> just ran for the same tile (masks in t.masks) or gmask points at the saved masks.
+// g_out = dL/d out of this thread's point.  Writes dL/dc of every row to `dcs` ([128][cd] fp32, aliasing t.x) and this thread's
+// share of dL/dp through the Fourier embedding to dpe_part ([kCG][128][4] fp32 at t.x + 2*TM*32; summed by the caller after a barrier).
 __device__ __forceinline__ void tile_backward(const KParams& P, const TcSmem& t, const DecRT& d, int lv, const PointGeom& G,
-                                              uint32_t tmem, uint32_t& parity, uint32_t& wparity, const float (&g_out)[4], float (&dpe)[3],
+                                              uint32_t tmem, uint32_t& parity, uint32_t& wparity, const float (&g_out)[4],
                                               const uint32_t* __restrict__ gmask /* saved masks of this point+decoder or nullptr */,
                                               bool& prefetched) {
-  const int row = threadIdx.x, warp = row >> 5;
+  const int row = threadIdx.x & (TM - 1), cg = threadIdx.x >> 7, warp = threadIdx.x >> 5;
   const float* Wg = t.wraw;                                 // resident from the recomputed forward, or loaded below
+  uint32_t mlo = 0, mhi = 0;                                // this thread's 8 ReLU bits of layers 0..3 (one byte each) and of layer 4
   if (gmask != nullptr) {                                   // no forward recompute: bring the decoder image in and the masks
     __syncthreads();
     if (!prefetched && threadIdx.x == 0) issue_decoder_tma(P, t, lv);
     prefetched = false;
 #pragma unroll
-    for (int i = 0; i < 5; i++) t.masks[i * TM + row] = gmask[i];
+    for (int i = 0; i < 4; i++) mlo |= (uint32_t) reinterpret_cast<const uint8_t*>(gmask)[i * 4 + cg] << (8 * i);
+    mhi = reinterpret_cast<const uint8_t*>(gmask)[16 + cg];
     mbar_wait(t.wbar, wparity); wparity ^= 1u;
     for (int i = threadIdx.x; i < 128; i += blockDim.x) t.bias[336 + i] = Wg[d.o_WO + (i >> 5) * Dec<1>::PH + (i & 31)];
     __syncthreads();
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; i++) mlo |= (uint32_t) reinterpret_cast<const uint8_t*>(t.masks)[(i * TM + row) * 4 + cg] << (8 * i);
+    mhi = reinterpret_cast<const uint8_t*>(t.masks)[(4 * TM + row) * 4 + cg];
   }
-  const uint32_t d1 = tmem, dcc = tmem + 32u, dfc = tmem + 96u;      // DC: cols [32,96)  DF: cols [96,192)  (D2 is dead)
-  const uint32_t my_lane = (uint32_t)(warp * 32) << 16;
+  const uint32_t my = ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kCW * cg);
+  const uint32_t dcc = tmem + 32u, dfc = tmem + 96u;       // DC: cols [32,96)  DF: cols [96,192)  (D2 is dead)
   float* g_hi = t.x; float* g_lo = t.x + TM * 32;
   float* du_hi = t.x + 2 * TM * 32; float* du_lo = t.x + 3 * TM * 32;
   constexpr int PH = Dec<1>::PH;
-  float g[32];
+  float g[kCW];
 #pragma unroll
-  for (int j = 0; j < 32; j++) {
+  for (int j = 0; j < kCW; j++) {
     float v = 0.0f;
 #pragma unroll
-    for (int o = 0; o < 4; o++) v = fmaf(t.bias[336 + o * 32 + j], g_out[o], v);       // rows >= NO are zero
+    for (int o = 0; o < 4; o++) v = fmaf(t.bias[336 + o * 32 + kCW * cg + j], g_out[o], v);       // rows >= NO are zero
     g[j] = v;
   }
   uint32_t acc_dc = 0, acc_df = 0;
 #pragma unroll 1
   for (int i = 4; i >= 0; i--) {
-    const uint32_t m = t.masks[i * TM + row];
+    const uint32_t m = i == 4 ? mhi : (mlo >> (8 * i)) & 0xffu;
 #pragma unroll
-    for (int kq = 0; kq < 8; kq++) {
-      if (d.xyz) put4(g_hi, g_lo, row, kq, 32, make_float4(g[4 * kq], g[4 * kq + 1], g[4 * kq + 2], g[4 * kq + 3]));
-      put4(du_hi, du_lo, row, kq, 32, make_float4((m >> (4 * kq)) & 1u ? g[4 * kq] : 0.0f, (m >> (4 * kq + 1)) & 1u ? g[4 * kq + 1] : 0.0f,
-                                                   (m >> (4 * kq + 2)) & 1u ? g[4 * kq + 2] : 0.0f, (m >> (4 * kq + 3)) & 1u ? g[4 * kq + 3] : 0.0f));
+    for (int k = 0; k < kKQ; k++) {
+      if (d.xyz) put4(g_hi, g_lo, row, kKQ * cg + k, 32, make_float4(g[4 * k], g[4 * k + 1], g[4 * k + 2], g[4 * k + 3]));
+      put4(du_hi, du_lo, row, kKQ * cg + k, 32, make_float4((m >> (4 * k)) & 1u ? g[4 * k] : 0.0f, (m >> (4 * k + 1)) & 1u ? g[4 * k + 1] : 0.0f,
+                                                             (m >> (4 * k + 2)) & 1u ? g[4 * k + 2] : 0.0f, (m >> (4 * k + 3)) & 1u ? g[4 * k + 3] : 0.0f));
     }
     {   // one batch per layer: DC += G * Wc_i (dL/dc through fc_c) ; D1 = DU * W_i[:, hidden] (g_i) ; DF += DU * W_i[:, first] (i = 3, 0)
       float* wcT = t.wa;                         // [cd x 32] hi|lo (<= 16 KB)
@@ -388,7 +428,7 @@ __device__ __forceinline__ void tile_backward(const KParams& P, const TcSmem& t,
       if (threadIdx.x == 0) {
         tc_fence_after();
         if (d.xyz) mma_3x(dcc, g_hi, g_lo, 32, 0, wcT, wcT + d.cd * 32, 32, 0, 4, d.cd, acc_dc);
-        if (i >= 1) { uint32_t a1 = 0; mma_3x(d1, du_hi, du_lo, 32, 0, whT, whT + 32 * 32, 32, 0, 4, 32, a1); }
+        if (i >= 1) { uint32_t a1 = 0; mma_3x(tmem, du_hi, du_lo, 32, 0, whT, whT + 32 * 32, 32, 0, 4, 32, a1); }
         if (i == 3 || i == 0) mma_3x(dfc, du_hi, du_lo, 32, 0, weT, weT + d.firstp * 32, 32, 0, 4, d.firstp, acc_df);
         mma_commit(t.bar);
       }
@@ -396,30 +436,31 @@ __device__ __forceinline__ void tile_backward(const KParams& P, const TcSmem& t,
       mbar_wait(t.bar, parity); parity ^= 1u;
       tc_fence_after();
     }
-    if (i >= 1) tmem_ld32(d1 + my_lane, g);
+    if (i >= 1) tmem_ld8(tmem + my, g);
     tc_fence_before();
   }
   // ---- dL/dc rows -> shared (plain fp32 [128][cd]); all MMAs reading t.x have completed
   float* dcs = t.x;
   {
-    float v[32];
+    float v[kCW];
     const int nch = d.xyz ? (d.cd >> 5) : 1;
     for (int c = 0; c < nch; c++) {
-      tmem_ld32((d.xyz ? dcc : dfc) + 32u * c + my_lane, v);
+      tmem_ld8((d.xyz ? dcc : dfc) + 32u * c + my, v);
 #pragma unroll
-      for (int kq = 0; kq < 8; kq++) *reinterpret_cast<float4*>(dcs + row * d.cd + 32 * c + 4 * kq) = make_float4(v[4 * kq], v[4 * kq + 1], v[4 * kq + 2], v[4 * kq + 3]);
+      for (int k = 0; k < kKQ; k++)
+        *reinterpret_cast<float4*>(dcs + row * d.cd + 32 * c + kCW * cg + 4 * k) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
     }
   }
-  // ---- embedding chain: dp += B (cos(pB) * dfirst)
-  dpe[0] = dpe[1] = dpe[2] = 0.0f;
+  // ---- embedding chain: dp += B (cos(pB) * dfirst), this thread's features; partial sums to shared memory
+  float dpe[3] = {0.0f, 0.0f, 0.0f};
   if (d.xyz) {
     const float* B = Wg + d.o_B;
     for (int c = 0; c < 3; c++) {
-      float v[32];
-      tmem_ld32(dfc + 32u * c + my_lane, v);
+      float v[kCW];
+      tmem_ld8(dfc + 32u * c + my, v);
 #pragma unroll
-      for (int j = 0; j < 32; j++) {
-        const int f = 32 * c + j;
+      for (int j = 0; j < kCW; j++) {
+        const int f = 32 * c + kCW * cg + j;
         if (f < kEmb) {
           const float b0 = B[f], b1 = B[kEmbPad + f], b2 = B[2 * kEmbPad + f];
           float x = G.pf[0] * b0; x = fmaf(G.pf[1], b1, x); x = fmaf(G.pf[2], b2, x);
@@ -429,21 +470,31 @@ __device__ __forceinline__ void tile_backward(const KParams& P, const TcSmem& t,
       }
     }
   }
+  *reinterpret_cast<float4*>(t.x + 2 * TM * 32 + (cg * TM + row) * 4) = make_float4(dpe[0], dpe[1], dpe[2], 0.0f);
   tc_fence_before();
 }
+// dL/dp of `row` through the embedding: sum of the kCG partials tile_backward left in shared memory (call after a CTA barrier)
+__device__ __forceinline__ void dpe_sum(const TcSmem& t, int row, float (&dpe)[3]) {
+  dpe[0] = dpe[1] = dpe[2] = 0.0f;
+#pragma unroll
+  for (int c = 0; c < kCG; c++) {
+    const float4 v = *reinterpret_cast<const float4*>(t.x + 2 * TM * 32 + (c * TM + row) * 4);
+    dpe[0] += v.x; dpe[1] += v.y; dpe[2] += v.z;
+  }
+}
 
-// Backward of gather_rows for the warp's 32 rows: dc rows come from `dcs` ([128][cd] fp32).  Scatter-adds into dgrid (if non-null)
+// Backward of gather_rows (same warp -> rows mapping): dc rows come from `dcs` ([128][cd] fp32).  Scatter-adds into dgrid (if non-null)
 // and hands the normalised-coordinate gradient of each point to emit(row, gx).
 template <typename F>
 __device__ __forceinline__ void scatter_rows(const nsb_grid& g, float* __restrict__ dgrid, const int32_t* __restrict__ slots,
                                              const float* __restrict__ dcs, int cd,
                                              const float xn[3], int warp, int lane, F&& emit) {
   const bool fast = grid_fast(g);
-  const int q = lane & 7;
+  const int q = lane & 7, qd = warp & 3, it0 = (warp >> 2) * (8 / kCG);
 #pragma unroll 1
-  for (int it = 0; it < 8; it++) {
+  for (int it = it0; it < it0 + 8 / kCG; it++) {
     const int src_lane = it * 4 + (lane >> 3);
-    const int row = warp * 32 + src_lane;
+    const int row = qd * 32 + src_lane;
     float x[3];
     x[0] = __shfl_sync(0xffffffffu, xn[0], src_lane); x[1] = __shfl_sync(0xffffffffu, xn[1], src_lane); x[2] = __shfl_sync(0xffffffffu, xn[2], src_lane);
     const Tri t = make_tri(x, g.W, g.H, g.D);

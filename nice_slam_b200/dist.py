@@ -143,3 +143,70 @@ class ShardedTrackingIteration:
         self.ctx.load_device_inputs(rays_o, rays_d, gt_depth, gt_color)
         self.prepare(c, decoders, dirs, w_color, handle_dynamic, use_color)
         return self.enqueue()
+
+
+class ShardedMappingIteration:
+    """One Mapper.optimize_map joint iteration (src/Mapper.py:482-503) on this rank's shard of the window's ray batch.
+    Replicated: grids, decoders, poses.  Exchanges: MAX of the batch depth maxima before sampling (Renderer.py:109,144) and ONE
+    SUM all-reduce of the context's packed float32 block [loss | keyframe pose grads | decoder grads | compact voxel grads]
+    (steps.IterationContext.packed) -- after it every rank holds the full-batch gradients and takes the identical optimiser step.
+    Split-phase like ShardedTrackingIteration; graph-capturable."""
+
+    def __init__(self, ctx):
+        assert ctx.kind == "map"
+        self.ctx = ctx
+        self._p = None
+
+    def prepare(self, c, decoders, dirs=None, frame_offsets=None, w_color=0.2):
+        from . import _lib
+        from .renderer import _inputs, _linspaces
+        x = self.ctx
+        ro, rd, gd, gc = x.device_views()
+        call, grids, _ = x.r._call(c, decoders, x.stage, gd if x.render_with_depth else None, x.dev)
+        t_u, t_s = _linspaces(x.r.N_samples, x.r.N_surface, x.dev)
+        inp = _inputs(call, ro, rd, x.depth_max, t_u, t_s, [g.detach() for g in grids])
+        fo = _lib.ForwardOutputs(x.depth.data_ptr(), x.var.data_ptr(), x.rgb.data_ptr(), x.z_vals.data_ptr(), x.raw.data_ptr(), None,
+                                 x.masks.data_ptr())
+        bw = x._grads(c)
+        bw.z_vals, bw.raw, bw.g_depth, bw.g_rgb, bw.masks = (x.z_vals.data_ptr(), x.raw.data_ptr(), x.g_depth.data_ptr(),
+                                                              x.g_rgb.data_ptr(), x.masks.data_ptr())
+        ws_off = (_lib.lib().nsb_tracking_seeds_workspace(x.n) + 15) & ~15
+        bw.workspace = x.ws.data_ptr() + ws_off
+        self._p = dict(call=call, grids=grids, lin=(t_u, t_s), inp=inp, fo=fo, bw=bw, dirs=dirs, offs=frame_offsets, gd=gd, gc=gc,
+                       w_color=w_color, uc=int(x.stage == "color"))
+
+    def enqueue(self):
+        import ctypes as C
+        from . import _lib
+        from .renderer import _VP, _stream
+        L = _lib.lib()
+        x, p = self.ctx, self._p
+        n, st = x.n, _stream()
+        x.zero_grads()
+        if x.render_with_depth:
+            _lib.check(L.nsb_batch_max_depth(_VP(p["gd"].data_ptr()), n, _VP(x.depth_max.data_ptr()), st), "nsb_batch_max_depth")
+            exchange_depth_max(x.depth_max)
+        _lib.check(L.nsb_render_forward(C.byref(p["inp"]), C.byref(p["fo"]), st), "nsb_render_forward")
+        _lib.check(L.nsb_mapping_seeds(_VP(x.depth.data_ptr()), _VP(x.rgb.data_ptr()), _VP(p["gd"].data_ptr()), _VP(p["gc"].data_ptr()), n,
+                                       p["w_color"], p["uc"], _VP(x.g_depth.data_ptr()), _VP(x.g_rgb.data_ptr()), _VP(x.loss.data_ptr()), st),
+                   "nsb_mapping_seeds")
+        _lib.check(L.nsb_render_backward(C.byref(p["inp"]), C.byref(p["bw"]), st), "nsb_render_backward")
+        x.finish_packed(p["dirs"], p["offs"])
+        return reduce_sum(x.packed)
+
+    def build_graph(self):
+        try:
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                self.enqueue(); self.enqueue()
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.enqueue()
+            return g
+        except Exception:
+            torch.cuda.synchronize()
+            return None

@@ -19,8 +19,26 @@ from .renderer import _VP, _inputs, _linspaces, _stream, _Call, _require_cuda
 KERNEL_LAUNCHES_PER_ITERATION = 4       # batch_max, render_fwd, seeds, render_bwd (+1 unpack when decoder grads are requested)
 
 
+def packed_layout(n_frames, grad_decoders, masked_counts):
+    """Sections of the packed float32 gradient block of a mapping iteration: {name: (offset, numel)}, total floats.
+    [loss,0,0,0 | 'frames': 12 per keyframe | 'dec_<level>': canonical flat decoder order | '<grid key>': [n_selected,32] compact]"""
+    L = _lib.lib()
+    up4 = lambda v: (v + 3) & ~3
+    off, sect = 4, {}
+    sect["frames"] = (off, 12 * n_frames); off += up4(12 * n_frames)
+    for lvl in grad_decoders:
+        nf = L.nsb_flat_decoder_floats(LEVELS.index(lvl))
+        sect["dec_" + lvl] = (off, nf); off += up4(nf)
+    for key, count in masked_counts:
+        sect[key] = (off, 32 * count); off += 32 * count
+    return sect, off
+
+
 class IterationContext:
-    def __init__(self, renderer, n_rays, stage, device, kind="track", grad_grids=(), grad_decoders=(), coarse_mapper=False):
+    def __init__(self, renderer, n_rays, stage, device, kind="track", grad_grids=(), grad_decoders=(), coarse_mapper=False,
+                 masked=None, n_frames=0):
+        """masked: {grid key: masked.MaskedVoxels} -- those grids get COMPACT [n_selected,32] gradients (Mapper.py:317-333) instead of
+        dense ones; n_frames: keyframes of the bundle-adjustment window whose d c2w is wanted (pose_grad_frames)."""
         L = _lib.lib()
         self.r, self.n, self.stage, self.kind = renderer, int(n_rays), stage, kind
         self.dev = torch.device(device)
@@ -52,8 +70,17 @@ class IterationContext:
         self.gt_color = torch.empty(n, 3, dtype=f64 if kind == "track" else f32, device=dev)
         self.grad_grids = tuple(grad_grids)
         self.grad_decoders = tuple(grad_decoders)
-        self.d_grid = {}
-        self.d_flat = {lvl: torch.zeros(L.nsb_flat_decoder_floats(LEVELS.index(lvl)), dtype=f32, device=dev) for lvl in self.grad_decoders}
+        self.masked = dict(masked or {})
+        self.n_frames = int(n_frames)
+        # packed float32 gradient block = what a sharded mapping iteration all-reduces in ONE collective:
+        #   [loss, 0, 0, 0 | d c2w of the keyframes (12 each) | decoder grads (canonical flat order) | compact voxel grads]
+        # every section starts on a 16-byte boundary (the voxel scatter uses 16-byte vector reductions)
+        sect, off = packed_layout(self.n_frames, self.grad_decoders, [(k, self.masked[k].count) for k in self.grad_grids if k in self.masked])
+        self.sections = sect
+        self.packed = torch.zeros(off, dtype=f32, device=dev)
+        self.d_frames = self.packed[4: 4 + 12 * self.n_frames].view(self.n_frames, 12)
+        self.d_grid = {key: self.packed[sect[key][0]: sect[key][0] + sect[key][1]].view(-1, 32) for key in self.grad_grids if key in self.masked}
+        self.d_flat = {lvl: self.packed[sect["dec_" + lvl][0]: sect["dec_" + lvl][0] + sect["dec_" + lvl][1]] for lvl in self.grad_decoders}
         self.buf = _lib.IterationBuffers(self.depth.data_ptr(), self.var.data_ptr(), self.rgb.data_ptr(), self.z_vals.data_ptr(),
                                          self.raw.data_ptr(), self.masks.data_ptr(), self.g_depth.data_ptr(), self.g_rgb.data_ptr(), self.loss.data_ptr(),
                                          self.depth_max.data_ptr(), self.ws.data_ptr(), self.ws.numel(), None, None)
@@ -71,20 +98,41 @@ class IterationContext:
 
     # ------------------------------------------------------------------------------------------
     def _grads(self, c):
+        """nsb_backward_args with the output pointers of this context; (re)zeroes the accumulation buffers."""
         bw = _lib.BackwardArgs()
         bw.d_rays_o, bw.d_rays_d = self.d_rays_o.data_ptr(), self.d_rays_d.data_ptr()
         for lvl in self.levels:
-            key = "grid_" + lvl
+            key, li = "grid_" + lvl, LEVELS.index(lvl)
             if key in self.grad_grids:
-                g = c[key]
-                if key not in self.d_grid or self.d_grid[key].stride() != g.stride():
-                    self.d_grid[key] = torch.empty_strided(g.size(), g.stride(), dtype=g.dtype, device=g.device)
-                self.d_grid[key].zero_()                      # dense voxel-gradient buffer, accumulated by the kernel
-                bw.d_grid[LEVELS.index(lvl)] = self.d_grid[key].data_ptr()
+                if key in self.masked:                            # compact gradient of the frustum-selected voxels
+                    if self.masked[key].count > 0:
+                        bw.d_grid[li] = self.d_grid[key].data_ptr()
+                        bw.slot_map[li] = self.masked[key].slot_map.data_ptr()
+                else:                                             # dense gradient with the grid's own strides
+                    g = c[key]
+                    if key not in self.d_grid or self.d_grid[key].stride() != g.stride():
+                        self.d_grid[key] = torch.empty_strided(g.size(), g.stride(), dtype=g.dtype, device=g.device)
+                    bw.d_grid[li] = self.d_grid[key].data_ptr()
             if lvl in self.d_flat:
-                self.d_flat[lvl].zero_()
-                bw.d_flat[LEVELS.index(lvl)] = self.d_flat[lvl].data_ptr()
+                bw.d_flat[li] = self.d_flat[lvl].data_ptr()
+        self.zero_grads()
         return bw
+
+    def zero_grads(self):
+        if self.packed.numel() > 4:
+            self.packed.zero_()                                   # one memset: loss slot, keyframe poses, decoder and compact voxel grads
+        for key, t in self.d_grid.items():
+            if key not in self.masked:
+                t.zero_()
+
+    def finish_packed(self, dirs=None, frame_offsets=None):
+        """After run(): loss -> packed[0] and, for a BA window, d c2w of every keyframe -> packed frames section."""
+        self.packed[0:1].copy_(self.loss)
+        if self.n_frames > 0:
+            _lib.check(_lib.lib().nsb_pose_grad_frames(_VP(dirs.data_ptr()), _VP(self.d_rays_o.data_ptr()), _VP(self.d_rays_d.data_ptr()),
+                                                       _VP(frame_offsets.data_ptr()), self.n_frames, _VP(self.d_frames.data_ptr()), _stream()),
+                       "nsb_pose_grad_frames")
+        return self.packed
 
     def run(self, c, decoders, rays_o, rays_d, gt_depth, gt_color, w_color=None, handle_dynamic=True, use_color=True):
         """Enqueue one iteration on the current stream (inputs already on the device).  Results stay on the device:
