@@ -148,6 +148,8 @@ struct KParams {
   int has_gt;
   int n_dec;                    // decoders of this stage, in the reference's evaluation order
   int dec[3];
+  int dec_pos[3];               // position of dec[i] in the stage's full decoder list (slot of its saved ReLU masks)
+  int accumulate_rays;          // backward: add to d_rays_o / d_rays_d instead of overwriting (second launch of a split backward)
   int wbytes;                   // bytes reserved for the weight image in shared memory
   int max_pts, max_rays;        // per-CTA capacities the shared-memory carve-up was sized for
 };
@@ -585,6 +587,10 @@ __device__ __forceinline__ void bwd_ray_reduce(const KParams& P, const Smem& sm,
       const int r = t / 3, a = t - 3 * r;
       double so = 0.0, sd = 0.0;
       for (int s = 0; s < P.S; s++) { const double v = sm.dp[3 * (r * P.S + s) + a]; so += v; sd += v * sm.zs[r * P.S + s]; }
+      if (P.accumulate_rays) {                                   // this ray's earlier contribution was written by the first launch
+        if (P.bw.d_rays_o != nullptr) so += (double)P.bw.d_rays_o[3 * (r0 + r) + a];
+        if (P.bw.d_rays_d != nullptr) sd += (double)P.bw.d_rays_d[3 * (r0 + r) + a];
+      }
       if (P.bw.d_rays_o != nullptr) P.bw.d_rays_o[3 * (r0 + r) + a] = (float)so;
       if (P.bw.d_rays_d != nullptr) P.bw.d_rays_d[3 * (r0 + r) + a] = (float)sd;
     }
@@ -663,7 +669,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) render_bwd_tc_kernel(const __
     for (int qd = 0; qd < P.n_dec; qd++) {
       const int lv = P.dec[qd];
       const DecRT d = make_dec(lv);
-      const uint32_t* gm = P.bw.masks != nullptr ? P.bw.masks + ((((long long)blockIdx.x * P.rays_per_block) * P.S + lpc) * 15 + qd * 5) : nullptr;
+      const uint32_t* gm = P.bw.masks != nullptr ? P.bw.masks + ((((long long)blockIdx.x * P.rays_per_block) * P.S + lpc) * 15 + P.dec_pos[qd] * 5) : nullptr;
       if (gm == nullptr) { float out[4]; bool pf0 = false; tc::tile_forward<true>(P, t, d, lv, G, tmem, parity, wparity, out, nullptr, pf0, -1); }
       float g_out[4] = {0.f, 0.f, 0.f, 0.f};
       if (lp < Pb) {
@@ -735,6 +741,8 @@ static void fill_common(KParams& K, const nsb_render_inputs* in) {
   K.has_gt = (in->gt_depth != nullptr && in->stage != NSB_STAGE_COARSE) ? 1 : 0;    // Renderer.py:88-92
   K.S = in->n_samples + (K.has_gt ? in->n_surface : 0);
   K.n_dec = stage_decoders(in->stage, K.dec);
+  for (int i = 0; i < 3; i++) K.dec_pos[i] = i;
+  K.accumulate_rays = 0;
   int wb = 0;
   for (int i = 0; i < K.n_dec; i++) { const int b = packed_floats(K.dec[i]) * 4; wb = b > wb ? b : wb; }
   K.wbytes = wb;
@@ -806,7 +814,7 @@ extern "C" int nsb_render_forward(const nsb_render_inputs* in, const nsb_forward
   choose_config(in->n_rays, K.S, kRowsFwd, false, K.wbytes, 8, &K, &warps, &smem);
   if (smem > kSmemCap) { set_error("shared-memory budget exceeded (%zu bytes)", smem); return NSB_ERR_UNSUPPORTED; }
   const int grid = (in->n_rays + K.rays_per_block - 1) / K.rays_per_block;
-  if (g_mlp_backend != 1 && K.S <= kMaxPtsTc) {          // tensor-core decoders, 128 threads, <= 2 tiles of 128 points per CTA
+  if (g_mlp_backend != 1 && K.S <= kMaxPtsTc) {          // tensor-core decoders, 512 threads, <= 2 tiles of 128 points per CTA
     choose_config(in->n_rays, K.S, kRowsFwd, false, K.wbytes, 8, &K, &warps, &smem, kMaxPtsTc);
     const int grid_tc = (in->n_rays + K.rays_per_block - 1) / K.rays_per_block;
     const size_t smem_tc = tc_total_smem(K.max_pts, K.max_rays);
@@ -878,15 +886,36 @@ extern "C" int nsb_render_backward(const nsb_render_inputs* in, const nsb_backwa
   int warps; size_t smem;
   choose_config(in->n_rays, K.S, kRowsBwd, true, K.wbytes, 8, &K, &warps, &smem);
   if (smem > kSmemCap) { set_error("shared-memory budget exceeded (%zu bytes)", smem); return NSB_ERR_UNSUPPORTED; }
-  const int grid = (in->n_rays + K.rays_per_block - 1) / K.rays_per_block;
-  if (g_mlp_backend != 1 && !any_w && K.S <= kMaxPtsTc) {        // tensor-core decoders; decoder-weight gradients are SIMT-only for now
-    choose_config(in->n_rays, K.S, kRowsBwd, true, K.wbytes, 8, &K, &warps, &smem, kMaxPtsTc);
-    const int grid_tc = (in->n_rays + K.rays_per_block - 1) / K.rays_per_block;
-    const size_t smem_tc = tc_total_smem(K.max_pts, K.max_rays, true);
-    if (smem_tc > kSmemCap) { set_error("shared-memory budget exceeded (%zu bytes)", smem_tc); return NSB_ERR_UNSUPPORTED; }
-    render_bwd_tc_kernel<<<grid_tc, tc::kThreads, smem_tc, st>>>(K);
-    return check_cuda(cudaGetLastError(), "render_bwd_tc_kernel launch");
+  if (g_mlp_backend != 1 && K.S <= kMaxPtsTc) {
+    // Tensor-core kernel for the decoders that only need input gradients (rays, voxels).  Decoders whose WEIGHT gradients are
+    // requested (the colour decoder in the mapper's colour stage, Mapper.py:339-341) go through the FP32-FMA kernel in a second
+    // launch that adds its share of the ray gradients.
+    KParams T = K;
+    T.n_dec = 0;
+    int n_w = 0, wdec[3], wpos[3];
+    for (int i = 0; i < K.n_dec; i++) {
+      if (bw->d_flat[K.dec[i]] != nullptr) { wdec[n_w] = K.dec[i]; wpos[n_w] = i; n_w++; }
+      else { T.dec[T.n_dec] = K.dec[i]; T.dec_pos[T.n_dec] = i; T.n_dec++; }
+    }
+    if (T.n_dec > 0) {
+      choose_config(in->n_rays, T.S, kRowsBwd, true, T.wbytes, 8, &T, &warps, &smem, kMaxPtsTc);
+      const int grid_tc = (in->n_rays + T.rays_per_block - 1) / T.rays_per_block;
+      const size_t smem_tc = tc_total_smem(T.max_pts, T.max_rays, true);
+      if (smem_tc > kSmemCap) { set_error("shared-memory budget exceeded (%zu bytes)", smem_tc); return NSB_ERR_UNSUPPORTED; }
+      render_bwd_tc_kernel<<<grid_tc, tc::kThreads, smem_tc, st>>>(T);
+      if ((rc = check_cuda(cudaGetLastError(), "render_bwd_tc_kernel launch"))) return rc;
+      if (n_w == 0) return NSB_OK;
+      K.accumulate_rays = 1;
+      K.n_dec = n_w;
+      for (int i = 0; i < n_w; i++) { K.dec[i] = wdec[i]; K.dec_pos[i] = wpos[i]; }
+      int wb = 0;
+      for (int i = 0; i < K.n_dec; i++) { const int b = packed_floats(K.dec[i]) * 4; wb = b > wb ? b : wb; }
+      K.wbytes = wb;
+      choose_config(in->n_rays, K.S, kRowsBwd, true, K.wbytes, 8, &K, &warps, &smem);
+      if (smem > kSmemCap) { set_error("shared-memory budget exceeded (%zu bytes)", smem); return NSB_ERR_UNSUPPORTED; }
+    }
   }
+  const int grid = (in->n_rays + K.rays_per_block - 1) / K.rays_per_block;
   render_bwd_kernel<<<grid, warps * 32, smem, st>>>(K);
   if ((rc = check_cuda(cudaGetLastError(), "render_bwd_kernel launch"))) return rc;
   if (any_w) return launch_unpack_grads(K.d_packed, bw->d_flat, st);

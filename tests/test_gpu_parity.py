@@ -348,3 +348,87 @@ def test_fused_mapping_iteration_matches_oracle(stage):
         for k, v in out["d_dec"][lvl].items():
             if k in mine:
                 assert rel(mine[k], v.reshape(-1)) < TOL, (lvl, k)
+
+
+# ------------------------------------------------------------------------------------ masked voxel parameterisation (Mapper.py:317-333)
+def _random_masks(grids, keys, frac=0.5, seed=11):
+    g = torch.Generator().manual_seed(seed)
+    return {k: torch.rand(grids[k].shape[2:], generator=g) < frac for k in keys}
+
+
+@pytest.mark.parametrize("layout", ["channels_last", "ncdhw"])
+def test_masked_voxels_gather_scatter_match_reference_indexing(layout):
+    """val_grad = val[mask] (Mapper.py:324) and val[mask] = val_grad (:399, :517) with the reference's repeated [1,32,D,H,W] mask."""
+    from nice_slam_b200.masked import MaskedVoxels
+    sc = su.load_scenes()["room0"]
+    grids = su.make_grids(sc, "soft")
+    renderer, c, dec = make_renderer(sc, grids, su.load_decoders("soft"), DEV, channels_last=(layout == "channels_last"))
+    for key, vm in _random_masks(grids, ("grid_middle", "grid_color")).items():
+        val = c[key]
+        mask5 = vm.to(DEV).unsqueeze(0).unsqueeze(0).repeat(1, 32, 1, 1, 1)          # Mapper.py:319-320
+        mv = MaskedVoxels(val, mask5)
+        assert mv.count == int(vm.sum())
+        slots = mv.slot_map.view(vm.shape).cpu()
+        assert torch.equal(slots >= 0, vm) and torch.equal(slots[vm], torch.arange(mv.count, dtype=torch.int32))
+        compact = mv.gather(val)
+        assert torch.equal(mv.to_reference(compact), val[mask5])
+        assert torch.equal(mv.from_reference(val[mask5]), compact)
+        new = torch.randn(mv.count, 32, device=DEV, generator=torch.Generator(device=DEV).manual_seed(2))
+        want = val.clone()
+        want[mask5] = mv.to_reference(new)
+        mv.scatter(val, new)
+        assert torch.equal(val, want)
+    empty = MaskedVoxels(c["grid_middle"], torch.zeros(grids["grid_middle"].shape[2:], dtype=torch.bool))
+    assert empty.count == 0 and bool((empty.slot_map == -1).all())
+
+
+@pytest.mark.parametrize("backend_decoder_grads", [False, True])
+def test_masked_mapping_iteration_packed_block(backend_decoder_grads):
+    """Compact voxel gradients == the dense ones restricted to the mask; the packed block [loss | keyframe pose grads | decoder grads |
+    voxel grads]; the sharded mapping iteration (world size 1) and its CUDA graph give the same block."""
+    from nice_slam_b200._lib import LEVELS
+    from nice_slam_b200.dist import ShardedMappingIteration
+    from nice_slam_b200.masked import MaskedVoxels
+    from nice_slam_b200.steps import IterationContext
+    sc = su.load_scenes()["room0"]
+    grids, dec_state = su.make_grids(sc, "soft"), su.load_decoders("soft")
+    renderer, c, dec = make_renderer(sc, grids, dec_state, DEV)
+    n_rays, n_frames = 330, 3
+    ro, rd, gd, gc = su.make_rays(sc, n_rays, seed=123)
+    dev_in = [t.to(DEV) for t in (ro, rd, gd, gc.float())]
+    dirs = torch.randn(n_rays, 3, generator=torch.Generator().manual_seed(7)).to(DEV)
+    offs = torch.tensor([0, 100, 230, 330], dtype=torch.int32, device=DEV)
+    keys = ("grid_fine", "grid_color", "grid_middle")
+    gdec = ("color",) if backend_decoder_grads else ()           # decoder grads -> FP32-FMA backward kernel, none -> tensor-core kernel
+    masks = _random_masks(grids, keys, 0.6)
+    dense = IterationContext(renderer, n_rays, "color", DEV, kind="map", grad_grids=keys, grad_decoders=gdec)
+    dense.run(c, dec, *dev_in)
+    mv = {k: MaskedVoxels(c[k], masks[k]) for k in keys}
+    ctx = IterationContext(renderer, n_rays, "color", DEV, kind="map", grad_grids=keys, grad_decoders=gdec, masked=mv, n_frames=n_frames)
+    for rep in range(2):
+        ctx.run(c, dec, *dev_in)
+    packed = ctx.finish_packed(dirs, offs).clone()
+    assert abs(float(packed[0]) - float(dense.loss)) < 1e-6 * abs(float(dense.loss))
+    for k in keys:
+        want = dense.d_grid[k][masks[k].to(DEV).unsqueeze(0).unsqueeze(0).expand_as(dense.d_grid[k])]
+        assert float(want.abs().max()) > 0
+        assert rel(mv[k].to_reference(ctx.d_grid[k]), want) < 1e-5, k
+        o, cnt = ctx.sections[k]
+        assert torch.equal(packed[o:o + cnt].view(-1, 32), ctx.d_grid[k])
+    for lvl in gdec:
+        assert rel(ctx.d_flat[lvl], dense.d_flat[lvl]) < 1e-5
+    for f in range(n_frames):
+        lo, hi = int(offs[f]), int(offs[f + 1])
+        want = torch.cat([ctx.d_rays_d[lo:hi].double().t() @ dirs[lo:hi].double(), ctx.d_rays_o[lo:hi].double().sum(0, keepdim=True).t()], 1)
+        assert rel(ctx.d_frames[f].view(3, 4), want) < 1e-5
+    # split-phase sharded iteration, no process group: same block; then replayed from a CUDA graph
+    ctx.load_device_inputs(*dev_in)
+    sh = ShardedMappingIteration(ctx)
+    sh.prepare(c, dec, dirs, offs)
+    got = sh.enqueue().clone()
+    assert rel(got, packed) < 1e-5
+    g = sh.build_graph()
+    assert g is not None
+    ctx.packed.fill_(7.0)
+    g.replay(); torch.cuda.synchronize()
+    assert rel(ctx.packed, packed) < 1e-5
