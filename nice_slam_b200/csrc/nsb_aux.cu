@@ -75,6 +75,63 @@ __global__ void pack_kernel(const __grid_constant__ PackArgs A) {
   }
 }
 
+// ---- tensor-core operand images (layout: nsb_common.cuh) --------------------------------------------------------------------
+// hi | lo of a [R x 32] canonical tile whose element (row, k) is get(row, k)
+template <typename F>
+__device__ __forceinline__ void emit_tile(float*& dst, int R, F&& get) {
+  float* hi = dst; float* lo = dst + R * 32;
+  for (int idx = threadIdx.x; idx < R * 32; idx += blockDim.x) {
+    const int r = idx >> 5, k = idx & 31;
+    const float v = get(r, k);
+    const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);          // the 19 bits the tensor core reads (nsb_tc.cuh)
+    const int o = ((r >> 3) * 8 + (k >> 2)) * 32 + (r & 7) * 4 + (k & 3);
+    hi[o] = h; lo[o] = v - h;
+  }
+  dst += 2 * R * 32;
+}
+template <int LV>
+__device__ void pack_operands_level(float* __restrict__ img /* packed image of this level: raw part already written */) {
+  using D = Dec<LV>;
+  const float* W = img;
+  constexpr int PH = D::PH;
+  const int o_wh[5] = {0, D::o_W1, D::o_W2, D::o_W3H, D::o_W4};
+  // forward
+  float* dst = img + op_fwd_offset(LV);
+  for (int i = threadIdx.x; i < kHdrFloats; i += blockDim.x) {
+    float v = 0.0f;
+    if (i < 160) v = W[D::o_b + i];
+    else if (i < 320) v = D::XYZ ? W[D::o_bc + (i - 160)] : 0.0f;
+    else if (i < 324) v = W[D::o_bo + (i - 320)];
+    else if (i >= 336 && i < 464) v = W[D::o_WO + ((i - 336) >> 5) * PH + ((i - 336) & 31)];
+    else if (i >= 464 && i < 464 + 3 * kEmbPad) v = D::XYZ ? W[D::o_B + (i - 464)] : 0.0f;
+    dst[i] = v;
+  }
+  dst += kHdrFloats;
+  if (D::XYZ)
+    for (int h = 0; h < D::CD / 32; h++)
+      emit_tile(dst, 160, [&](int r, int k) { return W[D::o_WC + r * D::PC + 32 * h + k]; });          // row r = 32 i + o
+  for (int b = 0; b < op_nblk(LV); b++)
+    emit_tile(dst, 64, [&](int r, int k) { return W[(r < 32 ? D::o_W0 : D::o_W3E) + (r & 31) * D::PF + 32 * b + k]; });
+  for (int i = 1; i < 5; i++) emit_tile(dst, 32, [&](int r, int k) { return W[o_wh[i] + r * PH + k]; });
+  // backward (transposed operands)
+  dst = img + op_bwd_offset(LV);
+  for (int i = 4; i >= 0; i--) {
+    if (D::XYZ) emit_tile(dst, D::CD, [&](int c, int k) { return W[D::o_WC + (i * 32 + k) * D::PC + c]; });
+    if (i >= 1) emit_tile(dst, 32, [&](int j, int k) { return W[o_wh[i] + k * PH + j]; });
+    if (i == 3 || i == 0) emit_tile(dst, D::FIRSTP, [&](int f, int k) { return W[(i == 0 ? D::o_W0 : D::o_W3E) + k * D::PF + f]; });
+  }
+}
+__global__ void pack_operands_kernel(const __grid_constant__ PackArgs A) {
+  const int lv = blockIdx.x;
+  if (!A.present[lv]) return;
+  switch (lv) {
+    case 0: pack_operands_level<0>(A.packed[0]); break;
+    case 1: pack_operands_level<1>(A.packed[1]); break;
+    case 2: pack_operands_level<2>(A.packed[2]); break;
+    default: pack_operands_level<3>(A.packed[3]); break;
+  }
+}
+
 int launch_unpack_grads(float* const d_packed[4], float* const d_flat[4], cudaStream_t st) {
   PackArgs A; memset(&A, 0, sizeof(A));
   for (int l = 0; l < 4; l++) { A.packed[l] = d_packed[l]; A.flat[l] = d_flat[l]; A.present[l] = d_packed[l] != nullptr && d_flat[l] != nullptr; }
@@ -388,7 +445,7 @@ extern "C" int nsb_version(void) { return NSB_VERSION; }
 extern "C" const char* nsb_last_error(void) { return g_err; }
 extern "C" size_t nsb_flat_decoder_floats(int level) { return level < 0 || level > 3 ? 0 : (size_t)flat_offset(level, 7, 0); }
 extern "C" long long nsb_flat_offset(int level, int kind, int layer) { return level < 0 || level > 3 ? -1 : flat_offset(level, kind, layer); }
-extern "C" size_t nsb_packed_decoder_floats(int level) { return level < 0 || level > 3 ? 0 : (size_t)packed_floats(level); }
+extern "C" size_t nsb_packed_decoder_floats(int level) { return level < 0 || level > 3 ? 0 : (size_t)packed_total_floats(level); }
 
 extern "C" int nsb_pack_decoders(const nsb_decoder_params* const params[4], float* const packed[4], void* stream) {
   if (!params || !packed) { set_error("params / packed NULL"); return NSB_ERR_ARG; }
@@ -404,6 +461,7 @@ extern "C" int nsb_pack_decoders(const nsb_decoder_params* const params[4], floa
     A.p[l] = p; A.packed[l] = packed[l]; A.present[l] = 1;
   }
   pack_kernel<0><<<4, 256, 0, (cudaStream_t)stream>>>(A);
+  pack_operands_kernel<<<4, 512, 0, (cudaStream_t)stream>>>(A);          // tensor-core operand images behind the fp32 image
   return check_cuda(cudaGetLastError(), "pack_decoders launch");
 }
 

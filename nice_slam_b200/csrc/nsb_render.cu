@@ -411,24 +411,27 @@ __global__ void __launch_bounds__(tc::kThreads, 1) render_fwd_tc_kernel(const __
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = threadIdx.x & (tc::TM - 1), cg = threadIdx.x >> 7;
   tc::TcSmem t;
-  tc::tc_carve(smem_raw, t);
+  tc::tc_carve(smem_raw, t, false);
   Smem sm;
-  smem_layout(0, P.max_pts, P.max_rays, 0, 0, false, &sm, smem_raw + ((tc::tc_smem_bytes() + 127) & ~size_t(127)));
+  smem_layout(0, P.max_pts, P.max_rays, 0, 0, false, &sm, smem_raw + ((tc::tc_smem_bytes(false) + 127) & ~size_t(127)));
   const BlockRange b = block_range(P);
   const int Pb = b.Pb;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(t.tmem)), "r"(tc::kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (threadIdx.x == 0) { mbar_init(t.bar, 1); mbar_init(t.wbar, 1); mbar_fence_init(); }
-  fwd_sample_sort(P, sm, b);                                     // contains __syncthreads(): TMEM address + barrier are visible after it
+  tc::Pipe pp; pp.par = 0; pp.hb = 0; pp.prefetched = true;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < tc::kNumBarsFwd; i++) mbar_init(t.bars + i, 1);
+    mbar_fence_init();
+    tc::issue_fwd_loads(P, t, P.dec[0], 0);                      // the first decoder's weights arrive under the sampling prologue
+  }
+  fwd_sample_sort(P, sm, b);                                     // contains __syncthreads(): TMEM address + barriers are visible after it
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = *t.tmem;
 
-  uint32_t parity = 0, wparity = 0;
-  bool prefetched = false;
   const int ntiles = (Pb + tc::TM - 1) / tc::TM;
   for (int tile = 0; tile < ntiles; tile++) {
     const int lp = tile * tc::TM + row;
@@ -451,7 +454,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) render_fwd_tc_kernel(const __
       float out[4];
       uint32_t* gm = (P.fo.masks != nullptr && lp < Pb) ? P.fo.masks + ((((long long)blockIdx.x * P.rays_per_block) * P.S + lp) * 15 + qd * 5) : nullptr;
       const int next_lv = qd + 1 < P.n_dec ? P.dec[qd + 1] : (tile + 1 < ntiles ? P.dec[0] : -1);
-      tc::tile_forward<false>(P, t, d, lv, G, tmem, parity, wparity, out, gm, prefetched, next_lv);
+      tc::tile_forward(P, t, d, lv, G, tmem, pp, out, gm, next_lv);
       if (lv == 3) { c0 = out[0]; c1 = out[1]; c2 = out[2]; } else occ += out[0];
       if (qd == 0 && cg == 0 && lp < Pb && P.fo.corner_idx != nullptr) {
         const nsb_grid& g = P.in.grid[lv];
@@ -635,9 +638,9 @@ __global__ void __launch_bounds__(tc::kThreads, 1) render_bwd_tc_kernel(const __
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = threadIdx.x & (tc::TM - 1);
   tc::TcSmem t;
-  tc::tc_carve(smem_raw, t);
+  tc::tc_carve(smem_raw, t, true);
   Smem sm;
-  smem_layout(0, P.max_pts, P.max_rays, 0, 0, true, &sm, smem_raw + ((tc::tc_smem_bytes() + 127) & ~size_t(127)));
+  smem_layout(0, P.max_pts, P.max_rays, 0, 0, true, &sm, smem_raw + ((tc::tc_smem_bytes(true) + 127) & ~size_t(127)));
   __shared__ float gC[kMaxRaysPerBlock * 3];
   const int r0 = blockIdx.x * P.rays_per_block;
   const int nr = P.in.n_rays - r0 < P.rays_per_block ? P.in.n_rays - r0 : P.rays_per_block;
@@ -646,15 +649,18 @@ __global__ void __launch_bounds__(tc::kThreads, 1) render_bwd_tc_kernel(const __
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(t.tmem)), "r"(tc::kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (threadIdx.x == 0) { mbar_init(t.bar, 1); mbar_init(t.wbar, 1); mbar_fence_init(); }
+  tc::Pipe pp; pp.par = 0; pp.hb = 0; pp.prefetched = true;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < tc::kNumBarsBwd; i++) mbar_init(t.bars + i, 1);
+    mbar_fence_init();
+    tc::issue_bwd_loads(P, t, P.dec[0], 0);                      // the first decoder's operands arrive under the compositing prologue
+  }
   bwd_prologue(P, sm, r0, nr, Pb, warp, tc::kThreads / 32, lane, gC);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = *t.tmem;
 
-  uint32_t parity = 0, wparity = 0;
-  bool prefetched = false;
   const int ntiles = (Pb + tc::TM - 1) / tc::TM;
   for (int tile = 0; tile < ntiles; tile++) {
     const int lp = tile * tc::TM + row;
@@ -669,19 +675,15 @@ __global__ void __launch_bounds__(tc::kThreads, 1) render_bwd_tc_kernel(const __
     for (int qd = 0; qd < P.n_dec; qd++) {
       const int lv = P.dec[qd];
       const DecRT d = make_dec(lv);
-      const uint32_t* gm = P.bw.masks != nullptr ? P.bw.masks + ((((long long)blockIdx.x * P.rays_per_block) * P.S + lpc) * 15 + P.dec_pos[qd] * 5) : nullptr;
-      if (gm == nullptr) { float out[4]; bool pf0 = false; tc::tile_forward<true>(P, t, d, lv, G, tmem, parity, wparity, out, nullptr, pf0, -1); }
+      const uint32_t* gm = P.bw.masks + ((((long long)blockIdx.x * P.rays_per_block) * P.S + lpc) * 15 + P.dec_pos[qd] * 5);   // saved by the forward kernel
       float g_out[4] = {0.f, 0.f, 0.f, 0.f};
       if (lp < Pb) {
         if (lv == 3) { const float w = sm.wgt[lp]; g_out[0] = w * gC[3 * ray]; g_out[1] = w * gC[3 * ray + 1]; g_out[2] = w * gC[3 * ray + 2]; }
         else g_out[0] = sm.gocc[lp];
       }
-      tc::tile_backward(P, t, d, lv, G, tmem, parity, wparity, g_out, gm, prefetched);
-      __syncthreads();                                           // dL/dc rows + the embedding partials are visible; the packed image is dead
-      if (gm != nullptr) {                                       // prefetch the next decoder's image under the scatter below
-        const int next_lv = qd + 1 < P.n_dec ? P.dec[qd + 1] : (tile + 1 < ntiles ? P.dec[0] : -1);
-        if (next_lv >= 0) { if (threadIdx.x == 0) tc::issue_decoder_tma(P, t, next_lv); prefetched = true; }
-      }
+      const int next_lv = qd + 1 < P.n_dec ? P.dec[qd + 1] : (tile + 1 < ntiles ? P.dec[0] : -1);
+      tc::tile_backward(P, t, d, lv, G, tmem, pp, g_out, gm, next_lv);
+      __syncthreads();                                           // dL/dc rows + the embedding partials are visible
       const double* bb = lv == 0 ? P.in.coarse_bound : P.in.bound;
       const double sc[3] = {2.0 / (bb[1] - bb[0]), 2.0 / (bb[3] - bb[2]), 2.0 / (bb[5] - bb[4])};      // d(normalised)/dp, common.py:280-282
       const float* xn = lv == 0 ? G.xnc : G.xn;
@@ -778,7 +780,7 @@ static void choose_config(int n_items, int S, int rows, bool bwd, int wbytes, in
 
 static int g_mlp_backend = 0;      // 0 = auto (tensor-core forward), 1 = SIMT, 2 = tcgen05
 static size_t tc_total_smem(int max_pts, int max_rays, bool bwd = false) {
-  return ((tc::tc_smem_bytes() + 127) & ~size_t(127)) + smem_layout(0, max_pts, max_rays, 0, 0, bwd, nullptr, nullptr);
+  return ((tc::tc_smem_bytes(bwd) + 127) & ~size_t(127)) + smem_layout(0, max_pts, max_rays, 0, 0, bwd, nullptr, nullptr);
 }
 
 static bool g_attr_set = false;
@@ -886,7 +888,7 @@ extern "C" int nsb_render_backward(const nsb_render_inputs* in, const nsb_backwa
   int warps; size_t smem;
   choose_config(in->n_rays, K.S, kRowsBwd, true, K.wbytes, 8, &K, &warps, &smem);
   if (smem > kSmemCap) { set_error("shared-memory budget exceeded (%zu bytes)", smem); return NSB_ERR_UNSUPPORTED; }
-  if (g_mlp_backend != 1 && K.S <= kMaxPtsTc) {
+  if (g_mlp_backend != 1 && K.S <= kMaxPtsTc && bw->masks != nullptr) {     // (no saved ReLU masks -> FP32 kernel, which recomputes the forward)
     // Tensor-core kernel for the decoders that only need input gradients (rays, voxels).  Decoders whose WEIGHT gradients are
     // requested (the colour decoder in the mapper's colour stage, Mapper.py:339-341) go through the FP32-FMA kernel in a second
     // launch that adds its share of the ray gradients.

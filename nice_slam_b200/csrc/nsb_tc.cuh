@@ -106,54 +106,74 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 }
 static_assert(kCW == 8, "epilogues use tcgen05.ld.32x32b.x8");
 
-// shared-memory regions of the tensor-core path (all 1024-byte aligned so that every tile start is 16-byte aligned)
+// ---- shared memory and barriers of the tensor-core kernels ---------------------------------------------------------------------
+// Weights are never staged by threads: nsb_pack_decoders leaves every MMA B operand as a ready-to-use hi|lo canonical tile in global
+// memory (operand images, nsb_common.cuh) and one elected thread streams them into fixed shared-memory regions with TMA bulk copies,
+// one mbarrier per region, always at least one consumer step ahead of the MMAs that read them.
 struct TcSmem {
-  float* x;        // 64 KB: C hi|lo (128 x 64 each)  -- later  E hi|lo (128 x 32) + H hi|lo (128 x 32), or two E blocks
-  float* wa;       // weight stage A: hi|lo, 32 x 96 each (24 KB)
-  float* wb;       // weight stage B: 24 KB, contiguous with wa
-  float* bias;     // 464 floats: b[5][32] | bc[5][32] | bo[4] | pad[12] | Wo[4][32]
-  uint32_t* masks; // [5][128] relu masks of the recomputed forward (backward kernel)
-  float* wraw;     // packed fp32 image of the current decoder (one TMA bulk copy per decoder and tile, overlapped with the gather)
-  uint64_t* wbar;  // TMA completion barrier
-  uint64_t* bar;   // MMA completion barrier
-  uint32_t* tmem;  // TMEM base address slot
+  float* x;          // 64 KB activation tiles: C hi|lo (128 x cd)  -> later E block 1 (first 32 KB) and H (second 32 KB); backward: G | DU, then dL/dc
+  float* e;          // forward: 32 KB E blocks 0 and 2, later the output-layer partial sums
+  float* wF;         // forward: fc_c chunk (40 KB)
+  float* wL;         // forward: two layer-0 chunks (2 x 16 KB)
+  float* wH;         // forward: hidden weights of layers 1..4 (32 KB)
+  float* wS;         // backward: two layer stages (2 x 48 KB)
+  float* hdr;        // 2 x kHdrFloats: biases, output weights, embedding matrix (double-buffered over decoders)
+  uint64_t* bars;    // mbarriers (see the B_* indices)
+  uint32_t* tmem;    // TMEM base address slot
 };
 constexpr int kXFloats = 2 * TM * 64;            // 16384 floats = 64 KB
-constexpr int kWaFloats = 2 * 32 * 96;           // 24 KB
-constexpr int kWbFloats = 2 * 32 * 96;           // 24 KB (contiguous with wa: 48 KB stage)
-__host__ __device__ inline size_t tc_smem_bytes() { return (size_t)(kXFloats + kWaFloats + kWbFloats + 464 + 5 * TM + kMaxPacked) * 4 + 64; }
-__device__ __forceinline__ void tc_carve(unsigned char* base, TcSmem& t) {
+constexpr int kEFloats = 2 * TM * 32;            // 32 KB
+// barrier indices.  forward: TMA arrivals W_*, MMA commits M_*; backward reuses W_HDR, W_S0/1 and M_B.
+enum { W_HDR = 0, W_F, W_L0, W_L1, W_H, M_FC, M_L0, M_L1, M_H, kNumBarsFwd, W_S0 = 1, W_S1 = 2, M_B = 3, kNumBarsBwd = 4 };
+__host__ __device__ inline size_t tc_smem_bytes(bool bwd) {
+  const size_t fl = bwd ? (size_t)kXFloats + 2 * kBwdStageFloats + 2 * kHdrFloats
+                        : (size_t)kXFloats + kEFloats + kFcChunk + 2 * kL0Chunk + 4 * kHChunk + 2 * kHdrFloats;
+  return fl * 4 + 128;
+}
+__device__ __forceinline__ void tc_carve(unsigned char* base, TcSmem& t, bool bwd) {
   float* f = reinterpret_cast<float*>(base);
   t.x = f; f += kXFloats;
-  t.wa = f; f += kWaFloats;
-  t.wb = f; f += kWbFloats;
-  t.bias = f; f += 464;
-  t.masks = reinterpret_cast<uint32_t*>(f); f += 5 * TM;
-  t.wraw = f; f += kMaxPacked;
-  t.bar = reinterpret_cast<uint64_t*>(f);
-  t.wbar = reinterpret_cast<uint64_t*>(f + 2);
-  t.tmem = reinterpret_cast<uint32_t*>(f + 4);
+  t.e = t.wF = t.wL = t.wH = t.wS = nullptr;
+  if (bwd) { t.wS = f; f += 2 * kBwdStageFloats; }
+  else { t.e = f; f += kEFloats; t.wF = f; f += kFcChunk; t.wL = f; f += 2 * kL0Chunk; t.wH = f; f += 4 * kHChunk; }
+  t.hdr = f; f += 2 * kHdrFloats;
+  t.bars = reinterpret_cast<uint64_t*>(f);
+  t.tmem = reinterpret_cast<uint32_t*>(f + 2 * 12);
 }
-
-// one elected thread: TMA bulk copy of decoder `lv`'s packed image into t.wraw, completion on t.wbar
-__device__ __forceinline__ void issue_decoder_tma(const KParams& P, const TcSmem& t, int lv) {
-  fence_proxy_async();
-  const uint32_t bytes = (uint32_t)packed_floats(lv) * 4u;
-  mbar_expect_tx(t.wbar, bytes);
-  const char* src = reinterpret_cast<const char*>(P.in.packed[lv]);
-  char* dst = reinterpret_cast<char*>(t.wraw);
-  for (uint32_t off = 0; off < bytes; off += 32768u) tma_bulk_g2s(dst + off, src + off, bytes - off < 32768u ? bytes - off : 32768u, t.wbar);
+// running state of the weight pipeline, identical in every thread (control flow is CTA-uniform)
+struct Pipe {
+  uint32_t par;          // bit i = parity the next wait on barrier i expects
+  int hb;                // header buffer of the current decoder
+  bool prefetched;       // the current decoder's first loads are already in flight
+};
+__device__ __forceinline__ void pipe_wait(const TcSmem& t, Pipe& p, int i, bool really = true) {
+  if (really) mbar_wait(t.bars + i, (p.par >> i) & 1u);
+  p.par ^= 1u << i;
 }
-
-// stage rows [0,32) x columns [c0, c0+K) of a packed fp32 matrix (row pitch `pitch`) as a canonical hi|lo tile pair of width K
-__device__ __forceinline__ void stage_w(float* __restrict__ dst, const float* __restrict__ src, int pitch, int c0, int K) {
-  float* hi = dst; float* lo = dst + 32 * K;
-  const int kq4 = K >> 2;
-  for (int i = threadIdx.x; i < 32 * kq4; i += blockDim.x) {
-    const int n = i / kq4, kq = i - n * kq4;
-    const float4 v = *reinterpret_cast<const float4*>(src + n * pitch + c0 + 4 * kq);
-    put4(hi, lo, n, kq, K, v);
-  }
+// one elected thread: bulk copy `floats` floats, completion on barrier i
+__device__ __forceinline__ void tma_load(const TcSmem& t, int i, float* dst, const float* src, int floats) {
+  const uint32_t bytes = (uint32_t)floats * 4u;
+  mbar_expect_tx(t.bars + i, bytes);
+  for (uint32_t off = 0; off < bytes; off += 32768u)
+    tma_bulk_g2s(reinterpret_cast<char*>(dst) + off, reinterpret_cast<const char*>(src) + off, bytes - off < 32768u ? bytes - off : 32768u, t.bars + i);
+}
+// first loads of decoder lv (forward): header, first fc_c chunk, first two layer-0 chunks, hidden weights
+__device__ __forceinline__ void issue_fwd_loads(const KParams& P, const TcSmem& t, int lv, int hb) {
+  const float* img = P.in.packed[lv] + op_fwd_offset(lv);
+  tma_load(t, W_HDR, t.hdr + hb * kHdrFloats, img, kHdrFloats);
+  const float* fc = img + kHdrFloats;
+  if (lv != 0) tma_load(t, W_F, t.wF, fc, kFcChunk);
+  const float* l0 = fc + op_fc_floats(lv);
+  tma_load(t, W_L0, t.wL, l0, kL0Chunk);
+  if (lv != 0) tma_load(t, W_L1, t.wL + kL0Chunk, l0 + kL0Chunk, kL0Chunk);
+  tma_load(t, W_H, t.wH, l0 + op_nblk(lv) * kL0Chunk, 4 * kHChunk);
+}
+// first loads of decoder lv (backward): header, layers 4 and 3
+__device__ __forceinline__ void issue_bwd_loads(const KParams& P, const TcSmem& t, int lv, int hb) {
+  tma_load(t, W_HDR, t.hdr + hb * kHdrFloats, P.in.packed[lv] + op_fwd_offset(lv), kHdrFloats);
+  const float* img = P.in.packed[lv] + op_bwd_offset(lv);
+  tma_load(t, W_S0, t.wS, img + op_bwd_layer_offset(lv, 4), op_bwd_layer_floats(lv, 4));
+  tma_load(t, W_S1, t.wS + kBwdStageFloats, img + op_bwd_layer_offset(lv, 3), op_bwd_layer_floats(lv, 3));
 }
 
 // 8 lanes per point, 4 points per pass: gather the 32 channels of `g` into columns [col0, col0+32) of the C tile.  Warp w serves
@@ -206,89 +226,84 @@ __device__ __forceinline__ void embed_row(float* __restrict__ e_hi, float* __res
 }
 
 // Forward of decoder `lv` for one 128-point tile.  Thread tid = (row = tid & 127, column group cg = tid >> 7).  On return out[o] holds
-// the decoder outputs of this thread's point (identical in the kCG threads of a row).  `parity` / `wparity` are the running phases of
-// t.bar / t.wbar.
-// TMEM: D1 = cols [0,32) (layers 0,1,2,4), D2 = [32,192) (fc_c of the five layers), D3 = [192,224) (layer 3; its skip part
-// E * W3E^T is accumulated while the embedding blocks are live for layer 0, so the embedding is computed once).
-// Sequential MMA batches per decoder: fc_c 1-2, layer 0: 3 (one per embedding block), layers 1..4: one each.
-template <bool KEEP>
+// the decoder outputs of this thread's point (identical in the kCG threads of a row).
+// TMEM: D1 = cols [0,32) (layers 0,1,2,4), D3 = [32,64) (layer 3; its skip part E * W3E^T is accumulated while the embedding blocks are
+// live for layer 0, so the embedding is computed once, by one N = 64 MMA per block), D2 = [64,224) (fc_c of the five layers, one N = 160 MMA).
+// Step order (xyz decoder):  gather C | fc_c MMAs (async) | E0 -> MMA | wait fc_c | E1 -> MMA | wait E0 | E2 -> MMA | five serial
+// epilogue -> MMA steps.  Each embedding block is computed while the previous block's MMAs run.
 __device__ __forceinline__ void tile_forward(const KParams& P, const TcSmem& t, const DecRT& d, int lv, const PointGeom& G,
-                                             uint32_t tmem, uint32_t& parity, uint32_t& wparity, float (&out)[4],
+                                             uint32_t tmem, Pipe& pp, float (&out)[4],
                                              uint32_t* __restrict__ gmask /* global [5] slot of this point+decoder, or nullptr */,
-                                             bool& prefetched /* this decoder's image is already in flight */, int next_lv /* prefetch after the last use, or -1 */) {
+                                             int next_lv /* decoder whose weights to prefetch once this one's regions are free, or -1 */) {
   const int row = threadIdx.x & (TM - 1), cg = threadIdx.x >> 7, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* Wg = t.wraw;                                // packed fp32 image of this decoder, staged by TMA below
-  float* c_hi = t.x; float* c_lo = t.x + TM * d.cd;
+  const bool t0 = threadIdx.x == 0;
   const uint32_t my = ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kCW * cg);      // TMEM lane quadrant + first column of this thread
-  const uint32_t d1 = tmem + my, d2 = tmem + 32u + my, d3 = tmem + 192u + my;
-  constexpr int PH = Dec<1>::PH;
+  const uint32_t d1 = tmem + my, d3 = tmem + 32u + my, d2 = tmem + 64u + my;
+  const float* hdr = t.hdr + pp.hb * kHdrFloats;
+  float* c_hi = t.x; float* c_lo = t.x + TM * d.cd;
 
-  __syncthreads();                       // previous decoder / tile: all reads of the weight image and of the tiles are done
-  if (!prefetched && threadIdx.x == 0) issue_decoder_tma(P, t, lv);      // overlaps with the gather below
-  prefetched = false;
+  __syncthreads();                       // previous decoder / tile: every read of x, e and of the header buffers is done
+  if (!pp.prefetched && t0) issue_fwd_loads(P, t, lv, pp.hb);
+  pp.prefetched = false;
   // ---- gather -> C tile
   const float* xn = lv == 0 ? G.xnc : G.xn;
   gather_rows(P.in.grid[lv], c_hi, c_lo, d.cd, 0, xn, warp, lane);
   if (lv == 2) gather_rows(P.in.grid[1], c_hi, c_lo, d.cd, 32, G.xn, warp, lane);
-  mbar_wait(t.wbar, wparity); wparity ^= 1u;
-  // biases + output weights -> shared (b[5][32] | bc[5][32] | bo[4] | pad | Wo[4][32])
-  for (int i = threadIdx.x; i < 464; i += blockDim.x) {
-    float v = 0.0f;
-    if (i < 160) v = Wg[d.o_b + i];
-    else if (i < 320) v = d.xyz ? Wg[d.o_bc + (i - 160)] : 0.0f;
-    else if (i < 324) v = Wg[d.o_bo + (i - 320)];
-    else if (i >= 336) v = Wg[d.o_WO + ((i - 336) >> 5) * PH + ((i - 336) & 31)];
-    t.bias[i] = v;
-  }
-  // ---- D2[:, 32i..32i+32) = C * Wc_i^T  (xyz decoders only); as many layers per batch as the 48 KB stage holds
+  // ---- D2 = C * [Wc_0; ..; Wc_4]^T  (xyz decoders), one 32-wide K half per chunk; not waited for until x is needed again
   if (d.xyz) {
-    const int per = d.cd == 64 ? 3 : 5;
-    for (int i0 = 0; i0 < 5; i0 += per) {
-      const int i1 = i0 + per < 5 ? i0 + per : 5;
-      for (int i = i0; i < i1; i++) stage_w(t.wa + (i - i0) * 2 * 32 * d.cd, Wg + d.o_WC + i * 32 * d.pc, d.pc, 0, d.cd);
-      publish_operands();
-      if (threadIdx.x == 0) {
+    publish_operands();
+    for (int h = 0; h < (d.cd >> 5); h++) {
+      if (t0) {
+        if (h > 0) { mbar_wait(t.bars + M_FC, (pp.par >> M_FC) & 1u);          // chunk 0 consumed: reload the region with chunk 1
+                     tma_load(t, W_F, t.wF, P.in.packed[lv] + op_fwd_offset(lv) + kHdrFloats + kFcChunk, kFcChunk); }
+        mbar_wait(t.bars + W_F, (pp.par >> W_F) & 1u);
         tc_fence_after();
-        for (int i = i0; i < i1; i++) {
-          uint32_t acc = 0;
-          const float* w = t.wa + (i - i0) * 2 * 32 * d.cd;
-          mma_3x(tmem + 32u + 32u * i, c_hi, c_lo, d.cd, 0, w, w + 32 * d.cd, d.cd, 0, d.cd >> 3, 32, acc);
-        }
-        mma_commit(t.bar);
+        uint32_t acc = h > 0 ? 1u : 0u;
+        mma_3x(tmem + 64u, c_hi, c_lo, d.cd, 32 * h, t.wF, t.wF + 160 * 32, 32, 0, 4, 160, acc);
+        mma_commit(t.bars + M_FC);
       }
+      pp.par ^= 1u << W_F;
+      if (h > 0) pp.par ^= 1u << M_FC;
       __syncwarp();
-      mbar_wait(t.bar, parity); parity ^= 1u;
-      tc_fence_after();
     }
   }
-  // ---- layer 0 (and the skip part of layer 3): first input = Fourier embedding (three 32-feature blocks) or, coarse, C itself
-  float* e_hi = d.xyz ? t.x : c_hi;
-  float* e_lo = d.xyz ? t.x + TM * 32 : c_lo;
+  // ---- layer 0 and the skip part of layer 3: [D1 | D3] += E_blk * [W0_blk; W3E_blk]^T.  E = Fourier embedding, or (coarse) C itself.
+  const float* B = hdr + 464;
+  const int nblk = d.xyz ? 3 : 1;
+  bool fc_pending = d.xyz != 0;
+  for (int blk = 0; blk < nblk; blk++) {
+    float* e_hi = !d.xyz ? c_hi : ((blk & 1) ? t.x : t.e);
+    float* e_lo = !d.xyz ? c_lo : e_hi + TM * 32;
+    if (d.xyz) {
+      if (blk == 0) pipe_wait(t, pp, W_HDR);                                   // embedding matrix
+      if (blk == 1) { pipe_wait(t, pp, M_FC); fc_pending = false; tc_fence_after(); }      // C is dead: x may be overwritten
+      if (blk == 2) {                                                          // block 0 consumed: e and weight slot 0 are free
+        pipe_wait(t, pp, M_L0); tc_fence_after();
+        if (t0) tma_load(t, W_L0, t.wL, P.in.packed[lv] + op_fwd_offset(lv) + kHdrFloats + op_fc_floats(lv) + 2 * kL0Chunk, kL0Chunk);
+      }
+      embed_row(e_hi, e_lo, B, G.pf, row, cg, blk);
+    }
+    publish_operands();
+    const int slot = blk & 1;
+    if (t0) {
+      mbar_wait(t.bars + W_L0 + slot, (pp.par >> (W_L0 + slot)) & 1u);
+      tc_fence_after();
+      uint32_t acc = blk > 0 ? 1u : 0u;
+      const float* w = t.wL + slot * kL0Chunk;
+      mma_3x(tmem, e_hi, e_lo, 32, 0, w, w + 64 * 32, 32, 0, 4, 64, acc);
+      mma_commit(t.bars + M_L0 + slot);
+    }
+    pp.par ^= 1u << (W_L0 + slot);
+    __syncwarp();
+  }
+  if (!d.xyz) pipe_wait(t, pp, W_HDR);
+  if (fc_pending) pipe_wait(t, pp, M_FC);
+  if (nblk > 1) pipe_wait(t, pp, M_L1);
+  pipe_wait(t, pp, M_L0);                                   // (blocks 0/2 use slot 0: the last commit on it is block nblk-1 or 2)
+  tc_fence_after();
   float* h_hi = t.x + 2 * TM * 32;
   float* h_lo = t.x + 3 * TM * 32;
-  {
-    uint32_t acc1 = 0, acc3 = 0;
-    const int nblk = d.xyz ? 3 : 1;
-    for (int blk = 0; blk < nblk; blk++) {
-      stage_w(t.wa, Wg + d.o_W0, d.pf, 32 * blk, 32);
-      stage_w(t.wa + 2 * 32 * 32, Wg + d.o_W3E, d.pf, 32 * blk, 32);
-      if (d.xyz) embed_row(e_hi, e_lo, Wg + d.o_B, G.pf, row, cg, blk);
-      publish_operands();
-      if (threadIdx.x == 0) {
-        tc_fence_after();
-        mma_3x(tmem, e_hi, e_lo, 32, 0, t.wa, t.wa + 32 * 32, 32, 0, 4, 32, acc1);
-        mma_3x(tmem + 192u, e_hi, e_lo, 32, 0, t.wa + 2 * 32 * 32, t.wa + 3 * 32 * 32, 32, 0, 4, 32, acc3);
-        mma_commit(t.bar);
-      }
-      __syncwarp();
-      mbar_wait(t.bar, parity); parity ^= 1u;              // E buffer / stage buffers free again
-      tc_fence_after();
-    }
-  }
-  // hidden-part weights of layers 1..4, all at once (4 x 8 KB): no staging on the critical path of the remaining layers
-  for (int i = 1; i < 5; i++) stage_w(t.wa + (i - 1) * 2 * 32 * 32, Wg + dec_wh(d, i), PH, 0, 32);
   float h[kCW];
-  uint8_t* smask = reinterpret_cast<uint8_t*>(t.masks);
 #pragma unroll 1
   for (int i = 0; i < 5; i++) {
     // ---- epilogue of layer i (this thread's kCW columns): h = relu(D + b_i) + (D2_i + bc_i)
@@ -296,38 +311,36 @@ __device__ __forceinline__ void tile_forward(const KParams& P, const TcSmem& t, 
     tmem_ld8(i == 3 ? d3 : d1, v1);
     uint32_t m = 0;
 #pragma unroll
-    for (int j = 0; j < kCW; j++) { const float u = v1[j] + t.bias[i * 32 + kCW * cg + j]; h[j] = u > 0.0f ? u : 0.0f; m |= u > 0.0f ? (1u << j) : 0u; }
-    if (KEEP) smask[(i * TM + row) * 4 + cg] = (uint8_t)m;                           // byte cg of the 32-bit ReLU mask word
-    if (gmask != nullptr) reinterpret_cast<uint8_t*>(gmask)[i * 4 + cg] = (uint8_t)m;
+    for (int j = 0; j < kCW; j++) { const float u = v1[j] + hdr[i * 32 + kCW * cg + j]; h[j] = u > 0.0f ? u : 0.0f; m |= u > 0.0f ? (1u << j) : 0u; }
+    if (gmask != nullptr) reinterpret_cast<uint8_t*>(gmask)[i * 4 + cg] = (uint8_t)m;      // byte cg of the 32-bit ReLU mask word
     if (d.xyz) {
       float v2[kCW];
       tmem_ld8(d2 + 32u * i, v2);
 #pragma unroll
-      for (int j = 0; j < kCW; j++) h[j] += v2[j] + t.bias[160 + i * 32 + kCW * cg + j];
+      for (int j = 0; j < kCW; j++) h[j] += v2[j] + hdr[160 + i * 32 + kCW * cg + j];
     }
     if (i == 4) break;
 #pragma unroll
     for (int k = 0; k < kKQ; k++) put4(h_hi, h_lo, row, kKQ * cg + k, 32, make_float4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]));
     publish_operands();                                      // (also orders this layer's TMEM reads before the next MMAs)
-    if (i == 0 && next_lv >= 0 && !KEEP) {                   // the packed image is dead (hidden weights + biases are staged): prefetch the next one
-      if (threadIdx.x == 0) issue_decoder_tma(P, t, next_lv);
-      prefetched = true;
-    }
-    if (threadIdx.x == 0) {
+    if (t0) {
+      if (i == 0) mbar_wait(t.bars + W_H, (pp.par >> W_H) & 1u);
       tc_fence_after();
-      const float* w = t.wa + i * 2 * 32 * 32;               // hidden weights of layer i+1
+      const float* w = t.wH + i * kHChunk;                   // hidden weights of layer i+1
       uint32_t acc = (i + 1 == 3) ? 1u : 0u;                 // layer 3 accumulates onto E * W3E^T
-      mma_3x((i + 1 == 3) ? tmem + 192u : tmem, h_hi, h_lo, 32, 0, w, w + 32 * 32, 32, 0, 4, 32, acc);
-      mma_commit(t.bar);
+      mma_3x((i + 1 == 3) ? tmem + 32u : tmem, h_hi, h_lo, 32, 0, w, w + 32 * 32, 32, 0, 4, 32, acc);
+      mma_commit(t.bars + M_H);
     }
+    if (i == 0) pp.par ^= 1u << W_H;
     __syncwarp();
-    mbar_wait(t.bar, parity); parity ^= 1u;
+    pipe_wait(t, pp, M_H);
     tc_fence_after();
   }
   tc_fence_before();
+  // every weight region is free again: prefetch the next decoder's first chunks under the output layer and the next gather
+  if (next_lv >= 0) { if (t0) issue_fwd_loads(P, t, next_lv, pp.hb ^ 1); pp.prefetched = true; }
   // ---- output layer: partial dot products over this thread's columns, summed over the kCG threads of the row through shared memory
-  // (the H tile is dead: layer 4 has consumed it)
-  float* part = h_hi;                                        // [kCG][TM][4]
+  float* part = d.xyz ? t.e : t.x;                           // [kCG][TM][4]   (E blocks / the coarse C tile are dead)
   {
     float s[4];
 #pragma unroll
@@ -335,110 +348,86 @@ __device__ __forceinline__ void tile_forward(const KParams& P, const TcSmem& t, 
       s[o] = 0.0f;
       if (o < d.no) {
 #pragma unroll
-        for (int j = 0; j < kCW; j++) s[o] = fmaf(h[j], t.bias[336 + o * 32 + kCW * cg + j], s[o]);
+        for (int j = 0; j < kCW; j++) s[o] = fmaf(h[j], hdr[336 + o * 32 + kCW * cg + j], s[o]);
       }
     }
     *reinterpret_cast<float4*>(part + (cg * TM + row) * 4) = make_float4(s[0], s[1], s[2], s[3]);
   }
   __syncthreads();
 #pragma unroll
-  for (int o = 0; o < 4; o++) out[o] = t.bias[320 + o];
+  for (int o = 0; o < 4; o++) out[o] = hdr[320 + o];
 #pragma unroll
   for (int c = 0; c < kCG; c++) {
     const float4 v = *reinterpret_cast<const float4*>(part + (c * TM + row) * 4);
     out[0] += v.x; out[1] += v.y; out[2] += v.z; out[3] += v.w;
   }
+  pp.hb ^= 1;
 }
 
-// transposed staging for the backward GEMMs: B[n][k] = W[k][c0 + n] for n < NR, k < 32  (canonical hi|lo tiles of width 32)
-__device__ __forceinline__ void stage_wT(float* __restrict__ dst, const float* __restrict__ src, int pitch, int c0, int NR) {
-  float* hi = dst; float* lo = dst + NR * 32;
-  const int nq4 = NR >> 2;
-  for (int i = threadIdx.x; i < 32 * nq4; i += blockDim.x) {
-    const int k = i / nq4, nq = i - k * nq4;
-    const float4 v = *reinterpret_cast<const float4*>(src + k * pitch + c0 + 4 * nq);
-    const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int n = 4 * nq + j;
-      const int idx = ((n >> 3) * 8 + (k >> 2)) * 32 + (n & 7) * 4 + (k & 3);
-      const float h = to_tf32(vv[j]);
-      hi[idx] = h; lo[idx] = vv[j] - h;
-    }
-  }
-}
-
-// Backward of decoder `lv` for one tile, input gradients only (rays + grid voxels; no decoder-weight gradients).
-// Precondition: tile_forward<true> just ran for the same tile (masks in t.masks) or gmask points at the saved masks.
-// g_out = dL/d out of this thread's point.  Writes dL/dc of every row to `dcs` ([128][cd] fp32, aliasing t.x) and this thread's
-// share of dL/dp through the Fourier embedding to dpe_part ([kCG][128][4] fp32 at t.x + 2*TM*32; summed by the caller after a barrier).
+// Backward of decoder `lv` for one tile, input gradients only (rays + grid voxels; decoder-weight gradients go through the FP32 kernel).
+// gmask = the ReLU masks the forward kernel saved for this point+decoder.  g_out = dL/d out of this thread's point.
+// Writes dL/dc of every row to `dcs` ([128][cd] fp32, aliasing t.x) and this thread's share of dL/dp through the Fourier embedding to
+// [kCG][128][4] fp32 at t.x + 2*TM*32 (summed by the caller after a barrier: dpe_sum).
+// TMEM: D1 = [0,32) (g of the next layer), DC = [32,96) (dL/dc, accumulated over the layers), DF = [96,192) (dL/d first input).
+// One MMA batch per layer; the operands of layer i-2 are fetched by TMA while layer i computes (two 48 KB stages).
 __device__ __forceinline__ void tile_backward(const KParams& P, const TcSmem& t, const DecRT& d, int lv, const PointGeom& G,
-                                              uint32_t tmem, uint32_t& parity, uint32_t& wparity, const float (&g_out)[4],
-                                              const uint32_t* __restrict__ gmask /* saved masks of this point+decoder or nullptr */,
-                                              bool& prefetched) {
+                                              uint32_t tmem, Pipe& pp, const float (&g_out)[4], const uint32_t* __restrict__ gmask,
+                                              int next_lv) {
   const int row = threadIdx.x & (TM - 1), cg = threadIdx.x >> 7, warp = threadIdx.x >> 5;
-  const float* Wg = t.wraw;                                 // resident from the recomputed forward, or loaded below
+  const bool t0 = threadIdx.x == 0;
+  const float* hdr = t.hdr + pp.hb * kHdrFloats;
+  __syncthreads();                                          // previous decoder's scatter (reads of x) is done
+  if (!pp.prefetched && t0) issue_bwd_loads(P, t, lv, pp.hb);
+  pp.prefetched = false;
   uint32_t mlo = 0, mhi = 0;                                // this thread's 8 ReLU bits of layers 0..3 (one byte each) and of layer 4
-  if (gmask != nullptr) {                                   // no forward recompute: bring the decoder image in and the masks
-    __syncthreads();
-    if (!prefetched && threadIdx.x == 0) issue_decoder_tma(P, t, lv);
-    prefetched = false;
 #pragma unroll
-    for (int i = 0; i < 4; i++) mlo |= (uint32_t) reinterpret_cast<const uint8_t*>(gmask)[i * 4 + cg] << (8 * i);
-    mhi = reinterpret_cast<const uint8_t*>(gmask)[16 + cg];
-    mbar_wait(t.wbar, wparity); wparity ^= 1u;
-    for (int i = threadIdx.x; i < 128; i += blockDim.x) t.bias[336 + i] = Wg[d.o_WO + (i >> 5) * Dec<1>::PH + (i & 31)];
-    __syncthreads();
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; i++) mlo |= (uint32_t) reinterpret_cast<const uint8_t*>(t.masks)[(i * TM + row) * 4 + cg] << (8 * i);
-    mhi = reinterpret_cast<const uint8_t*>(t.masks)[(4 * TM + row) * 4 + cg];
-  }
+  for (int i = 0; i < 4; i++) mlo |= (uint32_t) reinterpret_cast<const uint8_t*>(gmask)[i * 4 + cg] << (8 * i);
+  mhi = reinterpret_cast<const uint8_t*>(gmask)[16 + cg];
+  pipe_wait(t, pp, W_HDR);
   const uint32_t my = ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kCW * cg);
-  const uint32_t dcc = tmem + 32u, dfc = tmem + 96u;       // DC: cols [32,96)  DF: cols [96,192)  (D2 is dead)
+  const uint32_t dcc = tmem + 32u, dfc = tmem + 96u;
   float* g_hi = t.x; float* g_lo = t.x + TM * 32;
   float* du_hi = t.x + 2 * TM * 32; float* du_lo = t.x + 3 * TM * 32;
-  constexpr int PH = Dec<1>::PH;
   float g[kCW];
 #pragma unroll
   for (int j = 0; j < kCW; j++) {
     float v = 0.0f;
 #pragma unroll
-    for (int o = 0; o < 4; o++) v = fmaf(t.bias[336 + o * 32 + kCW * cg + j], g_out[o], v);       // rows >= NO are zero
+    for (int o = 0; o < 4; o++) v = fmaf(hdr[336 + o * 32 + kCW * cg + j], g_out[o], v);       // rows >= NO are zero
     g[j] = v;
   }
   uint32_t acc_dc = 0, acc_df = 0;
+  const float* img = P.in.packed[lv] + op_bwd_offset(lv);
 #pragma unroll 1
   for (int i = 4; i >= 0; i--) {
     const uint32_t m = i == 4 ? mhi : (mlo >> (8 * i)) & 0xffu;
+    const int s = (4 - i) & 1;                               // stage of this layer's operands
 #pragma unroll
     for (int k = 0; k < kKQ; k++) {
       if (d.xyz) put4(g_hi, g_lo, row, kKQ * cg + k, 32, make_float4(g[4 * k], g[4 * k + 1], g[4 * k + 2], g[4 * k + 3]));
       put4(du_hi, du_lo, row, kKQ * cg + k, 32, make_float4((m >> (4 * k)) & 1u ? g[4 * k] : 0.0f, (m >> (4 * k + 1)) & 1u ? g[4 * k + 1] : 0.0f,
                                                              (m >> (4 * k + 2)) & 1u ? g[4 * k + 2] : 0.0f, (m >> (4 * k + 3)) & 1u ? g[4 * k + 3] : 0.0f));
     }
-    {   // one batch per layer: DC += G * Wc_i (dL/dc through fc_c) ; D1 = DU * W_i[:, hidden] (g_i) ; DF += DU * W_i[:, first] (i = 3, 0)
-      float* wcT = t.wa;                         // [cd x 32] hi|lo (<= 16 KB)
-      float* whT = t.wa + 2 * 64 * 32;           // [32 x 32] hi|lo (8 KB)
-      float* weT = t.wb;                         // [firstp x 32] hi|lo (<= 24 KB)
-      if (d.xyz) stage_wT(wcT, Wg + d.o_WC + i * 32 * d.pc, d.pc, 0, d.cd);
-      if (i >= 1) stage_wT(whT, Wg + dec_wh(d, i), PH, 0, 32);
-      if (i == 3 || i == 0) stage_wT(weT, Wg + (i == 0 ? d.o_W0 : d.o_W3E), d.pf, 0, d.firstp);
-      publish_operands();
-      if (threadIdx.x == 0) {
-        tc_fence_after();
-        if (d.xyz) mma_3x(dcc, g_hi, g_lo, 32, 0, wcT, wcT + d.cd * 32, 32, 0, 4, d.cd, acc_dc);
-        if (i >= 1) { uint32_t a1 = 0; mma_3x(tmem, du_hi, du_lo, 32, 0, whT, whT + 32 * 32, 32, 0, 4, 32, a1); }
-        if (i == 3 || i == 0) mma_3x(dfc, du_hi, du_lo, 32, 0, weT, weT + d.firstp * 32, 32, 0, 4, d.firstp, acc_df);
-        mma_commit(t.bar);
-      }
-      __syncwarp();
-      mbar_wait(t.bar, parity); parity ^= 1u;
+    publish_operands();
+    if (t0) {   // DC += G * Wc_i (dL/dc through fc_c) ; D1 = DU * W_i[:, hidden] (g_i) ; DF += DU * W_i[:, first] (i = 3, 0)
+      mbar_wait(t.bars + W_S0 + s, (pp.par >> (W_S0 + s)) & 1u);
       tc_fence_after();
+      const float* w = t.wS + s * kBwdStageFloats;
+      if (d.xyz) { mma_3x(dcc, g_hi, g_lo, 32, 0, w, w + d.cd * 32, 32, 0, 4, d.cd, acc_dc); w += 2 * d.cd * 32; }
+      if (i >= 1) { uint32_t a1 = 0; mma_3x(tmem, du_hi, du_lo, 32, 0, w, w + 32 * 32, 32, 0, 4, 32, a1); w += kHChunk; }
+      if (i == 3 || i == 0) mma_3x(dfc, du_hi, du_lo, 32, 0, w, w + d.firstp * 32, 32, 0, 4, d.firstp, acc_df);
+      mma_commit(t.bars + M_B);
     }
+    pp.par ^= 1u << (W_S0 + s);
+    __syncwarp();
+    pipe_wait(t, pp, M_B);
+    tc_fence_after();
+    if (t0 && i >= 2) tma_load(t, W_S0 + s, t.wS + s * kBwdStageFloats, img + op_bwd_layer_offset(lv, i - 2), op_bwd_layer_floats(lv, i - 2));
     if (i >= 1) tmem_ld8(tmem + my, g);
     tc_fence_before();
   }
+  // both stages are free: the next decoder's header and first two layers arrive under the epilogue and the scatter
+  if (next_lv >= 0) { if (t0) issue_bwd_loads(P, t, next_lv, pp.hb ^ 1); pp.prefetched = true; }
   // ---- dL/dc rows -> shared (plain fp32 [128][cd]); all MMAs reading t.x have completed
   float* dcs = t.x;
   {
@@ -454,7 +443,7 @@ __device__ __forceinline__ void tile_backward(const KParams& P, const TcSmem& t,
   // ---- embedding chain: dp += B (cos(pB) * dfirst), this thread's features; partial sums to shared memory
   float dpe[3] = {0.0f, 0.0f, 0.0f};
   if (d.xyz) {
-    const float* B = Wg + d.o_B;
+    const float* B = hdr + 464;
     for (int c = 0; c < 3; c++) {
       float v[kCW];
       tmem_ld8(dfc + 32u * c + my, v);
@@ -472,6 +461,7 @@ __device__ __forceinline__ void tile_backward(const KParams& P, const TcSmem& t,
   }
   *reinterpret_cast<float4*>(t.x + 2 * TM * 32 + (cg * TM + row) * 4) = make_float4(dpe[0], dpe[1], dpe[2], 0.0f);
   tc_fence_before();
+  pp.hb ^= 1;
 }
 // dL/dp of `row` through the embedding: sum of the kCG partials tile_backward left in shared memory (call after a CTA barrier)
 __device__ __forceinline__ void dpe_sum(const TcSmem& t, int row, float (&dpe)[3]) {
