@@ -215,6 +215,61 @@ def extra_workloads(sc, renderer, c, dec, dev, flush, peak):
     return out
 
 
+def scene_workloads(dev, flush):
+    """BASELINE configs[2], configs[3] volumes on one GPU: one mapping iteration (stage color, frustum-masked voxel parameterisation,
+    compact voxel grads + colour-decoder grads) on ScanNet scene0000 (5000 rays), Apartment as configured (0.98 M voxels, 10000 rays)
+    and Apartment with the TUM grid lengths (8.0 M voxels, 1.0 GB of grids -- larger than L2, so the gather really comes from HBM)."""
+    import torch.nn.functional as F
+    import scene_util as su
+    from gpu_util import make_renderer
+    from nice_slam_b200.masked import MaskedVoxels
+    from nice_slam_b200.steps import IterationContext
+    out = []
+    for name, n, variant in (("scene0000", 5000, None), ("apartment", 10000, None), ("apartment", 10000, "tum_grid_len")):
+        sc = dict(su.load_scenes()[name])
+        shapes = dict(sc["shapes"])
+        if variant:
+            shapes["grid_middle"] = list(shapes["grid_fine"])
+            shapes["grid_fine"] = shapes["grid_color"] = [2 * d + 1 for d in sc["shapes"]["grid_fine"]]
+        g = torch.Generator(device=dev).manual_seed(5)
+        grids = {}
+        for key in ("grid_coarse", "grid_middle", "grid_fine", "grid_color"):
+            D, H, W = shapes[key]
+            lo = torch.randn(1, 32, max(D // 4, 2), max(H // 4, 2), max(W // 4, 2), device=dev, generator=g)
+            t = F.interpolate(lo, size=(D, H, W), mode="trilinear", align_corners=True) * 0.3
+            t += torch.randn(t.shape, device=dev, generator=g) * (0.003 if key == "grid_fine" else 0.3)
+            grids[key] = t
+        renderer, c, dec = make_renderer(sc, grids, su.load_decoders("soft"), dev)
+        del grids
+        ro, rd, dirs, gd, gc = [t.to(dev) for t in make_batch(sc, n, 77)]
+        keys = ("grid_middle", "grid_fine", "grid_color")
+        mv = {}
+        for k in keys:
+            D, H, W = c[k].shape[2:]
+            m = torch.zeros(D, H, W, dtype=torch.bool, device=dev)
+            m[:, :, : int(0.6 * W)] = True
+            mv[k] = MaskedVoxels(c[k], m)
+        ctx = IterationContext(renderer, n, "color", dev, kind="map", grad_grids=keys, grad_decoders=("color",), masked=mv)
+        gcf = gc.float()
+        steps = 20
+        for _ in range(3):
+            ctx.run(c, dec, ro, rd, gd, gcf)
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in evs:
+            flush.zero_(); a.record(); ctx.run(c, dec, ro, rd, gd, gcf); b.record()
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+        assert torch.isfinite(ctx.loss).all()
+        vox = sum(int(c[k].shape[2] * c[k].shape[3] * c[k].shape[4]) for k in c)
+        bpr = 48 * 3 * 1024 * 2
+        out.append({"scene": name + ("+" + variant if variant else ""), "rays": n, "voxels": vox, "grid_mbytes": vox * 128 / 1e6,
+                    "ms_per_step": ms, "rays_per_s": n / (ms * 1e-3), "algorithmic_gbytes_per_s": n * bpr / (ms * 1e-3) / 1e9})
+        del ctx, mv, c, renderer
+        torch.cuda.empty_cache()
+    return out
+
+
 def mapping_sharded_workload(sc, renderer, c, dec, dev, flush, rank, world):
     """BASELINE configs[1]-style mapping iteration, ray-sharded (weak scaling: 996 rays = 6 keyframes x 166 px per GPU), with the
     frustum-masked voxel parameterisation: compact voxel gradients + colour-decoder gradients + keyframe pose gradients in one packed
@@ -238,7 +293,7 @@ def mapping_sharded_workload(sc, renderer, c, dec, dev, flush, rank, world):
     sh = ShardedMappingIteration(ctx)
     sh.prepare(c, dec, dirs, offs)
     sh.enqueue(); torch.cuda.synchronize()
-    g = sh.build_graph()
+    g = sh.build_graph() if os.environ.get("NSB_DIST_GRAPH", "1") == "1" else None
     ok = torch.tensor([1.0 if g is not None else 0.0], device=dev)
     if world > 1:
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
@@ -266,8 +321,16 @@ def mapping_sharded_workload(sc, renderer, c, dec, dev, flush, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------ native arm (GPU)
+def dbg(msg):
+    if os.environ.get("NSB_BENCH_DEBUG"):
+        print("[bench rank %s] %s" % (os.environ.get("RANK", "0"), msg), file=sys.stderr, flush=True)
+
+
 def run_native(args):
     import torch.distributed as dist
+    if os.environ.get("NSB_BENCH_DEBUG"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["NSB_BENCH_DEBUG"]), exit=True)      # where is every rank after N seconds?
     from nice_slam_b200.steps import IterationContext
     from nice_slam_b200.dist import ShardedTrackingIteration
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -283,7 +346,7 @@ def run_native(args):
     ro, rd, dirs, gd, gc = [t.to(dev) for t in host]
     ctx = IterationContext(renderer, RAYS_PER_GPU, STAGE, dev, kind="track")
     ctx.stage_host_inputs(host[0], host[1], host[3], host[4])
-    sharded = ShardedTrackingIteration(ctx) if world > 1 else None
+    sharded = ShardedTrackingIteration(ctx) if world > 1 else None            # in-kernel peer-memory exchanges when available, else NCCL
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
 
     use_graph = True
@@ -304,8 +367,20 @@ def run_native(args):
         ctx.load_device_inputs(ro, rd, gd, gc)
         sharded.prepare(c, dec, dirs)
         sharded.enqueue(); torch.cuda.synchronize()
-        g_dev = sharded.build_graph(host_io=False)
-        g_e2e = sharded.build_graph(host_io=True)
+        exchange = "NVLink peer memory, inside the batch_max / seeds / pose_grad kernels" if sharded.peers is not None else "NCCL (all-reduce MAX, all-gather, all-reduce SUM)"
+        if sharded.peers is not None:                              # cross-check the in-kernel exchanges against the NCCL collectives once
+            ref = ShardedTrackingIteration(ctx, exchange="nccl")
+            ref.prepare(c, dec, dirs)
+            want = ref.enqueue().clone()
+            got = sharded.enqueue().clone()
+            torch.cuda.synchronize()
+            assert torch.allclose(got, want, rtol=1e-9, atol=1e-12), (got, want)
+            dbg("peer exchange == NCCL exchange")
+        want_graph = os.environ.get("NSB_DIST_GRAPH", "1") == "1"
+        dbg("capturing sharded graphs" if want_graph else "eager sharded path")
+        g_dev = sharded.build_graph(host_io=False) if want_graph else None
+        g_e2e = sharded.build_graph(host_io=True) if want_graph else None
+        dbg("graphs done")
         flag = torch.tensor([1.0 if (g_dev is not None and g_e2e is not None) else 0.0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)                # all ranks must agree (collectives inside the graph)
         use_graph = bool(flag.item() > 0.5)
@@ -354,6 +429,7 @@ def run_native(args):
     step_dev(); torch.cuda.synchronize()
     assert torch.isfinite(ctx.loss if sharded is None else sharded.packed).all()
 
+    dbg("timing main loop")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -366,14 +442,15 @@ def run_native(args):
         flush.zero_(); ctx.run(c, dec, ro, rd, gd, gc); torch.cuda.synchronize()
         bwd_ms.append(ctx.ev_bwd[0].elapsed_time(ctx.ev_bwd[1]))
     ctx.time_backward(False)
+    dbg("warm + e2e loops")
     warm_ms, _, _ = timed(step_dev, args.steps, 3, False)                 # L2-warm (production steady state), reported as extra
     e2e_ms, _, _ = timed(step_e2e, args.steps, 3, True)
 
+    dbg("mapping sharded workload")
     map_sharded = mapping_sharded_workload(sc, renderer, c, dec, dev, flush, rank, world)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown(world)
         return
     ms = total_ms / args.steps
     rays = RAYS_PER_GPU * world
@@ -383,11 +460,12 @@ def run_native(args):
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "rays_per_step": rays, "l2": "flushed between steps (256 MiB memset outside the event pair)",
                        "launch": "CUDA graph replay (one graph per iteration)" if (sharded is None or use_graph) else "stream launches + NCCL",
-                       "parallelism": "ray-sharded x%d" % world, "timing": "sum of per-step CUDA-event pairs, max over ranks"},
+                       "parallelism": "ray-sharded x%d" % world, "exchange": exchange if sharded is not None else "none (single GPU)",
+                       "timing": "sum of per-step CUDA-event pairs, max over ranks"},
             "clocks": clocks,
             "e2e": {"value": rays / (e2e_ms / args.steps * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": ctx.h2d_bytes,
                     "d2h_bytes_per_step": (ctx.d2h_bytes + 96) if sharded is None else 13 * 8, "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": (5 if sharded is None else 6) * args.steps,
+            "gpu_launches": (5 if (sharded is None or sharded.peers is not None) else 6) * args.steps,
             "extra": {"l2_warm_ms_per_step": warm_ms / args.steps, "l2_warm_rays_per_s": rays / (warm_ms / args.steps * 1e-3),
                       "mapping_sharded_masked": map_sharded}}
     if bwd_ms:
@@ -399,6 +477,7 @@ def run_native(args):
                             "note": "200-ray tracking batch (100 CTAs on 148 SMs) is latency bound, not HBM bound: the grids are L2-resident (see DESIGN.md)"}
     if world == 1:
         line["extra"].update(extra_workloads(sc, renderer, c, dec, dev, flush, peak))
+        line["extra"]["mapping_other_scenes"] = scene_workloads(dev, flush)
         best = None
         for threads in sorted({1, os.cpu_count() or 1}):      # CPU grid_sample is single-threaded for batch 1; oversubscribed MKL is slower
             torch.set_num_threads(threads)
@@ -418,8 +497,21 @@ def run_native(args):
                                           % (k, best[1], os.cpu_count() or 1),
                                 "ms_per_step": dtc * 1e3}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown(world)
+
+
+def shutdown(world):
+    """Leave the process group.  Communicators that were captured into CUDA graphs can make destroy_process_group block: bounded wait,
+    then exit hard (everything has been printed and flushed by then)."""
+    if world <= 1:
+        return
+    import torch.distributed as dist
+    sys.stdout.flush(); sys.stderr.flush()
+    torch.cuda.synchronize()
+    t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    t.start(); t.join(15.0)
+    if t.is_alive():
+        os._exit(0)
 
 
 def main():

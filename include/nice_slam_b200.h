@@ -184,6 +184,32 @@ int nsb_compact_transpose(const float* src, float* dst, long long n_selected, in
 int nsb_pose_grad_frames(const float* dirs, const float* d_rays_o, const float* d_rays_d, const int32_t* frame_offsets,
                          int n_frames, float* out, void* stream);
 
+/* ---- exchanges of a ray-sharded tracking iteration through NVLink peer memory ---------------------------------
+ * A batch sharded over `world` GPUs (equal shards) needs three batch-global quantities: max(gt_depth) (Renderer.py:109,144), the
+ * median of the residuals (Tracker.py:113) and the sums of loss and pose gradient.  The *_peers variants of the three single-CTA
+ * kernels exchange them inside the kernel: every rank owns an exchange buffer of nsb_peer_buffer_bytes(max_rays) bytes, zeroed once,
+ * mapped on all ranks (CUDA IPC / torch symmetric memory); buffer[r] is rank r's buffer as addressable from THIS device.
+ * counters: device uint64[4] of this rank, zeroed once (sequence numbers; advanced by the kernels -> CUDA-graph replay safe).
+ * All ranks must enqueue the same sequence of *_peers calls; the kernels of one call spin until every rank has arrived. */
+#define NSB_MAX_PEERS 8
+typedef struct nsb_peers {
+  int rank, world;
+  void* buffer[NSB_MAX_PEERS];
+  unsigned long long* counters;
+  int max_rays;                  /* per-rank capacity of the residual pool the buffers were sized for */
+} nsb_peers;
+size_t nsb_peer_buffer_bytes(int max_rays);
+int nsb_batch_max_depth_peers(const float* gt_depth, int n, float* out2, const nsb_peers* peers, void* stream);
+/* as nsb_tracking_seeds with the median taken over ALL ranks' residuals (all-gathered through the exchange buffers); loss[0] = this
+ * rank's partial loss. */
+int nsb_tracking_seeds_peers(const double* depth, const double* var, const float* rgb, const float* gt_depth,
+                             const double* gt_rgb, int n, double w_color, int handle_dynamic, int use_color,
+                             const nsb_peers* peers, double* g_depth, float* g_rgb, double* loss,
+                             void* workspace, size_t workspace_bytes, void* stream);
+/* loss_and_d_c2w[13] = sum over ranks of [loss_local[0] | d c2w (12)], identical bits on every rank. */
+int nsb_pose_grad_peers(const float* dirs, const float* d_rays_o, const float* d_rays_d, int n, const double* loss_local,
+                        double* loss_and_d_c2w, const nsb_peers* peers, void* stream);
+
 /* Points-only decode (Renderer.eval_points, src/utils/Renderer.py:23-61): p f64 [P,3] -> raw f32 [P,4]. */
 int nsb_eval_points(const nsb_render_inputs* in, const double* points, int n_points, float* raw, void* stream);
 

@@ -53,6 +53,10 @@ class IterationBuffers(C.Structure):
                 ("event_bwd_begin", C.c_void_p), ("event_bwd_end", C.c_void_p)]
 
 
+class Peers(C.Structure):
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("buffer", C.c_void_p * 8), ("counters", C.c_void_p), ("max_rays", C.c_int)]
+
+
 # every symbol include/nice_slam_b200.h declares: (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -83,6 +87,10 @@ SYMBOLS = {
     "nsb_masked_scatter": (C.c_int, [C.POINTER(Grid), _P, _P, _P]),
     "nsb_compact_transpose": (C.c_int, [_P, _P, C.c_longlong, C.c_int, _P]),
     "nsb_pose_grad_frames": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P]),
+    "nsb_peer_buffer_bytes": (C.c_size_t, [C.c_int]),
+    "nsb_batch_max_depth_peers": (C.c_int, [_P, C.c_int, _P, C.POINTER(Peers), _P]),
+    "nsb_tracking_seeds_peers": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_double, C.c_int, C.c_int, C.POINTER(Peers), _P, _P, _P, _P, C.c_size_t, _P]),
+    "nsb_pose_grad_peers": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, C.POINTER(Peers), _P]),
 }
 
 _LIB = None

@@ -139,8 +139,47 @@ int launch_unpack_grads(float* const d_packed[4], float* const d_flat[4], cudaSt
   return check_cuda(cudaGetLastError(), "unpack_grads launch");
 }
 
+// ------------------------------------------------------------------------------------------------ in-kernel exchanges over peer memory
+// A ray-sharded tracking iteration needs three tiny batch-global quantities.  Instead of three NCCL launches the
+// single-CTA kernels that produce them exchange them themselves through NVLink peer memory (symmetric buffers, one per rank, mapped
+// on every rank): push the local value into slot [parity][my rank] of EVERY peer's buffer, st.release.sys a sequence number next to
+// it, spin (ld.acquire.sys) on the own buffer until all ranks' sequence numbers have arrived.  Parity double-buffering + one
+// sequence counter per channel make the buffers reusable without any reset; a rank cannot run two exchanges of a channel ahead
+// because the other channels of the same iteration need everybody.
+struct PeerX {
+  int rank, world;                   // world <= 1: no exchange
+  unsigned char* peer[NSB_MAX_PEERS];
+  unsigned long long* counter;       // this rank's sequence counters, one per channel
+  int max_n;                         // residual-pool capacity per rank
+};
+constexpr size_t kXMaxOff = 0, kXSumOff = 256, kXPoolFlagOff = 2304, kXPoolOff = 2560;
+__host__ __device__ inline size_t peer_buffer_bytes(int max_n) { return kXPoolOff + (size_t)2 * NSB_MAX_PEERS * (size_t)max_n * sizeof(double); }
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+// sequence number of this launch on channel c (CTA-uniform)
+__device__ __forceinline__ uint32_t peer_begin(const PeerX& px, int c, uint32_t* s_seq) {
+  if (threadIdx.x == 0) *s_seq = (uint32_t)(px.counter[c] + 1ull);
+  __syncthreads();
+  return *s_seq;
+}
+// all pushes of this CTA are done -> publish `seq` in slot [parity][rank] of every peer, wait for every rank's, remember the sequence
+__device__ __forceinline__ void peer_signal_wait(const PeerX& px, int c, size_t flag_off, size_t flag_stride, uint32_t seq) {
+  __threadfence_system();
+  __syncthreads();
+  const int par = seq & 1u;
+  if ((int)threadIdx.x < px.world) {
+    st_release_sys(reinterpret_cast<uint32_t*>(px.peer[threadIdx.x] + flag_off + ((size_t)par * NSB_MAX_PEERS + px.rank) * flag_stride), seq);
+    const uint32_t* mine = reinterpret_cast<const uint32_t*>(px.peer[px.rank] + flag_off + ((size_t)par * NSB_MAX_PEERS + threadIdx.x) * flag_stride);
+    while ((int)(ld_acquire_sys(mine) - seq) < 0) { }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) px.counter[c] = (unsigned long long)seq;
+}
+
 // ------------------------------------------------------------------------------------------------ batch max
-__global__ void batch_max_kernel(const float* __restrict__ gt, int n, float* __restrict__ out2) {
+__global__ void batch_max_kernel(const float* __restrict__ gt, int n, float* __restrict__ out2, const PeerX px) {
   __shared__ float red[32];
   float m = -INFINITY;
   for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, gt[i]);
@@ -154,6 +193,21 @@ __global__ void batch_max_kernel(const float* __restrict__ gt, int n, float* __r
       if (n <= 0) m = 0.0f;
       out2[0] = m;                       // torch.max(gt_depth)            (Renderer.py:144)
       out2[1] = __fmul_rn(m, 1.2f);      // torch.max(gt_depth*1.2): x -> fl(1.2f*x) is monotone, so max commutes (Renderer.py:109)
+    }
+  }
+  if (px.world > 1) {                    // MAX over the ray shards of all ranks (channel 0: slot = {max, flag} of 16 bytes)
+    __shared__ uint32_t s_seq;
+    const uint32_t seq = peer_begin(px, 0, &s_seq);
+    const int par = seq & 1u;
+    if ((int)threadIdx.x < px.world) {
+      float* slot = reinterpret_cast<float*>(px.peer[threadIdx.x] + kXMaxOff + ((size_t)par * NSB_MAX_PEERS + px.rank) * 16);
+      __stcg(slot, out2[0]);
+    }
+    peer_signal_wait(px, 0, kXMaxOff + 8, 16, seq);
+    if (threadIdx.x == 0) {
+      float mm = -INFINITY;
+      for (int r = 0; r < px.world; r++) mm = fmaxf(mm, __ldcg(reinterpret_cast<const float*>(px.peer[px.rank] + kXMaxOff + ((size_t)par * NSB_MAX_PEERS + r) * 16)));
+      out2[0] = mm; out2[1] = __fmul_rn(mm, 1.2f);
     }
   }
 }
@@ -184,41 +238,80 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 }
 __device__ __forceinline__ double sgn(double x) { return (x > 0.0) - (x < 0.0); }
 
+constexpr int kMedianDirect = 2048;
 // Tracker.optimize_cam_in_batch loss (src/Tracker.py:108-123); single CTA, residuals staged in `res`.
 __global__ void tracking_seeds_kernel(const double* __restrict__ depth, const double* __restrict__ var, const float* __restrict__ rgb,
                                       const float* __restrict__ gt, const double* __restrict__ gt_rgb, int n, double w_color,
                                       int handle_dynamic, int use_color, const double* __restrict__ pool, int n_pool,
                                       double* __restrict__ g_depth, float* __restrict__ g_rgb,
-                                      double* __restrict__ loss, double* __restrict__ res) {
+                                      double* __restrict__ loss, double* __restrict__ res, const PeerX px) {
   __shared__ double red[32];
-  __shared__ int ired[32];
+  __shared__ int hist[256];
+  __shared__ unsigned long long keys[kMedianDirect];
+  __shared__ unsigned long long med_key;
   __shared__ double med_s;
   for (int i = threadIdx.x; i < n; i += blockDim.x)
     res[i] = fabs((double)gt[i] - depth[i]) / sqrt(var[i] + 1e-10);
   __syncthreads();
   if (handle_dynamic) {
-    // torch.median = lower median = the element of rank (n-1)/2.  Radix select on the IEEE bit pattern (residuals are
-    // non-negative, so the unsigned 64-bit pattern is order preserving; NaN sorts last like torch.sort): 64 counting passes.
+    // torch.median = lower median = the element of rank (n-1)/2 of the IEEE bit patterns (residuals are non-negative, so the unsigned
+    // 64-bit pattern is order preserving; NaN sorts last like torch.sort).
     const double* mp = pool != nullptr ? pool : res;       // sharded batches: median over the all-gathered residuals
-    const int np = pool != nullptr ? n_pool : n;
-    int k = (np - 1) / 2;
-    unsigned long long prefix = 0ull;
-    for (int b = 63; b >= 0; --b) {
-      const unsigned long long maskhi = b == 63 ? 0ull : (~0ull << (b + 1));
-      int c = 0;
-      for (int i = threadIdx.x; i < np; i += blockDim.x) {
-        const unsigned long long key = (unsigned long long)__double_as_longlong(mp[i]);
-        c += ((key & maskhi) == prefix && !((key >> b) & 1ull)) ? 1 : 0;
+    int np = pool != nullptr ? n_pool : n;
+    int pool_pitch = 0;                                    // > 0: the pool is [world][pool_pitch] with n valid entries per rank
+    if (px.world > 1) {
+      // all-gather of the residuals through peer memory (channel 1): push this shard into block [parity][rank] of every peer's pool
+      __shared__ uint32_t s_seq;
+      const uint32_t seq = peer_begin(px, 1, &s_seq);
+      const int par = seq & 1u;
+      for (int i = threadIdx.x; i < n * px.world; i += blockDim.x) {
+        const int r = i / n, j = i - r * n;
+        __stcg(reinterpret_cast<double*>(px.peer[r] + kXPoolOff) + ((size_t)par * NSB_MAX_PEERS + px.rank) * px.max_n + j, res[j]);
       }
-      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-      if ((threadIdx.x & 31) == 0) ired[threadIdx.x >> 5] = c;
-      __syncthreads();
-      int tot = 0;
-      for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot += ired[w];
-      __syncthreads();
-      if (k >= tot) { k -= tot; prefix |= 1ull << b; }
+      peer_signal_wait(px, 1, kXPoolFlagOff, 16, seq);
+      mp = reinterpret_cast<const double*>(px.peer[px.rank] + kXPoolOff) + (size_t)par * NSB_MAX_PEERS * px.max_n;
+      np = n * px.world; pool_pitch = px.max_n;
     }
-    if (threadIdx.x == 0) med_s = __longlong_as_double((long long)prefix);
+    auto pool_at = [&](int i) { return pool_pitch ? __ldcg(mp + (size_t)(i / n) * pool_pitch + (i % n)) : mp[i]; };
+    const int k = (np - 1) / 2;
+    if (np <= kMedianDirect) {
+      // small pools (a tracking batch is 200 rays): direct rank counting from shared memory, no serial passes
+      for (int i = threadIdx.x; i < np; i += blockDim.x) keys[i] = (unsigned long long)__double_as_longlong(pool_at(i));
+      __syncthreads();
+      for (int i = threadIdx.x; i < np; i += blockDim.x) {
+        const unsigned long long key = keys[i];
+        int less = 0, eq = 0;
+        for (int j = 0; j < np; j++) { const unsigned long long o = keys[j]; less += o < key ? 1 : 0; eq += o == key ? 1 : 0; }
+        if (less <= k && k < less + eq) med_key = key;     // every thread that qualifies writes the same value
+      }
+      __syncthreads();
+    } else {
+      // radix select, 8 bits per pass (8 passes, 256-bin shared histogram)
+      unsigned long long prefix = 0ull;
+      int kk = k;
+      for (int shift = 56; shift >= 0; shift -= 8) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        const unsigned long long maskhi = shift == 56 ? 0ull : (~0ull << (shift + 8));
+        for (int i = threadIdx.x; i < np; i += blockDim.x) {
+          const unsigned long long key = (unsigned long long)__double_as_longlong(pool_at(i));
+          if ((key & maskhi) == prefix) atomicAdd(&hist[(int)((key >> shift) & 0xffull)], 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          int d = 0, c = 0;
+          while (d < 255 && c + hist[d] <= kk) { c += hist[d]; d++; }
+          hist[0] = d; hist[1] = c;                        // digit, elements below it
+        }
+        __syncthreads();
+        prefix |= (unsigned long long)hist[0] << shift;
+        kk -= hist[1];
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) med_key = prefix;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) med_s = __longlong_as_double((long long)med_key);
     __syncthreads();
   }
   double acc = 0.0;
@@ -264,7 +357,7 @@ __global__ void mapping_seeds_kernel(const double* __restrict__ depth, const flo
 
 // d c2w from ray gradients (single CTA, deterministic)
 __global__ void pose_grad_kernel(const float* __restrict__ dirs, const float* __restrict__ dro, const float* __restrict__ drd, int n,
-                                 double* __restrict__ out) {
+                                 double* __restrict__ out, const double* __restrict__ loss_local, const PeerX px) {
   __shared__ double red[32];
   double acc[12];
 #pragma unroll
@@ -278,7 +371,28 @@ __global__ void pose_grad_kernel(const float* __restrict__ dirs, const float* __
       acc[4 * i + 3] += (double)dro[3 * r + i];
     }
   }
-  for (int k = 0; k < 12; k++) { const double t = block_sum(acc[k], red); if (threadIdx.x == 0) out[k] = t; }
+  __shared__ double tot[13];
+  for (int k = 0; k < 12; k++) { const double t = block_sum(acc[k], red); if (threadIdx.x == 0) tot[k + 1] = t; }
+  if (px.world <= 1) {
+    if (threadIdx.x == 0) for (int k = 0; k < 12; k++) out[k] = tot[k + 1];
+    return;
+  }
+  // SUM over ranks of [loss | d c2w] through peer memory (channel 2: slot = 13 doubles + flag in 128 bytes); out = 13 doubles.
+  // Every rank adds the slots in rank order: bit-identical results everywhere.
+  __shared__ uint32_t s_seq;
+  if (threadIdx.x == 0) tot[0] = loss_local != nullptr ? loss_local[0] : 0.0;
+  const uint32_t seq = peer_begin(px, 2, &s_seq);
+  const int par = seq & 1u;
+  for (int i = threadIdx.x; i < 13 * px.world; i += blockDim.x) {
+    const int r = i / 13, k = i - 13 * r;
+    __stcg(reinterpret_cast<double*>(px.peer[r] + kXSumOff + ((size_t)par * NSB_MAX_PEERS + px.rank) * 128) + k, tot[k]);
+  }
+  peer_signal_wait(px, 2, kXSumOff + 104, 128, seq);
+  if (threadIdx.x < 13) {
+    double v = 0.0;
+    for (int r = 0; r < px.world; r++) v += __ldcg(reinterpret_cast<const double*>(px.peer[px.rank] + kXSumOff + ((size_t)par * NSB_MAX_PEERS + r) * 128) + threadIdx.x);
+    out[threadIdx.x] = v;
+  }
 }
 
 // ---- masked voxel parameterisation (Mapper.py:317-333, :393-401, :511-519) --------------------------------------------
@@ -393,10 +507,31 @@ __global__ void pose_grad_frames_kernel(const float* __restrict__ dirs, const fl
 
 using namespace nsb;
 
+static PeerX no_peers() { PeerX px; memset(&px, 0, sizeof(px)); return px; }
+static int make_peers(const nsb_peers* p, PeerX* px) {
+  if (!p || p->world < 2 || p->world > NSB_MAX_PEERS || p->rank < 0 || p->rank >= p->world || !p->counters || p->max_rays < 1) {
+    set_error("peer exchange: bad nsb_peers"); return NSB_ERR_ARG; }
+  memset(px, 0, sizeof(*px));
+  px->rank = p->rank; px->world = p->world; px->counter = p->counters; px->max_n = p->max_rays;
+  for (int r = 0; r < p->world; r++) {
+    if (!p->buffer[r]) { set_error("peer exchange: buffer[%d] is NULL", r); return NSB_ERR_ARG; }
+    px->peer[r] = static_cast<unsigned char*>(p->buffer[r]);
+  }
+  return NSB_OK;
+}
+extern "C" size_t nsb_peer_buffer_bytes(int max_rays) { return max_rays < 1 ? 0 : peer_buffer_bytes(max_rays); }
+
 extern "C" int nsb_pose_grad(const float* dirs, const float* d_rays_o, const float* d_rays_d, int n, double* d_c2w, void* stream) {
   if (n < 0 || !d_c2w || (n > 0 && (!dirs || !d_rays_o || !d_rays_d))) { set_error("pose_grad: bad arguments"); return NSB_ERR_ARG; }
-  pose_grad_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(dirs, d_rays_o, d_rays_d, n, d_c2w);
+  pose_grad_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(dirs, d_rays_o, d_rays_d, n, d_c2w, nullptr, no_peers());
   return check_cuda(cudaGetLastError(), "pose_grad launch");
+}
+extern "C" int nsb_pose_grad_peers(const float* dirs, const float* d_rays_o, const float* d_rays_d, int n, const double* loss_local,
+                                   double* loss_and_d_c2w, const nsb_peers* peers, void* stream) {
+  if (n < 0 || !loss_and_d_c2w || (n > 0 && (!dirs || !d_rays_o || !d_rays_d))) { set_error("pose_grad_peers: bad arguments"); return NSB_ERR_ARG; }
+  PeerX px; int rc = make_peers(peers, &px); if (rc) return rc;
+  pose_grad_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(dirs, d_rays_o, d_rays_d, n, loss_and_d_c2w, loss_local, px);
+  return check_cuda(cudaGetLastError(), "pose_grad_peers launch");
 }
 
 extern "C" size_t nsb_voxel_slots_workspace(long long n_voxels) {
@@ -467,8 +602,14 @@ extern "C" int nsb_pack_decoders(const nsb_decoder_params* const params[4], floa
 
 extern "C" int nsb_batch_max_depth(const float* gt_depth, int n, float* out2, void* stream) {
   if (!out2 || (n > 0 && !gt_depth) || n < 0) { set_error("batch_max_depth: bad arguments"); return NSB_ERR_ARG; }
-  batch_max_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(gt_depth, n, out2);
+  batch_max_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(gt_depth, n, out2, no_peers());
   return check_cuda(cudaGetLastError(), "batch_max launch");
+}
+extern "C" int nsb_batch_max_depth_peers(const float* gt_depth, int n, float* out2, const nsb_peers* peers, void* stream) {
+  if (!out2 || (n > 0 && !gt_depth) || n < 0) { set_error("batch_max_depth_peers: bad arguments"); return NSB_ERR_ARG; }
+  PeerX px; int rc = make_peers(peers, &px); if (rc) return rc;
+  batch_max_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(gt_depth, n, out2, px);
+  return check_cuda(cudaGetLastError(), "batch_max_peers launch");
 }
 
 extern "C" int nsb_bbox_prefilter(const float* rays_o, const float* rays_d, const float* gt_depth, int n,
@@ -504,8 +645,21 @@ extern "C" int nsb_tracking_seeds(const double* depth, const double* var, const 
   if (!workspace || workspace_bytes < nsb_tracking_seeds_workspace(n)) { set_error("tracking_seeds: workspace too small"); return NSB_ERR_ARG; }
   if (median_pool != nullptr && n_pool < 1) { set_error("tracking_seeds: empty median pool"); return NSB_ERR_ARG; }
   tracking_seeds_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(depth, var, rgb, gt_depth, gt_rgb, n, w_color, handle_dynamic, use_color,
-                                                               median_pool, n_pool, g_depth, g_rgb, loss, (double*)workspace);
+                                                               median_pool, n_pool, g_depth, g_rgb, loss, (double*)workspace, no_peers());
   return check_cuda(cudaGetLastError(), "tracking_seeds launch");
+}
+extern "C" int nsb_tracking_seeds_peers(const double* depth, const double* var, const float* rgb, const float* gt_depth,
+                                        const double* gt_rgb, int n, double w_color, int handle_dynamic, int use_color,
+                                        const nsb_peers* peers, double* g_depth, float* g_rgb, double* loss,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (n < 1 || !loss || !depth || !var || !rgb || !gt_depth || !g_depth || !g_rgb || (use_color && !gt_rgb)) {
+    set_error("tracking_seeds_peers: bad arguments"); return NSB_ERR_ARG; }
+  if (!workspace || workspace_bytes < nsb_tracking_seeds_workspace(n)) { set_error("tracking_seeds_peers: workspace too small"); return NSB_ERR_ARG; }
+  PeerX px; int rc = make_peers(peers, &px); if (rc) return rc;
+  if (n > px.max_n) { set_error("tracking_seeds_peers: n exceeds the exchange buffer capacity"); return NSB_ERR_ARG; }
+  tracking_seeds_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(depth, var, rgb, gt_depth, gt_rgb, n, w_color, handle_dynamic, use_color,
+                                                               nullptr, 0, g_depth, g_rgb, loss, (double*)workspace, px);
+  return check_cuda(cudaGetLastError(), "tracking_seeds_peers launch");
 }
 
 extern "C" int nsb_mapping_seeds(const double* depth, const float* rgb, const float* gt_depth, const float* gt_rgb, int n,

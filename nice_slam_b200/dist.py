@@ -52,6 +52,47 @@ def reduce_sum(packed):
     return packed
 
 
+class PeerExchange:
+    """NVLink peer-memory exchange buffers for the *_peers kernels (include/nice_slam_b200.h): one symmetric buffer per rank, mapped on
+    every rank through torch's symmetric-memory allocator (the plumbing); the exchanges themselves happen inside our kernels.
+    `PeerExchange.create` returns None when symmetric memory is not available (single process, CPU, unsupported fabric) -- the callers
+    then use the NCCL collectives."""
+
+    def __init__(self, buf, handle, counters, max_rays):
+        from . import _lib
+        self.buf, self.handle, self.counters, self.max_rays = buf, handle, counters, max_rays
+        rank, ws = world()
+        self.struct = _lib.Peers()
+        self.struct.rank, self.struct.world, self.struct.max_rays = rank, ws, max_rays
+        ptrs = list(handle.buffer_ptrs)
+        for r in range(ws):
+            self.struct.buffer[r] = ptrs[r]
+        self.struct.counters = counters.data_ptr()
+
+    @staticmethod
+    def create(max_rays, device):
+        rank, ws = world()
+        if ws < 2 or ws > 8 or torch.device(device).type != "cuda":
+            return None
+        ok = 1.0
+        px = None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            from . import _lib
+            nbytes = _lib.lib().nsb_peer_buffer_bytes(max_rays)
+            buf = symm.empty(nbytes, dtype=torch.uint8, device=device)
+            buf.zero_()
+            handle = symm.rendezvous(buf, dist.group.WORLD)
+            counters = torch.zeros(4, dtype=torch.int64, device=device)
+            px = PeerExchange(buf, handle, counters, max_rays)
+            torch.cuda.synchronize()
+        except Exception:                                     # noqa: BLE001 -- any failure means "no peer memory here"
+            ok = 0.0
+        flag = torch.tensor([ok], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)           # all ranks take the same path (also a barrier after the zero fill)
+        return px if flag.item() > 0.5 else None
+
+
 class ShardedTrackingIteration:
     """One tracking iteration on this rank's shard of a global ray batch (split-phase: the exchanges sit between the
     kernels).  With world_size == 1 it degenerates to the same kernels without collectives.
@@ -60,12 +101,14 @@ class ShardedTrackingIteration:
     only issues the kernels and the three collectives, so it can be replayed from a CUDA graph (NCCL collectives are
     graph-capturable) -- build_graph() returns None if capture is not possible and the caller falls back to enqueue()."""
 
-    def __init__(self, ctx):
+    def __init__(self, ctx, exchange="auto"):
+        """exchange: 'auto' = in-kernel exchanges over NVLink peer memory when available, else NCCL; 'nccl' = NCCL collectives."""
         self.ctx = ctx                      # steps.IterationContext(kind='track')
         dev = ctx.dev
         self.res = torch.empty(ctx.n, dtype=torch.float64, device=dev)
         self.allres = torch.empty(ctx.n * world()[1], dtype=torch.float64, device=dev)
         self.packed = torch.zeros(13, dtype=torch.float64, device=dev)      # [loss | d_c2w(12)]
+        self.peers = PeerExchange.create(ctx.n, dev) if exchange == "auto" else None
         self._p = None
 
     def prepare(self, c, decoders, dirs, w_color=0.5, handle_dynamic=True, use_color=True):
@@ -92,6 +135,19 @@ class ShardedTrackingIteration:
         x, p = self.ctx, self._p
         n = x.n
         st = _stream()
+        if self.peers is not None:
+            # five kernels, no collective launch: the three exchanges happen inside batch_max / seeds / pose_grad over peer memory
+            px = C.byref(self.peers.struct)
+            _lib.check(L.nsb_batch_max_depth_peers(_VP(p["gd"].data_ptr()), n, _VP(x.depth_max.data_ptr()), px, st), "nsb_batch_max_depth_peers")
+            _lib.check(L.nsb_render_forward(C.byref(p["inp"]), C.byref(p["fo"]), st), "nsb_render_forward")
+            _lib.check(L.nsb_tracking_seeds_peers(_VP(x.depth.data_ptr()), _VP(x.var.data_ptr()), _VP(x.rgb.data_ptr()), _VP(p["gd"].data_ptr()),
+                                                  _VP(p["gc"].data_ptr()), n, p["w_color"], p["hd"], p["uc"], px,
+                                                  _VP(x.g_depth.data_ptr()), _VP(x.g_rgb.data_ptr()), _VP(x.loss.data_ptr()),
+                                                  _VP(x.ws.data_ptr()), L.nsb_tracking_seeds_workspace(n), st), "nsb_tracking_seeds_peers")
+            _lib.check(L.nsb_render_backward(C.byref(p["inp"]), C.byref(p["bw"]), st), "nsb_render_backward")
+            _lib.check(L.nsb_pose_grad_peers(_VP(p["dirs"].data_ptr()), _VP(x.d_rays_o.data_ptr()), _VP(x.d_rays_d.data_ptr()), n,
+                                             _VP(x.loss.data_ptr()), _VP(self.packed.data_ptr()), px, st), "nsb_pose_grad_peers")
+            return self.packed
         _lib.check(L.nsb_batch_max_depth(_VP(p["gd"].data_ptr()), n, _VP(x.depth_max.data_ptr()), st), "nsb_batch_max_depth")
         exchange_depth_max(x.depth_max)
         _lib.check(L.nsb_render_forward(C.byref(p["inp"]), C.byref(p["fo"]), st), "nsb_render_forward")
