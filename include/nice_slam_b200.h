@@ -119,7 +119,14 @@ typedef struct {
   int32_t* corner_idx;           /* optional [N,S,3]: (ix0,iy0,iz0) of the stage's finest occupancy grid */
   uint32_t* masks;               /* optional [N,S,15]: ReLU sign bits of the 5 layers of up to 3 decoders (stage order); when the
                                     backward pass receives them it does not recompute the forward (tensor-core backend only) */
+  void* split_workspace;         /* optional device scratch of nsb_split_workspace_bytes(N, S) bytes, ZEROED ONCE by the caller (the library
+                                    leaves it clean): lets small batches (N <= 256 rays, several decoders) run one CTA per decoder
+                                    and ray group instead of one CTA per ray group; NULL = never split */
+  size_t split_workspace_bytes;
 } nsb_forward_outputs;
+
+/* 0 when the batch is too large to profit from decoder-parallel CTAs. */
+size_t nsb_split_workspace_bytes(int n_rays, int n_samples_total);
 
 /* Forward: sample -> gather -> decode -> composite  (Renderer.render_batch_ray, src/utils/Renderer.py:63-198) */
 int nsb_render_forward(const nsb_render_inputs* in, const nsb_forward_outputs* out, void* stream);
@@ -141,6 +148,8 @@ typedef struct {
                                     it is the [D*H*W] voxel -> slot table of nsb_voxel_slots() and d_grid[l] is the COMPACT gradient
                                     [n_selected][32] (slot-major, 32 channels contiguous) of the selected voxels only; voxels with
                                     slot -1 are not parameters and receive nothing.  NULL = d_grid[l] is dense. */
+  void* split_workspace;         /* as in nsb_forward_outputs (the same buffer may be passed to both) */
+  size_t split_workspace_bytes;
 } nsb_backward_args;
 
 size_t nsb_backward_workspace_bytes(void);
@@ -178,6 +187,19 @@ int nsb_masked_gather(const nsb_grid* grid, const int32_t* slot_map, float* comp
 int nsb_masked_scatter(const nsb_grid* grid, const int32_t* slot_map, const float* compact, void* stream); /* val[mask] = compact */
 /* to_reference != 0: [n][32] -> [32][n] (the reference's val[mask] order); 0: the inverse. */
 int nsb_compact_transpose(const float* src, float* dst, long long n_selected, int to_reference, void* stream);
+
+/* Frustum feature selection (Mapper.get_mask_from_c2w, src/Mapper.py:93-164) of one grid, on the device: every voxel centre is
+ * projected into the current frame (float32 camera transform, float64 intrinsics, like the reference's numpy code), the sensor
+ * depth is looked up with OpenCV's INTER_LINEAR remap arithmetic (1/32-pixel fixed point, BORDER_CONSTANT 0), zero look-ups are
+ * replaced by the maximum look-up, and the voxel is selected when it projects inside the image with 0 <= depth_cam <= sensor + 0.5,
+ * or lies within 0.5 of the camera centre.  c2w: HOST float[16] row-major.  xs/ys/zs: DEVICE voxel-centre coordinates per axis
+ * (W, H, D values: torch.linspace over the scene bound, Mapper.py:108-110).  depth: DEVICE float32 [img_h, img_w].
+ * voxel_mask: DEVICE uint8 [D*H*W] (d,h,w order) -- the input of nsb_voxel_slots.  ('grid_coarse' is always fully selected, :114-116:
+ * the caller fills ones.)  workspace: nsb_frustum_mask_workspace(D*H*W) bytes. */
+size_t nsb_frustum_mask_workspace(long long n_voxels);
+int nsb_frustum_mask(const float* c2w, const float* xs, const float* ys, const float* zs, int D, int H, int W,
+                     const float* depth, int img_h, int img_w, double fx, double fy, double cx, double cy,
+                     uint8_t* voxel_mask, void* workspace, size_t workspace_bytes, void* stream);
 
 /* d c2w per keyframe of a bundle-adjustment window (src/Mapper.py:437-467 concatenates per-frame ray blocks):
  * frame f owns rays [frame_offsets[f], frame_offsets[f+1]); out[f][12] (float32, row-major [3][4]) as nsb_pose_grad. */
@@ -233,6 +255,7 @@ typedef struct {
   void* event_bwd_begin; void* event_bwd_end;    /* optional cudaEvent_t recorded around the backward launch (profiling hook) */
 } nsb_iteration_buffers;
 
+/* The workspace must be ZEROED ONCE after allocation (it contains the split_workspace counters, see nsb_forward_outputs). */
 size_t nsb_iteration_workspace_bytes(int n_rays);
 
 /* `in->depth_max` is ignored (computed into buf->depth_max).  `grads` supplies only the OUTPUT pointers of

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnsb.so")
+LIB_PATH = os.environ.get("NSB_LIB") or os.path.join(_HERE, "libnsb.so")      # NSB_LIB: instrumented build for tools/phase_timing.py
 
 LEVELS = ("coarse", "middle", "fine", "color")
 STAGES = {"coarse": 0, "middle": 1, "fine": 2, "color": 3}
@@ -36,14 +36,15 @@ class RenderInputs(C.Structure):
 
 class ForwardOutputs(C.Structure):
     _fields_ = [("depth", C.c_void_p), ("var", C.c_void_p), ("rgb", C.c_void_p),
-                ("z_vals", C.c_void_p), ("raw", C.c_void_p), ("corner_idx", C.c_void_p), ("masks", C.c_void_p)]
+                ("z_vals", C.c_void_p), ("raw", C.c_void_p), ("corner_idx", C.c_void_p), ("masks", C.c_void_p),
+                ("split_workspace", C.c_void_p), ("split_workspace_bytes", C.c_size_t)]
 
 
 class BackwardArgs(C.Structure):
     _fields_ = [("z_vals", C.c_void_p), ("raw", C.c_void_p), ("g_depth", C.c_void_p), ("g_var", C.c_void_p),
                 ("g_rgb", C.c_void_p), ("d_rays_o", C.c_void_p), ("d_rays_d", C.c_void_p),
                 ("d_grid", C.c_void_p * 4), ("d_flat", C.c_void_p * 4), ("workspace", C.c_void_p), ("masks", C.c_void_p),
-                ("slot_map", C.c_void_p * 4)]
+                ("slot_map", C.c_void_p * 4), ("split_workspace", C.c_void_p), ("split_workspace_bytes", C.c_size_t)]
 
 
 class IterationBuffers(C.Structure):
@@ -87,6 +88,10 @@ SYMBOLS = {
     "nsb_masked_scatter": (C.c_int, [C.POINTER(Grid), _P, _P, _P]),
     "nsb_compact_transpose": (C.c_int, [_P, _P, C.c_longlong, C.c_int, _P]),
     "nsb_pose_grad_frames": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P]),
+    "nsb_split_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "nsb_frustum_mask_workspace": (C.c_size_t, [C.c_longlong]),
+    "nsb_frustum_mask": (C.c_int, [C.POINTER(C.c_float), _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int,
+                                   C.c_double, C.c_double, C.c_double, C.c_double, _P, _P, C.c_size_t, _P]),
     "nsb_peer_buffer_bytes": (C.c_size_t, [C.c_int]),
     "nsb_batch_max_depth_peers": (C.c_int, [_P, C.c_int, _P, C.POINTER(Peers), _P]),
     "nsb_tracking_seeds_peers": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_double, C.c_int, C.c_int, C.POINTER(Peers), _P, _P, _P, _P, C.c_size_t, _P]),

@@ -483,6 +483,77 @@ __global__ void compact_transpose_kernel(const float* __restrict__ src, float* _
   }
 }
 
+// ---- frustum feature selection (Mapper.get_mask_from_c2w, Mapper.py:93-164) -------------------------------------------------------
+struct FrustumArgs {
+  float w2c[12];                    // rows 0..2 of inverse(c2w), float32 like the reference's numpy pipeline
+  float cam_o[3];                   // c2w[:3,3]
+  const float* xs; const float* ys; const float* zs;      // voxel-centre coordinates per axis (torch.linspace over the bound, Mapper.py:108-110)
+  int D, H, W;
+  const float* depth; int img_h, img_w;
+  double fx, fy, cx, cy;
+};
+__device__ __forceinline__ float img_px(const float* __restrict__ img, int h, int w, int y, int x) {
+  return (x >= 0 && x < w && y >= 0 && y < h) ? __ldg(img + (long long)y * w + x) : 0.0f;      // BORDER_CONSTANT 0
+}
+// cv2.remap(..., INTER_LINEAR) of a float32 image at float32 coordinates: 1/32-pixel fixed point + float32 bilinear table (remap.cpp)
+__device__ __forceinline__ float remap_bilinear(const float* __restrict__ img, int h, int w, float x, float y) {
+  const long long sx = llrint((double)x * 32.0), sy = llrint((double)y * 32.0);
+  long long ixl = sx >> 5, iyl = sy >> 5;
+  ixl = ixl < -32768 ? -32768 : (ixl > 32767 ? 32767 : ixl); iyl = iyl < -32768 ? -32768 : (iyl > 32767 ? 32767 : iyl);
+  const int ix = (int)ixl, iy = (int)iyl;
+  const float fx = __fdiv_rn((float)(sx & 31), 32.0f), fy = __fdiv_rn((float)(sy & 31), 32.0f);
+  const float w00 = __fmul_rn(__fsub_rn(1.0f, fy), __fsub_rn(1.0f, fx)), w01 = __fmul_rn(__fsub_rn(1.0f, fy), fx);
+  const float w10 = __fmul_rn(fy, __fsub_rn(1.0f, fx)), w11 = __fmul_rn(fy, fx);
+  float r = __fmul_rn(img_px(img, h, w, iy, ix), w00);
+  r = __fadd_rn(r, __fmul_rn(img_px(img, h, w, iy, ix + 1), w01));
+  r = __fadd_rn(r, __fmul_rn(img_px(img, h, w, iy + 1, ix), w10));
+  return __fadd_rn(r, __fmul_rn(img_px(img, h, w, iy + 1, ix + 1), w11));
+}
+struct FrustumPoint { float u, v; double z; float px, py, pz; };
+__device__ __forceinline__ FrustumPoint frustum_project(const FrustumArgs& A, long long vox) {
+  const int w = (int)(vox % A.W), h = (int)((vox / A.W) % A.H), d = (int)(vox / ((long long)A.W * A.H));
+  FrustumPoint P; P.px = A.xs[w]; P.py = A.ys[h]; P.pz = A.zs[d];
+  float c[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)      // float32 matrix-vector product, left to right (Mapper.py:121-122)
+    c[i] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(A.w2c[4 * i], P.px), __fmul_rn(A.w2c[4 * i + 1], P.py)), __fmul_rn(A.w2c[4 * i + 2], P.pz)), A.w2c[4 * i + 3]);
+  c[0] = -c[0];                                                                     // :125
+  const double uu = __dadd_rn(__dmul_rn(A.fx, (double)c[0]), __dmul_rn(A.cx, (double)c[2]));      // K @ cam in float64 (:126)
+  const double vv = __dadd_rn(__dmul_rn(A.fy, (double)c[1]), __dmul_rn(A.cy, (double)c[2]));
+  P.z = __dadd_rn((double)c[2], 1e-5);                                              // :127
+  P.u = (float)__ddiv_rn(uu, P.z); P.v = (float)__ddiv_rn(vv, P.z);                 // :128-129
+  return P;
+}
+// pass 1: looked-up depth of every voxel + its maximum (non-negative floats: the bit pattern is monotone)
+__global__ void frustum_depth_kernel(const FrustumArgs A, float* __restrict__ depths, int* __restrict__ max_bits) {
+  const long long n = (long long)A.D * A.H * A.W;
+  float m = 0.0f;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (long long)gridDim.x * blockDim.x) {
+    const FrustumPoint P = frustum_project(A, v);
+    const float dep = remap_bilinear(A.depth, A.img_h, A.img_w, P.u, P.v);
+    depths[v] = dep;
+    m = fmaxf(m, dep);
+  }
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(max_bits, __float_as_int(m));
+}
+// pass 2: image-bounds test, depth test (zeros replaced by the maximum, :144-147), ball around the camera centre (:153-161)
+__global__ void frustum_mask_kernel(const FrustumArgs A, const float* __restrict__ depths, const int* __restrict__ max_bits, uint8_t* __restrict__ mask) {
+  const long long n = (long long)A.D * A.H * A.W;
+  const float dmax = __int_as_float(*max_bits);
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (long long)gridDim.x * blockDim.x) {
+    const FrustumPoint P = frustum_project(A, v);
+    float dep = depths[v];
+    if (dep == 0.0f) dep = dmax;
+    bool m = (P.u < (float)A.img_w) && (P.u > 0.0f) && (P.v < (float)A.img_h) && (P.v > 0.0f);
+    const double nz = -P.z;
+    m = m && (0.0 <= nz) && (nz <= (double)__fadd_rn(dep, 0.5f));                  // `depths + 0.5` stays float32 (numpy weak scalar), the comparison is float64
+    const float dx = __fsub_rn(P.px, A.cam_o[0]), dy = __fsub_rn(P.py, A.cam_o[1]), dz = __fsub_rn(P.pz, A.cam_o[2]);
+    const float dist = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    mask[v] = (m || dist < 0.25f) ? 1 : 0;
+  }
+}
+
 // d c2w of every keyframe block (one CTA per frame)
 __global__ void pose_grad_frames_kernel(const float* __restrict__ dirs, const float* __restrict__ dro, const float* __restrict__ drd,
                                         const int32_t* __restrict__ offs, float* __restrict__ out) {
@@ -568,6 +639,41 @@ extern "C" int nsb_compact_transpose(const float* src, float* dst, long long n_s
   compact_transpose_kernel<<<(unsigned)((n_selected + 31) / 32), 256, 0, (cudaStream_t)stream>>>(src, dst, n_selected, to_reference);
   return check_cuda(cudaGetLastError(), "compact_transpose launch");
 }
+extern "C" size_t nsb_frustum_mask_workspace(long long n_voxels) { return n_voxels <= 0 ? 16 : (size_t)n_voxels * sizeof(float) + 16; }
+extern "C" int nsb_frustum_mask(const float* c2w, const float* xs, const float* ys, const float* zs, int D, int H, int W,
+                                const float* depth, int img_h, int img_w, double fx, double fy, double cx, double cy,
+                                uint8_t* voxel_mask, void* workspace, size_t workspace_bytes, void* stream) {
+  const long long n = (long long)D * H * W;
+  if (!c2w || !xs || !ys || !zs || D < 1 || H < 1 || W < 1 || !depth || img_h < 1 || img_w < 1 || !voxel_mask || !workspace) {
+    set_error("frustum_mask: bad arguments"); return NSB_ERR_ARG; }
+  if (workspace_bytes < nsb_frustum_mask_workspace(n)) { set_error("frustum_mask: workspace too small"); return NSB_ERR_ARG; }
+  // inverse of the rigid-or-not 4x4 pose in double (Gauss-Jordan with partial pivoting), rounded to float32 like the reference's w2c
+  double a[4][8];
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) { a[i][j] = (double)c2w[4 * i + j]; a[i][4 + j] = i == j ? 1.0 : 0.0; }
+  for (int col = 0; col < 4; col++) {
+    int piv = col;
+    for (int r = col + 1; r < 4; r++) if (fabs(a[r][col]) > fabs(a[piv][col])) piv = r;
+    if (a[piv][col] == 0.0) { set_error("frustum_mask: singular c2w"); return NSB_ERR_ARG; }
+    if (piv != col) for (int j = 0; j < 8; j++) { const double t = a[col][j]; a[col][j] = a[piv][j]; a[piv][j] = t; }
+    const double inv = 1.0 / a[col][col];
+    for (int j = 0; j < 8; j++) a[col][j] *= inv;
+    for (int r = 0; r < 4; r++) if (r != col) { const double f = a[r][col]; if (f != 0.0) for (int j = 0; j < 8; j++) a[r][j] -= f * a[col][j]; }
+  }
+  FrustumArgs A;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 4; j++) A.w2c[4 * i + j] = (float)a[i][4 + j];
+  for (int i = 0; i < 3; i++) A.cam_o[i] = c2w[4 * i + 3];
+  A.xs = xs; A.ys = ys; A.zs = zs; A.D = D; A.H = H; A.W = W; A.depth = depth; A.img_h = img_h; A.img_w = img_w;
+  A.fx = fx; A.fy = fy; A.cx = cx; A.cy = cy;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* depths = static_cast<float*>(workspace);
+  int* max_bits = reinterpret_cast<int*>(static_cast<char*>(workspace) + (size_t)n * sizeof(float));
+  if (check_cuda(cudaMemsetAsync(max_bits, 0, sizeof(int), st), "frustum memset")) return NSB_ERR_CUDA;
+  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  frustum_depth_kernel<<<blocks, 256, 0, st>>>(A, depths, max_bits);
+  frustum_mask_kernel<<<blocks, 256, 0, st>>>(A, depths, max_bits, voxel_mask);
+  return check_cuda(cudaGetLastError(), "frustum_mask launch");
+}
+
 extern "C" int nsb_pose_grad_frames(const float* dirs, const float* d_rays_o, const float* d_rays_d, const int32_t* frame_offsets,
                                     int n_frames, float* out, void* stream) {
   if (n_frames < 0 || (n_frames > 0 && (!dirs || !d_rays_o || !d_rays_d || !frame_offsets || !out))) { set_error("pose_grad_frames: bad arguments"); return NSB_ERR_ARG; }

@@ -7,8 +7,13 @@ using namespace nsb;
 
 static size_t a16(size_t x) { return (x + 15) & ~size_t(15); }
 
+// workspace = [tracking-seeds scratch | packed weight-gradient images | decoder-parallel-CTA scratch (small batches only)]
+static size_t split_bytes(int n_rays) { return nsb_split_workspace_bytes(n_rays, NSB_MAX_SAMPLES); }
 extern "C" size_t nsb_iteration_workspace_bytes(int n_rays) {
-  return a16(nsb_tracking_seeds_workspace(n_rays)) + a16(nsb_backward_workspace_bytes());
+  return a16(nsb_tracking_seeds_workspace(n_rays)) + a16(nsb_backward_workspace_bytes()) + a16(split_bytes(n_rays));
+}
+static void* split_ptr(const nsb_iteration_buffers* b, int n_rays) {
+  return split_bytes(n_rays) ? reinterpret_cast<char*>(b->workspace) + a16(nsb_tracking_seeds_workspace(n_rays)) + a16(nsb_backward_workspace_bytes()) : nullptr;
 }
 
 static int check_buffers(const nsb_render_inputs* in, const nsb_iteration_buffers* b, const nsb_backward_args* g) {
@@ -26,7 +31,7 @@ static int forward_part(const nsb_render_inputs* in, const nsb_iteration_buffers
     if ((rc = nsb_batch_max_depth(in->gt_depth, in->n_rays, b->depth_max, stream))) return rc;
     in2->depth_max = b->depth_max;
   }
-  nsb_forward_outputs fo = {b->depth, b->var, b->rgb, b->z_vals, b->raw, nullptr, b->masks};
+  nsb_forward_outputs fo = {b->depth, b->var, b->rgb, b->z_vals, b->raw, nullptr, b->masks, split_ptr(b, in->n_rays), split_bytes(in->n_rays)};
   return nsb_render_forward(in2, &fo, stream);
 }
 
@@ -34,6 +39,7 @@ static int backward_part(const nsb_render_inputs* in2, const nsb_iteration_buffe
   nsb_backward_args bw = *g;
   bw.z_vals = b->z_vals; bw.raw = b->raw; bw.g_depth = b->g_depth; bw.g_var = nullptr; bw.g_rgb = b->g_rgb; bw.masks = b->masks;
   bw.workspace = reinterpret_cast<char*>(b->workspace) + a16(nsb_tracking_seeds_workspace(in2->n_rays));
+  bw.split_workspace = split_ptr(b, in2->n_rays); bw.split_workspace_bytes = split_bytes(in2->n_rays);
   if (b->event_bwd_begin) cudaEventRecord((cudaEvent_t)b->event_bwd_begin, (cudaStream_t)stream);
   const int rc = nsb_render_backward(in2, &bw, stream);
   if (b->event_bwd_end) cudaEventRecord((cudaEvent_t)b->event_bwd_end, (cudaStream_t)stream);

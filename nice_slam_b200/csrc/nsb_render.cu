@@ -150,6 +150,12 @@ struct KParams {
   int dec[3];
   int dec_pos[3];               // position of dec[i] in the stage's full decoder list (slot of its saved ReLU masks)
   int accumulate_rays;          // backward: add to d_rays_o / d_rays_d instead of overwriting (second launch of a split backward)
+  // decoder-parallel CTAs (tensor-core kernels, small batches): `split` CTAs share one ray group, CTA j evaluates decoder dec[j] only;
+  // their outputs meet in global scratch and the last CTA to arrive (group_done counter) composites / reduces.
+  int split;                    // 1 = one CTA evaluates all decoders of its rays
+  int* group_done;              // [n_groups] arrival counters, zero between launches (the last CTA resets its counter)
+  float4* fwd_parts;            // [n_dec][N*S] decoder outputs of the forward
+  double* ray_parts;            // [n_dec][N][6] per-decoder ray-gradient sums of the backward
   int wbytes;                   // bytes reserved for the weight image in shared memory
   int max_pts, max_rays;        // per-CTA capacities the shared-memory carve-up was sized for
 };
@@ -291,13 +297,13 @@ __device__ __forceinline__ void ray_weights(const float* __restrict__ rw, int S,
 // ------------------------------------------------------------------------------------------------
 // shared by the SIMT and the tensor-core forward kernels
 struct BlockRange { int r0, nr, Pb; };
-__device__ __forceinline__ BlockRange block_range(const KParams& P) {
+__device__ __forceinline__ BlockRange block_range(const KParams& P, int bid) {
   BlockRange b; b.r0 = 0; b.nr = 0;
   if (P.points != nullptr) {
-    const long long p0 = (long long)blockIdx.x * P.rays_per_block;
+    const long long p0 = (long long)bid * P.rays_per_block;
     b.Pb = (int)((P.n_points - p0) < P.rays_per_block ? (P.n_points - p0) : P.rays_per_block);
   } else {
-    b.r0 = blockIdx.x * P.rays_per_block;
+    b.r0 = bid * P.rays_per_block;
     b.nr = P.in.n_rays - b.r0 < P.rays_per_block ? P.in.n_rays - b.r0 : P.rays_per_block;
     b.Pb = b.nr * P.S;
   }
@@ -380,7 +386,7 @@ __global__ void __launch_bounds__(256, 1) render_fwd_kernel(const __grid_constan
   Smem sm;
   smem_layout(P.wbytes, P.max_pts, P.max_rays, warps, kRowsFwd, false, &sm, smem_raw);
   float* act = sm.act + (size_t)warp * kRowsFwd * kRowF;
-  const BlockRange b = block_range(P);
+  const BlockRange b = block_range(P, blockIdx.x);
   const int Pb = b.Pb;
   if (threadIdx.x == 0) { mbar_init(sm.bar, 1); mbar_fence_init(); }
   fwd_sample_sort(P, sm, b);
@@ -408,13 +414,17 @@ namespace nsb {
 // forward kernel, tensor-core (tcgen05, 3xTF32) decoders: 512 threads = four per point of a 128-point tile (nsb_tc.cuh)
 __global__ void __launch_bounds__(tc::kThreads, 1) render_fwd_tc_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];       // tiles need 16-byte alignment only (no-swizzle descriptors)
+  NSB_PH_RESET();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = threadIdx.x & (tc::TM - 1), cg = threadIdx.x >> 7;
   tc::TcSmem t;
   tc::tc_carve(smem_raw, t, false);
   Smem sm;
   smem_layout(0, P.max_pts, P.max_rays, 0, 0, false, &sm, smem_raw + ((tc::tc_smem_bytes(false) + 127) & ~size_t(127)));
-  const BlockRange b = block_range(P);
+  const int nsplit = P.split;                                    // decoder-parallel CTAs per ray group (1 = this CTA does all decoders)
+  const int bid = blockIdx.x / nsplit, my = blockIdx.x - bid * nsplit;
+  const int q0 = nsplit > 1 ? my : 0, q1 = nsplit > 1 ? my + 1 : P.n_dec;
+  const BlockRange b = block_range(P, bid);
   const int Pb = b.Pb;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(t.tmem)), "r"(tc::kTmemCols) : "memory");
@@ -424,13 +434,14 @@ __global__ void __launch_bounds__(tc::kThreads, 1) render_fwd_tc_kernel(const __
   if (threadIdx.x == 0) {
     for (int i = 0; i < tc::kNumBarsFwd; i++) mbar_init(t.bars + i, 1);
     mbar_fence_init();
-    tc::issue_fwd_loads(P, t, P.dec[0], 0);                      // the first decoder's weights arrive under the sampling prologue
+    tc::issue_fwd_loads(P, t, P.dec[q0], 0);                     // the first decoder's weights arrive under the sampling prologue
   }
   fwd_sample_sort(P, sm, b);                                     // contains __syncthreads(): TMEM address + barriers are visible after it
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = *t.tmem;
+  NSB_PH(13);                                                    // sampling / sorting prologue (mark 0 of the first decoder closes it)
 
   const int ntiles = (Pb + tc::TM - 1) / tc::TM;
   for (int tile = 0; tile < ntiles; tile++) {
@@ -438,7 +449,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) render_fwd_tc_kernel(const __
     const int lpc = lp < Pb ? lp : Pb - 1;
     PointGeom G;
     if (P.points != nullptr) {
-      const long long gp = (long long)blockIdx.x * P.rays_per_block + lpc;
+      const long long gp = (long long)bid * P.rays_per_block + lpc;
       const double pin[3] = {P.points[3 * gp], P.points[3 * gp + 1], P.points[3 * gp + 2]};
       make_point_from_p(P.in.bound, P.in.coarse_bound, pin, G);
     } else {
@@ -447,19 +458,22 @@ __global__ void __launch_bounds__(tc::kThreads, 1) render_fwd_tc_kernel(const __
       const float o[3] = {rr[0], rr[1], rr[2]}, dd[3] = {rr[3], rr[4], rr[5]};
       make_point(P.in.bound, P.in.coarse_bound, o, dd, sm.zs[lpc], G);
     }
+    const long long gp0 = ((long long)bid * P.rays_per_block) * P.S;             // global index of this CTA's first point
     float occ = 0.0f, c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
-    for (int qd = 0; qd < P.n_dec; qd++) {
+    for (int qd = q0; qd < q1; qd++) {
       const int lv = P.dec[qd];
       const DecRT d = make_dec(lv);
       float out[4];
-      uint32_t* gm = (P.fo.masks != nullptr && lp < Pb) ? P.fo.masks + ((((long long)blockIdx.x * P.rays_per_block) * P.S + lp) * 15 + qd * 5) : nullptr;
-      const int next_lv = qd + 1 < P.n_dec ? P.dec[qd + 1] : (tile + 1 < ntiles ? P.dec[0] : -1);
+      uint32_t* gm = (P.fo.masks != nullptr && lp < Pb) ? P.fo.masks + ((gp0 + lp) * 15 + qd * 5) : nullptr;
+      const int next_lv = qd + 1 < q1 ? P.dec[qd + 1] : (tile + 1 < ntiles ? P.dec[q0] : -1);
       tc::tile_forward(P, t, d, lv, G, tmem, pp, out, gm, next_lv);
       if (lv == 3) { c0 = out[0]; c1 = out[1]; c2 = out[2]; } else occ += out[0];
+      if (nsplit > 1 && cg == 0 && lp < Pb)                                     // this decoder's outputs -> global scratch
+        P.fwd_parts[(long long)qd * P.in.n_rays * P.S + gp0 + lp] = make_float4(out[0], out[1], out[2], out[3]);
       if (qd == 0 && cg == 0 && lp < Pb && P.fo.corner_idx != nullptr) {
         const nsb_grid& g = P.in.grid[lv];
         const Tri tr = make_tri(lv == 0 ? G.xnc : G.xn, g.W, g.H, g.D);
-        const long long gp = ((long long)blockIdx.x * P.rays_per_block) * P.S + lp;
+        const long long gp = gp0 + lp;
         P.fo.corner_idx[3 * gp] = tr.i0[0]; P.fo.corner_idx[3 * gp + 1] = tr.i0[1]; P.fo.corner_idx[3 * gp + 2] = tr.i0[2];
       }
     }
@@ -471,7 +485,33 @@ __global__ void __launch_bounds__(tc::kThreads, 1) render_fwd_tc_kernel(const __
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tc::kTmemCols) : "memory");
+  if (nsplit > 1) {
+    // decoder-parallel CTAs: the last CTA of the ray group to arrive gathers every decoder's outputs and composites
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int old = atomicAdd(P.group_done + bid, 1);
+      s_last = old == nsplit - 1;
+      if (s_last) P.group_done[bid] = 0;                           // everybody has arrived: leave the counter clean for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const long long gp0 = ((long long)bid * P.rays_per_block) * P.S, NS = (long long)P.in.n_rays * P.S;
+    for (int lp = threadIdx.x; lp < Pb; lp += blockDim.x) {
+      float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, occ = 0.0f;
+      for (int q = 0; q < P.n_dec; q++) {                          // same order as the single-CTA path: occ = fine + middle
+        const float4 v = __ldcg(P.fwd_parts + q * NS + gp0 + lp);
+        if (P.dec[q] == 3) { c0 = v.x; c1 = v.y; c2 = v.z; } else occ += v.x;
+      }
+      *reinterpret_cast<float4*>(sm.raw + 4 * lp) = make_float4(c0, c1, c2, occ);
+    }
+    __syncthreads();
+  }
+  NSB_PH(14);
   fwd_composite_store(P, sm, b, warp, tc::kThreads / 32, lane);
+  NSB_PH(15);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -635,6 +675,7 @@ __global__ void __launch_bounds__(256, 1) render_bwd_kernel(const __grid_constan
 // SIMT kernel for now (host dispatch).
 __global__ void __launch_bounds__(tc::kThreads, 1) render_bwd_tc_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  NSB_PH_RESET();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = threadIdx.x & (tc::TM - 1);
   tc::TcSmem t;
@@ -642,7 +683,10 @@ __global__ void __launch_bounds__(tc::kThreads, 1) render_bwd_tc_kernel(const __
   Smem sm;
   smem_layout(0, P.max_pts, P.max_rays, 0, 0, true, &sm, smem_raw + ((tc::tc_smem_bytes(true) + 127) & ~size_t(127)));
   __shared__ float gC[kMaxRaysPerBlock * 3];
-  const int r0 = blockIdx.x * P.rays_per_block;
+  const int nsplit = P.split;                                    // decoder-parallel CTAs per ray group
+  const int bid = blockIdx.x / nsplit, my = blockIdx.x - bid * nsplit;
+  const int q0 = nsplit > 1 ? my : 0, q1 = nsplit > 1 ? my + 1 : P.n_dec;
+  const int r0 = bid * P.rays_per_block;
   const int nr = P.in.n_rays - r0 < P.rays_per_block ? P.in.n_rays - r0 : P.rays_per_block;
   const int Pb = nr * P.S;
   if (warp == 0) {
@@ -653,7 +697,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) render_bwd_tc_kernel(const __
   if (threadIdx.x == 0) {
     for (int i = 0; i < tc::kNumBarsBwd; i++) mbar_init(t.bars + i, 1);
     mbar_fence_init();
-    tc::issue_bwd_loads(P, t, P.dec[0], 0);                      // the first decoder's operands arrive under the compositing prologue
+    tc::issue_bwd_loads(P, t, P.dec[q0], 0);                     // the first decoder's operands arrive under the compositing prologue
   }
   bwd_prologue(P, sm, r0, nr, Pb, warp, tc::kThreads / 32, lane, gC);
   tc::tc_fence_before();
@@ -672,18 +716,19 @@ __global__ void __launch_bounds__(tc::kThreads, 1) render_bwd_tc_kernel(const __
       const float o[3] = {rr[0], rr[1], rr[2]}, dd[3] = {rr[3], rr[4], rr[5]};
       make_point(P.in.bound, P.in.coarse_bound, o, dd, sm.zs[lpc], G);
     }
-    for (int qd = 0; qd < P.n_dec; qd++) {
+    for (int qd = q0; qd < q1; qd++) {
       const int lv = P.dec[qd];
       const DecRT d = make_dec(lv);
-      const uint32_t* gm = P.bw.masks + ((((long long)blockIdx.x * P.rays_per_block) * P.S + lpc) * 15 + P.dec_pos[qd] * 5);   // saved by the forward kernel
+      const uint32_t* gm = P.bw.masks + ((((long long)bid * P.rays_per_block) * P.S + lpc) * 15 + P.dec_pos[qd] * 5);   // saved by the forward kernel
       float g_out[4] = {0.f, 0.f, 0.f, 0.f};
       if (lp < Pb) {
         if (lv == 3) { const float w = sm.wgt[lp]; g_out[0] = w * gC[3 * ray]; g_out[1] = w * gC[3 * ray + 1]; g_out[2] = w * gC[3 * ray + 2]; }
         else g_out[0] = sm.gocc[lp];
       }
-      const int next_lv = qd + 1 < P.n_dec ? P.dec[qd + 1] : (tile + 1 < ntiles ? P.dec[0] : -1);
+      const int next_lv = qd + 1 < q1 ? P.dec[qd + 1] : (tile + 1 < ntiles ? P.dec[q0] : -1);
       tc::tile_backward(P, t, d, lv, G, tmem, pp, g_out, gm, next_lv);
       __syncthreads();                                           // dL/dc rows + the embedding partials are visible
+      NSB_PH(28);
       const double* bb = lv == 0 ? P.in.coarse_bound : P.in.bound;
       const double sc[3] = {2.0 / (bb[1] - bb[0]), 2.0 / (bb[3] - bb[2]), 2.0 / (bb[5] - bb[4])};      // d(normalised)/dp, common.py:280-282
       const float* xn = lv == 0 ? G.xnc : G.xn;
@@ -697,12 +742,50 @@ __global__ void __launch_bounds__(tc::kThreads, 1) render_bwd_tc_kernel(const __
           for (int a = 0; a < 3; a++) sm.dp[3 * l2 + a] += (double)dpe[a] + (double)gx[a] * sc[a];
         }
       });
+      NSB_PH(29);
     }
   }
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tc::kTmemCols) : "memory");
+  if (nsplit > 1) {
+    // decoder-parallel CTAs: per-decoder ray sums -> global scratch; the last CTA of the group adds them in decoder order
+    __shared__ int s_last;
+    for (int i = threadIdx.x; i < nr * 3; i += blockDim.x) {
+      const int r = i / 3, a = i - 3 * r;
+      double so = 0.0, sd = 0.0;
+      for (int s = 0; s < P.S; s++) { const double v = sm.dp[3 * (r * P.S + s) + a]; so += v; sd += v * sm.zs[r * P.S + s]; }
+      double* part = P.ray_parts + ((long long)my * P.in.n_rays + r0 + r) * 6;
+      part[a] = so; part[3 + a] = sd;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int old = atomicAdd(P.group_done + bid, 1);
+      s_last = old == nsplit - 1;
+      if (s_last) P.group_done[bid] = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int i = threadIdx.x; i < nr * 3; i += blockDim.x) {
+      const int r = i / 3, a = i - 3 * r;
+      double so = 0.0, sd = 0.0;
+      for (int q = 0; q < nsplit; q++) {
+        const double* part = P.ray_parts + ((long long)q * P.in.n_rays + r0 + r) * 6;
+        so += __ldcg(part + a); sd += __ldcg(part + 3 + a);
+      }
+      if (P.accumulate_rays) {
+        if (P.bw.d_rays_o != nullptr) so += (double)P.bw.d_rays_o[3 * (r0 + r) + a];
+        if (P.bw.d_rays_d != nullptr) sd += (double)P.bw.d_rays_d[3 * (r0 + r) + a];
+      }
+      if (P.bw.d_rays_o != nullptr) P.bw.d_rays_o[3 * (r0 + r) + a] = (float)so;
+      if (P.bw.d_rays_d != nullptr) P.bw.d_rays_d[3 * (r0 + r) + a] = (float)sd;
+    }
+    return;
+  }
   bwd_ray_reduce(P, sm, r0, nr);
+  NSB_PH(30);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -745,6 +828,7 @@ static void fill_common(KParams& K, const nsb_render_inputs* in) {
   K.n_dec = stage_decoders(in->stage, K.dec);
   for (int i = 0; i < 3; i++) K.dec_pos[i] = i;
   K.accumulate_rays = 0;
+  K.split = 1; K.group_done = nullptr; K.fwd_parts = nullptr; K.ray_parts = nullptr;
   int wb = 0;
   for (int i = 0; i < K.n_dec; i++) { const int b = packed_floats(K.dec[i]) * 4; wb = b > wb ? b : wb; }
   K.wbytes = wb;
@@ -783,6 +867,37 @@ static size_t tc_total_smem(int max_pts, int max_rays, bool bwd = false) {
   return ((tc::tc_smem_bytes(bwd) + 127) & ~size_t(127)) + smem_layout(0, max_pts, max_rays, 0, 0, bwd, nullptr, nullptr);
 }
 
+// ---- decoder-parallel CTAs: workspace layout and launch policy ------------------------------------------------------------------
+constexpr int kSplitMaxRays = 256;
+static size_t split_counters_bytes(int n_rays) { return align16((size_t)n_rays * sizeof(int)); }
+extern "C" size_t nsb_split_workspace_bytes(int n_rays, int S) {
+  if (n_rays < 1 || n_rays > kSplitMaxRays || S < 1) return 0;
+  const size_t fwd = (size_t)3 * n_rays * S * sizeof(float4), bwd = (size_t)3 * n_rays * 6 * sizeof(double);
+  return split_counters_bytes(n_rays) + (fwd > bwd ? fwd : bwd);
+}
+// Decide whether `nd` CTAs per ray group beat one.  Cost model = tiles a CTA walks through x decoders it evaluates x waves.
+// On success K->rays_per_block / max_pts / max_rays / split and the scratch pointers are set.
+static bool plan_split(KParams* K, int nd, void* ws, size_t ws_bytes) {
+  const int N = K->in.n_rays, S = K->S;
+  if (nd < 2 || K->points != nullptr || !ws || N > kSplitMaxRays || ws_bytes < nsb_split_workspace_bytes(N, S) || (reinterpret_cast<uintptr_t>(ws) & 15)) return false;
+  const int sms = sm_count();
+  int r_cap = kMaxPtsTc / S; if (r_cap < 1) return false; if (r_cap > kMaxRaysPerBlock) r_cap = kMaxRaysPerBlock;
+  int r1 = 0;
+  for (int r = 1; r <= r_cap; r++) if (((N + r - 1) / r) * nd <= sms) { r1 = r; break; }
+  if (!r1) return false;
+  auto tiles = [&](int r) { return (r * S + tc::TM - 1) / tc::TM; };
+  const int groups0 = (N + K->rays_per_block - 1) / K->rays_per_block;
+  const int cost0 = ((groups0 + sms - 1) / sms) * tiles(K->rays_per_block) * nd, cost1 = tiles(r1);
+  if (cost1 >= cost0) return false;
+  K->rays_per_block = r1; K->max_rays = r1; K->max_pts = ((r1 * S + kChunk - 1) / kChunk) * kChunk;
+  K->split = nd;
+  K->group_done = static_cast<int*>(ws);
+  char* rest = static_cast<char*>(ws) + split_counters_bytes(N);
+  K->fwd_parts = reinterpret_cast<float4*>(rest);
+  K->ray_parts = reinterpret_cast<double*>(rest);
+  return true;
+}
+
 static bool g_attr_set = false;
 static int set_attrs() {
   if (g_attr_set) return NSB_OK;
@@ -818,7 +933,8 @@ extern "C" int nsb_render_forward(const nsb_render_inputs* in, const nsb_forward
   const int grid = (in->n_rays + K.rays_per_block - 1) / K.rays_per_block;
   if (g_mlp_backend != 1 && K.S <= kMaxPtsTc) {          // tensor-core decoders, 512 threads, <= 2 tiles of 128 points per CTA
     choose_config(in->n_rays, K.S, kRowsFwd, false, K.wbytes, 8, &K, &warps, &smem, kMaxPtsTc);
-    const int grid_tc = (in->n_rays + K.rays_per_block - 1) / K.rays_per_block;
+    plan_split(&K, K.n_dec, out->split_workspace, out->split_workspace_bytes);
+    const int grid_tc = ((in->n_rays + K.rays_per_block - 1) / K.rays_per_block) * K.split;
     const size_t smem_tc = tc_total_smem(K.max_pts, K.max_rays);
     if (smem_tc > kSmemCap) { set_error("shared-memory budget exceeded (%zu bytes)", smem_tc); return NSB_ERR_UNSUPPORTED; }
     render_fwd_tc_kernel<<<grid_tc, tc::kThreads, smem_tc, (cudaStream_t)stream>>>(K);
@@ -901,7 +1017,8 @@ extern "C" int nsb_render_backward(const nsb_render_inputs* in, const nsb_backwa
     }
     if (T.n_dec > 0) {
       choose_config(in->n_rays, T.S, kRowsBwd, true, T.wbytes, 8, &T, &warps, &smem, kMaxPtsTc);
-      const int grid_tc = (in->n_rays + T.rays_per_block - 1) / T.rays_per_block;
+      plan_split(&T, T.n_dec, bw->split_workspace, bw->split_workspace_bytes);
+      const int grid_tc = ((in->n_rays + T.rays_per_block - 1) / T.rays_per_block) * T.split;
       const size_t smem_tc = tc_total_smem(T.max_pts, T.max_rays, true);
       if (smem_tc > kSmemCap) { set_error("shared-memory budget exceeded (%zu bytes)", smem_tc); return NSB_ERR_UNSUPPORTED; }
       render_bwd_tc_kernel<<<grid_tc, tc::kThreads, smem_tc, st>>>(T);
@@ -923,3 +1040,11 @@ extern "C" int nsb_render_backward(const nsb_render_inputs* in, const nsb_backwa
   if (any_w) return launch_unpack_grads(K.d_packed, bw->d_flat, st);
   return NSB_OK;
 }
+
+#ifdef NSB_PHASE_TIMING
+extern "C" int nsb_debug_phases(long long* out64, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out64, nsb::tc::g_phase, sizeof(long long) * 64);
+  if (e == cudaSuccess && reset) { long long z[64] = {0}; e = cudaMemcpyToSymbol(nsb::tc::g_phase, z, sizeof(z)); }
+  return e == cudaSuccess ? 0 : 1;
+}
+#endif

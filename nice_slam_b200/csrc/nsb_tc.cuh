@@ -18,6 +18,18 @@
 namespace nsb {
 namespace tc {
 
+// Optional phase timing (make TIMING=1 -> libnsb_timing.so, tools/phase_timing.py): thread 0 of CTA 0 accumulates the cycles between
+// consecutive marks per phase id; read back with nsb_debug_phases().  Compiled out of the product library.
+#ifdef NSB_PHASE_TIMING
+__device__ long long g_phase[64];
+__device__ long long g_phase_last;
+#define NSB_PH(id) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long c_ = clock64(); ::nsb::tc::g_phase[id] += c_ - ::nsb::tc::g_phase_last; ::nsb::tc::g_phase_last = c_; } } while (0)
+#define NSB_PH_RESET() do { if (blockIdx.x == 0 && threadIdx.x == 0) ::nsb::tc::g_phase_last = clock64(); } while (0)
+#else
+#define NSB_PH(id) do { } while (0)
+#define NSB_PH_RESET() do { } while (0)
+#endif
+
 constexpr int TM = 128;                 // points per tile
 constexpr uint32_t kTmemCols = 256;     // D1: [0,32)  D2: [32,192)
 // Four threads per point: thread tid owns row (tid & 127) and the 8-column group cg = tid >> 7 of every 32-wide epilogue.
@@ -243,12 +255,14 @@ __device__ __forceinline__ void tile_forward(const KParams& P, const TcSmem& t, 
   float* c_hi = t.x; float* c_lo = t.x + TM * d.cd;
 
   __syncthreads();                       // previous decoder / tile: every read of x, e and of the header buffers is done
+  NSB_PH(0);
   if (!pp.prefetched && t0) issue_fwd_loads(P, t, lv, pp.hb);
   pp.prefetched = false;
   // ---- gather -> C tile
   const float* xn = lv == 0 ? G.xnc : G.xn;
   gather_rows(P.in.grid[lv], c_hi, c_lo, d.cd, 0, xn, warp, lane);
   if (lv == 2) gather_rows(P.in.grid[1], c_hi, c_lo, d.cd, 32, G.xn, warp, lane);
+  NSB_PH(1);
   // ---- D2 = C * [Wc_0; ..; Wc_4]^T  (xyz decoders), one 32-wide K half per chunk; not waited for until x is needed again
   if (d.xyz) {
     publish_operands();
@@ -267,6 +281,7 @@ __device__ __forceinline__ void tile_forward(const KParams& P, const TcSmem& t, 
       __syncwarp();
     }
   }
+  NSB_PH(2);
   // ---- layer 0 and the skip part of layer 3: [D1 | D3] += E_blk * [W0_blk; W3E_blk]^T.  E = Fourier embedding, or (coarse) C itself.
   const float* B = hdr + 464;
   const int nblk = d.xyz ? 3 : 1;
@@ -295,12 +310,14 @@ __device__ __forceinline__ void tile_forward(const KParams& P, const TcSmem& t, 
     }
     pp.par ^= 1u << (W_L0 + slot);
     __syncwarp();
+    NSB_PH(3 + blk);
   }
   if (!d.xyz) pipe_wait(t, pp, W_HDR);
   if (fc_pending) pipe_wait(t, pp, M_FC);
   if (nblk > 1) pipe_wait(t, pp, M_L1);
   pipe_wait(t, pp, M_L0);                                   // (blocks 0/2 use slot 0: the last commit on it is block nblk-1 or 2)
   tc_fence_after();
+  NSB_PH(6);
   float* h_hi = t.x + 2 * TM * 32;
   float* h_lo = t.x + 3 * TM * 32;
   float h[kCW];
@@ -335,6 +352,7 @@ __device__ __forceinline__ void tile_forward(const KParams& P, const TcSmem& t, 
     __syncwarp();
     pipe_wait(t, pp, M_H);
     tc_fence_after();
+    NSB_PH(7 + i);
   }
   tc_fence_before();
   // every weight region is free again: prefetch the next decoder's first chunks under the output layer and the next gather
@@ -362,6 +380,7 @@ __device__ __forceinline__ void tile_forward(const KParams& P, const TcSmem& t, 
     out[0] += v.x; out[1] += v.y; out[2] += v.z; out[3] += v.w;
   }
   pp.hb ^= 1;
+  NSB_PH(12);
 }
 
 // Backward of decoder `lv` for one tile, input gradients only (rays + grid voxels; decoder-weight gradients go through the FP32 kernel).
@@ -377,6 +396,7 @@ __device__ __forceinline__ void tile_backward(const KParams& P, const TcSmem& t,
   const bool t0 = threadIdx.x == 0;
   const float* hdr = t.hdr + pp.hb * kHdrFloats;
   __syncthreads();                                          // previous decoder's scatter (reads of x) is done
+  NSB_PH(20);
   if (!pp.prefetched && t0) issue_bwd_loads(P, t, lv, pp.hb);
   pp.prefetched = false;
   uint32_t mlo = 0, mhi = 0;                                // this thread's 8 ReLU bits of layers 0..3 (one byte each) and of layer 4
@@ -398,6 +418,7 @@ __device__ __forceinline__ void tile_backward(const KParams& P, const TcSmem& t,
   }
   uint32_t acc_dc = 0, acc_df = 0;
   const float* img = P.in.packed[lv] + op_bwd_offset(lv);
+  NSB_PH(21);
 #pragma unroll 1
   for (int i = 4; i >= 0; i--) {
     const uint32_t m = i == 4 ? mhi : (mlo >> (8 * i)) & 0xffu;
@@ -425,6 +446,7 @@ __device__ __forceinline__ void tile_backward(const KParams& P, const TcSmem& t,
     if (t0 && i >= 2) tma_load(t, W_S0 + s, t.wS + s * kBwdStageFloats, img + op_bwd_layer_offset(lv, i - 2), op_bwd_layer_floats(lv, i - 2));
     if (i >= 1) tmem_ld8(tmem + my, g);
     tc_fence_before();
+    NSB_PH(22 + (4 - i));
   }
   // both stages are free: the next decoder's header and first two layers arrive under the epilogue and the scatter
   if (next_lv >= 0) { if (t0) issue_bwd_loads(P, t, next_lv, pp.hb ^ 1); pp.prefetched = true; }
@@ -462,6 +484,7 @@ __device__ __forceinline__ void tile_backward(const KParams& P, const TcSmem& t,
   *reinterpret_cast<float4*>(t.x + 2 * TM * 32 + (cg * TM + row) * 4) = make_float4(dpe[0], dpe[1], dpe[2], 0.0f);
   tc_fence_before();
   pp.hb ^= 1;
+  NSB_PH(27);
 }
 // dL/dp of `row` through the embedding: sum of the kCG partials tile_backward left in shared memory (call after a CTA barrier)
 __device__ __forceinline__ void dpe_sum(const TcSmem& t, int row, float (&dpe)[3]) {

@@ -64,3 +64,31 @@ class MaskedVoxels:
 
     def from_reference(self, vec):
         return self._transpose(vec.contiguous(), False).view(self.count, 32)
+
+
+def frustum_voxel_mask(renderer, c2w, key, grid, depth):
+    """Mapper.get_mask_from_c2w (src/Mapper.py:93-164) on the device: bool [D,H,W] mask of the voxels of `grid` ([1,32,D,H,W], key
+    'grid_middle' / 'grid_fine' / 'grid_color' / 'grid_coarse') that the current frame (pose `c2w` [4,4], sensor `depth` [H,W]) can see.
+    `renderer` supplies the scene bound and the intrinsics (the attributes the reference's Mapper copies from slam, Mapper.py:40-60)."""
+    L = _lib.lib()
+    if not grid.is_cuda:
+        raise RuntimeError("nice_slam_b200: frustum_voxel_mask needs CUDA tensors (no CPU fallback)")
+    dev = grid.device
+    D, H, W = grid.shape[2:]
+    if key == "grid_coarse":                                         # Mapper.py:114-116
+        return torch.ones(D, H, W, dtype=torch.bool, device=dev)
+    b = renderer.bound
+    # voxel-centre coordinates exactly as the reference builds them (float32 torch.linspace on the host, Mapper.py:108-110)
+    xs = torch.linspace(b[0][0], b[0][1], W).to(dev)
+    ys = torch.linspace(b[1][0], b[1][1], H).to(dev)
+    zs = torch.linspace(b[2][0], b[2][1], D).to(dev)
+    pose = torch.as_tensor(c2w).detach().to("cpu", torch.float32).contiguous()
+    c2w_host = (C.c_float * 16)(*pose.reshape(-1).tolist())
+    dep = torch.as_tensor(depth).to(dev, torch.float32).contiguous()
+    mask = torch.empty(D * H * W, dtype=torch.uint8, device=dev)
+    ws = torch.empty(L.nsb_frustum_mask_workspace(D * H * W), dtype=torch.uint8, device=dev)
+    _lib.check(L.nsb_frustum_mask(c2w_host, _VP(xs.data_ptr()), _VP(ys.data_ptr()), _VP(zs.data_ptr()), D, H, W,
+                                  _VP(dep.data_ptr()), dep.shape[0], dep.shape[1], float(renderer.fx), float(renderer.fy),
+                                  float(renderer.cx), float(renderer.cy), _VP(mask.data_ptr()), _VP(ws.data_ptr()), ws.numel(), _stream()),
+               "nsb_frustum_mask")
+    return mask.view(D, H, W).bool()

@@ -170,7 +170,10 @@ class _RenderFn(torch.autograd.Function):
         z_vals = torch.empty(n, S, dtype=torch.float64, device=dev)
         raw = torch.empty(n, S, 4, dtype=torch.float32, device=dev)
         masks = torch.empty(n, S, 15, dtype=torch.int32, device=dev)      # ReLU sign bits: lets backward skip the forward recompute
-        out = _lib.ForwardOutputs(depth.data_ptr(), var.data_ptr(), rgb.data_ptr(), z_vals.data_ptr(), raw.data_ptr(), None, masks.data_ptr())
+        nsplit = L.nsb_split_workspace_bytes(n, S)                        # small batches: one CTA per (ray group, decoder)
+        split = torch.zeros(nsplit, dtype=torch.uint8, device=dev) if nsplit else None
+        out = _lib.ForwardOutputs(depth.data_ptr(), var.data_ptr(), rgb.data_ptr(), z_vals.data_ptr(), raw.data_ptr(), None, masks.data_ptr(),
+                                  split.data_ptr() if nsplit else None, nsplit)
         corner = None
         if call.aux is not None:
             corner = torch.empty(n, S, 3, dtype=torch.int32, device=dev)
@@ -180,7 +183,7 @@ class _RenderFn(torch.autograd.Function):
             call.aux.update(z_vals=z_vals, raw=raw, corner_idx=corner)
         ctx.call = call
         ctx.n_lvl = n_lvl
-        ctx.keep = (ro, rd, depth_max, t_u, t_s, z_vals, raw, masks)
+        ctx.keep = (ro, rd, depth_max, t_u, t_s, z_vals, raw, masks, split)
         ctx.grids = [g.detach() for g in grids]
         ctx.param_shapes = [tuple(p.shape) for p in params]
         return depth, var, rgb
@@ -189,7 +192,7 @@ class _RenderFn(torch.autograd.Function):
     def backward(ctx, g_depth, g_var, g_rgb):
         L = _lib.lib()
         call = ctx.call
-        ro, rd, depth_max, t_u, t_s, z_vals, raw, masks = ctx.keep
+        ro, rd, depth_max, t_u, t_s, z_vals, raw, masks, split = ctx.keep
         dev = ro.device
         n = ro.shape[0]
         n_lvl = ctx.n_lvl
@@ -197,6 +200,8 @@ class _RenderFn(torch.autograd.Function):
         inp = _inputs(call, ro, rd, depth_max, t_u, t_s, ctx.grids)
         bw = _lib.BackwardArgs()
         bw.z_vals, bw.raw, bw.masks = z_vals.data_ptr(), raw.data_ptr(), masks.data_ptr()
+        if split is not None:
+            bw.split_workspace, bw.split_workspace_bytes = split.data_ptr(), split.numel()
         gd = g_depth.detach().contiguous().double() if g_depth is not None else torch.zeros(n, dtype=torch.float64, device=dev)
         gv = g_var.detach().contiguous().double() if g_var is not None else None
         gc = g_rgb.detach().contiguous().float() if g_rgb is not None else None

@@ -58,7 +58,9 @@ class IterationContext:
         self.g_rgb = torch.empty(n, 3, dtype=f32, device=dev)
         self.loss = torch.zeros(1, dtype=f64, device=dev)
         self.depth_max = torch.zeros(2, dtype=f32, device=dev)
-        self.ws = torch.empty(L.nsb_iteration_workspace_bytes(n), dtype=torch.uint8, device=dev)
+        self.ws = torch.zeros(L.nsb_iteration_workspace_bytes(n), dtype=torch.uint8, device=dev)     # zeroed once: holds the split counters
+        self.split_ws = torch.zeros(max(L.nsb_split_workspace_bytes(n, S), 16), dtype=torch.uint8, device=dev)   # decoder-parallel CTAs (small batches)
+        self.split_bytes = L.nsb_split_workspace_bytes(n, S)
         self.d_out = torch.empty(n * 6, dtype=f32, device=dev)          # [d_rays_o | d_rays_d], one block for the read-back
         self.d_rays_o = self.d_out[: 3 * n].view(n, 3)
         self.d_rays_d = self.d_out[3 * n:].view(n, 3)

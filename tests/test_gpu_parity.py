@@ -432,3 +432,104 @@ def test_masked_mapping_iteration_packed_block(backend_decoder_grads):
     ctx.packed.fill_(7.0)
     g.replay(); torch.cuda.synchronize()
     assert rel(ctx.packed, packed) < 1e-5
+
+
+# ------------------------------------------------------------------------------------ more edge cases
+def test_render_img_matches_oracle_per_ray_batch():
+    """Renderer.render_img (Renderer.py:200-255): full image in ray_batch_size chunks; the batch-global depth maxima are per chunk,
+    exactly as in the reference."""
+    from types import SimpleNamespace
+    from gpu_util import make_cfg
+    from nice_slam_b200.decoders import NICEDecoders
+    from nice_slam_b200.renderer import FusedRenderer
+    sc = dict(su.load_scenes()["room0"])
+    H, W = 12, 20
+    cam = dict(sc["cam"]); cam.update(H=H, W=W, fx=15.0, fy=15.0, cx=9.5, cy=5.5)
+    grids, dec_state = su.make_grids(sc, "soft"), su.load_decoders("soft")
+    c = {k: v.to(DEV) for k, v in grids.items()}
+    slam = SimpleNamespace(nice=True, bound=su.scene_bound(sc), shared_c=c, H=H, W=W, fx=cam["fx"], fy=cam["fy"], cx=cam["cx"], cy=cam["cy"])
+    r = FusedRenderer(make_cfg(sc), SimpleNamespace(nice=True), slam, ray_batch_size=100)
+    dec = NICEDecoders.from_state(dec_state, DEV)
+    c2w = su.make_pose(sc, 4)
+    g = torch.Generator().manual_seed(12)
+    gt = torch.rand(H, W, generator=g) * 3 + 0.5
+    gt[2, 3] = 0
+    d, u, col = r.render_img(slam.shared_c, dec, c2w.to(DEV), DEV, "color", gt_depth=gt.to(DEV))
+    assert d.shape == (H, W) and u.shape == (H, W) and col.shape == (H, W, 3)
+    # oracle: same rays (get_rays, common.py:248-266), same chunking
+    i, j = torch.meshgrid(torch.linspace(0, W - 1, W), torch.linspace(0, H - 1, H), indexing="ij")
+    i, j = i.t(), j.t()
+    dirs = torch.stack([(i - cam["cx"]) / cam["fx"], -(j - cam["cy"]) / cam["fy"], -torch.ones_like(i)], -1)
+    rd = torch.sum(dirs.reshape(H, W, 1, 3) * c2w[:3, :3], -1).reshape(-1, 3)
+    ro = c2w[:3, -1].expand(rd.shape)
+    bound = su.scene_bound(sc)
+    wd, wu, wc = [], [], []
+    for s in range(0, H * W, 100):
+        a, b_, cc = tp.render_batch_ray(grids, dec_state, rd[s:s + 100], ro[s:s + 100], "color", gt.reshape(-1)[s:s + 100], bound)
+        wd.append(a); wu.append(b_); wc.append(cc)
+    assert rel(d.reshape(-1), torch.cat(wd)) < TOL and rel(u.reshape(-1), torch.cat(wu)) < TOL and rel(col.reshape(-1, 3), torch.cat(wc)) < TOL
+
+
+def test_empty_batch_and_sample_count_limits():
+    sc = su.load_scenes()["room0"]
+    grids, dec_state = su.make_grids(sc, "soft"), su.load_decoders("soft")
+    renderer, c, dec = make_renderer(sc, grids, dec_state, DEV)
+    z3 = torch.zeros(0, 3, device=DEV)
+    d, u, col = renderer.render_batch_ray(c, dec, z3.clone().requires_grad_(True), z3.clone().requires_grad_(True), DEV, "color",
+                                          gt_depth=torch.zeros(0, device=DEV))
+    assert d.shape == (0,) and u.shape == (0,) and col.shape == (0, 3)
+    (d.sum() + col.sum()).backward()                                   # empty backward is a no-op, not an error
+    # the largest supported sample count (256 per ray) against the oracle; one more raises
+    bound = su.scene_bound(sc)
+    ro, rd, gd, _ = su.make_rays(sc, 9, seed=8)
+    r2, c2, dec2 = make_renderer(sc, grids, dec_state, DEV, n_samples=240, n_surface=16)
+    want = tp.render_batch_ray(grids, dec_state, rd, ro, "color", gd, bound, 240, 16)
+    got = r2.render_batch_ray(c2, dec2, rd.to(DEV), ro.to(DEV), DEV, "color", gt_depth=gd.to(DEV))
+    for a, b in zip(got, want):
+        assert rel(a, b) < TOL
+    r3, c3, dec3 = make_renderer(sc, grids, dec_state, DEV, n_samples=241, n_surface=16)
+    with pytest.raises(RuntimeError, match="exceeds"):
+        r3.render_batch_ray(c3, dec3, rd.to(DEV), ro.to(DEV), DEV, "color", gt_depth=gd.to(DEV))
+
+
+@pytest.mark.parametrize("scene", ["scene0000", "apartment"])
+def test_other_scene_volumes_against_oracle(scene):
+    """ScanNet scene0000 / Apartment bounds and grid shapes: forward + backward of a small batch."""
+    sc = su.load_scenes()[scene]
+    grids, dec_state = su.make_grids(sc, "soft"), su.load_decoders("soft")
+    renderer, c, dec = make_renderer(sc, grids, dec_state, DEV)
+    bound = su.scene_bound(sc)
+    ro, rd, gd, gc = su.make_rays(sc, 40, seed=17)
+    out = tp.iteration("track", grids, dec_state, ro, rd, gd, gc.double(), "color", bound)
+    r1, r2 = ro.to(DEV).requires_grad_(True), rd.to(DEV).requires_grad_(True)
+    aux = {}
+    d, u, col = renderer.render_batch_ray(c, dec, r2, r1, DEV, "color", gt_depth=gd.to(DEV), aux=aux)
+    assert torch.equal(aux["z_vals"].cpu(), tp.sample_z_vals(ro, rd, gd, bound, 32, 16, "color"))
+    tp.tracking_loss(d, u, col, gd.to(DEV), gc.double().to(DEV)).backward()
+    assert rel(d, out["depth"]) < TOL and rel(col, out["color"]) < TOL and rel(u, out["var"]) < TOL
+    assert rel(r1.grad, out["d_rays_o"]) < TOL and rel(r2.grad, out["d_rays_d"]) < TOL
+
+
+def test_frustum_mask_matches_real_mapper_masks():
+    """nsb_frustum_mask against the masks of the real Mapper.get_mask_from_c2w (tests/golden/mapper_*.pt); a voxel may differ only if it
+    sits on a decision boundary (the oracle reports how far every voxel is from each threshold)."""
+    import numpy as np
+    from oracle import frustum as fr
+    from nice_slam_b200.masked import MaskedVoxels, frustum_voxel_mask
+    sc = su.load_scenes()["room0"]
+    case = torch.load(os.path.join(su.GOLDEN, "mapper_color.pt"), map_location="cpu", weights_only=False)
+    depth, _ = su.make_frame(sc, case["frame_seed"])
+    c2w = su.make_pose(sc, 1)
+    renderer, c, dec = make_renderer(sc, su.make_grids(sc, "soft"), su.load_decoders("soft"), DEV)
+    bound = su.scene_bound(sc)
+    for key, want in case["masks"].items():
+        got = frustum_voxel_mask(renderer, c2w, key, c[key], depth.to(DEV)).cpu()
+        diff = got != want
+        if bool(diff.any()):
+            mg = {}
+            fr.frustum_mask(c2w, key, tuple(want.shape), depth.numpy(), bound, sc["cam"], margins=mg)
+            W_, H_, D_ = want.shape[2], want.shape[1], want.shape[0]
+            near = np.minimum.reduce([mg["uv"], mg["z"], mg["ball"]]).reshape(W_, H_, D_).transpose(2, 1, 0)
+            assert float(near[diff.numpy()].max()) < 1e-4, (key, int(diff.sum()))
+        assert int(diff.sum()) <= 2, (key, int(diff.sum()))
+        assert MaskedVoxels(c[key], got.to(DEV)).count == int(got.sum())

@@ -116,3 +116,24 @@ def test_mapper_boundary_capture(stage):
         assert mine["nnz"] == summ["nnz"] and torch.equal(mine["val"], summ["val"]), k
     for k, v in case["d_color_decoder"].items():
         assert torch.equal(out["d_dec"]["color"][k], v), k
+
+
+def test_frustum_oracle_matches_real_mapper_masks_and_cv2_remap():
+    """oracle/frustum.py against (a) the masks the REAL Mapper.get_mask_from_c2w produced (stored with the mapper captures) and
+    (b) cv2.remap itself for the bilinear look-up."""
+    import numpy as np
+    from oracle import frustum as fr
+    sc = su.load_scenes()["room0"]
+    case = torch.load(os.path.join(su.GOLDEN, "mapper_color.pt"), map_location="cpu", weights_only=False)
+    depth, _ = su.make_frame(sc, case["frame_seed"])
+    c2w = su.make_pose(sc, 1)
+    bound = su.scene_bound(sc)
+    for key, want in case["masks"].items():
+        got = fr.frustum_mask(c2w, key, tuple(want.shape), depth.numpy(), bound, sc["cam"])
+        assert torch.equal(got, want), key
+        assert key == "grid_coarse" or 0 < int(want.sum()) < want.numel()
+    cv2 = pytest.importorskip("cv2")
+    g = np.random.default_rng(0)
+    x = (g.random(20000) * 1300 - 50).astype(np.float32)
+    y = (g.random(20000) * 800 - 60).astype(np.float32)
+    assert np.array_equal(cv2.remap(depth.numpy(), x, y, interpolation=cv2.INTER_LINEAR)[:, 0], fr.remap_bilinear(depth.numpy(), x, y))
