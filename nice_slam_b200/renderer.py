@@ -178,7 +178,8 @@ class _RenderFn(torch.autograd.Function):
         if call.aux is not None:
             corner = torch.empty(n, S, 3, dtype=torch.int32, device=dev)
             out.corner_idx = corner.data_ptr()
-        _lib.check(L.nsb_render_forward(C.byref(inp), C.byref(out), _stream()), "nsb_render_forward")
+        if n > 0:                                                         # (an empty batch has no storage to point at)
+            _lib.check(L.nsb_render_forward(C.byref(inp), C.byref(out), _stream()), "nsb_render_forward")
         if call.aux is not None:
             call.aux.update(z_vals=z_vals, raw=raw, corner_idx=corner)
         ctx.call = call
