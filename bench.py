@@ -321,6 +321,13 @@ def mapping_sharded_workload(sc, renderer, c, dec, dev, flush, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------ native arm (GPU)
+# dram__bytes_read.sum + dram__bytes_write.sum of one render_bwd_tc_kernel launch of THIS workload (200 rays x 48, room0), taken from the
+# committed `ncu --set full` capture (never measured inside a timed run): the 48.5 MB of grids are L2-resident, so DRAM traffic is far
+# below the 29.5 MB of algorithmic gather bytes.
+NCU_DRAM_BYTES_PER_BWD_LAUNCH = 3994880
+NCU_TRAFFIC_SOURCE = "profiles/ncu_full_r01i_render_kernels.txt (ncu --set full, 3.99 MB read + 0 B written per launch)"
+
+
 def dbg(msg):
     if os.environ.get("NSB_BENCH_DEBUG"):
         print("[bench rank %s] %s" % (os.environ.get("RANK", "0"), msg), file=sys.stderr, flush=True)
@@ -395,7 +402,7 @@ def run_native(args):
             if use_graph:
                 g_e2e.replay()
             else:
-                ctx.d_in32.copy_(ctx.h_in32, non_blocking=True); ctx.gt_color.copy_(ctx.h_col, non_blocking=True)
+                ctx.d_in.copy_(ctx.h_in, non_blocking=True)
                 sharded.enqueue()
                 ctx.h_pose13.copy_(sharded.packed, non_blocking=True)
             torch.cuda.current_stream().synchronize()
@@ -464,7 +471,7 @@ def run_native(args):
                        "timing": "sum of per-step CUDA-event pairs, max over ranks"},
             "clocks": clocks,
             "e2e": {"value": rays / (e2e_ms / args.steps * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": ctx.h2d_bytes,
-                    "d2h_bytes_per_step": (ctx.d2h_bytes + 96) if sharded is None else 13 * 8, "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": ctx.d2h_bytes if sharded is None else 13 * 8, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": (5 if (sharded is None or sharded.peers is not None) else 6) * args.steps,
             "extra": {"l2_warm_ms_per_step": warm_ms / args.steps, "l2_warm_rays_per_s": rays / (warm_ms / args.steps * 1e-3),
                       "mapping_sharded_masked": map_sharded}}
@@ -472,7 +479,8 @@ def run_native(args):
         t_bwd = statistics.mean(bwd_ms) * 1e-3
         ach = BYTES_PER_RAY * RAYS_PER_GPU / t_bwd / 1e9
         line["roofline"] = {"bound": "hbm", "kernel": "render_bwd_tc_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                            "traffic": None, "peak_source": peak_src, "launch_ms": t_bwd * 1e3,
+                            "traffic": NCU_DRAM_BYTES_PER_BWD_LAUNCH, "traffic_source": NCU_TRAFFIC_SOURCE,
+                            "peak_source": peak_src, "launch_ms": t_bwd * 1e3,
                             "algorithmic_bytes_per_launch": BYTES_PER_RAY * RAYS_PER_GPU,
                             "note": "200-ray tracking batch (100 CTAs on 148 SMs) is latency bound, not HBM bound: the grids are L2-resident (see DESIGN.md)"}
     if world == 1:

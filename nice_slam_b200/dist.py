@@ -175,8 +175,7 @@ class ShardedTrackingIteration:
 
         def body():
             if host_io:
-                x.d_in32.copy_(x.h_in32, non_blocking=True)
-                x.gt_color.copy_(x.h_col, non_blocking=True)
+                x.d_in.copy_(x.h_in, non_blocking=True)
             self.enqueue()
             if host_io:
                 x.h_pose13.copy_(self.packed, non_blocking=True)

@@ -56,20 +56,27 @@ class IterationContext:
         self.masks = torch.empty(n, S, 15, dtype=torch.int32, device=dev)
         self.g_depth = torch.empty(n, dtype=f64, device=dev)
         self.g_rgb = torch.empty(n, 3, dtype=f32, device=dev)
-        self.loss = torch.zeros(1, dtype=f64, device=dev)
+        # results that travel back to the host live in ONE block so that the end-to-end form needs a single D2H copy:
+        #   [d_rays_o | d_rays_d] f32 (6n) | pad to 8 B | loss f64 | d c2w f64 [3,4]
+        res_off = ((n * 6 * 4 + 7) // 8) * 8
+        self.d_res = torch.zeros(res_off + 13 * 8, dtype=torch.uint8, device=dev)
+        self.loss = self.d_res[res_off: res_off + 8].view(f64)
         self.depth_max = torch.zeros(2, dtype=f32, device=dev)
         self.ws = torch.zeros(L.nsb_iteration_workspace_bytes(n), dtype=torch.uint8, device=dev)     # zeroed once: holds the split counters
         self.split_ws = torch.zeros(max(L.nsb_split_workspace_bytes(n, S), 16), dtype=torch.uint8, device=dev)   # decoder-parallel CTAs (small batches)
         self.split_bytes = L.nsb_split_workspace_bytes(n, S)
-        self.d_out = torch.empty(n * 6, dtype=f32, device=dev)          # [d_rays_o | d_rays_d], one block for the read-back
+        self.d_out = self.d_res[: n * 24].view(f32)                      # [d_rays_o | d_rays_d]
         self.d_rays_o = self.d_out[: 3 * n].view(n, 3)
         self.d_rays_d = self.d_out[3 * n:].view(n, 3)
-        self.d_c2w = torch.zeros(3, 4, dtype=f64, device=dev)
+        self.d_c2w = self.d_res[res_off + 8:].view(f64).view(3, 4)
         # device-side inputs (run_host copies into these; run() can alias caller tensors instead)
-        self.rays_o = torch.empty(n, 3, dtype=f32, device=dev)
-        self.rays_d = torch.empty(n, 3, dtype=f32, device=dev)
-        self.gt_depth = torch.empty(n, dtype=f32, device=dev)
-        self.gt_color = torch.empty(n, 3, dtype=f64 if kind == "track" else f32, device=dev)
+        # ... and the per-iteration inputs in one block (a single H2D copy):  [rays_o | rays_d | gt_depth] f32 (7n) | pad | gt_color
+        col_dt = f64 if kind == "track" else f32
+        col_off = ((n * 7 * 4 + 7) // 8) * 8
+        col_bytes = n * 3 * (8 if col_dt == f64 else 4)
+        self.d_in = torch.zeros(col_off + col_bytes, dtype=torch.uint8, device=dev)
+        self.d_in32 = self.d_in[: n * 28].view(f32)
+        self.gt_color = self.d_in[col_off:].view(col_dt).view(n, 3)
         self.grad_grids = tuple(grad_grids)
         self.grad_decoders = tuple(grad_decoders)
         self.masked = dict(masked or {})
@@ -88,15 +95,17 @@ class IterationContext:
                                          self.depth_max.data_ptr(), self.ws.data_ptr(), self.ws.numel(), None, None)
         self.ev_bwd = None
         # pinned host staging for run_host(): [rays_o | rays_d | gt_depth] f32, gt_color, and the read-back block
-        self.h_in32 = torch.empty(n * 7, dtype=f32).pin_memory() if dev.type == "cuda" else None
-        self.h_col = torch.empty(n, 3, dtype=self.gt_color.dtype).pin_memory() if dev.type == "cuda" else None
-        self.d_in32 = torch.empty(n * 7, dtype=f32, device=dev)
-        self.h_out = torch.empty(n * 6, dtype=f32).pin_memory() if dev.type == "cuda" else None
-        self.h_loss = torch.empty(1, dtype=f64).pin_memory() if dev.type == "cuda" else None
-        self.h_pose = torch.empty(3, 4, dtype=f64).pin_memory() if dev.type == "cuda" else None
-        self.h_pose13 = torch.empty(13, dtype=f64).pin_memory() if dev.type == "cuda" else None
-        self.h2d_bytes = n * 7 * 4 + self.gt_color.numel() * self.gt_color.element_size()
-        self.d2h_bytes = n * 6 * 4 + 8
+        cuda = dev.type == "cuda"
+        self.h_in = torch.zeros(self.d_in.numel(), dtype=torch.uint8).pin_memory() if cuda else None
+        self.h_in32 = self.h_in[: n * 28].view(f32) if cuda else None
+        self.h_col = self.h_in[col_off:].view(col_dt).view(n, 3) if cuda else None
+        self.h_res = torch.zeros(self.d_res.numel(), dtype=torch.uint8).pin_memory() if cuda else None
+        self.h_out = self.h_res[: n * 24].view(f32) if cuda else None
+        self.h_loss = self.h_res[res_off: res_off + 8].view(f64) if cuda else None
+        self.h_pose = self.h_res[res_off + 8:].view(f64).view(3, 4) if cuda else None
+        self.h_pose13 = torch.empty(13, dtype=f64).pin_memory() if cuda else None
+        self.h2d_bytes = self.d_in.numel()
+        self.d2h_bytes = self.d_res.numel()
 
     # ------------------------------------------------------------------------------------------
     def _grads(self, c):
@@ -193,15 +202,12 @@ class IterationContext:
 
         def body():
             if host_io:
-                self.d_in32.copy_(self.h_in32, non_blocking=True)
-                self.gt_color.copy_(self.h_col, non_blocking=True)
+                self.d_in.copy_(self.h_in, non_blocking=True)             # one H2D copy: rays, sensor depth and colour
             self.run(c, decoders, ro, rd, gd, gc, **kw)
             if dirs is not None:
                 self.pose_grad(dirs)
             if host_io:
-                self.h_out.copy_(self.d_out, non_blocking=True)
-                self.h_loss.copy_(self.loss, non_blocking=True)
-                self.h_pose.copy_(self.d_c2w, non_blocking=True)
+                self.h_res.copy_(self.d_res, non_blocking=True)           # one D2H copy: ray gradients, loss, pose gradient
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
@@ -226,11 +232,9 @@ class IterationContext:
         """End-to-end: pinned host inputs -> device -> iteration -> loss + ray gradients back to pinned host memory.
         Returns (loss float, d_rays [N,6] pinned host view).  Synchronises the current stream."""
         n = self.n
-        self.d_in32.copy_(self.h_in32, non_blocking=True)
-        self.gt_color.copy_(self.h_col, non_blocking=True)
+        self.d_in.copy_(self.h_in, non_blocking=True)
         ro, rd, gd = self.d_in32[: 3 * n].view(n, 3), self.d_in32[3 * n: 6 * n].view(n, 3), self.d_in32[6 * n:]
         self.run(c, decoders, ro, rd, gd, self.gt_color, **kw)
-        self.h_out.copy_(self.d_out, non_blocking=True)
-        self.h_loss.copy_(self.loss, non_blocking=True)
+        self.h_res.copy_(self.d_res, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(self.h_loss[0]), self.h_out.view(2, n, 3)
