@@ -174,7 +174,7 @@ def run_reference(args):
                                        % (args.steps, n_rays, best[1], os.cpu_count() or 1)},
             "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def extra_workloads(sc, renderer, c, dec, dev, flush, peak):
@@ -504,7 +504,7 @@ def run_native(args):
                                 "sample": "%d iterations of the same 200-ray batch, oracle/torch_port.py on PyTorch CPU (%d threads of %d cores)"
                                           % (k, best[1], os.cpu_count() or 1),
                                 "ms_per_step": dtc * 1e3}
-    print(json.dumps(line))
+    emit(line)
     shutdown(world)
 
 
@@ -522,7 +522,24 @@ def shutdown(world):
         os._exit(0)
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract goes to the real stdout; everything else this process (or a library: NCCL prints its version
+    banner to stdout) writes to fd 1 has been redirected to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)

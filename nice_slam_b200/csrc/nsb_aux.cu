@@ -238,7 +238,7 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 }
 __device__ __forceinline__ double sgn(double x) { return (x > 0.0) - (x < 0.0); }
 
-constexpr int kMedianDirect = 2048;
+constexpr int kMedianDirect = 512;       // larger pools: 8-pass radix select (the direct count is O(n^2))
 // Tracker.optimize_cam_in_batch loss (src/Tracker.py:108-123); single CTA, residuals staged in `res`.
 __global__ void tracking_seeds_kernel(const double* __restrict__ depth, const double* __restrict__ var, const float* __restrict__ rgb,
                                       const float* __restrict__ gt, const double* __restrict__ gt_rgb, int n, double w_color,
@@ -247,6 +247,8 @@ __global__ void tracking_seeds_kernel(const double* __restrict__ depth, const do
                                       double* __restrict__ loss, double* __restrict__ res, const PeerX px) {
   __shared__ double red[32];
   __shared__ int hist[256];
+  __shared__ int wtot[8];
+  __shared__ int sel[2];
   __shared__ unsigned long long keys[kMedianDirect];
   __shared__ unsigned long long med_key;
   __shared__ double med_s;
@@ -298,14 +300,21 @@ __global__ void tracking_seeds_kernel(const double* __restrict__ depth, const do
           if ((key & maskhi) == prefix) atomicAdd(&hist[(int)((key >> shift) & 0xffull)], 1);
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-          int d = 0, c = 0;
-          while (d < 255 && c + hist[d] <= kk) { c += hist[d]; d++; }
-          hist[0] = d; hist[1] = c;                        // digit, elements below it
+        // digit of the k-th key = the bin whose [exclusive, inclusive) prefix-count range contains kk (256 bins: 8 warps scan them)
+        {
+          const int v = threadIdx.x < 256 ? hist[threadIdx.x] : 0;
+          int incl = v;
+          for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += t; }
+          if (threadIdx.x < 256 && (threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = incl;
+          __syncthreads();
+          int before = 0;
+          for (int w = 0; w < (int)(threadIdx.x >> 5) && w < 8; w++) before += wtot[w];
+          incl += before;
+          if (threadIdx.x < 256 && incl - v <= kk && kk < incl) { sel[0] = (int)threadIdx.x; sel[1] = incl - v; }
+          __syncthreads();
         }
-        __syncthreads();
-        prefix |= (unsigned long long)hist[0] << shift;
-        kk -= hist[1];
+        prefix |= (unsigned long long)sel[0] << shift;
+        kk -= sel[1];
         __syncthreads();
       }
       if (threadIdx.x == 0) med_key = prefix;

@@ -135,12 +135,12 @@ def test_eval_points_matches_oracle():
         assert torch.equal(got[:, 3].cpu() == 100, want[:, 3] == 100)
 
 
-def test_seed_kernels_match_reference_losses():
+@pytest.mark.parametrize("n", [777, 200, 5000])      # radix-select median (> 512 residuals), direct rank counting, radix again
+def test_seed_kernels_match_reference_losses(n):
     import ctypes as C
     from nice_slam_b200 import _lib
     L = _lib.lib()
     g = torch.Generator().manual_seed(9)
-    n = 777
     depth = torch.rand(n, generator=g, dtype=torch.float64) * 3
     var = torch.rand(n, generator=g, dtype=torch.float64) * 0.1
     rgb = torch.rand(n, 3, generator=g)
@@ -160,6 +160,16 @@ def test_seed_kernels_match_reference_losses():
                                     C.c_void_p(lo.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(), st), "tracking_seeds")
     assert abs(float(lo) - float(loss)) < 1e-9 * abs(float(loss))
     assert rel(gD, d1.grad) < 1e-12 and rel(gC, c1.grad) < 1e-6
+    # median over an external pool (the all-gathered residuals of a sharded batch): mask = r < 10 * median(pool)
+    pool = torch.rand(1601, generator=g, dtype=torch.float64) * 2.0
+    res = torch.abs(gt.double() - depth) / torch.sqrt(var + 1e-10)
+    m = (res < 10 * pool.median()) & (gt > 0)
+    want = res[m].sum() + 0.5 * torch.abs(gt_rgb - rgb.double())[m].sum()
+    pool_d = dev(pool)
+    _lib.check(L.nsb_tracking_seeds(*[C.c_void_p(x.data_ptr()) for x in t], n, 0.5, 1, 1, C.c_void_p(pool_d.data_ptr()), pool.numel(),
+                                    C.c_void_p(gD.data_ptr()), C.c_void_p(gC.data_ptr()), C.c_void_p(lo.data_ptr()), C.c_void_p(ws.data_ptr()),
+                                    ws.numel(), st), "tracking_seeds(pool)")
+    assert float(want) > 0 and abs(float(lo) - float(want)) < 1e-9 * abs(float(want))
     # mapping
     d2 = depth.clone().requires_grad_(True); c2 = rgb.clone().requires_grad_(True)
     loss2 = tp.mapping_loss(d2, c2, gt, gt_rgb.float(), "color", 0.2)
