@@ -29,6 +29,7 @@ extern "C" {
 #define NSB_C_DIM 32              /* feature channels per grid     (configs/nice_slam.yaml:113) */
 #define NSB_HIDDEN 32             /* decoder width                 (src/conv_onet/models/decoder.py:293) */
 #define NSB_EMBED 93              /* Gaussian-Fourier mapping size (src/conv_onet/models/decoder.py:133) */
+#define NSB_INLINE_MAX_RAYS 1024  /* up to this batch size nsb_render_inputs.depth_max may be NULL: the kernels reduce gt_depth themselves */
 #define NSB_MAX_SAMPLES 256       /* N_samples + N_surface per ray supported by the kernels */
 
 typedef enum { NSB_OK = 0, NSB_ERR_ARG = -1, NSB_ERR_CUDA = -2, NSB_ERR_UNSUPPORTED = -3 } nsb_status;
@@ -103,7 +104,8 @@ typedef struct {
   const float* rays_o;           /* [N,3] */
   const float* rays_d;           /* [N,3] (not normalised) */
   const float* gt_depth;         /* [N] or NULL */
-  const float* depth_max;        /* device float[2] from nsb_batch_max_depth, NULL iff gt_depth NULL */
+  const float* depth_max;        /* device float[2] from nsb_batch_max_depth; NULL if gt_depth is NULL, and optionally NULL for batches
+                                    of <= NSB_INLINE_MAX_RAYS rays (then every CTA reduces gt_depth itself: one launch less) */
   const float* t_uniform;        /* device f32[n_samples]  = torch.linspace(0,1,n_samples) */
   const double* t_surface;       /* device f64[n_surface]  = torch.linspace(0,1,n_surface).double() */
   nsb_grid grid[4];              /* indexed by nsb_level; only the stage's grids are read */
@@ -150,6 +152,11 @@ typedef struct {
                                     slot -1 are not parameters and receive nothing.  NULL = d_grid[l] is dense. */
   void* split_workspace;         /* as in nsb_forward_outputs (the same buffer may be passed to both) */
   size_t split_workspace_bytes;
+  const float* pose_dirs;        /* optional [N,3] camera-frame ray directions: when given, d_c2w[12] (float64, row-major [3][4], as
+                                    nsb_pose_grad) is produced by the backward itself -- by the last CTA to finish, through the
+                                    zero-initialised, self-resetting device counter pose_counter -- instead of a separate launch */
+  double* d_c2w;
+  int* pose_counter;
 } nsb_backward_args;
 
 size_t nsb_backward_workspace_bytes(void);
@@ -258,7 +265,8 @@ typedef struct {
 /* The workspace must be ZEROED ONCE after allocation (it contains the split_workspace counters, see nsb_forward_outputs). */
 size_t nsb_iteration_workspace_bytes(int n_rays);
 
-/* `in->depth_max` is ignored (computed into buf->depth_max).  `grads` supplies only the OUTPUT pointers of
+/* `in->depth_max` is ignored (batches of more than NSB_INLINE_MAX_RAYS rays: computed into buf->depth_max; smaller ones: reduced
+ * inside the render kernel).  `grads` supplies only the OUTPUT pointers of
  * nsb_backward_args (d_rays_o, d_rays_d, d_grid, d_flat); its z_vals, raw, seed and workspace fields are ignored. */
 int nsb_tracking_iteration(const nsb_render_inputs* in, const nsb_iteration_buffers* buf, const double* gt_rgb,
                            double w_color, int handle_dynamic, int use_color, const nsb_backward_args* grads, void* stream);

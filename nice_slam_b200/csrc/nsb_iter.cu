@@ -27,7 +27,8 @@ static int check_buffers(const nsb_render_inputs* in, const nsb_iteration_buffer
 static int forward_part(const nsb_render_inputs* in, const nsb_iteration_buffers* b, nsb_render_inputs* in2, void* stream) {
   *in2 = *in;
   int rc;
-  if (in->gt_depth) {
+  in2->depth_max = nullptr;
+  if (in->gt_depth && in->n_rays > NSB_INLINE_MAX_RAYS) {          // small batches: the render kernel reduces gt_depth itself
     if ((rc = nsb_batch_max_depth(in->gt_depth, in->n_rays, b->depth_max, stream))) return rc;
     in2->depth_max = b->depth_max;
   }

@@ -312,7 +312,23 @@ __device__ __forceinline__ BlockRange block_range(const KParams& P, int bid) {
 // stratified + near-surface sampling and the stable merge (Renderer.py:82-170); leaves sorted z in sm.zs and zeroes sm.raw
 __device__ __forceinline__ void fwd_sample_sort(const KParams& P, const Smem& sm, const BlockRange& b) {
   if (P.points == nullptr) {
-    const float gtmax = P.has_gt ? P.in.depth_max[0] : 0.0f, gtmax12 = P.has_gt ? P.in.depth_max[1] : 0.0f;
+    float gtmax = 0.0f, gtmax12 = 0.0f;
+    if (P.has_gt) {
+      if (P.in.depth_max != nullptr) { gtmax = P.in.depth_max[0]; gtmax12 = P.in.depth_max[1]; }
+      else {
+        // small batches: every CTA reduces the batch's sensor depths itself (n_rays <= kInlineMaxRays floats from L2) instead of waiting
+        // for a separate single-CTA kernel: torch.max(gt_depth) and torch.max(gt_depth*1.2) = fl(1.2f * max)  (Renderer.py:109,144)
+        __shared__ float s_max[32];
+        float m = -INFINITY;
+        for (int i = threadIdx.x; i < P.in.n_rays; i += blockDim.x) m = fmaxf(m, __ldg(P.in.gt_depth + i));
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+        __syncthreads();
+        m = -INFINITY;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) m = fmaxf(m, s_max[w]);
+        gtmax = m; gtmax12 = __fmul_rn(m, 1.2f);
+      }
+    }
     block_setup_rays(P, sm, b.r0, b.nr, gtmax12);
     __syncthreads();
     double* zu = reinterpret_cast<double*>(sm.raw);              // unsorted samples (raw is not live yet)
@@ -640,6 +656,50 @@ __device__ __forceinline__ void bwd_ray_reduce(const KParams& P, const Smem& sm,
   }
 }
 
+// Fused pose gradient (optional): every CTA that has written ray gradients arrives on a grid-wide counter; the last one reduces
+// d c2w = [sum_r d_rays_d[r] (x) dirs[r] | sum_r d_rays_o[r]] over the whole batch (fixed thread mapping -> deterministic) and resets
+// the counter.  Saves the separate single-CTA pose_grad launch of a tracking iteration.
+__device__ __forceinline__ void fused_pose_grad(const KParams& P, int n_writers, double* __restrict__ s_pose /* [16][12] scratch in dynamic shared memory */) {
+  if (P.bw.pose_dirs == nullptr) return;
+  __shared__ int s_pose_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int old = atomicAdd(P.bw.pose_counter, 1);
+    s_pose_last = old == n_writers - 1;
+    if (s_pose_last) *P.bw.pose_counter = 0;
+  }
+  __syncthreads();
+  if (!s_pose_last) return;
+  __threadfence();
+  double acc[12];
+#pragma unroll
+  for (int k = 0; k < 12; k++) acc[k] = 0.0;
+  for (int r = threadIdx.x; r < P.in.n_rays; r += blockDim.x) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const double g = (double)__ldcg(P.bw.d_rays_d + 3 * r + i);
+#pragma unroll
+      for (int j = 0; j < 3; j++) acc[4 * i + j] += g * (double)__ldg(P.bw.pose_dirs + 3 * r + j);
+      acc[4 * i + 3] += (double)__ldcg(P.bw.d_rays_o + 3 * r + i);
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 12; k++) {
+    double v = acc[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && warp < 16) s_pose[warp * 12 + k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 12) {
+    double v = 0.0;
+    const int nw = (int)(blockDim.x >> 5) < 16 ? (int)(blockDim.x >> 5) : 16;
+    for (int w = 0; w < nw; w++) v += s_pose[w * 12 + threadIdx.x];
+    P.bw.d_c2w[threadIdx.x] = v;
+  }
+}
+
 __global__ void __launch_bounds__(256, 1) render_bwd_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5;
@@ -782,9 +842,12 @@ __global__ void __launch_bounds__(tc::kThreads, 1) render_bwd_tc_kernel(const __
       if (P.bw.d_rays_o != nullptr) P.bw.d_rays_o[3 * (r0 + r) + a] = (float)so;
       if (P.bw.d_rays_d != nullptr) P.bw.d_rays_d[3 * (r0 + r) + a] = (float)sd;
     }
+    fused_pose_grad(P, gridDim.x / nsplit, reinterpret_cast<double*>(smem_raw));     // one arrival per ray group (the tiles are dead)
     return;
   }
   bwd_ray_reduce(P, sm, r0, nr);
+  __syncthreads();
+  fused_pose_grad(P, gridDim.x, reinterpret_cast<double*>(smem_raw));
   NSB_PH(30);
 }
 
@@ -807,7 +870,8 @@ static int validate_inputs(const nsb_render_inputs* in, bool need_rays) {
     if (in->n_rays < 0) { set_error("n_rays < 0"); return NSB_ERR_ARG; }
     if (in->n_rays > 0 && (!in->rays_o || !in->rays_d)) { set_error("rays_o / rays_d are NULL"); return NSB_ERR_ARG; }
     if (in->n_samples < 1 || !in->t_uniform) { set_error("n_samples < 1 or t_uniform NULL"); return NSB_ERR_ARG; }
-    if (in->gt_depth && !in->depth_max) { set_error("gt_depth given without depth_max (call nsb_batch_max_depth)"); return NSB_ERR_ARG; }
+    if (in->gt_depth && !in->depth_max && in->n_rays > NSB_INLINE_MAX_RAYS) {
+      set_error("gt_depth given without depth_max: batches of more than %d rays need nsb_batch_max_depth", NSB_INLINE_MAX_RAYS); return NSB_ERR_ARG; }
   }
   int dec[3]; const int nd = stage_decoders(in->stage, dec);
   for (int i = 0; i < nd; i++) {
@@ -983,6 +1047,10 @@ extern "C" int nsb_render_backward(const nsb_render_inputs* in, const nsb_backwa
   if (K.S > NSB_MAX_SAMPLES) { set_error("n_samples+n_surface = %d exceeds %d", K.S, NSB_MAX_SAMPLES); return NSB_ERR_UNSUPPORTED; }
   cudaStream_t st = (cudaStream_t)stream;
   bool any_w = false;
+  const bool want_pose = bw->pose_dirs != nullptr;
+  if (want_pose && (!bw->d_c2w || !bw->pose_counter || !bw->d_rays_o || !bw->d_rays_d)) {
+    set_error("pose_dirs given without d_c2w / pose_counter / d_rays_o / d_rays_d"); return NSB_ERR_ARG; }
+  K.bw.pose_dirs = nullptr;                                        // fused only into the LAST launch that writes ray gradients (below)
   for (int l = 0; l < 4; l++) {
     if (bw->slot_map[l] != nullptr && bw->d_grid[l] != nullptr && (reinterpret_cast<uintptr_t>(bw->d_grid[l]) & 15) != 0) {
       set_error("compact d_grid[%d] must be 16-byte aligned", l); return NSB_ERR_ARG;
@@ -1021,6 +1089,7 @@ extern "C" int nsb_render_backward(const nsb_render_inputs* in, const nsb_backwa
       const int grid_tc = ((in->n_rays + T.rays_per_block - 1) / T.rays_per_block) * T.split;
       const size_t smem_tc = tc_total_smem(T.max_pts, T.max_rays, true);
       if (smem_tc > kSmemCap) { set_error("shared-memory budget exceeded (%zu bytes)", smem_tc); return NSB_ERR_UNSUPPORTED; }
+      if (n_w == 0 && want_pose) T.bw.pose_dirs = bw->pose_dirs;   // the tensor-core launch is the last writer of the ray gradients
       render_bwd_tc_kernel<<<grid_tc, tc::kThreads, smem_tc, st>>>(T);
       if ((rc = check_cuda(cudaGetLastError(), "render_bwd_tc_kernel launch"))) return rc;
       if (n_w == 0) return NSB_OK;
@@ -1037,7 +1106,8 @@ extern "C" int nsb_render_backward(const nsb_render_inputs* in, const nsb_backwa
   const int grid = (in->n_rays + K.rays_per_block - 1) / K.rays_per_block;
   render_bwd_kernel<<<grid, warps * 32, smem, st>>>(K);
   if ((rc = check_cuda(cudaGetLastError(), "render_bwd_kernel launch"))) return rc;
-  if (any_w) return launch_unpack_grads(K.d_packed, bw->d_flat, st);
+  if (any_w && (rc = launch_unpack_grads(K.d_packed, bw->d_flat, st))) return rc;
+  if (want_pose) return nsb_pose_grad(bw->pose_dirs, bw->d_rays_o, bw->d_rays_d, in->n_rays, bw->d_c2w, stream);   // FP32 path: separate launch
   return NSB_OK;
 }
 

@@ -111,6 +111,9 @@ class _Call:
                  "aux")
 
 
+INLINE_MAX_RAYS = 1024          # NSB_INLINE_MAX_RAYS of include/nice_slam_b200.h
+
+
 def _inputs(call, rays_o, rays_d, depth_max, t_u, t_s, grids):
     inp = _lib.RenderInputs()
     inp.stage = STAGES[call.stage]
@@ -122,7 +125,7 @@ def _inputs(call, rays_o, rays_d, depth_max, t_u, t_s, grids):
     inp.rays_o, inp.rays_d = rays_o.data_ptr(), rays_d.data_ptr()
     if call.gt_depth is not None:
         inp.gt_depth = call.gt_depth.data_ptr()
-        inp.depth_max = depth_max.data_ptr()
+        inp.depth_max = depth_max.data_ptr() if depth_max is not None else None      # None: reduced inside the kernel (small batches)
     inp.t_uniform = t_u.data_ptr()
     inp.t_surface = t_s.data_ptr() if t_s is not None else None
     for lvl, g in zip(call.levels, grids):
@@ -159,7 +162,7 @@ class _RenderFn(torch.autograd.Function):
         has_gt = call.gt_depth is not None and call.stage != "coarse"
         S = call.n_samples + (call.n_surface if has_gt else 0)
         depth_max = None
-        if call.gt_depth is not None:
+        if call.gt_depth is not None and n > INLINE_MAX_RAYS:             # smaller batches: the render kernel reduces gt_depth itself
             depth_max = torch.empty(2, dtype=torch.float32, device=dev)
             _lib.check(L.nsb_batch_max_depth(_ptr(call.gt_depth), n, _ptr(depth_max), _stream()), "nsb_batch_max_depth")
         t_u, t_s = _linspaces(call.n_samples, call.n_surface, dev)

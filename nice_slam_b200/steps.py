@@ -16,7 +16,8 @@ from . import _lib
 from ._lib import LEVELS, STAGE_DECODERS
 from .renderer import _VP, _inputs, _linspaces, _stream, _Call, _require_cuda
 
-KERNEL_LAUNCHES_PER_ITERATION = 4       # batch_max, render_fwd, seeds, render_bwd (+1 unpack when decoder grads are requested)
+KERNEL_LAUNCHES_PER_ITERATION = 3       # render_fwd, seeds, render_bwd for batches <= 1024 rays (the forward reduces the batch depth maxima
+                                        # itself, the backward produces d c2w itself); + batch_max above that, + unpack for decoder grads
 
 
 def packed_layout(n_frames, grad_decoders, masked_counts):
@@ -65,6 +66,7 @@ class IterationContext:
         self.ws = torch.zeros(L.nsb_iteration_workspace_bytes(n), dtype=torch.uint8, device=dev)     # zeroed once: holds the split counters
         self.split_ws = torch.zeros(max(L.nsb_split_workspace_bytes(n, S), 16), dtype=torch.uint8, device=dev)   # decoder-parallel CTAs (small batches)
         self.split_bytes = L.nsb_split_workspace_bytes(n, S)
+        self.pose_counter = torch.zeros(1, dtype=torch.int32, device=dev)      # arrival counter of the fused pose gradient (self-resetting)
         self.d_out = self.d_res[: n * 24].view(f32)                      # [d_rays_o | d_rays_d]
         self.d_rays_o = self.d_out[: 3 * n].view(n, 3)
         self.d_rays_d = self.d_out[3 * n:].view(n, 3)
@@ -145,9 +147,10 @@ class IterationContext:
                        "nsb_pose_grad_frames")
         return self.packed
 
-    def run(self, c, decoders, rays_o, rays_d, gt_depth, gt_color, w_color=None, handle_dynamic=True, use_color=True):
+    def run(self, c, decoders, rays_o, rays_d, gt_depth, gt_color, w_color=None, handle_dynamic=True, use_color=True, dirs=None):
         """Enqueue one iteration on the current stream (inputs already on the device).  Results stay on the device:
-        self.loss, self.depth/var/rgb, self.d_rays_o/d, self.d_grid[key], self.d_flat[level]."""
+        self.loss, self.depth/var/rgb, self.d_rays_o/d, self.d_grid[key], self.d_flat[level]; with `dirs` (camera-frame ray directions
+        [N,3]) also self.d_c2w, produced by the backward kernel itself."""
         L = _lib.lib()
         for t, nm in ((rays_o, "rays_o"), (rays_d, "rays_d"), (gt_depth, "gt_depth")):
             _require_cuda(t, nm)
@@ -155,6 +158,9 @@ class IterationContext:
         t_u, t_s = _linspaces(self.r.N_samples, self.r.N_surface, self.dev)
         inp = _inputs(call, rays_o, rays_d, self.depth_max, t_u, t_s, [g.detach() for g in grids])
         bw = self._grads(c)
+        if dirs is not None:
+            _require_cuda(dirs, "dirs")
+            bw.pose_dirs, bw.d_c2w, bw.pose_counter = dirs.data_ptr(), self.d_c2w.data_ptr(), self.pose_counter.data_ptr()
         if self.kind == "track":
             w = 0.5 if w_color is None else w_color
             _lib.check(L.nsb_tracking_iteration(C.byref(inp), C.byref(self.buf), _VP(gt_color.data_ptr()), w, int(handle_dynamic),
@@ -203,9 +209,7 @@ class IterationContext:
         def body():
             if host_io:
                 self.d_in.copy_(self.h_in, non_blocking=True)             # one H2D copy: rays, sensor depth and colour
-            self.run(c, decoders, ro, rd, gd, gc, **kw)
-            if dirs is not None:
-                self.pose_grad(dirs)
+            self.run(c, decoders, ro, rd, gd, gc, dirs=dirs, **kw)     # d c2w comes out of the backward kernel
             if host_io:
                 self.h_res.copy_(self.d_res, non_blocking=True)           # one D2H copy: ray gradients, loss, pose gradient
         cur = torch.cuda.current_stream()
