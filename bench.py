@@ -212,7 +212,23 @@ def extra_workloads(sc, renderer, c, dec, dev, flush, peak):
                       "hbm_frac": nn * BYTES_PER_RAY / (ms * 1e-3) / 1e9 / peak})
         del cx
     out["sweep_tracking_iteration"] = sweep
+    # bulk no-grad paths of the same forward kernel: Mesher-style eval_points and a full-image render
+    pts = (torch.rand(1 << 22, 3, device=dev, dtype=torch.float64) - 0.5) * 4.0 + torch.tensor(su_center(sc), device=dev, dtype=torch.float64)
+    ms = time_steps(lambda: renderer.eval_points(pts, dec, c, "fine", dev), 5, warmup=1)
+    out["eval_points_fine"] = {"points": pts.shape[0], "ms_per_call": ms, "mpoints_per_s": pts.shape[0] / (ms * 1e-3) / 1e6}
+    import scene_util as su
+    depth, _ = su.make_frame(sc, 3)
+    c2w = su.make_pose(sc, 3).to(dev)
+    gtd = depth.to(dev)
+    ms = time_steps(lambda: renderer.render_img(c, dec, c2w, dev, "color", gt_depth=gtd), 3, warmup=1)
+    out["render_img_color"] = {"rays": int(gtd.numel()), "samples": 48, "ms_per_image": ms, "rays_per_s": gtd.numel() / (ms * 1e-3)}
     return out
+
+
+def su_center(sc):
+    import scene_util as su
+    b = su.scene_bound(sc)
+    return [float((b[i][0] + b[i][1]) / 2) for i in range(3)]
 
 
 def scene_workloads(dev, flush):
