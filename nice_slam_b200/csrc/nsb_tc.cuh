@@ -2,17 +2,19 @@
 // accumulators in TMEM.  Included by nsb_render.cu (it uses that file's KParams / Smem / gather helpers).
 //
 // Why 3xTF32: plain TF32 operands miss the 1e-4 parity bar by an order of magnitude (probe: 3e-4 relative on a single
-// 32-wide GEMM); splitting every operand into hi = tf32(x), lo = tf32(x - hi) and issuing lo*hi + hi*lo + hi*hi gives
-// fp32-level results (probe_tcgen05.cu: 6e-6 abs on |ref| <= 20, same as an FP32 FMA chain).
+// 32-wide GEMM); splitting every operand into hi = the 19 bits the tensor core reads, lo = x - hi (exact) and issuing
+// lo*hi + hi*lo + hi*hi gives fp32-level results (probe_tcgen05.cu: 6e-6 abs on |ref| <= 20, same as an FP32 FMA chain).
 //
-// Tile = 128 sample points (one TMEM lane / one thread per point).  Operands live in shared memory in the canonical
-// K-major no-swizzle UMMA layout  [row/8][k/4][row%8][k%4]  (core matrix = 8 rows x 16 B): the epilogue thread of row r
-// writes 16-byte chunks that land conflict-free, and the same tile can later be read as an MN-major operand.
-// Per decoder and tile:
-//   gather -> C tile (hi/lo) -> D2[128 x 160] = C * Wc_i^T for the five layers (TMEM columns 32..191); C is dead after that,
-//   its shared memory is reused for the embedding blocks E (32 features at a time, recomputed) and the hidden state H;
-//   layer i: D1[128 x 32] = x_i * W_i^T ; epilogue (one thread per point): h = relu(D1 + b) + D2_i + bc -> H tile (hi/lo).
-// Weights are converted fp32 -> (hi, lo) canonical tiles on the fly from the packed image (L2 resident), one layer at a time.
+// Tile = 128 sample points = 128 TMEM lanes, four threads per point (512-thread CTA).  Activations live in shared memory in the
+// canonical K-major no-swizzle UMMA layout  [row/8][k/4][row%8][k%4]  (core matrix = 8 rows x 16 B): the threads of row r write
+// 16-byte chunks that land conflict-free.  Weights are never touched by threads: nsb_pack_decoders stores every MMA B operand
+// pre-split in that same layout (operand images, nsb_common.cuh) and one elected thread streams the chunks into fixed shared-memory
+// regions with TMA bulk copies, one mbarrier per region, at least one consumer step ahead.
+// Forward per decoder and tile:   gather -> C tile -> D2[128 x 160] = C * [Wc_0..Wc_4]^T (one N = 160 MMA group, not waited for)
+//   -> three embedding blocks E_b, each computed while the previous block's MMAs run: [D1 | D3] += E_b * [W0_b; W3E_b]^T (N = 64)
+//   -> layers 1..4: epilogue h = relu(D + b) + D2_i + bc -> H tile -> D = H * W_i^T (N = 32) -> output layer in registers.
+// Backward (input gradients; the forward saved the ReLU sign bits, nothing is recomputed): per layer one MMA batch
+//   {DC += G * Wc_i, g_i = DU * W_i, DF += DU * W_i^E} from the transposed operand image, two 48 KB stages, layer i-2 in flight.
 #pragma once
 
 namespace nsb {
