@@ -195,6 +195,17 @@ int nsb_masked_scatter(const nsb_grid* grid, const int32_t* slot_map, const floa
 /* to_reference != 0: [n][32] -> [32][n] (the reference's val[mask] order); 0: the inverse. */
 int nsb_compact_transpose(const float* src, float* dst, long long n_selected, int to_reference, void* stream);
 
+/* Fused Adam steps (torch.optim.Adam with its defaults -- no weight decay, no amsgrad -- as the mapper uses it, src/Mapper.py:365-379,
+ * per-group learning rates set per stage :412-419, step :504), float32 arithmetic in torch's operation order.  `step` = 1-based count of
+ * updates of these parameters; exp_avg / exp_avg_sq: caller-owned state, zeroed at creation.
+ * nsb_adam_masked_voxels: the parameters are the frustum-selected voxels of `grid`, updated IN PLACE on the shared grid storage from
+ * the compact gradient [n_selected][32] -- replaces val_grad = val[mask] ... step ... val[mask] = val_grad (:324, :399, :517).
+ * nsb_adam_decoder: the parameter tensors of one decoder, from its flat gradient (canonical order, nsb_flat_offset). */
+int nsb_adam_masked_voxels(const nsb_grid* grid, const int32_t* slot_map, const float* grad, float* exp_avg, float* exp_avg_sq,
+                           double lr, double beta1, double beta2, double eps, int step, void* stream);
+int nsb_adam_decoder(int level, const nsb_decoder_params* params, const float* grad_flat, float* exp_avg, float* exp_avg_sq,
+                     double lr, double beta1, double beta2, double eps, int step, void* stream);
+
 /* Frustum feature selection (Mapper.get_mask_from_c2w, src/Mapper.py:93-164) of one grid, on the device: every voxel centre is
  * projected into the current frame (float32 camera transform, float64 intrinsics, like the reference's numpy code), the sensor
  * depth is looked up with OpenCV's INTER_LINEAR remap arithmetic (1/32-pixel fixed point, BORDER_CONSTANT 0), zero look-ups are

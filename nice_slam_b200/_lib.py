@@ -90,6 +90,8 @@ SYMBOLS = {
     "nsb_compact_transpose": (C.c_int, [_P, _P, C.c_longlong, C.c_int, _P]),
     "nsb_pose_grad_frames": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P]),
     "nsb_split_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "nsb_adam_masked_voxels": (C.c_int, [C.POINTER(Grid), _P, _P, _P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, _P]),
+    "nsb_adam_decoder": (C.c_int, [C.c_int, C.POINTER(DecoderParams), _P, _P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, _P]),
     "nsb_frustum_mask_workspace": (C.c_size_t, [C.c_longlong]),
     "nsb_frustum_mask": (C.c_int, [C.POINTER(C.c_float), _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int,
                                    C.c_double, C.c_double, C.c_double, C.c_double, _P, _P, C.c_size_t, _P]),

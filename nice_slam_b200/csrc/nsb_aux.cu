@@ -563,6 +563,41 @@ __global__ void frustum_mask_kernel(const FrustumArgs A, const float* __restrict
   }
 }
 
+// ---- fused Adam on the packed gradient block (torch.optim.Adam defaults; Mapper.py:365-379, :412-419, :504) ------------------------
+struct AdamScalars { float w1, beta2, w2, inv_bc2_sqrt_div, eps, neg_step; };     // float32 casts of torch's python scalars
+__device__ __forceinline__ float adam_update(float p, float g, float& m, float& v, const AdamScalars& a) {
+  m = __fadd_rn(m, __fmul_rn(a.w1, __fsub_rn(g, m)));                                  // exp_avg.lerp_(grad, 1 - beta1)
+  v = __fadd_rn(__fmul_rn(v, a.beta2), __fmul_rn(__fmul_rn(a.w2, g), g));              // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1-beta2)
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), a.inv_bc2_sqrt_div), a.eps);   // (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
+  return __fadd_rn(p, __fmul_rn(a.neg_step, __fdiv_rn(m, denom)));                     // param.addcdiv_(exp_avg, denom, value=-step_size)
+}
+// one warp per voxel, lane = channel: the parameters ARE the selected voxels of the shared grid (updated in place)
+__global__ void adam_masked_kernel(nsb_grid g, const int32_t* __restrict__ slots, const float* __restrict__ grad, float* __restrict__ em,
+                                   float* __restrict__ ev, const AdamScalars a) {
+  const long long n = (long long)g.D * g.H * g.W;
+  const int lane = threadIdx.x & 31;
+  for (long long vx = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); vx < n; vx += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const int s = __ldg(slots + vx);
+    if (s < 0) continue;
+    const int w = (int)(vx % g.W), h = (int)((vx / g.W) % g.H), d = (int)(vx / ((long long)g.W * g.H));
+    float* cell = const_cast<float*>(g.data) + d * g.stride_d + h * g.stride_h + w * g.stride_w + lane * g.stride_c;
+    const long long i = (long long)s * 32 + lane;
+    float m = em[i], v = ev[i];
+    *cell = adam_update(*cell, grad[i], m, v, a);
+    em[i] = m; ev[i] = v;
+  }
+}
+struct AdamTable { float* param[24]; int off[24]; int n[24]; int count; };
+__global__ void adam_flat_kernel(const AdamTable T, const float* __restrict__ grad, float* __restrict__ em, float* __restrict__ ev, const AdamScalars a) {
+  for (int t = 0; t < T.count; t++)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T.n[t]; i += gridDim.x * blockDim.x) {
+      const int f = T.off[t] + i;
+      float m = em[f], v = ev[f];
+      T.param[t][i] = adam_update(T.param[t][i], grad[f], m, v, a);
+      em[f] = m; ev[f] = v;
+    }
+}
+
 // d c2w of every keyframe block (one CTA per frame)
 __global__ void pose_grad_frames_kernel(const float* __restrict__ dirs, const float* __restrict__ dro, const float* __restrict__ drd,
                                         const int32_t* __restrict__ offs, float* __restrict__ out) {
@@ -648,6 +683,43 @@ extern "C" int nsb_compact_transpose(const float* src, float* dst, long long n_s
   compact_transpose_kernel<<<(unsigned)((n_selected + 31) / 32), 256, 0, (cudaStream_t)stream>>>(src, dst, n_selected, to_reference);
   return check_cuda(cudaGetLastError(), "compact_transpose launch");
 }
+static int adam_scalars(double lr, double beta1, double beta2, double eps, int step, AdamScalars* a) {
+  if (step < 1 || !(beta1 >= 0.0 && beta1 < 1.0) || !(beta2 >= 0.0 && beta2 < 1.0) || !(eps >= 0.0)) { set_error("adam: bad hyper-parameters"); return NSB_ERR_ARG; }
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);      // python-float arithmetic of torch's _single_tensor_adam
+  a->w1 = (float)(1.0 - beta1); a->beta2 = (float)beta2; a->w2 = (float)(1.0 - beta2);
+  a->inv_bc2_sqrt_div = (float)sqrt(bc2); a->eps = (float)eps; a->neg_step = (float)(-(lr / bc1));
+  return NSB_OK;
+}
+extern "C" int nsb_adam_masked_voxels(const nsb_grid* grid, const int32_t* slot_map, const float* grad, float* exp_avg, float* exp_avg_sq,
+                                      double lr, double beta1, double beta2, double eps, int step, void* stream) {
+  if (!grid || !grid->data || !slot_map || !grad || !exp_avg || !exp_avg_sq || grid->D < 1 || grid->H < 1 || grid->W < 1) {
+    set_error("adam_masked_voxels: bad arguments"); return NSB_ERR_ARG; }
+  AdamScalars a; int rc = adam_scalars(lr, beta1, beta2, eps, step, &a); if (rc) return rc;
+  const long long n = (long long)grid->D * grid->H * grid->W;
+  const int blocks = (int)((n + 7) / 8 < 148 * 16 ? (n + 7) / 8 : 148 * 16);
+  adam_masked_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*grid, slot_map, grad, exp_avg, exp_avg_sq, a);
+  return check_cuda(cudaGetLastError(), "adam_masked_voxels launch");
+}
+extern "C" int nsb_adam_decoder(int level, const nsb_decoder_params* p, const float* grad_flat, float* exp_avg, float* exp_avg_sq,
+                                double lr, double beta1, double beta2, double eps, int step, void* stream) {
+  if (level < 0 || level > 3 || !p || !grad_flat || !exp_avg || !exp_avg_sq) { set_error("adam_decoder: bad arguments"); return NSB_ERR_ARG; }
+  AdamScalars a; int rc = adam_scalars(lr, beta1, beta2, eps, step, &a); if (rc) return rc;
+  AdamTable T; memset(&T, 0, sizeof(T));
+  auto add = [&](const float* ptr, int kind, int layer, int n) { T.param[T.count] = const_cast<float*>(ptr); T.off[T.count] = (int)flat_offset(level, kind, layer); T.n[T.count] = n; T.count++; };
+  const bool xyz = level != 0;
+  const int cd = level == 2 ? 64 : 32, no = level == 3 ? 4 : 1;
+  bool ok = p->Wo && p->bo;
+  for (int i = 0; i < 5; i++) ok = ok && p->W[i] && p->b[i] && (!xyz || (p->Wc[i] && p->bc[i]));
+  if (xyz) ok = ok && p->B;
+  if (!ok) { set_error("adam_decoder: NULL parameter pointers"); return NSB_ERR_ARG; }
+  if (xyz) add(p->B, 0, 0, 3 * kEmb);
+  for (int i = 0; i < 5; i++) { add(p->W[i], 1, i, kHid * dec_in(level, i)); add(p->b[i], 2, i, kHid); }
+  if (xyz) for (int i = 0; i < 5; i++) { add(p->Wc[i], 3, i, kHid * cd); add(p->bc[i], 4, i, kHid); }
+  add(p->Wo, 5, 0, no * kHid); add(p->bo, 6, 0, no);
+  adam_flat_kernel<<<32, 256, 0, (cudaStream_t)stream>>>(T, grad_flat, exp_avg, exp_avg_sq, a);
+  return check_cuda(cudaGetLastError(), "adam_decoder launch");
+}
+
 extern "C" size_t nsb_frustum_mask_workspace(long long n_voxels) { return n_voxels <= 0 ? 16 : (size_t)n_voxels * sizeof(float) + 16; }
 extern "C" int nsb_frustum_mask(const float* c2w, const float* xs, const float* ys, const float* zs, int D, int H, int W,
                                 const float* depth, int img_h, int img_w, double fx, double fy, double cx, double cy,

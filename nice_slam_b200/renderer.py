@@ -283,6 +283,12 @@ class FusedRenderer(object):
         self._cache = _PackCache()
 
     # ------------------------------------------------------------------ helpers
+    def invalidate_decoders(self, levels=None):
+        """Force a re-pack of the decoders' packed / operand images on the next call (needed only after parameter updates that bypass
+        torch's version counters, e.g. optim.FusedMapperAdam.step_decoder)."""
+        for lvl in (levels or list(self._cache.key.keys())):
+            self._cache.key.pop(lvl, None)
+
     def _bounds(self):
         b = self.bound.detach().cpu().double().reshape(6)
         return b.tolist(), (b * self.coarse_bound_enlarge).tolist()

@@ -543,3 +543,51 @@ def test_frustum_mask_matches_real_mapper_masks():
             assert float(near[diff.numpy()].max()) < 1e-4, (key, int(diff.sum()))
         assert int(diff.sum()) <= 2, (key, int(diff.sum()))
         assert MaskedVoxels(c[key], got.to(DEV)).count == int(got.sum())
+
+
+def test_fused_adam_matches_torch_adam():
+    """nsb_adam_masked_voxels / nsb_adam_decoder against torch.optim.Adam on the reference's parameterisation (val_grad = val[mask] as a
+    leaf, the colour decoder's parameters), three steps with changing gradients and learning rates (Mapper.py:365-379, :412-419, :504)."""
+    from nice_slam_b200._lib import LEVELS, flat_layout
+    from nice_slam_b200.masked import MaskedVoxels
+    from nice_slam_b200.optim import FusedMapperAdam
+    sc = su.load_scenes()["room0"]
+    grids, dec_state = su.make_grids(sc, "soft"), su.load_decoders("soft")
+    renderer, c, dec = make_renderer(sc, grids, dec_state, DEV)
+    key = "grid_middle"
+    vm = _random_masks(grids, (key,), 0.4)[key]
+    mv = MaskedVoxels(c[key], vm)
+    mask5 = vm.to(DEV).unsqueeze(0).unsqueeze(0).repeat(1, 32, 1, 1, 1)
+    # reference side: leaf parameter vectors + torch Adam
+    val_ref = c[key].clone()
+    val_grad = val_ref[mask5].clone().requires_grad_(True)
+    dec_ref = {k: v.detach().clone().requires_grad_(True) for k, v in dict(dec.color_decoder.named_parameters()).items()}
+    opt = torch.optim.Adam([{"params": [val_grad], "lr": 0.0}, {"params": list(dec_ref.values()), "lr": 0.0}])
+    fused = FusedMapperAdam()
+    lay = flat_layout(LEVELS.index("color"))
+    n_flat = sum(cnt for _, _, cnt in lay)
+    g = torch.Generator(device=DEV).manual_seed(4)
+    for step, (lr_v, lr_d) in enumerate([(0.1, 0.005), (0.005, 0.005), (0.005, 0.0)]):
+        gv = torch.randn(mv.count, 32, device=DEV, generator=g) * (10.0 ** (-step))
+        gflat = torch.randn(n_flat, device=DEV, generator=g) * 0.1
+        opt.param_groups[0]["lr"], opt.param_groups[1]["lr"] = lr_v, lr_d
+        val_grad.grad = mv.to_reference(gv)
+        for name, off, cnt in lay:
+            dec_ref[name].grad = gflat[off:off + cnt].view_as(dec_ref[name]).clone()
+        opt.step()
+        fused.step_voxels(key, c[key], mv, gv, lr_v)
+        fused.step_decoder("color", dec, gflat, lr_d, renderer=renderer)
+        want = val_ref.clone()
+        want[mask5] = val_grad.detach()
+        assert rel(c[key], want) < 1e-6, step
+        assert torch.equal(c[key][~mask5], val_ref[~mask5])                    # unselected voxels untouched
+        mine = dict(dec.color_decoder.named_parameters())
+        for name in dec_ref:
+            assert rel(mine[name], dec_ref[name]) < 1e-6, (step, name)
+    # the renderer sees the updated colour decoder (its packed image was invalidated)
+    ro, rd, gd, _ = su.make_rays(sc, 16, seed=1)
+    got = renderer.render_batch_ray(c, dec, rd.to(DEV), ro.to(DEV), DEV, "color", gt_depth=gd.to(DEV))
+    st = {lvl: dict(v) for lvl, v in dec_state.items()}
+    st["color"] = {k: v.detach().cpu() for k, v in dec_ref.items()}
+    want = tp.render_batch_ray({k: v.cpu().contiguous() for k, v in c.items()}, st, rd, ro, "color", gd, su.scene_bound(sc))
+    assert rel(got[2], want[2]) < TOL and rel(got[0], want[0]) < TOL
