@@ -259,7 +259,60 @@ def gen_mapper_cases():
             save("mapper_%s.pt" % stage, case)
 
 
+def gen_mapper_loop_case():
+    """Five REAL joint iterations of Mapper.optimize_map with the real torch.optim.Adam (3 x middle, fine, color): per-iteration ray
+    batches at the renderer boundary + the state the mapper leaves behind (selected voxels of every grid, colour decoder)."""
+    rh.import_reference()
+    sc, cfg, slam, renderer = ref_scene("room0", "soft")
+    mapper = rh.make_mapper(cfg, slam, renderer, coarse_mapper=False)
+    calls = record_renderer(renderer)
+    depth, color = su.make_frame(sc, 1)
+    c2w = su.make_pose(sc, 1)
+    import src.Mapper as mapper_mod
+    samples = []
+    _gs = mapper_mod.get_samples
+
+    def get_samples_rec(*a, **k):
+        r = _gs(*a, **k)
+        samples.append([t.detach().clone() for t in r])
+        return r
+    mapper_mod.get_samples = get_samples_rec
+    start = {k: v.detach().clone() for k, v in slam.shared_c.items()}
+    try:
+        torch.manual_seed(321)
+        mapper.optimize_map(5, 1.0, 0, color, depth, c2w, [], [], c2w)
+    finally:
+        mapper_mod.get_samples = _gs
+    its = []
+    for it, call in enumerate(calls):
+        s_o, s_d, s_gd, s_gc = samples[it]
+        keep = tp.bbox_prefilter(s_o.float(), s_d.float(), s_gd.float(), slam.bound)
+        assert torch.equal(s_o.float()[keep], call["rays_o"])
+        st = cfg["mapping"]["stage"][call["stage"]]
+        its.append(dict(stage=call["stage"], rays_o=call["rays_o"], rays_d=call["rays_d"], gt_depth=call["gt_depth"],
+                        gt_depth_loss=s_gd.float()[keep], gt_color=s_gc.float()[keep],
+                        lr=dict(decoders=st["decoders_lr"], middle=st["middle_lr"], fine=st["fine_lr"], color=st["color_lr"])))
+    final = {}
+    for key in ("grid_middle", "grid_fine", "grid_color"):
+        m = mapper.get_mask_from_c2w(c2w, key, slam.shared_c[key].shape[2:], depth.numpy())
+        vm = torch.from_numpy(np.ascontiguousarray(m)).permute(2, 1, 0).contiguous()
+        m5 = vm.unsqueeze(0).unsqueeze(0).expand_as(slam.shared_c[key])
+        after, before = slam.shared_c[key][m5].detach().clone(), start[key][m5]
+        g = torch.Generator().manual_seed(99)
+        pick = torch.randperm(after.numel(), generator=g)[:8192].clone()          # (a view would drag the whole permutation into the file)
+        final[key] = dict(idx=pick, val=after[pick].clone(), delta_norm=float((after - before).double().norm()), norm=float(after.double().norm()),
+                          unselected_changed=bool((slam.shared_c[key][~m5] != start[key][~m5]).any()))
+    dec_final = {k: v.detach().clone() for k, v in slam.shared_decoders.color_decoder.state_dict().items()}
+    save("mapper_loop.pt", dict(scene="room0", variant="soft", frame_seed=1, pose_seed=1, iterations=its, final=final,
+                                color_decoder=dec_final, w_color_loss=cfg["mapping"]["w_color_loss"]))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "mapper_loop":
+        import warnings
+        warnings.filterwarnings("ignore")
+        gen_mapper_loop_case()
+        sys.exit(0)
     os.makedirs(GOLD, exist_ok=True)
     import warnings
     warnings.filterwarnings("ignore")
@@ -268,3 +321,4 @@ if __name__ == "__main__":
     gen_render_cases()
     gen_tracker_case()
     gen_mapper_cases()
+    gen_mapper_loop_case()

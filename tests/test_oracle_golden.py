@@ -137,3 +137,44 @@ def test_frustum_oracle_matches_real_mapper_masks_and_cv2_remap():
     x = (g.random(20000) * 1300 - 50).astype(np.float32)
     y = (g.random(20000) * 800 - 60).astype(np.float32)
     assert np.array_equal(cv2.remap(depth.numpy(), x, y, interpolation=cv2.INTER_LINEAR)[:, 0], fr.remap_bilinear(depth.numpy(), x, y))
+
+
+def test_oracle_reproduces_five_real_mapper_iterations_with_adam():
+    """tests/golden/mapper_loop.pt (real Mapper.optimize_map, real torch Adam, 3 x middle + fine + color) replayed with the oracle port:
+    frustum masks from oracle/frustum.py, masked leaf parameters val[mask] as in Mapper.py:317-333, the port's render + mapping loss,
+    torch Adam with the per-stage learning rates.  Pins the whole chain the native mapping loop (nice_slam_b200/mapping.py) replaces."""
+    from oracle import frustum as fr
+    case = torch.load(os.path.join(su.GOLDEN, "mapper_loop.pt"), map_location="cpu", weights_only=False)
+    sc = su.load_scenes()[case["scene"]]
+    grids, dec = su.make_grids(sc, case["variant"]), su.load_decoders(case["variant"])
+    depth, _ = su.make_frame(sc, case["frame_seed"])
+    c2w = su.make_pose(sc, case["pose_seed"])
+    bound = su.scene_bound(sc)
+    keys = ("grid_middle", "grid_fine", "grid_color")
+    m5 = {k: fr.frustum_mask(c2w, k, tuple(grids[k].shape[2:]), depth.numpy(), bound, sc["cam"]).unsqueeze(0).unsqueeze(0).expand_as(grids[k])
+          for k in keys}
+    val_grad = {k: grids[k][m5[k]].clone().requires_grad_(True) for k in keys}
+    dw = {n: {k: v.clone().requires_grad_(n == "color") for k, v in W.items()} for n, W in dec.items()}
+    opt = torch.optim.Adam([{"params": list(dw["color"].values()), "lr": 0}] + [{"params": [val_grad[k]], "lr": 0} for k in keys])
+    lv = {"middle": ("grid_middle",), "fine": ("grid_fine", "grid_middle"), "color": keys}
+    for it in case["iterations"]:
+        opt.param_groups[0]["lr"] = it["lr"]["decoders"]
+        for gi, k in enumerate(keys):
+            opt.param_groups[1 + gi]["lr"] = it["lr"][k[5:]]
+        g = {k: v.clone() for k, v in grids.items()}
+        for k in keys:
+            g[k][m5[k]] = val_grad[k]                                   # Mapper.py:393-401
+        opt.zero_grad()
+        d, _, col = tp.render_batch_ray(g, dw, it["rays_d"], it["rays_o"], it["stage"], it["gt_depth"], bound)
+        tp.mapping_loss(d, col, it["gt_depth_loss"], it["gt_color"], it["stage"], case["w_color_loss"]).backward()
+        for k in keys:
+            if k not in lv[it["stage"]]:
+                assert val_grad[k].grad is None or not bool(val_grad[k].grad.any())
+        opt.step()
+        for k in keys:
+            grids[k][m5[k]] = val_grad[k].detach()                       # Mapper.py:511-519
+    for k, fin in case["final"].items():
+        got = val_grad[k].detach()[fin["idx"]]
+        assert torch.allclose(got, fin["val"], rtol=1e-5, atol=1e-6), (k, float((got - fin["val"]).abs().max()))
+    for k, v in case["color_decoder"].items():
+        assert torch.allclose(dw["color"][k].detach(), v, rtol=1e-5, atol=1e-6), k
