@@ -203,6 +203,19 @@ def extra_workloads(sc, renderer, c, dec, dev, flush, peak):
     out["mapping_configs1"] = {"workload": "room0 mapping iteration, 996 rays x 48, stage color, dense voxel grads (middle+fine+color) + colour-decoder grads",
                                "ms_per_step": ms, "rays_per_s": n / (ms * 1e-3), "algorithmic_bytes_per_ray": bpr,
                                "hbm_frac": n * bpr / (ms * 1e-3) / 1e9 / peak}
+    # the same iteration inside the native mapper loop: frustum-selected voxels (on-GPU mask of a synthetic frame), compact gradients,
+    # fused Adam in place on the grids + on the colour decoder (nice_slam_b200/mapping.py) -- what one joint_iter of Mapper.optimize_map costs
+    import copy
+    import scene_util as su
+    from nice_slam_b200.mapping import FusedMappingLoop
+    depth1, _ = su.make_frame(sc, 1)
+    loop = FusedMappingLoop(renderer, {k: v.clone() for k, v in c.items()}, copy.deepcopy(dec), su.make_pose(sc, 1), depth1.to(dev))
+    lr = dict(decoders=0.005, middle=0.005, fine=0.005, color=0.005)
+    ms = time_steps(lambda: loop.iteration("color", ro, rd, gd, gcf, lr), 50)
+    out["mapping_loop_step"] = {"workload": "one joint iteration of the native mapper loop, stage color, 996 rays: fused iteration (compact voxel grads of the "
+                                            "frustum selection + colour-decoder grads) + fused Adam (3 grids in place + colour decoder)",
+                                "selected_voxels": {k: m.count for k, m in loop.masked.items()}, "ms_per_step": ms, "rays_per_s": n / (ms * 1e-3)}
+    del loop
     sweep = []
     for nn, steps in ((1024, 100), (8192, 30), (65536, 8)):
         ro, rd, dirs, gd, gc = [t.to(dev) for t in make_batch(sc, nn, 200 + nn)]
