@@ -353,8 +353,8 @@ def mapping_sharded_workload(sc, renderer, c, dec, dev, flush, rank, world):
 # dram__bytes_read.sum + dram__bytes_write.sum of one render_bwd_tc_kernel launch of THIS workload (200 rays x 48, room0), taken from the
 # committed `ncu --set full` capture (never measured inside a timed run): the 48.5 MB of grids are L2-resident, so DRAM traffic is far
 # below the 29.5 MB of algorithmic gather bytes.
-NCU_DRAM_BYTES_PER_BWD_LAUNCH = 3994880
-NCU_TRAFFIC_SOURCE = "profiles/ncu_full_r01i_render_kernels.txt (ncu --set full, 3.99 MB read + 0 B written per launch)"
+NCU_DRAM_BYTES_PER_BWD_LAUNCH = 4003840
+NCU_TRAFFIC_SOURCE = "profiles/ncu_full_r01m_render_kernels.txt (ncu --set full, 4.00 MB read + 0 B written per launch)"
 
 
 def dbg(msg):
