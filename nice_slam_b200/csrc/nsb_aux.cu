@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include "nsb_common.cuh"
+#include "nsb_seeds.cuh"
 #include "nsb_geom.cuh"
 
 namespace nsb {
@@ -139,45 +140,6 @@ int launch_unpack_grads(float* const d_packed[4], float* const d_flat[4], cudaSt
   return check_cuda(cudaGetLastError(), "unpack_grads launch");
 }
 
-// ------------------------------------------------------------------------------------------------ in-kernel exchanges over peer memory
-// A ray-sharded tracking iteration needs three tiny batch-global quantities.  Instead of three NCCL launches the
-// single-CTA kernels that produce them exchange them themselves through NVLink peer memory (symmetric buffers, one per rank, mapped
-// on every rank): push the local value into slot [parity][my rank] of EVERY peer's buffer, st.release.sys a sequence number next to
-// it, spin (ld.acquire.sys) on the own buffer until all ranks' sequence numbers have arrived.  Parity double-buffering + one
-// sequence counter per channel make the buffers reusable without any reset; a rank cannot run two exchanges of a channel ahead
-// because the other channels of the same iteration need everybody.
-struct PeerX {
-  int rank, world;                   // world <= 1: no exchange
-  unsigned char* peer[NSB_MAX_PEERS];
-  unsigned long long* counter;       // this rank's sequence counters, one per channel
-  int max_n;                         // residual-pool capacity per rank
-};
-constexpr size_t kXMaxOff = 0, kXSumOff = 256, kXPoolFlagOff = 2304, kXPoolOff = 2560;
-__host__ __device__ inline size_t peer_buffer_bytes(int max_n) { return kXPoolOff + (size_t)2 * NSB_MAX_PEERS * (size_t)max_n * sizeof(double); }
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
-}
-// sequence number of this launch on channel c (CTA-uniform)
-__device__ __forceinline__ uint32_t peer_begin(const PeerX& px, int c, uint32_t* s_seq) {
-  if (threadIdx.x == 0) *s_seq = (uint32_t)(px.counter[c] + 1ull);
-  __syncthreads();
-  return *s_seq;
-}
-// all pushes of this CTA are done -> publish `seq` in slot [parity][rank] of every peer, wait for every rank's, remember the sequence
-__device__ __forceinline__ void peer_signal_wait(const PeerX& px, int c, size_t flag_off, size_t flag_stride, uint32_t seq) {
-  __threadfence_system();
-  __syncthreads();
-  const int par = seq & 1u;
-  if ((int)threadIdx.x < px.world) {
-    st_release_sys(reinterpret_cast<uint32_t*>(px.peer[threadIdx.x] + flag_off + ((size_t)par * NSB_MAX_PEERS + px.rank) * flag_stride), seq);
-    const uint32_t* mine = reinterpret_cast<const uint32_t*>(px.peer[px.rank] + flag_off + ((size_t)par * NSB_MAX_PEERS + threadIdx.x) * flag_stride);
-    while ((int)(ld_acquire_sys(mine) - seq) < 0) { }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) px.counter[c] = (unsigned long long)seq;
-}
-
 // ------------------------------------------------------------------------------------------------ batch max
 __global__ void batch_max_kernel(const float* __restrict__ gt, int n, float* __restrict__ out2, const PeerX px) {
   __shared__ float red[32];
@@ -224,21 +186,8 @@ __global__ void prefilter_kernel(const float* __restrict__ ro, const float* __re
 }
 
 // ------------------------------------------------------------------------------------------------ loss seeds
-__device__ __forceinline__ double block_sum(double v, double* red) {
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  double t = 0.0;
-  if (threadIdx.x < 32) {
-    t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-  }
-  __syncthreads();
-  return t;   // valid in thread 0
-}
-__device__ __forceinline__ double sgn(double x) { return (x > 0.0) - (x < 0.0); }
-
-constexpr int kMedianDirect = 512;       // larger pools: 8-pass radix select (the direct count is O(n^2))
+// Stand-alone single-CTA kernels (large batches, sharded batches, direct C-ABI use).  nsb_seeds.cuh holds the same computations as
+// device functions over caller-provided scratch for the tail of the forward kernels (small batches: no separate launch).
 // Tracker.optimize_cam_in_batch loss (src/Tracker.py:108-123); single CTA, residuals staged in `res`.
 __global__ void tracking_seeds_kernel(const double* __restrict__ depth, const double* __restrict__ var, const float* __restrict__ rgb,
                                       const float* __restrict__ gt, const double* __restrict__ gt_rgb, int n, double w_color,

@@ -152,6 +152,20 @@ __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterp
 __device__ __forceinline__ int swz(int r, int q) { return ((q ^ (r >> 1)) & 3) << 2; }
 __device__ __forceinline__ int act_idx(int r, int pt) { return r * kRowF + swz(r, pt >> 2) + (pt & 3); }
 
+// Loss seeds fused into the forward launch (small batches): the last CTA of the forward kernel to finish computes them (nsb_seeds.cuh).
+// Internal to the library: nsb_tracking_iteration / nsb_mapping_iteration use it through render_forward_fused().
+struct FusedSeeds {
+  int kind;                      // 0 = none, 1 = tracking (Tracker.py:108-123), 2 = mapping (Mapper.py:487-493)
+  const void* gt_rgb;            // float64 [N,3] (tracking) / float32 [N,3] (mapping)
+  const float* gt_depth_loss;    // mapping: the depth the loss supervises with
+  double w_color;
+  int handle_dynamic, use_color;
+  double* g_depth; float* g_rgb; double* loss;
+  double* res;                   // tracking: residual scratch [N]
+  int* counter;                  // grid-wide arrival counter, zero between launches
+};
+int render_forward_fused(const nsb_render_inputs* in, const nsb_forward_outputs* out, const FusedSeeds* fs, void* stream);
+
 // error plumbing shared by the API translation units
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);

@@ -1,6 +1,7 @@
 // nsb_iter.cu -- one optimisation iteration enqueued by a single C call:
 //   batch depth maxima -> render forward -> loss seeds -> render backward
 // (Tracker.optimize_cam_in_batch, src/Tracker.py:106-125; one joint_iter of Mapper.optimize_map, src/Mapper.py:482-503).
+#include <cstring>
 #include "nsb_common.cuh"
 
 using namespace nsb;
@@ -10,7 +11,11 @@ static size_t a16(size_t x) { return (x + 15) & ~size_t(15); }
 // workspace = [tracking-seeds scratch | packed weight-gradient images | decoder-parallel-CTA scratch (small batches only)]
 static size_t split_bytes(int n_rays) { return nsb_split_workspace_bytes(n_rays, NSB_MAX_SAMPLES); }
 extern "C" size_t nsb_iteration_workspace_bytes(int n_rays) {
-  return a16(nsb_tracking_seeds_workspace(n_rays)) + a16(nsb_backward_workspace_bytes()) + a16(split_bytes(n_rays));
+  return a16(nsb_tracking_seeds_workspace(n_rays)) + a16(nsb_backward_workspace_bytes()) + a16(split_bytes(n_rays)) + 16;     // + fused-seeds counter
+}
+static int* seeds_counter(const nsb_iteration_buffers* b, int n_rays) {
+  return reinterpret_cast<int*>(reinterpret_cast<char*>(b->workspace) + a16(nsb_tracking_seeds_workspace(n_rays)) + a16(nsb_backward_workspace_bytes()) +
+                                a16(split_bytes(n_rays)));
 }
 static void* split_ptr(const nsb_iteration_buffers* b, int n_rays) {
   return split_bytes(n_rays) ? reinterpret_cast<char*>(b->workspace) + a16(nsb_tracking_seeds_workspace(n_rays)) + a16(nsb_backward_workspace_bytes()) : nullptr;
@@ -24,7 +29,7 @@ static int check_buffers(const nsb_render_inputs* in, const nsb_iteration_buffer
   return NSB_OK;
 }
 
-static int forward_part(const nsb_render_inputs* in, const nsb_iteration_buffers* b, nsb_render_inputs* in2, void* stream) {
+static int forward_part(const nsb_render_inputs* in, const nsb_iteration_buffers* b, nsb_render_inputs* in2, const FusedSeeds* fs, void* stream) {
   *in2 = *in;
   int rc;
   in2->depth_max = nullptr;
@@ -33,7 +38,7 @@ static int forward_part(const nsb_render_inputs* in, const nsb_iteration_buffers
     in2->depth_max = b->depth_max;
   }
   nsb_forward_outputs fo = {b->depth, b->var, b->rgb, b->z_vals, b->raw, nullptr, b->masks, split_ptr(b, in->n_rays), split_bytes(in->n_rays)};
-  return nsb_render_forward(in2, &fo, stream);
+  return render_forward_fused(in2, &fo, fs, stream);
 }
 
 static int backward_part(const nsb_render_inputs* in2, const nsb_iteration_buffers* b, const nsb_backward_args* g, void* stream) {
@@ -52,9 +57,18 @@ extern "C" int nsb_tracking_iteration(const nsb_render_inputs* in, const nsb_ite
   int rc = check_buffers(in, buf, grads); if (rc) return rc;
   if (!in->gt_depth) { set_error("tracking iteration needs gt_depth"); return NSB_ERR_ARG; }
   nsb_render_inputs in2;
-  if ((rc = forward_part(in, buf, &in2, stream))) return rc;
-  if ((rc = nsb_tracking_seeds(buf->depth, buf->var, buf->rgb, in->gt_depth, gt_rgb, in->n_rays, w_color, handle_dynamic, use_color,
-                               nullptr, 0, buf->g_depth, buf->g_rgb, buf->loss, buf->workspace, nsb_tracking_seeds_workspace(in->n_rays), stream))) return rc;
+  // small batches: the last CTA of the forward launch computes the loss seeds itself (no separate single-CTA launch)
+  const bool fuse = in->n_rays > 0 && in->n_rays <= 512;          // (the median by direct rank counting, nsb_seeds.cuh)
+  FusedSeeds fs; memset(&fs, 0, sizeof(fs));
+  if (fuse) {
+    fs.kind = 1; fs.gt_rgb = gt_rgb; fs.w_color = w_color; fs.handle_dynamic = handle_dynamic; fs.use_color = use_color;
+    fs.g_depth = buf->g_depth; fs.g_rgb = buf->g_rgb; fs.loss = buf->loss; fs.res = static_cast<double*>(buf->workspace);
+    fs.counter = seeds_counter(buf, in->n_rays);
+    if (use_color && !gt_rgb) { set_error("tracking iteration: use_color without gt_rgb"); return NSB_ERR_ARG; }
+  }
+  if ((rc = forward_part(in, buf, &in2, fuse ? &fs : nullptr, stream))) return rc;
+  if (!fuse && (rc = nsb_tracking_seeds(buf->depth, buf->var, buf->rgb, in->gt_depth, gt_rgb, in->n_rays, w_color, handle_dynamic, use_color,
+                                        nullptr, 0, buf->g_depth, buf->g_rgb, buf->loss, buf->workspace, nsb_tracking_seeds_workspace(in->n_rays), stream))) return rc;
   return backward_part(&in2, buf, grads, stream);
 }
 
@@ -64,8 +78,15 @@ extern "C" int nsb_mapping_iteration(const nsb_render_inputs* in, const nsb_iter
   const float* gtl = gt_depth_loss ? gt_depth_loss : in->gt_depth;
   if (!gtl) { set_error("mapping iteration needs a depth to supervise with"); return NSB_ERR_ARG; }
   nsb_render_inputs in2;
-  if ((rc = forward_part(in, buf, &in2, stream))) return rc;
   const int use_color = in->stage == NSB_STAGE_COLOR;                      // Mapper.py:490
-  if ((rc = nsb_mapping_seeds(buf->depth, buf->rgb, gtl, gt_rgb, in->n_rays, w_color, use_color, buf->g_depth, buf->g_rgb, buf->loss, stream))) return rc;
+  const bool fuse = in->n_rays > 0 && in->n_rays <= NSB_INLINE_MAX_RAYS;
+  FusedSeeds fs; memset(&fs, 0, sizeof(fs));
+  if (fuse) {
+    if (use_color && !gt_rgb) { set_error("mapping iteration: colour stage without gt_rgb"); return NSB_ERR_ARG; }
+    fs.kind = 2; fs.gt_rgb = gt_rgb; fs.gt_depth_loss = gtl; fs.w_color = w_color; fs.use_color = use_color;
+    fs.g_depth = buf->g_depth; fs.g_rgb = buf->g_rgb; fs.loss = buf->loss; fs.counter = seeds_counter(buf, in->n_rays);
+  }
+  if ((rc = forward_part(in, buf, &in2, fuse ? &fs : nullptr, stream))) return rc;
+  if (!fuse && (rc = nsb_mapping_seeds(buf->depth, buf->rgb, gtl, gt_rgb, in->n_rays, w_color, use_color, buf->g_depth, buf->g_rgb, buf->loss, stream))) return rc;
   return backward_part(&in2, buf, grads, stream);
 }

@@ -15,6 +15,7 @@
 #include "nsb_common.cuh"
 #include "nsb_geom.cuh"
 #include "nsb_mlp.cuh"
+#include "nsb_seeds.cuh"
 
 namespace nsb {
 
@@ -156,6 +157,7 @@ struct KParams {
   int* group_done;              // [n_groups] arrival counters, zero between launches (the last CTA resets its counter)
   float4* fwd_parts;            // [n_dec][N*S] decoder outputs of the forward
   double* ray_parts;            // [n_dec][N][6] per-decoder ray-gradient sums of the backward
+  FusedSeeds fs;                // forward: loss seeds computed by the last CTA to finish (kind 0 = not fused)
   int wbytes;                   // bytes reserved for the weight image in shared memory
   int max_pts, max_rays;        // per-CTA capacities the shared-memory carve-up was sized for
 };
@@ -393,6 +395,22 @@ __device__ __forceinline__ void fwd_composite_store(const KParams& P, const Smem
       *reinterpret_cast<float4*>(P.fo.raw + 4 * (g0 + lp)) = *reinterpret_cast<float4*>(sm.raw + 4 * lp);
 }
 
+// Loss seeds fused into the forward launch: the last of `n_participants` CTAs (those that stored ray outputs) reads every ray's
+// depth / variance / colour back and runs the single-CTA seed computation.  scratch = dead dynamic shared memory of this CTA.
+__device__ __forceinline__ void fused_seeds_tail(const KParams& P, int n_participants, unsigned char* scratch) {
+  if (P.fs.kind == 0) return;
+  __shared__ int s_seeds_last;
+  if (!grid_last_arrival(P.fs.counter, n_participants, &s_seeds_last)) return;
+  if (P.fs.kind == 1) {
+    PeerX px; px.rank = 0; px.world = 0; px.counter = nullptr; px.max_n = 0;
+    tracking_seeds_body(P.fo.depth, P.fo.var, P.fo.rgb, P.in.gt_depth, static_cast<const double*>(P.fs.gt_rgb), P.in.n_rays, P.fs.w_color,
+                        P.fs.handle_dynamic, P.fs.use_color, nullptr, 0, P.fs.g_depth, P.fs.g_rgb, P.fs.loss, P.fs.res, px, scratch);
+  } else {
+    mapping_seeds_body(P.fo.depth, P.fo.rgb, P.fs.gt_depth_loss, static_cast<const float*>(P.fs.gt_rgb), P.in.n_rays, P.fs.w_color, P.fs.use_color,
+                       P.fs.g_depth, P.fs.g_rgb, P.fs.loss, scratch);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward kernel, FP32-FMA (SIMT) decoders
 __global__ void __launch_bounds__(256, 1) render_fwd_kernel(const __grid_constant__ KParams P) {
@@ -420,6 +438,7 @@ __global__ void __launch_bounds__(256, 1) render_fwd_kernel(const __grid_constan
   }
   __syncthreads();
   fwd_composite_store(P, sm, b, warp, warps, L.lane);
+  fused_seeds_tail(P, gridDim.x, smem_raw);
 }
 
 }  // namespace nsb
@@ -528,6 +547,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) render_fwd_tc_kernel(const __
   NSB_PH(14);
   fwd_composite_store(P, sm, b, warp, tc::kThreads / 32, lane);
   NSB_PH(15);
+  fused_seeds_tail(P, gridDim.x / nsplit, smem_raw);             // (split launches: one participant per ray group, the compositing CTA)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -893,6 +913,7 @@ static void fill_common(KParams& K, const nsb_render_inputs* in) {
   for (int i = 0; i < 3; i++) K.dec_pos[i] = i;
   K.accumulate_rays = 0;
   K.split = 1; K.group_done = nullptr; K.fwd_parts = nullptr; K.ray_parts = nullptr;
+  memset(&K.fs, 0, sizeof(K.fs));
   int wb = 0;
   for (int i = 0; i < K.n_dec; i++) { const int b = packed_floats(K.dec[i]) * 4; wb = b > wb ? b : wb; }
   K.wbytes = wb;
@@ -983,10 +1004,14 @@ extern "C" int nsb_set_option(const char* key, int value) {
 }
 
 extern "C" int nsb_render_forward(const nsb_render_inputs* in, const nsb_forward_outputs* out, void* stream) {
+  return nsb::render_forward_fused(in, out, nullptr, stream);
+}
+int nsb::render_forward_fused(const nsb_render_inputs* in, const nsb_forward_outputs* out, const nsb::FusedSeeds* fs, void* stream) {
   int rc = validate_inputs(in, true); if (rc) return rc;
   if (!out || !out->depth || !out->var || !out->rgb) { set_error("forward outputs missing"); return NSB_ERR_ARG; }
   if (in->n_rays == 0) return NSB_OK;
   KParams K; fill_common(K, in); K.fo = *out; memset(&K.bw, 0, sizeof(K.bw));
+  if (fs != nullptr) K.fs = *fs;
   if (g_mlp_backend == 1 || K.S > kMaxPtsTc) K.fo.masks = nullptr;        // only the tensor-core forward produces masks
   if (K.S > NSB_MAX_SAMPLES) { set_error("n_samples+n_surface = %d exceeds %d", K.S, NSB_MAX_SAMPLES); return NSB_ERR_UNSUPPORTED; }
   if (K.has_gt && in->n_surface > 0 && !in->t_surface) { set_error("t_surface NULL"); return NSB_ERR_ARG; }

@@ -1,0 +1,211 @@
+// nsb_seeds.cuh -- device bodies of the loss-seed computations (Tracker.py:108-123, Mapper.py:487-493) and the peer-memory exchange
+// helpers.  Used by the stand-alone single-CTA kernels of nsb_aux.cu and, fused, by the LAST CTA of the forward render kernels
+// (nsb_render.cu): for small batches the loss seeds are produced by the forward launch itself.
+#pragma once
+#include "nsb_common.cuh"
+
+namespace nsb {
+
+// ------------------------------------------------------------------------------------------------ in-kernel exchanges over peer memory
+// A ray-sharded tracking iteration needs three tiny batch-global quantities.  Instead of three NCCL launches the
+// single-CTA kernels that produce them exchange them themselves through NVLink peer memory (symmetric buffers, one per rank, mapped
+// on every rank): push the local value into slot [parity][my rank] of EVERY peer's buffer, st.release.sys a sequence number next to
+// it, spin (ld.acquire.sys) on the own buffer until all ranks' sequence numbers have arrived.  Parity double-buffering + one
+// sequence counter per channel make the buffers reusable without any reset; a rank cannot run two exchanges of a channel ahead
+// because the other channels of the same iteration need everybody.
+struct PeerX {
+  int rank, world;                   // world <= 1: no exchange
+  unsigned char* peer[NSB_MAX_PEERS];
+  unsigned long long* counter;       // this rank's sequence counters, one per channel
+  int max_n;                         // residual-pool capacity per rank
+};
+constexpr size_t kXMaxOff = 0, kXSumOff = 256, kXPoolFlagOff = 2304, kXPoolOff = 2560;
+__host__ __device__ inline size_t peer_buffer_bytes(int max_n) { return kXPoolOff + (size_t)2 * NSB_MAX_PEERS * (size_t)max_n * sizeof(double); }
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+// sequence number of this launch on channel c (CTA-uniform)
+__device__ __forceinline__ uint32_t peer_begin(const PeerX& px, int c, uint32_t* s_seq) {
+  if (threadIdx.x == 0) *s_seq = (uint32_t)(px.counter[c] + 1ull);
+  __syncthreads();
+  return *s_seq;
+}
+// all pushes of this CTA are done -> publish `seq` in slot [parity][rank] of every peer, wait for every rank's, remember the sequence
+__device__ __forceinline__ void peer_signal_wait(const PeerX& px, int c, size_t flag_off, size_t flag_stride, uint32_t seq) {
+  __threadfence_system();
+  __syncthreads();
+  const int par = seq & 1u;
+  if ((int)threadIdx.x < px.world) {
+    st_release_sys(reinterpret_cast<uint32_t*>(px.peer[threadIdx.x] + flag_off + ((size_t)par * NSB_MAX_PEERS + px.rank) * flag_stride), seq);
+    const uint32_t* mine = reinterpret_cast<const uint32_t*>(px.peer[px.rank] + flag_off + ((size_t)par * NSB_MAX_PEERS + threadIdx.x) * flag_stride);
+    while ((int)(ld_acquire_sys(mine) - seq) < 0) { }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) px.counter[c] = (unsigned long long)seq;
+}
+
+
+constexpr int kMedianDirect = 512;       // larger pools: 8-pass radix select (the direct count is O(n^2))
+constexpr int kSeedsScratchBytes = 34 * 8 + kMedianDirect * 8 + (256 + 8 + 2 + 2) * 4;
+
+// ------------------------------------------------------------------------------------------------ loss seeds
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x < 32) {
+    t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  __syncthreads();
+  return t;   // valid in thread 0
+}
+__device__ __forceinline__ double sgn(double x) { return (x > 0.0) - (x < 0.0); }
+
+// Tracker.optimize_cam_in_batch loss (src/Tracker.py:108-123); single CTA, residuals staged in `res`.
+__device__ __forceinline__ void tracking_seeds_body(const double* __restrict__ depth, const double* __restrict__ var, const float* __restrict__ rgb,
+                                      const float* __restrict__ gt, const double* __restrict__ gt_rgb, int n, double w_color,
+                                      int handle_dynamic, int use_color, const double* __restrict__ pool, int n_pool,
+                                      double* __restrict__ g_depth, float* __restrict__ g_rgb,
+                                      double* __restrict__ loss, double* __restrict__ res, const PeerX& px, unsigned char* __restrict__ scratch) {
+  // scratch (kSeedsScratchBytes, 16-byte aligned shared memory): red[32] f64 | med_s f64 | med_key u64 | keys[kMedianDirect] u64 | hist[256] | wtot[8] | sel[2] | seq
+  double* red = reinterpret_cast<double*>(scratch);
+  double& med_s = red[32];
+  unsigned long long& med_key = *reinterpret_cast<unsigned long long*>(red + 33);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(red + 34);
+  int* hist = reinterpret_cast<int*>(keys + kMedianDirect);
+  int* wtot = hist + 256;
+  int* sel = wtot + 8;
+  uint32_t* s_seq_p = reinterpret_cast<uint32_t*>(sel + 2);
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    res[i] = fabs((double)gt[i] - depth[i]) / sqrt(var[i] + 1e-10);
+  __syncthreads();
+  if (handle_dynamic) {
+    // torch.median = lower median = the element of rank (n-1)/2 of the IEEE bit patterns (residuals are non-negative, so the unsigned
+    // 64-bit pattern is order preserving; NaN sorts last like torch.sort).
+    const double* mp = pool != nullptr ? pool : res;       // sharded batches: median over the all-gathered residuals
+    int np = pool != nullptr ? n_pool : n;
+    int pool_pitch = 0;                                    // > 0: the pool is [world][pool_pitch] with n valid entries per rank
+    if (px.world > 1) {
+      // all-gather of the residuals through peer memory (channel 1): push this shard into block [parity][rank] of every peer's pool
+      const uint32_t seq = peer_begin(px, 1, s_seq_p);
+      const int par = seq & 1u;
+      for (int i = threadIdx.x; i < n * px.world; i += blockDim.x) {
+        const int r = i / n, j = i - r * n;
+        __stcg(reinterpret_cast<double*>(px.peer[r] + kXPoolOff) + ((size_t)par * NSB_MAX_PEERS + px.rank) * px.max_n + j, res[j]);
+      }
+      peer_signal_wait(px, 1, kXPoolFlagOff, 16, seq);
+      mp = reinterpret_cast<const double*>(px.peer[px.rank] + kXPoolOff) + (size_t)par * NSB_MAX_PEERS * px.max_n;
+      np = n * px.world; pool_pitch = px.max_n;
+    }
+    auto pool_at = [&](int i) { return pool_pitch ? __ldcg(mp + (size_t)(i / n) * pool_pitch + (i % n)) : mp[i]; };
+    const int k = (np - 1) / 2;
+    if (np <= kMedianDirect) {
+      // small pools (a tracking batch is 200 rays): direct rank counting from shared memory, no serial passes
+      for (int i = threadIdx.x; i < np; i += blockDim.x) keys[i] = (unsigned long long)__double_as_longlong(pool_at(i));
+      __syncthreads();
+      for (int i = threadIdx.x; i < np; i += blockDim.x) {
+        const unsigned long long key = keys[i];
+        int less = 0, eq = 0;
+        for (int j = 0; j < np; j++) { const unsigned long long o = keys[j]; less += o < key ? 1 : 0; eq += o == key ? 1 : 0; }
+        if (less <= k && k < less + eq) med_key = key;     // every thread that qualifies writes the same value
+      }
+      __syncthreads();
+    } else {
+      // radix select, 8 bits per pass (8 passes, 256-bin shared histogram)
+      unsigned long long prefix = 0ull;
+      int kk = k;
+      for (int shift = 56; shift >= 0; shift -= 8) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        const unsigned long long maskhi = shift == 56 ? 0ull : (~0ull << (shift + 8));
+        for (int i = threadIdx.x; i < np; i += blockDim.x) {
+          const unsigned long long key = (unsigned long long)__double_as_longlong(pool_at(i));
+          if ((key & maskhi) == prefix) atomicAdd(&hist[(int)((key >> shift) & 0xffull)], 1);
+        }
+        __syncthreads();
+        // digit of the k-th key = the bin whose [exclusive, inclusive) prefix-count range contains kk (256 bins: 8 warps scan them)
+        {
+          const int v = threadIdx.x < 256 ? hist[threadIdx.x] : 0;
+          int incl = v;
+          for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += t; }
+          if (threadIdx.x < 256 && (threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = incl;
+          __syncthreads();
+          int before = 0;
+          for (int w = 0; w < (int)(threadIdx.x >> 5) && w < 8; w++) before += wtot[w];
+          incl += before;
+          if (threadIdx.x < 256 && incl - v <= kk && kk < incl) { sel[0] = (int)threadIdx.x; sel[1] = incl - v; }
+          __syncthreads();
+        }
+        prefix |= (unsigned long long)sel[0] << shift;
+        kk -= sel[1];
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) med_key = prefix;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) med_s = __longlong_as_double((long long)med_key);
+    __syncthreads();
+  }
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double r = res[i];
+    bool m = gt[i] > 0.0f;
+    if (handle_dynamic) m = m && (r < 10.0 * med_s);
+    double gd = 0.0; float gc[3] = {0.f, 0.f, 0.f};
+    if (m) {
+      acc += r;
+      gd = -sgn((double)gt[i] - depth[i]) / sqrt(var[i] + 1e-10);
+      if (use_color) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) { const double df = gt_rgb[3 * i + a] - (double)rgb[3 * i + a]; acc += w_color * fabs(df); gc[a] = (float)(-w_color * sgn(df)); }
+      }
+    }
+    g_depth[i] = gd; g_rgb[3 * i] = gc[0]; g_rgb[3 * i + 1] = gc[1]; g_rgb[3 * i + 2] = gc[2];
+  }
+  const double tot = block_sum(acc, red);
+  if (threadIdx.x == 0) loss[0] = tot;
+}
+
+// Mapper.optimize_map loss (src/Mapper.py:487-493); single CTA (deterministic sum)
+__device__ __forceinline__ void mapping_seeds_body(const double* __restrict__ depth, const float* __restrict__ rgb, const float* __restrict__ gt,
+                                     const float* __restrict__ gt_rgb, int n, double w_color, int use_color,
+                                     double* __restrict__ g_depth, float* __restrict__ g_rgb, double* __restrict__ loss,
+                                     unsigned char* __restrict__ scratch) {
+  double* red = reinterpret_cast<double*>(scratch);
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double gd = 0.0;
+    if (gt[i] > 0.0f) { const double df = (double)gt[i] - depth[i]; acc += fabs(df); gd = -sgn(df); }
+    g_depth[i] = gd;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      float g = 0.0f;
+      if (use_color) { const float df = gt_rgb[3 * i + a] - rgb[3 * i + a]; acc += w_color * (double)fabsf(df); g = (float)(-w_color * sgn((double)df)); }
+      g_rgb[3 * i + a] = g;
+    }
+  }
+  const double tot = block_sum(acc, red);
+  if (threadIdx.x == 0) loss[0] = tot;
+}
+
+
+// Grid-wide "last CTA" election: every participating CTA calls it once after its global writes; returns true in exactly one CTA (all of
+// its threads), after every other participant's writes are visible.  counter: zero between launches (the winner resets it).
+__device__ __forceinline__ bool grid_last_arrival(int* counter, int n_participants, int* s_flag) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int old = atomicAdd(counter, 1);
+    *s_flag = old == n_participants - 1;
+    if (*s_flag) *counter = 0;
+  }
+  __syncthreads();
+  const bool last = *s_flag != 0;
+  if (last) __threadfence();
+  return last;
+}
+
+}  // namespace nsb

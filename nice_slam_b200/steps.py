@@ -16,8 +16,9 @@ from . import _lib
 from ._lib import LEVELS, STAGE_DECODERS
 from .renderer import _VP, _inputs, _linspaces, _stream, _Call, _require_cuda
 
-KERNEL_LAUNCHES_PER_ITERATION = 3       # render_fwd, seeds, render_bwd for batches <= 1024 rays (the forward reduces the batch depth maxima
-                                        # itself, the backward produces d c2w itself); + batch_max above that, + unpack for decoder grads
+KERNEL_LAUNCHES_PER_ITERATION = 2       # render_fwd + render_bwd for batches <= 1024 rays: the forward reduces the batch depth maxima itself and
+                                        # its last CTA computes the loss seeds, the backward's last CTA produces d c2w; larger batches add
+                                        # batch_max + seeds launches, decoder gradients an unpack launch
 
 
 def packed_layout(n_frames, grad_decoders, masked_counts):
