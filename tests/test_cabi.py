@@ -137,3 +137,26 @@ def test_bench_reference_arm_prints_one_contract_line():
         assert key in line, key
     assert line["impl"] == "reference" and line["unit"] == "rays/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_iteration_context_block_layouts_on_cpu():
+    """Host-side layout logic of steps.IterationContext (no kernel runs): the single-copy input / result blocks and the packed gradient block."""
+    from types import SimpleNamespace
+    from nice_slam_b200 import _lib
+    from nice_slam_b200.steps import IterationContext, packed_layout
+    r = SimpleNamespace(N_samples=32, N_surface=16)
+    for kind, col_dt in (("track", torch.float64), ("map", torch.float32)):
+        n = 37
+        x = IterationContext(r, n, "color", "cpu", kind=kind, grad_decoders=("color",) if kind == "map" else (), n_frames=3 if kind == "map" else 0)
+        ro, rd, gd, gc = x.device_views()
+        assert ro.shape == (n, 3) and rd.shape == (n, 3) and gd.shape == (n,) and gc.shape == (n, 3) and gc.dtype == col_dt
+        x.d_in.zero_(); gc.fill_(1.0); assert float(ro.abs().sum() + rd.abs().sum() + gd.abs().sum()) == 0.0      # colour does not overlap the rays
+        ro.fill_(2.0); rd.fill_(3.0); gd.fill_(4.0); assert float(gc.sum()) == 3 * n
+        assert gc.data_ptr() % 8 == 0 and x.loss.data_ptr() % 8 == 0 and x.d_c2w.data_ptr() == x.loss.data_ptr() + 8
+        assert x.d_rays_o.data_ptr() == x.d_res.data_ptr() and x.d_rays_d.data_ptr() == x.d_res.data_ptr() + 12 * n
+        assert x.h2d_bytes == x.d_in.numel() and x.d2h_bytes == x.d_res.numel()
+        if kind == "map":
+            sect, total = packed_layout(3, ("color",), [("grid_fine", 10)])
+            assert sect["frames"] == (4, 36) and sect["dec_color"][0] == 40 and sect["dec_color"][1] == _lib.lib().nsb_flat_decoder_floats(3)
+            assert sect["grid_fine"][0] % 4 == 0 and total == sect["grid_fine"][0] + 320          # voxel sections are 16-byte aligned
+            assert x.packed.numel() == 40 + ((15899 + 3) // 4) * 4 and x.d_frames.shape == (3, 12) and x.d_flat["color"].numel() == 15899
