@@ -77,8 +77,12 @@ size_t nsb_packed_decoder_floats(int level);
 
 int nsb_version(void);
 const char* nsb_last_error(void);
-/* Process-wide options.  "mlp_backend": 0 = auto (default), 1 = FP32-FMA decoders, 2 = tcgen05 (3xTF32) decoders. */
+/* Process-wide options.  "mlp_backend": 0 = auto (default: tcgen05 tile kernels), 1 = FP32-FMA decoders, 2 = tcgen05 round-1 ray-group
+ * kernels, 3 = tcgen05 tile kernels (3xTF32, two CTAs per SM). */
 int nsb_set_option(const char* key, int value);
+
+/* Diagnostic: resident CTAs per SM of the tile-centric tensor-core kernels (2 = the design point: two tiles in flight per SM). */
+int nsb_debug_occupancy(int* fwd_ctas_per_sm, int* bwd_ctas_per_sm);
 
 /* Pack decoders' parameters into the kernels' shared-memory image (one launch for all four).
  * params[l] == NULL skips level l.  packed[l] must hold nsb_packed_decoder_floats(l) floats.

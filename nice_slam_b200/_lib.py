@@ -65,6 +65,7 @@ SYMBOLS = {
     "nsb_version": (C.c_int, []),
     "nsb_last_error": (C.c_char_p, []),
     "nsb_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "nsb_debug_occupancy": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "nsb_flat_decoder_floats": (C.c_size_t, [C.c_int]),
     "nsb_flat_offset": (C.c_longlong, [C.c_int, C.c_int, C.c_int]),
     "nsb_packed_decoder_floats": (C.c_size_t, [C.c_int]),

@@ -122,6 +122,45 @@ __device__ void pack_operands_level(float* __restrict__ img /* packed image of t
     if (i == 3 || i == 0) emit_tile(dst, D::FIRSTP, [&](int f, int k) { return W[(i == 0 ? D::o_W0 : D::o_W3E) + k * D::PF + f]; });
   }
 }
+// ---- v2 operand images: units for the tile kernels (layout: nsb_common.cuh op2_*) -------------------------------------------------
+// hi | lo of a [R x KW] canonical tile ([row/8][k/4][row%8][k%4]) whose element (row, k) is get(row, k)
+template <typename F>
+__device__ __forceinline__ void emit_unit(float*& dst, int R, int KW, F&& get) {
+  float* hi = dst; float* lo = dst + R * KW;
+  for (int idx = threadIdx.x; idx < R * KW; idx += blockDim.x) {
+    const int r = idx / KW, k = idx - r * KW;
+    const float v = get(r, k);
+    const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    const int o = ((r >> 3) * (KW >> 2) + (k >> 2)) * 32 + (r & 7) * 4 + (k & 3);
+    hi[o] = h; lo[o] = v - h;
+  }
+  dst += 2 * R * KW;
+}
+template <int LV>
+__device__ void pack_units_level(float* __restrict__ img) {
+  using D = Dec<LV>;
+  const float* W = img;
+  constexpr int PH = D::PH;
+  const int o_wh[5] = {0, D::o_W1, D::o_W2, D::o_W3H, D::o_W4};
+  float* dst = img + op2_fwd_offset(LV);
+  if (D::XYZ)
+    for (int u = 0; u < D::CD / 8; u++)
+      emit_unit(dst, 160, 8, [&](int r, int k) { return W[D::o_WC + r * D::PC + 8 * u + k]; });
+  for (int b = 0; b < op_nblk(LV); b++)
+    for (int h = 0; h < 2; h++)
+      emit_unit(dst, 64, 16, [&](int r, int k) { return W[(r < 32 ? D::o_W0 : D::o_W3E) + (r & 31) * D::PF + 32 * b + 16 * h + k]; });
+  for (int i = 1; i < 5; i++) emit_unit(dst, 32, 32, [&](int r, int k) { return W[o_wh[i] + r * PH + k]; });
+  dst = img + op2_bwd_offset(LV);
+  for (int i = 4; i >= 0; i--) {
+    if (D::XYZ)
+      for (int c2 = 0; c2 < D::CD / 32; c2++)
+        emit_unit(dst, 32, 32, [&](int c, int k) { return W[D::o_WC + (i * 32 + k) * D::PC + 32 * c2 + c]; });
+    if (i >= 1) emit_unit(dst, 32, 32, [&](int j, int k) { return W[o_wh[i] + k * PH + j]; });
+    if (i == 3 || i == 0)
+      for (int fb = 0; fb < D::FIRSTP / 32; fb++)
+        emit_unit(dst, 32, 32, [&](int f, int k) { return W[(i == 0 ? D::o_W0 : D::o_W3E) + k * D::PF + 32 * fb + f]; });
+  }
+}
 __global__ void pack_operands_kernel(const __grid_constant__ PackArgs A) {
   const int lv = blockIdx.x;
   if (!A.present[lv]) return;
@@ -130,6 +169,12 @@ __global__ void pack_operands_kernel(const __grid_constant__ PackArgs A) {
     case 1: pack_operands_level<1>(A.packed[1]); break;
     case 2: pack_operands_level<2>(A.packed[2]); break;
     default: pack_operands_level<3>(A.packed[3]); break;
+  }
+  switch (lv) {
+    case 0: pack_units_level<0>(A.packed[0]); break;
+    case 1: pack_units_level<1>(A.packed[1]); break;
+    case 2: pack_units_level<2>(A.packed[2]); break;
+    default: pack_units_level<3>(A.packed[3]); break;
   }
 }
 

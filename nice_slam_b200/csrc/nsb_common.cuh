@@ -87,7 +87,27 @@ __host__ __device__ constexpr int op_bwd_layer_offset(int lv, int i) {      // l
 __host__ __device__ constexpr int op_bwd_floats(int lv) { return op_bwd_layer_offset(lv, -1); }
 __host__ __device__ constexpr int op_fwd_offset(int lv) { return packed_floats(lv); }
 __host__ __device__ constexpr int op_bwd_offset(int lv) { return packed_floats(lv) + op_fwd_floats(lv); }
-__host__ __device__ constexpr int packed_total_floats(int lv) { return packed_floats(lv) + op_fwd_floats(lv) + op_bwd_floats(lv); }
+// ---- v2 operand images (tile kernels, nsb_tile.cuh): the same matrices cut into UNITS that stream through a 4-slot ring ----------------
+//   forward : FC_u, u < cd/8   : [160 x 8]  rows 32 i + o = Wc_i[o][8 u + k]                                  (2560 floats hi|lo)
+//             L0_{b,h}, h < 2  : [64 x 16]  rows o = W0[o][32 b + 16 h + k], rows 32 + o = W3E[o][...]          (2048 floats)
+//             H_i, i = 1..4    : [32 x 32]  rows o = W_i[o][hidden k]                                          (2048 floats)
+//   backward: for i = 4..0: DC_{i,c2}, c2 < cd/32 : rows c = Wc_i[k][32 c2 + c] | D1_i (i >= 1): rows j = W_i[k][hidden j]
+//             | DF_{i,fb} (i = 3, 0), fb < firstp/32 : rows f = W_i[k][first-input 32 fb + f]                  (all [32 x 32], 2048 floats)
+__host__ __device__ constexpr int op2_fc_units(int lv) { return lv == 0 ? 0 : op_cd(lv) / 8; }
+__host__ __device__ constexpr int op2_fwd_units(int lv) { return op2_fc_units(lv) + 2 * op_nblk(lv) + 4; }
+__host__ __device__ constexpr int op2_fwd_floats(int lv) { return op2_fc_units(lv) * 2560 + (2 * op_nblk(lv) + 4) * 2048; }
+__host__ __device__ constexpr int op2_bwd_layer_units(int lv, int i) {
+  return (lv != 0 ? op_cd(lv) / 32 : 0) + (i >= 1 ? 1 : 0) + ((i == 3 || i == 0) ? op_firstp(lv) / 32 : 0);
+}
+__host__ __device__ constexpr int op2_bwd_units(int lv) {
+  int n = 0;
+  for (int i = 0; i < 5; i++) n += op2_bwd_layer_units(lv, i);
+  return n;
+}
+__host__ __device__ constexpr int op2_bwd_floats(int lv) { return op2_bwd_units(lv) * 2048; }
+__host__ __device__ constexpr int op2_fwd_offset(int lv) { return packed_floats(lv) + op_fwd_floats(lv) + op_bwd_floats(lv); }
+__host__ __device__ constexpr int op2_bwd_offset(int lv) { return op2_fwd_offset(lv) + op2_fwd_floats(lv); }
+__host__ __device__ constexpr int packed_total_floats(int lv) { return op2_bwd_offset(lv) + op2_bwd_floats(lv); }
 constexpr int kBwdStageFloats = op_bwd_layer_floats(2, 3);      // largest backward layer chunk (fine decoder, layer 3): 48 KB
 static_assert(kBwdStageFloats == 12288, "backward stage size");
 

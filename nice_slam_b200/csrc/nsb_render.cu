@@ -157,6 +157,10 @@ struct KParams {
   int* group_done;              // [n_groups] arrival counters, zero between launches (the last CTA resets its counter)
   float4* fwd_parts;            // [n_dec][N*S] decoder outputs of the forward
   double* ray_parts;            // [n_dec][N][6] per-decoder ray-gradient sums of the backward
+  // tile kernels (nsb_tile.cuh): item = (128-point tile, decoder); `split` items per tile
+  int* ray_cnt;                 // [N] completion counters of the rays, zero between launches (the completing CTA resets them)
+  float4* tile_parts;           // forward: [split][N*S] per-item decoder outputs (split == 1: aliases fo.raw)
+  int tile_rays;                // backward: rays one tile can touch (stride of ray_parts per item)
   FusedSeeds fs;                // forward: loss seeds computed by the last CTA to finish (kind 0 = not fused)
   int wbytes;                   // bytes reserved for the weight image in shared memory
   int max_pts, max_rays;        // per-CTA capacities the shared-memory carve-up was sized for
@@ -871,6 +875,10 @@ __global__ void __launch_bounds__(tc::kThreads, 1) render_bwd_tc_kernel(const __
   NSB_PH(30);
 }
 
+}  // namespace nsb
+#include "nsb_tile.cuh"
+namespace nsb {
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -912,7 +920,7 @@ static void fill_common(KParams& K, const nsb_render_inputs* in) {
   K.n_dec = stage_decoders(in->stage, K.dec);
   for (int i = 0; i < 3; i++) K.dec_pos[i] = i;
   K.accumulate_rays = 0;
-  K.split = 1; K.group_done = nullptr; K.fwd_parts = nullptr; K.ray_parts = nullptr;
+  K.split = 1; K.group_done = nullptr; K.fwd_parts = nullptr; K.ray_parts = nullptr; K.ray_cnt = nullptr; K.tile_parts = nullptr; K.tile_rays = 0;
   memset(&K.fs, 0, sizeof(K.fs));
   int wb = 0;
   for (int i = 0; i < K.n_dec; i++) { const int b = packed_floats(K.dec[i]) * 4; wb = b > wb ? b : wb; }
@@ -955,16 +963,51 @@ static size_t tc_total_smem(int max_pts, int max_rays, bool bwd = false) {
 // ---- decoder-parallel CTAs: workspace layout and launch policy ------------------------------------------------------------------
 constexpr int kSplitMaxRays = 256;
 static size_t split_counters_bytes(int n_rays) { return align16((size_t)n_rays * sizeof(int)); }
-extern "C" size_t nsb_split_workspace_bytes(int n_rays, int S) {
+static size_t old_split_workspace_bytes(int n_rays, int S) {
   if (n_rays < 1 || n_rays > kSplitMaxRays || S < 1) return 0;
   const size_t fwd = (size_t)3 * n_rays * S * sizeof(float4), bwd = (size_t)3 * n_rays * 6 * sizeof(double);
   return split_counters_bytes(n_rays) + (fwd > bwd ? fwd : bwd);
+}
+// ---- tile kernels: workspace = [16 B | ray completion counters (N ints) | per-item scratch] -----------------------------------------
+// per-item scratch: forward = decoder outputs [split][N*S] float4 (only when items are split per decoder; otherwise they live in fo.raw),
+// backward = ray-gradient parts [tiles * split][kMaxTileRays][6] f64.  Items are split per decoder for batches of up to kSplitMaxPts points
+// (finer granularity for small and medium batches); larger batches evaluate all decoders of a tile in one CTA.
+constexpr long long kSplitMaxPts = 262144;
+struct TileWs { int split; int* ray_cnt; void* scratch; };
+static long long tile_count(long long n_points) { return (n_points + tc::TM - 1) / tc::TM; }
+static int tile_rays(int S) { const int r = (tc::TM - 1) / S + 2; return r < tl::kMaxTileRays ? r : tl::kMaxTileRays; }
+static size_t tile_ws_need(int N, int S, int split, bool bwd) {
+  const long long NS = (long long)N * S;
+  const size_t scratch = bwd ? (size_t)tile_count(NS) * split * tile_rays(S) * 6 * sizeof(double) : (split > 1 ? (size_t)split * NS * sizeof(float4) : 0);
+  return 16 + align16((size_t)N * sizeof(int)) + scratch;
+}
+static bool tile_ws_plan(void* ws, size_t bytes, int N, int S, int n_dec, bool bwd, TileWs* out) {
+  if (!ws || (reinterpret_cast<uintptr_t>(ws) & 15)) return false;
+  int split = ((long long)N * S <= kSplitMaxPts && n_dec > 1) ? n_dec : 1;
+  if (bytes < tile_ws_need(N, S, split, bwd)) split = 1;
+  if (bytes < tile_ws_need(N, S, split, bwd)) return false;
+  out->split = split;
+  out->ray_cnt = reinterpret_cast<int*>(static_cast<char*>(ws) + 16);
+  out->scratch = static_cast<char*>(ws) + 16 + align16((size_t)N * sizeof(int));
+  return true;
+}
+extern "C" size_t nsb_split_workspace_bytes(int n_rays, int S) {
+  if (n_rays < 1 || S < 1) return 0;
+  auto need = [&](int s) {
+    const int split = (long long)n_rays * s <= kSplitMaxPts ? 3 : 1;
+    const size_t a = tile_ws_need(n_rays, s, split, false), b = tile_ws_need(n_rays, s, split, true);
+    return a > b ? a : b;
+  };
+  size_t m = need(S);
+  if (S >= NSB_MAX_SAMPLES) for (int s = tl::kMinSamples; s < NSB_MAX_SAMPLES; s++) { const size_t v = need(s); if (v > m) m = v; }   // "any S" sizing (nsb_iteration_workspace_bytes)
+  const size_t old = old_split_workspace_bytes(n_rays, S);
+  return m > old ? m : old;
 }
 // Decide whether `nd` CTAs per ray group beat one.  Cost model = tiles a CTA walks through x decoders it evaluates x waves.
 // On success K->rays_per_block / max_pts / max_rays / split and the scratch pointers are set.
 static bool plan_split(KParams* K, int nd, void* ws, size_t ws_bytes) {
   const int N = K->in.n_rays, S = K->S;
-  if (nd < 2 || K->points != nullptr || !ws || N > kSplitMaxRays || ws_bytes < nsb_split_workspace_bytes(N, S) || (reinterpret_cast<uintptr_t>(ws) & 15)) return false;
+  if (nd < 2 || K->points != nullptr || !ws || N > kSplitMaxRays || ws_bytes < old_split_workspace_bytes(N, S) || (reinterpret_cast<uintptr_t>(ws) & 15)) return false;
   const int sms = sm_count();
   int r_cap = kMaxPtsTc / S; if (r_cap < 1) return false; if (r_cap > kMaxRaysPerBlock) r_cap = kMaxRaysPerBlock;
   int r1 = 0;
@@ -983,11 +1026,18 @@ static bool plan_split(KParams* K, int nd, void* ws, size_t ws_bytes) {
   return true;
 }
 
+static size_t tile_smem_bytes(bool bwd) { return tl::common_bytes(bwd) + (bwd ? sizeof(tl::BwdExtra) : 0); }
+static bool use_tile_kernels(int S) { return (g_mlp_backend == 0 || g_mlp_backend == 3) && S >= tl::kMinSamples && S <= NSB_MAX_SAMPLES; }
 static bool g_attr_set = false;
 static int set_attrs() {
   if (g_attr_set) return NSB_OK;
   if (check_cuda(cudaFuncSetAttribute(render_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap), "fwd tc smem attr")) return NSB_ERR_CUDA;
   if (check_cuda(cudaFuncSetAttribute(render_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap), "bwd tc smem attr")) return NSB_ERR_CUDA;
+  if (check_cuda(cudaFuncSetAttribute(render_fwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(false)), "fwd tile smem attr")) return NSB_ERR_CUDA;
+  if (check_cuda(cudaFuncSetAttribute(render_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(true)), "bwd tile smem attr")) return NSB_ERR_CUDA;
+  // two CTAs per SM need the full shared-memory carve-out (2 x ~111 KB of the 228 KB)
+  if (check_cuda(cudaFuncSetAttribute(render_fwd_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared), "fwd tile carveout")) return NSB_ERR_CUDA;
+  if (check_cuda(cudaFuncSetAttribute(render_bwd_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared), "bwd tile carveout")) return NSB_ERR_CUDA;
   if (check_cuda(cudaFuncSetAttribute(render_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap), "fwd smem attr")) return NSB_ERR_CUDA;
   if (check_cuda(cudaFuncSetAttribute(render_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap), "bwd smem attr")) return NSB_ERR_CUDA;
   g_attr_set = true;
@@ -999,7 +1049,7 @@ static int set_attrs() {
 using namespace nsb;
 
 extern "C" int nsb_set_option(const char* key, int value) {
-  if (key && !strcmp(key, "mlp_backend")) { if (value < 0 || value > 2) { set_error("mlp_backend must be 0 (auto), 1 (simt) or 2 (tcgen05)"); return NSB_ERR_ARG; } g_mlp_backend = value; return NSB_OK; }
+  if (key && !strcmp(key, "mlp_backend")) { if (value < 0 || value > 3) { set_error("mlp_backend must be 0 (auto = tile kernels), 1 (FP32-FMA), 2 (tcgen05, round-1 ray-group kernels) or 3 (tcgen05 tile kernels)"); return NSB_ERR_ARG; } g_mlp_backend = value; return NSB_OK; }
   set_error("unknown option %s", key ? key : "(null)"); return NSB_ERR_ARG;
 }
 
@@ -1012,15 +1062,26 @@ int nsb::render_forward_fused(const nsb_render_inputs* in, const nsb_forward_out
   if (in->n_rays == 0) return NSB_OK;
   KParams K; fill_common(K, in); K.fo = *out; memset(&K.bw, 0, sizeof(K.bw));
   if (fs != nullptr) K.fs = *fs;
-  if (g_mlp_backend == 1 || K.S > kMaxPtsTc) K.fo.masks = nullptr;        // only the tensor-core forward produces masks
+  if (g_mlp_backend == 1 || K.S > kMaxPtsTc || (g_mlp_backend != 2 && !use_tile_kernels(K.S))) K.fo.masks = nullptr;        // only the tensor-core forward produces masks
   if (K.S > NSB_MAX_SAMPLES) { set_error("n_samples+n_surface = %d exceeds %d", K.S, NSB_MAX_SAMPLES); return NSB_ERR_UNSUPPORTED; }
   if (K.has_gt && in->n_surface > 0 && !in->t_surface) { set_error("t_surface NULL"); return NSB_ERR_ARG; }
   if ((rc = set_attrs())) return rc;
+  if (use_tile_kernels(K.S)) {                            // tile kernels: item = (128-point tile, decoder), two CTAs per SM
+    if (!out->z_vals || !out->raw) { set_error("the tensor-core forward needs z_vals and raw outputs"); return NSB_ERR_ARG; }
+    TileWs w;
+    if (!tile_ws_plan(out->split_workspace, out->split_workspace_bytes, in->n_rays, K.S, K.n_dec, false, &w)) {
+      set_error("split_workspace missing or smaller than nsb_split_workspace_bytes(%d, %d)", in->n_rays, K.S); return NSB_ERR_ARG; }
+    K.split = w.split; K.ray_cnt = w.ray_cnt;
+    K.tile_parts = w.split > 1 ? static_cast<float4*>(w.scratch) : reinterpret_cast<float4*>(out->raw);
+    const long long grid_t = tile_count((long long)in->n_rays * K.S) * K.split;
+    render_fwd_tile_kernel<<<(unsigned)grid_t, tl::kThreads, tile_smem_bytes(false), (cudaStream_t)stream>>>(K);
+    return check_cuda(cudaGetLastError(), "render_fwd_tile_kernel launch");
+  }
   int warps; size_t smem;
   choose_config(in->n_rays, K.S, kRowsFwd, false, K.wbytes, 8, &K, &warps, &smem);
   if (smem > kSmemCap) { set_error("shared-memory budget exceeded (%zu bytes)", smem); return NSB_ERR_UNSUPPORTED; }
   const int grid = (in->n_rays + K.rays_per_block - 1) / K.rays_per_block;
-  if (g_mlp_backend != 1 && K.S <= kMaxPtsTc) {          // tensor-core decoders, 512 threads, <= 2 tiles of 128 points per CTA
+  if (g_mlp_backend == 2 && K.S <= kMaxPtsTc) {          // tensor-core decoders, 512 threads, <= 2 tiles of 128 points per CTA
     choose_config(in->n_rays, K.S, kRowsFwd, false, K.wbytes, 8, &K, &warps, &smem, kMaxPtsTc);
     plan_split(&K, K.n_dec, out->split_workspace, out->split_workspace_bytes);
     const int grid_tc = ((in->n_rays + K.rays_per_block - 1) / K.rays_per_block) * K.split;
@@ -1050,7 +1111,12 @@ extern "C" int nsb_eval_points(const nsb_render_inputs* in, const double* points
   const size_t smem = smem_layout(K.wbytes, ppb, 1, warps, kRowsFwd, false, nullptr, nullptr);
   K.rays_per_block = ppb; K.max_pts = ppb; K.max_rays = 1;
   const int grid = (n_points + ppb - 1) / ppb;
-  if (g_mlp_backend != 1) {
+  if (g_mlp_backend == 0 || g_mlp_backend == 3) {
+    K.split = 1;
+    render_fwd_tile_kernel<<<(unsigned)tile_count(n_points), tl::kThreads, tile_smem_bytes(false), (cudaStream_t)stream>>>(K);
+    return check_cuda(cudaGetLastError(), "render_fwd_tile_kernel(points) launch");
+  }
+  if (g_mlp_backend == 2) {
     render_fwd_tc_kernel<<<grid, tc::kThreads, tc_total_smem(K.max_pts, K.max_rays), (cudaStream_t)stream>>>(K);
     return check_cuda(cudaGetLastError(), "render_fwd_tc_kernel(points) launch");
   }
@@ -1097,7 +1163,7 @@ extern "C" int nsb_render_backward(const nsb_render_inputs* in, const nsb_backwa
   int warps; size_t smem;
   choose_config(in->n_rays, K.S, kRowsBwd, true, K.wbytes, 8, &K, &warps, &smem);
   if (smem > kSmemCap) { set_error("shared-memory budget exceeded (%zu bytes)", smem); return NSB_ERR_UNSUPPORTED; }
-  if (g_mlp_backend != 1 && K.S <= kMaxPtsTc && bw->masks != nullptr) {     // (no saved ReLU masks -> FP32 kernel, which recomputes the forward)
+  if (bw->masks != nullptr && ((g_mlp_backend == 2 && K.S <= kMaxPtsTc) || use_tile_kernels(K.S))) {     // (no saved ReLU masks -> FP32 kernel, which recomputes the forward)
     // Tensor-core kernel for the decoders that only need input gradients (rays, voxels).  Decoders whose WEIGHT gradients are
     // requested (the colour decoder in the mapper's colour stage, Mapper.py:339-341) go through the FP32-FMA kernel in a second
     // launch that adds its share of the ray gradients.
@@ -1109,14 +1175,24 @@ extern "C" int nsb_render_backward(const nsb_render_inputs* in, const nsb_backwa
       else { T.dec[T.n_dec] = K.dec[i]; T.dec_pos[T.n_dec] = i; T.n_dec++; }
     }
     if (T.n_dec > 0) {
+      if (n_w == 0 && want_pose) T.bw.pose_dirs = bw->pose_dirs;   // the tensor-core launch is the last writer of the ray gradients
+      if (use_tile_kernels(T.S)) {
+        TileWs w;
+        if (!tile_ws_plan(bw->split_workspace, bw->split_workspace_bytes, in->n_rays, T.S, T.n_dec, true, &w)) {
+          set_error("split_workspace missing or smaller than nsb_split_workspace_bytes(%d, %d)", in->n_rays, T.S); return NSB_ERR_ARG; }
+        T.split = w.split; T.ray_cnt = w.ray_cnt; T.ray_parts = static_cast<double*>(w.scratch); T.tile_rays = tile_rays(T.S);
+        const long long grid_t = tile_count((long long)in->n_rays * T.S) * T.split;
+        render_bwd_tile_kernel<<<(unsigned)grid_t, tl::kThreads, tile_smem_bytes(true), st>>>(T);
+        if ((rc = check_cuda(cudaGetLastError(), "render_bwd_tile_kernel launch"))) return rc;
+      } else {
       choose_config(in->n_rays, T.S, kRowsBwd, true, T.wbytes, 8, &T, &warps, &smem, kMaxPtsTc);
       plan_split(&T, T.n_dec, bw->split_workspace, bw->split_workspace_bytes);
       const int grid_tc = ((in->n_rays + T.rays_per_block - 1) / T.rays_per_block) * T.split;
       const size_t smem_tc = tc_total_smem(T.max_pts, T.max_rays, true);
       if (smem_tc > kSmemCap) { set_error("shared-memory budget exceeded (%zu bytes)", smem_tc); return NSB_ERR_UNSUPPORTED; }
-      if (n_w == 0 && want_pose) T.bw.pose_dirs = bw->pose_dirs;   // the tensor-core launch is the last writer of the ray gradients
       render_bwd_tc_kernel<<<grid_tc, tc::kThreads, smem_tc, st>>>(T);
       if ((rc = check_cuda(cudaGetLastError(), "render_bwd_tc_kernel launch"))) return rc;
+      }
       if (n_w == 0) return NSB_OK;
       K.accumulate_rays = 1;
       K.n_dec = n_w;
@@ -1133,6 +1209,14 @@ extern "C" int nsb_render_backward(const nsb_render_inputs* in, const nsb_backwa
   if ((rc = check_cuda(cudaGetLastError(), "render_bwd_kernel launch"))) return rc;
   if (any_w && (rc = launch_unpack_grads(K.d_packed, bw->d_flat, st))) return rc;
   if (want_pose) return nsb_pose_grad(bw->pose_dirs, bw->d_rays_o, bw->d_rays_d, in->n_rays, bw->d_c2w, stream);   // FP32 path: separate launch
+  return NSB_OK;
+}
+
+// resident CTAs per SM of the tile kernels (diagnostic; 2 = the design point)
+extern "C" int nsb_debug_occupancy(int* fwd, int* bwd) {
+  int rc = set_attrs(); if (rc) return rc;
+  if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(fwd, render_fwd_tile_kernel, tl::kThreads, tile_smem_bytes(false)), "occupancy fwd")) return NSB_ERR_CUDA;
+  if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(bwd, render_bwd_tile_kernel, tl::kThreads, tile_smem_bytes(true)), "occupancy bwd")) return NSB_ERR_CUDA;
   return NSB_OK;
 }
 

@@ -1,0 +1,941 @@
+// nsb_tile.cuh -- tile-centric tensor-core kernels (round 2): two co-resident CTAs per SM, warp-specialised control warp.
+//
+// Work item = (128-point TILE of the batch's global (ray, sample) order, decoder).  A tile is independent of ray boundaries, so every
+// tile is full (no padding rows for S = 48), small batches spread over all SMs (200 rays x 48 x 3 decoders = 225 items, all resident
+// at once at two CTAs per SM) and the shared-memory footprint no longer grows with the number of samples per ray.  What needs whole
+// rays -- compositing in the forward, the ray-gradient sums in the backward -- is done by the CTA that COMPLETES a ray: every item
+// bumps the counters of the rays it touches after publishing its per-point results, the CTA that brings a counter to its target value
+// composites / reduces that ray from global (L2) scratch in a fixed order (bit-reproducible), and resets the counter.
+//
+// CTA = 288 threads: 8 epilogue warps (two threads per tile row: thread tid owns row tid & 127 and the 16-column half tid >> 7 of every
+// 32-wide epilogue; warp w touches TMEM lanes [32 (w & 3), +32) = its rows) + 1 control warp whose lane 0 is the TMA producer AND the
+// tcgen05.mma issuer:
+//   * weights stream through a 4-slot ring of 10 KB operand UNITS (pre-split hi|lo canonical tiles, consumption order, nsb_common.cuh)
+//     with full (TMA -> issuer) and empty (tcgen05.commit -> producer) mbarriers: three units of prefetch, no thread touches a weight;
+//   * activations ping-pong between two 32 KB operand buffers; epilogue threads publish a tile by fence.proxy.async + mbarrier.arrive
+//     (A_ready, 256 arrivals), the issuer answers with tcgen05.commit on the buffer's `done` barrier -- no __syncthreads in the chain,
+//     and the gather / embedding of tile n+1 overlaps the MMAs of tile n.
+// Shared memory: 64 KB activations + 40 KB ring + 6 KB headers + < 6 KB state <= 113 KB, TMEM 256 columns -> two CTAs per SM, i.e. two
+// tiles in flight per SM with the hardware interleaving their (latency-bound) chains.
+//
+// Arithmetic is that of nsb_tc.cuh (3xTF32 split, same operand order), so results match the round-1 kernels to rounding of the output
+// layer's partial sums.
+#pragma once
+
+namespace nsb {
+namespace tl {
+
+using tc::TM;
+constexpr int kEpiThreads = 256;
+constexpr int kThreads = 288;                 // + one control warp
+constexpr int kCtlWarp = 8;
+constexpr int kCG = 2, kCW = 16, kKQ = 4;      // column halves per row, columns per thread, 16-byte chunks per thread
+constexpr uint32_t kTmemCols = 256;
+constexpr int kSlots = 4;
+constexpr int kSlotFloatsFwd = 2560;          // 10 KB: the largest forward unit (fc_c: [160 x 8] hi|lo)
+constexpr int kSlotFloatsBwd = 2048;          //  8 KB: every backward unit is [32 x 32] hi|lo
+constexpr int kABufFloats = 2 * TM * 32;      // one [128 x 32] operand tile, hi|lo = 32 KB
+constexpr int kMaxTileRays = 18;              // rays one tile can touch (S >= 8)
+constexpr int kMinSamples = 8;
+constexpr long long kWaitCycles = 4000000000ll;      // ~2 s: a wait that long is a protocol bug -> trap instead of hanging the GPU
+
+// barrier indices
+enum { B_FULL = 0, B_EMPTY = 4, B_HDR = 8, B_AREADY = 10, B_DONE = 12, kNumBars = 14 };
+
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol error traps (the launch fails with an error) instead of hanging the device
+__device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > kWaitCycles) { printf("nsb: mbarrier wait timed out (block %d thread %d bar %p parity %u)\n", blockIdx.x, threadIdx.x, (void*)bar, parity); __trap(); }
+  }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }     // the 256 epilogue threads only
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 16; j++) v[j] = __uint_as_float(r[j]);
+}
+
+// ---- shared memory -------------------------------------------------------------------------------------------------------------
+struct TileSmem {
+  float* a[2];        // operand buffers
+  float* ring;        // kSlots x slot_floats
+  int slot_floats;
+  float* hdr;         // 2 x kHdrFloats
+  uint64_t* bars;
+  uint32_t* tmem;
+  unsigned char* extra;      // kernel-specific state behind the common part
+};
+__host__ __device__ constexpr size_t common_bytes(bool bwd) {     // + barriers (14 x 8) + TMEM slot
+  return (2 * (size_t)kABufFloats + (size_t)kSlots * (bwd ? kSlotFloatsBwd : kSlotFloatsFwd) + 2 * kHdrFloats) * 4 + 128;
+}
+__device__ __forceinline__ void carve(unsigned char* base, TileSmem& t, bool bwd) {
+  float* f = reinterpret_cast<float*>(base);
+  t.a[0] = f; f += kABufFloats; t.a[1] = f; f += kABufFloats;
+  t.slot_floats = bwd ? kSlotFloatsBwd : kSlotFloatsFwd;
+  t.ring = f; f += kSlots * t.slot_floats;
+  t.hdr = f; f += 2 * kHdrFloats;
+  t.bars = reinterpret_cast<uint64_t*>(f);
+  t.tmem = reinterpret_cast<uint32_t*>(f + 2 * kNumBars);
+  t.extra = base + common_bytes(bwd);
+}
+
+// ---- unit sequences of the v2 operand images (nsb_common.cuh: op2_*) ---------------------------------------------------------------
+__device__ __forceinline__ int fwd_units(int lv) { return op2_fwd_units(lv); }
+__device__ __forceinline__ int bwd_units(int lv) { return op2_bwd_units(lv); }
+
+// Producer cursor: walks the units of the decoders this CTA evaluates, in consumption order.
+struct Loader {
+  const KParams* P;
+  int q, q1;          // current / end decoder slot
+  int k;              // unit index inside decoder q
+  uint32_t loaded;    // units issued so far (global sequence number of the next one)
+  bool bwd;
+};
+__device__ __forceinline__ bool loader_done(const Loader& L) { return L.q >= L.q1; }
+__device__ __forceinline__ void loader_issue(Loader& L, const TileSmem& t) {
+  const int lv = L.P->dec[L.q];
+  const float* img = L.P->in.packed[lv] + (L.bwd ? op2_bwd_offset(lv) : op2_fwd_offset(lv));
+  int off, floats;
+  if (L.bwd) { off = L.k * 2048; floats = 2048; }
+  else {
+    const int nfc = op2_fc_units(lv);
+    if (L.k < nfc) { off = L.k * 2560; floats = 2560; } else { off = nfc * 2560 + (L.k - nfc) * 2048; floats = 2048; }
+  }
+  const int slot = L.loaded & (kSlots - 1);
+  uint64_t* bar = t.bars + B_FULL + slot;
+  mbar_expect_tx(bar, (uint32_t)floats * 4u);
+  tma_bulk_g2s(t.ring + slot * t.slot_floats, img + off, (uint32_t)floats * 4u, bar);
+  L.loaded++;
+  if (++L.k == (L.bwd ? bwd_units(lv) : fwd_units(lv))) { L.k = 0; L.q++; }
+}
+// refill one slot if a unit is pending and its slot's previous occupant has been issued (blocking on that unit's MMAs)
+__device__ __forceinline__ bool loader_refill(Loader& L, const TileSmem& t, uint32_t issued) {
+  if (loader_done(L) || L.loaded >= issued + kSlots) return false;
+  if (L.loaded >= kSlots) { const uint32_t prev = L.loaded - kSlots; mbar_wait_b(t.bars + B_EMPTY + (prev & (kSlots - 1)), (prev >> 2) & 1u); }
+  loader_issue(L, t);
+  return true;
+}
+__device__ __forceinline__ void load_header(const KParams& P, const TileSmem& t, int lv, int hb) {
+  uint64_t* bar = t.bars + B_HDR + hb;
+  mbar_expect_tx(bar, kHdrFloats * 4u);
+  tma_bulk_g2s(t.hdr + hb * kHdrFloats, P.in.packed[lv] + op_fwd_offset(lv), kHdrFloats * 4u, bar);
+}
+
+// Issuer state (control thread)
+struct Issuer {
+  Loader L;
+  uint32_t issued;    // units consumed so far
+  uint32_t g;         // operand groups consumed so far (forward: buffer = g & 1)
+};
+// wait for the operands of group `g` on A_ready[b]; while they are not there, keep the ring full
+__device__ __forceinline__ void issuer_wait_operands(Issuer& I, const TileSmem& t, int b, uint32_t parity) {
+  uint64_t* bar = t.bars + B_AREADY + b;
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (!loader_refill(I.L, t, I.issued) && clock64() - t0 > kWaitCycles) { printf("nsb: issuer timed out waiting for operands (block %d)\n", blockIdx.x); __trap(); }
+  }
+  tc::tc_fence_after();
+}
+// request every unit whose slot is already free (non-blocking)
+__device__ __forceinline__ void loader_top_up(Loader& L, const TileSmem& t, uint32_t issued) {
+  while (!loader_done(L) && L.loaded < issued + kSlots) {
+    if (L.loaded >= kSlots) { const uint32_t prev = L.loaded - kSlots; if (!mbar_try(t.bars + B_EMPTY + (prev & (kSlots - 1)), (prev >> 2) & 1u)) return; }
+    loader_issue(L, t);
+  }
+}
+// the unit the issuer is about to consume: make sure it was requested, wait for it, return its slot base
+__device__ __forceinline__ const float* issuer_unit(Issuer& I, const TileSmem& t) {
+  loader_top_up(I.L, t, I.issued);
+  while (I.L.loaded <= I.issued) loader_refill(I.L, t, I.issued);
+  const int slot = I.issued & (kSlots - 1);
+  mbar_wait_b(t.bars + B_FULL + slot, (I.issued >> 2) & 1u);
+  return t.ring + slot * t.slot_floats;
+}
+__device__ __forceinline__ void issuer_unit_done(Issuer& I, const TileSmem& t) {
+  tc::mma_commit(t.bars + B_EMPTY + (I.issued & (kSlots - 1)));
+  I.issued++;
+}
+
+// D[128 x N] (+)= A[:, ka0 .. ka0 + 8 ksteps) * B^T, 3xTF32.  A: [128 x 32] hi|lo tile; B: unit [N x KB] hi|lo, product starts at column kb0.
+__device__ __forceinline__ void mma_unit(uint32_t d_tmem, const float* a, int ka0, const float* b, int N, int KB, int kb0, int ksteps, uint32_t& acc) {
+  tc::mma_3x(d_tmem, a, a + TM * 32, 32, ka0, b, b + N * KB, KB, kb0, ksteps, N, acc);
+}
+
+// ---- epilogue-side helpers -------------------------------------------------------------------------------------------------------
+// operands of this thread are written: make them visible to the async proxy, order earlier TMEM reads, arrive
+__device__ __forceinline__ void publish(const TileSmem& t, int b) {
+  fence_proxy_async(); tc::tc_fence_before();
+  mbar_arrive(t.bars + B_AREADY + b);
+}
+__device__ __forceinline__ void wait_group(const TileSmem& t, uint32_t m) {      // MMAs of operand group m (and all earlier ones) have completed
+  mbar_wait_b(t.bars + B_DONE + (m & 1u), (m >> 1) & 1u);
+  tc::tc_fence_after();
+}
+
+// 8 lanes per point, 4 points per pass: 32 channels of grid `g` -> [128 x 32] tile.  Warp w serves the rows of its lane quadrant (w & 3);
+// the eight passes of a quadrant are split over the two warps that share it (two batches of two passes, 16 loads in flight per lane).
+__device__ __forceinline__ void gather_tile(const nsb_grid& g, float* __restrict__ c_hi, const float xn[3], int warp, int lane) {
+  float* c_lo = c_hi + TM * 32;
+  const bool fast = grid_fast(g);
+  const int q = lane & 7, qd = warp & 3, it0 = (warp >> 2) * 4;
+#pragma unroll 1
+  for (int b = 0; b < 2; b++) {
+    Tri t[2]; float4 v[2][8];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int src_lane = (it0 + 2 * b + u) * 4 + (lane >> 3);
+      float x[3];
+      x[0] = __shfl_sync(0xffffffffu, xn[0], src_lane); x[1] = __shfl_sync(0xffffffffu, xn[1], src_lane); x[2] = __shfl_sync(0xffffffffu, xn[2], src_lane);
+      t[u] = make_tri(x, g.W, g.H, g.D);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        int cx, cy, cz;
+        tri_corner_clamped(t[u], k, g.W, g.H, g.D, cx, cy, cz);
+        v[u][k] = grid_load4(g, cz * g.stride_d + cy * g.stride_h + cx * g.stride_w, 4 * q, fast);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const float w = tri_weight(t[u], k);
+        acc.x = fmaf(v[u][k].x, w, acc.x); acc.y = fmaf(v[u][k].y, w, acc.y); acc.z = fmaf(v[u][k].z, w, acc.z); acc.w = fmaf(v[u][k].w, w, acc.w);
+      }
+      tc::put4(c_hi, c_lo, qd * 32 + (it0 + 2 * b + u) * 4 + (lane >> 3), q, 32, acc);
+    }
+  }
+}
+// this thread's 16 features of embedding block `blk` of its point -> [128 x 32] tile
+__device__ __forceinline__ void embed_tile(float* __restrict__ e_hi, const float* __restrict__ B, const float pf[3], int row, int cg, int blk) {
+  float* e_lo = e_hi + TM * 32;
+#pragma unroll
+  for (int kq = kKQ * cg; kq < kKQ * cg + kKQ; kq++) {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int f = 32 * blk + 4 * kq + j;
+      float x = pf[0] * B[f]; x = fmaf(pf[1], B[kEmbPad + f], x); x = fmaf(pf[2], B[2 * kEmbPad + f], x);
+      v[j] = f < kEmb ? __sinf(reduce_2pi(x)) : 0.0f;
+    }
+    tc::put4(e_hi, e_lo, row, kq, 32, make_float4(v[0], v[1], v[2], v[3]));
+  }
+}
+
+// ---- forward of one decoder for this CTA's tile: control side ---------------------------------------------------------------------
+// TMEM: D1 = [0,32), D3 = [32,64) (layer 3; its skip part is accumulated while the embedding blocks are live), D2 = [64,224) (fc_c of the five layers)
+__device__ __forceinline__ void ctl_forward(Issuer& I, const TileSmem& t, int lv, uint32_t tmem) {
+  const bool xyz = lv != 0;
+  if (xyz) {
+    for (int half = 0; half < op_cd(lv) / 32; half++) {           // C tile(s): own grid, then (fine) the middle grid
+      const int b = I.g & 1;
+      issuer_wait_operands(I, t, b, (I.g >> 1) & 1u);
+      for (int u = 0; u < 4; u++) {
+        const float* w = issuer_unit(I, t);
+        uint32_t acc = (half == 0 && u == 0) ? 0u : 1u;
+        mma_unit(tmem + 64u, t.a[b], 8 * u, w, 160, 8, 0, 1, acc);
+        issuer_unit_done(I, t);
+      }
+      tc::mma_commit(t.bars + B_DONE + b);
+      I.g++;
+    }
+  }
+  const int nblk = xyz ? 3 : 1;
+  for (int blk = 0; blk < nblk; blk++) {                          // [D1 | D3] += E_blk * [W0_blk; W3E_blk]^T   (coarse: E = C)
+    const int b = I.g & 1;
+    issuer_wait_operands(I, t, b, (I.g >> 1) & 1u);
+    for (int h = 0; h < 2; h++) {
+      const float* w = issuer_unit(I, t);
+      uint32_t acc = (blk == 0 && h == 0) ? 0u : 1u;
+      mma_unit(tmem, t.a[b], 16 * h, w, 64, 16, 0, 2, acc);
+      issuer_unit_done(I, t);
+    }
+    tc::mma_commit(t.bars + B_DONE + b);
+    I.g++;
+  }
+  for (int i = 1; i < 5; i++) {                                   // layer i from the H tile of layer i-1
+    const int b = I.g & 1;
+    issuer_wait_operands(I, t, b, (I.g >> 1) & 1u);
+    const float* w = issuer_unit(I, t);
+    uint32_t acc = i == 3 ? 1u : 0u;
+    mma_unit(i == 3 ? tmem + 32u : tmem, t.a[b], 0, w, 32, 32, 0, 4, acc);
+    issuer_unit_done(I, t);
+    tc::mma_commit(t.bars + B_DONE + b);
+    I.g++;
+  }
+}
+
+// ---- forward of one decoder: epilogue side.  n = operand-group counter (same sequence as the issuer's).  out[] = decoder outputs of this row.
+__device__ __forceinline__ void epi_forward(const KParams& P, const TileSmem& t, int lv, const PointGeom& G, uint32_t tmem, uint32_t& n, int hb, uint32_t hdr_parity,
+                                            float (&out)[4], uint32_t* __restrict__ gmask) {
+  const int row = threadIdx.x & (TM - 1), cg = threadIdx.x >> 7, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool xyz = lv != 0;
+  const int cd = op_cd(lv), no = lv == 3 ? 4 : 1;
+  const uint32_t my = ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kCW * cg);
+  const uint32_t d1 = tmem + my, d3 = tmem + 32u + my, d2 = tmem + 64u + my;
+  const float* hdr = t.hdr + hb * kHdrFloats;
+  if (xyz) {
+    for (int half = 0; half < cd / 32; half++) {
+      if (n >= 2) wait_group(t, n - 2);
+      gather_tile(P.in.grid[half == 0 ? lv : 1], t.a[n & 1], G.xn, warp, lane);
+      publish(t, n & 1); n++;
+    }
+    mbar_wait_b(t.bars + B_HDR + hb, hdr_parity);
+    for (int blk = 0; blk < 3; blk++) {
+      if (n >= 2) wait_group(t, n - 2);
+      embed_tile(t.a[n & 1], hdr + 464, G.pf, row, cg, blk);
+      publish(t, n & 1); n++;
+    }
+  } else {
+    if (n >= 2) wait_group(t, n - 2);
+    gather_tile(P.in.grid[0], t.a[n & 1], G.xnc, warp, lane);
+    publish(t, n & 1); n++;
+    mbar_wait_b(t.bars + B_HDR + hb, hdr_parity);
+  }
+  float h[kCW];
+#pragma unroll 1
+  for (int i = 0; i < 5; i++) {
+    wait_group(t, n - 1);                                        // pre-activation of layer i (and, in order, everything before it)
+    float v1[kCW];
+    tmem_ld16(i == 3 ? d3 : d1, v1);
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < kCW; j++) { const float u = v1[j] + hdr[i * 32 + kCW * cg + j]; h[j] = u > 0.0f ? u : 0.0f; m |= u > 0.0f ? (1u << j) : 0u; }
+    if (gmask != nullptr) reinterpret_cast<uint16_t*>(gmask)[i * 2 + cg] = (uint16_t)m;          // halfword cg of the 32-bit ReLU mask word
+    if (xyz) {
+      float v2[kCW];
+      tmem_ld16(d2 + 32u * i, v2);
+#pragma unroll
+      for (int j = 0; j < kCW; j++) h[j] += v2[j] + hdr[160 + i * 32 + kCW * cg + j];
+    }
+    if (i == 4) break;
+    float* h_hi = t.a[n & 1];
+#pragma unroll
+    for (int k = 0; k < kKQ; k++) tc::put4(h_hi, h_hi + TM * 32, row, kKQ * cg + k, 32, make_float4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]));
+    publish(t, n & 1); n++;
+  }
+  tc::tc_fence_before();
+  // output layer: partial dot products over this thread's columns, summed over the two threads of the row through shared memory.
+  // (buffer (n & 1) is free: its last reader was group n-2, complete.)
+  float* part = t.a[n & 1];
+  {
+    float s[4];
+#pragma unroll
+    for (int o = 0; o < 4; o++) {
+      s[o] = 0.0f;
+      if (o < no) {
+#pragma unroll
+        for (int j = 0; j < kCW; j++) s[o] = fmaf(h[j], hdr[336 + o * 32 + kCW * cg + j], s[o]);
+      }
+    }
+    *reinterpret_cast<float4*>(part + (cg * TM + row) * 4) = make_float4(s[0], s[1], s[2], s[3]);
+  }
+  epi_sync();
+#pragma unroll
+  for (int o = 0; o < 4; o++) out[o] = hdr[320 + o];
+#pragma unroll
+  for (int c = 0; c < kCG; c++) {
+    const float4 v = *reinterpret_cast<const float4*>(part + (c * TM + row) * 4);
+    out[0] += v.x; out[1] += v.y; out[2] += v.z; out[3] += v.w;
+  }
+  epi_sync();                                                    // partials consumed before the next decoder's gather reuses the buffer
+}
+
+// ---- backward of one decoder (input gradients): control side ----------------------------------------------------------------------
+// TMEM: D1 = [0,32) (g of the next layer), DC = [32,96) (dL/dc), DF = [96,192) (dL/d first input).  One operand group per layer: G in a[0], DU in a[1].
+__device__ __forceinline__ void ctl_backward(Issuer& I, const TileSmem& t, int lv, uint32_t tmem) {
+  const bool xyz = lv != 0;
+  const int cd = op_cd(lv), nfb = op_firstp(lv) / 32;
+  uint32_t acc_dc = 0, acc_df = 0;
+  for (int i = 4; i >= 0; i--) {
+    issuer_wait_operands(I, t, 0, I.g & 1u);
+    if (xyz) for (int c2 = 0; c2 < cd / 32; c2++) {               // DC += G * Wc_i
+      const float* w = issuer_unit(I, t);
+      uint32_t acc = acc_dc;
+      mma_unit(tmem + 32u + 32u * c2, t.a[0], 0, w, 32, 32, 0, 4, acc);
+      issuer_unit_done(I, t);
+    }
+    acc_dc = 1u;
+    if (i >= 1) {                                                 // D1 = DU * W_i[:, hidden]
+      const float* w = issuer_unit(I, t);
+      uint32_t acc = 0u;
+      mma_unit(tmem, t.a[1], 0, w, 32, 32, 0, 4, acc);
+      issuer_unit_done(I, t);
+    }
+    if (i == 3 || i == 0) {                                       // DF += DU * W_i[:, first input]
+      for (int fb = 0; fb < nfb; fb++) {
+        const float* w = issuer_unit(I, t);
+        uint32_t acc = acc_df;
+        mma_unit(tmem + 96u + 32u * fb, t.a[1], 0, w, 32, 32, 0, 4, acc);
+        issuer_unit_done(I, t);
+      }
+      acc_df = 1u;
+    }
+    tc::mma_commit(t.bars + B_DONE);
+    I.g++;
+  }
+}
+
+// ---- backward of one decoder: epilogue side.  Leaves dL/dc rows ([128][cd] fp32) in a[0] and the embedding-chain partials of dL/dp
+// ([2][128][4] fp32) in a[1]; the caller scatters after an epi_sync().
+__device__ __forceinline__ void epi_backward(const KParams& P, const TileSmem& t, int lv, const PointGeom& G, uint32_t tmem, uint32_t& n, int hb, uint32_t hdr_parity,
+                                             const float (&g_out)[4], const uint32_t* __restrict__ gmask) {
+  const int row = threadIdx.x & (TM - 1), cg = threadIdx.x >> 7, warp = threadIdx.x >> 5;
+  const bool xyz = lv != 0;
+  const int cd = op_cd(lv);
+  const float* hdr = t.hdr + hb * kHdrFloats;
+  const uint16_t* gm16 = reinterpret_cast<const uint16_t*>(gmask) + cg;      // halfword cg of the five 32-bit ReLU mask words
+  const uint32_t m01 = (uint32_t)gm16[0] | ((uint32_t)gm16[2] << 16), m23 = (uint32_t)gm16[4] | ((uint32_t)gm16[6] << 16), m4 = gm16[8];
+  mbar_wait_b(t.bars + B_HDR + hb, hdr_parity);
+  const uint32_t my = ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kCW * cg);
+  const uint32_t dcc = tmem + 32u, dfc = tmem + 96u;
+  float* g_hi = t.a[0]; float* du_hi = t.a[1];
+  float g[kCW];
+#pragma unroll
+  for (int j = 0; j < kCW; j++) {
+    float v = 0.0f;
+#pragma unroll
+    for (int o = 0; o < 4; o++) v = fmaf(hdr[336 + o * 32 + kCW * cg + j], g_out[o], v);       // rows >= NO are zero
+    g[j] = v;
+  }
+#pragma unroll 1
+  for (int i = 4; i >= 0; i--) {
+    const uint32_t m = i == 4 ? m4 : (((i & 2) ? m23 : m01) >> (16 * (i & 1))) & 0xffffu;
+#pragma unroll
+    for (int k = 0; k < kKQ; k++) {
+      if (xyz) tc::put4(g_hi, g_hi + TM * 32, row, kKQ * cg + k, 32, make_float4(g[4 * k], g[4 * k + 1], g[4 * k + 2], g[4 * k + 3]));
+      tc::put4(du_hi, du_hi + TM * 32, row, kKQ * cg + k, 32,
+               make_float4((m >> (4 * k)) & 1u ? g[4 * k] : 0.0f, (m >> (4 * k + 1)) & 1u ? g[4 * k + 1] : 0.0f,
+                           (m >> (4 * k + 2)) & 1u ? g[4 * k + 2] : 0.0f, (m >> (4 * k + 3)) & 1u ? g[4 * k + 3] : 0.0f));
+    }
+    publish(t, 0);
+    mbar_wait_b(t.bars + B_DONE, n & 1u); n++;
+    tc::tc_fence_after();
+    if (i >= 1) tmem_ld16(tmem + my, g);
+    tc::tc_fence_before();
+  }
+  // dL/dc rows -> a[0] (plain fp32 [128][cd]); every MMA reading the buffers has completed
+  float* dcs = t.a[0];
+  {
+    float v[kCW];
+    const int nch = xyz ? (cd >> 5) : 1;
+    for (int c = 0; c < nch; c++) {
+      tmem_ld16((xyz ? dcc : dfc) + 32u * c + my, v);
+#pragma unroll
+      for (int k = 0; k < kKQ; k++)
+        *reinterpret_cast<float4*>(dcs + row * cd + 32 * c + kCW * cg + 4 * k) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    }
+  }
+  float dpe[3] = {0.0f, 0.0f, 0.0f};
+  if (xyz) {
+    const float* B = hdr + 464;
+    for (int c = 0; c < 3; c++) {
+      float v[kCW];
+      tmem_ld16(dfc + 32u * c + my, v);
+#pragma unroll
+      for (int j = 0; j < kCW; j++) {
+        const int f = 32 * c + kCW * cg + j;
+        if (f < kEmb) {
+          const float b0 = B[f], b1 = B[kEmbPad + f], b2 = B[2 * kEmbPad + f];
+          float x = G.pf[0] * b0; x = fmaf(G.pf[1], b1, x); x = fmaf(G.pf[2], b2, x);
+          const float dx = __cosf(reduce_2pi(x)) * v[j];
+          dpe[0] = fmaf(b0, dx, dpe[0]); dpe[1] = fmaf(b1, dx, dpe[1]); dpe[2] = fmaf(b2, dx, dpe[2]);
+        }
+      }
+    }
+  }
+  *reinterpret_cast<float4*>(t.a[1] + (cg * TM + row) * 4) = make_float4(dpe[0], dpe[1], dpe[2], 0.0f);
+  tc::tc_fence_before();
+}
+
+// Backward of gather_tile (same warp -> rows mapping).  dcs = [128][cd] fp32.  emit(row, gx) once per point.
+template <typename F>
+__device__ __forceinline__ void scatter_tile(const nsb_grid& g, float* __restrict__ dgrid, const int32_t* __restrict__ slots,
+                                             const float* __restrict__ dcs, int cd, const float xn[3], int warp, int lane, F&& emit) {
+  const bool fast = grid_fast(g);
+  const int q = lane & 7, qd = warp & 3, it0 = (warp >> 2) * 4;
+#pragma unroll 1
+  for (int it = it0; it < it0 + 4; it++) {
+    const int src_lane = it * 4 + (lane >> 3);
+    const int row = qd * 32 + src_lane;
+    float x[3];
+    x[0] = __shfl_sync(0xffffffffu, xn[0], src_lane); x[1] = __shfl_sync(0xffffffffu, xn[1], src_lane); x[2] = __shfl_sync(0xffffffffu, xn[2], src_lane);
+    const Tri t = make_tri(x, g.W, g.H, g.D);
+    const float4 d4 = *reinterpret_cast<const float4*>(dcs + row * cd + 4 * q);
+    const float dc[4] = {d4.x, d4.y, d4.z, d4.w};
+    float gi[3] = {0.f, 0.f, 0.f};
+    long long offs[8]; float4 vv[8]; bool ins[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      int cx, cy, cz;
+      ins[k] = tri_corner(t, k, g.W, g.H, g.D, cx, cy, cz);
+      tri_corner_clamped(t, k, g.W, g.H, g.D, cx, cy, cz);
+      offs[k] = cz * g.stride_d + cy * g.stride_h + cx * g.stride_w;
+      vv[k] = grid_load4(g, offs[k], 4 * q, fast);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if (ins[k]) {
+        const float4 v = vv[k];
+        const float dot = v.x * dc[0] + v.y * dc[1] + v.z * dc[2] + v.w * dc[3];
+        if (dgrid != nullptr) {
+          int cx, cy, cz;
+          tri_corner(t, k, g.W, g.H, g.D, cx, cy, cz);
+          voxel_grad_add(g, dgrid, slots, offs[k], cx, cy, cz, q, fast, tri_weight(t, k), dc);
+        }
+        const float wx = (k & 1) ? t.w1[0] : t.w0[0], wy = (k & 2) ? t.w1[1] : t.w0[1], wz = (k & 4) ? t.w1[2] : t.w0[2];
+        gi[0] += ((k & 1) ? 1.f : -1.f) * wy * wz * dot;
+        gi[1] += ((k & 2) ? 1.f : -1.f) * wx * wz * dot;
+        gi[2] += ((k & 4) ? 1.f : -1.f) * wx * wy * dot;
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      float v = gi[a];
+      v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
+      gi[a] = v;
+    }
+    if (q == 0) {
+      const int size[3] = {g.W, g.H, g.D};
+      float gx[3];
+#pragma unroll
+      for (int a = 0; a < 3; a++) gx[a] = t.clipg[a] * ((float)(size[a] - 1) * 0.5f) * gi[a];
+      emit(row, gx);
+    }
+  }
+}
+
+// ---- tile <-> ray bookkeeping ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int tiles_of_ray(int ray, int S) {
+  const long long p0 = (long long)ray * S;
+  return (int)((p0 + S - 1) / TM - p0 / TM) + 1;
+}
+// Bump the completion counters of the rays [ray_lo, ray_lo + nr) this item touched; returns (CTA-uniform) how many of them this CTA
+// completed, their indices in s_done[].  Every thread must call it, after its global writes.  target = items per tile (split).
+__device__ __forceinline__ int complete_rays(int* __restrict__ ray_cnt, int ray_lo, int nr, int S, int per_tile, int* s_done, int* s_ndone) {
+  __threadfence();
+  if (threadIdx.x == 0) *s_ndone = 0;
+  __syncthreads();
+  if ((int)threadIdx.x < nr) {
+    const int ray = ray_lo + threadIdx.x;
+    const int target = tiles_of_ray(ray, S) * per_tile;
+    const int old = atomicAdd(ray_cnt + ray, 1);
+    if (old == target - 1) { ray_cnt[ray] = 0; s_done[atomicAdd(s_ndone, 1)] = ray; }
+  }
+  __syncthreads();
+  const int nd = *s_ndone;
+  if (nd > 0) __threadfence();
+  return nd;
+}
+
+// raw2outputs_nerf_color of one completed ray by one warp (common.py:204-245 incl. the out-of-bound override of Renderer.py:57).
+// scratch: per-warp shared memory, composite_scratch_bytes(S) bytes, 16-byte aligned: raw [S] float4 | z [S] f64 | w [S] f32.
+__host__ __device__ inline size_t composite_scratch_bytes(int S) { return ((size_t)28 * S + 15) & ~size_t(15); }
+__device__ __forceinline__ void composite_ray(const KParams& P, int ray, int lane, unsigned char* scratch) {
+  const int S = P.S;
+  float* rw = reinterpret_cast<float*>(scratch);
+  double* zz = reinterpret_cast<double*>(rw + 4 * S);
+  float* wq = reinterpret_cast<float*>(zz + S);
+  float o[3], d[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) { o[a] = P.in.rays_o[3 * ray + a]; d[a] = P.in.rays_d[3 * ray + a]; }
+  const long long g0 = (long long)ray * S, NS = (long long)P.in.n_rays * S;
+  for (int s = lane; s < S; s += 32) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < P.split; q++) {                           // decoder order: occ = fine + middle, rgb = colour decoder (zeros elsewhere)
+      const float4 p = __ldcg(P.tile_parts + q * NS + g0 + s);
+      v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+    }
+    const double z = __ldcg(P.fo.z_vals + g0 + s);
+    PointGeom G; make_point(P.in.bound, P.in.coarse_bound, o, d, z, G);
+    if (!G.inb) v.w = 100.0f;
+    zz[s] = z;
+    *reinterpret_cast<float4*>(rw + 4 * s) = v;
+    *reinterpret_cast<float4*>(P.fo.raw + 4 * (g0 + s)) = v;
+  }
+  __syncwarp();
+  ray_weights(rw, S, lane, wq, nullptr);
+  __syncwarp();
+  float c0 = 0.f, c1 = 0.f, c2 = 0.f; double dsum = 0.0;
+  for (int s = lane; s < S; s += 32) {
+    const float w = wq[s];
+    c0 = fmaf(w, rw[4 * s], c0); c1 = fmaf(w, rw[4 * s + 1], c1); c2 = fmaf(w, rw[4 * s + 2], c2);
+    dsum += (double)w * zz[s];
+  }
+  c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2); dsum = warp_sum(dsum);
+  double v = 0.0;
+  for (int s = lane; s < S; s += 32) { const double tt = zz[s] - dsum; v += (double)wq[s] * tt * tt; }
+  v = warp_sum(v);
+  if (lane == 0) {
+    P.fo.depth[ray] = dsum; P.fo.var[ray] = v;
+    P.fo.rgb[3 * ray] = c0; P.fo.rgb[3 * ray + 1] = c1; P.fo.rgb[3 * ray + 2] = c2;
+  }
+  __syncwarp();
+}
+
+}  // namespace tl
+
+// ================================================================================================================================
+// forward kernel
+// ================================================================================================================================
+__global__ void __maxnreg__(112) render_fwd_tile_kernel(const __grid_constant__ KParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  using namespace tl;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = tid & (TM - 1), cg = tid >> 7;            // (control warp: row/cg unused)
+  const bool epi = warp < kCtlWarp;
+  TileSmem t; carve(smem_raw, t, false);
+  __shared__ int s_ndone, s_done[kMaxTileRays], s_last;
+  __shared__ float s_max[16];
+
+  const bool points = P.points != nullptr;
+  const int nsplit = P.split;
+  const int tile = blockIdx.x / nsplit, my = blockIdx.x - tile * nsplit;
+  const int q0 = nsplit > 1 ? my : 0, q1 = nsplit > 1 ? my + 1 : P.n_dec;
+  const long long NP = points ? (long long)P.n_points : (long long)P.in.n_rays * P.S;
+  const long long gp0 = (long long)tile * TM;
+  const int npts = (int)(NP - gp0 < TM ? NP - gp0 : TM);
+  const int S = P.S;
+  int ray_lo = 0, nr = 0;
+  if (!points) { ray_lo = (int)(gp0 / S); nr = (int)((gp0 + npts - 1) / S) - ray_lo + 1; }
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(t.tmem)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  Issuer I; I.L.P = &P; I.L.q = q0; I.L.q1 = q1; I.L.k = 0; I.L.loaded = 0; I.L.bwd = false; I.issued = 0; I.g = 0;
+  if (tid == kEpiThreads) {
+    for (int i = 0; i < kNumBars; i++) mbar_init(t.bars + i, (i == B_AREADY || i == B_AREADY + 1) ? kEpiThreads : 1);
+    mbar_fence_init();
+    load_header(P, t, P.dec[q0], 0);
+    for (int i = 0; i < kSlots; i++) loader_issue(I.L, t);      // (every decoder has >= 6 units)
+  }
+
+  // ---- prologue: this tile's rays -> sorted sample depths -> this row's point
+  PointGeom G;
+  const int lp = row < npts ? row : npts - 1;
+  if (points) {
+    const long long gp = gp0 + lp;
+    const double pin[3] = {P.points[3 * gp], P.points[3 * gp + 1], P.points[3 * gp + 2]};
+    make_point_from_p(P.in.bound, P.in.coarse_bound, pin, G);
+    __syncthreads();
+  } else {
+    float gtmax = 0.0f, gtmax12 = 0.0f;
+    if (P.has_gt) {
+      if (P.in.depth_max != nullptr) { gtmax = P.in.depth_max[0]; gtmax12 = P.in.depth_max[1]; }
+      else {                                                      // small batches: every CTA reduces the sensor depths itself (Renderer.py:109,144)
+        float m = -INFINITY;
+        for (int i = tid; i < P.in.n_rays; i += kThreads) m = fmaxf(m, __ldg(P.in.gt_depth + i));
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) s_max[warp] = m;
+        __syncthreads();
+        m = -INFINITY;
+        for (int w = 0; w < kThreads / 32; w++) m = fmaxf(m, s_max[w]);
+        gtmax = m; gtmax12 = __fmul_rn(m, 1.2f);
+      }
+    }
+    // scratch in the (still unused) operand buffers: ray table [nr][8] f32 + far [nr] f64 | unsorted z [nr*S] | sorted z [nr*S]
+    float* rays = t.a[0];
+    double* far = reinterpret_cast<double*>(t.a[0] + 8 * kMaxTileRays);
+    double* zu = far + kMaxTileRays;
+    double* zs = zu + (size_t)nr * S;
+    for (int r = tid; r < nr; r += kThreads) {
+      float o[3], d[3];
+#pragma unroll
+      for (int a = 0; a < 3; a++) { o[a] = P.in.rays_o[3 * (ray_lo + r) + a]; d[a] = P.in.rays_d[3 * (ray_lo + r) + a]; }
+      const float gt = P.has_gt ? P.in.gt_depth[ray_lo + r] : 0.0f;
+      const RaySampler rs = make_sampler(P.in.bound, o, d, P.has_gt, gt, gtmax12);
+#pragma unroll
+      for (int a = 0; a < 3; a++) { rays[8 * r + a] = o[a]; rays[8 * r + 3 + a] = d[a]; }
+      rays[8 * r + 6] = rs.near; rays[8 * r + 7] = gt; far[r] = rs.far;
+    }
+    __syncthreads();
+    for (int i = tid; i < nr * S; i += kThreads) {
+      const int r = i / S, s = i - r * S;
+      RaySampler rs; rs.near = rays[8 * r + 6]; rs.gt = rays[8 * r + 7]; rs.far = far[r]; rs.has_gt = P.has_gt;
+      zu[i] = sample_z(rs, s, P.in.n_samples, P.in.t_uniform, P.in.t_surface, gtmax);
+    }
+    __syncthreads();
+    for (int i = tid; i < nr * S; i += kThreads) {                 // stable rank sort == torch.sort (Renderer.py:168-170)
+      const int r = i / S, s = i - r * S;
+      const double zi = zu[i];
+      const double* zr = zu + r * S;
+      int rank = 0;
+      for (int j = 0; j < S; j++) { const double zj = zr[j]; rank += (z_less(zj, zi) || (!z_less(zi, zj) && j < s)) ? 1 : 0; }
+      zs[r * S + rank] = zi;
+    }
+    __syncthreads();
+    {
+      const long long gp = gp0 + lp;
+      const int r = (int)(gp / S) - ray_lo, s = (int)(gp - (long long)(ray_lo + r) * S);
+      const double z = zs[r * S + s];
+      const float o[3] = {rays[8 * r], rays[8 * r + 1], rays[8 * r + 2]}, dd[3] = {rays[8 * r + 3], rays[8 * r + 4], rays[8 * r + 5]};
+      make_point(P.in.bound, P.in.coarse_bound, o, dd, z, G);
+      if (epi && cg == 0 && row < npts && my == 0) P.fo.z_vals[gp] = z;
+    }
+    __syncthreads();                                              // the scratch is dead: the operand buffers may be written
+  }
+  tc::tc_fence_before();
+  __syncthreads();                                                // TMEM address + barrier initialisation visible
+  tc::tc_fence_after();
+  const uint32_t tmem = *t.tmem;
+
+  float occ = 0.0f, c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
+  if (!epi) {
+    if (lane == 0) {
+      for (int qd = q0; qd < q1; qd++) {
+        ctl_forward(I, t, P.dec[qd], tmem);
+        // the first operands of decoder qd have arrived => decoder qd-1 is finished: its header buffer is free for decoder qd+1 -- but the
+        // issue point after the whole decoder is just as good for a 3 KB load that is needed one decoder later
+        if (qd + 1 < q1) load_header(P, t, P.dec[qd + 1], (qd + 1 - q0) & 1);
+      }
+    }
+    __syncwarp();
+  } else {
+    uint32_t n = 0;
+    for (int qd = q0; qd < q1; qd++) {
+      const int lv = P.dec[qd];
+      float out[4];
+      uint32_t* gm = (P.fo.masks != nullptr && row < npts) ? P.fo.masks + ((gp0 + row) * 15 + qd * 5) : nullptr;
+      const int dq = qd - q0;
+      epi_forward(P, t, lv, G, tmem, n, dq & 1, (dq >> 1) & 1u, out, gm);
+      if (lv == 3) { c0 = out[0]; c1 = out[1]; c2 = out[2]; } else occ += out[0];
+      if (qd == 0 && cg == 0 && row < npts && P.fo.corner_idx != nullptr) {
+        const nsb_grid& g = P.in.grid[lv];
+        const Tri tr = make_tri(lv == 0 ? G.xnc : G.xn, g.W, g.H, g.D);
+        const long long gp = gp0 + row;
+        P.fo.corner_idx[3 * gp] = tr.i0[0]; P.fo.corner_idx[3 * gp + 1] = tr.i0[1]; P.fo.corner_idx[3 * gp + 2] = tr.i0[2];
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+
+  if (points) {                                                   // Renderer.eval_points: raw with the out-of-bound override
+    if (epi && cg == 0 && row < npts) *reinterpret_cast<float4*>(P.points_raw + 4 * (gp0 + row)) = make_float4(c0, c1, c2, G.inb ? occ : 100.0f);
+    return;
+  }
+  if (epi && cg == 0 && row < npts) P.tile_parts[(long long)my * NP + gp0 + row] = make_float4(c0, c1, c2, occ);
+  const int nd = complete_rays(P.ray_cnt, ray_lo, nr, S, nsplit, s_done, &s_ndone);
+  for (int k = warp; k < nd; k += kThreads / 32) composite_ray(P, s_done[k], lane, smem_raw + (size_t)warp * composite_scratch_bytes(S));
+  // loss seeds: the last CTA of the grid to get here sees every ray composited
+  if (P.fs.kind != 0 && grid_last_arrival(P.fs.counter, gridDim.x, &s_last)) {
+    if (P.fs.kind == 1) {
+      PeerX px; px.rank = 0; px.world = 0; px.counter = nullptr; px.max_n = 0;
+      tracking_seeds_body(P.fo.depth, P.fo.var, P.fo.rgb, P.in.gt_depth, static_cast<const double*>(P.fs.gt_rgb), P.in.n_rays, P.fs.w_color,
+                          P.fs.handle_dynamic, P.fs.use_color, nullptr, 0, P.fs.g_depth, P.fs.g_rgb, P.fs.loss, P.fs.res, px, smem_raw);
+    } else {
+      mapping_seeds_body(P.fo.depth, P.fo.rgb, P.fs.gt_depth_loss, static_cast<const float*>(P.fs.gt_rgb), P.in.n_rays, P.fs.w_color, P.fs.use_color,
+                         P.fs.g_depth, P.fs.g_rgb, P.fs.loss, smem_raw);
+    }
+  }
+}
+
+// ================================================================================================================================
+// backward kernel (input gradients: rays + grid voxels)
+// ================================================================================================================================
+namespace tl {
+struct BwdExtra {            // behind the common shared-memory part
+  double dp[TM * 3];
+  double z[TM];
+  float gocc[TM];
+  float wgt[TM];
+  float gc[kMaxTileRays * 3];
+};
+}  // namespace tl
+
+__global__ void __maxnreg__(112) render_bwd_tile_kernel(const __grid_constant__ KParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  using namespace tl;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = tid & (TM - 1), cg = tid >> 7;
+  const bool epi = warp < kCtlWarp;
+  TileSmem t; carve(smem_raw, t, true);
+  BwdExtra& X = *reinterpret_cast<BwdExtra*>(t.extra);
+  __shared__ int s_ndone, s_done[kMaxTileRays];
+
+  const int nsplit = P.split;
+  const int tile = blockIdx.x / nsplit, my = blockIdx.x - tile * nsplit;
+  const int q0 = nsplit > 1 ? my : 0, q1 = nsplit > 1 ? my + 1 : P.n_dec;
+  const int S = P.S;
+  const long long NP = (long long)P.in.n_rays * S;
+  const long long gp0 = (long long)tile * TM;
+  const int npts = (int)(NP - gp0 < TM ? NP - gp0 : TM);
+  const int ray_lo = (int)(gp0 / S), nr = (int)((gp0 + npts - 1) / S) - ray_lo + 1;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(t.tmem)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  Issuer I; I.L.P = &P; I.L.q = q0; I.L.q1 = q1; I.L.k = 0; I.L.loaded = 0; I.L.bwd = true; I.issued = 0; I.g = 0;
+  if (tid == kEpiThreads) {
+    for (int i = 0; i < kNumBars; i++) mbar_init(t.bars + i, (i == B_AREADY || i == B_AREADY + 1) ? kEpiThreads : 1);
+    mbar_fence_init();
+    load_header(P, t, P.dec[q0], 0);
+    for (int i = 0; i < kSlots; i++) loader_issue(I.L, t);
+  }
+
+  // ---- prologue: per ray of this tile, compositing weights and dL/d(occupancy logit); scratch in the operand buffers
+  for (int i = tid; i < TM * 3; i += kThreads) X.dp[i] = 0.0;
+  for (int r = warp; r < nr; r += kThreads / 32) {
+    const int ray = ray_lo + r;
+    float* rw = t.a[0] + (size_t)warp * ((6 * S + 3) & ~3);       // per warp (16-byte aligned): raw [4S] | w [S] | go [S]
+    float* wq = rw + 4 * S; float* go = wq + S;
+    const long long g0 = (long long)ray * S;
+    float o[3], d[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) { o[a] = P.in.rays_o[3 * ray + a]; d[a] = P.in.rays_d[3 * ray + a]; }
+    for (int s = lane; s < S; s += 32) *reinterpret_cast<float4*>(rw + 4 * s) = *reinterpret_cast<const float4*>(P.bw.raw + 4 * (g0 + s));
+    __syncwarp();
+    const double gD = P.bw.g_depth != nullptr ? P.bw.g_depth[ray] : 0.0;
+    const double gV = P.bw.g_var != nullptr ? P.bw.g_var[ray] : 0.0;
+    float g3[3] = {0.f, 0.f, 0.f};
+    if (P.bw.g_rgb != nullptr) { g3[0] = P.bw.g_rgb[3 * ray]; g3[1] = P.bw.g_rgb[3 * ray + 1]; g3[2] = P.bw.g_rgb[3 * ray + 2]; }
+    if (lane == 0) { X.gc[3 * r] = g3[0]; X.gc[3 * r + 1] = g3[1]; X.gc[3 * r + 2] = g3[2]; }
+    ray_weights(rw, S, lane, wq, go);                            // go[] temporarily holds T_s
+    __syncwarp();
+    const double* z = P.bw.z_vals + g0;
+    double Dm = 0.0;
+    for (int s = lane; s < S; s += 32) Dm += (double)wq[s] * z[s];
+    Dm = warp_sum(Dm);
+    double swt = 0.0;
+    for (int s = lane; s < S; s += 32) swt += (double)wq[s] * (z[s] - Dm);
+    swt = warp_sum(swt);
+    const double gDe = gD + gV * (-2.0 * swt);
+    float carry = 0.0f;
+    const int nblk = (S + 31) / 32;
+    for (int b = nblk - 1; b >= 0; b--) {
+      const int s = b * 32 + lane;
+      const bool v = s < S;
+      float gw = 0.0f, al = 0.0f, T = 0.0f, w = 0.0f;
+      if (v) {
+        al = sigmoid_f(10.0f * rw[4 * s + 3]); T = go[s]; w = wq[s];
+        const double tt = z[s] - Dm;
+        gw = (float)(gDe * z[s] + gV * tt * tt) + g3[0] * rw[4 * s] + g3[1] * rw[4 * s + 1] + g3[2] * rw[4 * s + 2];
+      }
+      const float incl = warp_incl_suffix_sum(gw * w, lane);
+      float excl = __shfl_down_sync(0xffffffffu, incl, 1);
+      if (lane == 31) excl = 0.0f;
+      const float R = carry + excl;
+      if (v) {
+        const long long gp = g0 + s;
+        if (gp >= gp0 && gp < gp0 + npts) {                      // only the samples of this tile are needed
+          PointGeom Gs; make_point(P.in.bound, P.in.coarse_bound, o, d, z[s], Gs);
+          const float qd = (1.0f - al) + 1e-10f;
+          const float ga = T * gw - R / qd;
+          X.gocc[gp - gp0] = Gs.inb ? 10.0f * al * (1.0f - al) * ga : 0.0f;
+          X.wgt[gp - gp0] = w;
+        }
+      }
+      carry += __shfl_sync(0xffffffffu, incl, 0);
+    }
+  }
+  PointGeom G;
+  const int lp = row < npts ? row : npts - 1;
+  const long long gpr = gp0 + lp;
+  const int rayr = (int)(gpr / S);
+  {
+    float o[3], d[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) { o[a] = P.in.rays_o[3 * rayr + a]; d[a] = P.in.rays_d[3 * rayr + a]; }
+    const double z = P.bw.z_vals[gpr];
+    make_point(P.in.bound, P.in.coarse_bound, o, d, z, G);
+    if (epi && cg == 0) X.z[row] = z;
+  }
+  tc::tc_fence_before();
+  __syncthreads();                                                // prologue scratch dead, gocc / wgt / gc visible, TMEM address + barriers visible
+  tc::tc_fence_after();
+  const uint32_t tmem = *t.tmem;
+
+  if (!epi) {
+    if (lane == 0) {
+      for (int qd = q0; qd < q1; qd++) {
+        ctl_backward(I, t, P.dec[qd], tmem);
+        if (qd + 1 < q1) load_header(P, t, P.dec[qd + 1], (qd + 1 - q0) & 1);
+      }
+    }
+    __syncwarp();
+  } else {
+    uint32_t n = 0;
+    for (int qd = q0; qd < q1; qd++) {
+      const int lv = P.dec[qd];
+      const uint32_t* gm = P.bw.masks + ((gp0 + lp) * 15 + P.dec_pos[qd] * 5);
+      float g_out[4] = {0.f, 0.f, 0.f, 0.f};
+      if (row < npts) {
+        if (lv == 3) { const float w = X.wgt[row]; const float* gc = X.gc + 3 * (rayr - ray_lo); g_out[0] = w * gc[0]; g_out[1] = w * gc[1]; g_out[2] = w * gc[2]; }
+        else g_out[0] = X.gocc[row];
+      }
+      const int dq = qd - q0;
+      epi_backward(P, t, lv, G, tmem, n, dq & 1, (dq >> 1) & 1u, g_out, gm);
+      epi_sync();                                                 // dL/dc rows + embedding partials visible
+      const double* bb = lv == 0 ? P.in.coarse_bound : P.in.bound;
+      const double sc[3] = {2.0 / (bb[1] - bb[0]), 2.0 / (bb[3] - bb[2]), 2.0 / (bb[5] - bb[4])};      // d(normalised)/dp, common.py:280-282
+      const float* xn = lv == 0 ? G.xnc : G.xn;
+      scatter_tile(P.in.grid[lv], P.bw.d_grid[lv], P.bw.slot_map[lv], t.a[0], op_cd(lv), xn, warp, lane, [&](int prow, const float gx[3]) {
+        if (prow < npts) {
+          const float4 p0 = *reinterpret_cast<const float4*>(t.a[1] + prow * 4);
+          const float4 p1 = *reinterpret_cast<const float4*>(t.a[1] + (TM + prow) * 4);
+          const float dpe[3] = {p0.x + p1.x, p0.y + p1.y, p0.z + p1.z};
+#pragma unroll
+          for (int a = 0; a < 3; a++) X.dp[3 * prow + a] += (double)dpe[a] + (double)gx[a] * sc[a];
+        }
+      });
+      epi_sync();                                                 // reads of a[0] / a[1] done before the next decoder overwrites them
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+
+  // per-ray sums of this item: d rays_o = sum_s dp, d rays_d = sum_s z_s dp (pts = o + d z, Renderer.py:172-174) -> global scratch
+  const int RT = P.tile_rays;                                     // rays a tile can touch: stride of the per-item parts
+  double* parts = P.ray_parts + ((long long)tile * nsplit + my) * RT * 6;
+  for (int i = tid; i < nr * 3; i += kThreads) {
+    const int r = i / 3, a = i - 3 * r;
+    const long long g0 = (long long)(ray_lo + r) * S;
+    const int s0 = (int)(g0 > gp0 ? g0 - gp0 : 0), s1 = (int)(g0 + S - gp0 < npts ? g0 + S - gp0 : npts);
+    double so = 0.0, sd = 0.0;
+    for (int p = s0; p < s1; p++) { const double v = X.dp[3 * p + a]; so += v; sd += v * X.z[p]; }
+    parts[r * 6 + a] = so; parts[r * 6 + 3 + a] = sd;
+  }
+  const int nd = complete_rays(P.ray_cnt, ray_lo, nr, S, nsplit, s_done, &s_ndone);
+  for (int i = tid; i < nd * 3; i += kThreads) {                  // the completing CTA adds the parts in (tile, decoder) order
+    const int ray = s_done[i / 3], a = i % 3;
+    const long long p0 = (long long)ray * S;
+    const int t0 = (int)(p0 / TM), t1 = (int)((p0 + S - 1) / TM);
+    double so = 0.0, sd = 0.0;
+    for (int tt = t0; tt <= t1; tt++) {
+      const int rl = (int)(((long long)tt * TM) / S);
+      for (int q = 0; q < nsplit; q++) {
+        const double* pp = P.ray_parts + (((long long)tt * nsplit + q) * RT + (ray - rl)) * 6;
+        so += __ldcg(pp + a); sd += __ldcg(pp + 3 + a);
+      }
+    }
+    if (P.accumulate_rays) {
+      if (P.bw.d_rays_o != nullptr) so += (double)P.bw.d_rays_o[3 * ray + a];
+      if (P.bw.d_rays_d != nullptr) sd += (double)P.bw.d_rays_d[3 * ray + a];
+    }
+    if (P.bw.d_rays_o != nullptr) P.bw.d_rays_o[3 * ray + a] = (float)so;
+    if (P.bw.d_rays_d != nullptr) P.bw.d_rays_d[3 * ray + a] = (float)sd;
+  }
+  fused_pose_grad(P, gridDim.x, reinterpret_cast<double*>(smem_raw));
+}
+
+}  // namespace nsb

@@ -307,7 +307,165 @@ def gen_mapper_loop_case():
                                 color_decoder=dec_final, w_color_loss=cfg["mapping"]["w_color_loss"]))
 
 
+def _ba_setup():
+    """Reference mapper with bundle adjustment on a window of 5 keyframes + the current frame (6 x 166 rays)."""
+    rh.import_reference()
+    sc, cfg, slam, renderer = ref_scene("room0", "soft")
+    mapper = rh.make_mapper(cfg, slam, renderer, coarse_mapper=False, BA=True)
+    mapper.mapping_window_size = 6                  # 4 overlap-selected keyframes + the last keyframe + the current frame
+    mapper.keyframe_selection_method = "overlap"
+    kf_dict, kf_list = [], []
+    for k in range(5):
+        depth, color = su.make_frame(sc, 10 + k)
+        c2w = su.make_pose(sc, 10 + k)
+        gt = c2w.clone()
+        gt[:3, 3] += 0.01 * (k + 1)                 # est != gt, as in a real run (gt is only logged)
+        kf_dict.append(dict(gt_c2w=gt, idx=5 * k, color=color, depth=depth, est_c2w=c2w.clone()))
+        kf_list.append(5 * k)
+    mapper.keyframe_dict, mapper.keyframe_list = kf_dict, kf_list
+    depth, color = su.make_frame(sc, 1)
+    c2w = su.make_pose(sc, 1)
+    return sc, cfg, slam, renderer, mapper, kf_dict, kf_list, depth, color, c2w
+
+
+def _record_ba(mapper_mod, samples, uv):
+    """Wrap get_samples / get_sample_uv of src.Mapper / src.common so that every per-frame draw is recorded."""
+    import src.common as common_mod
+    _gs, _guv = mapper_mod.get_samples, common_mod.get_sample_uv
+
+    def get_sample_uv_rec(*a, **k):
+        r = _guv(*a, **k)
+        uv.append((r[0].detach().clone(), r[1].detach().clone()))
+        return r
+
+    def get_samples_rec(*a, **k):
+        n0 = len(uv)
+        r = _gs(*a, **k)
+        samples.append(dict(rays_o=r[0].detach().clone(), rays_d=r[1].detach().clone(), depth=r[2].detach().clone(), color=r[3].detach().clone(),
+                            i=uv[n0][0], j=uv[n0][1], c2w=a[11].detach().clone()))
+        return r
+    mapper_mod.get_samples = get_samples_rec
+    common_mod.get_sample_uv = get_sample_uv_rec
+
+    def restore():
+        mapper_mod.get_samples, common_mod.get_sample_uv = _gs, _guv
+    return restore
+
+
+def gen_mapper_ba_cases():
+    """(a) mapper_ba_grads.pt: one window of REAL Mapper.optimize_map iterations with BA=True whose optimiser only records (no updates):
+    per stage the ray batch at the renderer boundary, the frame of every ray, and every gradient incl. camera_tensor.grad of the five
+    non-fixed frames.  (b) mapper_ba_loop.pt: eight real iterations with the real torch.optim.Adam (4 x middle, fine, 3 x color): the pixel
+    draws of every frame and iteration, and what the mapper leaves behind (poses of the window, selected voxels, colour decoder)."""
+    ref = rh.import_reference()
+    import src.Mapper as mapper_mod
+    # ---------------------------------------------------------------- (a) gradients
+    sc, cfg, slam, renderer, mapper, kf_dict, kf_list, depth, color, c2w = _ba_setup()
+    calls = record_renderer(renderer)
+    samples, uv = [], []
+    restore = _record_ba(mapper_mod, samples, uv)
+    RecOptim.instances.clear()
+    _adam = torch.optim.Adam
+    torch.optim.Adam = RecOptim
+    try:
+        torch.manual_seed(777); np.random.seed(777)
+        mapper.optimize_map(5, 1.0, 30, color, depth, c2w, kf_dict, kf_list, c2w)
+    finally:
+        torch.optim.Adam = _adam
+        restore()
+    opt = RecOptim.instances[-1]
+    sel = samples[:1]                                  # first get_samples call = keyframe_selection_overlap's own draw
+    per_it = [samples[1 + 6 * it: 1 + 6 * (it + 1)] for it in range(5)]
+    assert len(samples) == 1 + 6 * 5 and len(opt.param_groups) == 6 and len(opt.param_groups[5]["params"]) == 5
+    masks = {}
+    for key, val in slam.shared_c.items():
+        m = mapper.get_mask_from_c2w(c2w, key, val.shape[2:], depth.numpy())
+        masks[key] = torch.from_numpy(np.ascontiguousarray(m)).permute(2, 1, 0).contiguous()
+    # window order and which frame is fixed: re-derive from the recorded per-frame poses of iteration 0
+    frames_c2w = [s["c2w"][:3] for s in per_it[0]]
+    cases = {}
+    names = ["decoders", "grid_coarse", "grid_middle", "grid_fine", "grid_color", "cameras"]
+    for it in (0, 3, 4):
+        call = calls[it]
+        fr = per_it[it]
+        ro = torch.cat([f["rays_o"].float() for f in fr]); rd = torch.cat([f["rays_d"].float() for f in fr])
+        gd = torch.cat([f["depth"].float() for f in fr]); gc = torch.cat([f["color"].float() for f in fr])
+        fid = torch.cat([torch.full((f["rays_o"].shape[0],), k, dtype=torch.int32) for k, f in enumerate(fr)])
+        keep = tp.bbox_prefilter(ro, rd, gd, slam.bound)
+        assert torch.equal(ro[keep], call["rays_o"]) and torch.equal(rd[keep], call["rays_d"])
+        grads = {}
+        for gi, nm in enumerate(names):
+            gl = opt.steps[it][gi]
+            if nm == "decoders":
+                pn = [k for k, _ in slam.shared_decoders.color_decoder.named_parameters()]
+                grads["color_decoder"] = {k: g for k, g in zip(pn, gl) if g is not None}
+            elif nm == "cameras":
+                grads["cameras"] = torch.stack([g if g is not None else torch.zeros(7) for g in gl])
+            elif gl and gl[0] is not None:
+                grads[nm] = su.grid_summary(gl[0], n_sample=4096)
+        cases[call["stage"]] = dict(rays_o=call["rays_o"], rays_d=call["rays_d"], gt_depth=call["gt_depth"], gt_depth_loss=gd[keep], gt_color=gc[keep],
+                                    frame_of_ray=fid[keep], pix_i=torch.cat([f["i"] for f in fr])[keep], pix_j=torch.cat([f["j"] for f in fr])[keep],
+                                    depth=call["depth"], rgb=call["rgb"], d_cameras=grads.pop("cameras"), d_color_decoder=grads.pop("color_decoder"),
+                                    masked_grads=grads)
+    cam0 = torch.stack([p.detach().clone() for p in opt.param_groups[5]["params"]])
+    save("mapper_ba_grads.pt", dict(scene="room0", variant="soft", frame_seed=1, pose_seed=1, keyframe_seeds=list(range(10, 15)), masks=masks,
+                                    window_c2w=torch.stack(frames_c2w), camera_tensors=cam0, stages=cases,
+                                    selection_pixels=dict(i=sel[0]["i"], j=sel[0]["j"])))
+    # ---------------------------------------------------------------- (b) real Adam, poses move
+    sc, cfg, slam, renderer, mapper, kf_dict, kf_list, depth, color, c2w = _ba_setup()
+    samples, uv = [], []
+    restore = _record_ba(mapper_mod, samples, uv)
+    start = {k: v.detach().clone() for k, v in slam.shared_c.items()}
+    n_it = 8
+    cam_hist = []
+    _adam = torch.optim.Adam
+
+    class SpyAdam(_adam):                              # the real Adam; only looks at the pose group before every step
+        def step(self, *a, **k):
+            cams = self.param_groups[5]["params"]
+            cam_hist.append(dict(cam=torch.stack([c.detach().clone() for c in cams]), grad=torch.stack([c.grad.detach().clone() for c in cams])))
+            return super().step(*a, **k)
+    torch.optim.Adam = SpyAdam
+    try:
+        torch.manual_seed(777); np.random.seed(777)
+        new_c2w = mapper.optimize_map(n_it, 1.0, 30, color, depth, c2w, kf_dict, kf_list, c2w)
+    finally:
+        torch.optim.Adam = _adam
+        restore()
+    per_it = [samples[1 + 6 * it: 1 + 6 * (it + 1)] for it in range(n_it)]
+    window0 = torch.stack([s["c2w"][:3] for s in per_it[0]])        # poses the window started from (row order = optimize_frame order)
+    draws = [dict(i=torch.stack([f["i"] for f in fr]), j=torch.stack([f["j"] for f in fr]),
+                  depth=torch.stack([f["depth"].float() for f in fr]), color=torch.stack([f["color"].float() for f in fr])) for fr in per_it]
+    # which keyframe each window row is: match the starting poses against the keyframe poses
+    ident = []
+    for r in range(6):
+        hit = [k for k in range(5) if torch.allclose(su.make_pose(sc, 10 + k)[:3], window0[r][:3], atol=1e-5)]
+        ident.append(hit[0] if hit else -1)
+    final_c2w = torch.stack([(kf_dict[k]["est_c2w"] if k >= 0 else new_c2w)[:3].detach().clone() for k in ident])
+    final = {}
+    for key in ("grid_middle", "grid_fine", "grid_color"):
+        m = mapper.get_mask_from_c2w(c2w, key, slam.shared_c[key].shape[2:], depth.numpy())
+        vm = torch.from_numpy(np.ascontiguousarray(m)).permute(2, 1, 0).contiguous()
+        m5 = vm.unsqueeze(0).unsqueeze(0).expand_as(slam.shared_c[key])
+        after, before = slam.shared_c[key][m5].detach().clone(), start[key][m5]
+        g = torch.Generator().manual_seed(99)
+        pick = torch.randperm(after.numel(), generator=g)[:8192].clone()
+        final[key] = dict(idx=pick, val=after[pick].clone(), delta_norm=float((after - before).double().norm()), norm=float(after.double().norm()))
+    stages = ["middle" if it <= int(n_it * mapper.middle_iter_ratio) else ("fine" if it <= int(n_it * mapper.fine_iter_ratio) else "color") for it in range(n_it)]
+    lrs = [dict(decoders=cfg["mapping"]["stage"][s]["decoders_lr"], middle=cfg["mapping"]["stage"][s]["middle_lr"], fine=cfg["mapping"]["stage"][s]["fine_lr"],
+                color=cfg["mapping"]["stage"][s]["color_lr"]) for s in stages]
+    save("mapper_ba_loop.pt", dict(scene="room0", variant="soft", frame_seed=1, pose_seed=1, keyframe_seeds=list(range(10, 15)), window_keyframes=ident,
+                                   window_c2w=window0.clone(), final_c2w=final_c2w, camera_tensors=cam_hist[0]["cam"], camera_history=cam_hist, stages=stages, lrs=lrs, BA_cam_lr=cfg["mapping"]["BA_cam_lr"],
+                                   draws=draws, final=final, color_decoder={k: v.detach().clone() for k, v in slam.shared_decoders.color_decoder.state_dict().items()},
+                                   w_color_loss=cfg["mapping"]["w_color_loss"]))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "mapper_ba":
+        import warnings
+        warnings.filterwarnings("ignore")
+        gen_mapper_ba_cases()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "mapper_loop":
         import warnings
         warnings.filterwarnings("ignore")
@@ -322,3 +480,4 @@ if __name__ == "__main__":
     gen_tracker_case()
     gen_mapper_cases()
     gen_mapper_loop_case()
+    gen_mapper_ba_cases()

@@ -178,3 +178,100 @@ def test_oracle_reproduces_five_real_mapper_iterations_with_adam():
         assert torch.allclose(got, fin["val"], rtol=1e-5, atol=1e-6), (k, float((got - fin["val"]).abs().max()))
     for k, v in case["color_decoder"].items():
         assert torch.allclose(dw["color"][k].detach(), v, rtol=1e-5, atol=1e-6), k
+
+
+def _ba_fixed_row(case_window_c2w, cams):
+    """The window row that has no camera tensor (the oldest frame, Mapper.py:350): the one whose pose no tensor reproduces."""
+    poses = tp.camera_from_tensor(cams)
+    for r in range(case_window_c2w.shape[0]):
+        if not any(torch.allclose(poses[k], case_window_c2w[r], atol=1e-5) for k in range(poses.shape[0])):
+            return r
+    raise AssertionError("no fixed row")
+
+
+@pytest.mark.parametrize("stage", ["middle", "fine", "color"])
+def test_oracle_reproduces_ba_window_gradients(stage):
+    """tests/golden/mapper_ba_grads.pt: REAL Mapper.optimize_map with BA=True on a window of 5 keyframes + the current frame
+    (src/Mapper.py:346-363,437-467).  The oracle chain camera tensor -> c2w -> rays -> render -> loss reproduces camera_tensor.grad of
+    every non-fixed frame, the masked voxel gradients and the colour-decoder gradients."""
+    case = torch.load(os.path.join(su.GOLDEN, "mapper_ba_grads.pt"), map_location="cpu", weights_only=False)
+    sc = su.load_scenes()[case["scene"]]
+    grids, dec, bound = su.make_grids(sc, case["variant"]), su.load_decoders(case["variant"]), su.scene_bound(sc)
+    cam = sc["cam"]
+    st = case["stages"][stage]
+    cams = case["camera_tensors"].clone().requires_grad_(True)
+    fixed = _ba_fixed_row(case["window_c2w"], case["camera_tensors"])
+    ro, rd = tp.ba_window_rays(cams, case["window_c2w"][fixed], fixed, st["pix_i"], st["pix_j"], st["frame_of_ray"], cam["fx"], cam["fy"], cam["cx"], cam["cy"])
+    assert torch.equal(ro.detach(), st["rays_o"]) and torch.equal(rd.detach(), st["rays_d"])          # ray generation is bit-exact
+    keys = {"middle": ("grid_middle",), "fine": ("grid_middle", "grid_fine"), "color": ("grid_middle", "grid_fine", "grid_color")}[stage]
+    g = {k: v.clone().requires_grad_(k in keys) for k, v in grids.items()}
+    dw = {n: {k: v.clone().requires_grad_(n == "color") for k, v in W.items()} for n, W in dec.items()}
+    d, _, col = tp.render_batch_ray(g, dw, rd, ro, stage, st["gt_depth"], bound)
+    assert torch.equal(d.detach(), st["depth"]) and torch.equal(col.detach(), st["rgb"])
+    tp.mapping_loss(d, col, st["gt_depth_loss"], st["gt_color"], stage).backward()
+    assert rel(cams.grad, st["d_cameras"]) < 1e-5, rel(cams.grad, st["d_cameras"])
+    assert float(st["d_cameras"].abs().min()) > 0                                                  # every non-fixed frame gets a gradient
+    for k, summ in st["masked_grads"].items():
+        m = case["masks"][k]
+        mine = su.grid_summary(g[k].grad[m.unsqueeze(0).unsqueeze(0).expand_as(g[k])], n_sample=4096)
+        assert mine["nnz"] == summ["nnz"] and torch.allclose(mine["val"], summ["val"], rtol=1e-5, atol=1e-9), k
+    for k, v in st["d_color_decoder"].items():
+        assert torch.allclose(dw["color"][k].grad, v, rtol=1e-4, atol=1e-7), k
+
+
+def test_oracle_reproduces_ba_loop_with_adam():
+    """tests/golden/mapper_ba_loop.pt: eight REAL joint iterations with bundle adjustment and the real torch Adam (4 x middle, fine, 3 x color;
+    the pose group has lr = BA_cam_lr in stage color only, Mapper.py:417-424, but its Adam state advances in every iteration).  Replayed with
+    the oracle: per-iteration rays regenerated from the CURRENT camera tensors and the recorded pixel draws, bbox pre-filter, masked leaf
+    voxels, port render + loss, torch Adam with the six parameter groups.  Checks the poses the mapper wrote back (Mapper.py:521-540)."""
+    from oracle import frustum as fr
+    case = torch.load(os.path.join(su.GOLDEN, "mapper_ba_loop.pt"), map_location="cpu", weights_only=False)
+    sc = su.load_scenes()[case["scene"]]
+    cam = sc["cam"]
+    grids, dec = su.make_grids(sc, case["variant"]), su.load_decoders(case["variant"])
+    depth, _ = su.make_frame(sc, case["frame_seed"])
+    c2w_cur = su.make_pose(sc, case["pose_seed"])
+    bound = su.scene_bound(sc)
+    keys = ("grid_middle", "grid_fine", "grid_color")
+    m5 = {k: fr.frustum_mask(c2w_cur, k, tuple(grids[k].shape[2:]), depth.numpy(), bound, sc["cam"]).unsqueeze(0).unsqueeze(0).expand_as(grids[k])
+          for k in keys}
+    val_grad = {k: grids[k][m5[k]].clone().requires_grad_(True) for k in keys}
+    dw = {n: {k: v.clone().requires_grad_(n == "color") for k, v in W.items()} for n, W in dec.items()}
+    win = case["window_keyframes"]
+    fixed = win.index(min(k for k in win if k >= 0))                       # oldest keyframe of the window is fixed (Mapper.py:262,350)
+    # start from the camera tensors the reference derived from the keyframes' est_c2w (get_tensor_from_camera, src/common.py:179-200): the L1
+    # losses make the pose gradients discontinuous, so a 1e-8 difference in the starting quaternion shows up at the 1e-4 level in the gradients
+    cams = [case["camera_tensors"][k].clone().requires_grad_(True) for k in range(5)]
+    opt = torch.optim.Adam([{"params": list(dw["color"].values()), "lr": 0}, {"params": [], "lr": 0}] + [{"params": [val_grad[k]], "lr": 0} for k in keys]
+                           + [{"params": cams, "lr": 0}])
+    for it, (stage, lr, dr) in enumerate(zip(case["stages"], case["lrs"], case["draws"])):
+        opt.param_groups[0]["lr"] = lr["decoders"]
+        for gi, k in enumerate(keys):
+            opt.param_groups[2 + gi]["lr"] = lr[k[5:]]
+        if stage == "color":
+            opt.param_groups[5]["lr"] = case["BA_cam_lr"]
+        g = {k: v.clone() for k, v in grids.items()}
+        for k in keys:
+            g[k][m5[k]] = val_grad[k]
+        opt.zero_grad()
+        n = dr["i"].shape[1]
+        fid = torch.arange(6).repeat_interleave(n)
+        ro, rd = tp.ba_window_rays(torch.stack(cams), case["window_c2w"][fixed], fixed, dr["i"].reshape(-1), dr["j"].reshape(-1), fid,
+                                   cam["fx"], cam["fy"], cam["cx"], cam["cy"])
+        gd, gc = dr["depth"].reshape(-1), dr["color"].reshape(-1, 3)
+        keep = tp.bbox_prefilter(ro, rd, gd, bound)
+        d, _, col = tp.render_batch_ray(g, dw, rd[keep], ro[keep], stage, gd[keep], bound)
+        tp.mapping_loss(d, col, gd[keep], gc[keep], stage, case["w_color_loss"]).backward()
+        hist = case["camera_history"][it]
+        assert rel(torch.stack([c.detach() for c in cams]), hist["cam"]) < 1e-6 and rel(torch.stack([c.grad for c in cams]), hist["grad"]) < 1e-4, it
+        opt.step()
+        for k in keys:
+            grids[k][m5[k]] = val_grad[k].detach()
+    got = tp.camera_from_tensor(torch.stack([c.detach() for c in cams]))
+    want = torch.stack([case["final_c2w"][r] for r in range(6) if r != fixed])
+    moved = (want - torch.stack([case["window_c2w"][r] for r in range(6) if r != fixed])).abs().amax((1, 2))
+    assert float(moved.min()) > 5e-4                                       # the poses did move
+    assert float((got - want).abs().max()) < 2e-5, float((got - want).abs().max())
+    for k, fin in case["final"].items():
+        gotv = val_grad[k].detach()[fin["idx"]]
+        assert torch.allclose(gotv, fin["val"], rtol=1e-4, atol=2e-5), (k, float((gotv - fin["val"]).abs().max()))
