@@ -228,6 +228,21 @@ int nsb_frustum_mask(const float* c2w, const float* xs, const float* ys, const f
 int nsb_pose_grad_frames(const float* dirs, const float* d_rays_o, const float* d_rays_d, const int32_t* frame_offsets,
                          int n_frames, float* out, void* stream);
 
+/* ---- bundle-adjustment window (src/Mapper.py:346-363 camera tensors, :437-467 per-frame get_samples, :521-540 write-back) -----------------
+ * A window has n_frames rows (the selected keyframes + the current frame).  Row f is either optimised -- its pose is camera tensor
+ * cams[cam_row[f]] = [qw,qx,qy,qz,tx,ty,tz] (get_tensor_from_camera, src/common.py:179-200) -- or fixed (cam_row[f] = -1: the oldest frame,
+ * Mapper.py:350; its pose is fixed_c2w[f], row-major [3][4]).
+ * nsb_window_rays: c2w_out[f] = get_camera_from_tensor(cams[cam_row[f]]) (quad2rotation, src/common.py:137-176) or fixed_c2w[f]; then for
+ * every ray r of frame frame_of_ray[r] at pixel (pix_i, pix_j): get_rays_from_uv (src/common.py:74-89) -> rays_o, rays_d and (optional)
+ * the camera-frame direction `dirs` that nsb_pose_grad_frames needs.  All float32, the reference's operation order.
+ * nsb_adam_poses: d_c2w[f] ([3][4] float32 per window row, from nsb_pose_grad_frames) is chained through quad2rotation to the gradient of
+ * the camera tensors (written to d_cams [n_cams][7] if non-NULL) and torch.optim.Adam's update is applied to `cams` in place. */
+int nsb_window_rays(const float* cams, const int32_t* cam_row, const float* fixed_c2w, int n_frames,
+                    const float* pix_i, const float* pix_j, const int32_t* frame_of_ray, int n_rays,
+                    double fx, double fy, double cx, double cy, float* c2w_out, float* rays_o, float* rays_d, float* dirs, void* stream);
+int nsb_adam_poses(float* cams, const int32_t* cam_row, int n_frames, const float* d_c2w, float* exp_avg, float* exp_avg_sq, float* d_cams,
+                   double lr, double beta1, double beta2, double eps, int step, void* stream);
+
 /* ---- exchanges of a ray-sharded tracking iteration through NVLink peer memory ---------------------------------
  * A batch sharded over `world` GPUs (equal shards) needs three batch-global quantities: max(gt_depth) (Renderer.py:109,144), the
  * median of the residuals (Tracker.py:113) and the sums of loss and pose gradient.  The *_peers variants of the three single-CTA

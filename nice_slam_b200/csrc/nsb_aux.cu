@@ -239,124 +239,18 @@ __global__ void tracking_seeds_kernel(const double* __restrict__ depth, const do
                                       int handle_dynamic, int use_color, const double* __restrict__ pool, int n_pool,
                                       double* __restrict__ g_depth, float* __restrict__ g_rgb,
                                       double* __restrict__ loss, double* __restrict__ res, const PeerX px) {
-  __shared__ double red[32];
-  __shared__ int hist[256];
-  __shared__ int wtot[8];
-  __shared__ int sel[2];
-  __shared__ unsigned long long keys[kMedianDirect];
-  __shared__ unsigned long long med_key;
-  __shared__ double med_s;
-  for (int i = threadIdx.x; i < n; i += blockDim.x)
-    res[i] = fabs((double)gt[i] - depth[i]) / sqrt(var[i] + 1e-10);
-  __syncthreads();
-  if (handle_dynamic) {
-    // torch.median = lower median = the element of rank (n-1)/2 of the IEEE bit patterns (residuals are non-negative, so the unsigned
-    // 64-bit pattern is order preserving; NaN sorts last like torch.sort).
-    const double* mp = pool != nullptr ? pool : res;       // sharded batches: median over the all-gathered residuals
-    int np = pool != nullptr ? n_pool : n;
-    int pool_pitch = 0;                                    // > 0: the pool is [world][pool_pitch] with n valid entries per rank
-    if (px.world > 1) {
-      // all-gather of the residuals through peer memory (channel 1): push this shard into block [parity][rank] of every peer's pool
-      __shared__ uint32_t s_seq;
-      const uint32_t seq = peer_begin(px, 1, &s_seq);
-      const int par = seq & 1u;
-      for (int i = threadIdx.x; i < n * px.world; i += blockDim.x) {
-        const int r = i / n, j = i - r * n;
-        __stcg(reinterpret_cast<double*>(px.peer[r] + kXPoolOff) + ((size_t)par * NSB_MAX_PEERS + px.rank) * px.max_n + j, res[j]);
-      }
-      peer_signal_wait(px, 1, kXPoolFlagOff, 16, seq);
-      mp = reinterpret_cast<const double*>(px.peer[px.rank] + kXPoolOff) + (size_t)par * NSB_MAX_PEERS * px.max_n;
-      np = n * px.world; pool_pitch = px.max_n;
-    }
-    auto pool_at = [&](int i) { return pool_pitch ? __ldcg(mp + (size_t)(i / n) * pool_pitch + (i % n)) : mp[i]; };
-    const int k = (np - 1) / 2;
-    if (np <= kMedianDirect) {
-      // small pools (a tracking batch is 200 rays): direct rank counting from shared memory, no serial passes
-      for (int i = threadIdx.x; i < np; i += blockDim.x) keys[i] = (unsigned long long)__double_as_longlong(pool_at(i));
-      __syncthreads();
-      for (int i = threadIdx.x; i < np; i += blockDim.x) {
-        const unsigned long long key = keys[i];
-        int less = 0, eq = 0;
-        for (int j = 0; j < np; j++) { const unsigned long long o = keys[j]; less += o < key ? 1 : 0; eq += o == key ? 1 : 0; }
-        if (less <= k && k < less + eq) med_key = key;     // every thread that qualifies writes the same value
-      }
-      __syncthreads();
-    } else {
-      // radix select, 8 bits per pass (8 passes, 256-bin shared histogram)
-      unsigned long long prefix = 0ull;
-      int kk = k;
-      for (int shift = 56; shift >= 0; shift -= 8) {
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
-        __syncthreads();
-        const unsigned long long maskhi = shift == 56 ? 0ull : (~0ull << (shift + 8));
-        for (int i = threadIdx.x; i < np; i += blockDim.x) {
-          const unsigned long long key = (unsigned long long)__double_as_longlong(pool_at(i));
-          if ((key & maskhi) == prefix) atomicAdd(&hist[(int)((key >> shift) & 0xffull)], 1);
-        }
-        __syncthreads();
-        // digit of the k-th key = the bin whose [exclusive, inclusive) prefix-count range contains kk (256 bins: 8 warps scan them)
-        {
-          const int v = threadIdx.x < 256 ? hist[threadIdx.x] : 0;
-          int incl = v;
-          for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += t; }
-          if (threadIdx.x < 256 && (threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = incl;
-          __syncthreads();
-          int before = 0;
-          for (int w = 0; w < (int)(threadIdx.x >> 5) && w < 8; w++) before += wtot[w];
-          incl += before;
-          if (threadIdx.x < 256 && incl - v <= kk && kk < incl) { sel[0] = (int)threadIdx.x; sel[1] = incl - v; }
-          __syncthreads();
-        }
-        prefix |= (unsigned long long)sel[0] << shift;
-        kk -= sel[1];
-        __syncthreads();
-      }
-      if (threadIdx.x == 0) med_key = prefix;
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) med_s = __longlong_as_double((long long)med_key);
-    __syncthreads();
-  }
-  double acc = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const double r = res[i];
-    bool m = gt[i] > 0.0f;
-    if (handle_dynamic) m = m && (r < 10.0 * med_s);
-    double gd = 0.0; float gc[3] = {0.f, 0.f, 0.f};
-    if (m) {
-      acc += r;
-      gd = -sgn((double)gt[i] - depth[i]) / sqrt(var[i] + 1e-10);
-      if (use_color) {
-#pragma unroll
-        for (int a = 0; a < 3; a++) { const double df = gt_rgb[3 * i + a] - (double)rgb[3 * i + a]; acc += w_color * fabs(df); gc[a] = (float)(-w_color * sgn(df)); }
-      }
-    }
-    g_depth[i] = gd; g_rgb[3 * i] = gc[0]; g_rgb[3 * i + 1] = gc[1]; g_rgb[3 * i + 2] = gc[2];
-  }
-  const double tot = block_sum(acc, red);
-  if (threadIdx.x == 0) loss[0] = tot;
+  __shared__ __align__(16) unsigned char scratch[kSeedsScratchBytes];
+  tracking_seeds_body(depth, var, rgb, gt, gt_rgb, n, w_color, handle_dynamic, use_color, pool, n_pool, g_depth, g_rgb, loss, res, px, scratch);
 }
 
 // Mapper.optimize_map loss (src/Mapper.py:487-493); single CTA (deterministic sum)
 __global__ void mapping_seeds_kernel(const double* __restrict__ depth, const float* __restrict__ rgb, const float* __restrict__ gt,
                                      const float* __restrict__ gt_rgb, int n, double w_color, int use_color,
                                      double* __restrict__ g_depth, float* __restrict__ g_rgb, double* __restrict__ loss) {
-  __shared__ double red[32];
-  double acc = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    double gd = 0.0;
-    if (gt[i] > 0.0f) { const double df = (double)gt[i] - depth[i]; acc += fabs(df); gd = -sgn(df); }
-    g_depth[i] = gd;
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-      float g = 0.0f;
-      if (use_color) { const float df = gt_rgb[3 * i + a] - rgb[3 * i + a]; acc += w_color * (double)fabsf(df); g = (float)(-w_color * sgn((double)df)); }
-      g_rgb[3 * i + a] = g;
-    }
-  }
-  const double tot = block_sum(acc, red);
-  if (threadIdx.x == 0) loss[0] = tot;
+  __shared__ __align__(16) unsigned char scratch[kSeedsScratchBytes];
+  mapping_seeds_body(depth, rgb, gt, gt_rgb, n, w_color, use_color, g_depth, g_rgb, loss, scratch);
 }
+
 
 // d c2w from ray gradients (single CTA, deterministic)
 __global__ void pose_grad_kernel(const float* __restrict__ dirs, const float* __restrict__ dro, const float* __restrict__ drd, int n,
@@ -712,6 +606,96 @@ extern "C" int nsb_adam_decoder(int level, const nsb_decoder_params* p, const fl
   add(p->Wo, 5, 0, no * kHid); add(p->bo, 6, 0, no);
   adam_flat_kernel<<<32, 256, 0, (cudaStream_t)stream>>>(T, grad_flat, exp_avg, exp_avg_sq, a);
   return check_cuda(cudaGetLastError(), "adam_decoder launch");
+}
+
+// ---- bundle-adjustment window: poses <-> rays (Mapper.py:346-363, :437-467, :521-540; common.py:74-89, :137-176) --------------------------
+// quad2rotation (src/common.py:137-160), float32, same expression order; c2w row-major [3][4]
+__device__ __forceinline__ void cam_to_c2w(const float* __restrict__ cam, float* __restrict__ m) {
+  const float qr = cam[0], qi = cam[1], qj = cam[2], qk = cam[3];
+  const float nn = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(qr, qr), __fmul_rn(qi, qi)), __fmul_rn(qj, qj)), __fmul_rn(qk, qk));
+  const float s = __fdiv_rn(2.0f, nn);
+  m[0] = __fsub_rn(1.0f, __fmul_rn(s, __fadd_rn(__fmul_rn(qj, qj), __fmul_rn(qk, qk))));
+  m[1] = __fmul_rn(s, __fsub_rn(__fmul_rn(qi, qj), __fmul_rn(qk, qr)));
+  m[2] = __fmul_rn(s, __fadd_rn(__fmul_rn(qi, qk), __fmul_rn(qj, qr)));
+  m[4] = __fmul_rn(s, __fadd_rn(__fmul_rn(qi, qj), __fmul_rn(qk, qr)));
+  m[5] = __fsub_rn(1.0f, __fmul_rn(s, __fadd_rn(__fmul_rn(qi, qi), __fmul_rn(qk, qk))));
+  m[6] = __fmul_rn(s, __fsub_rn(__fmul_rn(qj, qk), __fmul_rn(qi, qr)));
+  m[8] = __fmul_rn(s, __fsub_rn(__fmul_rn(qi, qk), __fmul_rn(qj, qr)));
+  m[9] = __fmul_rn(s, __fadd_rn(__fmul_rn(qj, qk), __fmul_rn(qi, qr)));
+  m[10] = __fsub_rn(1.0f, __fmul_rn(s, __fadd_rn(__fmul_rn(qi, qi), __fmul_rn(qj, qj))));
+  m[3] = cam[4]; m[7] = cam[5]; m[11] = cam[6];
+}
+// poses of the window rows: row f uses camera tensor cam_row[f] (>= 0) or, for the fixed oldest frame (-1), fixed_c2w[f]
+__global__ void window_poses_kernel(const float* __restrict__ cams, const int32_t* __restrict__ cam_row, const float* __restrict__ fixed_c2w,
+                                    int n_frames, float* __restrict__ c2w_out) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_frames) return;
+  float m[12];
+  if (cam_row[f] >= 0) cam_to_c2w(cams + 7 * cam_row[f], m);
+  else for (int k = 0; k < 12; k++) m[k] = fixed_c2w[12 * f + k];
+  for (int k = 0; k < 12; k++) c2w_out[12 * f + k] = m[k];
+}
+// get_rays_from_uv (src/common.py:74-89): dirs = [(i-cx)/fx, -(j-cy)/fy, -1]; rays_d = sum_j dirs_j * R[:, j]; rays_o = t
+__global__ void window_rays_kernel(const float* __restrict__ c2w, const float* __restrict__ pix_i, const float* __restrict__ pix_j,
+                                   const int32_t* __restrict__ frame_of_ray, int n, float fx, float fy, float cx, float cy,
+                                   float* __restrict__ rays_o, float* __restrict__ rays_d, float* __restrict__ dirs) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const float* m = c2w + 12 * frame_of_ray[r];
+  const float d0 = __fdiv_rn(__fsub_rn(pix_i[r], cx), fx), d1 = -__fdiv_rn(__fsub_rn(pix_j[r], cy), fy), d2 = -1.0f;
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    rays_d[3 * r + a] = __fadd_rn(__fadd_rn(__fmul_rn(d0, m[4 * a]), __fmul_rn(d1, m[4 * a + 1])), __fmul_rn(d2, m[4 * a + 2]));
+    rays_o[3 * r + a] = m[4 * a + 3];
+  }
+  if (dirs != nullptr) { dirs[3 * r] = d0; dirs[3 * r + 1] = d1; dirs[3 * r + 2] = d2; }
+}
+// d camera tensor = (d c2w / d camera tensor)^T d c2w  (backward of get_camera_from_tensor), then torch.optim.Adam's update in place.
+// One thread per camera tensor (a window has <= a few dozen).  g: d c2w [3][4] of the tensor's window row.
+__global__ void adam_poses_kernel(float* __restrict__ cams, const int32_t* __restrict__ cam_row, int n_frames, const float* __restrict__ d_c2w,
+                                  float* __restrict__ em, float* __restrict__ ev, float* __restrict__ d_cams, const AdamScalars a) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_frames || cam_row[f] < 0) return;
+  const int c = cam_row[f];
+  const float* g = d_c2w + 12 * f;
+  float* q = cams + 7 * c;
+  const float r = q[0], i = q[1], j = q[2], k = q[3];
+  const float nn = r * r + i * i + j * j + k * k, s = 2.0f / nn;
+  const float G00 = g[0], G01 = g[1], G02 = g[2], G10 = g[4], G11 = g[5], G12 = g[6], G20 = g[8], G21 = g[9], G22 = g[10];
+  // R = I - s A' (diagonal) / s A (off-diagonal);  dL/ds, then ds/dq = -s^2 q
+  const float dLds = -(G00 * (j * j + k * k) + G11 * (i * i + k * k) + G22 * (i * i + j * j))
+                     + G01 * (i * j - k * r) + G02 * (i * k + j * r) + G10 * (i * j + k * r) + G12 * (j * k - i * r) + G20 * (i * k - j * r) + G21 * (j * k + i * r);
+  float dq[7];
+  dq[0] = s * (-k * G01 + j * G02 + k * G10 - i * G12 - j * G20 + i * G21) - dLds * s * s * r;
+  dq[1] = s * (-2.0f * i * (G11 + G22) + j * G01 + k * G02 + j * G10 - r * G12 + k * G20 + r * G21) - dLds * s * s * i;
+  dq[2] = s * (-2.0f * j * (G00 + G22) + i * G01 + r * G02 + i * G10 + k * G12 - r * G20 + k * G21) - dLds * s * s * j;
+  dq[3] = s * (-2.0f * k * (G00 + G11) - r * G01 + i * G02 + r * G10 + j * G12 + i * G20 + j * G21) - dLds * s * s * k;
+  dq[4] = g[3]; dq[5] = g[7]; dq[6] = g[11];
+#pragma unroll
+  for (int t = 0; t < 7; t++) {
+    const float gr = dq[t];
+    if (d_cams != nullptr) d_cams[7 * c + t] = gr;
+    float m = em[7 * c + t], v = ev[7 * c + t];
+    q[t] = adam_update(q[t], gr, m, v, a);
+    em[7 * c + t] = m; ev[7 * c + t] = v;
+  }
+}
+extern "C" int nsb_window_rays(const float* cams, const int32_t* cam_row, const float* fixed_c2w, int n_frames,
+                               const float* pix_i, const float* pix_j, const int32_t* frame_of_ray, int n_rays,
+                               double fx, double fy, double cx, double cy, float* c2w_out, float* rays_o, float* rays_d, float* dirs, void* stream) {
+  if (n_frames < 1 || !cam_row || !c2w_out || (!cams && !fixed_c2w) || n_rays < 0 || (n_rays > 0 && (!pix_i || !pix_j || !frame_of_ray || !rays_o || !rays_d))) {
+    set_error("window_rays: bad arguments"); return NSB_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  window_poses_kernel<<<(n_frames + 63) / 64, 64, 0, st>>>(cams, cam_row, fixed_c2w, n_frames, c2w_out);
+  if (n_rays > 0) window_rays_kernel<<<(n_rays + 255) / 256, 256, 0, st>>>(c2w_out, pix_i, pix_j, frame_of_ray, n_rays, (float)fx, (float)fy, (float)cx, (float)cy, rays_o, rays_d, dirs);
+  return check_cuda(cudaGetLastError(), "window_rays launch");
+}
+extern "C" int nsb_adam_poses(float* cams, const int32_t* cam_row, int n_frames, const float* d_c2w, float* exp_avg, float* exp_avg_sq, float* d_cams,
+                              double lr, double beta1, double beta2, double eps, int step, void* stream) {
+  if (!cams || !cam_row || n_frames < 1 || !d_c2w || !exp_avg || !exp_avg_sq) { set_error("adam_poses: bad arguments"); return NSB_ERR_ARG; }
+  AdamScalars a; int rc = adam_scalars(lr, beta1, beta2, eps, step, &a); if (rc) return rc;
+  adam_poses_kernel<<<(n_frames + 63) / 64, 64, 0, (cudaStream_t)stream>>>(cams, cam_row, n_frames, d_c2w, exp_avg, exp_avg_sq, d_cams, a);
+  return check_cuda(cudaGetLastError(), "adam_poses launch");
 }
 
 extern "C" size_t nsb_frustum_mask_workspace(long long n_voxels) { return n_voxels <= 0 ? 16 : (size_t)n_voxels * sizeof(float) + 16; }

@@ -8,18 +8,18 @@ using namespace nsb;
 
 static size_t a16(size_t x) { return (x + 15) & ~size_t(15); }
 
-// workspace = [tracking-seeds scratch | packed weight-gradient images | decoder-parallel-CTA scratch (small batches only)]
+// workspace = [fused-seeds counter (16 B) | tracking-seeds scratch | packed weight-gradient images | tile-kernel workspace = the rest].
+// Only the first 16 bytes and the END of the buffer (ray completion counters, nsb_render.cu) hold state that must stay zero between calls,
+// so one buffer sized for a capacity serves batches of varying size.
 static size_t split_bytes(int n_rays) { return nsb_split_workspace_bytes(n_rays, NSB_MAX_SAMPLES); }
 extern "C" size_t nsb_iteration_workspace_bytes(int n_rays) {
-  return a16(nsb_tracking_seeds_workspace(n_rays)) + a16(nsb_backward_workspace_bytes()) + a16(split_bytes(n_rays)) + 16;     // + fused-seeds counter
+  return 16 + a16(nsb_tracking_seeds_workspace(n_rays)) + a16(nsb_backward_workspace_bytes()) + a16(split_bytes(n_rays));
 }
-static int* seeds_counter(const nsb_iteration_buffers* b, int n_rays) {
-  return reinterpret_cast<int*>(reinterpret_cast<char*>(b->workspace) + a16(nsb_tracking_seeds_workspace(n_rays)) + a16(nsb_backward_workspace_bytes()) +
-                                a16(split_bytes(n_rays)));
-}
-static void* split_ptr(const nsb_iteration_buffers* b, int n_rays) {
-  return split_bytes(n_rays) ? reinterpret_cast<char*>(b->workspace) + a16(nsb_tracking_seeds_workspace(n_rays)) + a16(nsb_backward_workspace_bytes()) : nullptr;
-}
+static int* seeds_counter(const nsb_iteration_buffers* b, int) { return reinterpret_cast<int*>(b->workspace); }
+static void* seeds_scratch(const nsb_iteration_buffers* b) { return reinterpret_cast<char*>(b->workspace) + 16; }
+static size_t split_offset(int n_rays) { return 16 + a16(nsb_tracking_seeds_workspace(n_rays)) + a16(nsb_backward_workspace_bytes()); }
+static void* split_ptr(const nsb_iteration_buffers* b, int n_rays) { return reinterpret_cast<char*>(b->workspace) + split_offset(n_rays); }
+static size_t split_room(const nsb_iteration_buffers* b, int n_rays) { return b->workspace_bytes - split_offset(n_rays); }
 
 static int check_buffers(const nsb_render_inputs* in, const nsb_iteration_buffers* b, const nsb_backward_args* g) {
   if (!in || !b || !g) { set_error("iteration: NULL argument"); return NSB_ERR_ARG; }
@@ -37,15 +37,15 @@ static int forward_part(const nsb_render_inputs* in, const nsb_iteration_buffers
     if ((rc = nsb_batch_max_depth(in->gt_depth, in->n_rays, b->depth_max, stream))) return rc;
     in2->depth_max = b->depth_max;
   }
-  nsb_forward_outputs fo = {b->depth, b->var, b->rgb, b->z_vals, b->raw, nullptr, b->masks, split_ptr(b, in->n_rays), split_bytes(in->n_rays)};
+  nsb_forward_outputs fo = {b->depth, b->var, b->rgb, b->z_vals, b->raw, nullptr, b->masks, split_ptr(b, in->n_rays), split_room(b, in->n_rays)};
   return render_forward_fused(in2, &fo, fs, stream);
 }
 
 static int backward_part(const nsb_render_inputs* in2, const nsb_iteration_buffers* b, const nsb_backward_args* g, void* stream) {
   nsb_backward_args bw = *g;
   bw.z_vals = b->z_vals; bw.raw = b->raw; bw.g_depth = b->g_depth; bw.g_var = nullptr; bw.g_rgb = b->g_rgb; bw.masks = b->masks;
-  bw.workspace = reinterpret_cast<char*>(b->workspace) + a16(nsb_tracking_seeds_workspace(in2->n_rays));
-  bw.split_workspace = split_ptr(b, in2->n_rays); bw.split_workspace_bytes = split_bytes(in2->n_rays);
+  bw.workspace = reinterpret_cast<char*>(b->workspace) + 16 + a16(nsb_tracking_seeds_workspace(in2->n_rays));
+  bw.split_workspace = split_ptr(b, in2->n_rays); bw.split_workspace_bytes = split_room(b, in2->n_rays);
   if (b->event_bwd_begin) cudaEventRecord((cudaEvent_t)b->event_bwd_begin, (cudaStream_t)stream);
   const int rc = nsb_render_backward(in2, &bw, stream);
   if (b->event_bwd_end) cudaEventRecord((cudaEvent_t)b->event_bwd_end, (cudaStream_t)stream);
@@ -62,13 +62,13 @@ extern "C" int nsb_tracking_iteration(const nsb_render_inputs* in, const nsb_ite
   FusedSeeds fs; memset(&fs, 0, sizeof(fs));
   if (fuse) {
     fs.kind = 1; fs.gt_rgb = gt_rgb; fs.w_color = w_color; fs.handle_dynamic = handle_dynamic; fs.use_color = use_color;
-    fs.g_depth = buf->g_depth; fs.g_rgb = buf->g_rgb; fs.loss = buf->loss; fs.res = static_cast<double*>(buf->workspace);
+    fs.g_depth = buf->g_depth; fs.g_rgb = buf->g_rgb; fs.loss = buf->loss; fs.res = static_cast<double*>(seeds_scratch(buf));
     fs.counter = seeds_counter(buf, in->n_rays);
     if (use_color && !gt_rgb) { set_error("tracking iteration: use_color without gt_rgb"); return NSB_ERR_ARG; }
   }
   if ((rc = forward_part(in, buf, &in2, fuse ? &fs : nullptr, stream))) return rc;
   if (!fuse && (rc = nsb_tracking_seeds(buf->depth, buf->var, buf->rgb, in->gt_depth, gt_rgb, in->n_rays, w_color, handle_dynamic, use_color,
-                                        nullptr, 0, buf->g_depth, buf->g_rgb, buf->loss, buf->workspace, nsb_tracking_seeds_workspace(in->n_rays), stream))) return rc;
+                                        nullptr, 0, buf->g_depth, buf->g_rgb, buf->loss, seeds_scratch(buf), nsb_tracking_seeds_workspace(in->n_rays), stream))) return rc;
   return backward_part(&in2, buf, grads, stream);
 }
 

@@ -929,10 +929,14 @@ static void fill_common(KParams& K, const nsb_render_inputs* in) {
   for (int l = 0; l < 4; l++) K.d_packed[l] = nullptr;
 }
 
-static int g_sm_count = 0;
+// per-device caches (one process may drive several GPUs: the reference configures tracker and mapper devices separately)
+constexpr int kMaxDevices = 64;
+static int g_sm_count[kMaxDevices] = {0};
+static int current_device() { int dev = 0; cudaGetDevice(&dev); return dev >= 0 && dev < kMaxDevices ? dev : 0; }
 static int sm_count() {
-  if (g_sm_count == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev); if (g_sm_count <= 0) g_sm_count = 148; }
-  return g_sm_count;
+  const int dev = current_device();
+  if (g_sm_count[dev] == 0) { cudaDeviceGetAttribute(&g_sm_count[dev], cudaDevAttrMultiProcessorCount, dev); if (g_sm_count[dev] <= 0) g_sm_count[dev] = 148; }
+  return g_sm_count[dev];
 }
 
 // choose rays per CTA and warps per CTA: fill all SMs once before growing CTAs (latency-bound small batches),
@@ -976,30 +980,41 @@ constexpr long long kSplitMaxPts = 262144;
 struct TileWs { int split; int* ray_cnt; void* scratch; };
 static long long tile_count(long long n_points) { return (n_points + tc::TM - 1) / tc::TM; }
 static int tile_rays(int S) { const int r = (tc::TM - 1) / S + 2; return r < tl::kMaxTileRays ? r : tl::kMaxTileRays; }
-static size_t tile_ws_need(int N, int S, int split, bool bwd) {
+// Layout: [scratch ... | ray counters (N ints) at the very END of the buffer].  The counters must stay zero between launches (the completing
+// CTA resets them) while the scratch is left dirty; anchoring the counters at the end keeps the two apart when one buffer, sized for a
+// capacity, serves batches of varying size (the mapper's bbox pre-filter changes N every iteration): counters of any N <= capacity live
+// in the last 4 * capacity bytes, which no scratch of a batch <= capacity reaches (the sizing below is monotone in N).
+static size_t tile_scratch_bytes(int N, int S, int split, bool bwd) {
   const long long NS = (long long)N * S;
-  const size_t scratch = bwd ? (size_t)tile_count(NS) * split * tile_rays(S) * 6 * sizeof(double) : (split > 1 ? (size_t)split * NS * sizeof(float4) : 0);
-  return 16 + align16((size_t)N * sizeof(int)) + scratch;
+  return bwd ? (size_t)tile_count(NS) * split * tile_rays(S) * 6 * sizeof(double) : (split > 1 ? (size_t)split * NS * sizeof(float4) : 0);
 }
+static size_t tile_ws_need(int N, int S, int split, bool bwd) { return 16 + align16((size_t)N * sizeof(int)) + align16(tile_scratch_bytes(N, S, split, bwd)); }
 static bool tile_ws_plan(void* ws, size_t bytes, int N, int S, int n_dec, bool bwd, TileWs* out) {
   if (!ws || (reinterpret_cast<uintptr_t>(ws) & 15)) return false;
+  bytes &= ~size_t(15);
   int split = ((long long)N * S <= kSplitMaxPts && n_dec > 1) ? n_dec : 1;
   if (bytes < tile_ws_need(N, S, split, bwd)) split = 1;
   if (bytes < tile_ws_need(N, S, split, bwd)) return false;
   out->split = split;
-  out->ray_cnt = reinterpret_cast<int*>(static_cast<char*>(ws) + 16);
-  out->scratch = static_cast<char*>(ws) + 16 + align16((size_t)N * sizeof(int));
+  out->ray_cnt = reinterpret_cast<int*>(static_cast<char*>(ws) + bytes - align16((size_t)N * sizeof(int)));
+  out->scratch = static_cast<char*>(ws);
   return true;
 }
 extern "C" size_t nsb_split_workspace_bytes(int n_rays, int S) {
   if (n_rays < 1 || S < 1) return 0;
-  auto need = [&](int s) {
-    const int split = (long long)n_rays * s <= kSplitMaxPts ? 3 : 1;
-    const size_t a = tile_ws_need(n_rays, s, split, false), b = tile_ws_need(n_rays, s, split, true);
+  auto need_exact = [&](int n, int s) {
+    const int split = (long long)n * s <= kSplitMaxPts ? 3 : 1;
+    const size_t a = tile_scratch_bytes(n, s, split, false), b = tile_scratch_bytes(n, s, split, true);
+    return align16(a > b ? a : b);
+  };
+  auto need = [&](int s) {                                  // monotone in n_rays: also covers the largest batch that still splits per decoder
+    const long long n_small = kSplitMaxPts / s;
+    const size_t a = need_exact(n_rays, s), b = need_exact((int)(n_small < n_rays ? (n_small > 0 ? n_small : 1) : n_rays), s);
     return a > b ? a : b;
   };
   size_t m = need(S);
   if (S >= NSB_MAX_SAMPLES) for (int s = tl::kMinSamples; s < NSB_MAX_SAMPLES; s++) { const size_t v = need(s); if (v > m) m = v; }   // "any S" sizing (nsb_iteration_workspace_bytes)
+  m += 16 + align16((size_t)n_rays * sizeof(int));
   const size_t old = old_split_workspace_bytes(n_rays, S);
   return m > old ? m : old;
 }
@@ -1028,9 +1043,10 @@ static bool plan_split(KParams* K, int nd, void* ws, size_t ws_bytes) {
 
 static size_t tile_smem_bytes(bool bwd) { return tl::common_bytes(bwd) + (bwd ? sizeof(tl::BwdExtra) : 0); }
 static bool use_tile_kernels(int S) { return (g_mlp_backend == 0 || g_mlp_backend == 3) && S >= tl::kMinSamples && S <= NSB_MAX_SAMPLES; }
-static bool g_attr_set = false;
+static bool g_attr_set[kMaxDevices] = {false};
 static int set_attrs() {
-  if (g_attr_set) return NSB_OK;
+  const int dev = current_device();
+  if (g_attr_set[dev]) return NSB_OK;
   if (check_cuda(cudaFuncSetAttribute(render_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap), "fwd tc smem attr")) return NSB_ERR_CUDA;
   if (check_cuda(cudaFuncSetAttribute(render_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap), "bwd tc smem attr")) return NSB_ERR_CUDA;
   if (check_cuda(cudaFuncSetAttribute(render_fwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(false)), "fwd tile smem attr")) return NSB_ERR_CUDA;
@@ -1040,7 +1056,7 @@ static int set_attrs() {
   if (check_cuda(cudaFuncSetAttribute(render_bwd_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared), "bwd tile carveout")) return NSB_ERR_CUDA;
   if (check_cuda(cudaFuncSetAttribute(render_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap), "fwd smem attr")) return NSB_ERR_CUDA;
   if (check_cuda(cudaFuncSetAttribute(render_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap), "bwd smem attr")) return NSB_ERR_CUDA;
-  g_attr_set = true;
+  g_attr_set[dev] = true;
   return NSB_OK;
 }
 

@@ -2,6 +2,7 @@
 // helpers.  Used by the stand-alone single-CTA kernels of nsb_aux.cu and, fused, by the LAST CTA of the forward render kernels
 // (nsb_render.cu): for small batches the loss seeds are produced by the forward launch itself.
 #pragma once
+#include <cstdio>
 #include "nsb_common.cuh"
 
 namespace nsb {
@@ -19,6 +20,7 @@ struct PeerX {
   unsigned long long* counter;       // this rank's sequence counters, one per channel
   int max_n;                         // residual-pool capacity per rank
 };
+constexpr long long kPeerWaitCycles = 20000000000ll;        // ~10 s at 1.9 GHz
 constexpr size_t kXMaxOff = 0, kXSumOff = 256, kXPoolFlagOff = 2304, kXPoolOff = 2560;
 __host__ __device__ inline size_t peer_buffer_bytes(int max_n) { return kXPoolOff + (size_t)2 * NSB_MAX_PEERS * (size_t)max_n * sizeof(double); }
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -39,7 +41,11 @@ __device__ __forceinline__ void peer_signal_wait(const PeerX& px, int c, size_t 
   if ((int)threadIdx.x < px.world) {
     st_release_sys(reinterpret_cast<uint32_t*>(px.peer[threadIdx.x] + flag_off + ((size_t)par * NSB_MAX_PEERS + px.rank) * flag_stride), seq);
     const uint32_t* mine = reinterpret_cast<const uint32_t*>(px.peer[px.rank] + flag_off + ((size_t)par * NSB_MAX_PEERS + threadIdx.x) * flag_stride);
-    while ((int)(ld_acquire_sys(mine) - seq) < 0) { }
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(mine) - seq) < 0) {
+      // a rank that never arrives (crashed process, mismatched call sequence) must not hang the device: fail the launch instead
+      if (clock64() - t0 > kPeerWaitCycles) { printf("nsb: peer exchange timed out (rank %d waiting for rank %d, channel %d, seq %u)\n", px.rank, (int)threadIdx.x, c, seq); __trap(); }
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) px.counter[c] = (unsigned long long)seq;

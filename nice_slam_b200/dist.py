@@ -145,7 +145,7 @@ class ShardedTrackingIteration:
             _lib.check(L.nsb_tracking_seeds_peers(_VP(x.depth.data_ptr()), _VP(x.var.data_ptr()), _VP(x.rgb.data_ptr()), _VP(p["gd"].data_ptr()),
                                                   _VP(p["gc"].data_ptr()), n, p["w_color"], p["hd"], p["uc"], px,
                                                   _VP(x.g_depth.data_ptr()), _VP(x.g_rgb.data_ptr()), _VP(x.loss.data_ptr()),
-                                                  _VP(x.ws.data_ptr()), L.nsb_tracking_seeds_workspace(n), st), "nsb_tracking_seeds_peers")
+                                                  _VP(x.seeds_ws.data_ptr()), L.nsb_tracking_seeds_workspace(n), st), "nsb_tracking_seeds_peers")
             _lib.check(L.nsb_render_backward(C.byref(p["inp"]), C.byref(p["bw"]), st), "nsb_render_backward")
             _lib.check(L.nsb_pose_grad_peers(_VP(p["dirs"].data_ptr()), _VP(x.d_rays_o.data_ptr()), _VP(x.d_rays_d.data_ptr()), n,
                                              _VP(x.loss.data_ptr()), _VP(self.packed.data_ptr()), px, st), "nsb_pose_grad_peers")
@@ -162,7 +162,7 @@ class ShardedTrackingIteration:
         _lib.check(L.nsb_tracking_seeds(_VP(x.depth.data_ptr()), _VP(x.var.data_ptr()), _VP(x.rgb.data_ptr()), _VP(p["gd"].data_ptr()),
                                         _VP(p["gc"].data_ptr()), n, p["w_color"], p["hd"], p["uc"], pool, n_pool,
                                         _VP(x.g_depth.data_ptr()), _VP(x.g_rgb.data_ptr()), _VP(self.packed.data_ptr()),
-                                        _VP(x.ws.data_ptr()), L.nsb_tracking_seeds_workspace(n), st), "nsb_tracking_seeds")
+                                        _VP(x.seeds_ws.data_ptr()), L.nsb_tracking_seeds_workspace(n), st), "nsb_tracking_seeds")
         _lib.check(L.nsb_render_backward(C.byref(p["inp"]), C.byref(p["bw"]), st), "nsb_render_backward")
         _lib.check(L.nsb_pose_grad(_VP(p["dirs"].data_ptr()), _VP(x.d_rays_o.data_ptr()), _VP(x.d_rays_d.data_ptr()), n,
                                    _VP(self.packed.data_ptr() + 8), st), "nsb_pose_grad")
@@ -229,8 +229,7 @@ class ShardedMappingIteration:
             bw.split_workspace, bw.split_workspace_bytes = x.split_ws.data_ptr(), x.split_bytes
         bw.z_vals, bw.raw, bw.g_depth, bw.g_rgb, bw.masks = (x.z_vals.data_ptr(), x.raw.data_ptr(), x.g_depth.data_ptr(),
                                                               x.g_rgb.data_ptr(), x.masks.data_ptr())
-        ws_off = (_lib.lib().nsb_tracking_seeds_workspace(x.n) + 15) & ~15
-        bw.workspace = x.ws.data_ptr() + ws_off
+        bw.workspace = x.bwd_ws.data_ptr()
         self._p = dict(call=call, grids=grids, lin=(t_u, t_s), inp=inp, fo=fo, bw=bw, dirs=dirs, offs=frame_offsets, gd=gd, gc=gc,
                        w_color=w_color, uc=int(x.stage == "color"))
 

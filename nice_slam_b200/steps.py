@@ -38,11 +38,12 @@ def packed_layout(n_frames, grad_decoders, masked_counts):
 
 class IterationContext:
     def __init__(self, renderer, n_rays, stage, device, kind="track", grad_grids=(), grad_decoders=(), coarse_mapper=False,
-                 masked=None, n_frames=0):
+                 masked=None, n_frames=0, host_staging=True):
         """masked: {grid key: masked.MaskedVoxels} -- those grids get COMPACT [n_selected,32] gradients (Mapper.py:317-333) instead of
         dense ones; n_frames: keyframes of the bundle-adjustment window whose d c2w is wanted (pose_grad_frames)."""
         L = _lib.lib()
         self.r, self.n, self.stage, self.kind = renderer, int(n_rays), stage, kind
+        self.n_last = self.n                  # rays of the last run() (<= capacity n)
         self.dev = torch.device(device)
         self.levels = STAGE_DECODERS[stage]
         self.render_with_depth = not (kind == "map" and (stage == "coarse" or coarse_mapper))
@@ -65,6 +66,9 @@ class IterationContext:
         self.loss = self.d_res[res_off: res_off + 8].view(f64)
         self.depth_max = torch.zeros(2, dtype=f32, device=dev)
         self.ws = torch.zeros(L.nsb_iteration_workspace_bytes(n), dtype=torch.uint8, device=dev)     # zeroed once: holds the split counters
+        # stand-alone scratch for the split-phase (sharded) forms, which call the pieces of an iteration one by one (dist.py)
+        self.seeds_ws = torch.empty(max(L.nsb_tracking_seeds_workspace(n), 16), dtype=torch.uint8, device=dev)
+        self.bwd_ws = torch.empty(L.nsb_backward_workspace_bytes(), dtype=torch.uint8, device=dev)
         self.split_ws = torch.zeros(max(L.nsb_split_workspace_bytes(n, S), 16), dtype=torch.uint8, device=dev)   # decoder-parallel CTAs (small batches)
         self.split_bytes = L.nsb_split_workspace_bytes(n, S)
         self.pose_counter = torch.zeros(1, dtype=torch.int32, device=dev)      # arrival counter of the fused pose gradient (self-resetting)
@@ -98,7 +102,7 @@ class IterationContext:
                                          self.depth_max.data_ptr(), self.ws.data_ptr(), self.ws.numel(), None, None)
         self.ev_bwd = None
         # pinned host staging for run_host(): [rays_o | rays_d | gt_depth] f32, gt_color, and the read-back block
-        cuda = dev.type == "cuda"
+        cuda = dev.type == "cuda" and host_staging      # (pin_memory is a synchronising cudaHostAlloc: skipped when run_host() is never used)
         self.h_in = torch.zeros(self.d_in.numel(), dtype=torch.uint8).pin_memory() if cuda else None
         self.h_in32 = self.h_in[: n * 28].view(f32) if cuda else None
         self.h_col = self.h_in[col_off:].view(col_dt).view(n, 3) if cuda else None
@@ -153,8 +157,7 @@ class IterationContext:
         self.loss, self.depth/var/rgb, self.d_rays_o/d, self.d_grid[key], self.d_flat[level]; with `dirs` (camera-frame ray directions
         [N,3]) also self.d_c2w, produced by the backward kernel itself."""
         L = _lib.lib()
-        for t, nm in ((rays_o, "rays_o"), (rays_d, "rays_d"), (gt_depth, "gt_depth")):
-            _require_cuda(t, nm)
+        n = self._check_inputs(rays_o, rays_d, gt_depth, gt_color)
         call, grids, _ = self.r._call(c, decoders, self.stage, gt_depth if self.render_with_depth else None, self.dev)
         t_u, t_s = _linspaces(self.r.N_samples, self.r.N_surface, self.dev)
         inp = _inputs(call, rays_o, rays_d, self.depth_max, t_u, t_s, [g.detach() for g in grids])
@@ -172,6 +175,24 @@ class IterationContext:
                                                C.byref(bw), _stream()), "nsb_mapping_iteration")
         return self.loss
 
+    def _check_inputs(self, rays_o, rays_d, gt_depth, gt_color):
+        """The kernels read these tensors through raw pointers: refuse anything that is not exactly what they expect (a stride-0 expand()
+        view such as the reference's rays_o, a float64 depth, a batch larger than the context's buffers ...) instead of reading garbage.
+        Batches SMALLER than the context's capacity are fine (every buffer is sized for self.n; the bbox pre-filter of the mapper makes the
+        count vary per iteration, Mapper.py:471-481).  Returns the batch size."""
+        n = int(rays_o.shape[0])
+        if n < 1 or n > self.n:
+            raise RuntimeError("nice_slam_b200: batch of %d rays does not fit this IterationContext (capacity %d)" % (n, self.n))
+        col_dt = torch.float64 if self.kind == "track" else torch.float32
+        for t, nm, shape, dt in ((rays_o, "rays_o", (n, 3), torch.float32), (rays_d, "rays_d", (n, 3), torch.float32),
+                                 (gt_depth, "gt_depth", (n,), torch.float32), (gt_color, "gt_color", (n, 3), col_dt)):
+            _require_cuda(t, nm)
+            if tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous():
+                raise RuntimeError("nice_slam_b200: %s must be a contiguous %s tensor of shape %s, got %s %s%s" %
+                                   (nm, dt, shape, t.dtype, tuple(t.shape), "" if t.is_contiguous() else " (non-contiguous)"))
+        self.n_last = n
+        return n
+
     def time_backward(self, enable=True):
         """Profiling hook: have the library record CUDA events around the backward launch of every run()."""
         if enable:
@@ -185,7 +206,7 @@ class IterationContext:
 
     def pose_grad(self, dirs):
         """d c2w [3,4] (f64, device) of the last run() from the ray gradients (nsb_pose_grad)."""
-        _lib.check(_lib.lib().nsb_pose_grad(_VP(dirs.data_ptr()), _VP(self.d_rays_o.data_ptr()), _VP(self.d_rays_d.data_ptr()), self.n,
+        _lib.check(_lib.lib().nsb_pose_grad(_VP(dirs.data_ptr()), _VP(self.d_rays_o.data_ptr()), _VP(self.d_rays_d.data_ptr()), self.n_last,
                                             _VP(self.d_c2w.data_ptr()), _stream()), "nsb_pose_grad")
         return self.d_c2w
 
@@ -197,7 +218,10 @@ class IterationContext:
 
     def load_device_inputs(self, rays_o, rays_d, gt_depth, gt_color):
         ro, rd, gd, gc = self.device_views()
-        ro.copy_(rays_o); rd.copy_(rays_d); gd.copy_(gt_depth); gc.copy_(gt_color)
+        for dst, src, nm in ((ro, rays_o, "rays_o"), (rd, rays_d, "rays_d"), (gd, gt_depth, "gt_depth"), (gc, gt_color, "gt_color")):
+            if tuple(src.shape) != tuple(dst.shape):
+                raise RuntimeError("nice_slam_b200: %s has shape %s, this IterationContext holds %s" % (nm, tuple(src.shape), tuple(dst.shape)))
+            dst.copy_(src)                    # copy_ converts dtype / strides (a stride-0 expand() view is materialised here)
 
     def build_graph(self, c, decoders, dirs=None, host_io=False, **kw):
         """Capture one whole iteration into a CUDA graph (launch-bound small batches: one graph launch instead of
