@@ -80,6 +80,8 @@ SYMBOLS = {
     "nsb_pose_grad": (C.c_int, [_P, _P, _P, C.c_int, _P, _P]),
     "nsb_iteration_workspace_bytes": (C.c_size_t, [C.c_int]),
     "nsb_tracking_iteration": (C.c_int, [C.POINTER(RenderInputs), C.POINTER(IterationBuffers), _P, C.c_double, C.c_int, C.c_int, C.POINTER(BackwardArgs), _P]),
+    "nsb_tracking_iteration_peers": (C.c_int, [C.POINTER(RenderInputs), C.POINTER(IterationBuffers), _P, C.c_double, C.c_int, C.c_int, C.POINTER(BackwardArgs),
+                                               C.POINTER(Peers), _P, _P]),
     "nsb_mapping_iteration": (C.c_int, [C.POINTER(RenderInputs), C.POINTER(IterationBuffers), _P, _P, C.c_double, C.POINTER(BackwardArgs), _P]),
     "nsb_mapping_seeds": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_double, C.c_int, _P, _P, _P, _P]),
     "nsb_tracking_seeds_workspace": (C.c_size_t, [C.c_int]),

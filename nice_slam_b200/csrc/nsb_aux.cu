@@ -275,21 +275,10 @@ __global__ void pose_grad_kernel(const float* __restrict__ dirs, const float* __
     return;
   }
   // SUM over ranks of [loss | d c2w] through peer memory (channel 2: slot = 13 doubles + flag in 128 bytes); out = 13 doubles.
-  // Every rank adds the slots in rank order: bit-identical results everywhere.
   __shared__ uint32_t s_seq;
   if (threadIdx.x == 0) tot[0] = loss_local != nullptr ? loss_local[0] : 0.0;
-  const uint32_t seq = peer_begin(px, 2, &s_seq);
-  const int par = seq & 1u;
-  for (int i = threadIdx.x; i < 13 * px.world; i += blockDim.x) {
-    const int r = i / 13, k = i - 13 * r;
-    __stcg(reinterpret_cast<double*>(px.peer[r] + kXSumOff + ((size_t)par * NSB_MAX_PEERS + px.rank) * 128) + k, tot[k]);
-  }
-  peer_signal_wait(px, 2, kXSumOff + 104, 128, seq);
-  if (threadIdx.x < 13) {
-    double v = 0.0;
-    for (int r = 0; r < px.world; r++) v += __ldcg(reinterpret_cast<const double*>(px.peer[px.rank] + kXSumOff + ((size_t)par * NSB_MAX_PEERS + r) * 128) + threadIdx.x);
-    out[threadIdx.x] = v;
-  }
+  __syncthreads();
+  peer_sum13(px, tot, 13, out, &s_seq);
 }
 
 // ---- masked voxel parameterisation (Mapper.py:317-333, :393-401, :511-519) --------------------------------------------
@@ -522,6 +511,7 @@ static int make_peers(const nsb_peers* p, PeerX* px) {
   }
   return NSB_OK;
 }
+int nsb::make_peerx(const nsb_peers* p, PeerX* px) { return make_peers(p, px); }
 extern "C" size_t nsb_peer_buffer_bytes(int max_rays) { return max_rays < 1 ? 0 : peer_buffer_bytes(max_rays); }
 
 extern "C" int nsb_pose_grad(const float* dirs, const float* d_rays_o, const float* d_rays_d, int n, double* d_c2w, void* stream) {

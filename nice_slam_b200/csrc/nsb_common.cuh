@@ -174,6 +174,15 @@ __device__ __forceinline__ int act_idx(int r, int pt) { return r * kRowF + swz(r
 
 // Loss seeds fused into the forward launch (small batches): the last CTA of the forward kernel to finish computes them (nsb_seeds.cuh).
 // Internal to the library: nsb_tracking_iteration / nsb_mapping_iteration use it through render_forward_fused().
+// exchange buffers of a ray-sharded iteration as the kernels see them (nsb_peers of the C ABI; helpers in nsb_seeds.cuh)
+struct PeerX {
+  int rank, world;                   // world <= 1: no exchange
+  unsigned char* peer[NSB_MAX_PEERS];
+  unsigned long long* counter;       // this rank's sequence counters, one per channel
+  int max_n;                         // residual-pool capacity per rank
+};
+// What the LAST CTA of a sharded backward launch adds to the fused pose gradient: SUM over ranks of [loss | d c2w] -> out13
+struct PeerTail { PeerX px; const double* loss; double* out13; };
 struct FusedSeeds {
   int kind;                      // 0 = none, 1 = tracking (Tracker.py:108-123), 2 = mapping (Mapper.py:487-493)
   const void* gt_rgb;            // float64 [N,3] (tracking) / float32 [N,3] (mapping)
@@ -183,8 +192,11 @@ struct FusedSeeds {
   double* g_depth; float* g_rgb; double* loss;
   double* res;                   // tracking: residual scratch [N]
   int* counter;                  // grid-wide arrival counter, zero between launches
+  PeerX px;                      // world > 1: sharded tracking batch -- depth maxima and the median pool are exchanged inside the forward launch
 };
 int render_forward_fused(const nsb_render_inputs* in, const nsb_forward_outputs* out, const FusedSeeds* fs, void* stream);
+int render_backward_tail(const nsb_render_inputs* in, const nsb_backward_args* bw, const PeerTail* tail, void* stream);
+int make_peerx(const struct nsb_peers* p, PeerX* px);
 
 // error plumbing shared by the API translation units
 void set_error(const char* fmt, ...);

@@ -41,13 +41,13 @@ static int forward_part(const nsb_render_inputs* in, const nsb_iteration_buffers
   return render_forward_fused(in2, &fo, fs, stream);
 }
 
-static int backward_part(const nsb_render_inputs* in2, const nsb_iteration_buffers* b, const nsb_backward_args* g, void* stream) {
+static int backward_part(const nsb_render_inputs* in2, const nsb_iteration_buffers* b, const nsb_backward_args* g, void* stream, const PeerTail* tail = nullptr) {
   nsb_backward_args bw = *g;
   bw.z_vals = b->z_vals; bw.raw = b->raw; bw.g_depth = b->g_depth; bw.g_var = nullptr; bw.g_rgb = b->g_rgb; bw.masks = b->masks;
   bw.workspace = reinterpret_cast<char*>(b->workspace) + 16 + a16(nsb_tracking_seeds_workspace(in2->n_rays));
   bw.split_workspace = split_ptr(b, in2->n_rays); bw.split_workspace_bytes = split_room(b, in2->n_rays);
   if (b->event_bwd_begin) cudaEventRecord((cudaEvent_t)b->event_bwd_begin, (cudaStream_t)stream);
-  const int rc = nsb_render_backward(in2, &bw, stream);
+  const int rc = render_backward_tail(in2, &bw, tail, stream);
   if (b->event_bwd_end) cudaEventRecord((cudaEvent_t)b->event_bwd_end, (cudaStream_t)stream);
   return rc;
 }
@@ -70,6 +70,30 @@ extern "C" int nsb_tracking_iteration(const nsb_render_inputs* in, const nsb_ite
   if (!fuse && (rc = nsb_tracking_seeds(buf->depth, buf->var, buf->rgb, in->gt_depth, gt_rgb, in->n_rays, w_color, handle_dynamic, use_color,
                                         nullptr, 0, buf->g_depth, buf->g_rgb, buf->loss, seeds_scratch(buf), nsb_tracking_seeds_workspace(in->n_rays), stream))) return rc;
   return backward_part(&in2, buf, grads, stream);
+}
+
+// Ray-sharded tracking iteration in TWO launches per rank: the forward exchanges the depth maxima (every CTA) and the residual pool of the
+// median (last CTA, which then computes the loss seeds); the backward's last CTA sums [loss | d c2w] over the ranks.
+extern "C" int nsb_tracking_iteration_peers(const nsb_render_inputs* in, const nsb_iteration_buffers* buf, const double* gt_rgb,
+                                            double w_color, int handle_dynamic, int use_color, const nsb_backward_args* grads,
+                                            const nsb_peers* peers, double* loss_and_d_c2w, void* stream) {
+  int rc = check_buffers(in, buf, grads); if (rc) return rc;
+  if (!in->gt_depth || !loss_and_d_c2w) { set_error("sharded tracking iteration needs gt_depth and an output for [loss | d c2w]"); return NSB_ERR_ARG; }
+  if (in->n_rays < 1 || in->n_rays > 512) { set_error("sharded tracking iteration: 1..512 rays per rank (got %d)", in->n_rays); return NSB_ERR_UNSUPPORTED; }
+  if (!grads->pose_dirs || !grads->d_c2w || !grads->pose_counter) { set_error("sharded tracking iteration needs pose_dirs / d_c2w / pose_counter"); return NSB_ERR_ARG; }
+  if (use_color && !gt_rgb) { set_error("tracking iteration: use_color without gt_rgb"); return NSB_ERR_ARG; }
+  PeerX px;
+  if ((rc = make_peerx(peers, &px))) return rc;
+  if (in->n_rays > px.max_n) { set_error("sharded tracking iteration: %d rays exceed the exchange buffers' capacity %d", in->n_rays, px.max_n); return NSB_ERR_ARG; }
+  FusedSeeds fs; memset(&fs, 0, sizeof(fs));
+  fs.kind = 1; fs.gt_rgb = gt_rgb; fs.w_color = w_color; fs.handle_dynamic = handle_dynamic; fs.use_color = use_color;
+  fs.g_depth = buf->g_depth; fs.g_rgb = buf->g_rgb; fs.loss = buf->loss; fs.res = static_cast<double*>(seeds_scratch(buf));
+  fs.counter = seeds_counter(buf, in->n_rays);
+  fs.px = px;
+  nsb_render_inputs in2;
+  if ((rc = forward_part(in, buf, &in2, &fs, stream))) return rc;
+  PeerTail tail; tail.px = px; tail.loss = buf->loss; tail.out13 = loss_and_d_c2w;
+  return backward_part(&in2, buf, grads, stream, &tail);
 }
 
 extern "C" int nsb_mapping_iteration(const nsb_render_inputs* in, const nsb_iteration_buffers* buf, const float* gt_depth_loss,

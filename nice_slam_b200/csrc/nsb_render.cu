@@ -162,6 +162,7 @@ struct KParams {
   float4* tile_parts;           // forward: [split][N*S] per-item decoder outputs (split == 1: aliases fo.raw)
   int tile_rays;                // backward: rays one tile can touch (stride of ray_parts per item)
   FusedSeeds fs;                // forward: loss seeds computed by the last CTA to finish (kind 0 = not fused)
+  PeerTail tail;                // backward: sum of [loss | d c2w] over ranks by the last CTA (px.world <= 1: none)
   int wbytes;                   // bytes reserved for the weight image in shared memory
   int max_pts, max_rays;        // per-CTA capacities the shared-memory carve-up was sized for
 };
@@ -683,8 +684,8 @@ __device__ __forceinline__ void bwd_ray_reduce(const KParams& P, const Smem& sm,
 // Fused pose gradient (optional): every CTA that has written ray gradients arrives on a grid-wide counter; the last one reduces
 // d c2w = [sum_r d_rays_d[r] (x) dirs[r] | sum_r d_rays_o[r]] over the whole batch (fixed thread mapping -> deterministic) and resets
 // the counter.  Saves the separate single-CTA pose_grad launch of a tracking iteration.
-__device__ __forceinline__ void fused_pose_grad(const KParams& P, int n_writers, double* __restrict__ s_pose /* [16][12] scratch in dynamic shared memory */) {
-  if (P.bw.pose_dirs == nullptr) return;
+__device__ __forceinline__ bool fused_pose_grad(const KParams& P, int n_writers, double* __restrict__ s_pose /* [16][12] scratch in dynamic shared memory */) {
+  if (P.bw.pose_dirs == nullptr) return false;
   __shared__ int s_pose_last;
   __threadfence();
   __syncthreads();
@@ -694,7 +695,7 @@ __device__ __forceinline__ void fused_pose_grad(const KParams& P, int n_writers,
     if (s_pose_last) *P.bw.pose_counter = 0;
   }
   __syncthreads();
-  if (!s_pose_last) return;
+  if (!s_pose_last) return false;
   __threadfence();
   double acc[12];
 #pragma unroll
@@ -722,6 +723,7 @@ __device__ __forceinline__ void fused_pose_grad(const KParams& P, int n_writers,
     for (int w = 0; w < nw; w++) v += s_pose[w * 12 + threadIdx.x];
     P.bw.d_c2w[threadIdx.x] = v;
   }
+  return true;                                                   // this CTA was the last one: d_c2w is complete (written by threads 0..11)
 }
 
 __global__ void __launch_bounds__(256, 1) render_bwd_kernel(const __grid_constant__ KParams P) {
@@ -921,7 +923,7 @@ static void fill_common(KParams& K, const nsb_render_inputs* in) {
   for (int i = 0; i < 3; i++) K.dec_pos[i] = i;
   K.accumulate_rays = 0;
   K.split = 1; K.group_done = nullptr; K.fwd_parts = nullptr; K.ray_parts = nullptr; K.ray_cnt = nullptr; K.tile_parts = nullptr; K.tile_rays = 0;
-  memset(&K.fs, 0, sizeof(K.fs));
+  memset(&K.fs, 0, sizeof(K.fs)); memset(&K.tail, 0, sizeof(K.tail));
   int wb = 0;
   for (int i = 0; i < K.n_dec; i++) { const int b = packed_floats(K.dec[i]) * 4; wb = b > wb ? b : wb; }
   K.wbytes = wb;
@@ -1082,6 +1084,8 @@ int nsb::render_forward_fused(const nsb_render_inputs* in, const nsb_forward_out
   if (K.S > NSB_MAX_SAMPLES) { set_error("n_samples+n_surface = %d exceeds %d", K.S, NSB_MAX_SAMPLES); return NSB_ERR_UNSUPPORTED; }
   if (K.has_gt && in->n_surface > 0 && !in->t_surface) { set_error("t_surface NULL"); return NSB_ERR_ARG; }
   if ((rc = set_attrs())) return rc;
+  if (K.fs.px.world > 1 && !(use_tile_kernels(K.S) && in->depth_max == nullptr && in->gt_depth != nullptr)) {
+    set_error("in-kernel exchanges of a sharded forward need the tile kernels and <= %d rays per rank", NSB_INLINE_MAX_RAYS); return NSB_ERR_UNSUPPORTED; }
   if (use_tile_kernels(K.S)) {                            // tile kernels: item = (128-point tile, decoder), two CTAs per SM
     if (!out->z_vals || !out->raw) { set_error("the tensor-core forward needs z_vals and raw outputs"); return NSB_ERR_ARG; }
     TileWs w;
@@ -1147,6 +1151,9 @@ extern "C" size_t nsb_backward_workspace_bytes(void) {
 }
 
 extern "C" int nsb_render_backward(const nsb_render_inputs* in, const nsb_backward_args* bw, void* stream) {
+  return nsb::render_backward_tail(in, bw, nullptr, stream);
+}
+int nsb::render_backward_tail(const nsb_render_inputs* in, const nsb_backward_args* bw, const nsb::PeerTail* tail, void* stream) {
   int rc = validate_inputs(in, true); if (rc) return rc;
   if (!bw || !bw->z_vals || !bw->raw) { set_error("backward needs z_vals and raw from the forward pass"); return NSB_ERR_ARG; }
   if (in->n_rays == 0) return NSB_OK;
@@ -1197,10 +1204,15 @@ extern "C" int nsb_render_backward(const nsb_render_inputs* in, const nsb_backwa
         if (!tile_ws_plan(bw->split_workspace, bw->split_workspace_bytes, in->n_rays, T.S, T.n_dec, true, &w)) {
           set_error("split_workspace missing or smaller than nsb_split_workspace_bytes(%d, %d)", in->n_rays, T.S); return NSB_ERR_ARG; }
         T.split = w.split; T.ray_cnt = w.ray_cnt; T.ray_parts = static_cast<double*>(w.scratch); T.tile_rays = tile_rays(T.S);
+        if (tail != nullptr && tail->px.world > 1) {
+          if (n_w != 0 || T.bw.pose_dirs == nullptr) { set_error("sharded backward tail needs pose_dirs and no decoder weight gradients"); return NSB_ERR_ARG; }
+          T.tail = *tail;
+        }
         const long long grid_t = tile_count((long long)in->n_rays * T.S) * T.split;
         render_bwd_tile_kernel<<<(unsigned)grid_t, tl::kThreads, tile_smem_bytes(true), st>>>(T);
         if ((rc = check_cuda(cudaGetLastError(), "render_bwd_tile_kernel launch"))) return rc;
       } else {
+      if (tail != nullptr && tail->px.world > 1) { set_error("sharded backward tail needs the tile kernels"); return NSB_ERR_UNSUPPORTED; }
       choose_config(in->n_rays, T.S, kRowsBwd, true, T.wbytes, 8, &T, &warps, &smem, kMaxPtsTc);
       plan_split(&T, T.n_dec, bw->split_workspace, bw->split_workspace_bytes);
       const int grid_tc = ((in->n_rays + T.rays_per_block - 1) / T.rays_per_block) * T.split;

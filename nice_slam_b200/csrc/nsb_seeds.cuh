@@ -14,12 +14,6 @@ namespace nsb {
 // it, spin (ld.acquire.sys) on the own buffer until all ranks' sequence numbers have arrived.  Parity double-buffering + one
 // sequence counter per channel make the buffers reusable without any reset; a rank cannot run two exchanges of a channel ahead
 // because the other channels of the same iteration need everybody.
-struct PeerX {
-  int rank, world;                   // world <= 1: no exchange
-  unsigned char* peer[NSB_MAX_PEERS];
-  unsigned long long* counter;       // this rank's sequence counters, one per channel
-  int max_n;                         // residual-pool capacity per rank
-};
 constexpr long long kPeerWaitCycles = 20000000000ll;        // ~10 s at 1.9 GHz
 constexpr size_t kXMaxOff = 0, kXSumOff = 256, kXPoolFlagOff = 2304, kXPoolOff = 2560;
 __host__ __device__ inline size_t peer_buffer_bytes(int max_n) { return kXPoolOff + (size_t)2 * NSB_MAX_PEERS * (size_t)max_n * sizeof(double); }
@@ -51,6 +45,53 @@ __device__ __forceinline__ void peer_signal_wait(const PeerX& px, int c, size_t 
   if (threadIdx.x == 0) px.counter[c] = (unsigned long long)seq;
 }
 
+
+// ---- exchanges fused into multi-CTA kernels (tile kernels, nsb_tile.cuh) ----------------------------------------------------------------
+// MAX over ranks of one float, needed by EVERY CTA of the grid before it can sample (channel 0): CTA 0 pushes this rank's value to every
+// peer and raises the flags; all CTAs spin on this rank's own buffer.  The sequence number is read, not advanced: the grid's last CTA
+// advances the channel with peer_advance() once every CTA has passed this point.
+__device__ __forceinline__ float peer_max_all_ctas(const PeerX& px, float local, uint32_t* s_seq) {
+  if (threadIdx.x == 0) *s_seq = (uint32_t)(px.counter[0] + 1ull);
+  __syncthreads();
+  const uint32_t seq = *s_seq;
+  const int par = seq & 1u;
+  if (blockIdx.x == 0) {
+    if ((int)threadIdx.x < px.world) {
+      __stcg(reinterpret_cast<float*>(px.peer[threadIdx.x] + kXMaxOff + ((size_t)par * NSB_MAX_PEERS + px.rank) * 16), local);
+      __threadfence_system();
+      st_release_sys(reinterpret_cast<uint32_t*>(px.peer[threadIdx.x] + kXMaxOff + 8 + ((size_t)par * NSB_MAX_PEERS + px.rank) * 16), seq);
+    }
+  }
+  if ((int)threadIdx.x < px.world) {
+    const uint32_t* mine = reinterpret_cast<const uint32_t*>(px.peer[px.rank] + kXMaxOff + 8 + ((size_t)par * NSB_MAX_PEERS + threadIdx.x) * 16);
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(mine) - seq) < 0) {
+      if (clock64() - t0 > kPeerWaitCycles) { printf("nsb: peer depth-max exchange timed out (rank %d waiting for rank %d, seq %u)\n", px.rank, (int)threadIdx.x, seq); __trap(); }
+    }
+  }
+  __syncthreads();
+  float m = -INFINITY;
+  for (int r = 0; r < px.world; r++) m = fmaxf(m, __ldcg(reinterpret_cast<const float*>(px.peer[px.rank] + kXMaxOff + ((size_t)par * NSB_MAX_PEERS + r) * 16)));
+  return m;
+}
+__device__ __forceinline__ void peer_advance(const PeerX& px, int c) {      // one thread of the grid's last CTA
+  px.counter[c] = px.counter[c] + 1ull;
+}
+// SUM over ranks of `n_val` (<= 13) doubles held in shared memory `tot` (channel 2), rank order -> identical bits on every rank.  Single CTA.
+__device__ __forceinline__ void peer_sum13(const PeerX& px, const double* __restrict__ tot, int n_val, double* __restrict__ out, uint32_t* s_seq) {
+  const uint32_t seq = peer_begin(px, 2, s_seq);
+  const int par = seq & 1u;
+  for (int i = threadIdx.x; i < n_val * px.world; i += blockDim.x) {
+    const int r = i / n_val, k = i - n_val * r;
+    __stcg(reinterpret_cast<double*>(px.peer[r] + kXSumOff + ((size_t)par * NSB_MAX_PEERS + px.rank) * 128) + k, tot[k]);
+  }
+  peer_signal_wait(px, 2, kXSumOff + 104, 128, seq);
+  if ((int)threadIdx.x < n_val) {
+    double v = 0.0;
+    for (int r = 0; r < px.world; r++) v += __ldcg(reinterpret_cast<const double*>(px.peer[px.rank] + kXSumOff + ((size_t)par * NSB_MAX_PEERS + r) * 128) + threadIdx.x);
+    out[threadIdx.x] = v;
+  }
+}
 
 constexpr int kMedianDirect = 512;       // larger pools: 8-pass radix select (the direct count is O(n^2))
 constexpr int kSeedsScratchBytes = 34 * 8 + kMedianDirect * 8 + (256 + 8 + 2 + 2) * 4;

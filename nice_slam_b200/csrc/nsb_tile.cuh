@@ -13,7 +13,7 @@
 //   * weights stream through a 4-slot ring of 10 KB operand UNITS (pre-split hi|lo canonical tiles, consumption order, nsb_common.cuh)
 //     with full (TMA -> issuer) and empty (tcgen05.commit -> producer) mbarriers: three units of prefetch, no thread touches a weight;
 //   * activations ping-pong between two 32 KB operand buffers; epilogue threads publish a tile by fence.proxy.async + mbarrier.arrive
-//     (A_ready, 256 arrivals), the issuer answers with tcgen05.commit on the buffer's `done` barrier -- no __syncthreads in the chain,
+//     (A_ready, one arrival per warp), the issuer answers with tcgen05.commit on the buffer's `done` barrier -- no __syncthreads in the chain,
 //     and the gather / embedding of tile n+1 overlaps the MMAs of tile n.
 // Shared memory: 64 KB activations + 40 KB ring + 6 KB headers + < 6 KB state <= 113 KB, TMEM 256 columns -> two CTAs per SM, i.e. two
 // tiles in flight per SM with the hardware interleaving their (latency-bound) chains.
@@ -45,6 +45,13 @@ enum { B_FULL = 0, B_EMPTY = 4, B_HDR = 8, B_AREADY = 10, B_DONE = 12, kNumBars 
 __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// non-blocking poll (try_wait may suspend the thread for a hardware-defined time before it answers "not yet")
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
                : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
@@ -131,6 +138,13 @@ __device__ __forceinline__ bool loader_refill(Loader& L, const TileSmem& t, uint
   loader_issue(L, t);
   return true;
 }
+// request every unit whose slot is already free (non-blocking)
+__device__ __forceinline__ void loader_top_up(Loader& L, const TileSmem& t, uint32_t issued) {
+  while (!loader_done(L) && L.loaded < issued + kSlots) {
+    if (L.loaded >= kSlots) { const uint32_t prev = L.loaded - kSlots; if (!mbar_test(t.bars + B_EMPTY + (prev & (kSlots - 1)), (prev >> 2) & 1u)) return; }
+    loader_issue(L, t);
+  }
+}
 __device__ __forceinline__ void load_header(const KParams& P, const TileSmem& t, int lv, int hb) {
   uint64_t* bar = t.bars + B_HDR + hb;
   mbar_expect_tx(bar, kHdrFloats * 4u);
@@ -147,17 +161,11 @@ struct Issuer {
 __device__ __forceinline__ void issuer_wait_operands(Issuer& I, const TileSmem& t, int b, uint32_t parity) {
   uint64_t* bar = t.bars + B_AREADY + b;
   const long long t0 = clock64();
-  while (!mbar_try(bar, parity)) {
-    if (!loader_refill(I.L, t, I.issued) && clock64() - t0 > kWaitCycles) { printf("nsb: issuer timed out waiting for operands (block %d)\n", blockIdx.x); __trap(); }
+  while (!mbar_test(bar, parity)) {                              // poll: the ring is topped up between polls
+    loader_top_up(I.L, t, I.issued);
+    if (clock64() - t0 > kWaitCycles) { printf("nsb: issuer timed out waiting for operands (block %d)\n", blockIdx.x); __trap(); }
   }
   tc::tc_fence_after();
-}
-// request every unit whose slot is already free (non-blocking)
-__device__ __forceinline__ void loader_top_up(Loader& L, const TileSmem& t, uint32_t issued) {
-  while (!loader_done(L) && L.loaded < issued + kSlots) {
-    if (L.loaded >= kSlots) { const uint32_t prev = L.loaded - kSlots; if (!mbar_try(t.bars + B_EMPTY + (prev & (kSlots - 1)), (prev >> 2) & 1u)) return; }
-    loader_issue(L, t);
-  }
 }
 // the unit the issuer is about to consume: make sure it was requested, wait for it, return its slot base
 __device__ __forceinline__ const float* issuer_unit(Issuer& I, const TileSmem& t) {
@@ -173,15 +181,30 @@ __device__ __forceinline__ void issuer_unit_done(Issuer& I, const TileSmem& t) {
 }
 
 // D[128 x N] (+)= A[:, ka0 .. ka0 + 8 ksteps) * B^T, 3xTF32.  A: [128 x 32] hi|lo tile; B: unit [N x KB] hi|lo, product starts at column kb0.
+// The issuing thread is on the critical path of every layer step: descriptors are built once per unit and advanced by plain adds
+// (one k-step of 8 floats = two 128-byte core matrices = +16 in the 16-byte-granular start-address field; shared memory < 256 KB, so the
+// 14-bit field never carries).
 __device__ __forceinline__ void mma_unit(uint32_t d_tmem, const float* a, int ka0, const float* b, int N, int KB, int kb0, int ksteps, uint32_t& acc) {
-  tc::mma_3x(d_tmem, a, a + TM * 32, 32, ka0, b, b + N * KB, KB, kb0, ksteps, N, acc);
+  const uint32_t idesc = tc::make_idesc(TM, N);
+  uint64_t ah = tc::make_desc(a + (ka0 >> 2) * 32, 128u, 8u * 128u);
+  uint64_t bh = tc::make_desc(b + (kb0 >> 2) * 32, 128u, (uint32_t)(KB >> 2) * 128u);
+  uint64_t al = ah + (uint64_t)((TM * 32 * 4) >> 4);
+  uint64_t bl = bh + (uint64_t)((N * KB * 4) >> 4);
+#pragma unroll 1
+  for (int ks = 0; ks < ksteps; ks++) {
+    tc::mma_tf32(d_tmem, al, bh, idesc, acc); acc = 1u;
+    tc::mma_tf32(d_tmem, ah, bl, idesc, 1u);
+    tc::mma_tf32(d_tmem, ah, bh, idesc, 1u);
+    ah += 16u; al += 16u; bh += 16u; bl += 16u;
+  }
 }
 
 // ---- epilogue-side helpers -------------------------------------------------------------------------------------------------------
 // operands of this thread are written: make them visible to the async proxy, order earlier TMEM reads, arrive
 __device__ __forceinline__ void publish(const TileSmem& t, int b) {
   fence_proxy_async(); tc::tc_fence_before();
-  mbar_arrive(t.bars + B_AREADY + b);
+  __syncwarp();                                                 // one arrival per warp (256 arrivals on one barrier word serialise)
+  if ((threadIdx.x & 31) == 0) mbar_arrive(t.bars + B_AREADY + b);
 }
 __device__ __forceinline__ void wait_group(const TileSmem& t, uint32_t m) {      // MMAs of operand group m (and all earlier ones) have completed
   mbar_wait_b(t.bars + B_DONE + (m & 1u), (m >> 1) & 1u);
@@ -189,37 +212,31 @@ __device__ __forceinline__ void wait_group(const TileSmem& t, uint32_t m) {     
 }
 
 // 8 lanes per point, 4 points per pass: 32 channels of grid `g` -> [128 x 32] tile.  Warp w serves the rows of its lane quadrant (w & 3);
-// the eight passes of a quadrant are split over the two warps that share it (two batches of two passes, 16 loads in flight per lane).
+// the eight passes of a quadrant are split over the two warps that share it.
 __device__ __forceinline__ void gather_tile(const nsb_grid& g, float* __restrict__ c_hi, const float xn[3], int warp, int lane) {
   float* c_lo = c_hi + TM * 32;
   const bool fast = grid_fast(g);
   const int q = lane & 7, qd = warp & 3, it0 = (warp >> 2) * 4;
 #pragma unroll 1
-  for (int b = 0; b < 2; b++) {
-    Tri t[2]; float4 v[2][8];
+  for (int it = it0; it < it0 + 4; it++) {                       // 8 loads in flight per lane; the co-resident CTA supplies the rest of the MLP
+    const int src_lane = it * 4 + (lane >> 3);
+    float x[3];
+    x[0] = __shfl_sync(0xffffffffu, xn[0], src_lane); x[1] = __shfl_sync(0xffffffffu, xn[1], src_lane); x[2] = __shfl_sync(0xffffffffu, xn[2], src_lane);
+    const Tri t = make_tri(x, g.W, g.H, g.D);
+    float4 v[8];
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
-      const int src_lane = (it0 + 2 * b + u) * 4 + (lane >> 3);
-      float x[3];
-      x[0] = __shfl_sync(0xffffffffu, xn[0], src_lane); x[1] = __shfl_sync(0xffffffffu, xn[1], src_lane); x[2] = __shfl_sync(0xffffffffu, xn[2], src_lane);
-      t[u] = make_tri(x, g.W, g.H, g.D);
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        int cx, cy, cz;
-        tri_corner_clamped(t[u], k, g.W, g.H, g.D, cx, cy, cz);
-        v[u][k] = grid_load4(g, cz * g.stride_d + cy * g.stride_h + cx * g.stride_w, 4 * q, fast);
-      }
+    for (int k = 0; k < 8; k++) {
+      int cx, cy, cz;
+      tri_corner_clamped(t, k, g.W, g.H, g.D, cx, cy, cz);
+      v[k] = grid_load4(g, cz * g.stride_d + cy * g.stride_h + cx * g.stride_w, 4 * q, fast);
     }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const float w = tri_weight(t[u], k);
-        acc.x = fmaf(v[u][k].x, w, acc.x); acc.y = fmaf(v[u][k].y, w, acc.y); acc.z = fmaf(v[u][k].z, w, acc.z); acc.w = fmaf(v[u][k].w, w, acc.w);
-      }
-      tc::put4(c_hi, c_lo, qd * 32 + (it0 + 2 * b + u) * 4 + (lane >> 3), q, 32, acc);
+    for (int k = 0; k < 8; k++) {
+      const float w = tri_weight(t, k);
+      acc.x = fmaf(v[k].x, w, acc.x); acc.y = fmaf(v[k].y, w, acc.y); acc.z = fmaf(v[k].z, w, acc.z); acc.w = fmaf(v[k].w, w, acc.w);
     }
+    tc::put4(c_hi, c_lo, qd * 32 + src_lane, q, 32, acc);
   }
 }
 // this thread's 16 features of embedding block `blk` of its point -> [128 x 32] tile
@@ -480,25 +497,20 @@ __device__ __forceinline__ void scatter_tile(const nsb_grid& g, float* __restric
     const float4 d4 = *reinterpret_cast<const float4*>(dcs + row * cd + 4 * q);
     const float dc[4] = {d4.x, d4.y, d4.z, d4.w};
     float gi[3] = {0.f, 0.f, 0.f};
-    long long offs[8]; float4 vv[8]; bool ins[8];
+    float4 vv[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       int cx, cy, cz;
-      ins[k] = tri_corner(t, k, g.W, g.H, g.D, cx, cy, cz);
       tri_corner_clamped(t, k, g.W, g.H, g.D, cx, cy, cz);
-      offs[k] = cz * g.stride_d + cy * g.stride_h + cx * g.stride_w;
-      vv[k] = grid_load4(g, offs[k], 4 * q, fast);
+      vv[k] = grid_load4(g, cz * g.stride_d + cy * g.stride_h + cx * g.stride_w, 4 * q, fast);
     }
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      if (ins[k]) {
+      int cx, cy, cz;
+      if (tri_corner(t, k, g.W, g.H, g.D, cx, cy, cz)) {         // corners outside the grid get neither gradient nor a dot product
         const float4 v = vv[k];
         const float dot = v.x * dc[0] + v.y * dc[1] + v.z * dc[2] + v.w * dc[3];
-        if (dgrid != nullptr) {
-          int cx, cy, cz;
-          tri_corner(t, k, g.W, g.H, g.D, cx, cy, cz);
-          voxel_grad_add(g, dgrid, slots, offs[k], cx, cy, cz, q, fast, tri_weight(t, k), dc);
-        }
+        if (dgrid != nullptr) voxel_grad_add(g, dgrid, slots, cz * g.stride_d + cy * g.stride_h + cx * g.stride_w, cx, cy, cz, q, fast, tri_weight(t, k), dc);
         const float wx = (k & 1) ? t.w1[0] : t.w0[0], wy = (k & 2) ? t.w1[1] : t.w0[1], wz = (k & 4) ? t.w1[2] : t.w0[2];
         gi[0] += ((k & 1) ? 1.f : -1.f) * wy * wz * dot;
         gi[1] += ((k & 2) ? 1.f : -1.f) * wx * wz * dot;
@@ -603,6 +615,7 @@ __global__ void __maxnreg__(112) render_fwd_tile_kernel(const __grid_constant__ 
   TileSmem t; carve(smem_raw, t, false);
   __shared__ int s_ndone, s_done[kMaxTileRays], s_last;
   __shared__ float s_max[16];
+  __shared__ uint32_t s_seq;
 
   const bool points = P.points != nullptr;
   const int nsplit = P.split;
@@ -621,7 +634,7 @@ __global__ void __maxnreg__(112) render_fwd_tile_kernel(const __grid_constant__ 
   }
   Issuer I; I.L.P = &P; I.L.q = q0; I.L.q1 = q1; I.L.k = 0; I.L.loaded = 0; I.L.bwd = false; I.issued = 0; I.g = 0;
   if (tid == kEpiThreads) {
-    for (int i = 0; i < kNumBars; i++) mbar_init(t.bars + i, (i == B_AREADY || i == B_AREADY + 1) ? kEpiThreads : 1);
+    for (int i = 0; i < kNumBars; i++) mbar_init(t.bars + i, (i == B_AREADY || i == B_AREADY + 1) ? kEpiThreads / 32 : 1);
     mbar_fence_init();
     load_header(P, t, P.dec[q0], 0);
     for (int i = 0; i < kSlots; i++) loader_issue(I.L, t);      // (every decoder has >= 6 units)
@@ -647,6 +660,7 @@ __global__ void __maxnreg__(112) render_fwd_tile_kernel(const __grid_constant__ 
         __syncthreads();
         m = -INFINITY;
         for (int w = 0; w < kThreads / 32; w++) m = fmaxf(m, s_max[w]);
+        if (P.fs.px.world > 1) m = peer_max_all_ctas(P.fs.px, m, &s_seq);      // sharded batch: MAX over the ranks' shards (Renderer.py:109,144)
         gtmax = m; gtmax12 = __fmul_rn(m, 1.2f);
       }
     }
@@ -738,9 +752,9 @@ __global__ void __maxnreg__(112) render_fwd_tile_kernel(const __grid_constant__ 
   // loss seeds: the last CTA of the grid to get here sees every ray composited
   if (P.fs.kind != 0 && grid_last_arrival(P.fs.counter, gridDim.x, &s_last)) {
     if (P.fs.kind == 1) {
-      PeerX px; px.rank = 0; px.world = 0; px.counter = nullptr; px.max_n = 0;
       tracking_seeds_body(P.fo.depth, P.fo.var, P.fo.rgb, P.in.gt_depth, static_cast<const double*>(P.fs.gt_rgb), P.in.n_rays, P.fs.w_color,
-                          P.fs.handle_dynamic, P.fs.use_color, nullptr, 0, P.fs.g_depth, P.fs.g_rgb, P.fs.loss, P.fs.res, px, smem_raw);
+                          P.fs.handle_dynamic, P.fs.use_color, nullptr, 0, P.fs.g_depth, P.fs.g_rgb, P.fs.loss, P.fs.res, P.fs.px, smem_raw);
+      if (P.fs.px.world > 1 && P.in.depth_max == nullptr && tid == 0) peer_advance(P.fs.px, 0);      // every CTA is past the depth-max exchange
     } else {
       mapping_seeds_body(P.fo.depth, P.fo.rgb, P.fs.gt_depth_loss, static_cast<const float*>(P.fs.gt_rgb), P.in.n_rays, P.fs.w_color, P.fs.use_color,
                          P.fs.g_depth, P.fs.g_rgb, P.fs.loss, smem_raw);
@@ -786,7 +800,7 @@ __global__ void __maxnreg__(112) render_bwd_tile_kernel(const __grid_constant__ 
   }
   Issuer I; I.L.P = &P; I.L.q = q0; I.L.q1 = q1; I.L.k = 0; I.L.loaded = 0; I.L.bwd = true; I.issued = 0; I.g = 0;
   if (tid == kEpiThreads) {
-    for (int i = 0; i < kNumBars; i++) mbar_init(t.bars + i, (i == B_AREADY || i == B_AREADY + 1) ? kEpiThreads : 1);
+    for (int i = 0; i < kNumBars; i++) mbar_init(t.bars + i, (i == B_AREADY || i == B_AREADY + 1) ? kEpiThreads / 32 : 1);
     mbar_fence_init();
     load_header(P, t, P.dec[q0], 0);
     for (int i = 0; i < kSlots; i++) loader_issue(I.L, t);
@@ -935,7 +949,16 @@ __global__ void __maxnreg__(112) render_bwd_tile_kernel(const __grid_constant__ 
     if (P.bw.d_rays_o != nullptr) P.bw.d_rays_o[3 * ray + a] = (float)so;
     if (P.bw.d_rays_d != nullptr) P.bw.d_rays_d[3 * ray + a] = (float)sd;
   }
-  fused_pose_grad(P, gridDim.x, reinterpret_cast<double*>(smem_raw));
+  if (fused_pose_grad(P, gridDim.x, reinterpret_cast<double*>(smem_raw)) && P.tail.px.world > 1) {
+    // sharded tracking batch: SUM over ranks of [loss | d c2w] by this (last) CTA -- identical bits on every rank
+    __shared__ double tot[13];
+    __shared__ uint32_t s_seq2;
+    __syncthreads();
+    if (tid == 0) tot[0] = P.tail.loss != nullptr ? P.tail.loss[0] : 0.0;
+    if (tid < 12) tot[1 + tid] = P.bw.d_c2w[tid];
+    __syncthreads();
+    peer_sum13(P.tail.px, tot, 13, P.tail.out13, &s_seq2);
+  }
 }
 
 }  // namespace nsb

@@ -110,6 +110,15 @@ class ShardedTrackingIteration:
         self.packed = torch.zeros(13, dtype=torch.float64, device=dev)      # [loss | d_c2w(12)]
         self.peers = PeerExchange.create(ctx.n, dev) if exchange == "auto" else None
         self._p = None
+        # every rank's shard must have the same number of rays: the pooled median indexes the gathered residuals as [world][n] and
+        # all_gather_into_tensor needs equal sizes (pad the global batch to a multiple of the world size, or pass `counts` to gather_residuals)
+        if world()[1] > 1:
+            nn = torch.tensor([ctx.n, -ctx.n], dtype=torch.int64, device=dev)
+            dist.all_reduce(nn, op=dist.ReduceOp.MAX)
+            if int(nn[0]) != -int(nn[1]):
+                raise RuntimeError("nice_slam_b200: ShardedTrackingIteration needs equal shard sizes on all ranks (got %d here, max %d, min %d)"
+                                   % (ctx.n, int(nn[0]), -int(nn[1])))
+        self.fused = self.peers is not None and ctx.n <= 512          # whole iteration in two launches (exchanges inside the render kernels)
 
     def prepare(self, c, decoders, dirs, w_color=0.5, handle_dynamic=True, use_color=True):
         from . import _lib
@@ -137,6 +146,15 @@ class ShardedTrackingIteration:
         x, p = self.ctx, self._p
         n = x.n
         st = _stream()
+        if self.peers is not None and self.fused:
+            # TWO launches, no collective: depth maxima + median pool are exchanged inside the forward launch, [loss | d c2w] inside the backward's
+            bw = p["bw"]
+            bw.pose_dirs, bw.d_c2w, bw.pose_counter = p["dirs"].data_ptr(), x.d_c2w.data_ptr(), x.pose_counter.data_ptr()
+            inp = p["inp"]
+            inp.depth_max = None                                       # reduced + exchanged inside the forward kernel
+            _lib.check(L.nsb_tracking_iteration_peers(C.byref(inp), C.byref(x.buf), _VP(p["gc"].data_ptr()), p["w_color"], p["hd"], p["uc"], C.byref(bw),
+                                                      C.byref(self.peers.struct), _VP(self.packed.data_ptr()), st), "nsb_tracking_iteration_peers")
+            return self.packed
         if self.peers is not None:
             # five kernels, no collective launch: the three exchanges happen inside batch_max / seeds / pose_grad over peer memory
             px = C.byref(self.peers.struct)
@@ -214,7 +232,10 @@ class ShardedMappingIteration:
         self.ctx = ctx
         self._p = None
 
-    def prepare(self, c, decoders, dirs=None, frame_offsets=None, w_color=0.2):
+    def prepare(self, c, decoders, dirs=None, frame_offsets=None, w_color=0.2, global_gt_depth=None):
+        """global_gt_depth: the sensor depths of the WHOLE batch (every rank samples the same window pixels from replicated keyframes, so it
+        has them): the batch depth maxima (Renderer.py:109,144) are then computed locally on the full batch before sharding and the iteration
+        needs exactly ONE collective, the all-reduce of the packed gradient block.  None: MAX all-reduce of the shard maxima."""
         from . import _lib
         from .renderer import _inputs, _linspaces
         x = self.ctx
@@ -231,7 +252,8 @@ class ShardedMappingIteration:
                                                               x.g_rgb.data_ptr(), x.masks.data_ptr())
         bw.workspace = x.bwd_ws.data_ptr()
         self._p = dict(call=call, grids=grids, lin=(t_u, t_s), inp=inp, fo=fo, bw=bw, dirs=dirs, offs=frame_offsets, gd=gd, gc=gc,
-                       w_color=w_color, uc=int(x.stage == "color"))
+                       w_color=w_color, uc=int(x.stage == "color"), ggd=global_gt_depth)
+        self.collectives_per_step = (1 if (global_gt_depth is not None or not x.render_with_depth) else 2) if world()[1] > 1 else 0
 
     def enqueue(self):
         import ctypes as C
@@ -242,8 +264,11 @@ class ShardedMappingIteration:
         n, st = x.n, _stream()
         x.zero_grads()
         if x.render_with_depth:
-            _lib.check(L.nsb_batch_max_depth(_VP(p["gd"].data_ptr()), n, _VP(x.depth_max.data_ptr()), st), "nsb_batch_max_depth")
-            exchange_depth_max(x.depth_max)
+            if p["ggd"] is not None:                               # maxima of the full batch, no exchange
+                _lib.check(L.nsb_batch_max_depth(_VP(p["ggd"].data_ptr()), p["ggd"].numel(), _VP(x.depth_max.data_ptr()), st), "nsb_batch_max_depth")
+            else:
+                _lib.check(L.nsb_batch_max_depth(_VP(p["gd"].data_ptr()), n, _VP(x.depth_max.data_ptr()), st), "nsb_batch_max_depth")
+                exchange_depth_max(x.depth_max)
         _lib.check(L.nsb_render_forward(C.byref(p["inp"]), C.byref(p["fo"]), st), "nsb_render_forward")
         _lib.check(L.nsb_mapping_seeds(_VP(x.depth.data_ptr()), _VP(x.rgb.data_ptr()), _VP(p["gd"].data_ptr()), _VP(p["gc"].data_ptr()), n,
                                        p["w_color"], p["uc"], _VP(x.g_depth.data_ptr()), _VP(x.g_rgb.data_ptr()), _VP(x.loss.data_ptr()), st),

@@ -85,3 +85,60 @@ def test_peer_exchange_kernels_two_ranks_on_one_gpu(world, n):
         assert abs(float(tot[0] - loss[0])) <= 1e-9 * abs(float(loss[0]))
         assert float((tot[1:] - pose).abs().max()) <= 1e-9 * float(pose.abs().max())
         assert int(ctrs[0][0]) == rnd + 1 and int(ctrs[0][1]) == rnd + 1 and int(ctrs[0][2]) == rnd + 1
+
+
+@pytest.mark.parametrize("world,n", [(2, 100), (2, 37)])
+def test_two_launch_sharded_tracking_iteration_on_one_gpu(world, n):
+    """nsb_tracking_iteration_peers (forward + backward launches with the exchanges inside the tile kernels) for `world` ranks on ONE GPU
+    (one stream and one set of buffers per rank) == the single-rank tracking iteration over the whole batch: same depth maxima (hence
+    bit-identical samples), same median, same seeds, [loss | d c2w] summed over the ranks; replayed three times."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import scene_util as su
+    from gpu_util import make_renderer, rel
+    from nice_slam_b200.renderer import _inputs, _linspaces
+    from nice_slam_b200.steps import IterationContext
+    L = _lib.lib()
+    sc = su.load_scenes()["room0"]
+    renderer, c, dec = make_renderer(sc, su.make_grids(sc, "soft"), su.load_decoders("soft"), DEV)
+    N = world * n
+    ro, rd, gd, gc = su.make_rays(sc, N, seed=77)
+    dirs = torch.randn(N, 3, generator=torch.Generator().manual_seed(8))
+    full = IterationContext(renderer, N, "color", DEV, kind="track")
+    full.run(c, dec, ro.to(DEV), rd.to(DEV), gd.to(DEV), gc.double().to(DEV), dirs=dirs.to(DEV))
+    torch.cuda.synchronize()
+    want = torch.cat([full.loss.reshape(1), full.d_c2w.reshape(-1)]).clone()
+    want_rays = torch.cat([full.d_rays_o, full.d_rays_d], 1).clone()
+    nbytes = L.nsb_peer_buffer_bytes(n)
+    bufs = [torch.zeros(nbytes, dtype=torch.uint8, device=DEV) for _ in range(world)]
+    ctrs = [torch.zeros(4, dtype=torch.int64, device=DEV) for _ in range(world)]
+    peers = [_peers(r, world, bufs, ctrs[r], n) for r in range(world)]
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    ranks = []
+    for r in range(world):
+        sl = slice(r * n, (r + 1) * n)
+        x = IterationContext(renderer, n, "color", DEV, kind="track")
+        x.load_device_inputs(ro[sl].to(DEV), rd[sl].to(DEV), gd[sl].to(DEV), gc[sl].double().to(DEV))
+        vro, vrd, vgd, vgc = x.device_views()
+        call, grids, _ = renderer._call(c, dec, "color", vgd, torch.device(DEV))
+        t_u, t_s = _linspaces(renderer.N_samples, renderer.N_surface, torch.device(DEV))
+        inp = _inputs(call, vro, vrd, None, t_u, t_s, [g.detach() for g in grids])
+        bw = x._grads(c)
+        d = dirs[sl].to(DEV).contiguous()
+        bw.pose_dirs, bw.d_c2w, bw.pose_counter = d.data_ptr(), x.d_c2w.data_ptr(), x.pose_counter.data_ptr()
+        ranks.append(dict(x=x, inp=inp, bw=bw, gc=vgc, dirs=d, keep=(call, grids, t_u, t_s), out=torch.zeros(13, dtype=torch.float64, device=DEV)))
+    torch.cuda.synchronize()
+    for rnd in range(3):
+        for r in range(world):
+            k = ranks[r]
+            _lib.check(L.nsb_tracking_iteration_peers(C.byref(k["inp"]), C.byref(k["x"].buf), VP(k["gc"].data_ptr()), 0.5, 1, 1, C.byref(k["bw"]),
+                                                      C.byref(peers[r]), VP(k["out"].data_ptr()), VP(streams[r].cuda_stream)), "tracking_iteration_peers")
+        torch.cuda.synchronize()
+        for r in range(world):
+            k = ranks[r]
+            assert torch.equal(k["out"], ranks[0]["out"])
+            sl = slice(r * n, (r + 1) * n)
+            got_rays = torch.cat([k["x"].d_rays_o, k["x"].d_rays_d], 1)
+            assert rel(got_rays, want_rays[sl]) < 1e-5, (rnd, r, rel(got_rays, want_rays[sl]))
+        assert rel(ranks[0]["out"], want) < 1e-6, (rnd, rel(ranks[0]["out"], want))
+        assert all(int(ctrs[r][ch]) == rnd + 1 for r in range(world) for ch in range(3))
