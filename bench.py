@@ -132,6 +132,25 @@ def cpu_iteration_fn(sc, batch):
     return step
 
 
+def pick_cpu_threads(sc, batch):
+    """(seconds per iteration, threads): the faster of {1, all cores} by the MEDIAN of three timed iterations after one warm-up
+    (CPU grid_sample is single-threaded for batch 1 and oversubscribed MKL can be slower than one thread; a single sample per setting
+    made the choice flip between runs).  Leaves torch's thread count at the chosen setting."""
+    best = None
+    for threads in sorted({1, os.cpu_count() or 1}):
+        torch.set_num_threads(threads)
+        step = cpu_iteration_fn(sc, batch)
+        step()
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter(); step(); ts.append(time.perf_counter() - t0)
+        dt = statistics.median(ts)
+        if best is None or dt < best[0]:
+            best = (dt, threads)
+    torch.set_num_threads(best[1])
+    return best
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -139,19 +158,7 @@ def run_reference(args):
     import scene_util as su
     sc = su.load_scenes()["room0"]
     batch = make_batch(sc, RAYS_PER_GPU, 0)
-    best = None
-    for threads in sorted({1, os.cpu_count() or 1}):        # CPU grid_sample is single-threaded for batch 1: report the faster setting
-        torch.set_num_threads(threads)
-        step = cpu_iteration_fn(sc, batch)
-        for _ in range(max(1, min(args.warmup, 3))):
-            step()
-        t0 = time.perf_counter()
-        for _ in range(max(1, min(args.steps, 8))):
-            step()
-        dt = (time.perf_counter() - t0) / max(1, min(args.steps, 8))
-        if best is None or dt < best[0]:
-            best = (dt, threads)
-    torch.set_num_threads(best[1])
+    best = pick_cpu_threads(sc, batch)
     # bounded sample: keep the whole run within ~2.5 minutes whatever --steps is
     n_rays = RAYS_PER_GPU
     budget = 150.0
@@ -515,15 +522,7 @@ def run_native(args):
     if world == 1:
         line["extra"].update(extra_workloads(sc, renderer, c, dec, dev, flush, peak))
         line["extra"]["mapping_other_scenes"] = scene_workloads(dev, flush)
-        best = None
-        for threads in sorted({1, os.cpu_count() or 1}):      # CPU grid_sample is single-threaded for batch 1; oversubscribed MKL is slower
-            torch.set_num_threads(threads)
-            step = cpu_iteration_fn(sc, host)
-            step()
-            t0c = time.perf_counter(); step(); dt1 = time.perf_counter() - t0c
-            if best is None or dt1 < best[0]:
-                best = (dt1, threads)
-        torch.set_num_threads(best[1])
+        best = pick_cpu_threads(sc, host)
         step = cpu_iteration_fn(sc, host)
         t0c, k = time.perf_counter(), 0
         while k < 10 or time.perf_counter() - t0c < 10.0:

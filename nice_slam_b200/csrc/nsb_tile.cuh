@@ -7,14 +7,14 @@
 // bumps the counters of the rays it touches after publishing its per-point results, the CTA that brings a counter to its target value
 // composites / reduces that ray from global (L2) scratch in a fixed order (bit-reproducible), and resets the counter.
 //
-// CTA = 288 threads: 8 epilogue warps (two threads per tile row: thread tid owns row tid & 127 and the 16-column half tid >> 7 of every
-// 32-wide epilogue; warp w touches TMEM lanes [32 (w & 3), +32) = its rows) + 1 control warp whose lane 0 is the TMA producer AND the
-// tcgen05.mma issuer:
-//   * weights stream through a 4-slot ring of 10 KB operand UNITS (pre-split hi|lo canonical tiles, consumption order, nsb_common.cuh)
-//     with full (TMA -> issuer) and empty (tcgen05.commit -> producer) mbarriers: three units of prefetch, no thread touches a weight;
-//   * activations ping-pong between two 32 KB operand buffers; epilogue threads publish a tile by fence.proxy.async + mbarrier.arrive
-//     (A_ready, one arrival per warp), the issuer answers with tcgen05.commit on the buffer's `done` barrier -- no __syncthreads in the chain,
-//     and the gather / embedding of tile n+1 overlaps the MMAs of tile n.
+// CTA = 256 threads = two threads per tile row: thread tid owns row tid & 127 and the 16-column half tid >> 7 of every 32-wide epilogue
+// (warp w touches TMEM lanes [32 (w & 3), +32) = its rows).  Thread 0 is also the TMA producer and the tcgen05.mma issuer (a ninth, dedicated
+// control warp was measured first: registers are allocated per 4-warp granule, so 9 warps cost 12 warps' worth and only ONE CTA fitted per SM):
+//   * weights stream through a 4-slot ring of operand UNITS (pre-split hi|lo canonical tiles, consumption order, nsb_common.cuh) with full
+//     (TMA -> issuer) and empty (tcgen05.commit -> producer) mbarriers: three units of prefetch, no thread touches a weight;
+//   * activations ping-pong between two 32 KB operand buffers; warps publish a tile by fence.proxy.async + one mbarrier.arrive per warp
+//     (A_ready); thread 0 waits for the eight arrivals, issues the group's MMAs and commits to the buffer's `done` barrier -- there is no
+//     __syncthreads in the chain, and the gather / embedding of tile n+1 overlaps the MMAs of tile n.
 // Shared memory: 64 KB activations + 40 KB ring + 6 KB headers + < 6 KB state <= 113 KB, TMEM 256 columns -> two CTAs per SM, i.e. two
 // tiles in flight per SM with the hardware interleaving their (latency-bound) chains.
 //
@@ -26,9 +26,8 @@ namespace nsb {
 namespace tl {
 
 using tc::TM;
-constexpr int kEpiThreads = 256;
-constexpr int kThreads = 288;                 // + one control warp
-constexpr int kCtlWarp = 8;
+constexpr int kThreads = 256;                 // 8 warps: register allocation is per 4-warp granule, a ninth (control) warp would cost 12 warps' worth
+constexpr int kEpiThreads = kThreads;
 constexpr int kCG = 2, kCW = 16, kKQ = 4;      // column halves per row, columns per thread, 16-byte chunks per thread
 constexpr uint32_t kTmemCols = 256;
 constexpr int kSlots = 4;
@@ -66,7 +65,7 @@ __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }     // the 256 epilogue threads only
+__device__ __forceinline__ void epi_sync() { __syncthreads(); }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
@@ -255,53 +254,48 @@ __device__ __forceinline__ void embed_tile(float* __restrict__ e_hi, const float
   }
 }
 
-// ---- forward of one decoder for this CTA's tile: control side ---------------------------------------------------------------------
+// ---- forward: what the issuing thread (thread 0) does after the CTA published operand group I.g --------------------------------------------
 // TMEM: D1 = [0,32), D3 = [32,64) (layer 3; its skip part is accumulated while the embedding blocks are live), D2 = [64,224) (fc_c of the five layers)
-__device__ __forceinline__ void ctl_forward(Issuer& I, const TileSmem& t, int lv, uint32_t tmem) {
-  const bool xyz = lv != 0;
-  if (xyz) {
-    for (int half = 0; half < op_cd(lv) / 32; half++) {           // C tile(s): own grid, then (fine) the middle grid
-      const int b = I.g & 1;
-      issuer_wait_operands(I, t, b, (I.g >> 1) & 1u);
-      for (int u = 0; u < 4; u++) {
-        const float* w = issuer_unit(I, t);
-        uint32_t acc = (half == 0 && u == 0) ? 0u : 1u;
-        mma_unit(tmem + 64u, t.a[b], 8 * u, w, 160, 8, 0, 1, acc);
-        issuer_unit_done(I, t);
-      }
-      tc::mma_commit(t.bars + B_DONE + b);
-      I.g++;
-    }
-  }
-  const int nblk = xyz ? 3 : 1;
-  for (int blk = 0; blk < nblk; blk++) {                          // [D1 | D3] += E_blk * [W0_blk; W3E_blk]^T   (coarse: E = C)
-    const int b = I.g & 1;
-    issuer_wait_operands(I, t, b, (I.g >> 1) & 1u);
-    for (int h = 0; h < 2; h++) {
-      const float* w = issuer_unit(I, t);
-      uint32_t acc = (blk == 0 && h == 0) ? 0u : 1u;
-      mma_unit(tmem, t.a[b], 16 * h, w, 64, 16, 0, 2, acc);
-      issuer_unit_done(I, t);
-    }
-    tc::mma_commit(t.bars + B_DONE + b);
-    I.g++;
-  }
-  for (int i = 1; i < 5; i++) {                                   // layer i from the H tile of layer i-1
-    const int b = I.g & 1;
-    issuer_wait_operands(I, t, b, (I.g >> 1) & 1u);
+__device__ __forceinline__ void issue_fc(Issuer& I, const TileSmem& t, uint32_t tmem, int half) {      // C tile `half` -> D2 += C * Wc^T (four K = 8 units)
+  const int b = I.g & 1;
+  issuer_wait_operands(I, t, b, (I.g >> 1) & 1u);
+  for (int u = 0; u < 4; u++) {
     const float* w = issuer_unit(I, t);
-    uint32_t acc = i == 3 ? 1u : 0u;
-    mma_unit(i == 3 ? tmem + 32u : tmem, t.a[b], 0, w, 32, 32, 0, 4, acc);
+    uint32_t acc = (half == 0 && u == 0) ? 0u : 1u;
+    mma_unit(tmem + 64u, t.a[b], 8 * u, w, 160, 8, 0, 1, acc);
     issuer_unit_done(I, t);
-    tc::mma_commit(t.bars + B_DONE + b);
-    I.g++;
   }
+  tc::mma_commit(t.bars + B_DONE + b);
+  I.g++;
+}
+__device__ __forceinline__ void issue_l0(Issuer& I, const TileSmem& t, uint32_t tmem, int blk) {       // [D1 | D3] += E_blk * [W0_blk; W3E_blk]^T   (coarse: E = C)
+  const int b = I.g & 1;
+  issuer_wait_operands(I, t, b, (I.g >> 1) & 1u);
+  for (int h = 0; h < 2; h++) {
+    const float* w = issuer_unit(I, t);
+    uint32_t acc = (blk == 0 && h == 0) ? 0u : 1u;
+    mma_unit(tmem, t.a[b], 16 * h, w, 64, 16, 0, 2, acc);
+    issuer_unit_done(I, t);
+  }
+  tc::mma_commit(t.bars + B_DONE + b);
+  I.g++;
+}
+__device__ __forceinline__ void issue_h(Issuer& I, const TileSmem& t, uint32_t tmem, int i) {          // layer i (1..4) from the H tile of layer i-1
+  const int b = I.g & 1;
+  issuer_wait_operands(I, t, b, (I.g >> 1) & 1u);
+  const float* w = issuer_unit(I, t);
+  uint32_t acc = i == 3 ? 1u : 0u;
+  mma_unit(i == 3 ? tmem + 32u : tmem, t.a[b], 0, w, 32, 32, 0, 4, acc);
+  issuer_unit_done(I, t);
+  tc::mma_commit(t.bars + B_DONE + b);
+  I.g++;
 }
 
 // ---- forward of one decoder: epilogue side.  n = operand-group counter (same sequence as the issuer's).  out[] = decoder outputs of this row.
-__device__ __forceinline__ void epi_forward(const KParams& P, const TileSmem& t, int lv, const PointGeom& G, uint32_t tmem, uint32_t& n, int hb, uint32_t hdr_parity,
+__device__ __forceinline__ void epi_forward(const KParams& P, const TileSmem& t, Issuer& I, int lv, const PointGeom& G, uint32_t tmem, uint32_t& n, int hb, uint32_t hdr_parity,
                                             float (&out)[4], uint32_t* __restrict__ gmask) {
   const int row = threadIdx.x & (TM - 1), cg = threadIdx.x >> 7, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool t0 = threadIdx.x == 0;                            // the issuing thread: after every publish it waits for the other warps and issues the group's MMAs
   const bool xyz = lv != 0;
   const int cd = op_cd(lv), no = lv == 3 ? 4 : 1;
   const uint32_t my = ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kCW * cg);
@@ -312,17 +306,20 @@ __device__ __forceinline__ void epi_forward(const KParams& P, const TileSmem& t,
       if (n >= 2) wait_group(t, n - 2);
       gather_tile(P.in.grid[half == 0 ? lv : 1], t.a[n & 1], G.xn, warp, lane);
       publish(t, n & 1); n++;
+      if (t0) issue_fc(I, t, tmem, half);
     }
     mbar_wait_b(t.bars + B_HDR + hb, hdr_parity);
     for (int blk = 0; blk < 3; blk++) {
       if (n >= 2) wait_group(t, n - 2);
       embed_tile(t.a[n & 1], hdr + 464, G.pf, row, cg, blk);
       publish(t, n & 1); n++;
+      if (t0) issue_l0(I, t, tmem, blk);
     }
   } else {
     if (n >= 2) wait_group(t, n - 2);
     gather_tile(P.in.grid[0], t.a[n & 1], G.xnc, warp, lane);
     publish(t, n & 1); n++;
+    if (t0) issue_l0(I, t, tmem, 0);
     mbar_wait_b(t.bars + B_HDR + hb, hdr_parity);
   }
   float h[kCW];
@@ -346,6 +343,7 @@ __device__ __forceinline__ void epi_forward(const KParams& P, const TileSmem& t,
 #pragma unroll
     for (int k = 0; k < kKQ; k++) tc::put4(h_hi, h_hi + TM * 32, row, kKQ * cg + k, 32, make_float4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]));
     publish(t, n & 1); n++;
+    if (t0) issue_h(I, t, tmem, i + 1);
   }
   tc::tc_fence_before();
   // output layer: partial dot products over this thread's columns, summed over the two threads of the row through shared memory.
@@ -374,44 +372,39 @@ __device__ __forceinline__ void epi_forward(const KParams& P, const TileSmem& t,
   epi_sync();                                                    // partials consumed before the next decoder's gather reuses the buffer
 }
 
-// ---- backward of one decoder (input gradients): control side ----------------------------------------------------------------------
-// TMEM: D1 = [0,32) (g of the next layer), DC = [32,96) (dL/dc), DF = [96,192) (dL/d first input).  One operand group per layer: G in a[0], DU in a[1].
-__device__ __forceinline__ void ctl_backward(Issuer& I, const TileSmem& t, int lv, uint32_t tmem) {
+// ---- backward (input gradients): what the issuing thread does after the CTA published layer i's operands (G in a[0], DU in a[1]) ---------------
+// TMEM: D1 = [0,32) (g of the next layer), DC = [32,96) (dL/dc), DF = [96,192) (dL/d first input).
+__device__ __forceinline__ void issue_bwd_layer(Issuer& I, const TileSmem& t, uint32_t tmem, int lv, int i) {
   const bool xyz = lv != 0;
   const int cd = op_cd(lv), nfb = op_firstp(lv) / 32;
-  uint32_t acc_dc = 0, acc_df = 0;
-  for (int i = 4; i >= 0; i--) {
-    issuer_wait_operands(I, t, 0, I.g & 1u);
-    if (xyz) for (int c2 = 0; c2 < cd / 32; c2++) {               // DC += G * Wc_i
-      const float* w = issuer_unit(I, t);
-      uint32_t acc = acc_dc;
-      mma_unit(tmem + 32u + 32u * c2, t.a[0], 0, w, 32, 32, 0, 4, acc);
-      issuer_unit_done(I, t);
-    }
-    acc_dc = 1u;
-    if (i >= 1) {                                                 // D1 = DU * W_i[:, hidden]
-      const float* w = issuer_unit(I, t);
-      uint32_t acc = 0u;
-      mma_unit(tmem, t.a[1], 0, w, 32, 32, 0, 4, acc);
-      issuer_unit_done(I, t);
-    }
-    if (i == 3 || i == 0) {                                       // DF += DU * W_i[:, first input]
-      for (int fb = 0; fb < nfb; fb++) {
-        const float* w = issuer_unit(I, t);
-        uint32_t acc = acc_df;
-        mma_unit(tmem + 96u + 32u * fb, t.a[1], 0, w, 32, 32, 0, 4, acc);
-        issuer_unit_done(I, t);
-      }
-      acc_df = 1u;
-    }
-    tc::mma_commit(t.bars + B_DONE);
-    I.g++;
+  issuer_wait_operands(I, t, 0, I.g & 1u);
+  if (xyz) for (int c2 = 0; c2 < cd / 32; c2++) {               // DC += G * Wc_i
+    const float* w = issuer_unit(I, t);
+    uint32_t acc = i == 4 ? 0u : 1u;
+    mma_unit(tmem + 32u + 32u * c2, t.a[0], 0, w, 32, 32, 0, 4, acc);
+    issuer_unit_done(I, t);
   }
+  if (i >= 1) {                                                 // D1 = DU * W_i[:, hidden]
+    const float* w = issuer_unit(I, t);
+    uint32_t acc = 0u;
+    mma_unit(tmem, t.a[1], 0, w, 32, 32, 0, 4, acc);
+    issuer_unit_done(I, t);
+  }
+  if (i == 3 || i == 0) {                                       // DF += DU * W_i[:, first input]
+    for (int fb = 0; fb < nfb; fb++) {
+      const float* w = issuer_unit(I, t);
+      uint32_t acc = i == 3 ? 0u : 1u;
+      mma_unit(tmem + 96u + 32u * fb, t.a[1], 0, w, 32, 32, 0, 4, acc);
+      issuer_unit_done(I, t);
+    }
+  }
+  tc::mma_commit(t.bars + B_DONE);
+  I.g++;
 }
 
 // ---- backward of one decoder: epilogue side.  Leaves dL/dc rows ([128][cd] fp32) in a[0] and the embedding-chain partials of dL/dp
 // ([2][128][4] fp32) in a[1]; the caller scatters after an epi_sync().
-__device__ __forceinline__ void epi_backward(const KParams& P, const TileSmem& t, int lv, const PointGeom& G, uint32_t tmem, uint32_t& n, int hb, uint32_t hdr_parity,
+__device__ __forceinline__ void epi_backward(const KParams& P, const TileSmem& t, Issuer& I, int lv, const PointGeom& G, uint32_t tmem, uint32_t& n, int hb, uint32_t hdr_parity,
                                              const float (&g_out)[4], const uint32_t* __restrict__ gmask) {
   const int row = threadIdx.x & (TM - 1), cg = threadIdx.x >> 7, warp = threadIdx.x >> 5;
   const bool xyz = lv != 0;
@@ -442,6 +435,7 @@ __device__ __forceinline__ void epi_backward(const KParams& P, const TileSmem& t
                            (m >> (4 * k + 2)) & 1u ? g[4 * k + 2] : 0.0f, (m >> (4 * k + 3)) & 1u ? g[4 * k + 3] : 0.0f));
     }
     publish(t, 0);
+    if (threadIdx.x == 0) issue_bwd_layer(I, t, tmem, lv, i);
     mbar_wait_b(t.bars + B_DONE, n & 1u); n++;
     tc::tc_fence_after();
     if (i >= 1) tmem_ld16(tmem + my, g);
@@ -606,12 +600,11 @@ __device__ __forceinline__ void composite_ray(const KParams& P, int ray, int lan
 // ================================================================================================================================
 // forward kernel
 // ================================================================================================================================
-__global__ void __maxnreg__(112) render_fwd_tile_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(tl::kThreads, 2) render_fwd_tile_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using namespace tl;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = tid & (TM - 1), cg = tid >> 7;            // (control warp: row/cg unused)
-  const bool epi = warp < kCtlWarp;
   TileSmem t; carve(smem_raw, t, false);
   __shared__ int s_ndone, s_done[kMaxTileRays], s_last;
   __shared__ float s_max[16];
@@ -633,7 +626,7 @@ __global__ void __maxnreg__(112) render_fwd_tile_kernel(const __grid_constant__ 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   Issuer I; I.L.P = &P; I.L.q = q0; I.L.q1 = q1; I.L.k = 0; I.L.loaded = 0; I.L.bwd = false; I.issued = 0; I.g = 0;
-  if (tid == kEpiThreads) {
+  if (tid == 0) {
     for (int i = 0; i < kNumBars; i++) mbar_init(t.bars + i, (i == B_AREADY || i == B_AREADY + 1) ? kEpiThreads / 32 : 1);
     mbar_fence_init();
     load_header(P, t, P.dec[q0], 0);
@@ -701,7 +694,7 @@ __global__ void __maxnreg__(112) render_fwd_tile_kernel(const __grid_constant__ 
       const double z = zs[r * S + s];
       const float o[3] = {rays[8 * r], rays[8 * r + 1], rays[8 * r + 2]}, dd[3] = {rays[8 * r + 3], rays[8 * r + 4], rays[8 * r + 5]};
       make_point(P.in.bound, P.in.coarse_bound, o, dd, z, G);
-      if (epi && cg == 0 && row < npts && my == 0) P.fo.z_vals[gp] = z;
+      if (cg == 0 && row < npts && my == 0) P.fo.z_vals[gp] = z;
     }
     __syncthreads();                                              // the scratch is dead: the operand buffers may be written
   }
@@ -711,24 +704,15 @@ __global__ void __maxnreg__(112) render_fwd_tile_kernel(const __grid_constant__ 
   const uint32_t tmem = *t.tmem;
 
   float occ = 0.0f, c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
-  if (!epi) {
-    if (lane == 0) {
-      for (int qd = q0; qd < q1; qd++) {
-        ctl_forward(I, t, P.dec[qd], tmem);
-        // the first operands of decoder qd have arrived => decoder qd-1 is finished: its header buffer is free for decoder qd+1 -- but the
-        // issue point after the whole decoder is just as good for a 3 KB load that is needed one decoder later
-        if (qd + 1 < q1) load_header(P, t, P.dec[qd + 1], (qd + 1 - q0) & 1);
-      }
-    }
-    __syncwarp();
-  } else {
+  {
     uint32_t n = 0;
     for (int qd = q0; qd < q1; qd++) {
       const int lv = P.dec[qd];
       float out[4];
       uint32_t* gm = (P.fo.masks != nullptr && row < npts) ? P.fo.masks + ((gp0 + row) * 15 + qd * 5) : nullptr;
       const int dq = qd - q0;
-      epi_forward(P, t, lv, G, tmem, n, dq & 1, (dq >> 1) & 1u, out, gm);
+      if (tid == 0 && qd + 1 < q1) load_header(P, t, P.dec[qd + 1], (dq + 1) & 1);      // (decoder qd-1 ended with CTA barriers: its buffer is free)
+      epi_forward(P, t, I, lv, G, tmem, n, dq & 1, (dq >> 1) & 1u, out, gm);
       if (lv == 3) { c0 = out[0]; c1 = out[1]; c2 = out[2]; } else occ += out[0];
       if (qd == 0 && cg == 0 && row < npts && P.fo.corner_idx != nullptr) {
         const nsb_grid& g = P.in.grid[lv];
@@ -743,10 +727,10 @@ __global__ void __maxnreg__(112) render_fwd_tile_kernel(const __grid_constant__ 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
 
   if (points) {                                                   // Renderer.eval_points: raw with the out-of-bound override
-    if (epi && cg == 0 && row < npts) *reinterpret_cast<float4*>(P.points_raw + 4 * (gp0 + row)) = make_float4(c0, c1, c2, G.inb ? occ : 100.0f);
+    if (cg == 0 && row < npts) *reinterpret_cast<float4*>(P.points_raw + 4 * (gp0 + row)) = make_float4(c0, c1, c2, G.inb ? occ : 100.0f);
     return;
   }
-  if (epi && cg == 0 && row < npts) P.tile_parts[(long long)my * NP + gp0 + row] = make_float4(c0, c1, c2, occ);
+  if (cg == 0 && row < npts) P.tile_parts[(long long)my * NP + gp0 + row] = make_float4(c0, c1, c2, occ);
   const int nd = complete_rays(P.ray_cnt, ray_lo, nr, S, nsplit, s_done, &s_ndone);
   for (int k = warp; k < nd; k += kThreads / 32) composite_ray(P, s_done[k], lane, smem_raw + (size_t)warp * composite_scratch_bytes(S));
   // loss seeds: the last CTA of the grid to get here sees every ray composited
@@ -775,12 +759,11 @@ struct BwdExtra {            // behind the common shared-memory part
 };
 }  // namespace tl
 
-__global__ void __maxnreg__(112) render_bwd_tile_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(tl::kThreads, 2) render_bwd_tile_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using namespace tl;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = tid & (TM - 1), cg = tid >> 7;
-  const bool epi = warp < kCtlWarp;
   TileSmem t; carve(smem_raw, t, true);
   BwdExtra& X = *reinterpret_cast<BwdExtra*>(t.extra);
   __shared__ int s_ndone, s_done[kMaxTileRays];
@@ -799,7 +782,7 @@ __global__ void __maxnreg__(112) render_bwd_tile_kernel(const __grid_constant__ 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   Issuer I; I.L.P = &P; I.L.q = q0; I.L.q1 = q1; I.L.k = 0; I.L.loaded = 0; I.L.bwd = true; I.issued = 0; I.g = 0;
-  if (tid == kEpiThreads) {
+  if (tid == 0) {
     for (int i = 0; i < kNumBars; i++) mbar_init(t.bars + i, (i == B_AREADY || i == B_AREADY + 1) ? kEpiThreads / 32 : 1);
     mbar_fence_init();
     load_header(P, t, P.dec[q0], 0);
@@ -871,22 +854,14 @@ __global__ void __maxnreg__(112) render_bwd_tile_kernel(const __grid_constant__ 
     for (int a = 0; a < 3; a++) { o[a] = P.in.rays_o[3 * rayr + a]; d[a] = P.in.rays_d[3 * rayr + a]; }
     const double z = P.bw.z_vals[gpr];
     make_point(P.in.bound, P.in.coarse_bound, o, d, z, G);
-    if (epi && cg == 0) X.z[row] = z;
+    if (cg == 0) X.z[row] = z;
   }
   tc::tc_fence_before();
   __syncthreads();                                                // prologue scratch dead, gocc / wgt / gc visible, TMEM address + barriers visible
   tc::tc_fence_after();
   const uint32_t tmem = *t.tmem;
 
-  if (!epi) {
-    if (lane == 0) {
-      for (int qd = q0; qd < q1; qd++) {
-        ctl_backward(I, t, P.dec[qd], tmem);
-        if (qd + 1 < q1) load_header(P, t, P.dec[qd + 1], (qd + 1 - q0) & 1);
-      }
-    }
-    __syncwarp();
-  } else {
+  {
     uint32_t n = 0;
     for (int qd = q0; qd < q1; qd++) {
       const int lv = P.dec[qd];
@@ -897,7 +872,8 @@ __global__ void __maxnreg__(112) render_bwd_tile_kernel(const __grid_constant__ 
         else g_out[0] = X.gocc[row];
       }
       const int dq = qd - q0;
-      epi_backward(P, t, lv, G, tmem, n, dq & 1, (dq >> 1) & 1u, g_out, gm);
+      if (tid == 0 && qd + 1 < q1) load_header(P, t, P.dec[qd + 1], (dq + 1) & 1);      // (the previous decoder ended with CTA barriers: its buffer is free)
+      epi_backward(P, t, I, lv, G, tmem, n, dq & 1, (dq >> 1) & 1u, g_out, gm);
       epi_sync();                                                 // dL/dc rows + embedding partials visible
       const double* bb = lv == 0 ? P.in.coarse_bound : P.in.bound;
       const double sc[3] = {2.0 / (bb[1] - bb[0]), 2.0 / (bb[3] - bb[2]), 2.0 / (bb[5] - bb[4])};      // d(normalised)/dp, common.py:280-282

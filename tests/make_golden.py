@@ -460,7 +460,61 @@ def gen_mapper_ba_cases():
                                    w_color_loss=cfg["mapping"]["w_color_loss"]))
 
 
+def gen_keyframe_overlap_case():
+    """keyframe_overlap.pt: the REAL Mapper.keyframe_selection_overlap (src/Mapper.py:166-228) on twelve synthetic keyframes -- some looking
+    the same way as the current frame, some turned away (no overlap) -- with the pixel draw, the per-keyframe percent_inside and the
+    selection the reference made under a fixed numpy seed."""
+    rh.import_reference()
+    import src.Mapper as mapper_mod
+    sc, cfg, slam, renderer = ref_scene("room0", "soft")
+    mapper = rh.make_mapper(cfg, slam, renderer)
+    depth, color = su.make_frame(sc, 1)
+    c2w = su.make_pose(sc, 1)
+    g = torch.Generator().manual_seed(2024)
+    kf = []
+    for k in range(12):
+        p = su.make_pose(sc, 40 + k)
+        if k % 3 == 2:                                    # every third keyframe looks backwards: no overlap
+            flip = torch.diag(torch.tensor([-1.0, 1.0, -1.0]))
+            p[:3, :3] = p[:3, :3] @ flip
+        p[:3, 3] += (torch.rand(3, generator=g) - 0.5) * 2.0
+        kf.append(dict(est_c2w=p, gt_c2w=p.clone(), idx=5 * k, depth=depth, color=color))
+    samples, recorded = [], []
+    _gs = mapper_mod.get_samples
+
+    def get_samples_rec(*a, **k):
+        r = _gs(*a, **k)
+        samples.append([t.detach().clone() for t in r])
+        return r
+    mapper_mod.get_samples = get_samples_rec
+    # percent_inside is not returned by the reference: recompute it from the list it sorts by wrapping `sorted`
+    import builtins
+    _sorted = builtins.sorted
+
+    def sorted_rec(it, *a, **k):
+        it = list(it)
+        if it and isinstance(it[0], dict) and "percent_inside" in it[0]:
+            recorded.append([(d["id"], float(d["percent_inside"])) for d in it])
+        return _sorted(it, *a, **k)
+    mapper_mod.sorted = sorted_rec
+    try:
+        torch.manual_seed(99); np.random.seed(99)
+        sel = mapper.keyframe_selection_overlap(color, depth, c2w, kf, 4)
+    finally:
+        mapper_mod.get_samples = _gs
+        del mapper_mod.sorted
+    ro, rd, gd, gc = samples[0]
+    save("keyframe_overlap.pt", dict(scene="room0", frame_seed=1, pose_seed=1, keyframe_c2w=torch.stack([d["est_c2w"] for d in kf]),
+                                     rays_o=ro, rays_d=rd, gt_depth=gd, percent_inside=[p for _, p in recorded[0]], k=4, numpy_seed=99,
+                                     selected=[int(x) for x in sel]))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "keyframes":
+        import warnings
+        warnings.filterwarnings("ignore")
+        gen_keyframe_overlap_case()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "mapper_ba":
         import warnings
         warnings.filterwarnings("ignore")
@@ -481,3 +535,4 @@ if __name__ == "__main__":
     gen_mapper_cases()
     gen_mapper_loop_case()
     gen_mapper_ba_cases()
+    gen_keyframe_overlap_case()

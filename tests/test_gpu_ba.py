@@ -107,17 +107,28 @@ def test_ba_window_gradients_against_real_mapper(stage):
     m = torch.zeros(5, 7, device=DEV); v = torch.zeros(5, 7, device=DEV); dc = torch.zeros(5, 7, device=DEV)
     _lib.check(L.nsb_adam_poses(VP(cams.data_ptr()), VP(cam_row_d.data_ptr()), F, VP(ctx.d_frames.data_ptr()), VP(m.data_ptr()), VP(v.data_ptr()), VP(dc.data_ptr()),
                                 0.0, 0.9, 0.999, 1e-8, 1, None), "adam_poses")
-    assert rel(dc, st["d_cameras"]) < 1e-4, rel(dc, st["d_cameras"])
+    # The mapping loss is an L1: a ray whose rendered depth (colour) is within rounding of the sensor value can take the other sign on the GPU,
+    # which changes ITS gradient by 200 % and the window's pose gradient by ~2/976.  So: per-ray gradients against the oracle on the same rays
+    # (all but a handful must agree to 1e-4 of the largest), and the camera gradients to the knife-edge budget of a few such rays.
+    lv = {"middle": ("grid_middle",), "fine": ("grid_middle", "grid_fine"), "color": ("grid_middle", "grid_fine", "grid_color")}[stage]
+    want = tp.iteration("map", su.make_grids(sc, case["variant"]), su.load_decoders(case["variant"]), st["rays_o"], st["rays_d"], st["gt_depth_loss"], st["gt_color"],
+                        stage, su.scene_bound(sc), grad_grids=lv, grad_decoders=())
+    per_ray = torch.cat([ctx.d_rays_o, ctx.d_rays_d], 1).cpu() - torch.cat([want["d_rays_o"], want["d_rays_d"]], 1)
+    scale = float(torch.cat([want["d_rays_o"], want["d_rays_d"]], 1).abs().max())
+    flipped = int((per_ray.abs().amax(1) > 1e-4 * scale).sum())
+    assert flipped <= 3, flipped
+    assert rel(dc, st["d_cameras"]) < 1e-4 + 4e-3 * flipped, (rel(dc, st["d_cameras"]), flipped)
+    tol = 1e-4 + 4e-3 * flipped
     for k, summ in st["masked_grads"].items():
         got = mv[k].to_reference(ctx.d_grid[k]).cpu()
         mine = su.grid_summary(got, n_sample=4096)
-        assert abs(mine["norm"] - summ["norm"]) < 1e-4 * summ["norm"], k
-        assert rel(got[summ["idx"]], summ["val"]) < 1e-4, k
+        assert abs(mine["norm"] - summ["norm"]) < tol * summ["norm"], k
+        assert rel(got[summ["idx"]], summ["val"]) < tol, k
     if stage == "color":
         lay = {nm: (off, cnt) for nm, off, cnt in flat_layout(LEVELS.index("color"))}
         for k, vgrad in st["d_color_decoder"].items():
             off, cnt = lay[k]
-            assert rel(ctx.d_flat["color"][off:off + cnt].view_as(vgrad), vgrad) < 1e-4, k
+            assert rel(ctx.d_flat["color"][off:off + cnt].view_as(vgrad), vgrad) < tol, k
 
 
 def test_ba_loop_against_real_mapper():

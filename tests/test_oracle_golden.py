@@ -275,3 +275,20 @@ def test_oracle_reproduces_ba_loop_with_adam():
     for k, fin in case["final"].items():
         gotv = val_grad[k].detach()[fin["idx"]]
         assert torch.allclose(gotv, fin["val"], rtol=1e-4, atol=2e-5), (k, float((gotv - fin["val"]).abs().max()))
+
+
+def test_keyframe_overlap_oracle_matches_real_mapper():
+    """oracle/keyframes.py against the REAL Mapper.keyframe_selection_overlap (tests/golden/keyframe_overlap.pt): the same percent_inside for
+    every keyframe (exact counts) and, under the same numpy seed, the same selected keyframes."""
+    import numpy as np
+    from oracle import keyframes as kf
+    case = torch.load(os.path.join(su.GOLDEN, "keyframe_overlap.pt"), map_location="cpu", weights_only=False)
+    sc = su.load_scenes()[case["scene"]]
+    cam = sc["cam"]
+    pts = kf.overlap_points(case["rays_o"], case["rays_d"], case["gt_depth"])
+    per = [kf.percent_inside(pts, c2w, cam["H"], cam["W"], cam["fx"], cam["fy"], cam["cx"], cam["cy"])[0] for c2w in case["keyframe_c2w"]]
+    assert [float(p) for p in per] == case["percent_inside"]
+    assert sum(p == 0 for p in per) >= 3 and sum(p > 0 for p in per) > case["k"]
+    # the reference draws its pixels with the torch RNG first; only the numpy stream matters for the permutation
+    rng = np.random.RandomState(case["numpy_seed"])
+    assert [int(x) for x in kf.select(per, case["k"], rng)] == case["selected"]
