@@ -228,6 +228,19 @@ int nsb_frustum_mask(const float* c2w, const float* xs, const float* ys, const f
 int nsb_pose_grad_frames(const float* dirs, const float* d_rays_o, const float* d_rays_d, const int32_t* frame_offsets,
                          int n_frames, float* out, void* stream);
 
+/* ---- keyframe store (src/Mapper.py:166-228 overlap selection, :437-462 per-frame samples) -----------------------------------
+ * nsb_keyframe_overlap: for each of n_keyframes world-to-camera matrices w2c[k] (row-major [4][4] float32 = numpy.linalg.inv(est_c2w), as the
+ * reference computes it on the host), counts[k] = number of the n_rays * n_samples points  o + d * (0.8 gt (1 - t) + (gt + 0.5) t)  that project
+ * to  edge < u < W - edge, edge < v < H - edge  in front of the camera (Mapper.py:186-216; percent_inside = counts[k] / (n_rays * n_samples)).
+ * t_vals = torch.linspace(0, 1, n_samples) (float32, device).
+ * nsb_keyframe_gather: out_depth[f][k] = depth[slot[f]][pix_j[f][k]][pix_i[f][k]] (and the 3 colour channels) from keyframe images kept
+ * resident on the device ([n_slots][H][W] float32, [n_slots][H][W][3] float32) instead of Mapper.py:439-440's per-iteration host->device copy. */
+int nsb_keyframe_overlap(const float* rays_o, const float* rays_d, const float* gt_depth, int n_rays, const float* t_vals, int n_samples,
+                         const float* w2c, int n_keyframes, int H, int W, double fx, double fy, double cx, double cy, int edge,
+                         int32_t* counts, void* stream);
+int nsb_keyframe_gather(const float* depth, const float* color, const int32_t* slot, const int32_t* pix_i, const int32_t* pix_j,
+                        int n_frames, int n_pix, int H, int W, float* out_depth, float* out_color, void* stream);
+
 /* ---- bundle-adjustment window (src/Mapper.py:346-363 camera tensors, :437-467 per-frame get_samples, :521-540 write-back) -----------------
  * A window has n_frames rows (the selected keyframes + the current frame).  Row f is either optimised -- its pose is camera tensor
  * cams[cam_row[f]] = [qw,qx,qy,qz,tx,ty,tz] (get_tensor_from_camera, src/common.py:179-200) -- or fixed (cam_row[f] = -1: the oldest frame,

@@ -98,6 +98,9 @@ SYMBOLS = {
     "nsb_frustum_mask_workspace": (C.c_size_t, [C.c_longlong]),
     "nsb_frustum_mask": (C.c_int, [C.POINTER(C.c_float), _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int,
                                    C.c_double, C.c_double, C.c_double, C.c_double, _P, _P, C.c_size_t, _P]),
+    "nsb_keyframe_overlap": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                       C.c_int, _P, _P]),
+    "nsb_keyframe_gather": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "nsb_window_rays": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _P, _P, _P, _P, _P]),
     "nsb_adam_poses": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, _P]),
     "nsb_peer_buffer_bytes": (C.c_size_t, [C.c_int]),

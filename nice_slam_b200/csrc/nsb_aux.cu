@@ -776,6 +776,79 @@ extern "C" int nsb_bbox_prefilter(const float* rays_o, const float* rays_d, cons
   return check_cuda(cudaGetLastError(), "prefilter launch");
 }
 
+// ------------------------------------------------------------------------------------------------ keyframe store
+// Mapper.keyframe_selection_overlap (src/Mapper.py:186-218): the n_samples points of every sampled ray of the current frame, between
+// 0.8 * gt_depth and gt_depth + 0.5, are projected into every keyframe; counts[k] = points inside keyframe k's (edge-cropped) image and in
+// front of its camera.  One CTA per keyframe.  float32 points and w2c product, float64 intrinsics product, float32 pixel compare -- the
+// dtype flow of the reference's torch / numpy code.
+__global__ void keyframe_overlap_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ gt_depth,
+                                        int n_rays, const float* __restrict__ t_vals, int n_samples, const float* __restrict__ w2c,
+                                        int H, int W, double fx, double fy, double cx, double cy, int edge, int32_t* __restrict__ counts) {
+  __shared__ int red[32];
+  const float* m = w2c + (size_t)blockIdx.x * 16;
+  float M[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) M[i] = m[i];
+  int cnt = 0;
+  const int np = n_rays * n_samples;
+  for (int p = threadIdx.x; p < np; p += blockDim.x) {
+    const int r = p / n_samples, s = p - r * n_samples;
+    const float gd = gt_depth[r], t = t_vals[s];
+    const float z = __fadd_rn(__fmul_rn(__fmul_rn(gd, 0.8f), __fsub_rn(1.0f, t)), __fmul_rn(__fadd_rn(gd, 0.5f), t));      // Mapper.py:189-192
+    float x[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) x[a] = __fadd_rn(rays_o[3 * r + a], __fmul_rn(rays_d[3 * r + a], z));                          // :193-194
+    float c[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++)                                                                                                // w2c @ [x, 1], :203
+      c[a] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[4 * a], x[0]), __fmul_rn(M[4 * a + 1], x[1])), __fmul_rn(M[4 * a + 2], x[2])), M[4 * a + 3]);
+    const double X = -(double)c[0], Y = (double)c[1], Z = (double)c[2];                                                        // :207
+    const double uz = Z + 1e-5;                                                                                                // K @ cam, :208-209
+    const float u = (float)((fx * X + cx * Z) / uz), v = (float)((fy * Y + cy * Z) / uz);                                      // :210-211
+    const bool in = u < (float)(W - edge) && u > (float)edge && v < (float)(H - edge) && v > (float)edge && uz < 0.0;          // :213-215
+    cnt += in ? 1 : 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) counts[blockIdx.x] = t;
+  }
+}
+extern "C" int nsb_keyframe_overlap(const float* rays_o, const float* rays_d, const float* gt_depth, int n_rays, const float* t_vals, int n_samples,
+                                    const float* w2c, int n_keyframes, int H, int W, double fx, double fy, double cx, double cy, int edge,
+                                    int32_t* counts, void* stream) {
+  if (n_rays < 0 || n_samples < 1 || n_keyframes < 0 || (n_keyframes > 0 && (!w2c || !counts)) || (n_rays > 0 && (!rays_o || !rays_d || !gt_depth || !t_vals))) {
+    set_error("keyframe_overlap: bad arguments"); return NSB_ERR_ARG; }
+  if (n_keyframes == 0) return NSB_OK;
+  keyframe_overlap_kernel<<<n_keyframes, 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, gt_depth, n_rays, t_vals, n_samples, w2c, H, W, fx, fy, cx, cy, edge, counts);
+  return check_cuda(cudaGetLastError(), "keyframe_overlap launch");
+}
+
+// Per-frame pixel samples of a mapping window from the device-resident keyframe store (what Mapper.py:437-462 obtains with a host->device copy of
+// the full keyframe images followed by get_samples' indexing): out_depth[f][k] = depth[slot[f]][j][i], out_color likewise (3 channels).
+__global__ void keyframe_gather_kernel(const float* __restrict__ depth, const float* __restrict__ color, const int32_t* __restrict__ slot,
+                                       const int32_t* __restrict__ pix_i, const int32_t* __restrict__ pix_j, int n_frames, int n_pix, int H, int W,
+                                       float* __restrict__ out_depth, float* __restrict__ out_color) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_frames * n_pix) return;
+  const int f = idx / n_pix;
+  const size_t px = ((size_t)slot[f] * H + pix_j[idx]) * W + pix_i[idx];
+  out_depth[idx] = depth[px];
+  out_color[3 * idx] = color[3 * px]; out_color[3 * idx + 1] = color[3 * px + 1]; out_color[3 * idx + 2] = color[3 * px + 2];
+}
+extern "C" int nsb_keyframe_gather(const float* depth, const float* color, const int32_t* slot, const int32_t* pix_i, const int32_t* pix_j,
+                                   int n_frames, int n_pix, int H, int W, float* out_depth, float* out_color, void* stream) {
+  if (n_frames < 0 || n_pix < 0 || H < 1 || W < 1 || (n_frames * n_pix > 0 && (!depth || !color || !slot || !pix_i || !pix_j || !out_depth || !out_color))) {
+    set_error("keyframe_gather: bad arguments"); return NSB_ERR_ARG; }
+  const int n = n_frames * n_pix;
+  if (n == 0) return NSB_OK;
+  keyframe_gather_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(depth, color, slot, pix_i, pix_j, n_frames, n_pix, H, W, out_depth, out_color);
+  return check_cuda(cudaGetLastError(), "keyframe_gather launch");
+}
+
 extern "C" size_t nsb_tracking_seeds_workspace(int n) { return (size_t)(n > 0 ? n : 1) * sizeof(double); }
 
 __global__ void residuals_kernel(const double* __restrict__ depth, const double* __restrict__ var, const float* __restrict__ gt,

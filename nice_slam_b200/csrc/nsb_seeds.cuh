@@ -2,6 +2,10 @@
 // helpers.  Used by the stand-alone single-CTA kernels of nsb_aux.cu and, fused, by the LAST CTA of the forward render kernels
 // (nsb_render.cu): for small batches the loss seeds are produced by the forward launch itself.
 #pragma once
+// NOTE: no __restrict__ in this header.  These bodies communicate between threads through `scratch` / `res` across __syncthreads() and, in the
+// fused form, read depth / var / rgb that OTHER CTAs of the same launch have just written.  With noalias pointers the compiler may treat a
+// barrier as not touching that memory: it forwarded `sel[]` across the barrier of the radix select (loading it BEFORE the writer's store in the
+// other threads) -- found with n > 512 in the stand-alone kernel -- and it may route const noalias loads through the non-coherent path.
 #include <cstdio>
 #include "nsb_common.cuh"
 
@@ -78,7 +82,7 @@ __device__ __forceinline__ void peer_advance(const PeerX& px, int c) {      // o
   px.counter[c] = px.counter[c] + 1ull;
 }
 // SUM over ranks of `n_val` (<= 13) doubles held in shared memory `tot` (channel 2), rank order -> identical bits on every rank.  Single CTA.
-__device__ __forceinline__ void peer_sum13(const PeerX& px, const double* __restrict__ tot, int n_val, double* __restrict__ out, uint32_t* s_seq) {
+__device__ __forceinline__ void peer_sum13(const PeerX& px, const double* tot, int n_val, double* out, uint32_t* s_seq) {
   const uint32_t seq = peer_begin(px, 2, s_seq);
   const int par = seq & 1u;
   for (int i = threadIdx.x; i < n_val * px.world; i += blockDim.x) {
@@ -112,11 +116,11 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 __device__ __forceinline__ double sgn(double x) { return (x > 0.0) - (x < 0.0); }
 
 // Tracker.optimize_cam_in_batch loss (src/Tracker.py:108-123); single CTA, residuals staged in `res`.
-__device__ __forceinline__ void tracking_seeds_body(const double* __restrict__ depth, const double* __restrict__ var, const float* __restrict__ rgb,
-                                      const float* __restrict__ gt, const double* __restrict__ gt_rgb, int n, double w_color,
-                                      int handle_dynamic, int use_color, const double* __restrict__ pool, int n_pool,
-                                      double* __restrict__ g_depth, float* __restrict__ g_rgb,
-                                      double* __restrict__ loss, double* __restrict__ res, const PeerX& px, unsigned char* __restrict__ scratch) {
+__device__ __forceinline__ void tracking_seeds_body(const double* depth, const double* var, const float* rgb,
+                                      const float* gt, const double* gt_rgb, int n, double w_color,
+                                      int handle_dynamic, int use_color, const double* pool, int n_pool,
+                                      double* g_depth, float* g_rgb,
+                                      double* loss, double* res, const PeerX& px, unsigned char* scratch) {
   // scratch (kSeedsScratchBytes, 16-byte aligned shared memory): red[32] f64 | med_s f64 | med_key u64 | keys[kMedianDirect] u64 | hist[256] | wtot[8] | sel[2] | seq
   double* red = reinterpret_cast<double*>(scratch);
   double& med_s = red[32];
@@ -217,10 +221,10 @@ __device__ __forceinline__ void tracking_seeds_body(const double* __restrict__ d
 }
 
 // Mapper.optimize_map loss (src/Mapper.py:487-493); single CTA (deterministic sum)
-__device__ __forceinline__ void mapping_seeds_body(const double* __restrict__ depth, const float* __restrict__ rgb, const float* __restrict__ gt,
-                                     const float* __restrict__ gt_rgb, int n, double w_color, int use_color,
-                                     double* __restrict__ g_depth, float* __restrict__ g_rgb, double* __restrict__ loss,
-                                     unsigned char* __restrict__ scratch) {
+__device__ __forceinline__ void mapping_seeds_body(const double* depth, const float* rgb, const float* gt,
+                                     const float* gt_rgb, int n, double w_color, int use_color,
+                                     double* g_depth, float* g_rgb, double* loss,
+                                     unsigned char* scratch) {
   double* red = reinterpret_cast<double*>(scratch);
   double acc = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {

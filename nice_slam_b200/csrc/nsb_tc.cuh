@@ -49,7 +49,7 @@ __device__ __forceinline__ float to_tf32(float x) { return __uint_as_float(__flo
 // element (row r, k) of a canonical tile of width K floats
 __device__ __forceinline__ int canon_q(int r, int kq, int K) { return ((r >> 3) * (K >> 2) + kq) * 32 + (r & 7) * 4; }
 
-__device__ __forceinline__ void put4(float* __restrict__ hi, float* __restrict__ lo, int r, int kq, int K, float4 v) {
+__device__ __forceinline__ void put4(float* hi, float* lo, int r, int kq, int K, float4 v) {
   const int idx = canon_q(r, kq, K);
   float4 h, l;
   h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
@@ -192,7 +192,7 @@ __device__ __forceinline__ void issue_bwd_loads(const KParams& P, const TcSmem& 
 
 // 8 lanes per point, 4 points per pass: gather the 32 channels of `g` into columns [col0, col0+32) of the C tile.  Warp w serves
 // the rows of its lane quadrant (w & 3); the eight passes of a quadrant are split over the kCG warps that share it.
-__device__ __forceinline__ void gather_rows(const nsb_grid& g, float* __restrict__ c_hi, float* __restrict__ c_lo, int KC, int col0,
+__device__ __forceinline__ void gather_rows(const nsb_grid& g, float* c_hi, float* c_lo, int KC, int col0,
                                             const float xn[3], int warp, int lane) {
   const bool fast = grid_fast(g);
   const int q = lane & 7, qd = warp & 3, it0 = (warp >> 2) * (8 / kCG);
@@ -224,7 +224,7 @@ __device__ __forceinline__ void gather_rows(const nsb_grid& g, float* __restrict
 }
 
 // this thread's kCW features of E block `blk` (features 32*blk .. +31, zero beyond 93) of its point -> canonical hi|lo tile of width 32
-__device__ __forceinline__ void embed_row(float* __restrict__ e_hi, float* __restrict__ e_lo, const float* __restrict__ B /*packed [3][96]*/,
+__device__ __forceinline__ void embed_row(float* e_hi, float* e_lo, const float* B /*packed [3][96]*/,
                                           const float pf[3], int row, int cg, int blk) {
 #pragma unroll
   for (int kq = kKQ * cg; kq < kKQ * cg + kKQ; kq++) {
@@ -502,7 +502,7 @@ __device__ __forceinline__ void dpe_sum(const TcSmem& t, int row, float (&dpe)[3
 // and hands the normalised-coordinate gradient of each point to emit(row, gx).
 template <typename F>
 __device__ __forceinline__ void scatter_rows(const nsb_grid& g, float* __restrict__ dgrid, const int32_t* __restrict__ slots,
-                                             const float* __restrict__ dcs, int cd,
+                                             const float* dcs, int cd,
                                              const float xn[3], int warp, int lane, F&& emit) {
   const bool fast = grid_fast(g);
   const int q = lane & 7, qd = warp & 3, it0 = (warp >> 2) * (8 / kCG);

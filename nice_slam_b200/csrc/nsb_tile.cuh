@@ -156,46 +156,70 @@ struct Issuer {
   uint32_t issued;    // units consumed so far
   uint32_t g;         // operand groups consumed so far (forward: buffer = g & 1)
 };
-// wait for the operands of group `g` on A_ready[b]; while they are not there, keep the ring full
+// The issue path is executed by ALL lanes of warp 0, converged: everything that feeds a tcgen05.mma (descriptors, TMEM address, the
+// counters `issued` / `g`) is computed identically in every lane from warp-uniform inputs, so ptxas keeps it in uniform registers and one
+// elected lane issues the instruction.  (Issued from a single divergent thread, every MMA was wrapped in an ELECT / 5 x R2UR.BROADCAST /
+// branch "waterfall": ~1 k cycles per 32 x 32 layer of twelve MMAs, 40 % of both kernels.)  Only the TMA producer bookkeeping (Loader) is
+// lane 0's private, divergent state.
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.b32 %0, 1, 0, q;\n\t}" : "=r"(p) :: "memory");
+  return p;
+}
+// wait for the operands of group `g` on A_ready[b]; while they are not there, lane 0 keeps the ring full
 __device__ __forceinline__ void issuer_wait_operands(Issuer& I, const TileSmem& t, int b, uint32_t parity) {
   uint64_t* bar = t.bars + B_AREADY + b;
   const long long t0 = clock64();
   while (!mbar_test(bar, parity)) {                              // poll: the ring is topped up between polls
-    loader_top_up(I.L, t, I.issued);
+    if ((threadIdx.x & 31) == 0) loader_top_up(I.L, t, I.issued);
     if (clock64() - t0 > kWaitCycles) { printf("nsb: issuer timed out waiting for operands (block %d)\n", blockIdx.x); __trap(); }
   }
+  __syncwarp();
   tc::tc_fence_after();
 }
-// the unit the issuer is about to consume: make sure it was requested, wait for it, return its slot base
+// the unit the issuer is about to consume: make sure it was requested (lane 0), wait for it (all lanes), return its slot base
 __device__ __forceinline__ const float* issuer_unit(Issuer& I, const TileSmem& t) {
-  loader_top_up(I.L, t, I.issued);
-  while (I.L.loaded <= I.issued) loader_refill(I.L, t, I.issued);
+  if ((threadIdx.x & 31) == 0) {
+    loader_top_up(I.L, t, I.issued);
+    while (I.L.loaded <= I.issued) loader_refill(I.L, t, I.issued);
+  }
+  __syncwarp();
   const int slot = I.issued & (kSlots - 1);
   mbar_wait_b(t.bars + B_FULL + slot, (I.issued >> 2) & 1u);
+  __syncwarp();
   return t.ring + slot * t.slot_floats;
 }
 __device__ __forceinline__ void issuer_unit_done(Issuer& I, const TileSmem& t) {
-  tc::mma_commit(t.bars + B_EMPTY + (I.issued & (kSlots - 1)));
+  if (elect_one()) tc::mma_commit(t.bars + B_EMPTY + (I.issued & (kSlots - 1)));
+  __syncwarp();
   I.issued++;
+}
+__device__ __forceinline__ void issuer_group_done(const TileSmem& t, int bar) {
+  if (elect_one()) tc::mma_commit(t.bars + bar);
+  __syncwarp();
 }
 
 // D[128 x N] (+)= A[:, ka0 .. ka0 + 8 ksteps) * B^T, 3xTF32.  A: [128 x 32] hi|lo tile; B: unit [N x KB] hi|lo, product starts at column kb0.
 // The issuing thread is on the critical path of every layer step: descriptors are built once per unit and advanced by plain adds
 // (one k-step of 8 floats = two 128-byte core matrices = +16 in the 16-byte-granular start-address field; shared memory < 256 KB, so the
 // 14-bit field never carries).
-__device__ __forceinline__ void mma_unit(uint32_t d_tmem, const float* a, int ka0, const float* b, int N, int KB, int kb0, int ksteps, uint32_t& acc) {
+template <int KSTEPS>
+__device__ __forceinline__ void mma_unit(uint32_t d_tmem, const float* a, int ka0, const float* b, int N, int KB, int kb0, uint32_t& acc) {
   const uint32_t idesc = tc::make_idesc(TM, N);
-  uint64_t ah = tc::make_desc(a + (ka0 >> 2) * 32, 128u, 8u * 128u);
-  uint64_t bh = tc::make_desc(b + (kb0 >> 2) * 32, 128u, (uint32_t)(KB >> 2) * 128u);
-  uint64_t al = ah + (uint64_t)((TM * 32 * 4) >> 4);
-  uint64_t bl = bh + (uint64_t)((N * KB * 4) >> 4);
-#pragma unroll 1
-  for (int ks = 0; ks < ksteps; ks++) {
-    tc::mma_tf32(d_tmem, al, bh, idesc, acc); acc = 1u;
-    tc::mma_tf32(d_tmem, ah, bl, idesc, 1u);
-    tc::mma_tf32(d_tmem, ah, bh, idesc, 1u);
-    ah += 16u; al += 16u; bh += 16u; bl += 16u;
+  const uint64_t ah = tc::make_desc(a + (ka0 >> 2) * 32, 128u, 8u * 128u);
+  const uint64_t bh = tc::make_desc(b + (kb0 >> 2) * 32, 128u, (uint32_t)(KB >> 2) * 128u);
+  const uint64_t al = ah + (uint64_t)((TM * 32 * 4) >> 4);
+  const uint64_t bl = bh + (uint64_t)((N * KB * 4) >> 4);
+  if (elect_one()) {
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ks++) {
+      tc::mma_tf32(d_tmem, al + 16u * ks, bh + 16u * ks, idesc, ks == 0 ? acc : 1u);
+      tc::mma_tf32(d_tmem, ah + 16u * ks, bl + 16u * ks, idesc, 1u);
+      tc::mma_tf32(d_tmem, ah + 16u * ks, bh + 16u * ks, idesc, 1u);
+    }
   }
+  __syncwarp();
+  acc = 1u;
 }
 
 // ---- epilogue-side helpers -------------------------------------------------------------------------------------------------------
@@ -211,35 +235,54 @@ __device__ __forceinline__ void wait_group(const TileSmem& t, uint32_t m) {     
 }
 
 // 8 lanes per point, 4 points per pass: 32 channels of grid `g` -> [128 x 32] tile.  Warp w serves the rows of its lane quadrant (w & 3);
-// the eight passes of a quadrant are split over the two warps that share it.
-__device__ __forceinline__ void gather_tile(const nsb_grid& g, float* __restrict__ c_hi, const float xn[3], int warp, int lane) {
+// the eight passes of a quadrant are split over the two warps that share it.  The loads of pass i+1 are issued before pass i is consumed
+// (16 x 16-byte loads in flight per lane), corner offsets come from per-axis offsets (two adds per corner).
+struct GatherPass {
+  float4 v[8];
+  float w[8];
+  int src_lane;
+};
+__device__ __forceinline__ void gather_issue(const nsb_grid& g, bool fast, const float xn[3], int it, int lane, GatherPass& gp) {
+  const int q = lane & 7;
+  gp.src_lane = it * 4 + (lane >> 3);
+  float x[3];
+  x[0] = __shfl_sync(0xffffffffu, xn[0], gp.src_lane); x[1] = __shfl_sync(0xffffffffu, xn[1], gp.src_lane); x[2] = __shfl_sync(0xffffffffu, xn[2], gp.src_lane);
+  const Tri t = make_tri(x, g.W, g.H, g.D);
+  // branch-free clamped corners (tri_corner_clamped): the clamped upper corner carries weight exactly 0
+  const long long ox[2] = {(long long)t.i0[0] * g.stride_w, (long long)min(t.i0[0] + 1, g.W - 1) * g.stride_w};
+  const long long oy[2] = {(long long)t.i0[1] * g.stride_h, (long long)min(t.i0[1] + 1, g.H - 1) * g.stride_h};
+  const long long oz[2] = {(long long)t.i0[2] * g.stride_d, (long long)min(t.i0[2] + 1, g.D - 1) * g.stride_d};
+#pragma unroll
+  for (int k = 0; k < 8; k++) gp.v[k] = grid_load4(g, oz[k >> 2] + oy[(k >> 1) & 1] + ox[k & 1], 4 * q, fast);
+  const float wxy[4] = {__fmul_rn(t.w0[0], t.w0[1]), __fmul_rn(t.w1[0], t.w0[1]), __fmul_rn(t.w0[0], t.w1[1]), __fmul_rn(t.w1[0], t.w1[1])};
+#pragma unroll
+  for (int k = 0; k < 8; k++) gp.w[k] = __fmul_rn(wxy[k & 3], (k & 4) ? t.w1[2] : t.w0[2]);      // == tri_weight(t, k)
+}
+__device__ __forceinline__ void gather_consume(float* c_hi, float* c_lo, int qd, int lane, const GatherPass& gp) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const float w = gp.w[k];
+    acc.x = fmaf(gp.v[k].x, w, acc.x); acc.y = fmaf(gp.v[k].y, w, acc.y); acc.z = fmaf(gp.v[k].z, w, acc.z); acc.w = fmaf(gp.v[k].w, w, acc.w);
+  }
+  tc::put4(c_hi, c_lo, qd * 32 + gp.src_lane, lane & 7, 32, acc);
+}
+__device__ __forceinline__ void gather_tile(const nsb_grid& g, float* c_hi, const float xn[3], int warp, int lane) {
   float* c_lo = c_hi + TM * 32;
   const bool fast = grid_fast(g);
-  const int q = lane & 7, qd = warp & 3, it0 = (warp >> 2) * 4;
-#pragma unroll 1
-  for (int it = it0; it < it0 + 4; it++) {                       // 8 loads in flight per lane; the co-resident CTA supplies the rest of the MLP
-    const int src_lane = it * 4 + (lane >> 3);
-    float x[3];
-    x[0] = __shfl_sync(0xffffffffu, xn[0], src_lane); x[1] = __shfl_sync(0xffffffffu, xn[1], src_lane); x[2] = __shfl_sync(0xffffffffu, xn[2], src_lane);
-    const Tri t = make_tri(x, g.W, g.H, g.D);
-    float4 v[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      int cx, cy, cz;
-      tri_corner_clamped(t, k, g.W, g.H, g.D, cx, cy, cz);
-      v[k] = grid_load4(g, cz * g.stride_d + cy * g.stride_h + cx * g.stride_w, 4 * q, fast);
-    }
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      const float w = tri_weight(t, k);
-      acc.x = fmaf(v[k].x, w, acc.x); acc.y = fmaf(v[k].y, w, acc.y); acc.z = fmaf(v[k].z, w, acc.z); acc.w = fmaf(v[k].w, w, acc.w);
-    }
-    tc::put4(c_hi, c_lo, qd * 32 + src_lane, q, 32, acc);
-  }
+  const int qd = warp & 3, it0 = (warp >> 2) * 4;
+  GatherPass A, B;
+  gather_issue(g, fast, xn, it0, lane, A);
+  gather_issue(g, fast, xn, it0 + 1, lane, B);
+  gather_consume(c_hi, c_lo, qd, lane, A);
+  gather_issue(g, fast, xn, it0 + 2, lane, A);
+  gather_consume(c_hi, c_lo, qd, lane, B);
+  gather_issue(g, fast, xn, it0 + 3, lane, B);
+  gather_consume(c_hi, c_lo, qd, lane, A);
+  gather_consume(c_hi, c_lo, qd, lane, B);
 }
 // this thread's 16 features of embedding block `blk` of its point -> [128 x 32] tile
-__device__ __forceinline__ void embed_tile(float* __restrict__ e_hi, const float* __restrict__ B, const float pf[3], int row, int cg, int blk) {
+__device__ __forceinline__ void embed_tile(float* e_hi, const float* B, const float pf[3], int row, int cg, int blk) {
   float* e_lo = e_hi + TM * 32;
 #pragma unroll
   for (int kq = kKQ * cg; kq < kKQ * cg + kKQ; kq++) {
@@ -262,10 +305,10 @@ __device__ __forceinline__ void issue_fc(Issuer& I, const TileSmem& t, uint32_t 
   for (int u = 0; u < 4; u++) {
     const float* w = issuer_unit(I, t);
     uint32_t acc = (half == 0 && u == 0) ? 0u : 1u;
-    mma_unit(tmem + 64u, t.a[b], 8 * u, w, 160, 8, 0, 1, acc);
+    mma_unit<1>(tmem + 64u, t.a[b], 8 * u, w, 160, 8, 0, acc);
     issuer_unit_done(I, t);
   }
-  tc::mma_commit(t.bars + B_DONE + b);
+  issuer_group_done(t, B_DONE + b);
   I.g++;
 }
 __device__ __forceinline__ void issue_l0(Issuer& I, const TileSmem& t, uint32_t tmem, int blk) {       // [D1 | D3] += E_blk * [W0_blk; W3E_blk]^T   (coarse: E = C)
@@ -274,10 +317,10 @@ __device__ __forceinline__ void issue_l0(Issuer& I, const TileSmem& t, uint32_t 
   for (int h = 0; h < 2; h++) {
     const float* w = issuer_unit(I, t);
     uint32_t acc = (blk == 0 && h == 0) ? 0u : 1u;
-    mma_unit(tmem, t.a[b], 16 * h, w, 64, 16, 0, 2, acc);
+    mma_unit<2>(tmem, t.a[b], 16 * h, w, 64, 16, 0, acc);
     issuer_unit_done(I, t);
   }
-  tc::mma_commit(t.bars + B_DONE + b);
+  issuer_group_done(t, B_DONE + b);
   I.g++;
 }
 __device__ __forceinline__ void issue_h(Issuer& I, const TileSmem& t, uint32_t tmem, int i) {          // layer i (1..4) from the H tile of layer i-1
@@ -285,9 +328,9 @@ __device__ __forceinline__ void issue_h(Issuer& I, const TileSmem& t, uint32_t t
   issuer_wait_operands(I, t, b, (I.g >> 1) & 1u);
   const float* w = issuer_unit(I, t);
   uint32_t acc = i == 3 ? 1u : 0u;
-  mma_unit(i == 3 ? tmem + 32u : tmem, t.a[b], 0, w, 32, 32, 0, 4, acc);
+  mma_unit<4>(i == 3 ? tmem + 32u : tmem, t.a[b], 0, w, 32, 32, 0, acc);
   issuer_unit_done(I, t);
-  tc::mma_commit(t.bars + B_DONE + b);
+  issuer_group_done(t, B_DONE + b);
   I.g++;
 }
 
@@ -295,7 +338,7 @@ __device__ __forceinline__ void issue_h(Issuer& I, const TileSmem& t, uint32_t t
 __device__ __forceinline__ void epi_forward(const KParams& P, const TileSmem& t, Issuer& I, int lv, const PointGeom& G, uint32_t tmem, uint32_t& n, int hb, uint32_t hdr_parity,
                                             float (&out)[4], uint32_t* __restrict__ gmask) {
   const int row = threadIdx.x & (TM - 1), cg = threadIdx.x >> 7, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool t0 = threadIdx.x == 0;                            // the issuing thread: after every publish it waits for the other warps and issues the group's MMAs
+  const bool t0 = threadIdx.x < 32;                            // the issuing WARP (converged): after every publish it waits for the other warps and issues the group's MMAs
   const bool xyz = lv != 0;
   const int cd = op_cd(lv), no = lv == 3 ? 4 : 1;
   const uint32_t my = ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kCW * cg);
@@ -303,17 +346,22 @@ __device__ __forceinline__ void epi_forward(const KParams& P, const TileSmem& t,
   const float* hdr = t.hdr + hb * kHdrFloats;
   if (xyz) {
     for (int half = 0; half < cd / 32; half++) {
-      if (n >= 2) wait_group(t, n - 2);
+      if (n >= 2) { wait_group(t, n - 2); if (threadIdx.x == 0) loader_top_up(I.L, t, I.issued); }
       gather_tile(P.in.grid[half == 0 ? lv : 1], t.a[n & 1], G.xn, warp, lane);
+      NSB_PH(1);
       publish(t, n & 1); n++;
       if (t0) issue_fc(I, t, tmem, half);
+      NSB_PH(2);
     }
     mbar_wait_b(t.bars + B_HDR + hb, hdr_parity);
     for (int blk = 0; blk < 3; blk++) {
-      if (n >= 2) wait_group(t, n - 2);
+      if (n >= 2) { wait_group(t, n - 2); if (threadIdx.x == 0) loader_top_up(I.L, t, I.issued); }
+      NSB_PH(6);
       embed_tile(t.a[n & 1], hdr + 464, G.pf, row, cg, blk);
+      NSB_PH(3);
       publish(t, n & 1); n++;
       if (t0) issue_l0(I, t, tmem, blk);
+      NSB_PH(4);
     }
   } else {
     if (n >= 2) wait_group(t, n - 2);
@@ -326,6 +374,8 @@ __device__ __forceinline__ void epi_forward(const KParams& P, const TileSmem& t,
 #pragma unroll 1
   for (int i = 0; i < 5; i++) {
     wait_group(t, n - 1);                                        // pre-activation of layer i (and, in order, everything before it)
+    if (threadIdx.x == 0) loader_top_up(I.L, t, I.issued);       // the layer's weight slots are free: request the next units now, under the epilogue
+    NSB_PH(7);
     float v1[kCW];
     tmem_ld16(i == 3 ? d3 : d1, v1);
     uint32_t m = 0;
@@ -342,9 +392,12 @@ __device__ __forceinline__ void epi_forward(const KParams& P, const TileSmem& t,
     float* h_hi = t.a[n & 1];
 #pragma unroll
     for (int k = 0; k < kKQ; k++) tc::put4(h_hi, h_hi + TM * 32, row, kKQ * cg + k, 32, make_float4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]));
+    NSB_PH(8);
     publish(t, n & 1); n++;
     if (t0) issue_h(I, t, tmem, i + 1);
+    NSB_PH(9);
   }
+  NSB_PH(8);
   tc::tc_fence_before();
   // output layer: partial dot products over this thread's columns, summed over the two threads of the row through shared memory.
   // (buffer (n & 1) is free: its last reader was group n-2, complete.)
@@ -370,6 +423,7 @@ __device__ __forceinline__ void epi_forward(const KParams& P, const TileSmem& t,
     out[0] += v.x; out[1] += v.y; out[2] += v.z; out[3] += v.w;
   }
   epi_sync();                                                    // partials consumed before the next decoder's gather reuses the buffer
+  NSB_PH(12);
 }
 
 // ---- backward (input gradients): what the issuing thread does after the CTA published layer i's operands (G in a[0], DU in a[1]) ---------------
@@ -381,24 +435,24 @@ __device__ __forceinline__ void issue_bwd_layer(Issuer& I, const TileSmem& t, ui
   if (xyz) for (int c2 = 0; c2 < cd / 32; c2++) {               // DC += G * Wc_i
     const float* w = issuer_unit(I, t);
     uint32_t acc = i == 4 ? 0u : 1u;
-    mma_unit(tmem + 32u + 32u * c2, t.a[0], 0, w, 32, 32, 0, 4, acc);
+    mma_unit<4>(tmem + 32u + 32u * c2, t.a[0], 0, w, 32, 32, 0, acc);
     issuer_unit_done(I, t);
   }
   if (i >= 1) {                                                 // D1 = DU * W_i[:, hidden]
     const float* w = issuer_unit(I, t);
     uint32_t acc = 0u;
-    mma_unit(tmem, t.a[1], 0, w, 32, 32, 0, 4, acc);
+    mma_unit<4>(tmem, t.a[1], 0, w, 32, 32, 0, acc);
     issuer_unit_done(I, t);
   }
   if (i == 3 || i == 0) {                                       // DF += DU * W_i[:, first input]
     for (int fb = 0; fb < nfb; fb++) {
       const float* w = issuer_unit(I, t);
       uint32_t acc = i == 3 ? 0u : 1u;
-      mma_unit(tmem + 96u + 32u * fb, t.a[1], 0, w, 32, 32, 0, 4, acc);
+      mma_unit<4>(tmem + 96u + 32u * fb, t.a[1], 0, w, 32, 32, 0, acc);
       issuer_unit_done(I, t);
     }
   }
-  tc::mma_commit(t.bars + B_DONE);
+  issuer_group_done(t, B_DONE);
   I.g++;
 }
 
@@ -434,13 +488,18 @@ __device__ __forceinline__ void epi_backward(const KParams& P, const TileSmem& t
                make_float4((m >> (4 * k)) & 1u ? g[4 * k] : 0.0f, (m >> (4 * k + 1)) & 1u ? g[4 * k + 1] : 0.0f,
                            (m >> (4 * k + 2)) & 1u ? g[4 * k + 2] : 0.0f, (m >> (4 * k + 3)) & 1u ? g[4 * k + 3] : 0.0f));
     }
+    NSB_PH(22);
     publish(t, 0);
-    if (threadIdx.x == 0) issue_bwd_layer(I, t, tmem, lv, i);
+    if (threadIdx.x < 32) issue_bwd_layer(I, t, tmem, lv, i);
+    NSB_PH(23);
     mbar_wait_b(t.bars + B_DONE, n & 1u); n++;
     tc::tc_fence_after();
+    if (threadIdx.x == 0) loader_top_up(I.L, t, I.issued);       // slots of this layer are free: fetch the next layer's units under the epilogue
+    NSB_PH(24);
     if (i >= 1) tmem_ld16(tmem + my, g);
     tc::tc_fence_before();
   }
+  NSB_PH(22);
   // dL/dc rows -> a[0] (plain fp32 [128][cd]); every MMA reading the buffers has completed
   float* dcs = t.a[0];
   {
@@ -473,12 +532,13 @@ __device__ __forceinline__ void epi_backward(const KParams& P, const TileSmem& t
   }
   *reinterpret_cast<float4*>(t.a[1] + (cg * TM + row) * 4) = make_float4(dpe[0], dpe[1], dpe[2], 0.0f);
   tc::tc_fence_before();
+  NSB_PH(27);
 }
 
 // Backward of gather_tile (same warp -> rows mapping).  dcs = [128][cd] fp32.  emit(row, gx) once per point.
 template <typename F>
 __device__ __forceinline__ void scatter_tile(const nsb_grid& g, float* __restrict__ dgrid, const int32_t* __restrict__ slots,
-                                             const float* __restrict__ dcs, int cd, const float xn[3], int warp, int lane, F&& emit) {
+                                             const float* dcs, int cd, const float xn[3], int warp, int lane, F&& emit) {
   const bool fast = grid_fast(g);
   const int q = lane & 7, qd = warp & 3, it0 = (warp >> 2) * 4;
 #pragma unroll 1
@@ -534,7 +594,7 @@ __device__ __forceinline__ int tiles_of_ray(int ray, int S) {
 }
 // Bump the completion counters of the rays [ray_lo, ray_lo + nr) this item touched; returns (CTA-uniform) how many of them this CTA
 // completed, their indices in s_done[].  Every thread must call it, after its global writes.  target = items per tile (split).
-__device__ __forceinline__ int complete_rays(int* __restrict__ ray_cnt, int ray_lo, int nr, int S, int per_tile, int* s_done, int* s_ndone) {
+__device__ __forceinline__ int complete_rays(int* ray_cnt, int ray_lo, int nr, int S, int per_tile, int* s_done, int* s_ndone) {
   __threadfence();
   if (threadIdx.x == 0) *s_ndone = 0;
   __syncthreads();
@@ -625,6 +685,7 @@ __global__ void __launch_bounds__(tl::kThreads, 2) render_fwd_tile_kernel(const 
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(t.tmem)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  NSB_PH_RESET();
   Issuer I; I.L.P = &P; I.L.q = q0; I.L.q1 = q1; I.L.k = 0; I.L.loaded = 0; I.L.bwd = false; I.issued = 0; I.g = 0;
   if (tid == 0) {
     for (int i = 0; i < kNumBars; i++) mbar_init(t.bars + i, (i == B_AREADY || i == B_AREADY + 1) ? kEpiThreads / 32 : 1);
@@ -657,6 +718,7 @@ __global__ void __launch_bounds__(tl::kThreads, 2) render_fwd_tile_kernel(const 
         gtmax = m; gtmax12 = __fmul_rn(m, 1.2f);
       }
     }
+    NSB_PH(40);
     // scratch in the (still unused) operand buffers: ray table [nr][8] f32 + far [nr] f64 | unsorted z [nr*S] | sorted z [nr*S]
     float* rays = t.a[0];
     double* far = reinterpret_cast<double*>(t.a[0] + 8 * kMaxTileRays);
@@ -673,21 +735,47 @@ __global__ void __launch_bounds__(tl::kThreads, 2) render_fwd_tile_kernel(const 
       rays[8 * r + 6] = rs.near; rays[8 * r + 7] = gt; far[r] = rs.far;
     }
     __syncthreads();
+    NSB_PH(41);
     for (int i = tid; i < nr * S; i += kThreads) {
       const int r = i / S, s = i - r * S;
       RaySampler rs; rs.near = rays[8 * r + 6]; rs.gt = rays[8 * r + 7]; rs.far = far[r]; rs.has_gt = P.has_gt;
       zu[i] = sample_z(rs, s, P.in.n_samples, P.in.t_uniform, P.in.t_surface, gtmax);
     }
     __syncthreads();
-    for (int i = tid; i < nr * S; i += kThreads) {                 // stable rank sort == torch.sort (Renderer.py:168-170)
+    NSB_PH(42);
+    // torch.sort of the concatenation [uniform | surface] (Renderer.py:168-170).  Both lists come out of linspace-style formulas and are
+    // normally non-decreasing: then the stable rank of an element is its index in its own list plus a binary-search count in the other one
+    // (merge by ranks).  A ray whose lists are not sorted (far < near, NaN) takes the general stable rank sort -- same values either way.
+    int* unsorted = reinterpret_cast<int*>(zs + (size_t)nr * S);
+    for (int r = tid; r < nr; r += kThreads) unsorted[r] = 0;
+    __syncthreads();
+    const int nu = P.in.n_samples < S ? P.in.n_samples : S;
+    for (int i = tid; i < nr * S; i += kThreads) {
+      const int r = i / S, s = i - r * S;
+      if (s != 0 && s != nu) { const double a = zu[i - 1], b = zu[i]; if (!(a <= b)) unsorted[r] = 1; }
+      else if (zu[i] != zu[i]) unsorted[r] = 1;
+    }
+    __syncthreads();
+    for (int i = tid; i < nr * S; i += kThreads) {
       const int r = i / S, s = i - r * S;
       const double zi = zu[i];
       const double* zr = zu + r * S;
-      int rank = 0;
-      for (int j = 0; j < S; j++) { const double zj = zr[j]; rank += (z_less(zj, zi) || (!z_less(zi, zj) && j < s)) ? 1 : 0; }
+      int rank;
+      if (!unsorted[r]) {
+        // uniform element: + #{surface < z}; surface element: + #{uniform <= z} (cat order = uniform first, stable)
+        const bool uni = s < nu;
+        const double* other = uni ? zr + nu : zr;
+        int lo = 0, hi = uni ? S - nu : nu;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; const double zm = other[mid]; if (uni ? (zm < zi) : (zm <= zi)) lo = mid + 1; else hi = mid; }
+        rank = (uni ? s : s - nu) + lo;
+      } else {
+        rank = 0;
+        for (int j = 0; j < S; j++) { const double zj = zr[j]; rank += (z_less(zj, zi) || (!z_less(zi, zj) && j < s)) ? 1 : 0; }
+      }
       zs[r * S + rank] = zi;
     }
     __syncthreads();
+    NSB_PH(43);
     {
       const long long gp = gp0 + lp;
       const int r = (int)(gp / S) - ray_lo, s = (int)(gp - (long long)(ray_lo + r) * S);
@@ -702,6 +790,7 @@ __global__ void __launch_bounds__(tl::kThreads, 2) render_fwd_tile_kernel(const 
   __syncthreads();                                                // TMEM address + barrier initialisation visible
   tc::tc_fence_after();
   const uint32_t tmem = *t.tmem;
+  NSB_PH(44);
 
   float occ = 0.0f, c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
   {
@@ -725,6 +814,7 @@ __global__ void __launch_bounds__(tl::kThreads, 2) render_fwd_tile_kernel(const 
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+  NSB_PH(14);
 
   if (points) {                                                   // Renderer.eval_points: raw with the out-of-bound override
     if (cg == 0 && row < npts) *reinterpret_cast<float4*>(P.points_raw + 4 * (gp0 + row)) = make_float4(c0, c1, c2, G.inb ? occ : 100.0f);
@@ -732,7 +822,9 @@ __global__ void __launch_bounds__(tl::kThreads, 2) render_fwd_tile_kernel(const 
   }
   if (cg == 0 && row < npts) P.tile_parts[(long long)my * NP + gp0 + row] = make_float4(c0, c1, c2, occ);
   const int nd = complete_rays(P.ray_cnt, ray_lo, nr, S, nsplit, s_done, &s_ndone);
+  NSB_PH(15);
   for (int k = warp; k < nd; k += kThreads / 32) composite_ray(P, s_done[k], lane, smem_raw + (size_t)warp * composite_scratch_bytes(S));
+  NSB_PH(16);
   // loss seeds: the last CTA of the grid to get here sees every ray composited
   if (P.fs.kind != 0 && grid_last_arrival(P.fs.counter, gridDim.x, &s_last)) {
     if (P.fs.kind == 1) {
@@ -781,6 +873,7 @@ __global__ void __launch_bounds__(tl::kThreads, 2) render_bwd_tile_kernel(const 
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(t.tmem)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  NSB_PH_RESET();
   Issuer I; I.L.P = &P; I.L.q = q0; I.L.q1 = q1; I.L.k = 0; I.L.loaded = 0; I.L.bwd = true; I.issued = 0; I.g = 0;
   if (tid == 0) {
     for (int i = 0; i < kNumBars; i++) mbar_init(t.bars + i, (i == B_AREADY || i == B_AREADY + 1) ? kEpiThreads / 32 : 1);
@@ -844,6 +937,7 @@ __global__ void __launch_bounds__(tl::kThreads, 2) render_bwd_tile_kernel(const 
       carry += __shfl_sync(0xffffffffu, incl, 0);
     }
   }
+  NSB_PH(20);
   PointGeom G;
   const int lp = row < npts ? row : npts - 1;
   const long long gpr = gp0 + lp;
@@ -860,6 +954,7 @@ __global__ void __launch_bounds__(tl::kThreads, 2) render_bwd_tile_kernel(const 
   __syncthreads();                                                // prologue scratch dead, gocc / wgt / gc visible, TMEM address + barriers visible
   tc::tc_fence_after();
   const uint32_t tmem = *t.tmem;
+  NSB_PH(21);
 
   {
     uint32_t n = 0;
@@ -888,6 +983,7 @@ __global__ void __launch_bounds__(tl::kThreads, 2) render_bwd_tile_kernel(const 
         }
       });
       epi_sync();                                                 // reads of a[0] / a[1] done before the next decoder overwrites them
+      NSB_PH(29);
     }
   }
   tc::tc_fence_before();
@@ -905,7 +1001,9 @@ __global__ void __launch_bounds__(tl::kThreads, 2) render_bwd_tile_kernel(const 
     for (int p = s0; p < s1; p++) { const double v = X.dp[3 * p + a]; so += v; sd += v * X.z[p]; }
     parts[r * 6 + a] = so; parts[r * 6 + 3 + a] = sd;
   }
+  NSB_PH(30);
   const int nd = complete_rays(P.ray_cnt, ray_lo, nr, S, nsplit, s_done, &s_ndone);
+  NSB_PH(31);
   for (int i = tid; i < nd * 3; i += kThreads) {                  // the completing CTA adds the parts in (tile, decoder) order
     const int ray = s_done[i / 3], a = i % 3;
     const long long p0 = (long long)ray * S;
@@ -925,6 +1023,7 @@ __global__ void __launch_bounds__(tl::kThreads, 2) render_bwd_tile_kernel(const 
     if (P.bw.d_rays_o != nullptr) P.bw.d_rays_o[3 * ray + a] = (float)so;
     if (P.bw.d_rays_d != nullptr) P.bw.d_rays_d[3 * ray + a] = (float)sd;
   }
+  NSB_PH(32);
   if (fused_pose_grad(P, gridDim.x, reinterpret_cast<double*>(smem_raw)) && P.tail.px.world > 1) {
     // sharded tracking batch: SUM over ranks of [loss | d c2w] by this (last) CTA -- identical bits on every rank
     __shared__ double tot[13];
