@@ -35,6 +35,9 @@ import torch  # noqa: E402
 RAYS_PER_GPU = 200
 STAGE = "color"
 BYTES_PER_RAY = 48 * 3 * 1024            # S x G(stage) x 1024 B gathered per ray (tracking: no scatter) = 147456
+MAC_PER_POINT = 51653                    # forward MACs per sample point in stage color (fine + color + middle decoders)
+# tracking iteration: forward + input-gradient backward (~ the same MACs), 2 flops per MAC; the tensor cores execute 3x that (3xTF32 split)
+FLOPS_PER_RAY = 48 * MAC_PER_POINT * 2 * 2
 METRIC = "rendered rays/sec"
 WORKLOAD = "room0 tracking iteration (fwd+loss+bwd), 200 rays x 48 samples (32+16) per GPU, stage color, full grids"
 
@@ -46,6 +49,15 @@ def peaks():
         with open(path) as f:
             return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def tensor_peak():
+    """TF32 dense tensor peak in TFLOP/s: half the measured bf16 cuBLAS burst figure (TF32 runs at half the bf16 rate on B200)."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("bf16_tflops", 1590.0) / 2, "0.5 x measured bf16 burst (MEASURED_PEAKS.json bf16_tflops)"
+    return 1590.0 / 2, "0.5 x fallback bf16 (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -223,15 +235,22 @@ def extra_workloads(sc, renderer, c, dec, dev, flush, peak):
                                             "frustum selection + colour-decoder grads) + fused Adam (3 grids in place + colour decoder)",
                                 "selected_voxels": {k: m.count for k, m in loop.masked.items()}, "ms_per_step": ms, "rays_per_s": n / (ms * 1e-3)}
     del loop
+    # BASELINE configs[4]: ray-throughput sweep, tracking-style iteration (fwd + loss + bwd), stage color, N_surface = 16 fixed,
+    # N_samples in {16, 32, 80} -> S in {32, 48, 96} samples per ray; one GPU here, --gpus N shards the 200-ray line
+    from gpu_util import make_renderer
     sweep = []
-    for nn, steps in ((1024, 100), (8192, 30), (65536, 8)):
-        ro, rd, dirs, gd, gc = [t.to(dev) for t in make_batch(sc, nn, 200 + nn)]
-        cx = IterationContext(renderer, nn, "color", dev, kind="track")
-        ms = time_steps(lambda: cx.run(c, dec, ro, rd, gd, gc), steps)
-        sweep.append({"rays": nn, "samples": 48, "ms_per_step": ms, "rays_per_s": nn / (ms * 1e-3),
-                      "hbm_frac": nn * BYTES_PER_RAY / (ms * 1e-3) / 1e9 / peak})
-        del cx
+    for n_uniform in (16, 32, 80):
+        S = n_uniform + 16
+        rr = renderer if n_uniform == 32 else make_renderer(sc, {k: v for k, v in c.items()}, su.load_decoders("soft"), dev, n_samples=n_uniform)[0]
+        for nn, steps in ((256, 100), (1024, 100), (4096, 40), (16384, 12), (65536, 5)):
+            ro, rd, dirs, gd, gc = [t.to(dev) for t in make_batch(sc, nn, 200 + nn)]
+            cx = IterationContext(rr, nn, "color", dev, kind="track", host_staging=False)
+            ms = time_steps(lambda: cx.run(c, dec, ro, rd, gd, gc), steps)
+            sweep.append({"rays": nn, "samples": S, "ms_per_step": ms, "rays_per_s": nn / (ms * 1e-3),
+                          "hbm_frac": nn * S * 3 * 1024 / (ms * 1e-3) / 1e9 / peak})
+            del cx
     out["sweep_tracking_iteration"] = sweep
+    out["dropin"] = dropin_iterations(sc, renderer, c, dec, dev, time_steps)
     # bulk no-grad paths of the same forward kernel: Mesher-style eval_points and a full-image render
     pts = (torch.rand(1 << 22, 3, device=dev, dtype=torch.float64) - 0.5) * 4.0 + torch.tensor(su_center(sc), device=dev, dtype=torch.float64)
     ms = time_steps(lambda: renderer.eval_points(pts, dec, c, "fine", dev), 5, warmup=1)
@@ -245,20 +264,105 @@ def extra_workloads(sc, renderer, c, dec, dev, flush, peak):
     return out
 
 
+def dropin_iterations(sc, renderer, c, dec, dev, time_steps):
+    """The reference call surface, timed: an UNMODIFIED caller doing render_batch_ray + its own torch loss + loss.backward() (autograd) around
+    FusedRenderer -- what Tracker.optimize_cam_in_batch (src/Tracker.py:106-125) and one joint_iter of Mapper.optimize_map (src/Mapper.py:482-503)
+    cost when only `slam.renderer` is swapped, Adam step excluded as in the headline.  Same batches and timing rules as the fused
+    numbers: the difference is the price of the torch glue (autograd graph, dense zero-filled grid gradients, separate loss kernels)."""
+    import scene_util as su
+    out = {}
+    # tracking: camera tensor -> c2w -> rays (get_rays_from_uv) -> render -> tracking loss -> backward to the 7 pose numbers
+    ro, rd, dirs, gd, gc = [t.to(dev) for t in make_batch(sc, RAYS_PER_GPU, 0)]
+    from nice_slam_b200.mapping import tensor_from_c2w
+    cam = tensor_from_c2w(su.make_pose(sc, 0)).to(dev).requires_grad_(True)
+
+    def quad2rot(q):
+        two_s = 2.0 / (q * q).sum()
+        qr, qi, qj, qk = q[0], q[1], q[2], q[3]
+        return torch.stack([1 - two_s * (qj ** 2 + qk ** 2), two_s * (qi * qj - qk * qr), two_s * (qi * qk + qj * qr),
+                            two_s * (qi * qj + qk * qr), 1 - two_s * (qi ** 2 + qk ** 2), two_s * (qj * qk - qi * qr),
+                            two_s * (qi * qk - qj * qr), two_s * (qj * qk + qi * qr), 1 - two_s * (qi ** 2 + qj ** 2)]).reshape(3, 3)
+
+    def track():
+        cam.grad = None
+        R = quad2rot(cam[:4])
+        rays_d = torch.sum(dirs.reshape(-1, 1, 3) * R, -1)
+        rays_o = cam[4:].expand(rays_d.shape)
+        depth, unc, color = renderer.render_batch_ray(c, dec, rays_d, rays_o, dev, "color", gt_depth=gd)
+        unc = unc.detach()
+        tmp = torch.abs(gd - depth) / torch.sqrt(unc + 1e-10)
+        mask = (tmp < 10 * tmp.median()) & (gd > 0)
+        loss = tmp[mask].sum() + 0.5 * torch.abs(gc - color)[mask].sum()
+        loss.backward()
+    out["tracking_iter_ms"] = time_steps(track, 100)
+    # mapping: dense leaf grids + colour-decoder leaves (the reference's val[mask] = val_grad indexing is the caller's and not timed here)
+    n = 996
+    ro, rd, dirs, gd, gc = [t.to(dev) for t in make_batch(sc, n, 101)]
+    gcf = gc.float()
+    cm = {k: v.detach().clone().requires_grad_(k != "grid_coarse") for k, v in c.items()}
+    import copy
+    dm = copy.deepcopy(dec)
+    for name, p in dm.named_parameters():
+        p.requires_grad_(name.startswith("color_decoder"))
+
+    def mapit():
+        for v in cm.values():
+            v.grad = None
+        for p in dm.parameters():
+            p.grad = None
+        depth, unc, color = renderer.render_batch_ray(cm, dm, rd, ro, dev, "color", gt_depth=gd)
+        m = gd > 0
+        loss = torch.abs(gd[m] - depth[m]).sum() + 0.2 * torch.abs(gcf - color).sum()
+        loss.backward()
+    out["mapping_iter_ms"] = time_steps(mapit, 50)
+    out["note"] = ("FusedRenderer.render_batch_ray + torch loss + autograd (the drop-in path of INTEGRATION.md); compare with ms_per_step (tracking) and "
+                   "extra.mapping_configs1 (mapping) of the fused C-ABI iterations")
+    return out
+
+
 def su_center(sc):
     import scene_util as su
     b = su.scene_bound(sc)
     return [float((b[i][0] + b[i][1]) / 2) for i in range(3)]
 
 
-def scene_workloads(dev, flush):
-    """BASELINE configs[2], configs[3] volumes on one GPU: one mapping iteration (stage color, frustum-masked voxel parameterisation,
-    compact voxel grads + colour-decoder grads) on ScanNet scene0000 (5000 rays), Apartment as configured (0.98 M voxels, 10000 rays)
-    and Apartment with the TUM grid lengths (8.0 M voxels, 1.0 GB of grids -- larger than L2, so the gather really comes from HBM)."""
+def frustum_masks(renderer, c, sc, seed, dev, keys):
+    """{key: MaskedVoxels}: the voxels the synthetic frame `seed` sees (nsb_frustum_mask = Mapper.get_mask_from_c2w, src/Mapper.py:93-164)."""
+    import scene_util as su
+    from nice_slam_b200.masked import MaskedVoxels, frustum_voxel_mask
+    depth, _ = su.make_frame(sc, seed)
+    pose = su.make_pose(sc, seed)
+    return {k: MaskedVoxels(c[k], frustum_voxel_mask(renderer, pose, k, c[k], depth.to(dev))) for k in keys}
+
+
+def timed_sharded(fn, steps, flush, dev, world):
+    """ms per step: CUDA-event pairs around every step on this rank, L2 flushed between steps, max over ranks."""
+    import torch.distributed as dist
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in evs:
+        flush.zero_(); a.record(); fn(); b.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs) / steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t)
+
+
+def scene_workloads(dev, flush, rank, world):
+    """BASELINE configs[2], configs[3]: one mapping iteration (stage color, frustum-masked voxel parameterisation, compact voxel grads +
+    colour-decoder grads in one packed block) on ScanNet scene0000 (5000 rays), Apartment as configured (0.98 M voxels, 10000 rays) and Apartment
+    with the TUM grid lengths (8.0 M voxels, 1.0 GB of grids -- larger than L2, so the gather really comes from HBM).  STRONG scaling: the global
+    batch is fixed and ray-sharded over the ranks (contiguous shards), the batch depth maxima come from the full batch on every rank and the
+    packed gradient block is all-reduced ONCE per iteration.  Runs on every rank; the report is returned on every rank."""
     import torch.nn.functional as F
     import scene_util as su
     from gpu_util import make_renderer
-    from nice_slam_b200.masked import MaskedVoxels
+    from nice_slam_b200.dist import ShardedMappingIteration, shard_bounds
     from nice_slam_b200.steps import IterationContext
     out = []
     for name, n, variant in (("scene0000", 5000, None), ("apartment", 10000, None), ("apartment", 10000, "tum_grid_len")):
@@ -277,83 +381,59 @@ def scene_workloads(dev, flush):
             grids[key] = t
         renderer, c, dec = make_renderer(sc, grids, su.load_decoders("soft"), dev)
         del grids
-        ro, rd, dirs, gd, gc = [t.to(dev) for t in make_batch(sc, n, 77)]
+        ro, rd, dirs, gd, gc = [t.to(dev) for t in make_batch(sc, n, 77)]          # the same global batch on every rank
         keys = ("grid_middle", "grid_fine", "grid_color")
-        mv = {}
-        for k in keys:
-            D, H, W = c[k].shape[2:]
-            m = torch.zeros(D, H, W, dtype=torch.bool, device=dev)
-            m[:, :, : int(0.6 * W)] = True
-            mv[k] = MaskedVoxels(c[k], m)
-        ctx = IterationContext(renderer, n, "color", dev, kind="map", grad_grids=keys, grad_decoders=("color",), masked=mv)
-        gcf = gc.float()
-        steps = 20
-        for _ in range(3):
-            ctx.run(c, dec, ro, rd, gd, gcf)
-        torch.cuda.synchronize()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        for a, b in evs:
-            flush.zero_(); a.record(); ctx.run(c, dec, ro, rd, gd, gcf); b.record()
-        torch.cuda.synchronize()
-        ms = sum(a.elapsed_time(b) for a, b in evs) / steps
-        assert torch.isfinite(ctx.loss).all()
+        mv = frustum_masks(renderer, c, sc, 77, dev, keys)
+        lo_, hi_ = shard_bounds(n, rank, world)
+        ctx = IterationContext(renderer, hi_ - lo_, "color", dev, kind="map", grad_grids=keys, grad_decoders=("color",), masked=mv, host_staging=False)
+        ctx.load_device_inputs(ro[lo_:hi_], rd[lo_:hi_], gd[lo_:hi_], gc[lo_:hi_].float())
+        sh = ShardedMappingIteration(ctx)
+        sh.prepare(c, dec, global_gt_depth=gd)
+        ms = timed_sharded(sh.enqueue, 20, flush, dev, world)
+        assert torch.isfinite(ctx.packed).all()
         vox = sum(int(c[k].shape[2] * c[k].shape[3] * c[k].shape[4]) for k in c)
         bpr = 48 * 3 * 1024 * 2
-        out.append({"scene": name + ("+" + variant if variant else ""), "rays": n, "voxels": vox, "grid_mbytes": vox * 128 / 1e6,
-                    "ms_per_step": ms, "rays_per_s": n / (ms * 1e-3), "algorithmic_gbytes_per_s": n * bpr / (ms * 1e-3) / 1e9})
-        del ctx, mv, c, renderer
+        out.append({"scene": name + ("+" + variant if variant else ""), "rays_global": n, "rays_per_gpu": hi_ - lo_, "voxels": vox, "grid_mbytes": vox * 128 / 1e6,
+                    "selected_voxels": {k: m.count for k, m in mv.items()}, "allreduce_bytes": int(ctx.packed.numel() * 4),
+                    "collectives_per_step": sh.collectives_per_step, "scaling": "strong", "ms_per_step": ms, "rays_per_s": n / (ms * 1e-3),
+                    "algorithmic_gbytes_per_s": n * bpr / (ms * 1e-3) / 1e9})
+        del ctx, sh, mv, c, renderer
         torch.cuda.empty_cache()
     return out
 
 
 def mapping_sharded_workload(sc, renderer, c, dec, dev, flush, rank, world):
     """BASELINE configs[1]-style mapping iteration, ray-sharded (weak scaling: 996 rays = 6 keyframes x 166 px per GPU), with the
-    frustum-masked voxel parameterisation: compact voxel gradients + colour-decoder gradients + keyframe pose gradients in one packed
-    float32 block and ONE all-reduce per iteration.  Runs on every rank; returns the report on rank 0."""
+    frustum-masked voxel parameterisation (nsb_frustum_mask of the current frame): compact voxel gradients + colour-decoder gradients + keyframe
+    pose gradients in one packed float32 block and ONE all-reduce per iteration -- the batch depth maxima are taken over the whole window batch,
+    which every rank knows (replicated keyframes), before sharding.  Runs on every rank; returns the report on every rank."""
     import torch.distributed as dist
     from nice_slam_b200.dist import ShardedMappingIteration
-    from nice_slam_b200.masked import MaskedVoxels
     from nice_slam_b200.steps import IterationContext
     n, n_frames = 996, 6
-    ro, rd, dirs, gd, gc = [t.to(dev) for t in make_batch(sc, n, 301 + rank)]
+    batches = [make_batch(sc, n, 301 + r) for r in range(world)]
+    ro, rd, dirs, gd, gc = [t.to(dev) for t in batches[rank]]
+    gd_global = torch.cat([b[3] for b in batches]).to(dev)
     keys = ("grid_middle", "grid_fine", "grid_color")
-    mv = {}
-    for k in keys:                                                # frustum stand-in: the 60 % of the volume in front of the camera
-        D, H, W = c[k].shape[2:]
-        m = torch.zeros(D, H, W, dtype=torch.bool, device=dev)
-        m[:, :, : int(0.6 * W)] = True
-        mv[k] = MaskedVoxels(c[k], m)
-    ctx = IterationContext(renderer, n, "color", dev, kind="map", grad_grids=keys, grad_decoders=("color",), masked=mv, n_frames=n_frames)
+    mv = frustum_masks(renderer, c, sc, 301, dev, keys)
+    ctx = IterationContext(renderer, n, "color", dev, kind="map", grad_grids=keys, grad_decoders=("color",), masked=mv, n_frames=n_frames, host_staging=False)
     ctx.load_device_inputs(ro, rd, gd, gc.float())
     offs = torch.tensor([i * 166 for i in range(n_frames + 1)], dtype=torch.int32, device=dev)
     sh = ShardedMappingIteration(ctx)
-    sh.prepare(c, dec, dirs, offs)
+    sh.prepare(c, dec, dirs, offs, global_gt_depth=gd_global)
     sh.enqueue(); torch.cuda.synchronize()
     g = sh.build_graph() if os.environ.get("NSB_DIST_GRAPH", "1") == "1" else None
     ok = torch.tensor([1.0 if g is not None else 0.0], device=dev)
     if world > 1:
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     use_graph = bool(ok.item() > 0.5)
-    fn = g.replay if use_graph else sh.enqueue
-    steps = 100
-    for _ in range(5):
-        fn()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    for a, b in evs:
-        flush.zero_(); a.record(); fn(); b.record()
-    torch.cuda.synchronize()
-    t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs) / steps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t)
+    ms = timed_sharded(g.replay if use_graph else sh.enqueue, 100, flush, dev, world)
     assert torch.isfinite(ctx.packed).all()
-    return {"workload": "room0 mapping iteration, 996 rays x 48 per GPU, stage color, masked voxel parameterisation (60 % of the volume), "
-                        "compact voxel grads + colour-decoder grads + 6 keyframe pose grads",
+    return {"workload": "room0 mapping iteration, 996 rays x 48 per GPU (weak scaling), stage color, frustum-masked voxel parameterisation (on-GPU frustum mask of "
+                        "the frame), compact voxel grads + colour-decoder grads + 6 keyframe pose grads",
+            "selected_voxels": {k: m.count for k, m in mv.items()},
             "ms_per_step": ms, "rays_per_s": n * world / (ms * 1e-3), "allreduce_bytes": int(ctx.packed.numel() * 4),
-            "collectives_per_step": (2 if world > 1 else 0), "launch": "CUDA graph" if use_graph else "stream launches"}
+            "collectives_per_step": sh.collectives_per_step, "launch": "CUDA graph" if use_graph else "stream launches"}
 
 
 # ------------------------------------------------------------------------------------------------ native arm (GPU)
@@ -361,7 +441,7 @@ def mapping_sharded_workload(sc, renderer, c, dec, dev, flush, rank, world):
 # committed `ncu --set full` capture (never measured inside a timed run): the 48.5 MB of grids are L2-resident, so DRAM traffic is far
 # below the 29.5 MB of algorithmic gather bytes.
 NCU_DRAM_BYTES_PER_BWD_LAUNCH = 4003840
-NCU_TRAFFIC_SOURCE = "profiles/ncu_full_r01m_render_kernels.txt (ncu --set full, 4.00 MB read + 0 B written per launch)"
+NCU_TRAFFIC_SOURCE = "profiles/ncu_full_r02_render_kernels.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
 
 
 def dbg(msg):
@@ -491,6 +571,8 @@ def run_native(args):
 
     dbg("mapping sharded workload")
     map_sharded = mapping_sharded_workload(sc, renderer, c, dec, dev, flush, rank, world)
+    dbg("strong-scaled scene workloads")
+    scenes = scene_workloads(dev, flush, rank, world)
 
     if rank != 0:
         shutdown(world)
@@ -502,26 +584,39 @@ def run_native(args):
     line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "rays_per_step": rays, "l2": "flushed between steps (256 MiB memset outside the event pair)",
+                       "batch": "every step replays the same synthetic ray batch (fixed seed); grids and decoders are not updated between steps",
                        "launch": "CUDA graph replay (one graph per iteration)" if (sharded is None or use_graph) else "stream launches + NCCL",
                        "parallelism": "ray-sharded x%d" % world, "exchange": exchange if sharded is not None else "none (single GPU)",
                        "timing": "sum of per-step CUDA-event pairs, max over ranks"},
             "clocks": clocks,
             "e2e": {"value": rays / (e2e_ms / args.steps * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": ctx.h2d_bytes,
                     "d2h_bytes_per_step": ctx.d2h_bytes if sharded is None else 13 * 8, "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": (2 if sharded is None else (5 if sharded.peers is not None else 6)) * args.steps,
+            "gpu_launches": (2 if sharded is None else (2 if sharded.fused else (5 if sharded.peers is not None else 6))) * args.steps,
             "extra": {"l2_warm_ms_per_step": warm_ms / args.steps, "l2_warm_rays_per_s": rays / (warm_ms / args.steps * 1e-3),
-                      "mapping_sharded_masked": map_sharded}}
+                      "mapping_sharded_masked": map_sharded, "mapping_other_scenes": scenes}}
     if bwd_ms:
         t_bwd = statistics.mean(bwd_ms) * 1e-3
         ach = BYTES_PER_RAY * RAYS_PER_GPU / t_bwd / 1e9
-        line["roofline"] = {"bound": "hbm", "kernel": "render_bwd_tc_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+        it_ach = BYTES_PER_RAY * rays / (ms * 1e-3) / 1e9 / world          # per GPU
+        line["roofline"] = {"bound": "hbm", "kernel": "render_bwd_tile_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                             "traffic": NCU_DRAM_BYTES_PER_BWD_LAUNCH, "traffic_source": NCU_TRAFFIC_SOURCE,
                             "peak_source": peak_src, "launch_ms": t_bwd * 1e3,
                             "algorithmic_bytes_per_launch": BYTES_PER_RAY * RAYS_PER_GPU,
-                            "note": "200-ray tracking batch (100 CTAs on 148 SMs) is latency bound, not HBM bound: the grids are L2-resident (see DESIGN.md)"}
+                            # SURVEY 8d charges the gather ONCE per fused fwd+bwd iteration: the same bytes over the whole step time
+                            "iteration_achieved": it_ach, "iteration_frac": it_ach / peak,
+                            "note": "frac = the iteration's algorithmic gather bytes over the backward launch alone; iteration_frac = the same bytes over "
+                                    "ms_per_step (the figure SURVEY 8d defines).  The 200-ray batch (225 tile x decoder CTAs) is latency bound, not HBM "
+                                    "bound: the 48.5 MB of grids are L2-resident (see DESIGN.md)"}
+        tpk, tpk_src = tensor_peak()
+        tf = FLOPS_PER_RAY * rays / (ms * 1e-3) / 1e12 / world
+        line["roofline_tensor"] = {"bound": "tensor", "dtype": "tf32 (3xTF32 split: every product is three tcgen05.mma.kind::tf32)", "unit": "TFLOP/s",
+                                   "algorithmic": tf, "achieved": 3 * tf, "peak": tpk, "frac": 3 * tf / tpk, "peak_source": tpk_src,
+                                   "flops_per_ray": FLOPS_PER_RAY,
+                                   "note": "per GPU, whole iteration; algorithmic = fp32-equivalent flops of the decoders' forward + input-gradient backward "
+                                           "(SURVEY 8a MAC counts), achieved = what the tensor cores execute for them; sm__pipe_tensor_cycles_active from the "
+                                           "ncu capture is in profiles/"}
     if world == 1:
         line["extra"].update(extra_workloads(sc, renderer, c, dec, dev, flush, peak))
-        line["extra"]["mapping_other_scenes"] = scene_workloads(dev, flush)
         best = pick_cpu_threads(sc, host)
         step = cpu_iteration_fn(sc, host)
         t0c, k = time.perf_counter(), 0

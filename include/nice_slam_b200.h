@@ -129,6 +129,10 @@ typedef struct {
                                     leaves it clean): lets small batches (N <= 256 rays, several decoders) run one CTA per decoder
                                     and ray group instead of one CTA per ray group; NULL = never split */
   size_t split_workspace_bytes;
+  float* acts;                   /* optional [N,S,5,32] float32: outputs of the five hidden layers of the decoder whose WEIGHT gradients the
+                                    backward will be asked for (the colour decoder in stage color, src/Mapper.py:339-341).  When the forward
+                                    keeps them, the backward computes those weight gradients on the tensor cores (dW = dU^T X contracted over
+                                    the points of a tile) instead of the FP32-FMA pass that recomputes the forward.  NULL = not kept. */
 } nsb_forward_outputs;
 
 /* 0 when the batch is too large to profit from decoder-parallel CTAs. */
@@ -161,6 +165,7 @@ typedef struct {
                                     zero-initialised, self-resetting device counter pose_counter -- instead of a separate launch */
   double* d_c2w;
   int* pose_counter;
+  const float* acts;             /* nsb_forward_outputs.acts of the same forward, or NULL */
 } nsb_backward_args;
 
 size_t nsb_backward_workspace_bytes(void);
@@ -303,6 +308,7 @@ typedef struct {
   float* depth_max;                              /* [2]               batch depth maxima          */
   void* workspace; size_t workspace_bytes;       /* >= nsb_iteration_workspace_bytes(N)           */
   void* event_bwd_begin; void* event_bwd_end;    /* optional cudaEvent_t recorded around the backward launch (profiling hook) */
+  float* acts;                                   /* [N,S,5,32] or NULL (see nsb_forward_outputs.acts): needed for tensor-core weight gradients */
 } nsb_iteration_buffers;
 
 /* The workspace must be ZEROED ONCE after allocation (it contains the split_workspace counters, see nsb_forward_outputs). */

@@ -163,6 +163,7 @@ struct KParams {
   int tile_rays;                // backward: rays one tile can touch (stride of ray_parts per item)
   FusedSeeds fs;                // forward: loss seeds computed by the last CTA to finish (kind 0 = not fused)
   PeerTail tail;                // backward: sum of [loss | d c2w] over ranks by the last CTA (px.world <= 1: none)
+  int acts_lv;                  // forward: decoder level whose layer outputs go to fo.acts (-1: none)
   int wbytes;                   // bytes reserved for the weight image in shared memory
   int max_pts, max_rays;        // per-CTA capacities the shared-memory carve-up was sized for
 };
@@ -419,7 +420,7 @@ __device__ __forceinline__ void fused_seeds_tail(const KParams& P, int n_partici
 // ------------------------------------------------------------------------------------------------
 // forward kernel, FP32-FMA (SIMT) decoders
 __global__ void __launch_bounds__(256, 1) render_fwd_kernel(const __grid_constant__ KParams P) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5;
   const LaneId L = make_lane(threadIdx.x & 31);
   Smem sm;
@@ -453,7 +454,7 @@ namespace nsb {
 // ------------------------------------------------------------------------------------------------
 // forward kernel, tensor-core (tcgen05, 3xTF32) decoders: 512 threads = four per point of a 128-point tile (nsb_tc.cuh)
 __global__ void __launch_bounds__(tc::kThreads, 1) render_fwd_tc_kernel(const __grid_constant__ KParams P) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];       // tiles need 16-byte alignment only (no-swizzle descriptors)
+  extern __shared__ __align__(1024) unsigned char smem_raw[];       // tiles need 16-byte alignment only (no-swizzle descriptors)
   NSB_PH_RESET();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = threadIdx.x & (tc::TM - 1), cg = threadIdx.x >> 7;
@@ -727,7 +728,7 @@ __device__ __forceinline__ bool fused_pose_grad(const KParams& P, int n_writers,
 }
 
 __global__ void __launch_bounds__(256, 1) render_bwd_kernel(const __grid_constant__ KParams P) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5;
   const LaneId L = make_lane(threadIdx.x & 31);
   Smem sm;
@@ -760,7 +761,7 @@ __global__ void __launch_bounds__(256, 1) render_bwd_kernel(const __grid_constan
 // backward kernel, tensor-core decoders (input gradients: rays + grid voxels).  Decoder-weight gradients stay on the
 // SIMT kernel for now (host dispatch).
 __global__ void __launch_bounds__(tc::kThreads, 1) render_bwd_tc_kernel(const __grid_constant__ KParams P) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   NSB_PH_RESET();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = threadIdx.x & (tc::TM - 1);
@@ -928,6 +929,7 @@ static void fill_common(KParams& K, const nsb_render_inputs* in) {
   for (int i = 0; i < K.n_dec; i++) { const int b = packed_floats(K.dec[i]) * 4; wb = b > wb ? b : wb; }
   K.wbytes = wb;
   K.points = nullptr; K.points_raw = nullptr; K.n_points = 0;
+  K.acts_lv = in->stage == NSB_STAGE_COLOR ? 3 : -1;      // the colour decoder is the only one whose weights the mapper optimises (Mapper.py:339-341)
   for (int l = 0; l < 4; l++) K.d_packed[l] = nullptr;
 }
 
@@ -961,6 +963,7 @@ static void choose_config(int n_items, int S, int rows, bool bwd, int wbytes, in
   *smem = smem_layout(wbytes, max_pts, r, w, rows, bwd, nullptr, nullptr);
 }
 
+static int g_wgrad_tc = 1;         // decoder weight gradients on the tensor cores when the forward kept the layer outputs (0: FP32-FMA pass)
 static int g_mlp_backend = 0;      // 0 = auto (tensor-core forward), 1 = SIMT, 2 = tcgen05
 static size_t tc_total_smem(int max_pts, int max_rays, bool bwd = false) {
   return ((tc::tc_smem_bytes(bwd) + 127) & ~size_t(127)) + smem_layout(0, max_pts, max_rays, 0, 0, bwd, nullptr, nullptr);
@@ -1044,6 +1047,7 @@ static bool plan_split(KParams* K, int nd, void* ws, size_t ws_bytes) {
 }
 
 static size_t tile_smem_bytes(bool bwd) { return tl::common_bytes(bwd) + (bwd ? sizeof(tl::BwdExtra) : 0); }
+static size_t tile_wg_smem_bytes() { return tl::kWgBytes + tile_smem_bytes(true) + 1024; }
 static bool use_tile_kernels(int S) { return (g_mlp_backend == 0 || g_mlp_backend == 3) && S >= tl::kMinSamples && S <= NSB_MAX_SAMPLES; }
 static bool g_attr_set[kMaxDevices] = {false};
 static int set_attrs() {
@@ -1053,6 +1057,7 @@ static int set_attrs() {
   if (check_cuda(cudaFuncSetAttribute(render_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap), "bwd tc smem attr")) return NSB_ERR_CUDA;
   if (check_cuda(cudaFuncSetAttribute(render_fwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(false)), "fwd tile smem attr")) return NSB_ERR_CUDA;
   if (check_cuda(cudaFuncSetAttribute(render_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(true)), "bwd tile smem attr")) return NSB_ERR_CUDA;
+  if (check_cuda(cudaFuncSetAttribute(render_bwd_wg_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_wg_smem_bytes()), "bwd wg tile smem attr")) return NSB_ERR_CUDA;
   // two CTAs per SM need the full shared-memory carve-out (2 x ~111 KB of the 228 KB)
   if (check_cuda(cudaFuncSetAttribute(render_fwd_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared), "fwd tile carveout")) return NSB_ERR_CUDA;
   if (check_cuda(cudaFuncSetAttribute(render_bwd_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared), "bwd tile carveout")) return NSB_ERR_CUDA;
@@ -1067,6 +1072,7 @@ static int set_attrs() {
 using namespace nsb;
 
 extern "C" int nsb_set_option(const char* key, int value) {
+  if (key && !strcmp(key, "wgrad_tc")) { g_wgrad_tc = value != 0; return NSB_OK; }
   if (key && !strcmp(key, "mlp_backend")) { if (value < 0 || value > 3) { set_error("mlp_backend must be 0 (auto = tile kernels), 1 (FP32-FMA), 2 (tcgen05, round-1 ray-group kernels) or 3 (tcgen05 tile kernels)"); return NSB_ERR_ARG; } g_mlp_backend = value; return NSB_OK; }
   set_error("unknown option %s", key ? key : "(null)"); return NSB_ERR_ARG;
 }
@@ -1197,6 +1203,9 @@ int nsb::render_backward_tail(const nsb_render_inputs* in, const nsb_backward_ar
       if (bw->d_flat[K.dec[i]] != nullptr) { wdec[n_w] = K.dec[i]; wpos[n_w] = i; n_w++; }
       else { T.dec[T.n_dec] = K.dec[i]; T.dec_pos[T.n_dec] = i; T.n_dec++; }
     }
+    // Weight gradients on the tensor cores: the colour decoder, when the forward kept its layer outputs (acts) -- a second tile launch with one item
+    // per tile (one CTA per SM) after the input-gradient launch of the other decoders; it adds its share of the ray gradients.
+    const bool wg_tc = n_w == 1 && wdec[0] == 3 && bw->acts != nullptr && use_tile_kernels(K.S) && g_wgrad_tc && (tail == nullptr || tail->px.world <= 1);
     if (T.n_dec > 0) {
       if (n_w == 0 && want_pose) T.bw.pose_dirs = bw->pose_dirs;   // the tensor-core launch is the last writer of the ray gradients
       if (use_tile_kernels(T.S)) {
@@ -1223,6 +1232,21 @@ int nsb::render_backward_tail(const nsb_render_inputs* in, const nsb_backward_ar
       }
       if (n_w == 0) return NSB_OK;
       K.accumulate_rays = 1;
+    }
+    if (wg_tc) {
+      KParams W = K;
+      W.n_dec = 1; W.dec[0] = wdec[0]; W.dec_pos[0] = wpos[0];
+      W.accumulate_rays = T.n_dec > 0 ? 1 : 0;
+      W.bw.pose_dirs = want_pose ? bw->pose_dirs : nullptr;          // last writer of the ray gradients: d c2w by its last CTA
+      TileWs w;
+      if (!tile_ws_plan(bw->split_workspace, bw->split_workspace_bytes, in->n_rays, W.S, 1, true, &w)) {
+        set_error("split_workspace missing or smaller than nsb_split_workspace_bytes(%d, %d)", in->n_rays, W.S); return NSB_ERR_ARG; }
+      W.split = 1; W.ray_cnt = w.ray_cnt; W.ray_parts = static_cast<double*>(w.scratch); W.tile_rays = tile_rays(W.S);
+      render_bwd_wg_tile_kernel<<<(unsigned)tile_count((long long)in->n_rays * W.S), tl::kThreads, tile_wg_smem_bytes(), st>>>(W);
+      if ((rc = check_cuda(cudaGetLastError(), "render_bwd_wg_tile_kernel launch"))) return rc;
+      return launch_unpack_grads(W.d_packed, bw->d_flat, st);
+    }
+    if (T.n_dec > 0) {
       K.n_dec = n_w;
       for (int i = 0; i < n_w; i++) { K.dec[i] = wdec[i]; K.dec_pos[i] = wpos[i]; }
       int wb = 0;

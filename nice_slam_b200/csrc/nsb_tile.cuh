@@ -336,7 +336,7 @@ __device__ __forceinline__ void issue_h(Issuer& I, const TileSmem& t, uint32_t t
 
 // ---- forward of one decoder: epilogue side.  n = operand-group counter (same sequence as the issuer's).  out[] = decoder outputs of this row.
 __device__ __forceinline__ void epi_forward(const KParams& P, const TileSmem& t, Issuer& I, int lv, const PointGeom& G, uint32_t tmem, uint32_t& n, int hb, uint32_t hdr_parity,
-                                            float (&out)[4], uint32_t* __restrict__ gmask) {
+                                            float (&out)[4], uint32_t* __restrict__ gmask, float* acts = nullptr) {
   const int row = threadIdx.x & (TM - 1), cg = threadIdx.x >> 7, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool t0 = threadIdx.x < 32;                            // the issuing WARP (converged): after every publish it waits for the other warps and issues the group's MMAs
   const bool xyz = lv != 0;
@@ -388,6 +388,10 @@ __device__ __forceinline__ void epi_forward(const KParams& P, const TileSmem& t,
 #pragma unroll
       for (int j = 0; j < kCW; j++) h[j] += v2[j] + hdr[160 + i * 32 + kCW * cg + j];
     }
+    if (acts != nullptr) {                                       // layer outputs kept for the tensor-core weight gradients of the backward
+#pragma unroll
+      for (int k = 0; k < kKQ; k++) __stcg(reinterpret_cast<float4*>(acts + i * 32 + 4 * k), make_float4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]));
+    }
     if (i == 4) break;
     float* h_hi = t.a[n & 1];
 #pragma unroll
@@ -426,6 +430,134 @@ __device__ __forceinline__ void epi_forward(const KParams& P, const TileSmem& t,
   NSB_PH(12);
 }
 
+// ---- tensor-core weight gradients (the colour decoder in the mapper's colour stage, src/Mapper.py:339-341,503) --------------------------------
+// dW_i = DU_i^T X_i, dWc_i = G_i^T C, dWo = g_out^T H_4, dB = P^T DX are contractions over the POINTS of a tile: both operands of the MMA have the
+// points as K.  A row-major [128 points][32 features] tile is exactly an MN-major operand (M / N = feature contiguous, K = point strided), which
+// kind::tf32 accepts in the SWIZZLE_128B_BASE32B shared-memory layout (descriptor layout type 1): 128-byte rows, the 32-byte chunk c of row p stored
+// at chunk c ^ (p & 3).  Nothing is transposed: the epilogue threads write the same rows they own in the K-major chain tiles a second time in this
+// layout (DU_i, G_i -> A operand, M = 128 = [DU | G | unused | unused] through the leading-dimension stride), the layer inputs X_i come back from the
+// forward's `acts`, C and the embedding blocks are recomputed.  One MMA group = 16 k-steps x 3 (3xTF32) with N = 32 into TMEM columns [192, 224);
+// rows 0..31 (DU part) or 32..63 (G part) are then reduced into the packed gradient image with 16-byte vector reductions.
+constexpr int kMnTile = TM * 32;                               // floats of one tile (16 KB)
+constexpr size_t kWgBytes = (size_t)6 * kMnTile * 4;           // A: DU hi|lo, G hi|lo (64 KB)  B: one tile hi|lo (32 KB)
+constexpr uint32_t kWgCol = 192u;                              // TMEM columns [192, 224) of the weight-gradient accumulator
+struct WgSmem { float* du; float* g; float* b; uint64_t* bar; uint32_t phase; float* dpk; };
+__device__ __forceinline__ void split4(const float4 v, float4& h, float4& l) {
+  h = make_float4(tc::to_tf32(v.x), tc::to_tf32(v.y), tc::to_tf32(v.z), tc::to_tf32(v.w));
+  l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+}
+// features [16 cg, 16 cg + 16) of row p -> hi | lo tiles
+__device__ __forceinline__ void put_mn16(float* hi, int p, int cg, const float (&v)[kCW]) {
+  float* lo = hi + kMnTile;
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    const int base = p * 32 + ((((2 * cg + c) ^ p) & 3) << 3);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      float4 xh, xl; split4(make_float4(v[8 * c + 4 * h], v[8 * c + 4 * h + 1], v[8 * c + 4 * h + 2], v[8 * c + 4 * h + 3]), xh, xl);
+      *reinterpret_cast<float4*>(hi + base + 4 * h) = xh; *reinterpret_cast<float4*>(lo + base + 4 * h) = xl;
+    }
+  }
+}
+__device__ __forceinline__ void get_mn16(const float* hi, int p, int cg, float (&v)[kCW]) {      // hi + lo = the value that was split
+  const float* lo = hi + kMnTile;
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    const int base = p * 32 + ((((2 * cg + c) ^ p) & 3) << 3);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const float4 a = *reinterpret_cast<const float4*>(hi + base + 4 * h), b = *reinterpret_cast<const float4*>(lo + base + 4 * h);
+      v[8 * c + 4 * h] = a.x + b.x; v[8 * c + 4 * h + 1] = a.y + b.y; v[8 * c + 4 * h + 2] = a.z + b.z; v[8 * c + 4 * h + 3] = a.w + b.w;
+    }
+  }
+}
+// gather_tile with the MN-major destination (lane q of a point holds channels [4 q, 4 q + 4))
+__device__ __forceinline__ void gather_tile_mn(const nsb_grid& g, float* c_hi, const float xn[3], int warp, int lane) {
+  float* c_lo = c_hi + kMnTile;
+  const bool fast = grid_fast(g);
+  const int qd = warp & 3, it0 = (warp >> 2) * 4, q = lane & 7;
+#pragma unroll 1
+  for (int it = it0; it < it0 + 4; it++) {
+    GatherPass A;
+    gather_issue(g, fast, xn, it, lane, A);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const float w = A.w[k];
+      acc.x = fmaf(A.v[k].x, w, acc.x); acc.y = fmaf(A.v[k].y, w, acc.y); acc.z = fmaf(A.v[k].z, w, acc.z); acc.w = fmaf(A.v[k].w, w, acc.w);
+    }
+    const int p = qd * 32 + A.src_lane;
+    float4 xh, xl; split4(acc, xh, xl);
+    const int o = p * 32 + ((((q >> 1) ^ p) & 3) << 3) + 4 * (q & 1);
+    *reinterpret_cast<float4*>(c_hi + o) = xh; *reinterpret_cast<float4*>(c_lo + o) = xl;
+  }
+}
+__device__ __forceinline__ uint64_t make_desc_mn(const float* smem, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_u32(smem) >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                                      // SWIZZLE_128B_BASE32B
+  return d;
+}
+// warp 0, converged: D_w[128 x 32] = [DU | G | . | .]^T-contraction with the B tile over the 128 points; commits to w.bar
+__device__ __forceinline__ void issue_wg_group(const WgSmem& w, uint32_t tmem) {
+  tc::tc_fence_after();
+  const uint32_t idesc = tc::make_idesc(TM, 32) | (1u << 15) | (1u << 16);          // A and B MN-major
+  const uint64_t ah = make_desc_mn(w.du, 2u * kMnTile * 4u, 512u), al = ah + (uint64_t)((kMnTile * 4) >> 4);
+  const uint64_t bh = make_desc_mn(w.b, 2u * kMnTile * 4u, 512u), bl = bh + (uint64_t)((kMnTile * 4) >> 4);
+  if (elect_one()) {
+#pragma unroll
+    for (int ks = 0; ks < TM / 8; ks++) {                       // 8 points per MMA = 1024 bytes of rows
+      tc::mma_tf32(tmem + kWgCol, al + 64u * ks, bh + 64u * ks, idesc, ks == 0 ? 0u : 1u);
+      tc::mma_tf32(tmem + kWgCol, ah + 64u * ks, bl + 64u * ks, idesc, 1u);
+      tc::mma_tf32(tmem + kWgCol, ah + 64u * ks, bh + 64u * ks, idesc, 1u);
+    }
+    tc::mma_commit(w.bar);
+  }
+  __syncwarp();
+}
+// One group: the B tile (and, the first time in a layer, the A tiles) have been written by all threads.  part 0 = rows of the DU block (D rows 0..31),
+// part 1 = rows of the G block (32..63); dst = packed-image address of element (out 0, in 0), pitch in floats; n_rows <= 32 rows are reduced.
+__device__ __forceinline__ void wg_group(WgSmem& w, uint32_t tmem, int part, float* dst, int pitch, int n_rows, bool transposed3 = false) {
+  fence_proxy_async(); tc::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) issue_wg_group(w, tmem);
+  mbar_wait_b(w.bar, w.phase); w.phase ^= 1u;
+  tc::tc_fence_after();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cg = threadIdx.x >> 7;
+  if ((warp & 3) == part) {
+    float v[kCW];
+    tmem_ld16(tmem + kWgCol + ((uint32_t)(part * 32) << 16) + (uint32_t)(kCW * cg), v);
+    if (transposed3) {                                           // dB[a][f] = D[f][a], a < 3 (the B tile held the three coordinates in columns 0..2)
+      if (cg == 0 && lane < n_rows) { atomicAdd(dst + lane, v[0]); atomicAdd(dst + pitch + lane, v[1]); atomicAdd(dst + 2 * pitch + lane, v[2]); }
+    } else if (lane < n_rows) {
+      float* d = dst + (size_t)lane * pitch + kCW * cg;
+#pragma unroll
+      for (int k = 0; k < kKQ; k++) red_add_v4(d + 4 * k, v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    }
+  }
+  tc::tc_fence_before();
+}
+// column sums of a [32 rows (lanes)][16] register tile: lane l returns the sum of column ((l >> 4) & 1) * 8 + ((l >> 3) & 1) * 4 + ((l >> 2) & 1) * 2 + ((l >> 1) & 1)
+__device__ __forceinline__ float warp_colsum16(const float (&v)[kCW], int lane) {
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) { const float give = (lane & 16) ? v[j] : v[j + 8], keep = (lane & 16) ? v[j + 8] : v[j]; a[j] = keep + __shfl_xor_sync(0xffffffffu, give, 16); }
+  float b[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) { const float give = (lane & 8) ? a[j] : a[j + 4], keep = (lane & 8) ? a[j + 4] : a[j]; b[j] = keep + __shfl_xor_sync(0xffffffffu, give, 8); }
+  float c[2];
+#pragma unroll
+  for (int j = 0; j < 2; j++) { const float give = (lane & 4) ? b[j] : b[j + 2], keep = (lane & 4) ? b[j + 2] : b[j]; c[j] = keep + __shfl_xor_sync(0xffffffffu, give, 4); }
+  const float give = (lane & 2) ? c[0] : c[1], keep = (lane & 2) ? c[1] : c[0];
+  float d = keep + __shfl_xor_sync(0xffffffffu, give, 2);
+  d += __shfl_xor_sync(0xffffffffu, d, 1);
+  return d;
+}
+__device__ __forceinline__ int colsum_col(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
+
 // ---- backward (input gradients): what the issuing thread does after the CTA published layer i's operands (G in a[0], DU in a[1]) ---------------
 // TMEM: D1 = [0,32) (g of the next layer), DC = [32,96) (dL/dc), DF = [96,192) (dL/d first input).
 __device__ __forceinline__ void issue_bwd_layer(Issuer& I, const TileSmem& t, uint32_t tmem, int lv, int i) {
@@ -458,9 +590,13 @@ __device__ __forceinline__ void issue_bwd_layer(Issuer& I, const TileSmem& t, ui
 
 // ---- backward of one decoder: epilogue side.  Leaves dL/dc rows ([128][cd] fp32) in a[0] and the embedding-chain partials of dL/dp
 // ([2][128][4] fp32) in a[1]; the caller scatters after an epi_sync().
+template <bool WG>
 __device__ __forceinline__ void epi_backward(const KParams& P, const TileSmem& t, Issuer& I, int lv, const PointGeom& G, uint32_t tmem, uint32_t& n, int hb, uint32_t hdr_parity,
-                                             const float (&g_out)[4], const uint32_t* __restrict__ gmask) {
+                                             const float (&g_out)[4], const uint32_t* __restrict__ gmask, WgSmem* w = nullptr, const float* acts_row = nullptr) {
   const int row = threadIdx.x & (TM - 1), cg = threadIdx.x >> 7, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  using DW = Dec<3>;                                             // packed gradient image of the colour decoder (the only WG decoder)
+  float creg[kCW];                                               // WG: this thread's 16 grid features of its point
   const bool xyz = lv != 0;
   const int cd = op_cd(lv);
   const float* hdr = t.hdr + hb * kHdrFloats;
@@ -478,9 +614,45 @@ __device__ __forceinline__ void epi_backward(const KParams& P, const TileSmem& t
     for (int o = 0; o < 4; o++) v = fmaf(hdr[336 + o * 32 + kCW * cg + j], g_out[o], v);       // rows >= NO are zero
     g[j] = v;
   }
+  if constexpr (WG) {
+    // grid features of this point -> registers (gathered once through the B tile)
+    gather_tile_mn(P.in.grid[lv], w->b, G.xn, warp, lane);
+    __syncthreads();
+    get_mn16(w->b, row, cg, creg);
+    __syncthreads();
+    // output layer: dWo = g_out^T H_4 (A block 0 = g_out in columns 0..3), dbo = column sums of g_out
+    float go[kCW];
+#pragma unroll
+    for (int j = 0; j < kCW; j++) go[j] = (cg == 0 && j < 4) ? g_out[j] : 0.0f;
+    put_mn16(w->du, row, cg, go);
+    float h4[kCW];
+#pragma unroll
+    for (int k = 0; k < kKQ; k++) {
+      const float4 v = acts_row != nullptr ? __ldcg(reinterpret_cast<const float4*>(acts_row + 4 * 32 + 4 * k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      h4[4 * k] = v.x; h4[4 * k + 1] = v.y; h4[4 * k + 2] = v.z; h4[4 * k + 3] = v.w;
+    }
+    put_mn16(w->b, row, cg, h4);
+    wg_group(*w, tmem, 0, w->dpk + DW::o_WO, DW::PH, 4);
+    if (cg == 0) {
+      const float sb = warp_colsum16(go, lane);
+      const int col = colsum_col(lane);
+      if ((lane & 1) == 0 && col < 4) atomicAdd(w->dpk + DW::o_bo + col, sb);
+    }
+  }
 #pragma unroll 1
   for (int i = 4; i >= 0; i--) {
     const uint32_t m = i == 4 ? m4 : (((i & 2) ? m23 : m01) >> (16 * (i & 1))) & 0xffffu;
+    if constexpr (WG) {
+      float du[kCW];
+#pragma unroll
+      for (int j = 0; j < kCW; j++) du[j] = (m >> j) & 1u ? g[j] : 0.0f;
+      put_mn16(w->du, row, cg, du); put_mn16(w->g, row, cg, g);
+      const float sb = warp_colsum16(du, lane), sc = warp_colsum16(g, lane);      // db_i, dbc_i
+      if ((lane & 1) == 0) {
+        const int col = kCW * cg + colsum_col(lane);
+        atomicAdd(w->dpk + DW::o_b + 32 * i + col, sb); atomicAdd(w->dpk + DW::o_bc + 32 * i + col, sc);
+      }
+    }
 #pragma unroll
     for (int k = 0; k < kKQ; k++) {
       if (xyz) tc::put4(g_hi, g_hi + TM * 32, row, kKQ * cg + k, 32, make_float4(g[4 * k], g[4 * k + 1], g[4 * k + 2], g[4 * k + 3]));
@@ -492,6 +664,35 @@ __device__ __forceinline__ void epi_backward(const KParams& P, const TileSmem& t
     publish(t, 0);
     if (threadIdx.x < 32) issue_bwd_layer(I, t, tmem, lv, i);
     NSB_PH(23);
+    if constexpr (WG) {                                          // weight gradients of layer i (the chain's MMAs run meanwhile)
+      if (i >= 1) {                                              // hidden input H_{i-1}
+        float xr[kCW];
+#pragma unroll
+        for (int k = 0; k < kKQ; k++) {
+          const float4 v = acts_row != nullptr ? __ldcg(reinterpret_cast<const float4*>(acts_row + (i - 1) * 32 + 4 * k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          xr[4 * k] = v.x; xr[4 * k + 1] = v.y; xr[4 * k + 2] = v.z; xr[4 * k + 3] = v.w;
+        }
+        put_mn16(w->b, row, cg, xr);
+        const int o_wh = i == 1 ? DW::o_W1 : i == 2 ? DW::o_W2 : i == 3 ? DW::o_W3H : DW::o_W4;
+        wg_group(*w, tmem, 0, w->dpk + o_wh, DW::PH, 32);
+      }
+      put_mn16(w->b, row, cg, creg);                             // dWc_i = G_i^T C
+      wg_group(*w, tmem, 1, w->dpk + DW::o_WC + 32 * i * DW::PC, DW::PC, 32);
+      if (i == 3 || i == 0) {                                    // embedding part of W_0 / W_3
+        const float* B = hdr + 464;
+        for (int blk = 0; blk < 3; blk++) {
+          float e[kCW];
+#pragma unroll
+          for (int j = 0; j < kCW; j++) {
+            const int f = 32 * blk + kCW * cg + j;
+            float x = G.pf[0] * B[f]; x = fmaf(G.pf[1], B[kEmbPad + f], x); x = fmaf(G.pf[2], B[2 * kEmbPad + f], x);
+            e[j] = f < kEmb ? __sinf(reduce_2pi(x)) : 0.0f;
+          }
+          put_mn16(w->b, row, cg, e);
+          wg_group(*w, tmem, 0, w->dpk + (i == 0 ? DW::o_W0 : DW::o_W3E) + 32 * blk, DW::PF, 32);
+        }
+      }
+    }
     mbar_wait_b(t.bars + B_DONE, n & 1u); n++;
     tc::tc_fence_after();
     if (threadIdx.x == 0) loader_top_up(I.L, t, I.issued);       // slots of this layer are free: fetch the next layer's units under the epilogue
@@ -515,18 +716,32 @@ __device__ __forceinline__ void epi_backward(const KParams& P, const TileSmem& t
   float dpe[3] = {0.0f, 0.0f, 0.0f};
   if (xyz) {
     const float* B = hdr + 464;
+    if constexpr (WG) {                                          // B tile of the dB groups: the point's coordinates in columns 0..2
+      float pv[kCW];
+#pragma unroll
+      for (int j = 0; j < kCW; j++) pv[j] = (cg == 0 && j < 3) ? G.pf[j] : 0.0f;
+      put_mn16(w->b, row, cg, pv);
+    }
     for (int c = 0; c < 3; c++) {
       float v[kCW];
       tmem_ld16(dfc + 32u * c + my, v);
+      float dxv[kCW];
 #pragma unroll
       for (int j = 0; j < kCW; j++) {
         const int f = 32 * c + kCW * cg + j;
+        dxv[j] = 0.0f;
         if (f < kEmb) {
           const float b0 = B[f], b1 = B[kEmbPad + f], b2 = B[2 * kEmbPad + f];
           float x = G.pf[0] * b0; x = fmaf(G.pf[1], b1, x); x = fmaf(G.pf[2], b2, x);
           const float dx = __cosf(reduce_2pi(x)) * v[j];
+          dxv[j] = dx;
           dpe[0] = fmaf(b0, dx, dpe[0]); dpe[1] = fmaf(b1, dx, dpe[1]); dpe[2] = fmaf(b2, dx, dpe[2]);
         }
+      }
+      if constexpr (WG) {                                        // dB[a][f] = sum_p p_a cos(.) dE_f  (embedder._B is a parameter of the decoder)
+        put_mn16(w->du, row, cg, dxv);
+        const int nf = kEmb - 32 * c < 32 ? kEmb - 32 * c : 32;
+        wg_group(*w, tmem, 0, w->dpk + DW::o_B + 32 * c, kEmbPad, nf, true);
       }
     }
   }
@@ -661,7 +876,7 @@ __device__ __forceinline__ void composite_ray(const KParams& P, int ray, int lan
 // forward kernel
 // ================================================================================================================================
 __global__ void __launch_bounds__(tl::kThreads, 2) render_fwd_tile_kernel(const __grid_constant__ KParams P) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   using namespace tl;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = tid & (TM - 1), cg = tid >> 7;            // (control warp: row/cg unused)
@@ -801,7 +1016,8 @@ __global__ void __launch_bounds__(tl::kThreads, 2) render_fwd_tile_kernel(const 
       uint32_t* gm = (P.fo.masks != nullptr && row < npts) ? P.fo.masks + ((gp0 + row) * 15 + qd * 5) : nullptr;
       const int dq = qd - q0;
       if (tid == 0 && qd + 1 < q1) load_header(P, t, P.dec[qd + 1], (dq + 1) & 1);      // (decoder qd-1 ended with CTA barriers: its buffer is free)
-      epi_forward(P, t, I, lv, G, tmem, n, dq & 1, (dq >> 1) & 1u, out, gm);
+      float* acts = (P.fo.acts != nullptr && lv == P.acts_lv && row < npts) ? P.fo.acts + ((gp0 + row) * 5) * 32 + kCW * cg : nullptr;
+      epi_forward(P, t, I, lv, G, tmem, n, dq & 1, (dq >> 1) & 1u, out, gm, acts);
       if (lv == 3) { c0 = out[0]; c1 = out[1]; c2 = out[2]; } else occ += out[0];
       if (qd == 0 && cg == 0 && row < npts && P.fo.corner_idx != nullptr) {
         const nsb_grid& g = P.in.grid[lv];
@@ -851,14 +1067,23 @@ struct BwdExtra {            // behind the common shared-memory part
 };
 }  // namespace tl
 
-__global__ void __launch_bounds__(tl::kThreads, 2) render_bwd_tile_kernel(const __grid_constant__ KParams P) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+// WG = true: the item's decoder (the colour decoder) also gets its WEIGHT gradients (tensor-core contraction over the tile's points, see the
+// "tensor-core weight gradients" helpers): 96 KB more shared memory in front of the common part -> one CTA per SM.
+template <bool WG>
+__device__ __forceinline__ void render_bwd_tile_body(const KParams& P) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   using namespace tl;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = tid & (TM - 1), cg = tid >> 7;
-  TileSmem t; carve(smem_raw, t, true);
+  // (WG: the MN-major tiles need the 1024-byte alignment of their swizzle pattern: aligned by hand, 1 KB of slack in the launch size)
+  unsigned char* sbase = WG ? smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u) : smem_raw;
+  TileSmem t; carve(sbase + (WG ? kWgBytes : 0), t, true);
   BwdExtra& X = *reinterpret_cast<BwdExtra*>(t.extra);
   __shared__ int s_ndone, s_done[kMaxTileRays];
+  __shared__ __align__(8) uint64_t s_wgbar;
+  WgSmem wg;
+  wg.du = reinterpret_cast<float*>(sbase); wg.g = wg.du + 2 * kMnTile; wg.b = wg.du + 4 * kMnTile; wg.bar = &s_wgbar; wg.phase = 0u;
+  wg.dpk = WG ? P.d_packed[P.dec[0]] : nullptr;
 
   const int nsplit = P.split;
   const int tile = blockIdx.x / nsplit, my = blockIdx.x - tile * nsplit;
@@ -877,6 +1102,7 @@ __global__ void __launch_bounds__(tl::kThreads, 2) render_bwd_tile_kernel(const 
   Issuer I; I.L.P = &P; I.L.q = q0; I.L.q1 = q1; I.L.k = 0; I.L.loaded = 0; I.L.bwd = true; I.issued = 0; I.g = 0;
   if (tid == 0) {
     for (int i = 0; i < kNumBars; i++) mbar_init(t.bars + i, (i == B_AREADY || i == B_AREADY + 1) ? kEpiThreads / 32 : 1);
+    if (WG) mbar_init(&s_wgbar, 1);
     mbar_fence_init();
     load_header(P, t, P.dec[q0], 0);
     for (int i = 0; i < kSlots; i++) loader_issue(I.L, t);
@@ -968,7 +1194,8 @@ __global__ void __launch_bounds__(tl::kThreads, 2) render_bwd_tile_kernel(const 
       }
       const int dq = qd - q0;
       if (tid == 0 && qd + 1 < q1) load_header(P, t, P.dec[qd + 1], (dq + 1) & 1);      // (the previous decoder ended with CTA barriers: its buffer is free)
-      epi_backward(P, t, I, lv, G, tmem, n, dq & 1, (dq >> 1) & 1u, g_out, gm);
+      const float* acts_row = (WG && row < npts) ? P.bw.acts + ((gp0 + row) * 5) * 32 + kCW * cg : nullptr;
+      epi_backward<WG>(P, t, I, lv, G, tmem, n, dq & 1, (dq >> 1) & 1u, g_out, gm, WG ? &wg : nullptr, acts_row);
       epi_sync();                                                 // dL/dc rows + embedding partials visible
       const double* bb = lv == 0 ? P.in.coarse_bound : P.in.bound;
       const double sc[3] = {2.0 / (bb[1] - bb[0]), 2.0 / (bb[3] - bb[2]), 2.0 / (bb[5] - bb[4])};      // d(normalised)/dp, common.py:280-282
@@ -1035,5 +1262,7 @@ __global__ void __launch_bounds__(tl::kThreads, 2) render_bwd_tile_kernel(const 
     peer_sum13(P.tail.px, tot, 13, P.tail.out13, &s_seq2);
   }
 }
+__global__ void __launch_bounds__(tl::kThreads, 2) render_bwd_tile_kernel(const __grid_constant__ KParams P) { render_bwd_tile_body<false>(P); }
+__global__ void __launch_bounds__(tl::kThreads, 1) render_bwd_wg_tile_kernel(const __grid_constant__ KParams P) { render_bwd_tile_body<true>(P); }
 
 }  // namespace nsb

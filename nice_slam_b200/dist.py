@@ -129,8 +129,10 @@ class ShardedTrackingIteration:
         t_u, t_s = _linspaces(x.r.N_samples, x.r.N_surface, x.dev)
         inp = _inputs(call, ro, rd, x.depth_max, t_u, t_s, [g.detach() for g in grids])
         fo = _lib.ForwardOutputs(x.depth.data_ptr(), x.var.data_ptr(), x.rgb.data_ptr(), x.z_vals.data_ptr(), x.raw.data_ptr(), None,
-                                 x.masks.data_ptr(), x.split_ws.data_ptr() if x.split_bytes else None, x.split_bytes)
+                                 x.masks.data_ptr(), x.split_ws.data_ptr() if x.split_bytes else None, x.split_bytes,
+                                 x.acts.data_ptr() if x.acts is not None else None)
         bw = x._grads(c)
+        bw.acts = x.acts.data_ptr() if x.acts is not None else None
         if x.split_bytes:
             bw.split_workspace, bw.split_workspace_bytes = x.split_ws.data_ptr(), x.split_bytes
         bw.z_vals, bw.raw, bw.g_depth, bw.g_rgb, bw.masks = (x.z_vals.data_ptr(), x.raw.data_ptr(), x.g_depth.data_ptr(),
@@ -244,8 +246,10 @@ class ShardedMappingIteration:
         t_u, t_s = _linspaces(x.r.N_samples, x.r.N_surface, x.dev)
         inp = _inputs(call, ro, rd, x.depth_max, t_u, t_s, [g.detach() for g in grids])
         fo = _lib.ForwardOutputs(x.depth.data_ptr(), x.var.data_ptr(), x.rgb.data_ptr(), x.z_vals.data_ptr(), x.raw.data_ptr(), None,
-                                 x.masks.data_ptr(), x.split_ws.data_ptr() if x.split_bytes else None, x.split_bytes)
+                                 x.masks.data_ptr(), x.split_ws.data_ptr() if x.split_bytes else None, x.split_bytes,
+                                 x.acts.data_ptr() if x.acts is not None else None)
         bw = x._grads(c)
+        bw.acts = x.acts.data_ptr() if x.acts is not None else None
         if x.split_bytes:
             bw.split_workspace, bw.split_workspace_bytes = x.split_ws.data_ptr(), x.split_bytes
         bw.z_vals, bw.raw, bw.g_depth, bw.g_rgb, bw.masks = (x.z_vals.data_ptr(), x.raw.data_ptr(), x.g_depth.data_ptr(),

@@ -175,8 +175,15 @@ class _RenderFn(torch.autograd.Function):
         masks = torch.empty(n, S, 15, dtype=torch.int32, device=dev)      # ReLU sign bits: lets backward skip the forward recompute
         nsplit = L.nsb_split_workspace_bytes(n, S)                        # small batches: one CTA per (ray group, decoder)
         split = torch.zeros(nsplit, dtype=torch.uint8, device=dev) if nsplit else None
+        # colour-decoder parameters that need a gradient (the mapper's colour stage, Mapper.py:339-341): keep the decoder's layer outputs so that
+        # the backward computes the weight gradients on the tensor cores
+        acts = None
+        if call.stage == "color":
+            k0 = 3 + n_lvl + sum(len(call.param_names[l]) for l in call.levels[: call.levels.index("color")])
+            if any(ctx.needs_input_grad[k0 + i] for i in range(len(call.param_names["color"]))):
+                acts = torch.empty(n, S, 5, 32, dtype=torch.float32, device=dev)
         out = _lib.ForwardOutputs(depth.data_ptr(), var.data_ptr(), rgb.data_ptr(), z_vals.data_ptr(), raw.data_ptr(), None, masks.data_ptr(),
-                                  split.data_ptr() if nsplit else None, nsplit)
+                                  split.data_ptr() if nsplit else None, nsplit, acts.data_ptr() if acts is not None else None)
         corner = None
         if call.aux is not None:
             corner = torch.empty(n, S, 3, dtype=torch.int32, device=dev)
@@ -188,6 +195,7 @@ class _RenderFn(torch.autograd.Function):
         ctx.call = call
         ctx.n_lvl = n_lvl
         ctx.keep = (ro, rd, depth_max, t_u, t_s, z_vals, raw, masks, split)
+        ctx.acts = acts
         ctx.grids = [g.detach() for g in grids]
         ctx.param_shapes = [tuple(p.shape) for p in params]
         return depth, var, rgb
@@ -206,6 +214,8 @@ class _RenderFn(torch.autograd.Function):
         bw.z_vals, bw.raw, bw.masks = z_vals.data_ptr(), raw.data_ptr(), masks.data_ptr()
         if split is not None:
             bw.split_workspace, bw.split_workspace_bytes = split.data_ptr(), split.numel()
+        if ctx.acts is not None:
+            bw.acts = ctx.acts.data_ptr()
         gd = g_depth.detach().contiguous().double() if g_depth is not None else torch.zeros(n, dtype=torch.float64, device=dev)
         gv = g_var.detach().contiguous().double() if g_var is not None else None
         gc = g_rgb.detach().contiguous().float() if g_rgb is not None else None

@@ -97,9 +97,13 @@ class IterationContext:
         self.d_frames = self.packed[4: 4 + 12 * self.n_frames].view(self.n_frames, 12)
         self.d_grid = {key: self.packed[sect[key][0]: sect[key][0] + sect[key][1]].view(-1, 32) for key in self.grad_grids if key in self.masked}
         self.d_flat = {lvl: self.packed[sect["dec_" + lvl][0]: sect["dec_" + lvl][0] + sect["dec_" + lvl][1]] for lvl in self.grad_decoders}
+        # layer outputs of the colour decoder, kept by the forward when its weight gradients are wanted: the backward then computes them on the
+        # tensor cores (nsb_forward_outputs.acts); 640 B per sample point
+        self.acts = torch.empty(n, S, 5, 32, dtype=f32, device=dev) if (stage == "color" and "color" in self.grad_decoders) else None
         self.buf = _lib.IterationBuffers(self.depth.data_ptr(), self.var.data_ptr(), self.rgb.data_ptr(), self.z_vals.data_ptr(),
                                          self.raw.data_ptr(), self.masks.data_ptr(), self.g_depth.data_ptr(), self.g_rgb.data_ptr(), self.loss.data_ptr(),
-                                         self.depth_max.data_ptr(), self.ws.data_ptr(), self.ws.numel(), None, None)
+                                         self.depth_max.data_ptr(), self.ws.data_ptr(), self.ws.numel(), None, None,
+                                         self.acts.data_ptr() if self.acts is not None else None)
         self.ev_bwd = None
         # pinned host staging for run_host(): [rays_o | rays_d | gt_depth] f32, gt_color, and the read-back block
         cuda = dev.type == "cuda" and host_staging      # (pin_memory is a synchronising cudaHostAlloc: skipped when run_host() is never used)

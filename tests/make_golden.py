@@ -97,46 +97,56 @@ def corner_indices(pts, bound, shape):
     return torch.stack(out, -1)
 
 
-def gen_render_cases():
+def _render_case(scene_name, variant, stage, n, sc, cfg, slam, renderer, ray_seed=3):
+    """One reference render_batch_ray + backward with random output seeds on `n` rays: inputs, outputs, z_vals, voxel-corner indices, all gradients."""
     primary = {"coarse": "grid_coarse", "middle": "grid_middle", "fine": "grid_fine", "color": "grid_fine"}
+    ro, rd, gd, gc = su.make_rays(sc, n, seed=ray_seed)
+    ro = ro.clone()
+    ro[:8, 0] += 5.0               # some rays leave the bound early -> out-of-bound samples
+    gt = None if stage == "coarse" else gd
+    lv = {"coarse": ["coarse"], "middle": ["middle"], "fine": ["fine", "middle"], "color": ["fine", "color", "middle"]}[stage]
+    ro1 = ro.clone().requires_grad_(True)
+    rd1 = rd.clone().requires_grad_(True)
+    c = {k: v.clone().requires_grad_(k[5:] in lv) for k, v in slam.shared_c.items()}
+    for p in slam.shared_decoders.parameters():
+        p.grad = None
+        p.requires_grad_(True)
+    d, u, col = renderer.render_batch_ray(c, slam.shared_decoders, rd1, ro1, "cpu", stage, gt_depth=gt)
+    g = torch.Generator().manual_seed(55)
+    gD = torch.randn(n, generator=g, dtype=torch.float64)
+    gV = torch.randn(n, generator=g, dtype=torch.float64) * 3
+    gC = torch.randn(n, 3, generator=g)
+    ((d * gD).sum() + (u * gV).sum() + (col * gC).sum()).backward()
+    z = tp.sample_z_vals(ro, rd, gt, slam.bound, cfg["rendering"]["N_samples"], cfg["rendering"]["N_surface"], stage)
+    pts = (ro[:, None, :] + rd[:, None, :] * z[:, :, None]).reshape(-1, 3)
+    bnd = slam.bound * 2 if stage == "coarse" else slam.bound
+    cidx = corner_indices(pts, bnd, sc["shapes"][primary[stage]]).reshape(n, -1, 3)
+    # sanity: the port reproduces the reference bit for bit on this very case
+    d2, u2, c2 = tp.render_batch_ray(slam.shared_c, tp.decoders_state(slam.shared_decoders), rd, ro, stage, gt, slam.bound)
+    assert torch.equal(d2, d.detach()) and torch.equal(u2, u.detach()) and torch.equal(c2, col.detach())
+    return dict(scene=scene_name, variant=variant, stage=stage, rays_o=ro, rays_d=rd, gt_depth=gt, g_depth=gD, g_var=gV, g_rgb=gC,
+                depth=d.detach(), var=u.detach(), rgb=col.detach(), z_vals=z, corner_idx=cidx,
+                d_rays_o=ro1.grad, d_rays_d=rd1.grad,
+                d_grid={k: su.grid_summary(c[k].grad) for k in c if c[k].grad is not None},
+                d_dec={l: {k: v.grad.clone() for k, v in getattr(slam.shared_decoders, l + "_decoder").named_parameters()
+                           if v.grad is not None} for l in lv})
+
+
+def gen_render_cases():
     for variant in ("soft", "init"):
         sc, cfg, slam, renderer = ref_scene("room0", variant)
         for stage in ("coarse", "middle", "fine", "color"):
             if variant == "init" and stage != "color":
                 continue
-            n = 96
-            ro, rd, gd, gc = su.make_rays(sc, n, seed=3)
-            ro = ro.clone()
-            ro[:8, 0] += 5.0               # some rays leave the bound early -> out-of-bound samples
-            gt = None if stage == "coarse" else gd
-            lv = {"coarse": ["coarse"], "middle": ["middle"], "fine": ["fine", "middle"], "color": ["fine", "color", "middle"]}[stage]
-            ro1 = ro.clone().requires_grad_(True)
-            rd1 = rd.clone().requires_grad_(True)
-            c = {k: v.clone().requires_grad_(k[5:] in lv) for k, v in slam.shared_c.items()}
-            for p in slam.shared_decoders.parameters():
-                p.grad = None
-                p.requires_grad_(True)
-            # capture z_vals by wrapping torch.sort? -> simpler: recompute with the (bit-identical) port, then assert
-            d, u, col = renderer.render_batch_ray(c, slam.shared_decoders, rd1, ro1, "cpu", stage, gt_depth=gt)
-            g = torch.Generator().manual_seed(55)
-            gD = torch.randn(n, generator=g, dtype=torch.float64)
-            gV = torch.randn(n, generator=g, dtype=torch.float64) * 3
-            gC = torch.randn(n, 3, generator=g)
-            ((d * gD).sum() + (u * gV).sum() + (col * gC).sum()).backward()
-            z = tp.sample_z_vals(ro, rd, gt, slam.bound, cfg["rendering"]["N_samples"], cfg["rendering"]["N_surface"], stage)
-            pts = (ro[:, None, :] + rd[:, None, :] * z[:, :, None]).reshape(-1, 3)
-            bnd = slam.bound * 2 if stage == "coarse" else slam.bound
-            cidx = corner_indices(pts, bnd, sc["shapes"][primary[stage]]).reshape(n, -1, 3)
-            # sanity: the port reproduces the reference bit for bit on this very case
-            d2, u2, c2 = tp.render_batch_ray(slam.shared_c, tp.decoders_state(slam.shared_decoders), rd, ro, stage, gt, slam.bound)
-            assert torch.equal(d2, d.detach()) and torch.equal(u2, u.detach()) and torch.equal(c2, col.detach())
-            case = dict(scene="room0", variant=variant, stage=stage, rays_o=ro, rays_d=rd, gt_depth=gt, g_depth=gD, g_var=gV, g_rgb=gC,
-                        depth=d.detach(), var=u.detach(), rgb=col.detach(), z_vals=z, corner_idx=cidx,
-                        d_rays_o=ro1.grad, d_rays_d=rd1.grad,
-                        d_grid={k: su.grid_summary(c[k].grad) for k in c if c[k].grad is not None},
-                        d_dec={l: {k: v.grad.clone() for k, v in getattr(slam.shared_decoders, l + "_decoder").named_parameters()
-                                   if v.grad is not None} for l in lv})
-            save("render_%s_%s.pt" % (stage, variant), case)
+            save("render_%s_%s.pt" % (stage, variant), _render_case("room0", variant, stage, 96, sc, cfg, slam, renderer))
+
+
+def gen_other_scene_cases():
+    """render_color_soft_<scene>.pt: the unmodified reference Renderer + autograd on the ScanNet scene0000 and Apartment volumes (SURVEY.md 8d
+    configs 3 and 4: other bounds, grid shapes and intrinsics than room0), stage color, 64 rays, voxel and decoder gradients included."""
+    for name in ("scene0000", "apartment"):
+        sc, cfg, slam, renderer = ref_scene(name, "soft")
+        save("render_color_soft_%s.pt" % name, _render_case(name, "soft", "color", 64, sc, cfg, slam, renderer, ray_seed=5))
 
 
 class RecOptim:
@@ -510,6 +520,9 @@ def gen_keyframe_overlap_case():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "scenes":
+        gen_other_scene_cases()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "keyframes":
         import warnings
         warnings.filterwarnings("ignore")
@@ -531,6 +544,7 @@ if __name__ == "__main__":
     gen_scenes()
     gen_decoders()
     gen_render_cases()
+    gen_other_scene_cases()
     gen_tracker_case()
     gen_mapper_cases()
     gen_mapper_loop_case()

@@ -445,6 +445,50 @@ def test_masked_mapping_iteration_packed_block(backend_decoder_grads):
 
 
 # ------------------------------------------------------------------------------------ more edge cases
+@pytest.mark.parametrize("n_rays", [96, 437, 1200])
+def test_tensor_core_weight_gradients_match_fp32_pass_and_oracle(n_rays):
+    """Colour-decoder weight gradients of a mapping iteration (src/Mapper.py:339-341,503): the tensor-core contraction over the points of a tile
+    (render_bwd_wg_tile_kernel, layer outputs kept by the forward) against the FP32-FMA pass that recomputes the forward (option wgrad_tc = 0)
+    and against the oracle; ragged last tile (n_rays * 48 is not a multiple of 128) and more tiles than SMs included."""
+    from nice_slam_b200 import _lib
+    from nice_slam_b200.steps import IterationContext
+    L = _lib.lib()
+    sc = su.load_scenes()["room0"]
+    grids, dec_state = su.make_grids(sc, "soft"), su.load_decoders("soft")
+    renderer, c, dec = make_renderer(sc, grids, dec_state, DEV)
+    ro, rd, gd, gc = su.make_rays(sc, n_rays, seed=31 + n_rays)
+    dev_in = [t.to(DEV) for t in (ro, rd, gd, gc.float())]
+    keys = ("grid_fine", "grid_color", "grid_middle")
+    out = {}
+    try:
+        for mode in (1, 0):
+            assert L.nsb_set_option(b"wgrad_tc", mode) == 0
+            ctx = IterationContext(renderer, n_rays, "color", DEV, kind="map", grad_grids=keys, grad_decoders=("color",))
+            for _ in range(2):                                        # twice: accumulation buffers are re-zeroed per run
+                ctx.run(c, dec, *dev_in)
+            torch.cuda.synchronize()
+            out[mode] = dict(flat=ctx.d_flat["color"].clone(), d_o=ctx.d_rays_o.clone(), d_d=ctx.d_rays_d.clone(), loss=float(ctx.loss),
+                             grid={k: ctx.d_grid[k].clone() for k in keys})
+    finally:
+        L.nsb_set_option(b"wgrad_tc", 1)
+    a, b = out[1], out[0]
+    assert abs(a["loss"] - b["loss"]) <= 1e-9 * abs(b["loss"])
+    assert float(b["flat"].abs().max()) > 0
+    lay = {nm: (off, cnt) for nm, off, cnt in _lib.flat_layout(_lib.LEVELS.index("color"))}
+    for nm, (off, cnt) in lay.items():                               # every parameter tensor on its own scale (weights, biases, embedding matrix)
+        assert rel(a["flat"][off:off + cnt], b["flat"][off:off + cnt]) < 2e-5, nm
+    assert rel(a["d_o"], b["d_o"]) < 1e-5 and rel(a["d_d"], b["d_d"]) < 1e-5
+    for k in keys:
+        assert rel(a["grid"][k], b["grid"][k]) < 1e-5, k
+    if n_rays <= 437:                                                # oracle (CPU autograd) on the smaller batches
+        bound = su.scene_bound(sc)
+        want = tp.iteration("map", grids, dec_state, ro, rd, gd, gc.float(), "color", bound, grad_grids=keys, grad_decoders=("color",))
+        flat = a["flat"].cpu()
+        for nm, v in want["d_dec"]["color"].items():
+            off, cnt = lay[nm]
+            assert rel(flat[off:off + cnt].view(v.shape), v) < 1e-4, nm
+
+
 def test_render_img_matches_oracle_per_ray_batch():
     """Renderer.render_img (Renderer.py:200-255): full image in ray_batch_size chunks; the batch-global depth maxima are per chunk,
     exactly as in the reference."""
