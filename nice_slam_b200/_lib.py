@@ -127,6 +127,9 @@ def lib():
         backend = os.environ.get("NSB_MLP_BACKEND")          # 1 = FP32-FMA decoders, 2 = tcgen05 decoders (default: auto)
         if backend is not None and h.nsb_set_option(b"mlp_backend", int(backend)) != 0:
             raise RuntimeError("bad NSB_MLP_BACKEND=%r" % backend)
+        wg = os.environ.get("NSB_WGRAD_TC")                  # 0 = decoder weight gradients by the FP32-FMA pass (default: tensor cores)
+        if wg is not None:
+            h.nsb_set_option(b"wgrad_tc", int(wg))
         _LIB = h
     return _LIB
 

@@ -108,7 +108,7 @@ class _PackCache:
 class _Call:
     """Non-tensor arguments of one render call."""
     __slots__ = ("stage", "levels", "bound", "cbound", "n_samples", "n_surface", "gt_depth", "packed", "param_names",
-                 "aux")
+                 "aux", "masked", "grid_data")
 
 
 INLINE_MAX_RAYS = 1024          # NSB_INLINE_MAX_RAYS of include/nice_slam_b200.h
@@ -166,7 +166,10 @@ class _RenderFn(torch.autograd.Function):
             depth_max = torch.empty(2, dtype=torch.float32, device=dev)
             _lib.check(L.nsb_batch_max_depth(_ptr(call.gt_depth), n, _ptr(depth_max), _stream()), "nsb_batch_max_depth")
         t_u, t_s = _linspaces(call.n_samples, call.n_surface, dev)
-        inp = _inputs(call, ro, rd, depth_max, t_u, t_s, [g.detach() for g in grids])
+        # a grid argument is either the grid itself or, for a frustum-masked grid (see FusedRenderer._masked_leaf), the mapper's 1-D leaf
+        # `val_grad`; the data the kernels read is always the full grid
+        data = [call.grid_data[j] if call.masked[j] is not None else grids[j].detach() for j in range(n_lvl)]
+        inp = _inputs(call, ro, rd, depth_max, t_u, t_s, data)
         depth = torch.empty(n, dtype=torch.float64, device=dev)
         var = torch.empty(n, dtype=torch.float64, device=dev)
         rgb = torch.empty(n, 3, dtype=torch.float32, device=dev)
@@ -196,7 +199,7 @@ class _RenderFn(torch.autograd.Function):
         ctx.n_lvl = n_lvl
         ctx.keep = (ro, rd, depth_max, t_u, t_s, z_vals, raw, masks, split)
         ctx.acts = acts
-        ctx.grids = [g.detach() for g in grids]
+        ctx.grids = data
         ctx.param_shapes = [tuple(p.shape) for p in params]
         return depth, var, rgb
 
@@ -226,8 +229,17 @@ class _RenderFn(torch.autograd.Function):
             d_d = torch.empty(n, 3, dtype=torch.float32, device=dev)
             bw.d_rays_o, bw.d_rays_d = d_o.data_ptr(), d_d.data_ptr()
         d_grids = [None] * n_lvl
+        compact = {}
         for j, lvl in enumerate(call.levels):
-            if needs[3 + j]:
+            if needs[3 + j] and call.masked[j] is not None:
+                # frustum-masked parameterisation (Mapper.py:321-333): COMPACT gradient of the selected voxels only -- no dense zero-fill, no
+                # index_put backward; converted to the reference's `val[mask]` order below
+                mv = call.masked[j]
+                dg = torch.zeros(max(mv.count, 1), 32, dtype=torch.float32, device=dev)
+                compact[j] = dg
+                li = LEVELS.index(lvl)
+                bw.d_grid[li], bw.slot_map[li] = dg.data_ptr(), mv.slot_map.data_ptr()
+            elif needs[3 + j]:
                 g = ctx.grids[j]
                 dg = torch.zeros_like(g)
                 if dg.stride() != g.stride():
@@ -259,6 +271,9 @@ class _RenderFn(torch.autograd.Function):
             _lib.check(L.nsb_render_backward(C.byref(inp), C.byref(bw), _stream()), "nsb_render_backward")
         elif d_o is not None:
             d_o.zero_(); d_d.zero_()
+        for j, dg in compact.items():
+            mv = call.masked[j]
+            d_grids[j] = mv.to_reference(dg[: mv.count]) if mv.count > 0 else torch.zeros(0, dtype=torch.float32, device=dev)
         return (None, d_o if needs[1] else None, d_d if needs[2] else None, *d_grids, *d_params)
 
 
@@ -282,10 +297,13 @@ class FusedRenderer(object):
         if convert_grids and getattr(slam, "shared_c", None) is not None:
             to_channels_last(slam.shared_c)        # layout conversion point, before Mapper/Tracker capture the dict
         self._cache = _PackCache()
+        self._mask_cache = {}
+        self.detect_masked_grids = True
 
     def __getstate__(self):                        # pickled into spawned processes: no device state travels
         d = dict(self.__dict__)
         d["_cache"] = None
+        d["_mask_cache"] = {}
         return d
 
     def __setstate__(self, d):
@@ -318,6 +336,7 @@ class FusedRenderer(object):
         call.packed, params = self._cache.get(decoders, call.levels, torch.device(device) if not isinstance(device, torch.device) else device)
         call.param_names = {lvl: [nm for nm, _, _ in _lib.flat_layout(LEVELS.index(lvl))] for lvl in call.levels}
         call.aux = aux
+        call.masked, call.grid_data = [None] * len(call.levels), [None] * len(call.levels)
         grids = [c["grid_" + lvl] for lvl in call.levels]
         plist = [params[lvl][nm] for lvl in call.levels for nm in call.param_names[lvl]]
         return call, grids, plist
@@ -329,7 +348,47 @@ class FusedRenderer(object):
         _require_cuda(rays_o, "rays_o")
         _require_cuda(rays_d, "rays_d")
         call, grids, plist = self._call(c, decoders, stage, gt_depth, rays_o.device, aux)
+        if self.detect_masked_grids and torch.is_grad_enabled():
+            for j, g in enumerate(grids):
+                sel = self._masked_leaf(g)
+                if sel is not None:                        # the mapper's `val[mask] = val_grad`: route the gradient to val_grad directly
+                    grids[j], call.masked[j], call.grid_data[j] = sel[0], sel[1], g.detach()
         return _RenderFn.apply(call, rays_o, rays_d, *grids, *plist)
+
+    def _masked_leaf(self, g):
+        """Detects the reference mapper's frustum-masked parameterisation at the boundary (src/Mapper.py:393-401): `val[mask] = val_grad; c[key] = val`
+        makes c[key] the output of an in-place index_put whose only differentiable input is the leaf `val_grad`.  Autograd would then need the DENSE
+        gradient of the grid (a 23-59 MB zero-fill + scatter per grid and iteration) just to gather `grad[mask]` back out of it.  When the pattern is
+        recognised -- IndexPutBackward0 with one boolean mask of the grid's shape that selects whole voxels (all 32 channels), a non-differentiable
+        target and a leaf of matching size -- returns (val_grad, MaskedVoxels): render_batch_ray then differentiates with respect to val_grad itself
+        and the backward kernel scatters into a compact [n_selected, 32] buffer.  Anything else returns None (dense path, same results)."""
+        fn = g.grad_fn
+        if fn is None or type(fn).__name__ != "IndexPutBackward0" or not g.is_cuda or g.dim() != 5:
+            return None
+        try:
+            idx, acc, nxt = fn._saved_indices, fn._saved_accumulate, fn.next_functions
+        except (AttributeError, RuntimeError):
+            return None
+        if acc or len(idx) != 1 or idx[0] is None or idx[0].dtype != torch.bool or tuple(idx[0].shape) != tuple(g.shape):
+            return None
+        if len(nxt) != 2 or nxt[0][0] is not None or nxt[1][0] is None or not hasattr(nxt[1][0], "variable"):
+            return None
+        leaf, mask = nxt[1][0].variable, idx[0]
+        key = (mask.data_ptr(), mask._version, tuple(mask.shape), str(mask.device))
+        mv = self._mask_cache.get(key)
+        if mv is None:
+            vm = mask[0, 0]
+            if not bool((mask == vm).all()):             # the reference repeats one voxel mask over the channels (Mapper.py:319-320)
+                self._mask_cache[key] = False
+                return None
+            from .masked import MaskedVoxels
+            mv = MaskedVoxels(g.detach(), vm)
+            if len(self._mask_cache) >= 16:
+                self._mask_cache.pop(next(iter(self._mask_cache)))
+            self._mask_cache[key] = mv
+        if mv is False or leaf.dim() != 1 or leaf.numel() != 32 * mv.count or leaf.dtype != torch.float32 or leaf.device != g.device:
+            return None
+        return leaf, mv
 
     def eval_points(self, p, decoders, c=None, stage="color", device="cuda:0"):
         """Occupancy/colour of free points (Renderer.eval_points, Renderer.py:23-61).  No autograd: inside

@@ -489,6 +489,49 @@ def test_tensor_core_weight_gradients_match_fp32_pass_and_oracle(n_rays):
             assert rel(flat[off:off + cnt].view(v.shape), v) < 1e-4, nm
 
 
+def test_unmodified_mapper_indexing_gets_compact_gradients():
+    """The reference mapper's own parameterisation at the renderer boundary (src/Mapper.py:317-333,393-401): `val_grad = Variable(val[mask])`,
+    then every iteration `val[mask] = val_grad; c[key] = val`.  FusedRenderer recognises the index_put and differentiates with respect to val_grad
+    directly (compact gradients, no dense zero-fill); the result equals the generic dense autograd path (detection switched off) and the oracle."""
+    sc = su.load_scenes()["room0"]
+    grids, dec_state = su.make_grids(sc, "soft"), su.load_decoders("soft")
+    renderer, c0, dec = make_renderer(sc, grids, dec_state, DEV)
+    n = 160
+    ro, rd, gd, gc = [t.to(DEV) for t in su.make_rays(sc, n, seed=77)]
+    keys = ("grid_middle", "grid_fine", "grid_color")
+    masks = _random_masks(grids, keys, 0.5)
+    for p in dec.parameters():
+        p.requires_grad_(False)
+    got = {}
+    for detect in (True, False):
+        renderer.detect_masked_grids = detect
+        c, leaves = {}, {}
+        for k, v in c0.items():
+            val = v.detach().clone(memory_format=torch.preserve_format)
+            if k in keys:
+                mask = masks[k].to(DEV).unsqueeze(0).unsqueeze(0).repeat(1, val.shape[1], 1, 1, 1)      # Mapper.py:319-320
+                val_grad = val[mask].clone().requires_grad_(True)                                      # :321-325
+                val[mask] = val_grad                                                                   # :399
+                leaves[k] = val_grad
+            c[k] = val
+        d, u, col = renderer.render_batch_ray(c, dec, rd, ro, DEV, "color", gt_depth=gd)
+        loss = torch.abs(gd - d)[gd > 0].sum() + 0.2 * torch.abs(gc.float() - col).sum()               # :487-493
+        loss.backward()
+        got[detect] = dict(loss=float(loss), grads={k: leaves[k].grad.clone() for k in keys})
+    renderer.detect_masked_grids = True
+    assert len(renderer._mask_cache) == 3 and all(v is not False for v in renderer._mask_cache.values())        # the pattern WAS recognised
+    assert abs(got[True]["loss"] - got[False]["loss"]) <= 1e-12 * abs(got[False]["loss"])
+    for k in keys:
+        a, b = got[True]["grads"][k], got[False]["grads"][k]
+        assert a.shape == b.shape and float(b.abs().max()) > 0
+        assert rel(a, b) < 1e-5, k
+    # oracle: dense CPU autograd restricted to the mask
+    want = tp.iteration("map", grids, dec_state, ro.cpu(), rd.cpu(), gd.cpu(), gc.float().cpu(), "color", su.scene_bound(sc), grad_grids=keys, grad_decoders=())
+    for k in keys:
+        m = masks[k].unsqueeze(0).unsqueeze(0).expand_as(grids[k])
+        assert rel(got[True]["grads"][k], want["d_" + k][m]) < 1e-4, k
+
+
 def test_render_img_matches_oracle_per_ray_batch():
     """Renderer.render_img (Renderer.py:200-255): full image in ray_batch_size chunks; the batch-global depth maxima are per chunk,
     exactly as in the reference."""
