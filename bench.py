@@ -569,10 +569,11 @@ def run_native(args):
     warm_ms, _, _ = timed(step_dev, args.steps, 3, False)                 # L2-warm (production steady state), reported as extra
     e2e_ms, _, _ = timed(step_e2e, args.steps, 3, True)
 
+    fast = os.environ.get("NSB_BENCH_FAST") == "1"              # development aid: headline numbers only (never used by the driver)
     dbg("mapping sharded workload")
-    map_sharded = mapping_sharded_workload(sc, renderer, c, dec, dev, flush, rank, world)
+    map_sharded = None if fast else mapping_sharded_workload(sc, renderer, c, dec, dev, flush, rank, world)
     dbg("strong-scaled scene workloads")
-    scenes = scene_workloads(dev, flush, rank, world)
+    scenes = None if fast else scene_workloads(dev, flush, rank, world)
 
     if rank != 0:
         shutdown(world)
@@ -615,7 +616,7 @@ def run_native(args):
                                    "note": "per GPU, whole iteration; algorithmic = fp32-equivalent flops of the decoders' forward + input-gradient backward "
                                            "(SURVEY 8a MAC counts), achieved = what the tensor cores execute for them; sm__pipe_tensor_cycles_active from the "
                                            "ncu capture is in profiles/"}
-    if world == 1:
+    if world == 1 and not fast:
         line["extra"].update(extra_workloads(sc, renderer, c, dec, dev, flush, peak))
         best = pick_cpu_threads(sc, host)
         step = cpu_iteration_fn(sc, host)

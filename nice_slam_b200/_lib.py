@@ -127,6 +127,9 @@ def lib():
         backend = os.environ.get("NSB_MLP_BACKEND")          # 1 = FP32-FMA decoders, 2 = tcgen05 decoders (default: auto)
         if backend is not None and h.nsb_set_option(b"mlp_backend", int(backend)) != 0:
             raise RuntimeError("bad NSB_MLP_BACKEND=%r" % backend)
+        sr = os.environ.get("NSB_SMALL_RAYS")                # auto back-end: batches up to this many rays use the ray-group kernels
+        if sr is not None and hasattr(h, "nsb_set_option"):
+            h.nsb_set_option(b"small_rays", int(sr))
         wg = os.environ.get("NSB_WGRAD_TC")                  # 0 = decoder weight gradients by the FP32-FMA pass (default: tensor cores)
         if wg is not None:
             h.nsb_set_option(b"wgrad_tc", int(wg))

@@ -1048,7 +1048,19 @@ static bool plan_split(KParams* K, int nd, void* ws, size_t ws_bytes) {
 
 static size_t tile_smem_bytes(bool bwd) { return tl::common_bytes(bwd) + (bwd ? sizeof(tl::BwdExtra) : 0); }
 static size_t tile_wg_smem_bytes() { return tl::kWgBytes + tile_smem_bytes(true) + 1024; }
-static bool use_tile_kernels(int S) { return (g_mlp_backend == 0 || g_mlp_backend == 3) && S >= tl::kMinSamples && S <= NSB_MAX_SAMPLES; }
+// Which tensor-core kernel family serves a launch.  mlp_backend 3: always the tile kernels; 2: always the round-1 ray-group kernels; 0 (auto): the
+// tile kernels, except that single-GPU batches of up to g_small_rays rays go to the ray-group kernels (512 threads on one tile at a time: shorter
+// per-tile chains; option "small_rays", 0 = never).  Forward and backward of an iteration see the same (S, n_rays) and so pick the same family
+// (the saved ReLU bits are laid out per family).
+static int g_small_rays = 0;
+static bool use_tile_kernels(int S, int n_rays, bool sharded) {
+  if (!(g_mlp_backend == 0 || g_mlp_backend == 3) || S < tl::kMinSamples || S > NSB_MAX_SAMPLES) return false;
+  if (g_mlp_backend == 0 && !sharded && n_rays <= g_small_rays && S <= kMaxPtsTc) return false;
+  return true;
+}
+static bool use_group_kernels(int S, int n_rays, bool sharded) {
+  return S <= kMaxPtsTc && (g_mlp_backend == 2 || (g_mlp_backend == 0 && !use_tile_kernels(S, n_rays, sharded)));
+}
 static bool g_attr_set[kMaxDevices] = {false};
 static int set_attrs() {
   const int dev = current_device();
@@ -1073,6 +1085,7 @@ using namespace nsb;
 
 extern "C" int nsb_set_option(const char* key, int value) {
   if (key && !strcmp(key, "wgrad_tc")) { g_wgrad_tc = value != 0; return NSB_OK; }
+  if (key && !strcmp(key, "small_rays")) { if (value < 0) { set_error("small_rays must be >= 0"); return NSB_ERR_ARG; } g_small_rays = value; return NSB_OK; }
   if (key && !strcmp(key, "mlp_backend")) { if (value < 0 || value > 3) { set_error("mlp_backend must be 0 (auto = tile kernels), 1 (FP32-FMA), 2 (tcgen05, round-1 ray-group kernels) or 3 (tcgen05 tile kernels)"); return NSB_ERR_ARG; } g_mlp_backend = value; return NSB_OK; }
   set_error("unknown option %s", key ? key : "(null)"); return NSB_ERR_ARG;
 }
@@ -1086,13 +1099,15 @@ int nsb::render_forward_fused(const nsb_render_inputs* in, const nsb_forward_out
   if (in->n_rays == 0) return NSB_OK;
   KParams K; fill_common(K, in); K.fo = *out; memset(&K.bw, 0, sizeof(K.bw));
   if (fs != nullptr) K.fs = *fs;
-  if (g_mlp_backend == 1 || K.S > kMaxPtsTc || (g_mlp_backend != 2 && !use_tile_kernels(K.S))) K.fo.masks = nullptr;        // only the tensor-core forward produces masks
+  const bool sharded = fs != nullptr && fs->px.world > 1;
+  const bool tile = use_tile_kernels(K.S, in->n_rays, sharded), group = use_group_kernels(K.S, in->n_rays, sharded);
+  if (!tile && !group) K.fo.masks = nullptr;                      // only the tensor-core forwards produce masks
   if (K.S > NSB_MAX_SAMPLES) { set_error("n_samples+n_surface = %d exceeds %d", K.S, NSB_MAX_SAMPLES); return NSB_ERR_UNSUPPORTED; }
   if (K.has_gt && in->n_surface > 0 && !in->t_surface) { set_error("t_surface NULL"); return NSB_ERR_ARG; }
   if ((rc = set_attrs())) return rc;
-  if (K.fs.px.world > 1 && !(use_tile_kernels(K.S) && in->depth_max == nullptr && in->gt_depth != nullptr)) {
+  if (K.fs.px.world > 1 && !(tile && in->depth_max == nullptr && in->gt_depth != nullptr)) {
     set_error("in-kernel exchanges of a sharded forward need the tile kernels and <= %d rays per rank", NSB_INLINE_MAX_RAYS); return NSB_ERR_UNSUPPORTED; }
-  if (use_tile_kernels(K.S)) {                            // tile kernels: item = (128-point tile, decoder), two CTAs per SM
+  if (tile) {                                             // tile kernels: item = (128-point tile, decoder), two CTAs per SM
     if (!out->z_vals || !out->raw) { set_error("the tensor-core forward needs z_vals and raw outputs"); return NSB_ERR_ARG; }
     TileWs w;
     if (!tile_ws_plan(out->split_workspace, out->split_workspace_bytes, in->n_rays, K.S, K.n_dec, false, &w)) {
@@ -1107,7 +1122,7 @@ int nsb::render_forward_fused(const nsb_render_inputs* in, const nsb_forward_out
   choose_config(in->n_rays, K.S, kRowsFwd, false, K.wbytes, 8, &K, &warps, &smem);
   if (smem > kSmemCap) { set_error("shared-memory budget exceeded (%zu bytes)", smem); return NSB_ERR_UNSUPPORTED; }
   const int grid = (in->n_rays + K.rays_per_block - 1) / K.rays_per_block;
-  if (g_mlp_backend == 2 && K.S <= kMaxPtsTc) {          // tensor-core decoders, 512 threads, <= 2 tiles of 128 points per CTA
+  if (group) {                                            // tensor-core decoders, 512 threads, <= 2 tiles of 128 points per CTA
     choose_config(in->n_rays, K.S, kRowsFwd, false, K.wbytes, 8, &K, &warps, &smem, kMaxPtsTc);
     plan_split(&K, K.n_dec, out->split_workspace, out->split_workspace_bytes);
     const int grid_tc = ((in->n_rays + K.rays_per_block - 1) / K.rays_per_block) * K.split;
@@ -1192,7 +1207,9 @@ int nsb::render_backward_tail(const nsb_render_inputs* in, const nsb_backward_ar
   int warps; size_t smem;
   choose_config(in->n_rays, K.S, kRowsBwd, true, K.wbytes, 8, &K, &warps, &smem);
   if (smem > kSmemCap) { set_error("shared-memory budget exceeded (%zu bytes)", smem); return NSB_ERR_UNSUPPORTED; }
-  if (bw->masks != nullptr && ((g_mlp_backend == 2 && K.S <= kMaxPtsTc) || use_tile_kernels(K.S))) {     // (no saved ReLU masks -> FP32 kernel, which recomputes the forward)
+  const bool sharded = tail != nullptr && tail->px.world > 1;
+  const bool tile = use_tile_kernels(K.S, in->n_rays, sharded), group = use_group_kernels(K.S, in->n_rays, sharded);
+  if (bw->masks != nullptr && (group || tile)) {                  // (no saved ReLU masks -> FP32 kernel, which recomputes the forward)
     // Tensor-core kernel for the decoders that only need input gradients (rays, voxels).  Decoders whose WEIGHT gradients are
     // requested (the colour decoder in the mapper's colour stage, Mapper.py:339-341) go through the FP32-FMA kernel in a second
     // launch that adds its share of the ray gradients.
@@ -1205,10 +1222,10 @@ int nsb::render_backward_tail(const nsb_render_inputs* in, const nsb_backward_ar
     }
     // Weight gradients on the tensor cores: the colour decoder, when the forward kept its layer outputs (acts) -- a second tile launch with one item
     // per tile (one CTA per SM) after the input-gradient launch of the other decoders; it adds its share of the ray gradients.
-    const bool wg_tc = n_w == 1 && wdec[0] == 3 && bw->acts != nullptr && use_tile_kernels(K.S) && g_wgrad_tc && (tail == nullptr || tail->px.world <= 1);
+    const bool wg_tc = n_w == 1 && wdec[0] == 3 && bw->acts != nullptr && tile && g_wgrad_tc && !sharded;
     if (T.n_dec > 0) {
       if (n_w == 0 && want_pose) T.bw.pose_dirs = bw->pose_dirs;   // the tensor-core launch is the last writer of the ray gradients
-      if (use_tile_kernels(T.S)) {
+      if (tile) {
         TileWs w;
         if (!tile_ws_plan(bw->split_workspace, bw->split_workspace_bytes, in->n_rays, T.S, T.n_dec, true, &w)) {
           set_error("split_workspace missing or smaller than nsb_split_workspace_bytes(%d, %d)", in->n_rays, T.S); return NSB_ERR_ARG; }

@@ -74,20 +74,35 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t da, uint64_t 
                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
-// D[128 x N] (+)= A[128 x kcount*8] * B[N x kcount*8]^T with the 3xTF32 split.  A/B tiles have widths KA/KB floats and
+// One lane of a CONVERGED warp (the MMA issue path runs in all lanes of warp 0: operands stay warp-uniform -> uniform registers, no per-MMA
+// ELECT / R2UR.BROADCAST waterfall as when a single divergent thread issues; see nsb_tile.cuh).
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.b32 %0, 1, 0, q;\n\t}" : "=r"(p) :: "memory");
+  return p;
+}
+// D[128 x N] (+)= A[128 x kcount*8] * B[N x kcount*8]^T with the 3xTF32 split.  Called by all lanes of warp 0.  A/B tiles have widths KA/KB floats and
 // the product starts at column ka0 / kb0 (multiples of 8).  `acc` is the running accumulate flag of this D.
 __device__ __forceinline__ void mma_3x(uint32_t d_tmem, const float* a_hi, const float* a_lo, int KA, int ka0,
                                        const float* b_hi, const float* b_lo, int KB, int kb0, int kcount, int N, uint32_t& acc) {
   const uint32_t idesc = make_idesc(TM, N);
   const uint32_t sboA = (uint32_t)(KA >> 2) * 128u, sboB = (uint32_t)(KB >> 2) * 128u;
-  for (int ks = 0; ks < kcount; ks++) {
-    const int oa = ((ka0 >> 2) + 2 * ks) * 32, ob = ((kb0 >> 2) + 2 * ks) * 32;
-    const uint64_t ah = make_desc(a_hi + oa, 128u, sboA), al = make_desc(a_lo + oa, 128u, sboA);
-    const uint64_t bh = make_desc(b_hi + ob, 128u, sboB), bl = make_desc(b_lo + ob, 128u, sboB);
-    mma_tf32(d_tmem, al, bh, idesc, acc); acc = 1u;
-    mma_tf32(d_tmem, ah, bl, idesc, 1u);
-    mma_tf32(d_tmem, ah, bh, idesc, 1u);
+  const uint64_t ah0 = make_desc(a_hi + (ka0 >> 2) * 32, 128u, sboA), al0 = make_desc(a_lo + (ka0 >> 2) * 32, 128u, sboA);
+  const uint64_t bh0 = make_desc(b_hi + (kb0 >> 2) * 32, 128u, sboB), bl0 = make_desc(b_lo + (kb0 >> 2) * 32, 128u, sboB);
+  if (elect_one()) {
+    for (int ks = 0; ks < kcount; ks++) {                      // one k-step of 8 floats = two core matrices = +16 in the 16-byte-granular address field
+      const uint64_t o = 16u * (uint64_t)ks;
+      mma_tf32(d_tmem, al0 + o, bh0 + o, idesc, ks == 0 ? acc : 1u);
+      mma_tf32(d_tmem, ah0 + o, bl0 + o, idesc, 1u);
+      mma_tf32(d_tmem, ah0 + o, bh0 + o, idesc, 1u);
+    }
   }
+  __syncwarp();
+  acc = 1u;
+}
+__device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
+  if (elect_one()) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  __syncwarp();
 }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -250,7 +265,7 @@ __device__ __forceinline__ void tile_forward(const KParams& P, const TcSmem& t, 
                                              uint32_t* __restrict__ gmask /* global [5] slot of this point+decoder, or nullptr */,
                                              int next_lv /* decoder whose weights to prefetch once this one's regions are free, or -1 */) {
   const int row = threadIdx.x & (TM - 1), cg = threadIdx.x >> 7, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool t0 = threadIdx.x == 0;
+  const bool t0 = threadIdx.x == 0, w0 = threadIdx.x < 32;
   const uint32_t my = ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kCW * cg);      // TMEM lane quadrant + first column of this thread
   const uint32_t d1 = tmem + my, d3 = tmem + 32u + my, d2 = tmem + 64u + my;
   const float* hdr = t.hdr + pp.hb * kHdrFloats;
@@ -269,14 +284,15 @@ __device__ __forceinline__ void tile_forward(const KParams& P, const TcSmem& t, 
   if (d.xyz) {
     publish_operands();
     for (int h = 0; h < (d.cd >> 5); h++) {
-      if (t0) {
+      if (w0) {
         if (h > 0) { mbar_wait(t.bars + M_FC, (pp.par >> M_FC) & 1u);          // chunk 0 consumed: reload the region with chunk 1
-                     tma_load(t, W_F, t.wF, P.in.packed[lv] + op_fwd_offset(lv) + kHdrFloats + kFcChunk, kFcChunk); }
+                     if (t0) tma_load(t, W_F, t.wF, P.in.packed[lv] + op_fwd_offset(lv) + kHdrFloats + kFcChunk, kFcChunk);
+                     __syncwarp(); }
         mbar_wait(t.bars + W_F, (pp.par >> W_F) & 1u);
         tc_fence_after();
         uint32_t acc = h > 0 ? 1u : 0u;
         mma_3x(tmem + 64u, c_hi, c_lo, d.cd, 32 * h, t.wF, t.wF + 160 * 32, 32, 0, 4, 160, acc);
-        mma_commit(t.bars + M_FC);
+        mma_commit_elect(t.bars + M_FC);
       }
       pp.par ^= 1u << W_F;
       if (h > 0) pp.par ^= 1u << M_FC;
@@ -302,13 +318,13 @@ __device__ __forceinline__ void tile_forward(const KParams& P, const TcSmem& t, 
     }
     publish_operands();
     const int slot = blk & 1;
-    if (t0) {
+    if (w0) {
       mbar_wait(t.bars + W_L0 + slot, (pp.par >> (W_L0 + slot)) & 1u);
       tc_fence_after();
       uint32_t acc = blk > 0 ? 1u : 0u;
       const float* w = t.wL + slot * kL0Chunk;
       mma_3x(tmem, e_hi, e_lo, 32, 0, w, w + 64 * 32, 32, 0, 4, 64, acc);
-      mma_commit(t.bars + M_L0 + slot);
+      mma_commit_elect(t.bars + M_L0 + slot);
     }
     pp.par ^= 1u << (W_L0 + slot);
     __syncwarp();
@@ -342,13 +358,13 @@ __device__ __forceinline__ void tile_forward(const KParams& P, const TcSmem& t, 
 #pragma unroll
     for (int k = 0; k < kKQ; k++) put4(h_hi, h_lo, row, kKQ * cg + k, 32, make_float4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]));
     publish_operands();                                      // (also orders this layer's TMEM reads before the next MMAs)
-    if (t0) {
+    if (w0) {
       if (i == 0) mbar_wait(t.bars + W_H, (pp.par >> W_H) & 1u);
       tc_fence_after();
       const float* w = t.wH + i * kHChunk;                   // hidden weights of layer i+1
       uint32_t acc = (i + 1 == 3) ? 1u : 0u;                 // layer 3 accumulates onto E * W3E^T
       mma_3x((i + 1 == 3) ? tmem + 32u : tmem, h_hi, h_lo, 32, 0, w, w + 32 * 32, 32, 0, 4, 32, acc);
-      mma_commit(t.bars + M_H);
+      mma_commit_elect(t.bars + M_H);
     }
     if (i == 0) pp.par ^= 1u << W_H;
     __syncwarp();
@@ -395,7 +411,7 @@ __device__ __forceinline__ void tile_backward(const KParams& P, const TcSmem& t,
                                               uint32_t tmem, Pipe& pp, const float (&g_out)[4], const uint32_t* __restrict__ gmask,
                                               int next_lv) {
   const int row = threadIdx.x & (TM - 1), cg = threadIdx.x >> 7, warp = threadIdx.x >> 5;
-  const bool t0 = threadIdx.x == 0;
+  const bool t0 = threadIdx.x == 0, w0 = threadIdx.x < 32;
   const float* hdr = t.hdr + pp.hb * kHdrFloats;
   __syncthreads();                                          // previous decoder's scatter (reads of x) is done
   NSB_PH(20);
@@ -432,14 +448,14 @@ __device__ __forceinline__ void tile_backward(const KParams& P, const TcSmem& t,
                                                              (m >> (4 * k + 2)) & 1u ? g[4 * k + 2] : 0.0f, (m >> (4 * k + 3)) & 1u ? g[4 * k + 3] : 0.0f));
     }
     publish_operands();
-    if (t0) {   // DC += G * Wc_i (dL/dc through fc_c) ; D1 = DU * W_i[:, hidden] (g_i) ; DF += DU * W_i[:, first] (i = 3, 0)
+    if (w0) {   // DC += G * Wc_i (dL/dc through fc_c) ; D1 = DU * W_i[:, hidden] (g_i) ; DF += DU * W_i[:, first] (i = 3, 0)
       mbar_wait(t.bars + W_S0 + s, (pp.par >> (W_S0 + s)) & 1u);
       tc_fence_after();
       const float* w = t.wS + s * kBwdStageFloats;
       if (d.xyz) { mma_3x(dcc, g_hi, g_lo, 32, 0, w, w + d.cd * 32, 32, 0, 4, d.cd, acc_dc); w += 2 * d.cd * 32; }
       if (i >= 1) { uint32_t a1 = 0; mma_3x(tmem, du_hi, du_lo, 32, 0, w, w + 32 * 32, 32, 0, 4, 32, a1); w += kHChunk; }
       if (i == 3 || i == 0) mma_3x(dfc, du_hi, du_lo, 32, 0, w, w + d.firstp * 32, 32, 0, 4, d.firstp, acc_df);
-      mma_commit(t.bars + M_B);
+      mma_commit_elect(t.bars + M_B);
     }
     pp.par ^= 1u << (W_S0 + s);
     __syncwarp();

@@ -161,11 +161,7 @@ struct Issuer {
 // elected lane issues the instruction.  (Issued from a single divergent thread, every MMA was wrapped in an ELECT / 5 x R2UR.BROADCAST /
 // branch "waterfall": ~1 k cycles per 32 x 32 layer of twelve MMAs, 40 % of both kernels.)  Only the TMA producer bookkeeping (Loader) is
 // lane 0's private, divergent state.
-__device__ __forceinline__ uint32_t elect_one() {
-  uint32_t p;
-  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.b32 %0, 1, 0, q;\n\t}" : "=r"(p) :: "memory");
-  return p;
-}
+using tc::elect_one;
 // wait for the operands of group `g` on A_ready[b]; while they are not there, lane 0 keeps the ring full
 __device__ __forceinline__ void issuer_wait_operands(Issuer& I, const TileSmem& t, int b, uint32_t parity) {
   uint64_t* bar = t.bars + B_AREADY + b;
@@ -346,7 +342,8 @@ __device__ __forceinline__ void epi_forward(const KParams& P, const TileSmem& t,
   const float* hdr = t.hdr + hb * kHdrFloats;
   if (xyz) {
     for (int half = 0; half < cd / 32; half++) {
-      if (n >= 2) { wait_group(t, n - 2); if (threadIdx.x == 0) loader_top_up(I.L, t, I.issued); }
+      if (n >= 2) wait_group(t, n - 2);
+      if (threadIdx.x == 0) loader_top_up(I.L, t, I.issued);     // request whatever fits the ring before the long gather
       gather_tile(P.in.grid[half == 0 ? lv : 1], t.a[n & 1], G.xn, warp, lane);
       NSB_PH(1);
       publish(t, n & 1); n++;
@@ -355,7 +352,8 @@ __device__ __forceinline__ void epi_forward(const KParams& P, const TileSmem& t,
     }
     mbar_wait_b(t.bars + B_HDR + hb, hdr_parity);
     for (int blk = 0; blk < 3; blk++) {
-      if (n >= 2) { wait_group(t, n - 2); if (threadIdx.x == 0) loader_top_up(I.L, t, I.issued); }
+      if (n >= 2) wait_group(t, n - 2);
+      if (threadIdx.x == 0) loader_top_up(I.L, t, I.issued);
       NSB_PH(6);
       embed_tile(t.a[n & 1], hdr + 464, G.pf, row, cg, blk);
       NSB_PH(3);

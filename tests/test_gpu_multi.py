@@ -57,7 +57,8 @@ def _worker(rank, world, port, q):
         if g is not None:
             sh.packed.zero_(); g.replay(); torch.cuda.synchronize()
             out["track_" + name + "_graph"] = (float((sh.packed - want).abs().max() / want.abs().max()), True)
-        assert torch.equal(ctx.d_rays_o, ctx.d_rays_o) and bool(torch.isfinite(ctx.d_rays_d).all())
+        # the shard's ray gradients are the full batch's rows [lo, hi) (the seeds use the batch-global median, so this checks the exchange too)
+        out["track_" + name + "_d_rays"] = (float((ctx.d_rays_d - full.d_rays_d[lo:hi]).abs().max() / full.d_rays_d.abs().max()), True)
         del g
     # ---- mapping: frustum-like masks, packed block, ONE all-reduce
     keys = ("grid_middle", "grid_fine", "grid_color")
@@ -81,6 +82,11 @@ def _worker(rank, world, port, q):
     scale = wantp.abs().max()
     out["map_packed"] = (float((gotp - wantp).abs().max() / scale), True)
     out["map_loss"] = (abs(float(gotp[0] - wantp[0])) / abs(float(wantp[0])), True)
+    ms1 = ShardedMappingIteration(mctx)
+    ms1.prepare(c, dec, dirs[lo:hi].to(dev), offs, global_gt_depth=gd.to(dev))      # depth maxima from the full batch: ONE collective per iteration
+    assert ms1.collectives_per_step == 1
+    got1 = ms1.enqueue().clone()
+    out["map_packed_one_collective"] = (float((got1 - wantp).abs().max() / scale), True)
     torch.cuda.synchronize()
     if rank == 0:
         q.put(out)
