@@ -334,6 +334,7 @@ __device__ __forceinline__ void fwd_sample_sort(const KParams& P, const Smem& sm
         __syncthreads();
         m = -INFINITY;
         for (int w = 0; w < (int)(blockDim.x >> 5); w++) m = fmaxf(m, s_max[w]);
+        if (P.fs.px.world > 1) { __shared__ uint32_t s_seq; m = peer_max_all_ctas(P.fs.px, m, &s_seq); }      // sharded batch: MAX over the ranks' shards
         gtmax = m; gtmax12 = __fmul_rn(m, 1.2f);
       }
     }
@@ -346,12 +347,33 @@ __device__ __forceinline__ void fwd_sample_sort(const KParams& P, const Smem& sm
       zu[lp] = sample_z(rs, i, P.in.n_samples, P.in.t_uniform, P.in.t_surface, gtmax);
     }
     __syncthreads();
-    for (int lp = threadIdx.x; lp < b.Pb; lp += blockDim.x) {    // stable rank sort == torch.sort (Renderer.py:168-170)
+    // torch.sort of [uniform | surface] (Renderer.py:168-170): both lists are normally non-decreasing -> merge by ranks (own index + binary-search
+    // count in the other list); a ray whose lists are not sorted (far < near, NaN) takes the general stable rank sort (same values either way)
+    __shared__ int s_unsorted[kMaxRaysPerBlock];
+    for (int r = threadIdx.x; r < b.nr; r += blockDim.x) s_unsorted[r] = 0;
+    __syncthreads();
+    const int nu = P.in.n_samples < P.S ? P.in.n_samples : P.S;
+    for (int lp = threadIdx.x; lp < b.Pb; lp += blockDim.x) {
+      const int ray = lp / P.S, i = lp - ray * P.S;
+      if (i != 0 && i != nu) { if (!(zu[lp - 1] <= zu[lp])) s_unsorted[ray] = 1; }
+      else if (zu[lp] != zu[lp]) s_unsorted[ray] = 1;
+    }
+    __syncthreads();
+    for (int lp = threadIdx.x; lp < b.Pb; lp += blockDim.x) {
       const int ray = lp / P.S, i = lp - ray * P.S;
       const double zi = zu[lp];
       const double* zr = zu + ray * P.S;
-      int rank = 0;
-      for (int j = 0; j < P.S; j++) { const double zj = zr[j]; rank += (z_less(zj, zi) || (!z_less(zi, zj) && j < i)) ? 1 : 0; }
+      int rank;
+      if (!s_unsorted[ray]) {
+        const bool uni = i < nu;
+        const double* other = uni ? zr + nu : zr;
+        int lo = 0, hi = uni ? P.S - nu : nu;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; const double zm = other[mid]; if (uni ? (zm < zi) : (zm <= zi)) lo = mid + 1; else hi = mid; }
+        rank = (uni ? i : i - nu) + lo;
+      } else {
+        rank = 0;
+        for (int j = 0; j < P.S; j++) { const double zj = zr[j]; rank += (z_less(zj, zi) || (!z_less(zi, zj) && j < i)) ? 1 : 0; }
+      }
       sm.zs[ray * P.S + rank] = zi;
     }
   }
@@ -408,9 +430,10 @@ __device__ __forceinline__ void fused_seeds_tail(const KParams& P, int n_partici
   __shared__ int s_seeds_last;
   if (!grid_last_arrival(P.fs.counter, n_participants, &s_seeds_last)) return;
   if (P.fs.kind == 1) {
-    PeerX px; px.rank = 0; px.world = 0; px.counter = nullptr; px.max_n = 0;
+    // (sharded batch: the residual pool of the median is exchanged inside; then every CTA of this grid is past the depth-max exchange)
     tracking_seeds_body(P.fo.depth, P.fo.var, P.fo.rgb, P.in.gt_depth, static_cast<const double*>(P.fs.gt_rgb), P.in.n_rays, P.fs.w_color,
-                        P.fs.handle_dynamic, P.fs.use_color, nullptr, 0, P.fs.g_depth, P.fs.g_rgb, P.fs.loss, P.fs.res, px, scratch);
+                        P.fs.handle_dynamic, P.fs.use_color, nullptr, 0, P.fs.g_depth, P.fs.g_rgb, P.fs.loss, P.fs.res, P.fs.px, scratch);
+    if (P.fs.px.world > 1 && P.in.depth_max == nullptr && threadIdx.x == 0) peer_advance(P.fs.px, 0);
   } else {
     mapping_seeds_body(P.fo.depth, P.fo.rgb, P.fs.gt_depth_loss, static_cast<const float*>(P.fs.gt_rgb), P.in.n_rays, P.fs.w_color, P.fs.use_color,
                        P.fs.g_depth, P.fs.g_rgb, P.fs.loss, scratch);
@@ -559,6 +582,17 @@ __global__ void __launch_bounds__(tc::kThreads, 1) render_fwd_tc_kernel(const __
 // ------------------------------------------------------------------------------------------------
 // backward kernel
 // ------------------------------------------------------------------------------------------------
+// sharded tracking batch: SUM over ranks of [loss | d c2w] by the (last) CTA that just reduced the pose gradient -- identical bits on every rank
+__device__ __forceinline__ void pose_tail_peers(const KParams& P) {
+  if (P.tail.px.world <= 1) return;
+  __shared__ double tot[13];
+  __shared__ uint32_t s_seq2;
+  __syncthreads();
+  if (threadIdx.x == 0) tot[0] = P.tail.loss != nullptr ? P.tail.loss[0] : 0.0;
+  if (threadIdx.x < 12) tot[1 + threadIdx.x] = P.bw.d_c2w[threadIdx.x];
+  __syncthreads();
+  peer_sum13(P.tail.px, tot, 13, P.tail.out13, &s_seq2);
+}
 __device__ __forceinline__ void chunk_backward(const KParams& P, const Smem& sm, float* act, int chunk, int Pb,
                                                const LaneId& L, uint32_t parity, const float* gC /*[R][3] smem*/,
                                                const int lv, const DecRT& d) {
@@ -869,12 +903,12 @@ __global__ void __launch_bounds__(tc::kThreads, 1) render_bwd_tc_kernel(const __
       if (P.bw.d_rays_o != nullptr) P.bw.d_rays_o[3 * (r0 + r) + a] = (float)so;
       if (P.bw.d_rays_d != nullptr) P.bw.d_rays_d[3 * (r0 + r) + a] = (float)sd;
     }
-    fused_pose_grad(P, gridDim.x / nsplit, reinterpret_cast<double*>(smem_raw));     // one arrival per ray group (the tiles are dead)
+    if (fused_pose_grad(P, gridDim.x / nsplit, reinterpret_cast<double*>(smem_raw))) pose_tail_peers(P);     // one arrival per ray group (the tiles are dead)
     return;
   }
   bwd_ray_reduce(P, sm, r0, nr);
   __syncthreads();
-  fused_pose_grad(P, gridDim.x, reinterpret_cast<double*>(smem_raw));
+  if (fused_pose_grad(P, gridDim.x, reinterpret_cast<double*>(smem_raw))) pose_tail_peers(P);
   NSB_PH(30);
 }
 
@@ -1052,10 +1086,10 @@ static size_t tile_wg_smem_bytes() { return tl::kWgBytes + tile_smem_bytes(true)
 // tile kernels, except that single-GPU batches of up to g_small_rays rays go to the ray-group kernels (512 threads on one tile at a time: shorter
 // per-tile chains; option "small_rays", 0 = never).  Forward and backward of an iteration see the same (S, n_rays) and so pick the same family
 // (the saved ReLU bits are laid out per family).
-static int g_small_rays = 0;
+static int g_small_rays = 256;
 static bool use_tile_kernels(int S, int n_rays, bool sharded) {
   if (!(g_mlp_backend == 0 || g_mlp_backend == 3) || S < tl::kMinSamples || S > NSB_MAX_SAMPLES) return false;
-  if (g_mlp_backend == 0 && !sharded && n_rays <= g_small_rays && S <= kMaxPtsTc) return false;
+  if (g_mlp_backend == 0 && n_rays <= g_small_rays && S <= kMaxPtsTc) return false;
   return true;
 }
 static bool use_group_kernels(int S, int n_rays, bool sharded) {
@@ -1105,8 +1139,8 @@ int nsb::render_forward_fused(const nsb_render_inputs* in, const nsb_forward_out
   if (K.S > NSB_MAX_SAMPLES) { set_error("n_samples+n_surface = %d exceeds %d", K.S, NSB_MAX_SAMPLES); return NSB_ERR_UNSUPPORTED; }
   if (K.has_gt && in->n_surface > 0 && !in->t_surface) { set_error("t_surface NULL"); return NSB_ERR_ARG; }
   if ((rc = set_attrs())) return rc;
-  if (K.fs.px.world > 1 && !(tile && in->depth_max == nullptr && in->gt_depth != nullptr)) {
-    set_error("in-kernel exchanges of a sharded forward need the tile kernels and <= %d rays per rank", NSB_INLINE_MAX_RAYS); return NSB_ERR_UNSUPPORTED; }
+  if (K.fs.px.world > 1 && !((tile || group) && in->depth_max == nullptr && in->gt_depth != nullptr)) {
+    set_error("in-kernel exchanges of a sharded forward need a tensor-core back-end and <= %d rays per rank", NSB_INLINE_MAX_RAYS); return NSB_ERR_UNSUPPORTED; }
   if (tile) {                                             // tile kernels: item = (128-point tile, decoder), two CTAs per SM
     if (!out->z_vals || !out->raw) { set_error("the tensor-core forward needs z_vals and raw outputs"); return NSB_ERR_ARG; }
     TileWs w;
@@ -1238,7 +1272,10 @@ int nsb::render_backward_tail(const nsb_render_inputs* in, const nsb_backward_ar
         render_bwd_tile_kernel<<<(unsigned)grid_t, tl::kThreads, tile_smem_bytes(true), st>>>(T);
         if ((rc = check_cuda(cudaGetLastError(), "render_bwd_tile_kernel launch"))) return rc;
       } else {
-      if (tail != nullptr && tail->px.world > 1) { set_error("sharded backward tail needs the tile kernels"); return NSB_ERR_UNSUPPORTED; }
+      if (tail != nullptr && tail->px.world > 1) {
+        if (n_w != 0 || T.bw.pose_dirs == nullptr) { set_error("sharded backward tail needs pose_dirs and no decoder weight gradients"); return NSB_ERR_ARG; }
+        T.tail = *tail;
+      }
       choose_config(in->n_rays, T.S, kRowsBwd, true, T.wbytes, 8, &T, &warps, &smem, kMaxPtsTc);
       plan_split(&T, T.n_dec, bw->split_workspace, bw->split_workspace_bytes);
       const int grid_tc = ((in->n_rays + T.rays_per_block - 1) / T.rays_per_block) * T.split;
