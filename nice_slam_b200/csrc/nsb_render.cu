@@ -1081,7 +1081,7 @@ static bool plan_split(KParams* K, int nd, void* ws, size_t ws_bytes) {
 }
 
 static size_t tile_smem_bytes(bool bwd) { return tl::common_bytes(bwd) + (bwd ? sizeof(tl::BwdExtra) : 0); }
-static size_t tile_wg_smem_bytes() { return tl::kWgBytes + tile_smem_bytes(true) + 1024; }
+static size_t tile_wg_smem_bytes() { return tl::kWgBytes + ((tile_smem_bytes(true) + 1023) & ~size_t(1023)) + 1024; }
 // Which tensor-core kernel family serves a launch.  mlp_backend 3: always the tile kernels; 2: always the round-1 ray-group kernels; 0 (auto): the
 // tile kernels, except that single-GPU batches of up to g_small_rays rays go to the ray-group kernels (512 threads on one tile at a time: shorter
 // per-tile chains; option "small_rays", 0 = never).  Forward and backward of an iteration see the same (S, n_rays) and so pick the same family

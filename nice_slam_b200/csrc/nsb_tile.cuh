@@ -194,33 +194,20 @@ __device__ __forceinline__ void issuer_group_done(const TileSmem& t, int bar) {
 // 14-bit field never carries).
 // ... followed, in the same elected lane, by the commits that release the unit's ring slot (`empty`) and, for the last unit of a group, signal the
 // group's completion (`done`, or nullptr)
-// shared-memory descriptor of a SWIZZLE_128B_BASE32B tile (layout type 1): 128-byte rows, the 32-byte chunk c of row p stored at c ^ (p & 3)
-__device__ __forceinline__ uint64_t make_desc_mn(const float* smem, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_u32(smem) >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)1 << 61;
-  return d;
-}
-// A1: the A tile is a row-major [128][32] tile in that layout read K-major (SBO = 512; one k-step of 8 floats = +32 bytes) -- the weight-gradient
-// kernel shares its chain operands with the point-contracting MMAs (profiles/probe_mn32c_r02.log, combo 12)
-template <int KSTEPS, bool A1 = false>
+template <int KSTEPS>
 __device__ __forceinline__ void mma_unit(Issuer& I, const TileSmem& t, uint32_t d_tmem, const float* a, int ka0, const float* b, int N, int KB, int kb0, uint32_t& acc,
                                          uint64_t* done = nullptr) {
   const uint32_t idesc = tc::make_idesc(TM, N);
-  const uint64_t ah = A1 ? make_desc_mn(a + ka0, 0u, 512u) : tc::make_desc(a + (ka0 >> 2) * 32, 128u, 8u * 128u);
+  const uint64_t ah = tc::make_desc(a + (ka0 >> 2) * 32, 128u, 8u * 128u);
   const uint64_t bh = tc::make_desc(b + (kb0 >> 2) * 32, 128u, (uint32_t)(KB >> 2) * 128u);
   const uint64_t al = ah + (uint64_t)((TM * 32 * 4) >> 4);
   const uint64_t bl = bh + (uint64_t)((N * KB * 4) >> 4);
-  constexpr uint32_t ka = A1 ? 2u : 16u;                        // A address advance per k-step, in 16-byte units
   if (elect_one()) {
 #pragma unroll
     for (int ks = 0; ks < KSTEPS; ks++) {
-      tc::mma_tf32(d_tmem, al + ka * ks, bh + 16u * ks, idesc, ks == 0 ? acc : 1u);
-      tc::mma_tf32(d_tmem, ah + ka * ks, bl + 16u * ks, idesc, 1u);
-      tc::mma_tf32(d_tmem, ah + ka * ks, bh + 16u * ks, idesc, 1u);
+      tc::mma_tf32(d_tmem, al + 16u * ks, bh + 16u * ks, idesc, ks == 0 ? acc : 1u);
+      tc::mma_tf32(d_tmem, ah + 16u * ks, bl + 16u * ks, idesc, 1u);
+      tc::mma_tf32(d_tmem, ah + 16u * ks, bh + 16u * ks, idesc, 1u);
     }
     tc::mma_commit(t.bars + B_EMPTY + (I.issued & (kSlots - 1)));
     if (done != nullptr) tc::mma_commit(done);
@@ -249,7 +236,8 @@ struct GatherPass {
   float w[8];
   int src_lane;
 };
-__device__ __forceinline__ void gather_issue(const nsb_grid& g, bool fast, const float xn[3], int it, int lane, GatherPass& gp) {
+template <bool FAST>
+__device__ __forceinline__ void gather_issue(const nsb_grid& g, const float xn[3], int it, int lane, GatherPass& gp) {
   const int q = lane & 7;
   gp.src_lane = it * 4 + (lane >> 3);
   float x[3];
@@ -260,7 +248,7 @@ __device__ __forceinline__ void gather_issue(const nsb_grid& g, bool fast, const
   const long long oy[2] = {(long long)t.i0[1] * g.stride_h, (long long)min(t.i0[1] + 1, g.H - 1) * g.stride_h};
   const long long oz[2] = {(long long)t.i0[2] * g.stride_d, (long long)min(t.i0[2] + 1, g.D - 1) * g.stride_d};
 #pragma unroll
-  for (int k = 0; k < 8; k++) gp.v[k] = grid_load4(g, oz[k >> 2] + oy[(k >> 1) & 1] + ox[k & 1], 4 * q, fast);
+  for (int k = 0; k < 8; k++) gp.v[k] = grid_load4(g, oz[k >> 2] + oy[(k >> 1) & 1] + ox[k & 1], 4 * q, FAST);
   const float wxy[4] = {__fmul_rn(t.w0[0], t.w0[1]), __fmul_rn(t.w1[0], t.w0[1]), __fmul_rn(t.w0[0], t.w1[1]), __fmul_rn(t.w1[0], t.w1[1])};
 #pragma unroll
   for (int k = 0; k < 8; k++) gp.w[k] = __fmul_rn(wxy[k & 3], (k & 4) ? t.w1[2] : t.w0[2]);      // == tri_weight(t, k)
@@ -274,19 +262,34 @@ __device__ __forceinline__ void gather_consume(float* c_hi, float* c_lo, int qd,
   }
   tc::put4(c_hi, c_lo, qd * 32 + gp.src_lane, lane & 7, 32, acc);
 }
-__device__ __forceinline__ void gather_tile(const nsb_grid& g, float* c_hi, const float xn[3], int warp, int lane) {
+// (the strided NCDHW form -- four scalar loads with 64-bit strides per corner -- is a separate, out-of-line copy: inlined next to the channels-last
+// form at every unrolled corner it made up a third of the forward kernel's 19 k instructions, and instruction fetch shows up in the stall samples)
+template <bool FAST>
+__device__ __forceinline__ void gather_tile_t(const nsb_grid& g, float* c_hi, const float xn[3], int warp, int lane) {
   float* c_lo = c_hi + TM * 32;
-  const bool fast = grid_fast(g);
   const int qd = warp & 3, it0 = (warp >> 2) * 4;
-  GatherPass A, B;
-  gather_issue(g, fast, xn, it0, lane, A);
-  gather_issue(g, fast, xn, it0 + 1, lane, B);
-  gather_consume(c_hi, c_lo, qd, lane, A);
-  gather_issue(g, fast, xn, it0 + 2, lane, A);
-  gather_consume(c_hi, c_lo, qd, lane, B);
-  gather_issue(g, fast, xn, it0 + 3, lane, B);
-  gather_consume(c_hi, c_lo, qd, lane, A);
-  gather_consume(c_hi, c_lo, qd, lane, B);
+  if (FAST) {
+    GatherPass A, B;
+    gather_issue<true>(g, xn, it0, lane, A);
+    gather_issue<true>(g, xn, it0 + 1, lane, B);
+    gather_consume(c_hi, c_lo, qd, lane, A);
+    gather_issue<true>(g, xn, it0 + 2, lane, A);
+    gather_consume(c_hi, c_lo, qd, lane, B);
+    gather_issue<true>(g, xn, it0 + 3, lane, B);
+    gather_consume(c_hi, c_lo, qd, lane, A);
+    gather_consume(c_hi, c_lo, qd, lane, B);
+  } else {
+#pragma unroll 1
+    for (int it = it0; it < it0 + 4; it++) { GatherPass A; gather_issue<false>(g, xn, it, lane, A); gather_consume(c_hi, c_lo, qd, lane, A); }
+  }
+}
+static __device__ __noinline__ void gather_tile_strided(const nsb_grid& g, float* c_hi, float x0, float x1, float x2, int warp, int lane) {
+  const float xn[3] = {x0, x1, x2};
+  gather_tile_t<false>(g, c_hi, xn, warp, lane);
+}
+__device__ __forceinline__ void gather_tile(const nsb_grid& g, float* c_hi, const float xn[3], int warp, int lane) {
+  if (grid_fast(g)) gather_tile_t<true>(g, c_hi, xn, warp, lane);
+  else gather_tile_strided(g, c_hi, xn[0], xn[1], xn[2], warp, lane);
 }
 // this thread's 16 features of embedding block `blk` of its point -> [128 x 32] tile
 __device__ __forceinline__ void embed_tile(float* e_hi, const float* B, const float pf[3], int row, int cg, int blk) {
@@ -442,13 +445,9 @@ __device__ __forceinline__ void epi_forward(const KParams& P, const TileSmem& t,
 // forward's `acts`, C and the embedding blocks are recomputed.  One MMA group = 16 k-steps x 3 (3xTF32) with N = 32 into TMEM columns [192, 224);
 // rows 0..31 (DU part) or 32..63 (G part) are then reduced into the packed gradient image with 16-byte vector reductions.
 constexpr int kMnTile = TM * 32;                               // floats of one tile (16 KB)
-constexpr size_t kWgBytes = (size_t)6 * kMnTile * 4;           // three B tiles hi|lo (96 KB): two for the rotating inputs, one for the grid features
-constexpr uint32_t kWgCol = 192u;                              // TMEM columns [192, 224) and [224, 256): accumulators of the two groups in flight
-// The chain operands of the weight-gradient kernel live in the SAME layout (the K-major read of a SWIZZLE_128B_BASE32B tile works with SBO = 512,
-// probe_mn32c combo 12): DU in t.a[0], G in t.a[1] are written once and serve both the layer's chain MMAs (A operand, K = features) and the
-// weight-gradient groups (A operand MN-major, K = points, M atoms 32 KB apart).
-struct WgPending { int slot, part, pitch, n_rows; float* dst; bool t3, valid; };
-struct WgSmem { float* bx[2]; float* bc; uint64_t* bar; uint32_t phase[2]; int next; float* dpk; WgPending pend; };
+constexpr size_t kWgBytes = (size_t)6 * kMnTile * 4;           // A: DU hi|lo, G hi|lo (64 KB)  B: one tile hi|lo (32 KB)
+constexpr uint32_t kWgCol = 192u;                              // TMEM columns [192, 224) of the weight-gradient accumulator
+struct WgSmem { float* du; float* g; float* b; uint64_t* bar; uint32_t phase; float* dpk; };
 __device__ __forceinline__ void split4(const float4 v, float4& h, float4& l) {
   h = make_float4(tc::to_tf32(v.x), tc::to_tf32(v.y), tc::to_tf32(v.z), tc::to_tf32(v.w));
   l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
@@ -486,7 +485,7 @@ __device__ __forceinline__ void gather_tile_mn(const nsb_grid& g, float* c_hi, c
 #pragma unroll 1
   for (int it = it0; it < it0 + 4; it++) {
     GatherPass A;
-    gather_issue(g, fast, xn, it, lane, A);
+    if (fast) gather_issue<true>(g, xn, it, lane, A); else gather_issue<false>(g, xn, it, lane, A);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -499,57 +498,54 @@ __device__ __forceinline__ void gather_tile_mn(const nsb_grid& g, float* c_hi, c
     *reinterpret_cast<float4*>(c_hi + o) = xh; *reinterpret_cast<float4*>(c_lo + o) = xl;
   }
 }
-// warp 0, converged: D_w[slot][128 x 32] = sum over the 128 points of A[p][m] B[p][n]; A = [a_tile | tile 32 KB further | . | .]; commits to bar[slot]
-__device__ __forceinline__ void issue_wg_group(const WgSmem& w, uint32_t tmem, int slot, const float* a_tile, const float* b_tile) {
+__device__ __forceinline__ uint64_t make_desc_mn(const float* smem, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_u32(smem) >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                                      // SWIZZLE_128B_BASE32B
+  return d;
+}
+// warp 0, converged: D_w[128 x 32] = [DU | G | . | .]^T-contraction with the B tile over the 128 points; commits to w.bar
+__device__ __forceinline__ void issue_wg_group(const WgSmem& w, uint32_t tmem) {
   tc::tc_fence_after();
   const uint32_t idesc = tc::make_idesc(TM, 32) | (1u << 15) | (1u << 16);          // A and B MN-major
-  const uint64_t ah = make_desc_mn(a_tile, 2u * kMnTile * 4u, 512u), al = ah + (uint64_t)((kMnTile * 4) >> 4);
-  const uint64_t bh = make_desc_mn(b_tile, 2u * kMnTile * 4u, 512u), bl = bh + (uint64_t)((kMnTile * 4) >> 4);
-  const uint32_t d = tmem + kWgCol + 32u * (uint32_t)slot;
+  const uint64_t ah = make_desc_mn(w.du, 2u * kMnTile * 4u, 512u), al = ah + (uint64_t)((kMnTile * 4) >> 4);
+  const uint64_t bh = make_desc_mn(w.b, 2u * kMnTile * 4u, 512u), bl = bh + (uint64_t)((kMnTile * 4) >> 4);
   if (elect_one()) {
 #pragma unroll
     for (int ks = 0; ks < TM / 8; ks++) {                       // 8 points per MMA = 1024 bytes of rows
-      tc::mma_tf32(d, al + 64u * ks, bh + 64u * ks, idesc, ks == 0 ? 0u : 1u);
-      tc::mma_tf32(d, ah + 64u * ks, bl + 64u * ks, idesc, 1u);
-      tc::mma_tf32(d, ah + 64u * ks, bh + 64u * ks, idesc, 1u);
+      tc::mma_tf32(tmem + kWgCol, al + 64u * ks, bh + 64u * ks, idesc, ks == 0 ? 0u : 1u);
+      tc::mma_tf32(tmem + kWgCol, ah + 64u * ks, bl + 64u * ks, idesc, 1u);
+      tc::mma_tf32(tmem + kWgCol, ah + 64u * ks, bh + 64u * ks, idesc, 1u);
     }
-    tc::mma_commit(w.bar + slot);
+    tc::mma_commit(w.bar);
   }
+  __syncwarp();
 }
-// retire a group: wait for its MMAs, reduce its useful rows into the packed gradient image.  part 0 = rows of the first A tile (D rows 0..31), part 1 = rows
-// of the second (32..63); dst = packed-image address of element (out 0, in 0), pitch in floats; n_rows <= 32 rows are reduced.
-__device__ __forceinline__ void wg_retire(WgSmem& w, uint32_t tmem) {
-  if (!w.pend.valid) return;
-  const WgPending q = w.pend;
-  mbar_wait_b(w.bar + q.slot, w.phase[q.slot]); w.phase[q.slot] ^= 1u;
+// One group: the B tile (and, the first time in a layer, the A tiles) have been written by all threads.  part 0 = rows of the DU block (D rows 0..31),
+// part 1 = rows of the G block (32..63); dst = packed-image address of element (out 0, in 0), pitch in floats; n_rows <= 32 rows are reduced.
+__device__ __forceinline__ void wg_group(WgSmem& w, uint32_t tmem, int part, float* dst, int pitch, int n_rows, bool transposed3 = false) {
+  fence_proxy_async(); tc::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) issue_wg_group(w, tmem);
+  mbar_wait_b(w.bar, w.phase); w.phase ^= 1u;
   tc::tc_fence_after();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cg = threadIdx.x >> 7;
-  if ((warp & 3) == q.part) {
+  if ((warp & 3) == part) {
     float v[kCW];
-    tmem_ld16(tmem + kWgCol + 32u * (uint32_t)q.slot + ((uint32_t)(q.part * 32) << 16) + (uint32_t)(kCW * cg), v);
-    if (q.t3) {                                                  // dB[a][f] = D[f][a], a < 3 (the B tile held the three coordinates in columns 0..2)
-      if (cg == 0 && lane < q.n_rows) { atomicAdd(q.dst + lane, v[0]); atomicAdd(q.dst + q.pitch + lane, v[1]); atomicAdd(q.dst + 2 * q.pitch + lane, v[2]); }
-    } else if (lane < q.n_rows) {
-      float* d = q.dst + (size_t)lane * q.pitch + kCW * cg;
+    tmem_ld16(tmem + kWgCol + ((uint32_t)(part * 32) << 16) + (uint32_t)(kCW * cg), v);
+    if (transposed3) {                                           // dB[a][f] = D[f][a], a < 3 (the B tile held the three coordinates in columns 0..2)
+      if (cg == 0 && lane < n_rows) { atomicAdd(dst + lane, v[0]); atomicAdd(dst + pitch + lane, v[1]); atomicAdd(dst + 2 * pitch + lane, v[2]); }
+    } else if (lane < n_rows) {
+      float* d = dst + (size_t)lane * pitch + kCW * cg;
 #pragma unroll
       for (int k = 0; k < kKQ; k++) red_add_v4(d + 4 * k, v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
     }
   }
   tc::tc_fence_before();
-  w.pend.valid = false;
 }
-// One group, software-pipelined one deep: the operand tiles have just been written by all threads -> publish, issue into the free accumulator slot,
-// THEN retire the group submitted before (its MMAs ran while this one's operands were being written; its reduction runs under this one's MMAs).
-__device__ __forceinline__ void wg_push(WgSmem& w, uint32_t tmem, const float* a_tile, const float* b_tile, int part, float* dst, int pitch, int n_rows, bool t3 = false) {
-  fence_proxy_async(); tc::tc_fence_before();
-  __syncthreads();
-  const int slot = w.next; w.next ^= 1;
-  if (threadIdx.x < 32) issue_wg_group(w, tmem, slot, a_tile, b_tile);
-  wg_retire(w, tmem);
-  w.pend.slot = slot; w.pend.part = part; w.pend.dst = dst; w.pend.pitch = pitch; w.pend.n_rows = n_rows; w.pend.t3 = t3; w.pend.valid = true;
-}
-// the B tile the NEXT group may write: its previous user (two groups back) was retired by the last wg_push
-__device__ __forceinline__ float* wg_next_b(const WgSmem& w) { return w.bx[w.next]; }
 // column sums of a [32 rows (lanes)][16] register tile: lane l returns the sum of column ((l >> 4) & 1) * 8 + ((l >> 3) & 1) * 4 + ((l >> 2) & 1) * 2 + ((l >> 1) & 1)
 __device__ __forceinline__ float warp_colsum16(const float (&v)[kCW], int lane) {
   float a[8];
@@ -570,28 +566,25 @@ __device__ __forceinline__ int colsum_col(int lane) { return ((lane >> 4) & 1) *
 
 // ---- backward (input gradients): what the issuing thread does after the CTA published layer i's operands (G in a[0], DU in a[1]) ---------------
 // TMEM: D1 = [0,32) (g of the next layer), DC = [32,96) (dL/dc), DF = [96,192) (dL/d first input).
-template <bool WG>
 __device__ __forceinline__ void issue_bwd_layer(Issuer& I, const TileSmem& t, uint32_t tmem, int lv, int i) {
-  const float* gbuf = WG ? t.a[1] : t.a[0];                     // (WG: DU in a[0], G in a[1] -- the order the weight-gradient A operand needs)
-  const float* dubuf = WG ? t.a[0] : t.a[1];
   const bool xyz = lv != 0;
   const int cd = op_cd(lv), nfb = op_firstp(lv) / 32;
   issuer_wait_operands(I, t, 0, I.g & 1u);
   if (xyz) for (int c2 = 0; c2 < cd / 32; c2++) {               // DC += G * Wc_i
     const float* w = issuer_unit(I, t);
     uint32_t acc = i == 4 ? 0u : 1u;
-    mma_unit<4, WG>(I, t, tmem + 32u + 32u * c2, gbuf, 0, w, 32, 32, 0, acc);
+    mma_unit<4>(I, t, tmem + 32u + 32u * c2, t.a[0], 0, w, 32, 32, 0, acc);
   }
   if (i >= 1) {                                                 // D1 = DU * W_i[:, hidden]
     const float* w = issuer_unit(I, t);
     uint32_t acc = 0u;
-    mma_unit<4, WG>(I, t, tmem, dubuf, 0, w, 32, 32, 0, acc);
+    mma_unit<4>(I, t, tmem, t.a[1], 0, w, 32, 32, 0, acc);
   }
   if (i == 3 || i == 0) {                                       // DF += DU * W_i[:, first input]
     for (int fb = 0; fb < nfb; fb++) {
       const float* w = issuer_unit(I, t);
       uint32_t acc = i == 3 ? 0u : 1u;
-      mma_unit<4, WG>(I, t, tmem + 96u + 32u * fb, dubuf, 0, w, 32, 32, 0, acc);
+      mma_unit<4>(I, t, tmem + 96u + 32u * fb, t.a[1], 0, w, 32, 32, 0, acc);
     }
   }
   issuer_group_done(t, B_DONE);
@@ -606,7 +599,7 @@ __device__ __forceinline__ void epi_backward(const KParams& P, const TileSmem& t
   const int row = threadIdx.x & (TM - 1), cg = threadIdx.x >> 7, warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   using DW = Dec<3>;                                             // packed gradient image of the colour decoder (the only WG decoder)
-
+  float creg[kCW];                                               // WG: this thread's 16 grid features of its point
   const bool xyz = lv != 0;
   const int cd = op_cd(lv);
   const float* hdr = t.hdr + hb * kHdrFloats;
@@ -625,21 +618,24 @@ __device__ __forceinline__ void epi_backward(const KParams& P, const TileSmem& t
     g[j] = v;
   }
   if constexpr (WG) {
-    // grid features of this point: the resident B tile of the dWc groups
-    gather_tile_mn(P.in.grid[lv], w->bc, G.xn, warp, lane);
-    // output layer: dWo = g_out^T H_4 (A = g_out in columns 0..3 of the DU tile), dbo = column sums of g_out
+    // grid features of this point -> registers (gathered once through the B tile)
+    gather_tile_mn(P.in.grid[lv], w->b, G.xn, warp, lane);
+    __syncthreads();
+    get_mn16(w->b, row, cg, creg);
+    __syncthreads();
+    // output layer: dWo = g_out^T H_4 (A block 0 = g_out in columns 0..3), dbo = column sums of g_out
     float go[kCW];
 #pragma unroll
     for (int j = 0; j < kCW; j++) go[j] = (cg == 0 && j < 4) ? g_out[j] : 0.0f;
-    put_mn16(t.a[0], row, cg, go);
+    put_mn16(w->du, row, cg, go);
     float h4[kCW];
 #pragma unroll
     for (int k = 0; k < kKQ; k++) {
       const float4 v = acts_row != nullptr ? __ldcg(reinterpret_cast<const float4*>(acts_row + 4 * 32 + 4 * k)) : make_float4(0.f, 0.f, 0.f, 0.f);
       h4[4 * k] = v.x; h4[4 * k + 1] = v.y; h4[4 * k + 2] = v.z; h4[4 * k + 3] = v.w;
     }
-    put_mn16(wg_next_b(*w), row, cg, h4);
-    wg_push(*w, tmem, t.a[0], wg_next_b(*w), 0, w->dpk + DW::o_WO, DW::PH, 4);
+    put_mn16(w->b, row, cg, h4);
+    wg_group(*w, tmem, 0, w->dpk + DW::o_WO, DW::PH, 4);
     if (cg == 0) {
       const float sb = warp_colsum16(go, lane);
       const int col = colsum_col(lane);
@@ -649,47 +645,42 @@ __device__ __forceinline__ void epi_backward(const KParams& P, const TileSmem& t
 #pragma unroll 1
   for (int i = 4; i >= 0; i--) {
     const uint32_t m = i == 4 ? m4 : (((i & 2) ? m23 : m01) >> (16 * (i & 1))) & 0xffffu;
-    float xr[kCW];                                               // WG: input of layer i (H_{i-1}), fetched early: its latency hides behind the operand writes
     if constexpr (WG) {
-      if (i >= 1) {
-#pragma unroll
-        for (int k = 0; k < kKQ; k++) {
-          const float4 v = acts_row != nullptr ? __ldcg(reinterpret_cast<const float4*>(acts_row + (i - 1) * 32 + 4 * k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          xr[4 * k] = v.x; xr[4 * k + 1] = v.y; xr[4 * k + 2] = v.z; xr[4 * k + 3] = v.w;
-        }
-      }
-      wg_retire(*w, tmem);                                       // the groups of the previous layer read the tiles about to be overwritten
-      __syncthreads();                                           // (every thread's reduction is done with TMEM / the barrier phase before the tiles change)
       float du[kCW];
 #pragma unroll
       for (int j = 0; j < kCW; j++) du[j] = (m >> j) & 1u ? g[j] : 0.0f;
-      put_mn16(t.a[0], row, cg, du); put_mn16(t.a[1], row, cg, g);                 // one copy: chain operands and weight-gradient A operand
+      put_mn16(w->du, row, cg, du); put_mn16(w->g, row, cg, g);
       const float sb = warp_colsum16(du, lane), sc = warp_colsum16(g, lane);      // db_i, dbc_i
       if ((lane & 1) == 0) {
         const int col = kCW * cg + colsum_col(lane);
         atomicAdd(w->dpk + DW::o_b + 32 * i + col, sb); atomicAdd(w->dpk + DW::o_bc + 32 * i + col, sc);
       }
-    } else {
+    }
 #pragma unroll
-      for (int k = 0; k < kKQ; k++) {
-        if (xyz) tc::put4(g_hi, g_hi + TM * 32, row, kKQ * cg + k, 32, make_float4(g[4 * k], g[4 * k + 1], g[4 * k + 2], g[4 * k + 3]));
-        tc::put4(du_hi, du_hi + TM * 32, row, kKQ * cg + k, 32,
-                 make_float4((m >> (4 * k)) & 1u ? g[4 * k] : 0.0f, (m >> (4 * k + 1)) & 1u ? g[4 * k + 1] : 0.0f,
-                             (m >> (4 * k + 2)) & 1u ? g[4 * k + 2] : 0.0f, (m >> (4 * k + 3)) & 1u ? g[4 * k + 3] : 0.0f));
-      }
+    for (int k = 0; k < kKQ; k++) {
+      if (xyz) tc::put4(g_hi, g_hi + TM * 32, row, kKQ * cg + k, 32, make_float4(g[4 * k], g[4 * k + 1], g[4 * k + 2], g[4 * k + 3]));
+      tc::put4(du_hi, du_hi + TM * 32, row, kKQ * cg + k, 32,
+               make_float4((m >> (4 * k)) & 1u ? g[4 * k] : 0.0f, (m >> (4 * k + 1)) & 1u ? g[4 * k + 1] : 0.0f,
+                           (m >> (4 * k + 2)) & 1u ? g[4 * k + 2] : 0.0f, (m >> (4 * k + 3)) & 1u ? g[4 * k + 3] : 0.0f));
     }
     NSB_PH(22);
     publish(t, 0);
-    if (threadIdx.x < 32) issue_bwd_layer<WG>(I, t, tmem, lv, i);
+    if (threadIdx.x < 32) issue_bwd_layer(I, t, tmem, lv, i);
     NSB_PH(23);
     if constexpr (WG) {                                          // weight gradients of layer i (the chain's MMAs run meanwhile)
       if (i >= 1) {                                              // hidden input H_{i-1}
-        float* bt = wg_next_b(*w);
-        put_mn16(bt, row, cg, xr);
+        float xr[kCW];
+#pragma unroll
+        for (int k = 0; k < kKQ; k++) {
+          const float4 v = acts_row != nullptr ? __ldcg(reinterpret_cast<const float4*>(acts_row + (i - 1) * 32 + 4 * k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          xr[4 * k] = v.x; xr[4 * k + 1] = v.y; xr[4 * k + 2] = v.z; xr[4 * k + 3] = v.w;
+        }
+        put_mn16(w->b, row, cg, xr);
         const int o_wh = i == 1 ? DW::o_W1 : i == 2 ? DW::o_W2 : i == 3 ? DW::o_W3H : DW::o_W4;
-        wg_push(*w, tmem, t.a[0], bt, 0, w->dpk + o_wh, DW::PH, 32);
+        wg_group(*w, tmem, 0, w->dpk + o_wh, DW::PH, 32);
       }
-      wg_push(*w, tmem, t.a[0], w->bc, 1, w->dpk + DW::o_WC + 32 * i * DW::PC, DW::PC, 32);        // dWc_i = G_i^T C (resident tile)
+      put_mn16(w->b, row, cg, creg);                             // dWc_i = G_i^T C
+      wg_group(*w, tmem, 1, w->dpk + DW::o_WC + 32 * i * DW::PC, DW::PC, 32);
       if (i == 3 || i == 0) {                                    // embedding part of W_0 / W_3
         const float* B = hdr + 464;
         for (int blk = 0; blk < 3; blk++) {
@@ -700,9 +691,8 @@ __device__ __forceinline__ void epi_backward(const KParams& P, const TileSmem& t
             float x = G.pf[0] * B[f]; x = fmaf(G.pf[1], B[kEmbPad + f], x); x = fmaf(G.pf[2], B[2 * kEmbPad + f], x);
             e[j] = f < kEmb ? __sinf(reduce_2pi(x)) : 0.0f;
           }
-          float* bt = wg_next_b(*w);
-          put_mn16(bt, row, cg, e);
-          wg_push(*w, tmem, t.a[0], bt, 0, w->dpk + (i == 0 ? DW::o_W0 : DW::o_W3E) + 32 * blk, DW::PF, 32);
+          put_mn16(w->b, row, cg, e);
+          wg_group(*w, tmem, 0, w->dpk + (i == 0 ? DW::o_W0 : DW::o_W3E) + 32 * blk, DW::PF, 32);
         }
       }
     }
@@ -714,7 +704,6 @@ __device__ __forceinline__ void epi_backward(const KParams& P, const TileSmem& t
     tc::tc_fence_before();
   }
   NSB_PH(22);
-  if constexpr (WG) { wg_retire(*w, tmem); __syncthreads(); }   // the last groups still read a[0] / a[1]
   // dL/dc rows -> a[0] (plain fp32 [128][cd]); every MMA reading the buffers has completed
   float* dcs = t.a[0];
   {
@@ -730,11 +719,11 @@ __device__ __forceinline__ void epi_backward(const KParams& P, const TileSmem& t
   float dpe[3] = {0.0f, 0.0f, 0.0f};
   if (xyz) {
     const float* B = hdr + 464;
-    if constexpr (WG) {                                          // B tile of the dB groups: the point's coordinates in columns 0..2 (the C tile is dead)
+    if constexpr (WG) {                                          // B tile of the dB groups: the point's coordinates in columns 0..2
       float pv[kCW];
 #pragma unroll
       for (int j = 0; j < kCW; j++) pv[j] = (cg == 0 && j < 3) ? G.pf[j] : 0.0f;
-      put_mn16(w->bc, row, cg, pv);
+      put_mn16(w->b, row, cg, pv);
     }
     for (int c = 0; c < 3; c++) {
       float v[kCW];
@@ -753,14 +742,12 @@ __device__ __forceinline__ void epi_backward(const KParams& P, const TileSmem& t
         }
       }
       if constexpr (WG) {                                        // dB[a][f] = sum_p p_a cos(.) dE_f  (embedder._B is a parameter of the decoder)
-        float* at = wg_next_b(*w);                               // A = the block's dx tile (rotating buffers), B = coordinates
-        put_mn16(at, row, cg, dxv);
+        put_mn16(w->du, row, cg, dxv);
         const int nf = kEmb - 32 * c < 32 ? kEmb - 32 * c : 32;
-        wg_push(*w, tmem, at, w->bc, 0, w->dpk + DW::o_B + 32 * c, kEmbPad, nf, true);
+        wg_group(*w, tmem, 0, w->dpk + DW::o_B + 32 * c, kEmbPad, nf, true);
       }
     }
   }
-  if constexpr (WG) wg_retire(*w, tmem);
   *reinterpret_cast<float4*>(t.a[1] + (cg * TM + row) * 4) = make_float4(dpe[0], dpe[1], dpe[2], 0.0f);
   tc::tc_fence_before();
   NSB_PH(27);
@@ -1096,10 +1083,9 @@ __device__ __forceinline__ void render_bwd_tile_body(const KParams& P) {
   TileSmem t; carve(sbase + (WG ? kWgBytes : 0), t, true);
   BwdExtra& X = *reinterpret_cast<BwdExtra*>(t.extra);
   __shared__ int s_ndone, s_done[kMaxTileRays];
-  __shared__ __align__(8) uint64_t s_wgbar[2];
+  __shared__ __align__(8) uint64_t s_wgbar;
   WgSmem wg;
-  wg.bx[0] = reinterpret_cast<float*>(sbase); wg.bx[1] = wg.bx[0] + 2 * kMnTile; wg.bc = wg.bx[0] + 4 * kMnTile;
-  wg.bar = s_wgbar; wg.phase[0] = wg.phase[1] = 0u; wg.next = 0; wg.pend.valid = false;
+  wg.du = reinterpret_cast<float*>(sbase); wg.g = wg.du + 2 * kMnTile; wg.b = wg.du + 4 * kMnTile; wg.bar = &s_wgbar; wg.phase = 0u;
   wg.dpk = WG ? P.d_packed[P.dec[0]] : nullptr;
 
   const int nsplit = P.split;
@@ -1119,7 +1105,7 @@ __device__ __forceinline__ void render_bwd_tile_body(const KParams& P) {
   Issuer I; I.L.P = &P; I.L.q = q0; I.L.q1 = q1; I.L.k = 0; I.L.loaded = 0; I.L.bwd = true; I.issued = 0; I.g = 0;
   if (tid == 0) {
     for (int i = 0; i < kNumBars; i++) mbar_init(t.bars + i, (i == B_AREADY || i == B_AREADY + 1) ? kEpiThreads / 32 : 1);
-    if (WG) { mbar_init(s_wgbar, 1); mbar_init(s_wgbar + 1, 1); }
+    if (WG) mbar_init(&s_wgbar, 1);
     mbar_fence_init();
     load_header(P, t, P.dec[q0], 0);
     for (int i = 0; i < kSlots; i++) loader_issue(I.L, t);

@@ -298,7 +298,7 @@ class FusedRenderer(object):
             to_channels_last(slam.shared_c)        # layout conversion point, before Mapper/Tracker capture the dict
         self._cache = _PackCache()
         self._mask_cache = {}
-        self.detect_masked_grids = False         # (enabled once validated on the GPU; tests switch it explicitly)
+        self.detect_masked_grids = True
 
     def __getstate__(self):                        # pickled into spawned processes: no device state travels
         d = dict(self.__dict__)
