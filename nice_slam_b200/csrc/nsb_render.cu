@@ -1083,10 +1083,11 @@ static bool plan_split(KParams* K, int nd, void* ws, size_t ws_bytes) {
 static size_t tile_smem_bytes(bool bwd) { return tl::common_bytes(bwd) + (bwd ? sizeof(tl::BwdExtra) : 0); }
 static size_t tile_wg_smem_bytes() { return tl::kWgBytes + ((tile_smem_bytes(true) + 1023) & ~size_t(1023)) + 1024; }
 // Which tensor-core kernel family serves a launch.  mlp_backend 3: always the tile kernels; 2: always the round-1 ray-group kernels; 0 (auto): the
-// tile kernels, except that single-GPU batches of up to g_small_rays rays go to the ray-group kernels (512 threads on one tile at a time: shorter
-// per-tile chains; option "small_rays", 0 = never).  Forward and backward of an iteration see the same (S, n_rays) and so pick the same family
-// (the saved ReLU bits are laid out per family).
-static int g_small_rays = 256;
+// tile kernels, except that batches of up to g_small_rays rays go to the ray-group kernels (option "small_rays"; default 0 = never: since the
+// channels-last gather became straight-line code the tile kernels are level with them at 200 rays -- 0.1105 ms per tracking iteration either way,
+// r02j / r02l -- and ahead everywhere else).  Forward and backward of an iteration see the same (S, n_rays) and so pick the same family (the saved
+// ReLU bits are laid out per family).
+static int g_small_rays = 0;
 static bool use_tile_kernels(int S, int n_rays, bool sharded) {
   if (!(g_mlp_backend == 0 || g_mlp_backend == 3) || S < tl::kMinSamples || S > NSB_MAX_SAMPLES) return false;
   if (g_mlp_backend == 0 && n_rays <= g_small_rays && S <= kMaxPtsTc) return false;

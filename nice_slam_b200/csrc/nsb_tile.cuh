@@ -754,6 +754,7 @@ __device__ __forceinline__ void epi_backward(const KParams& P, const TileSmem& t
 }
 
 // Backward of gather_tile (same warp -> rows mapping).  dcs = [128][cd] fp32.  emit(row, gx) once per point.
+// (unlike gather_tile, making the channels-last test a compile-time property of this loop measured SLOWER -- profiles/README.md, r02k)
 template <typename F>
 __device__ __forceinline__ void scatter_tile(const nsb_grid& g, float* __restrict__ dgrid, const int32_t* __restrict__ slots,
                                              const float* dcs, int cd, const float xn[3], int warp, int lane, F&& emit) {
