@@ -488,9 +488,13 @@ def run_native(args):
     else:
         # N > 1: split-phase iteration with the three NCCL exchanges; captured into one CUDA graph per rank when possible
         ctx.load_device_inputs(ro, rd, gd, gc)
-        sharded.prepare(c, dec, dirs)
+        # every rank knows the whole batch (a sharded tracker splits one pixel list): the batch depth maxima are reduced locally over all ranks' depths
+        # (one tiny launch) instead of being exchanged before sampling ("gt_max_depth computed once on the full batch")
+        gd_global = torch.cat([make_batch(sc, RAYS_PER_GPU, r)[3] for r in range(world)]).to(dev)
+        sharded.prepare(c, dec, dirs, global_gt_depth=gd_global)
         sharded.enqueue(); torch.cuda.synchronize()
-        exchange = "NVLink peer memory, inside the batch_max / seeds / pose_grad kernels" if sharded.peers is not None else "NCCL (all-reduce MAX, all-gather, all-reduce SUM)"
+        exchange = ("NVLink peer memory inside the two render launches (median pool in the forward's tail, [loss | d c2w] sum in the backward's); depth maxima from "
+                    "the full batch's depths, known on every rank") if sharded.peers is not None else "NCCL (all-reduce MAX, all-gather, all-reduce SUM)"
         if sharded.peers is not None:                              # cross-check the in-kernel exchanges against the NCCL collectives once
             ref = ShardedTrackingIteration(ctx, exchange="nccl")
             ref.prepare(c, dec, dirs)
@@ -592,7 +596,7 @@ def run_native(args):
             "clocks": clocks,
             "e2e": {"value": rays / (e2e_ms / args.steps * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": ctx.h2d_bytes,
                     "d2h_bytes_per_step": ctx.d2h_bytes if sharded is None else 13 * 8, "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": (2 if sharded is None else (2 if sharded.fused else (5 if sharded.peers is not None else 6))) * args.steps,
+            "gpu_launches": (2 if sharded is None else (3 if sharded.fused else (5 if sharded.peers is not None else 6))) * args.steps,
             "extra": {"l2_warm_ms_per_step": warm_ms / args.steps, "l2_warm_rays_per_s": rays / (warm_ms / args.steps * 1e-3),
                       "mapping_sharded_masked": map_sharded, "mapping_other_scenes": scenes}}
     if bwd_ms:

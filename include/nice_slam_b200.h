@@ -328,7 +328,8 @@ int nsb_mapping_iteration(const nsb_render_inputs* in, const nsb_iteration_buffe
  * exchanges the depth maxima (every CTA waits for all ranks' values before it samples) and, in its last CTA, the residual pool of the
  * median, then computes this shard's loss seeds; the last CTA of the backward launch sums [loss | d c2w] over the ranks in rank order
  * (loss_and_d_c2w[13], identical bits on every rank).  Arguments as nsb_tracking_iteration; grads->pose_dirs / d_c2w / pose_counter are
- * required.  Waits on a missing rank are bounded (the launch fails instead of hanging). */
+ * required.  Waits on a missing rank are bounded (the launch fails instead of hanging).  If in->depth_max is given (the maxima of the FULL batch,
+ * nsb_batch_max_depth over all ranks' sensor depths, which every rank of a sharded tracker knows) the depth-max exchange is skipped. */
 int nsb_tracking_iteration_peers(const nsb_render_inputs* in, const nsb_iteration_buffers* buf, const double* gt_rgb,
                                  double w_color, int handle_dynamic, int use_color, const nsb_backward_args* grads,
                                  const nsb_peers* peers, double* loss_and_d_c2w, void* stream);

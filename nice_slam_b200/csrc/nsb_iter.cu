@@ -29,9 +29,14 @@ static int check_buffers(const nsb_render_inputs* in, const nsb_iteration_buffer
   return NSB_OK;
 }
 
-static int forward_part(const nsb_render_inputs* in, const nsb_iteration_buffers* b, nsb_render_inputs* in2, const FusedSeeds* fs, void* stream) {
+static int forward_part(const nsb_render_inputs* in, const nsb_iteration_buffers* b, nsb_render_inputs* in2, const FusedSeeds* fs, void* stream,
+                        bool keep_depth_max = false) {
   *in2 = *in;
   int rc;
+  if (keep_depth_max && in->depth_max != nullptr) {                // the caller supplies the batch depth maxima (sharded batch: maxima of the FULL batch)
+    nsb_forward_outputs fo = {b->depth, b->var, b->rgb, b->z_vals, b->raw, nullptr, b->masks, split_ptr(b, in->n_rays), split_room(b, in->n_rays), b->acts};
+    return render_forward_fused(in2, &fo, fs, stream);
+  }
   in2->depth_max = nullptr;
   if (in->gt_depth && in->n_rays > NSB_INLINE_MAX_RAYS) {          // small batches: the render kernel reduces gt_depth itself
     if ((rc = nsb_batch_max_depth(in->gt_depth, in->n_rays, b->depth_max, stream))) return rc;
@@ -91,7 +96,7 @@ extern "C" int nsb_tracking_iteration_peers(const nsb_render_inputs* in, const n
   fs.counter = seeds_counter(buf, in->n_rays);
   fs.px = px;
   nsb_render_inputs in2;
-  if ((rc = forward_part(in, buf, &in2, &fs, stream))) return rc;
+  if ((rc = forward_part(in, buf, &in2, &fs, stream, true))) return rc;      // in->depth_max given: no depth-max exchange inside the forward
   PeerTail tail; tail.px = px; tail.loss = buf->loss; tail.out13 = loss_and_d_c2w;
   return backward_part(&in2, buf, grads, stream, &tail);
 }

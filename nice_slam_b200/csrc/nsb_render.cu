@@ -1140,7 +1140,7 @@ int nsb::render_forward_fused(const nsb_render_inputs* in, const nsb_forward_out
   if (K.S > NSB_MAX_SAMPLES) { set_error("n_samples+n_surface = %d exceeds %d", K.S, NSB_MAX_SAMPLES); return NSB_ERR_UNSUPPORTED; }
   if (K.has_gt && in->n_surface > 0 && !in->t_surface) { set_error("t_surface NULL"); return NSB_ERR_ARG; }
   if ((rc = set_attrs())) return rc;
-  if (K.fs.px.world > 1 && !((tile || group) && in->depth_max == nullptr && in->gt_depth != nullptr)) {
+  if (K.fs.px.world > 1 && !((tile || group) && in->gt_depth != nullptr)) {
     set_error("in-kernel exchanges of a sharded forward need a tensor-core back-end and <= %d rays per rank", NSB_INLINE_MAX_RAYS); return NSB_ERR_UNSUPPORTED; }
   if (tile) {                                             // tile kernels: item = (128-point tile, decoder), two CTAs per SM
     if (!out->z_vals || !out->raw) { set_error("the tensor-core forward needs z_vals and raw outputs"); return NSB_ERR_ARG; }

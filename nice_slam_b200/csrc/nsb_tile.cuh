@@ -842,12 +842,14 @@ __device__ __forceinline__ void composite_ray(const KParams& P, int ray, int lan
   for (int a = 0; a < 3; a++) { o[a] = P.in.rays_o[3 * ray + a]; d[a] = P.in.rays_d[3 * ray + a]; }
   const long long g0 = (long long)ray * S, NS = (long long)P.in.n_rays * S;
   for (int s = lane; s < S; s += 32) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int q = 0; q < P.split; q++) {                           // decoder order: occ = fine + middle, rgb = colour decoder (zeros elsewhere)
-      const float4 p = __ldcg(P.tile_parts + q * NS + g0 + s);
-      v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
-    }
+    // (all loads of the sample first: with a run-time trip count they were issued one L2 round trip after the other)
+    float4 pq[3];
+#pragma unroll
+    for (int q = 0; q < 3; q++) pq[q] = q < P.split ? __ldcg(P.tile_parts + q * NS + g0 + s) : make_float4(0.f, 0.f, 0.f, 0.f);
     const double z = __ldcg(P.fo.z_vals + g0 + s);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 3; q++) { v.x += pq[q].x; v.y += pq[q].y; v.z += pq[q].z; v.w += pq[q].w; }       // decoder order: occ = fine + middle, rgb = colour decoder (zeros elsewhere)
     PointGeom G; make_point(P.in.bound, P.in.coarse_bound, o, d, z, G);
     if (!G.inb) v.w = 100.0f;
     zz[s] = z;

@@ -120,7 +120,11 @@ class ShardedTrackingIteration:
                                    % (ctx.n, int(nn[0]), -int(nn[1])))
         self.fused = self.peers is not None and ctx.n <= 512          # whole iteration in two launches (exchanges inside the render kernels)
 
-    def prepare(self, c, decoders, dirs, w_color=0.5, handle_dynamic=True, use_color=True):
+    def prepare(self, c, decoders, dirs, w_color=0.5, handle_dynamic=True, use_color=True, global_gt_depth=None):
+        """global_gt_depth: the sensor depths of the WHOLE batch (a ray-sharded tracker splits a pixel list every rank knows: same frame, same
+        draws).  The batch depth maxima (Renderer.py:109,144) are then reduced locally over the full list (one tiny launch) and the iteration keeps
+        only the two exchanges that sit at kernel tails (median pool, [loss | d c2w] sum); without it every forward CTA first waits for all ranks'
+        shard maxima -- which exposes the launch skew between the ranks' independent graph replays."""
         from . import _lib
         from .renderer import _inputs, _linspaces
         x = self.ctx
@@ -138,7 +142,7 @@ class ShardedTrackingIteration:
         bw.z_vals, bw.raw, bw.g_depth, bw.g_rgb, bw.masks = (x.z_vals.data_ptr(), x.raw.data_ptr(), x.g_depth.data_ptr(),
                                                               x.g_rgb.data_ptr(), x.masks.data_ptr())
         self._p = dict(call=call, grids=grids, lin=(t_u, t_s), inp=inp, fo=fo, bw=bw, dirs=dirs, gd=gd, gc=gc,
-                       w_color=w_color, hd=int(handle_dynamic), uc=int(use_color))
+                       w_color=w_color, hd=int(handle_dynamic), uc=int(use_color), ggd=global_gt_depth)
 
     def enqueue(self):
         import ctypes as C
@@ -153,7 +157,11 @@ class ShardedTrackingIteration:
             bw = p["bw"]
             bw.pose_dirs, bw.d_c2w, bw.pose_counter = p["dirs"].data_ptr(), x.d_c2w.data_ptr(), x.pose_counter.data_ptr()
             inp = p["inp"]
-            inp.depth_max = None                                       # reduced + exchanged inside the forward kernel
+            if p["ggd"] is not None:                                   # maxima of the full batch, known locally: no exchange before sampling
+                _lib.check(L.nsb_batch_max_depth(_VP(p["ggd"].data_ptr()), p["ggd"].numel(), _VP(x.depth_max.data_ptr()), st), "nsb_batch_max_depth")
+                inp.depth_max = x.depth_max.data_ptr()
+            else:
+                inp.depth_max = None                                   # reduced + exchanged inside the forward kernel
             _lib.check(L.nsb_tracking_iteration_peers(C.byref(inp), C.byref(x.buf), _VP(p["gc"].data_ptr()), p["w_color"], p["hd"], p["uc"], C.byref(bw),
                                                       C.byref(self.peers.struct), _VP(self.packed.data_ptr()), st), "nsb_tracking_iteration_peers")
             return self.packed

@@ -48,9 +48,9 @@ def _worker(rank, world, port, q):
     want = torch.cat([full.loss.reshape(1), full.d_c2w.reshape(-1)]).clone()
     ctx = IterationContext(renderer, n_shard, "color", dev, kind="track")
     ctx.load_device_inputs(ro[lo:hi].to(dev), rd[lo:hi].to(dev), gd[lo:hi].to(dev), gc[lo:hi].double().to(dev))
-    for name in ("auto", "nccl"):
-        sh = ShardedTrackingIteration(ctx, exchange=name)
-        sh.prepare(c, dec, dirs[lo:hi].to(dev))
+    for name in ("auto", "nccl", "auto_global_max"):
+        sh = ShardedTrackingIteration(ctx, exchange=name.split("_")[0])
+        sh.prepare(c, dec, dirs[lo:hi].to(dev), global_gt_depth=gd.to(dev) if name.endswith("global_max") else None)
         got = sh.enqueue().clone()
         out["track_" + name] = (float((got - want).abs().max() / want.abs().max()), sh.peers is not None)
         g = sh.build_graph()

@@ -87,11 +87,12 @@ def test_peer_exchange_kernels_two_ranks_on_one_gpu(world, n):
         assert int(ctrs[0][0]) == rnd + 1 and int(ctrs[0][1]) == rnd + 1 and int(ctrs[0][2]) == rnd + 1
 
 
-@pytest.mark.parametrize("world,n", [(2, 100), (2, 37)])
-def test_two_launch_sharded_tracking_iteration_on_one_gpu(world, n):
+@pytest.mark.parametrize("world,n,global_max", [(2, 100, False), (2, 37, False), (2, 100, True)])
+def test_two_launch_sharded_tracking_iteration_on_one_gpu(world, n, global_max):
     """nsb_tracking_iteration_peers (forward + backward launches with the exchanges inside the tile kernels) for `world` ranks on ONE GPU
     (one stream and one set of buffers per rank) == the single-rank tracking iteration over the whole batch: same depth maxima (hence
-    bit-identical samples), same median, same seeds, [loss | d c2w] summed over the ranks; replayed three times."""
+    bit-identical samples), same median, same seeds, [loss | d c2w] summed over the ranks; replayed three times.  global_max: the depth maxima of the
+    FULL batch are handed in (nsb_batch_max_depth over all ranks' depths) and the depth-max exchange (channel 0) is not used."""
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")
     import scene_util as su
@@ -123,6 +124,10 @@ def test_two_launch_sharded_tracking_iteration_on_one_gpu(world, n):
         call, grids, _ = renderer._call(c, dec, "color", vgd, torch.device(DEV))
         t_u, t_s = _linspaces(renderer.N_samples, renderer.N_surface, torch.device(DEV))
         inp = _inputs(call, vro, vrd, None, t_u, t_s, [g.detach() for g in grids])
+        if global_max:
+            gd_all = gd.to(DEV)
+            _lib.check(L.nsb_batch_max_depth(VP(gd_all.data_ptr()), N, VP(x.depth_max.data_ptr()), VP(torch.cuda.current_stream().cuda_stream)), "batch_max")
+            inp.depth_max = x.depth_max.data_ptr()
         bw = x._grads(c)
         d = dirs[sl].to(DEV).contiguous()
         bw.pose_dirs, bw.d_c2w, bw.pose_counter = d.data_ptr(), x.d_c2w.data_ptr(), x.pose_counter.data_ptr()
@@ -141,4 +146,4 @@ def test_two_launch_sharded_tracking_iteration_on_one_gpu(world, n):
             got_rays = torch.cat([k["x"].d_rays_o, k["x"].d_rays_d], 1)
             assert rel(got_rays, want_rays[sl]) < 1e-5, (rnd, r, rel(got_rays, want_rays[sl]))
         assert rel(ranks[0]["out"], want) < 1e-6, (rnd, rel(ranks[0]["out"], want))
-        assert all(int(ctrs[r][ch]) == rnd + 1 for r in range(world) for ch in range(3))
+        assert all(int(ctrs[r][ch]) == rnd + 1 for r in range(world) for ch in ((1, 2) if global_max else (0, 1, 2)))
