@@ -1,21 +1,22 @@
 #!/bin/bash
-# quick GPU check: parity tests (stop at first failure), phase timing, short bench
 tag=${1:-q}
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -40 > gpurun_out/${tag}_tests.log
-echo "pytest exit ${PIPESTATUS[0]}" >> gpurun_out/${tag}_tests.log
-tail -6 gpurun_out/${tag}_tests.log
-NSB_LIB=nice_slam_b200/libnsb_timing.so timeout 300 python tools/phase_timing.py 200 > gpurun_out/${tag}_phase_200.txt 2>&1
-NSB_LIB=nice_slam_b200/libnsb_timing.so timeout 300 python tools/phase_timing.py 8192 > gpurun_out/${tag}_phase_8192.txt 2>&1
-cat gpurun_out/${tag}_phase_200.txt
-timeout 900 python bench.py --steps 200 --warmup 10 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
-echo "bench exit $?"; python - <<PYEOF
+timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -8 > gpurun_out/${tag}_tests.log; echo "pytest exit ${PIPESTATUS[0]}" >> gpurun_out/${tag}_tests.log; tail -4 gpurun_out/${tag}_tests.log
+for v in "NSB_X=0" "NSB_SMALL_RAYS=0"; do
+  env $v NSB_BENCH_FAST=1 timeout 600 python bench.py --steps 300 --warmup 10 > gpurun_out/${tag}_fast_${v%%=*}.json 2>/dev/null
+  python - <<PYEOF
 import json
-d=json.load(open("gpurun_out/${tag}_bench.json"))
-print("ms/step", d["ms_per_step"], "rays/s", d["value"], "e2e", d["e2e"]["ms_per_step"], "warm", d["extra"]["l2_warm_ms_per_step"])
-print("bwd launch ms", d["roofline"]["launch_ms"])
-for k in ("mapping_configs1","mapping_loop_step"): print(k, d["extra"][k]["ms_per_step"])
-print([ (x["rays"], round(x["ms_per_step"],3), round(x["rays_per_s"]/1e6,2)) for x in d["extra"]["sweep_tracking_iteration"]])
+d=json.load(open("gpurun_out/${tag}_fast_${v%%=*}.json"))
+print("fast bench [$v]: ms/step", round(d["ms_per_step"],5), "e2e", round(d["e2e"]["ms_per_step"],5), "warm", round(d["extra"]["l2_warm_ms_per_step"],5), "bwd", round(d["roofline"]["launch_ms"],5))
 PYEOF
-tail -3 gpurun_out/${tag}_bench.err
+done
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${tag}_map_launches.csv python tools/map_launches.py 996 > gpurun_out/${tag}_map_launches.log 2>&1
+python - <<PYEOF
+import csv
+rows=[r for r in csv.reader(open("gpurun_out/${tag}_map_launches.csv")) if len(r)>10]
+hdr=rows[0]; ki=hdr.index("Kernel Name"); vi=hdr.index("Metric Value")
+seq=[(r[ki].split("(")[0], float(r[vi])) for r in rows[1:]]
+idx=[i for i,(k,_) in enumerate(seq) if "render_fwd" in k]
+for k,v in seq[idx[-1]:]: print("%-60s %10.1f us" % (k[:60], v/1000 if v>1000 else v))
+PYEOF
