@@ -437,11 +437,11 @@ def mapping_sharded_workload(sc, renderer, c, dec, dev, flush, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------ native arm (GPU)
-# dram__bytes_read.sum + dram__bytes_write.sum of one render_bwd_tc_kernel launch of THIS workload (200 rays x 48, room0), taken from the
+# dram__bytes_read.sum + dram__bytes_write.sum of one render_bwd_tile_kernel launch of THIS workload (200 rays x 48, room0), taken from the
 # committed `ncu --set full` capture (never measured inside a timed run): the 48.5 MB of grids are L2-resident, so DRAM traffic is far
 # below the 29.5 MB of algorithmic gather bytes.
-NCU_DRAM_BYTES_PER_BWD_LAUNCH = 4003840
-NCU_TRAFFIC_SOURCE = "profiles/ncu_full_r02_render_kernels.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+NCU_DRAM_BYTES_PER_BWD_LAUNCH = 3777280
+NCU_TRAFFIC_SOURCE = "profiles/ncu_full_r02o_render_kernels.txt (ncu --set full: render_bwd_tile_kernel, 3.78 MB read + 0 B written per launch)"
 
 
 def dbg(msg):
