@@ -573,6 +573,21 @@ def run_native(args):
     warm_ms, _, _ = timed(step_dev, args.steps, 3, False)                 # L2-warm (production steady state), reported as extra
     e2e_ms, _, _ = timed(step_e2e, args.steps, 3, True)
 
+    # opt-in forward arithmetic (option fwd_f16: FP16 hi|lo operands, tcgen05 kind::f16 -- half the MMAs of the 3xTF32 forward):
+    # the same iteration re-captured with the option on, reported as an extra -- the headline above is the default 3xTF32 path
+    f16_opt = None
+    if sharded is None and os.environ.get("NSB_FWD_F16") is None:
+        from nice_slam_b200 import _lib
+        L = _lib.lib()
+        if L.nsb_set_option(b"fwd_f16", 1) == 0:
+            try:
+                g_f16 = ctx.build_graph(c, dec, dirs=dirs, host_io=False)
+                ms16, _, _ = timed(g_f16.replay, args.steps, 3, True)
+                f16_opt = {"ms_per_step": ms16 / args.steps, "rays_per_s": RAYS_PER_GPU / (ms16 / args.steps * 1e-3),
+                           "note": "nsb_set_option('fwd_f16', 1) / NSB_FWD_F16=1; default off: operands must stay inside the fp16 range and "
+                                   "values below 2^-14 keep an absolute (2^-25) rather than relative accuracy"}
+            finally:
+                L.nsb_set_option(b"fwd_f16", 0)
     fast = os.environ.get("NSB_BENCH_FAST") == "1"              # development aid: headline numbers only (never used by the driver)
     dbg("mapping sharded workload")
     map_sharded = None if fast else mapping_sharded_workload(sc, renderer, c, dec, dev, flush, rank, world)
@@ -598,7 +613,7 @@ def run_native(args):
                     "d2h_bytes_per_step": ctx.d2h_bytes if sharded is None else 13 * 8, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": (2 if sharded is None else (3 if sharded.fused else (5 if sharded.peers is not None else 6))) * args.steps,
             "extra": {"l2_warm_ms_per_step": warm_ms / args.steps, "l2_warm_rays_per_s": rays / (warm_ms / args.steps * 1e-3),
-                      "mapping_sharded_masked": map_sharded, "mapping_other_scenes": scenes}}
+                      "mapping_sharded_masked": map_sharded, "mapping_other_scenes": scenes, "fwd_f16_option": f16_opt}}
     if bwd_ms:
         t_bwd = statistics.mean(bwd_ms) * 1e-3
         ach = BYTES_PER_RAY * RAYS_PER_GPU / t_bwd / 1e9

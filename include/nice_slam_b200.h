@@ -266,7 +266,9 @@ int nsb_adam_poses(float* cams, const int32_t* cam_row, int n_frames, const floa
  * median of the residuals (Tracker.py:113) and the sums of loss and pose gradient.  The *_peers variants of the three single-CTA
  * kernels exchange them inside the kernel: every rank owns an exchange buffer of nsb_peer_buffer_bytes(max_rays) bytes, zeroed once,
  * mapped on all ranks (CUDA IPC / torch symmetric memory); buffer[r] is rank r's buffer as addressable from THIS device.
- * counters: device uint64[4] of this rank, zeroed once (sequence numbers; advanced by the kernels -> CUDA-graph replay safe).
+ * counters: device uint64[4] of this rank, zeroed once TOGETHER with the buffers (sequence numbers; advanced by the kernels -> CUDA-graph
+ * replay safe; every 8-byte word of an exchange carries its sequence number next to 4 bytes of payload, so data and arrival flag are one
+ * atomic word and no system-scope fence sits on the path).  Buffers: 16-byte aligned.
  * All ranks must enqueue the same sequence of *_peers calls; the kernels of one call spin until every rank has arrived. */
 #define NSB_MAX_PEERS 8
 typedef struct nsb_peers {

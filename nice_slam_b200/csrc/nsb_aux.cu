@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cuda_fp16.h>
 #include "nsb_common.cuh"
 #include "nsb_seeds.cuh"
 #include "nsb_geom.cuh"
@@ -162,6 +163,33 @@ __device__ void pack_units_level(float* __restrict__ img) {
         emit_unit(dst, 32, 32, [&](int f, int k) { return W[(i == 0 ? D::o_W0 : D::o_W3E) + k * D::PF + 32 * fb + f]; });
   }
 }
+// ---- v3 forward image: FP16 hi | lo units (layout: nsb_common.cuh op3_*) ----------------------------------------------------------------
+template <typename F>
+__device__ __forceinline__ void emit_unit_h16(__half*& dst, int R, int KW, F&& get) {
+  __half* hi = dst; __half* lo = dst + R * KW;
+  for (int idx = pk_tid(); idx < R * KW; idx += pk_nt()) {
+    const int r = idx / KW, k = idx - r * KW;
+    const float v = get(r, k);
+    const __half h = __float2half_rn(v);
+    const int o = ((r >> 3) * (KW >> 3) + (k >> 3)) * 64 + (r & 7) * 8 + (k & 7);
+    hi[o] = h; lo[o] = __float2half_rn(v - __half2float(h));
+  }
+  dst += 2 * R * KW;
+}
+template <int LV>
+__device__ void pack_units_h16_level(float* __restrict__ img) {
+  using D = Dec<LV>;
+  const float* W = img;
+  constexpr int PH = D::PH;
+  const int o_wh[5] = {0, D::o_W1, D::o_W2, D::o_W3H, D::o_W4};
+  __half* dst = reinterpret_cast<__half*>(img + op3_fwd_offset(LV));
+  if (D::XYZ)
+    for (int u = 0; u < D::CD / 16; u++)
+      emit_unit_h16(dst, 160, 16, [&](int r, int k) { return W[D::o_WC + r * D::PC + 16 * u + k]; });
+  for (int b = 0; b < op_nblk(LV); b++)
+    emit_unit_h16(dst, 64, 32, [&](int r, int k) { return W[(r < 32 ? D::o_W0 : D::o_W3E) + (r & 31) * D::PF + 32 * b + k]; });
+  for (int i = 1; i < 5; i++) emit_unit_h16(dst, 32, 32, [&](int r, int k) { return W[o_wh[i] + r * PH + k]; });
+}
 __global__ void pack_operands_kernel(const __grid_constant__ PackArgs A) {
   const int lv = blockIdx.x;
   if (!A.present[lv]) return;
@@ -176,6 +204,12 @@ __global__ void pack_operands_kernel(const __grid_constant__ PackArgs A) {
     case 1: pack_units_level<1>(A.packed[1]); break;
     case 2: pack_units_level<2>(A.packed[2]); break;
     default: pack_units_level<3>(A.packed[3]); break;
+  }
+  switch (lv) {
+    case 0: pack_units_h16_level<0>(A.packed[0]); break;
+    case 1: pack_units_h16_level<1>(A.packed[1]); break;
+    case 2: pack_units_h16_level<2>(A.packed[2]); break;
+    default: pack_units_h16_level<3>(A.packed[3]); break;
   }
 }
 
@@ -203,20 +237,19 @@ __global__ void batch_max_kernel(const float* __restrict__ gt, int n, float* __r
       out2[1] = __fmul_rn(m, 1.2f);      // torch.max(gt_depth*1.2): x -> fl(1.2f*x) is monotone, so max commutes (Renderer.py:109)
     }
   }
-  if (px.world > 1) {                    // MAX over the ray shards of all ranks (channel 0: slot = {max, flag} of 16 bytes)
+  if (px.world > 1) {                    // MAX over the ray shards of all ranks (channel 0: one LL word {max | sequence number} per rank)
     __shared__ uint32_t s_seq;
+    __syncthreads();
     const uint32_t seq = peer_begin(px, 0, &s_seq);
     const int par = seq & 1u;
-    if ((int)threadIdx.x < px.world) {
-      float* slot = reinterpret_cast<float*>(px.peer[threadIdx.x] + kXMaxOff + ((size_t)par * NSB_MAX_PEERS + px.rank) * 16);
-      __stcg(slot, out2[0]);
-    }
-    peer_signal_wait(px, 0, kXMaxOff + 8, 16, seq);
-    if (threadIdx.x == 0) {
+    if ((int)threadIdx.x < px.world) ll_put_f32(px.peer[threadIdx.x] + kXMaxOff + ((size_t)par * NSB_MAX_PEERS + px.rank) * 16, out2[0], seq);
+    if (threadIdx.x < 32) {
       float mm = -INFINITY;
-      for (int r = 0; r < px.world; r++) mm = fmaxf(mm, __ldcg(reinterpret_cast<const float*>(px.peer[px.rank] + kXMaxOff + ((size_t)par * NSB_MAX_PEERS + r) * 16)));
-      out2[0] = mm; out2[1] = __fmul_rn(mm, 1.2f);
+      if ((int)threadIdx.x < px.world) mm = ll_get_f32(px.peer[px.rank] + kXMaxOff + ((size_t)par * NSB_MAX_PEERS + threadIdx.x) * 16, seq, px, 0);
+      for (int o = 16; o > 0; o >>= 1) mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, o));
+      if (threadIdx.x == 0) { out2[0] = mm; out2[1] = __fmul_rn(mm, 1.2f); }
     }
+    peer_end(px, 0, seq);
   }
 }
 

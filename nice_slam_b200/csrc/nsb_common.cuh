@@ -8,6 +8,7 @@
 //   backward  dx[pt][i]  += DU[o][pt] * W[o][i]  (lanes read consecutive float4 along i in row o)
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include "../../include/nice_slam_b200.h"
 
@@ -107,7 +108,15 @@ __host__ __device__ constexpr int op2_bwd_units(int lv) {
 __host__ __device__ constexpr int op2_bwd_floats(int lv) { return op2_bwd_units(lv) * 2048; }
 __host__ __device__ constexpr int op2_fwd_offset(int lv) { return packed_floats(lv) + op_fwd_floats(lv) + op_bwd_floats(lv); }
 __host__ __device__ constexpr int op2_bwd_offset(int lv) { return op2_fwd_offset(lv) + op2_fwd_floats(lv); }
-__host__ __device__ constexpr int packed_total_floats(int lv) { return op2_bwd_offset(lv) + op2_bwd_floats(lv); }
+// ---- v3 forward image (tile kernels, option fwd_f16): the forward units as FP16 hi | lo pairs (x = hi + lo, hi = fp16(x), lo = fp16(x - hi): the same
+// ~22-bit effective mantissa as the 3xTF32 split at half the bytes; tcgen05 kind::f16 contracts K = 16 per instruction).  16-bit canonical K-major
+// tile: [row/8][k/8][row%8][k%8] halves (core matrix = 8 rows x 16 bytes).  Sizes in FLOAT units (2 halves each):
+//   FC_u, u < cd/16 : [160 x 16] (2560)   L0_b, b < nblk : [64 x 32] (2048)   H_i, i = 1..4 : [32 x 32] (1024)
+__host__ __device__ constexpr int op3_fc_units(int lv) { return lv == 0 ? 0 : op_cd(lv) / 16; }
+__host__ __device__ constexpr int op3_fwd_units(int lv) { return op3_fc_units(lv) + op_nblk(lv) + 4; }
+__host__ __device__ constexpr int op3_fwd_floats(int lv) { return op3_fc_units(lv) * 2560 + op_nblk(lv) * 2048 + 4 * 1024; }
+__host__ __device__ constexpr int op3_fwd_offset(int lv) { return op2_bwd_offset(lv) + op2_bwd_floats(lv); }
+__host__ __device__ constexpr int packed_total_floats(int lv) { return op3_fwd_offset(lv) + op3_fwd_floats(lv); }
 constexpr int kBwdStageFloats = op_bwd_layer_floats(2, 3);      // largest backward layer chunk (fine decoder, layer 3): 48 KB
 static_assert(kBwdStageFloats == 12288, "backward stage size");
 

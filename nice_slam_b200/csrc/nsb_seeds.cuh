@@ -14,16 +14,55 @@ namespace nsb {
 // ------------------------------------------------------------------------------------------------ in-kernel exchanges over peer memory
 // A ray-sharded tracking iteration needs three tiny batch-global quantities.  Instead of three NCCL launches the
 // single-CTA kernels that produce them exchange them themselves through NVLink peer memory (symmetric buffers, one per rank, mapped
-// on every rank): push the local value into slot [parity][my rank] of EVERY peer's buffer, st.release.sys a sequence number next to
-// it, spin (ld.acquire.sys) on the own buffer until all ranks' sequence numbers have arrived.  Parity double-buffering + one
-// sequence counter per channel make the buffers reusable without any reset; a rank cannot run two exchanges of a channel ahead
-// because the other channels of the same iteration need everybody.
+// on every rank): push the local value into slot [parity][my rank] of EVERY peer's buffer, each 8-byte word carrying the exchange's
+// sequence number next to 4 bytes of payload ("LL" words, below), and poll the own buffer until every rank's words show that number.
+// Parity double-buffering + one sequence counter per channel make the buffers reusable without any reset; a rank cannot run two
+// exchanges of a channel ahead because the other channels of the same iteration need everybody.
 constexpr long long kPeerWaitCycles = 20000000000ll;        // ~10 s at 1.9 GHz
-constexpr size_t kXMaxOff = 0, kXSumOff = 256, kXPoolFlagOff = 2304, kXPoolOff = 2560;
-__host__ __device__ inline size_t peer_buffer_bytes(int max_n) { return kXPoolOff + (size_t)2 * NSB_MAX_PEERS * (size_t)max_n * sizeof(double); }
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+// buffer: [depth maxima: 2 x 8 x one LL word (16-byte stride) | sums: 2 x 8 x 16 LL pairs | residual pool: 2 x 8 x max_n LL pairs | this rank's plain copy of
+// the gathered pool: 8 x max_n f64]
+constexpr size_t kXMaxOff = 0, kXSumOff = 256, kXSumStride = 256, kXPoolOff = kXSumOff + 2 * NSB_MAX_PEERS * kXSumStride;
+__host__ __device__ inline size_t peer_pool_plain_off(int max_n) { return kXPoolOff + (size_t)2 * NSB_MAX_PEERS * (size_t)max_n * 16; }
+__host__ __device__ inline size_t peer_buffer_bytes(int max_n) { return peer_pool_plain_off(max_n) + (size_t)NSB_MAX_PEERS * (size_t)max_n * sizeof(double); }
+// "LL" pairs (the low-latency protocol of the collective libraries): a double travels as two 8-byte words {32 bits of payload | the exchange's 32-bit
+// sequence number}, written with ONE 16-byte store.  An aligned 8-byte word is single-copy atomic, so data and "it has arrived" are the same
+// word: no system-scope fence on the sender (a membar.sys costs microseconds on a path that is all latency), no separate flag, and the receiver
+// polls exactly the words it consumes.  Used by the two exchanges of a ray-sharded tracking iteration (residual pool, [loss | d c2w] sum).
+__device__ __forceinline__ void ll_put(unsigned char* slot16, double v, uint32_t seq) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long w0 = ((unsigned long long)seq << 32) | (b & 0xffffffffull), w1 = ((unsigned long long)seq << 32) | (b >> 32);
+  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(slot16), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ double ll_get(const unsigned char* slot16, uint32_t seq, const PeerX& px, int c) {
+  unsigned long long w0, w1;
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot16) : "memory");
+    if ((uint32_t)(w0 >> 32) == seq && (uint32_t)(w1 >> 32) == seq) break;
+    // a rank that never arrives (crashed process, mismatched call sequence) must not hang the device: fail the launch instead
+    if (clock64() - t0 > kPeerWaitCycles) { printf("nsb: peer exchange timed out (rank %d, channel %d, seq %u)\n", px.rank, c, seq); __trap(); }
+  }
+  return __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
+}
+// one float as a single LL word
+__device__ __forceinline__ void ll_put_f32(unsigned char* slot8, float v, uint32_t seq) {
+  const unsigned long long w = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(v);
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(slot8), "l"(w) : "memory");
+}
+__device__ __forceinline__ float ll_get_f32(const unsigned char* slot8, uint32_t seq, const PeerX& px, int c) {
+  unsigned long long w;
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(slot8) : "memory");
+    if ((uint32_t)(w >> 32) == seq) break;
+    if (clock64() - t0 > kPeerWaitCycles) { printf("nsb: peer exchange timed out (rank %d, channel %d, seq %u)\n", px.rank, c, seq); __trap(); }
+  }
+  return __uint_as_float((uint32_t)w);
+}
+// close an LL exchange: every thread has consumed its words -> remember the sequence number
+__device__ __forceinline__ void peer_end(const PeerX& px, int c, uint32_t seq) {
+  __syncthreads();
+  if (threadIdx.x == 0) px.counter[c] = (unsigned long long)seq;
 }
 // sequence number of this launch on channel c (CTA-uniform)
 __device__ __forceinline__ uint32_t peer_begin(const PeerX& px, int c, uint32_t* s_seq) {
@@ -31,24 +70,6 @@ __device__ __forceinline__ uint32_t peer_begin(const PeerX& px, int c, uint32_t*
   __syncthreads();
   return *s_seq;
 }
-// all pushes of this CTA are done -> publish `seq` in slot [parity][rank] of every peer, wait for every rank's, remember the sequence
-__device__ __forceinline__ void peer_signal_wait(const PeerX& px, int c, size_t flag_off, size_t flag_stride, uint32_t seq) {
-  __threadfence_system();
-  __syncthreads();
-  const int par = seq & 1u;
-  if ((int)threadIdx.x < px.world) {
-    st_release_sys(reinterpret_cast<uint32_t*>(px.peer[threadIdx.x] + flag_off + ((size_t)par * NSB_MAX_PEERS + px.rank) * flag_stride), seq);
-    const uint32_t* mine = reinterpret_cast<const uint32_t*>(px.peer[px.rank] + flag_off + ((size_t)par * NSB_MAX_PEERS + threadIdx.x) * flag_stride);
-    const long long t0 = clock64();
-    while ((int)(ld_acquire_sys(mine) - seq) < 0) {
-      // a rank that never arrives (crashed process, mismatched call sequence) must not hang the device: fail the launch instead
-      if (clock64() - t0 > kPeerWaitCycles) { printf("nsb: peer exchange timed out (rank %d waiting for rank %d, channel %d, seq %u)\n", px.rank, (int)threadIdx.x, c, seq); __trap(); }
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) px.counter[c] = (unsigned long long)seq;
-}
-
 
 // ---- exchanges fused into multi-CTA kernels (tile kernels, nsb_tile.cuh) ----------------------------------------------------------------
 // MAX over ranks of one float, needed by EVERY CTA of the grid before it can sample (channel 0): CTA 0 pushes this rank's value to every
@@ -59,23 +80,18 @@ __device__ __forceinline__ float peer_max_all_ctas(const PeerX& px, float local,
   __syncthreads();
   const uint32_t seq = *s_seq;
   const int par = seq & 1u;
-  if (blockIdx.x == 0) {
-    if ((int)threadIdx.x < px.world) {
-      __stcg(reinterpret_cast<float*>(px.peer[threadIdx.x] + kXMaxOff + ((size_t)par * NSB_MAX_PEERS + px.rank) * 16), local);
-      __threadfence_system();
-      st_release_sys(reinterpret_cast<uint32_t*>(px.peer[threadIdx.x] + kXMaxOff + 8 + ((size_t)par * NSB_MAX_PEERS + px.rank) * 16), seq);
-    }
-  }
-  if ((int)threadIdx.x < px.world) {
-    const uint32_t* mine = reinterpret_cast<const uint32_t*>(px.peer[px.rank] + kXMaxOff + 8 + ((size_t)par * NSB_MAX_PEERS + threadIdx.x) * 16);
-    const long long t0 = clock64();
-    while ((int)(ld_acquire_sys(mine) - seq) < 0) {
-      if (clock64() - t0 > kPeerWaitCycles) { printf("nsb: peer depth-max exchange timed out (rank %d waiting for rank %d, seq %u)\n", px.rank, (int)threadIdx.x, seq); __trap(); }
-    }
+  __syncthreads();                                           // (*s_seq is reused for the result below)
+  if (blockIdx.x == 0 && (int)threadIdx.x < px.world)
+    ll_put_f32(px.peer[threadIdx.x] + kXMaxOff + ((size_t)par * NSB_MAX_PEERS + px.rank) * 16, local, seq);
+  float m = -INFINITY;
+  if (threadIdx.x < 32) {                                    // warp 0: lane r polls rank r's word, then the maximum over the lanes
+    if ((int)threadIdx.x < px.world) m = ll_get_f32(px.peer[px.rank] + kXMaxOff + ((size_t)par * NSB_MAX_PEERS + threadIdx.x) * 16, seq, px, 0);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) *reinterpret_cast<float*>(s_seq) = m;
   }
   __syncthreads();
-  float m = -INFINITY;
-  for (int r = 0; r < px.world; r++) m = fmaxf(m, __ldcg(reinterpret_cast<const float*>(px.peer[px.rank] + kXMaxOff + ((size_t)par * NSB_MAX_PEERS + r) * 16)));
+  m = *reinterpret_cast<const float*>(s_seq);
+  __syncthreads();
   return m;
 }
 __device__ __forceinline__ void peer_advance(const PeerX& px, int c) {      // one thread of the grid's last CTA
@@ -87,14 +103,14 @@ __device__ __forceinline__ void peer_sum13(const PeerX& px, const double* tot, i
   const int par = seq & 1u;
   for (int i = threadIdx.x; i < n_val * px.world; i += blockDim.x) {
     const int r = i / n_val, k = i - n_val * r;
-    __stcg(reinterpret_cast<double*>(px.peer[r] + kXSumOff + ((size_t)par * NSB_MAX_PEERS + px.rank) * 128) + k, tot[k]);
+    ll_put(px.peer[r] + kXSumOff + ((size_t)par * NSB_MAX_PEERS + px.rank) * kXSumStride + (size_t)k * 16, tot[k], seq);
   }
-  peer_signal_wait(px, 2, kXSumOff + 104, 128, seq);
   if ((int)threadIdx.x < n_val) {
     double v = 0.0;
-    for (int r = 0; r < px.world; r++) v += __ldcg(reinterpret_cast<const double*>(px.peer[px.rank] + kXSumOff + ((size_t)par * NSB_MAX_PEERS + r) * 128) + threadIdx.x);
+    for (int r = 0; r < px.world; r++) v += ll_get(px.peer[px.rank] + kXSumOff + ((size_t)par * NSB_MAX_PEERS + r) * kXSumStride + (size_t)threadIdx.x * 16, seq, px, 2);
     out[threadIdx.x] = v;
   }
+  peer_end(px, 2, seq);
 }
 
 constexpr int kMedianDirect = 512;       // larger pools: 8-pass radix select (the direct count is O(n^2))
@@ -145,29 +161,41 @@ __device__ __forceinline__ void tracking_seeds_body(const double* depth, const d
       const int par = seq & 1u;
       for (int i = threadIdx.x; i < n * px.world; i += blockDim.x) {
         const int r = i / n, j = i - r * n;
-        __stcg(reinterpret_cast<double*>(px.peer[r] + kXPoolOff) + ((size_t)par * NSB_MAX_PEERS + px.rank) * px.max_n + j, res[j]);
+        ll_put(px.peer[r] + kXPoolOff + (((size_t)par * NSB_MAX_PEERS + px.rank) * px.max_n + j) * 16, res[j], seq);
       }
-      peer_signal_wait(px, 1, kXPoolFlagOff, 16, seq);
-      mp = reinterpret_cast<const double*>(px.peer[px.rank] + kXPoolOff) + (size_t)par * NSB_MAX_PEERS * px.max_n;
+      // receive: each thread polls the words it owns and leaves the value in this rank's plain copy of the pool
+      double* plain = reinterpret_cast<double*>(px.peer[px.rank] + peer_pool_plain_off(px.max_n));
+      for (int i = threadIdx.x; i < n * px.world; i += blockDim.x) {
+        const int r = i / n, j = i - r * n;
+        plain[(size_t)r * px.max_n + j] = ll_get(px.peer[px.rank] + kXPoolOff + (((size_t)par * NSB_MAX_PEERS + r) * px.max_n + j) * 16, seq, px, 1);
+      }
+      peer_end(px, 1, seq);                                  // (its barrier also makes `plain` visible to the whole CTA)
+      mp = plain;
       np = n * px.world; pool_pitch = px.max_n;
     }
-    auto pool_at = [&](int i) { return pool_pitch ? __ldcg(mp + (size_t)(i / n) * pool_pitch + (i % n)) : mp[i]; };
+    auto pool_at = [&](int i) { return pool_pitch ? mp[(size_t)(i / n) * pool_pitch + (i % n)] : mp[i]; };
     const int k = (np - 1) / 2;
-    if (np <= kMedianDirect) {
-      // small pools (a tracking batch is 200 rays): direct rank counting from shared memory, no serial passes
-      for (int i = threadIdx.x; i < np; i += blockDim.x) keys[i] = (unsigned long long)__double_as_longlong(pool_at(i));
-      __syncthreads();
-      for (int i = threadIdx.x; i < np; i += blockDim.x) {
+    // the key of rank `want` among keys[0 .. cnt): direct rank counting from shared memory, no serial passes
+    auto select_direct = [&](int cnt, int want) {
+      for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
         const unsigned long long key = keys[i];
         int less = 0, eq = 0;
-        for (int j = 0; j < np; j++) { const unsigned long long o = keys[j]; less += o < key ? 1 : 0; eq += o == key ? 1 : 0; }
-        if (less <= k && k < less + eq) med_key = key;     // every thread that qualifies writes the same value
+        for (int j = 0; j < cnt; j++) { const unsigned long long o = keys[j]; less += o < key ? 1 : 0; eq += o == key ? 1 : 0; }
+        if (less <= want && want < less + eq) med_key = key;     // every thread that qualifies writes the same value
       }
       __syncthreads();
+    };
+    if (np <= kMedianDirect) {
+      // small pools (a tracking batch is 200 rays)
+      for (int i = threadIdx.x; i < np; i += blockDim.x) keys[i] = (unsigned long long)__double_as_longlong(pool_at(i));
+      __syncthreads();
+      select_direct(np, k);
     } else {
-      // radix select, 8 bits per pass (8 passes, 256-bin shared histogram)
+      // radix select, 8 bits per pass over a 256-bin shared histogram -- until the bin that holds the wanted rank is small enough for the direct
+      // count (residuals spread over many exponents: normally after the second pass), at most 8 passes
       unsigned long long prefix = 0ull;
       int kk = k;
+      bool direct = false;
       for (int shift = 56; shift >= 0; shift -= 8) {
         for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
         __syncthreads();
@@ -192,10 +220,26 @@ __device__ __forceinline__ void tracking_seeds_body(const double* depth, const d
         }
         prefix |= (unsigned long long)sel[0] << shift;
         kk -= sel[1];
+        const int cnt = hist[sel[0]];                        // keys that share the prefix (CTA-uniform)
+        __syncthreads();
+        if (shift > 0 && cnt <= kMedianDirect) {
+          if (threadIdx.x == 0) sel[0] = 0;
+          __syncthreads();
+          const unsigned long long maskall = ~0ull << shift;
+          for (int i = threadIdx.x; i < np; i += blockDim.x) {
+            const unsigned long long key = (unsigned long long)__double_as_longlong(pool_at(i));
+            if ((key & maskall) == prefix) keys[atomicAdd(&sel[0], 1)] = key;
+          }
+          __syncthreads();
+          select_direct(cnt, kk);
+          direct = true;
+          break;
+        }
+      }
+      if (!direct) {
+        if (threadIdx.x == 0) med_key = prefix;
         __syncthreads();
       }
-      if (threadIdx.x == 0) med_key = prefix;
-      __syncthreads();
     }
     if (threadIdx.x == 0) med_s = __longlong_as_double((long long)med_key);
     __syncthreads();

@@ -111,24 +111,31 @@ struct Loader {
   int q, q1;          // current / end decoder slot
   int k;              // unit index inside decoder q
   uint32_t loaded;    // units issued so far (global sequence number of the next one)
-  bool bwd;
+  int mode;           // 0 = forward (3xTF32 units), 1 = backward, 2 = forward with FP16 hi|lo units (op3_*)
 };
 __device__ __forceinline__ bool loader_done(const Loader& L) { return L.q >= L.q1; }
 __device__ __forceinline__ void loader_issue(Loader& L, const TileSmem& t) {
   const int lv = L.P->dec[L.q];
-  const float* img = L.P->in.packed[lv] + (L.bwd ? op2_bwd_offset(lv) : op2_fwd_offset(lv));
-  int off, floats;
-  if (L.bwd) { off = L.k * 2048; floats = 2048; }
-  else {
+  const float* img = L.P->in.packed[lv] + (L.mode == 1 ? op2_bwd_offset(lv) : L.mode == 2 ? op3_fwd_offset(lv) : op2_fwd_offset(lv));
+  int off, floats, n_units;
+  if (L.mode == 1) { off = L.k * 2048; floats = 2048; n_units = bwd_units(lv); }
+  else if (L.mode == 2) {
+    const int nfc = op3_fc_units(lv), nl0 = op_nblk(lv);
+    if (L.k < nfc) { off = L.k * 2560; floats = 2560; }
+    else if (L.k < nfc + nl0) { off = nfc * 2560 + (L.k - nfc) * 2048; floats = 2048; }
+    else { off = nfc * 2560 + nl0 * 2048 + (L.k - nfc - nl0) * 1024; floats = 1024; }
+    n_units = op3_fwd_units(lv);
+  } else {
     const int nfc = op2_fc_units(lv);
     if (L.k < nfc) { off = L.k * 2560; floats = 2560; } else { off = nfc * 2560 + (L.k - nfc) * 2048; floats = 2048; }
+    n_units = fwd_units(lv);
   }
   const int slot = L.loaded & (kSlots - 1);
   uint64_t* bar = t.bars + B_FULL + slot;
   mbar_expect_tx(bar, (uint32_t)floats * 4u);
   tma_bulk_g2s(t.ring + slot * t.slot_floats, img + off, (uint32_t)floats * 4u, bar);
   L.loaded++;
-  if (++L.k == (L.bwd ? bwd_units(lv) : fwd_units(lv))) { L.k = 0; L.q++; }
+  if (++L.k == n_units) { L.k = 0; L.q++; }
 }
 // refill one slot if a unit is pending and its slot's previous occupant has been issued (blocking on that unit's MMAs)
 __device__ __forceinline__ bool loader_refill(Loader& L, const TileSmem& t, uint32_t issued) {
@@ -216,6 +223,72 @@ __device__ __forceinline__ void mma_unit(Issuer& I, const TileSmem& t, uint32_t 
   acc = 1u;
 }
 
+// ---- FP16 hi|lo forward (option fwd_f16) ------------------------------------------------------------------------------------------------------
+// x = hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significant bits for |x| in [2^-3, 65504], an absolute error <= 2^-25 below (lo goes
+// subnormal) -- the forward's operands (features, sin embedding, ReLU outputs, weights) are O(1) values, far inside the 1e-4 tolerance of the
+// path.  kind::f16 contracts K = 16 per instruction: half the MMAs and half the shared-memory operand traffic of the 3xTF32 forward (which is
+// what bounds the MMA phases: every N <= 64 MMA re-reads its [128 x K] A slice).  Conversions saturate (cvt.rn.satfinite): an operand beyond
+// the fp16 range degrades instead of producing Inf/NaN.  The backward keeps 3xTF32 (gradients span far more than fp16's exponent range).
+// 16-bit canonical K-major tile of width K halves: [row/8][k/8][row%8][k%8]; hi tile, then lo tile.
+__device__ __forceinline__ uint32_t cvt_h2(float lo_elem, float hi_elem) {          // {fp16(lo_elem), fp16(hi_elem)} packed, saturating
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+__device__ __forceinline__ void split_h2(float x, float y, uint32_t& h, uint32_t& l) {
+  h = cvt_h2(x, y);
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h));
+  l = cvt_h2(x - f.x, y - f.y);
+}
+// four consecutive features (4-wide chunk kq of a 32-wide tile) of row r: 8 bytes in the hi tile, 8 in the lo tile
+__device__ __forceinline__ void put4_h(float* tile, int r, int kq, const float4 v) {
+  unsigned char* hi = reinterpret_cast<unsigned char*>(tile) + (((r >> 3) * 4 + (kq >> 1)) * 128 + (r & 7) * 16 + (kq & 1) * 8);
+  uint2 h, l;
+  split_h2(v.x, v.y, h.x, l.x); split_h2(v.z, v.w, h.y, l.y);
+  *reinterpret_cast<uint2*>(hi) = h;
+  *reinterpret_cast<uint2*>(hi + TM * 32 * 2) = l;
+}
+// this thread's 16 features (column group cg) of row r: two 16-byte chunks per tile
+__device__ __forceinline__ void put16_h(float* tile, int r, int cg, const float (&v)[kCW]) {
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    unsigned char* hi = reinterpret_cast<unsigned char*>(tile) + (((r >> 3) * 4 + 2 * cg + c) * 128 + (r & 7) * 16);
+    uint4 h, l;
+    split_h2(v[8 * c], v[8 * c + 1], h.x, l.x); split_h2(v[8 * c + 2], v[8 * c + 3], h.y, l.y);
+    split_h2(v[8 * c + 4], v[8 * c + 5], h.z, l.z); split_h2(v[8 * c + 6], v[8 * c + 7], h.w, l.w);
+    *reinterpret_cast<uint4*>(hi) = h;
+    *reinterpret_cast<uint4*>(hi + TM * 32 * 2) = l;
+  }
+}
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D[128 x N] (+)= A[:, ka0 .. ka0 + 16 KSTEPS) * B^T with the FP16 split.  A: [128 x 32] halves hi|lo; B: unit [N x KB] halves hi|lo.
+// (one k-step = 16 halves = two 128-byte core matrices = +16 in the start-address field, as for tf32)
+template <int KSTEPS>
+__device__ __forceinline__ void mma_unit_h(Issuer& I, const TileSmem& t, uint32_t d_tmem, const float* a, int ka0, const float* b, int N, int KB, uint32_t& acc,
+                                           uint64_t* done = nullptr) {
+  const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);      // D = F32, A = B = F16, both K-major
+  const uint64_t ah = tc::make_desc(a + (ka0 >> 3) * 32, 128u, 4u * 128u);
+  const uint64_t bh = tc::make_desc(b, 128u, (uint32_t)(KB >> 3) * 128u);
+  const uint64_t al = ah + (uint64_t)((TM * 32 * 2) >> 4);
+  const uint64_t bl = bh + (uint64_t)((N * KB * 2) >> 4);
+  if (elect_one()) {
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ks++) {
+      mma_f16(d_tmem, al + 16u * ks, bh + 16u * ks, idesc, ks == 0 ? acc : 1u);
+      mma_f16(d_tmem, ah + 16u * ks, bl + 16u * ks, idesc, 1u);
+      mma_f16(d_tmem, ah + 16u * ks, bh + 16u * ks, idesc, 1u);
+    }
+    tc::mma_commit(t.bars + B_EMPTY + (I.issued & (kSlots - 1)));
+    if (done != nullptr) tc::mma_commit(done);
+  }
+  I.issued++;
+  acc = 1u;
+}
+
 // ---- epilogue-side helpers -------------------------------------------------------------------------------------------------------
 // operands of this thread are written: make them visible to the async proxy, order earlier TMEM reads, arrive
 __device__ __forceinline__ void publish(const TileSmem& t, int b) {
@@ -253,6 +326,7 @@ __device__ __forceinline__ void gather_issue(const nsb_grid& g, const float xn[3
 #pragma unroll
   for (int k = 0; k < 8; k++) gp.w[k] = __fmul_rn(wxy[k & 3], (k & 4) ? t.w1[2] : t.w0[2]);      // == tri_weight(t, k)
 }
+template <bool H16 = false>
 __device__ __forceinline__ void gather_consume(float* c_hi, float* c_lo, int qd, int lane, const GatherPass& gp) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -260,11 +334,12 @@ __device__ __forceinline__ void gather_consume(float* c_hi, float* c_lo, int qd,
     const float w = gp.w[k];
     acc.x = fmaf(gp.v[k].x, w, acc.x); acc.y = fmaf(gp.v[k].y, w, acc.y); acc.z = fmaf(gp.v[k].z, w, acc.z); acc.w = fmaf(gp.v[k].w, w, acc.w);
   }
-  tc::put4(c_hi, c_lo, qd * 32 + gp.src_lane, lane & 7, 32, acc);
+  if (H16) put4_h(c_hi, qd * 32 + gp.src_lane, lane & 7, acc);
+  else tc::put4(c_hi, c_lo, qd * 32 + gp.src_lane, lane & 7, 32, acc);
 }
 // (the strided NCDHW form -- four scalar loads with 64-bit strides per corner -- is a separate, out-of-line copy: inlined next to the channels-last
 // form at every unrolled corner it made up a third of the forward kernel's 19 k instructions, and instruction fetch shows up in the stall samples)
-template <bool FAST>
+template <bool FAST, bool H16 = false>
 __device__ __forceinline__ void gather_tile_t(const nsb_grid& g, float* c_hi, const float xn[3], int warp, int lane) {
   float* c_lo = c_hi + TM * 32;
   const int qd = warp & 3, it0 = (warp >> 2) * 4;
@@ -272,26 +347,29 @@ __device__ __forceinline__ void gather_tile_t(const nsb_grid& g, float* c_hi, co
     GatherPass A, B;
     gather_issue<true>(g, xn, it0, lane, A);
     gather_issue<true>(g, xn, it0 + 1, lane, B);
-    gather_consume(c_hi, c_lo, qd, lane, A);
+    gather_consume<H16>(c_hi, c_lo, qd, lane, A);
     gather_issue<true>(g, xn, it0 + 2, lane, A);
-    gather_consume(c_hi, c_lo, qd, lane, B);
+    gather_consume<H16>(c_hi, c_lo, qd, lane, B);
     gather_issue<true>(g, xn, it0 + 3, lane, B);
-    gather_consume(c_hi, c_lo, qd, lane, A);
-    gather_consume(c_hi, c_lo, qd, lane, B);
+    gather_consume<H16>(c_hi, c_lo, qd, lane, A);
+    gather_consume<H16>(c_hi, c_lo, qd, lane, B);
   } else {
 #pragma unroll 1
-    for (int it = it0; it < it0 + 4; it++) { GatherPass A; gather_issue<false>(g, xn, it, lane, A); gather_consume(c_hi, c_lo, qd, lane, A); }
+    for (int it = it0; it < it0 + 4; it++) { GatherPass A; gather_issue<false>(g, xn, it, lane, A); gather_consume<H16>(c_hi, c_lo, qd, lane, A); }
   }
 }
+template <bool H16>
 static __device__ __noinline__ void gather_tile_strided(const nsb_grid& g, float* c_hi, float x0, float x1, float x2, int warp, int lane) {
   const float xn[3] = {x0, x1, x2};
-  gather_tile_t<false>(g, c_hi, xn, warp, lane);
+  gather_tile_t<false, H16>(g, c_hi, xn, warp, lane);
 }
+template <bool H16 = false>
 __device__ __forceinline__ void gather_tile(const nsb_grid& g, float* c_hi, const float xn[3], int warp, int lane) {
-  if (grid_fast(g)) gather_tile_t<true>(g, c_hi, xn, warp, lane);
-  else gather_tile_strided(g, c_hi, xn[0], xn[1], xn[2], warp, lane);
+  if (grid_fast(g)) gather_tile_t<true, H16>(g, c_hi, xn, warp, lane);
+  else gather_tile_strided<H16>(g, c_hi, xn[0], xn[1], xn[2], warp, lane);
 }
 // this thread's 16 features of embedding block `blk` of its point -> [128 x 32] tile
+template <bool H16 = false>
 __device__ __forceinline__ void embed_tile(float* e_hi, const float* B, const float pf[3], int row, int cg, int blk) {
   float* e_lo = e_hi + TM * 32;
 #pragma unroll
@@ -303,42 +381,62 @@ __device__ __forceinline__ void embed_tile(float* e_hi, const float* B, const fl
       float x = pf[0] * B[f]; x = fmaf(pf[1], B[kEmbPad + f], x); x = fmaf(pf[2], B[2 * kEmbPad + f], x);
       v[j] = f < kEmb ? __sinf(reduce_2pi(x)) : 0.0f;
     }
-    tc::put4(e_hi, e_lo, row, kq, 32, make_float4(v[0], v[1], v[2], v[3]));
+    if (H16) put4_h(e_hi, row, kq, make_float4(v[0], v[1], v[2], v[3]));
+    else tc::put4(e_hi, e_lo, row, kq, 32, make_float4(v[0], v[1], v[2], v[3]));
   }
 }
 
 // ---- forward: what the issuing thread (thread 0) does after the CTA published operand group I.g --------------------------------------------
 // TMEM: D1 = [0,32), D3 = [32,64) (layer 3; its skip part is accumulated while the embedding blocks are live), D2 = [64,224) (fc_c of the five layers)
+template <bool H16 = false>
 __device__ __forceinline__ void issue_fc(Issuer& I, const TileSmem& t, uint32_t tmem, int half) {      // C tile `half` -> D2 += C * Wc^T (four K = 8 units)
   const int b = I.g & 1;
   issuer_wait_operands(I, t, b, (I.g >> 1) & 1u);
-  for (int u = 0; u < 4; u++) {
-    const float* w = issuer_unit(I, t);
-    uint32_t acc = (half == 0 && u == 0) ? 0u : 1u;
-    mma_unit<1>(I, t, tmem + 64u, t.a[b], 8 * u, w, 160, 8, 0, acc, u == 3 ? t.bars + B_DONE + b : nullptr);
+  if constexpr (H16) {                                           // two [160 x 16] FP16 units
+    for (int u = 0; u < 2; u++) {
+      const float* w = issuer_unit(I, t);
+      uint32_t acc = (half == 0 && u == 0) ? 0u : 1u;
+      mma_unit_h<1>(I, t, tmem + 64u, t.a[b], 16 * u, w, 160, 16, acc, u == 1 ? t.bars + B_DONE + b : nullptr);
+    }
+  } else {
+    for (int u = 0; u < 4; u++) {
+      const float* w = issuer_unit(I, t);
+      uint32_t acc = (half == 0 && u == 0) ? 0u : 1u;
+      mma_unit<1>(I, t, tmem + 64u, t.a[b], 8 * u, w, 160, 8, 0, acc, u == 3 ? t.bars + B_DONE + b : nullptr);
+    }
   }
   I.g++;
 }
+template <bool H16 = false>
 __device__ __forceinline__ void issue_l0(Issuer& I, const TileSmem& t, uint32_t tmem, int blk) {       // [D1 | D3] += E_blk * [W0_blk; W3E_blk]^T   (coarse: E = C)
   const int b = I.g & 1;
   issuer_wait_operands(I, t, b, (I.g >> 1) & 1u);
-  for (int h = 0; h < 2; h++) {
+  if constexpr (H16) {                                           // one [64 x 32] FP16 unit
     const float* w = issuer_unit(I, t);
-    uint32_t acc = (blk == 0 && h == 0) ? 0u : 1u;
-    mma_unit<2>(I, t, tmem, t.a[b], 16 * h, w, 64, 16, 0, acc, h == 1 ? t.bars + B_DONE + b : nullptr);
+    uint32_t acc = blk == 0 ? 0u : 1u;
+    mma_unit_h<2>(I, t, tmem, t.a[b], 0, w, 64, 32, acc, t.bars + B_DONE + b);
+  } else {
+    for (int h = 0; h < 2; h++) {
+      const float* w = issuer_unit(I, t);
+      uint32_t acc = (blk == 0 && h == 0) ? 0u : 1u;
+      mma_unit<2>(I, t, tmem, t.a[b], 16 * h, w, 64, 16, 0, acc, h == 1 ? t.bars + B_DONE + b : nullptr);
+    }
   }
   I.g++;
 }
+template <bool H16 = false>
 __device__ __forceinline__ void issue_h(Issuer& I, const TileSmem& t, uint32_t tmem, int i) {          // layer i (1..4) from the H tile of layer i-1
   const int b = I.g & 1;
   issuer_wait_operands(I, t, b, (I.g >> 1) & 1u);
   const float* w = issuer_unit(I, t);
   uint32_t acc = i == 3 ? 1u : 0u;
-  mma_unit<4>(I, t, i == 3 ? tmem + 32u : tmem, t.a[b], 0, w, 32, 32, 0, acc, t.bars + B_DONE + b);
+  if (H16) mma_unit_h<2>(I, t, i == 3 ? tmem + 32u : tmem, t.a[b], 0, w, 32, 32, acc, t.bars + B_DONE + b);
+  else mma_unit<4>(I, t, i == 3 ? tmem + 32u : tmem, t.a[b], 0, w, 32, 32, 0, acc, t.bars + B_DONE + b);
   I.g++;
 }
 
 // ---- forward of one decoder: epilogue side.  n = operand-group counter (same sequence as the issuer's).  out[] = decoder outputs of this row.
+template <bool H16 = false>
 __device__ __forceinline__ void epi_forward(const KParams& P, const TileSmem& t, Issuer& I, int lv, const PointGeom& G, uint32_t tmem, uint32_t& n, int hb, uint32_t hdr_parity,
                                             float (&out)[4], uint32_t* __restrict__ gmask, float* acts = nullptr) {
   const int row = threadIdx.x & (TM - 1), cg = threadIdx.x >> 7, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -352,10 +450,10 @@ __device__ __forceinline__ void epi_forward(const KParams& P, const TileSmem& t,
     for (int half = 0; half < cd / 32; half++) {
       if (n >= 2) wait_group(t, n - 2);
       if (threadIdx.x == 0) loader_top_up(I.L, t, I.issued);     // request whatever fits the ring before the long gather
-      gather_tile(P.in.grid[half == 0 ? lv : 1], t.a[n & 1], G.xn, warp, lane);
+      gather_tile<H16>(P.in.grid[half == 0 ? lv : 1], t.a[n & 1], G.xn, warp, lane);
       NSB_PH(1);
       publish(t, n & 1); n++;
-      if (t0) issue_fc(I, t, tmem, half);
+      if (t0) issue_fc<H16>(I, t, tmem, half);
       NSB_PH(2);
     }
     mbar_wait_b(t.bars + B_HDR + hb, hdr_parity);
@@ -363,17 +461,17 @@ __device__ __forceinline__ void epi_forward(const KParams& P, const TileSmem& t,
       if (n >= 2) wait_group(t, n - 2);
       if (threadIdx.x == 0) loader_top_up(I.L, t, I.issued);
       NSB_PH(6);
-      embed_tile(t.a[n & 1], hdr + 464, G.pf, row, cg, blk);
+      embed_tile<H16>(t.a[n & 1], hdr + 464, G.pf, row, cg, blk);
       NSB_PH(3);
       publish(t, n & 1); n++;
-      if (t0) issue_l0(I, t, tmem, blk);
+      if (t0) issue_l0<H16>(I, t, tmem, blk);
       NSB_PH(4);
     }
   } else {
     if (n >= 2) wait_group(t, n - 2);
-    gather_tile(P.in.grid[0], t.a[n & 1], G.xnc, warp, lane);
+    gather_tile<H16>(P.in.grid[0], t.a[n & 1], G.xnc, warp, lane);
     publish(t, n & 1); n++;
-    if (t0) issue_l0(I, t, tmem, 0);
+    if (t0) issue_l0<H16>(I, t, tmem, 0);
     mbar_wait_b(t.bars + B_HDR + hb, hdr_parity);
   }
   float h[kCW];
@@ -400,11 +498,14 @@ __device__ __forceinline__ void epi_forward(const KParams& P, const TileSmem& t,
     }
     if (i == 4) break;
     float* h_hi = t.a[n & 1];
+    if (H16) put16_h(h_hi, row, cg, h);
+    else {
 #pragma unroll
-    for (int k = 0; k < kKQ; k++) tc::put4(h_hi, h_hi + TM * 32, row, kKQ * cg + k, 32, make_float4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]));
+      for (int k = 0; k < kKQ; k++) tc::put4(h_hi, h_hi + TM * 32, row, kKQ * cg + k, 32, make_float4(h[4 * k], h[4 * k + 1], h[4 * k + 2], h[4 * k + 3]));
+    }
     NSB_PH(8);
     publish(t, n & 1); n++;
-    if (t0) issue_h(I, t, tmem, i + 1);
+    if (t0) issue_h<H16>(I, t, tmem, i + 1);
     NSB_PH(9);
   }
   NSB_PH(8);
@@ -881,7 +982,8 @@ __device__ __forceinline__ void composite_ray(const KParams& P, int ray, int lan
 // ================================================================================================================================
 // forward kernel
 // ================================================================================================================================
-__global__ void __launch_bounds__(tl::kThreads, 2) render_fwd_tile_kernel(const __grid_constant__ KParams P) {
+template <bool H16>
+__device__ __forceinline__ void render_fwd_tile_body(const KParams& P) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   using namespace tl;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -907,7 +1009,7 @@ __global__ void __launch_bounds__(tl::kThreads, 2) render_fwd_tile_kernel(const 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   NSB_PH_RESET();
-  Issuer I; I.L.P = &P; I.L.q = q0; I.L.q1 = q1; I.L.k = 0; I.L.loaded = 0; I.L.bwd = false; I.issued = 0; I.g = 0;
+  Issuer I; I.L.P = &P; I.L.q = q0; I.L.q1 = q1; I.L.k = 0; I.L.loaded = 0; I.L.mode = H16 ? 2 : 0; I.issued = 0; I.g = 0;
   if (tid == 0) {
     for (int i = 0; i < kNumBars; i++) mbar_init(t.bars + i, (i == B_AREADY || i == B_AREADY + 1) ? kEpiThreads / 32 : 1);
     mbar_fence_init();
@@ -1023,7 +1125,7 @@ __global__ void __launch_bounds__(tl::kThreads, 2) render_fwd_tile_kernel(const 
       const int dq = qd - q0;
       if (tid == 0 && qd + 1 < q1) load_header(P, t, P.dec[qd + 1], (dq + 1) & 1);      // (decoder qd-1 ended with CTA barriers: its buffer is free)
       float* acts = (P.fo.acts != nullptr && lv == P.acts_lv && row < npts) ? P.fo.acts + ((gp0 + row) * 5) * 32 + kCW * cg : nullptr;
-      epi_forward(P, t, I, lv, G, tmem, n, dq & 1, (dq >> 1) & 1u, out, gm, acts);
+      epi_forward<H16>(P, t, I, lv, G, tmem, n, dq & 1, (dq >> 1) & 1u, out, gm, acts);
       if (lv == 3) { c0 = out[0]; c1 = out[1]; c2 = out[2]; } else occ += out[0];
       if (qd == 0 && cg == 0 && row < npts && P.fo.corner_idx != nullptr) {
         const nsb_grid& g = P.in.grid[lv];
@@ -1059,6 +1161,9 @@ __global__ void __launch_bounds__(tl::kThreads, 2) render_fwd_tile_kernel(const 
     }
   }
 }
+__global__ void __launch_bounds__(tl::kThreads, 2) render_fwd_tile_kernel(const __grid_constant__ KParams P) { render_fwd_tile_body<false>(P); }
+// forward with FP16 hi|lo operands (option fwd_f16; see mma_unit_h)
+__global__ void __launch_bounds__(tl::kThreads, 2) render_fwd_tile_h16_kernel(const __grid_constant__ KParams P) { render_fwd_tile_body<true>(P); }
 
 // ================================================================================================================================
 // backward kernel (input gradients: rays + grid voxels)
@@ -1105,7 +1210,7 @@ __device__ __forceinline__ void render_bwd_tile_body(const KParams& P) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   NSB_PH_RESET();
-  Issuer I; I.L.P = &P; I.L.q = q0; I.L.q1 = q1; I.L.k = 0; I.L.loaded = 0; I.L.bwd = true; I.issued = 0; I.g = 0;
+  Issuer I; I.L.P = &P; I.L.q = q0; I.L.q1 = q1; I.L.k = 0; I.L.loaded = 0; I.L.mode = 1; I.issued = 0; I.g = 0;
   if (tid == 0) {
     for (int i = 0; i < kNumBars; i++) mbar_init(t.bars + i, (i == B_AREADY || i == B_AREADY + 1) ? kEpiThreads / 32 : 1);
     if (WG) mbar_init(&s_wgbar, 1);

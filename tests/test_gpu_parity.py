@@ -445,6 +445,51 @@ def test_masked_mapping_iteration_packed_block(backend_decoder_grads):
 
 
 # ------------------------------------------------------------------------------------ more edge cases
+@pytest.mark.parametrize("stage,n_rays", [("color", 200), ("middle", 333), ("color", 1500)])
+def test_fp16_split_forward_matches_3xtf32_forward(stage, n_rays):
+    """Option fwd_f16: the forward's decoder GEMMs with FP16 hi | lo operands (tcgen05 kind::f16, K = 16 per instruction; nsb_tile.cuh mma_unit_h)
+    against the default 3xTF32 forward on the same inputs -- raw decoder outputs, rendered depth / colour, loss and the gradients that the
+    (unchanged, 3xTF32) backward derives from them.  Both sit ~1e-6 from the FP32 reference; the path's tolerance is 1e-4 (north_star)."""
+    from nice_slam_b200 import _lib
+    from nice_slam_b200.steps import IterationContext
+    L = _lib.lib()
+    sc = su.load_scenes()["room0"]
+    grids, dec_state = su.make_grids(sc, "soft"), su.load_decoders("soft")
+    renderer, c, dec = make_renderer(sc, grids, dec_state, DEV)
+    ro, rd, gd, gc = su.make_rays(sc, n_rays, seed=77 + n_rays)
+    dev_in = [t.to(DEV) for t in (ro, rd, gd, gc.float())]
+    keys = ("grid_fine", "grid_color", "grid_middle") if stage == "color" else ("grid_middle",)
+    out = {}
+    try:
+        for mode in (1, 0):
+            assert L.nsb_set_option(b"fwd_f16", mode) == 0
+            ctx = IterationContext(renderer, n_rays, stage, DEV, kind="map", grad_grids=keys)
+            for _ in range(2):
+                ctx.run(c, dec, *dev_in)
+            torch.cuda.synchronize()
+            out[mode] = dict(raw=ctx.raw.clone(), depth=ctx.depth.clone(), rgb=ctx.rgb.clone(), loss=float(ctx.loss), z=ctx.z_vals.clone(),
+                             d_o=ctx.d_rays_o.clone(), grid={k: ctx.d_grid[k].clone() for k in keys})
+    finally:
+        L.nsb_set_option(b"fwd_f16", 0)
+    a, b = out[1], out[0]
+    assert torch.equal(a["z"], b["z"])                                # sampling does not depend on the decoder arithmetic
+    assert torch.isfinite(a["raw"]).all()
+    assert float((a["raw"] - b["raw"]).abs().max()) > 0               # the option took effect (another arithmetic, not the same kernel)
+    assert rel(a["raw"], b["raw"]) < 1e-5
+    assert rel(a["depth"], b["depth"]) < 1e-5 and rel(a["rgb"], b["rgb"]) < 1e-5
+    assert abs(a["loss"] - b["loss"]) <= 1e-5 * abs(b["loss"])
+    # gradients: the L1 losses make a ray whose residual sits within ~1e-6 of zero flip the sign of its whole gradient between two arithmetics
+    # (a knife edge of the loss, not an error): allow a couple of such rays, everything else must agree
+    scale = float(b["d_o"].abs().max())
+    flipped = int(((a["d_o"] - b["d_o"]).abs().amax(dim=1) > 1e-4 * scale).sum())
+    assert flipped <= max(2, n_rays // 500), flipped
+    for k in keys:
+        if flipped == 0:
+            assert rel(a["grid"][k], b["grid"][k]) < 1e-4, k
+        else:
+            assert l2rel(a["grid"][k], b["grid"][k]) < 0.1 * flipped, k
+
+
 @pytest.mark.parametrize("n_rays", [96, 437, 1200])
 def test_tensor_core_weight_gradients_match_fp32_pass_and_oracle(n_rays):
     """Colour-decoder weight gradients of a mapping iteration (src/Mapper.py:339-341,503): the tensor-core contraction over the points of a tile

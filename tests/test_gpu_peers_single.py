@@ -25,7 +25,7 @@ def _peers(rank, world, bufs, counters, max_rays):
     return p
 
 
-@pytest.mark.parametrize("world,n", [(2, 150), (2, 400), (3, 64)])
+@pytest.mark.parametrize("world,n", [(2, 150), (2, 400), (3, 64), (4, 300)])
 def test_peer_exchange_kernels_two_ranks_on_one_gpu(world, n):
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")

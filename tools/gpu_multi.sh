@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/${tag}_smi.txt
 timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_gpu_peers_single.py -q -m gpu 2>&1 | tail -30 > gpurun_out/${tag}_tests.log; echo "pytest exit ${PIPESTATUS[0]}" >> gpurun_out/${tag}_tests.log; tail -6 gpurun_out/${tag}_tests.log
-for k in 1 $n; do
+for k in ${SKIP1:+} $([ -n "$SKIP1" ] || echo 1) $n; do
   if [ $k -eq 1 ]; then
     timeout 900 python bench.py --gpus 1 --steps 300 --warmup 10 > gpurun_out/${tag}_bench_n1.json 2> gpurun_out/${tag}_bench_n1.err
   else
