@@ -611,7 +611,7 @@ def run_native(args):
             "clocks": clocks,
             "e2e": {"value": rays / (e2e_ms / args.steps * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": ctx.h2d_bytes,
                     "d2h_bytes_per_step": ctx.d2h_bytes if sharded is None else 13 * 8, "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": (2 if sharded is None else (3 if sharded.fused else (5 if sharded.peers is not None else 6))) * args.steps,
+            "gpu_launches": (2 if sharded is None else (2 if sharded.fused else (5 if sharded.peers is not None else 6))) * args.steps,
             "extra": {"l2_warm_ms_per_step": warm_ms / args.steps, "l2_warm_rays_per_s": rays / (warm_ms / args.steps * 1e-3),
                       "mapping_sharded_masked": map_sharded, "mapping_other_scenes": scenes, "fwd_f16_option": f16_opt}}
     if bwd_ms:

@@ -29,6 +29,7 @@ extern "C" {
 #define NSB_C_DIM 32              /* feature channels per grid     (configs/nice_slam.yaml:113) */
 #define NSB_HIDDEN 32             /* decoder width                 (src/conv_onet/models/decoder.py:293) */
 #define NSB_EMBED 93              /* Gaussian-Fourier mapping size (src/conv_onet/models/decoder.py:133) */
+#define NSB_MAX_BATCH_DEPTHS 8192 /* nsb_render_inputs.n_batch: every CTA reduces the list itself (L2-resident) */
 #define NSB_INLINE_MAX_RAYS 1024  /* up to this batch size nsb_render_inputs.depth_max may be NULL: the kernels reduce gt_depth themselves */
 #define NSB_MAX_SAMPLES 256       /* N_samples + N_surface per ray supported by the kernels */
 
@@ -114,6 +115,10 @@ typedef struct {
   const double* t_surface;       /* device f64[n_surface]  = torch.linspace(0,1,n_surface).double() */
   nsb_grid grid[4];              /* indexed by nsb_level; only the stage's grids are read */
   const float* packed[4];        /* packed decoders (nsb_pack_decoders) */
+  const float* gt_depth_batch;   /* optional device f32[n_batch]: the sensor depths of the WHOLE batch this call renders a shard of (a ray-sharded
+                                    tracker splits a pixel list every rank knows).  When given (depth_max NULL), the batch depth maxima
+                                    (Renderer.py:109,144) are reduced over this list inside the kernel: no separate launch, no exchange. */
+  int32_t n_batch;               /* 1 .. NSB_MAX_BATCH_DEPTHS */
 } nsb_render_inputs;
 
 typedef struct {

@@ -31,7 +31,7 @@ class RenderInputs(C.Structure):
                 ("bound", C.c_double * 6), ("coarse_bound", C.c_double * 6),
                 ("rays_o", C.c_void_p), ("rays_d", C.c_void_p), ("gt_depth", C.c_void_p), ("depth_max", C.c_void_p),
                 ("t_uniform", C.c_void_p), ("t_surface", C.c_void_p),
-                ("grid", Grid * 4), ("packed", C.c_void_p * 4)]
+                ("grid", Grid * 4), ("packed", C.c_void_p * 4), ("gt_depth_batch", C.c_void_p), ("n_batch", C.c_int32)]
 
 
 class ForwardOutputs(C.Structure):

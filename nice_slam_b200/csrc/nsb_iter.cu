@@ -38,7 +38,7 @@ static int forward_part(const nsb_render_inputs* in, const nsb_iteration_buffers
     return render_forward_fused(in2, &fo, fs, stream);
   }
   in2->depth_max = nullptr;
-  if (in->gt_depth && in->n_rays > NSB_INLINE_MAX_RAYS) {          // small batches: the render kernel reduces gt_depth itself
+  if (in->gt_depth && in->gt_depth_batch == nullptr && in->n_rays > NSB_INLINE_MAX_RAYS) {          // small batches: the render kernel reduces gt_depth itself
     if ((rc = nsb_batch_max_depth(in->gt_depth, in->n_rays, b->depth_max, stream))) return rc;
     in2->depth_max = b->depth_max;
   }

@@ -327,14 +327,17 @@ __device__ __forceinline__ void fwd_sample_sort(const KParams& P, const Smem& sm
         // small batches: every CTA reduces the batch's sensor depths itself (n_rays <= kInlineMaxRays floats from L2) instead of waiting
         // for a separate single-CTA kernel: torch.max(gt_depth) and torch.max(gt_depth*1.2) = fl(1.2f * max)  (Renderer.py:109,144)
         __shared__ float s_max[32];
+        const bool whole = P.in.gt_depth_batch != nullptr;        // the depths of the whole (sharded) batch are known here: no exchange
+        const float* gsrc = whole ? P.in.gt_depth_batch : P.in.gt_depth;
+        const int gn = whole ? P.in.n_batch : P.in.n_rays;
         float m = -INFINITY;
-        for (int i = threadIdx.x; i < P.in.n_rays; i += blockDim.x) m = fmaxf(m, __ldg(P.in.gt_depth + i));
+        for (int i = threadIdx.x; i < gn; i += blockDim.x) m = fmaxf(m, __ldg(gsrc + i));
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
         __syncthreads();
         m = -INFINITY;
         for (int w = 0; w < (int)(blockDim.x >> 5); w++) m = fmaxf(m, s_max[w]);
-        if (P.fs.px.world > 1) { __shared__ uint32_t s_seq; m = peer_max_all_ctas(P.fs.px, m, &s_seq); }      // sharded batch: MAX over the ranks' shards
+        if (P.fs.px.world > 1 && !whole) { __shared__ uint32_t s_seq; m = peer_max_all_ctas(P.fs.px, m, &s_seq); }      // sharded batch: MAX over the ranks' shards
         gtmax = m; gtmax12 = __fmul_rn(m, 1.2f);
       }
     }
@@ -433,7 +436,7 @@ __device__ __forceinline__ void fused_seeds_tail(const KParams& P, int n_partici
     // (sharded batch: the residual pool of the median is exchanged inside; then every CTA of this grid is past the depth-max exchange)
     tracking_seeds_body(P.fo.depth, P.fo.var, P.fo.rgb, P.in.gt_depth, static_cast<const double*>(P.fs.gt_rgb), P.in.n_rays, P.fs.w_color,
                         P.fs.handle_dynamic, P.fs.use_color, nullptr, 0, P.fs.g_depth, P.fs.g_rgb, P.fs.loss, P.fs.res, P.fs.px, scratch);
-    if (P.fs.px.world > 1 && P.in.depth_max == nullptr && threadIdx.x == 0) peer_advance(P.fs.px, 0);
+    if (P.fs.px.world > 1 && P.in.depth_max == nullptr && P.in.gt_depth_batch == nullptr && threadIdx.x == 0) peer_advance(P.fs.px, 0);
   } else {
     mapping_seeds_body(P.fo.depth, P.fo.rgb, P.fs.gt_depth_loss, static_cast<const float*>(P.fs.gt_rgb), P.in.n_rays, P.fs.w_color, P.fs.use_color,
                        P.fs.g_depth, P.fs.g_rgb, P.fs.loss, scratch);
@@ -935,7 +938,9 @@ static int validate_inputs(const nsb_render_inputs* in, bool need_rays) {
     if (in->n_rays < 0) { set_error("n_rays < 0"); return NSB_ERR_ARG; }
     if (in->n_rays > 0 && (!in->rays_o || !in->rays_d)) { set_error("rays_o / rays_d are NULL"); return NSB_ERR_ARG; }
     if (in->n_samples < 1 || !in->t_uniform) { set_error("n_samples < 1 or t_uniform NULL"); return NSB_ERR_ARG; }
-    if (in->gt_depth && !in->depth_max && in->n_rays > NSB_INLINE_MAX_RAYS) {
+    if (in->gt_depth_batch && (!in->gt_depth || in->n_batch < 1 || in->n_batch > NSB_MAX_BATCH_DEPTHS)) {
+      set_error("gt_depth_batch needs gt_depth and 1 <= n_batch <= %d (got %d)", NSB_MAX_BATCH_DEPTHS, in->n_batch); return NSB_ERR_ARG; }
+    if (in->gt_depth && !in->depth_max && !in->gt_depth_batch && in->n_rays > NSB_INLINE_MAX_RAYS) {
       set_error("gt_depth given without depth_max: batches of more than %d rays need nsb_batch_max_depth", NSB_INLINE_MAX_RAYS); return NSB_ERR_ARG; }
   }
   int dec[3]; const int nd = stage_decoders(in->stage, dec);

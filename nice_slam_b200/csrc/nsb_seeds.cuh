@@ -175,8 +175,27 @@ __device__ __forceinline__ void tracking_seeds_body(const double* depth, const d
     }
     auto pool_at = [&](int i) { return pool_pitch ? mp[(size_t)(i / n) * pool_pitch + (i % n)] : mp[i]; };
     const int k = (np - 1) / 2;
-    // the key of rank `want` among keys[0 .. cnt): direct rank counting from shared memory, no serial passes
+    // the key of rank `want` among keys[0 .. cnt), cnt <= kMedianDirect: direct rank counting from shared memory (no serial passes) or a sort
     auto select_direct = [&](int cnt, int want) {
+      if (cnt > 256) {
+        // more than one key per thread: bitonic sort in shared memory (45 compare-exchange stages for 512 keys) beats cnt^2 / 256 comparisons.
+        // Padding with ~0 sorts behind every key (NaN patterns included), so the key of rank `want` is simply keys[want].
+        int m = 512;                                             // == kMedianDirect (capacity of keys[])
+        for (int i = cnt + threadIdx.x; i < m; i += blockDim.x) keys[i] = ~0ull;
+        __syncthreads();
+        for (int k2 = 2; k2 <= m; k2 <<= 1)
+          for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < m / 2; t += blockDim.x) {
+              const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+              const unsigned long long x = keys[i], y = keys[i | j];
+              if ((x > y) == ((i & k2) == 0)) { keys[i] = y; keys[i | j] = x; }
+            }
+            __syncthreads();
+          }
+        if (threadIdx.x == 0) med_key = keys[want];
+        __syncthreads();
+        return;
+      }
       for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
         const unsigned long long key = keys[i];
         int less = 0, eq = 0;

@@ -1030,14 +1030,17 @@ __device__ __forceinline__ void render_fwd_tile_body(const KParams& P) {
     if (P.has_gt) {
       if (P.in.depth_max != nullptr) { gtmax = P.in.depth_max[0]; gtmax12 = P.in.depth_max[1]; }
       else {                                                      // small batches: every CTA reduces the sensor depths itself (Renderer.py:109,144)
+        const bool whole = P.in.gt_depth_batch != nullptr;        // the depths of the whole (sharded) batch are known here: no exchange
+        const float* gsrc = whole ? P.in.gt_depth_batch : P.in.gt_depth;
+        const int gn = whole ? P.in.n_batch : P.in.n_rays;
         float m = -INFINITY;
-        for (int i = tid; i < P.in.n_rays; i += kThreads) m = fmaxf(m, __ldg(P.in.gt_depth + i));
+        for (int i = tid; i < gn; i += kThreads) m = fmaxf(m, __ldg(gsrc + i));
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         if (lane == 0) s_max[warp] = m;
         __syncthreads();
         m = -INFINITY;
         for (int w = 0; w < kThreads / 32; w++) m = fmaxf(m, s_max[w]);
-        if (P.fs.px.world > 1) m = peer_max_all_ctas(P.fs.px, m, &s_seq);      // sharded batch: MAX over the ranks' shards (Renderer.py:109,144)
+        if (P.fs.px.world > 1 && !whole) m = peer_max_all_ctas(P.fs.px, m, &s_seq);      // sharded batch: MAX over the ranks' shards (Renderer.py:109,144)
         gtmax = m; gtmax12 = __fmul_rn(m, 1.2f);
       }
     }
@@ -1154,7 +1157,7 @@ __device__ __forceinline__ void render_fwd_tile_body(const KParams& P) {
     if (P.fs.kind == 1) {
       tracking_seeds_body(P.fo.depth, P.fo.var, P.fo.rgb, P.in.gt_depth, static_cast<const double*>(P.fs.gt_rgb), P.in.n_rays, P.fs.w_color,
                           P.fs.handle_dynamic, P.fs.use_color, nullptr, 0, P.fs.g_depth, P.fs.g_rgb, P.fs.loss, P.fs.res, P.fs.px, smem_raw);
-      if (P.fs.px.world > 1 && P.in.depth_max == nullptr && tid == 0) peer_advance(P.fs.px, 0);      // every CTA is past the depth-max exchange
+      if (P.fs.px.world > 1 && P.in.depth_max == nullptr && P.in.gt_depth_batch == nullptr && tid == 0) peer_advance(P.fs.px, 0);      // every CTA is past the depth-max exchange
     } else {
       mapping_seeds_body(P.fo.depth, P.fo.rgb, P.fs.gt_depth_loss, static_cast<const float*>(P.fs.gt_rgb), P.in.n_rays, P.fs.w_color, P.fs.use_color,
                          P.fs.g_depth, P.fs.g_rgb, P.fs.loss, smem_raw);

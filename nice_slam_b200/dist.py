@@ -11,6 +11,9 @@ import torch
 import torch.distributed as dist
 
 
+MAX_BATCH_DEPTHS = 8192          # NSB_MAX_BATCH_DEPTHS (include/nice_slam_b200.h)
+
+
 def world():
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
@@ -157,11 +160,13 @@ class ShardedTrackingIteration:
             bw = p["bw"]
             bw.pose_dirs, bw.d_c2w, bw.pose_counter = p["dirs"].data_ptr(), x.d_c2w.data_ptr(), x.pose_counter.data_ptr()
             inp = p["inp"]
-            if p["ggd"] is not None:                                   # maxima of the full batch, known locally: no exchange before sampling
-                _lib.check(L.nsb_batch_max_depth(_VP(p["ggd"].data_ptr()), p["ggd"].numel(), _VP(x.depth_max.data_ptr()), st), "nsb_batch_max_depth")
-                inp.depth_max = x.depth_max.data_ptr()
-            else:
-                inp.depth_max = None                                   # reduced + exchanged inside the forward kernel
+            inp.depth_max = None                                       # shard maxima reduced + exchanged inside the forward kernel ...
+            if p["ggd"] is not None:                                   # ... or, the full batch's depths known locally: reduced there, no exchange
+                if p["ggd"].numel() <= MAX_BATCH_DEPTHS:
+                    inp.gt_depth_batch, inp.n_batch = p["ggd"].data_ptr(), p["ggd"].numel()
+                else:
+                    _lib.check(L.nsb_batch_max_depth(_VP(p["ggd"].data_ptr()), p["ggd"].numel(), _VP(x.depth_max.data_ptr()), st), "nsb_batch_max_depth")
+                    inp.depth_max = x.depth_max.data_ptr()
             _lib.check(L.nsb_tracking_iteration_peers(C.byref(inp), C.byref(x.buf), _VP(p["gc"].data_ptr()), p["w_color"], p["hd"], p["uc"], C.byref(bw),
                                                       C.byref(self.peers.struct), _VP(self.packed.data_ptr()), st), "nsb_tracking_iteration_peers")
             return self.packed

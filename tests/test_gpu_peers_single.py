@@ -87,7 +87,7 @@ def test_peer_exchange_kernels_two_ranks_on_one_gpu(world, n):
         assert int(ctrs[0][0]) == rnd + 1 and int(ctrs[0][1]) == rnd + 1 and int(ctrs[0][2]) == rnd + 1
 
 
-@pytest.mark.parametrize("world,n,global_max", [(2, 100, False), (2, 37, False), (2, 100, True)])
+@pytest.mark.parametrize("world,n,global_max", [(2, 100, False), (2, 37, False), (2, 100, True), (2, 100, "list"), (4, 160, "list")])
 def test_two_launch_sharded_tracking_iteration_on_one_gpu(world, n, global_max):
     """nsb_tracking_iteration_peers (forward + backward launches with the exchanges inside the tile kernels) for `world` ranks on ONE GPU
     (one stream and one set of buffers per rank) == the single-rank tracking iteration over the whole batch: same depth maxima (hence
@@ -124,14 +124,17 @@ def test_two_launch_sharded_tracking_iteration_on_one_gpu(world, n, global_max):
         call, grids, _ = renderer._call(c, dec, "color", vgd, torch.device(DEV))
         t_u, t_s = _linspaces(renderer.N_samples, renderer.N_surface, torch.device(DEV))
         inp = _inputs(call, vro, vrd, None, t_u, t_s, [g.detach() for g in grids])
-        if global_max:
+        if global_max == "list":                                   # the kernel reduces the full batch's depths itself
+            gd_all = gd.to(DEV)
+            inp.gt_depth_batch, inp.n_batch = gd_all.data_ptr(), N
+        elif global_max:
             gd_all = gd.to(DEV)
             _lib.check(L.nsb_batch_max_depth(VP(gd_all.data_ptr()), N, VP(x.depth_max.data_ptr()), VP(torch.cuda.current_stream().cuda_stream)), "batch_max")
             inp.depth_max = x.depth_max.data_ptr()
         bw = x._grads(c)
         d = dirs[sl].to(DEV).contiguous()
         bw.pose_dirs, bw.d_c2w, bw.pose_counter = d.data_ptr(), x.d_c2w.data_ptr(), x.pose_counter.data_ptr()
-        ranks.append(dict(x=x, inp=inp, bw=bw, gc=vgc, dirs=d, keep=(call, grids, t_u, t_s), out=torch.zeros(13, dtype=torch.float64, device=DEV)))
+        ranks.append(dict(x=x, inp=inp, bw=bw, gc=vgc, dirs=d, keep=(call, grids, t_u, t_s, gd_all if global_max else None), out=torch.zeros(13, dtype=torch.float64, device=DEV)))
     torch.cuda.synchronize()
     for rnd in range(3):
         for r in range(world):
