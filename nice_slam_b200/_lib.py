@@ -133,6 +133,9 @@ def lib():
         wg = os.environ.get("NSB_WGRAD_TC")                  # 0 = decoder weight gradients by the FP32-FMA pass (default: tensor cores)
         if wg is not None:
             h.nsb_set_option(b"wgrad_tc", int(wg))
+        pdl = os.environ.get("NSB_PDL")                      # 0 = plain stream order between the forward and backward launches of an iteration
+        if pdl is not None:
+            h.nsb_set_option(b"pdl", int(pdl))
         f16 = os.environ.get("NSB_FWD_F16")                  # 1 = forward decoders with FP16 hi|lo operands (kind::f16) instead of 3xTF32
         if f16 is not None:
             h.nsb_set_option(b"fwd_f16", int(f16))

@@ -1002,6 +1002,7 @@ static void choose_config(int n_items, int S, int rows, bool bwd, int wbytes, in
   *smem = smem_layout(wbytes, max_pts, r, w, rows, bwd, nullptr, nullptr);
 }
 
+static int g_pdl = 0;              // iteration entry points: the backward launch as a programmatic dependent of the forward launch
 static int g_fwd_f16 = 0;          // tile-kernel forward with FP16 hi|lo operands (kind::f16, K = 16 per MMA) instead of 3xTF32; see nsb_tile.cuh mma_unit_h
 static int g_wgrad_tc = 1;         // decoder weight gradients on the tensor cores when the forward kept the layer outputs (0: FP32-FMA pass)
 static int g_mlp_backend = 0;      // 0 = auto (tensor-core forward), 1 = SIMT, 2 = tcgen05
@@ -1129,6 +1130,7 @@ using namespace nsb;
 extern "C" int nsb_set_option(const char* key, int value) {
   if (key && !strcmp(key, "wgrad_tc")) { g_wgrad_tc = value != 0; return NSB_OK; }
   if (key && !strcmp(key, "fwd_f16")) { g_fwd_f16 = value != 0; return NSB_OK; }
+  if (key && !strcmp(key, "pdl")) { g_pdl = value != 0; return NSB_OK; }
   if (key && !strcmp(key, "small_rays")) { if (value < 0) { set_error("small_rays must be >= 0"); return NSB_ERR_ARG; } g_small_rays = value; return NSB_OK; }
   if (key && !strcmp(key, "mlp_backend")) { if (value < 0 || value > 3) { set_error("mlp_backend must be 0 (auto = tile kernels), 1 (FP32-FMA), 2 (tcgen05, round-1 ray-group kernels) or 3 (tcgen05 tile kernels)"); return NSB_ERR_ARG; } g_mlp_backend = value; return NSB_OK; }
   set_error("unknown option %s", key ? key : "(null)"); return NSB_ERR_ARG;
@@ -1218,9 +1220,9 @@ extern "C" size_t nsb_backward_workspace_bytes(void) {
 }
 
 extern "C" int nsb_render_backward(const nsb_render_inputs* in, const nsb_backward_args* bw, void* stream) {
-  return nsb::render_backward_tail(in, bw, nullptr, stream);
+  return nsb::render_backward_tail(in, bw, nullptr, stream, false);
 }
-int nsb::render_backward_tail(const nsb_render_inputs* in, const nsb_backward_args* bw, const nsb::PeerTail* tail, void* stream) {
+int nsb::render_backward_tail(const nsb_render_inputs* in, const nsb_backward_args* bw, const nsb::PeerTail* tail, void* stream, bool after_forward) {
   int rc = validate_inputs(in, true); if (rc) return rc;
   if (!bw || !bw->z_vals || !bw->raw) { set_error("backward needs z_vals and raw from the forward pass"); return NSB_ERR_ARG; }
   if (in->n_rays == 0) return NSB_OK;
@@ -1281,8 +1283,21 @@ int nsb::render_backward_tail(const nsb_render_inputs* in, const nsb_backward_ar
           T.tail = *tail;
         }
         const long long grid_t = tile_count((long long)in->n_rays * T.S) * T.split;
-        render_bwd_tile_kernel<<<(unsigned)grid_t, tl::kThreads, tile_smem_bytes(true), st>>>(T);
-        if ((rc = check_cuda(cudaGetLastError(), "render_bwd_tile_kernel launch"))) return rc;
+        if (after_forward && !any_w && g_pdl) {
+          // Programmatic dependent launch: the forward kernel signals `launch_dependents` when it starts, so this grid's CTAs become resident as
+          // forward CTAs retire and run their set-up (TMEM allocation, barrier init, first weight units through TMA) under the forward's tail
+          // (ray compositing, the last CTA's loss seeds / peer exchange); `griddepcontrol.wait` in front of the first read of a forward
+          // result holds them until the forward grid has completed and flushed.
+          cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+          cfg.gridDim = dim3((unsigned)grid_t); cfg.blockDim = dim3(tl::kThreads); cfg.dynamicSmemBytes = tile_smem_bytes(true); cfg.stream = st;
+          cudaLaunchAttribute at[1];
+          at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+          cfg.attrs = at; cfg.numAttrs = 1;
+          if ((rc = check_cuda(cudaLaunchKernelEx(&cfg, render_bwd_tile_kernel, T), "render_bwd_tile_kernel launch (dependent)"))) return rc;
+        } else {
+          render_bwd_tile_kernel<<<(unsigned)grid_t, tl::kThreads, tile_smem_bytes(true), st>>>(T);
+          if ((rc = check_cuda(cudaGetLastError(), "render_bwd_tile_kernel launch"))) return rc;
+        }
       } else {
       if (tail != nullptr && tail->px.world > 1) {
         if (n_w != 0 || T.bw.pose_dirs == nullptr) { set_error("sharded backward tail needs pose_dirs and no decoder weight gradients"); return NSB_ERR_ARG; }

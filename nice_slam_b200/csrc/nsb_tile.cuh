@@ -1141,6 +1141,9 @@ __device__ __forceinline__ void render_fwd_tile_body(const KParams& P) {
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+  // the decoder chain of this item is done: a backward launched as a programmatic dependent may take the slots that free up from here on and
+  // set up under the ray compositing / loss-seed tail (triggering at kernel start made the early backward CTAs compete with the chain: slower)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   NSB_PH(14);
 
   if (points) {                                                   // Renderer.eval_points: raw with the out-of-bound override
@@ -1222,8 +1225,11 @@ __device__ __forceinline__ void render_bwd_tile_body(const KParams& P) {
     for (int i = 0; i < kSlots; i++) loader_issue(I.L, t);
   }
 
-  // ---- prologue: per ray of this tile, compositing weights and dL/d(occupancy logit) (SURVEY.md 8.1); scratch in the operand buffers
   for (int i = tid; i < TM * 3; i += kThreads) X.dp[i] = 0.0;
+  // Launched as a programmatic dependent of the forward (nsb_render.cu): everything above ran under the forward's tail; nothing the forward
+  // produces (raw, z_vals, ReLU bits, loss seeds, completion counters) is touched before the forward grid has completed.  (No-op otherwise.)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // ---- prologue: per ray of this tile, compositing weights and dL/d(occupancy logit) (SURVEY.md 8.1); scratch in the operand buffers
   for (int r = warp; r < nr; r += kThreads / 32) {
     const int ray = ray_lo + r;
     float* rw = t.a[0] + (size_t)warp * ((6 * S + 3) & ~3);       // per warp (16-byte aligned): raw [4S] | w [S] | go [S]
