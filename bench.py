@@ -235,6 +235,15 @@ def extra_workloads(sc, renderer, c, dec, dev, flush, peak):
                                             "frustum selection + colour-decoder grads) + fused Adam (3 grids in place + colour decoder)",
                                 "selected_voxels": {k: m.count for k, m in loop.masked.items()}, "ms_per_step": ms, "rays_per_s": n / (ms * 1e-3)}
     del loop
+    # the coarse mapper's joint iteration (Mapper.py:403-404,484: stage 'coarse', rendered WITHOUT the depth guide -- 32 uniform samples in the
+    # enlarged bound -- and supervised with the sensor depth), native loop on the coarse grid only
+    loopc = FusedMappingLoop(renderer, {k: v.clone() for k, v in c.items()}, copy.deepcopy(dec), su.make_pose(sc, 1), depth1.to(dev), keys=("grid_coarse",))
+    lrc = dict(decoders=0.0, coarse=0.001)
+    ms = time_steps(lambda: loopc.iteration("coarse", ro, rd, gd, gcf, lrc), 50)
+    out["mapping_loop_step_coarse_mapper"] = {"workload": "one joint iteration of the coarse mapper in the native loop, stage coarse, 996 rays x 32 uniform samples "
+                                                          "(no depth guide), compact coarse-voxel grads + fused Adam in place",
+                                              "selected_voxels": {k: m.count for k, m in loopc.masked.items()}, "ms_per_step": ms, "rays_per_s": n / (ms * 1e-3)}
+    del loopc
     # BASELINE configs[4]: ray-throughput sweep, tracking-style iteration (fwd + loss + bwd), stage color, N_surface = 16 fixed,
     # N_samples in {16, 32, 80} -> S in {32, 48, 96} samples per ray; one GPU here, --gpus N shards the 200-ray line
     from gpu_util import make_renderer

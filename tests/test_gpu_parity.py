@@ -120,6 +120,82 @@ def test_mapper_iteration_against_real_mapper_capture(stage):
         assert rel(mine[k].grad, v) < TOL, (k, rel(mine[k].grad, v))
 
 
+@pytest.mark.parametrize("backend", [1, 2])
+def test_other_decoder_backends_match_the_default_one(backend):
+    """mlp_backend 1 (FP32-FMA decoders, render_fwd_kernel / render_bwd_kernel) and 2 (round-1 ray-group tcgen05 kernels) against the default tile
+    kernels on one tracking and one colour-stage mapping iteration, in this process (the whole suite also runs under NSB_MLP_BACKEND=1 / 2 in
+    tools/gpu_round.sh / gpu_final.sh; this keeps the other back-ends inside the default `pytest -m gpu` run)."""
+    from nice_slam_b200 import _lib
+    from nice_slam_b200.steps import IterationContext
+    L = _lib.lib()
+    sc = su.load_scenes()["room0"]
+    renderer, c, dec = make_renderer(sc, su.make_grids(sc, "soft"), su.load_decoders("soft"), DEV)
+    n = 150
+    ro, rd, gd, gc = su.make_rays(sc, n, seed=404)
+    dirs = torch.randn(n, 3, generator=torch.Generator().manual_seed(3)).to(DEV)
+    keys = ("grid_fine", "grid_color", "grid_middle")
+    out = {}
+    try:
+        for b in (0, backend):
+            assert L.nsb_set_option(b"mlp_backend", b) == 0
+            t = IterationContext(renderer, n, "color", DEV, kind="track")
+            t.run(c, dec, ro.to(DEV), rd.to(DEV), gd.to(DEV), gc.double().to(DEV), dirs=dirs)
+            m = IterationContext(renderer, n, "color", DEV, kind="map", grad_grids=keys, grad_decoders=("color",))
+            m.run(c, dec, ro.to(DEV), rd.to(DEV), gd.to(DEV), gc.float().to(DEV))
+            torch.cuda.synchronize()
+            out[b] = dict(z=t.z_vals.clone(), depth=t.depth.clone(), rgb=t.rgb.clone(), loss=float(t.loss), d_c2w=t.d_c2w.clone(),
+                          rays=torch.cat([t.d_rays_o, t.d_rays_d], 1).clone(), mloss=float(m.loss), flat=m.d_flat["color"].clone(),
+                          grid={k: m.d_grid[k].clone() for k in keys})
+    finally:
+        L.nsb_set_option(b"mlp_backend", 0)
+    a, w = out[backend], out[0]
+    assert torch.equal(a["z"], w["z"])
+    assert rel(a["depth"], w["depth"]) < 2e-5 and rel(a["rgb"], w["rgb"]) < 2e-5
+    assert abs(a["loss"] - w["loss"]) <= 2e-5 * abs(w["loss"]) and abs(a["mloss"] - w["mloss"]) <= 2e-5 * abs(w["mloss"])
+    # (an L1 residual within ~1e-6 of zero flips the sign of that ray's gradient between two arithmetics: a knife edge of the loss, not an error)
+    flipped = int(((a["rays"] - w["rays"]).abs().amax(dim=1) > 1e-4 * float(w["rays"].abs().max())).sum())
+    assert flipped <= 1, flipped
+    if flipped == 0:
+        assert rel(a["d_c2w"], w["d_c2w"]) < 1e-4 and rel(a["flat"], w["flat"]) < 1e-4
+        for k in keys:
+            assert rel(a["grid"][k], w["grid"][k]) < 1e-4, k
+
+
+def test_coarse_mapper_iteration_in_the_native_loop_against_real_mapper_capture():
+    """The coarse mapper's joint iteration (Mapper.py:403-404,484: stage 'coarse', gt_depth=None for the renderer, sensor depth in the loss) through
+    the native loop's pieces -- frustum-masked parameterisation of grid_coarse, fused mapping iteration with compact gradients, fused Adam -- against
+    the real coarse Mapper.optimize_map capture (tests/golden/mapper_coarse.pt): rendered depth, the masked voxel gradient, and one Adam step."""
+    from nice_slam_b200.mapping import FusedMappingLoop
+    from nice_slam_b200.masked import MaskedVoxels
+    case = torch.load(os.path.join(su.GOLDEN, "mapper_coarse.pt"), map_location="cpu", weights_only=False)
+    assert case["coarse_mapper"] and case["gt_depth"] is None
+    sc = su.load_scenes()[case["scene"]]
+    renderer, c, dec = make_renderer(sc, su.make_grids(sc, case["variant"]), su.load_decoders(case["variant"]), DEV)
+    depth1, _ = su.make_frame(sc, 1)
+    loop = FusedMappingLoop(renderer, c, dec, su.make_pose(sc, 1), depth1.to(DEV), keys=("grid_coarse",), w_color=sc["mapping"]["w_color_loss"])
+    mask = case["masks"]["grid_coarse"].to(DEV)
+    loop.masked["grid_coarse"] = MaskedVoxels(c["grid_coarse"], mask)          # the real mapper's selection (the on-GPU mask has its own test)
+    before = c["grid_coarse"].detach().clone()
+    ro, rd = case["rays_o"].to(DEV), case["rays_d"].to(DEV)
+    loop.iteration("coarse", ro, rd, case["gt_depth_loss"].to(DEV), case["gt_color"].to(DEV), dict(decoders=0.0, coarse=0.001))
+    torch.cuda.synchronize()
+    ctx = loop._ctx["coarse"]
+    n = ro.shape[0]
+    assert ctx.z_vals.shape[1] == renderer.N_samples                 # no surface samples: the renderer got no depth
+    assert rel(ctx.depth[:n], case["depth"]) < TOL and rel(ctx.var[:n], case["var"]) < TOL
+    summ = case["masked_grads"]["grid_coarse"]
+    got = ctx.d_grid["grid_coarse"][: int(mask.sum())].t().reshape(-1).cpu()     # the reference's val[mask] order is channel-major
+    assert rel(got[summ["idx"]], summ["val"]) < TOL
+    assert abs(float(got.double().norm()) - summ["norm"]) < TOL * summ["norm"]
+    # first Adam step on the selected voxels only: -lr * sign-like update where the gradient is non-zero, everything else untouched
+    delta = (c["grid_coarse"].detach() - before)
+    sel = mask.unsqueeze(0).unsqueeze(0).expand_as(delta)
+    assert int((delta[~sel] != 0).sum()) == 0                        # (the coarse selection is the whole grid, Mapper.py:113-116: nothing outside)
+    g = ctx.d_grid["grid_coarse"][: int(mask.sum())].t().reshape(-1)
+    want = -0.001 * g / (g.abs() + 1e-8)
+    assert rel(delta[sel], want) < 1e-4
+
+
 def test_eval_points_matches_oracle():
     sc = su.load_scenes()["room0"]
     grids, dec_state = su.make_grids(sc, "soft"), su.load_decoders("soft")
