@@ -217,6 +217,14 @@ int nsb_compact_transpose(const float* src, float* dst, long long n_selected, in
  * nsb_adam_decoder: the parameter tensors of one decoder, from its flat gradient (canonical order, nsb_flat_offset). */
 int nsb_adam_masked_voxels(const nsb_grid* grid, const int32_t* slot_map, const float* grad, float* exp_avg, float* exp_avg_sq,
                            double lr, double beta1, double beta2, double eps, int step, void* stream);
+/* The mapper's whole optimiser.step() (Mapper.py:504) in one launch: up to four voxel groups (as nsb_adam_masked_voxels, each with its own
+ * learning rate and step count) and optionally one decoder (as nsb_adam_decoder; dec_level < 0: none). */
+typedef struct nsb_adam_voxel_group {
+  nsb_grid grid; const int32_t* slot_map; const float* grad; float* exp_avg; float* exp_avg_sq; double lr; int step;
+} nsb_adam_voxel_group;
+int nsb_adam_mapper_step(const nsb_adam_voxel_group* groups, int n_groups, int dec_level, const nsb_decoder_params* dec_params,
+                         const float* dec_grad_flat, float* dec_exp_avg, float* dec_exp_avg_sq, double dec_lr, int dec_step,
+                         double beta1, double beta2, double eps, void* stream);
 int nsb_adam_decoder(int level, const nsb_decoder_params* params, const float* grad_flat, float* exp_avg, float* exp_avg_sq,
                      double lr, double beta1, double beta2, double eps, int step, void* stream);
 

@@ -21,6 +21,11 @@ class Grid(C.Structure):
                 ("stride_c", C.c_int64), ("stride_d", C.c_int64), ("stride_h", C.c_int64), ("stride_w", C.c_int64)]
 
 
+class AdamVoxelGroup(C.Structure):
+    _fields_ = [("grid", Grid), ("slot_map", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("lr", C.c_double), ("step", C.c_int)]
+
+
 class DecoderParams(C.Structure):
     _fields_ = [("B", C.c_void_p), ("W", C.c_void_p * 5), ("b", C.c_void_p * 5),
                 ("Wc", C.c_void_p * 5), ("bc", C.c_void_p * 5), ("Wo", C.c_void_p), ("bo", C.c_void_p)]
@@ -94,6 +99,8 @@ SYMBOLS = {
     "nsb_pose_grad_frames": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P]),
     "nsb_split_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "nsb_adam_masked_voxels": (C.c_int, [C.POINTER(Grid), _P, _P, _P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, _P]),
+    "nsb_adam_mapper_step": (C.c_int, [C.POINTER(AdamVoxelGroup), C.c_int, C.c_int, C.POINTER(DecoderParams), _P, _P, _P, C.c_double, C.c_int,
+                                       C.c_double, C.c_double, C.c_double, _P]),
     "nsb_adam_decoder": (C.c_int, [C.c_int, C.POINTER(DecoderParams), _P, _P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, _P]),
     "nsb_frustum_mask_workspace": (C.c_size_t, [C.c_longlong]),
     "nsb_frustum_mask": (C.c_int, [C.POINTER(C.c_float), _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int,

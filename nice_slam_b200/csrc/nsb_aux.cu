@@ -26,11 +26,12 @@ int check_cuda(cudaError_t e, const char* what) {
 // Maps every element of the reference parameter tensors to its slot in the packed image (nsb_common.cuh).
 // DIR = 0: packed[slot] = param[i] ; DIR = 1: flat_grad[flat_i] += packed_grad[slot]
 struct PackArgs { nsb_decoder_params p[4]; float* packed[4]; float* flat[4]; int present[4]; };
-// The pack kernels run blockIdx.x = decoder level, blockIdx.y = slice: every loop is a grid-stride loop over the level's slices (the images of
-// a decoder are ~0.3 MB of independent elements; one CTA per level took 46 + 34 us of every colour-decoder optimiser step).
-__device__ __forceinline__ int pk_tid() { return blockIdx.y * blockDim.x + threadIdx.x; }
-__device__ __forceinline__ int pk_nt() { return gridDim.y * blockDim.x; }
-constexpr int kPackSlices = 16;
+// The pack kernels run blockIdx.x = decoder level, blockIdx.y = slice.  The work of a level is a SEQUENCE of small independent pieces (23
+// parameter tensors; ~75 operand tiles / units of <= 5120 elements): piece number e belongs to slice e % gridDim.y, whose 256 threads stride
+// over it.  (One CTA per level took 46 + 34 us of every colour-decoder optimiser step; striding every piece over all slices still walked the
+// pieces one after the other -- ~1 us of load -> store latency each, 15 + 26 us; now a slice handles 2-3 pieces.)
+__device__ __forceinline__ bool pk_mine(int& e) { return (e++ % (int)gridDim.y) == (int)blockIdx.y; }
+constexpr int kPackSlices = 32;
 
 template <int LV, int DIR>
 __device__ void pack_level(const PackArgs& A) {
@@ -38,9 +39,10 @@ __device__ void pack_level(const PackArgs& A) {
   float* pk = A.packed[LV];
   const nsb_decoder_params& p = A.p[LV];
   float* fl = A.flat[LV];
-  const int tid = pk_tid(), nt = pk_nt();                         // (DIR == 0: the launcher has zeroed the image, pads included)
+  int e = 0;                                                      // (DIR == 0: the launcher has zeroed the image, pads included)
   auto xfer = [&](const float* src, long long flat_off, int n, auto slot) {
-    for (int i = tid; i < n; i += nt) {
+    if (!pk_mine(e)) return;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
       const int s = slot(i);
       if (DIR == 0) pk[s] = src[i]; else fl[flat_off + i] += pk[s];
     }
@@ -81,26 +83,27 @@ __global__ void pack_kernel(const __grid_constant__ PackArgs A) {
 // ---- tensor-core operand images (layout: nsb_common.cuh) --------------------------------------------------------------------
 // hi | lo of a [R x 32] canonical tile whose element (row, k) is get(row, k)
 template <typename F>
-__device__ __forceinline__ void emit_tile(float*& dst, int R, F&& get) {
+__device__ __forceinline__ void emit_tile(float*& dst, int& e, int R, F&& get) {
   float* hi = dst; float* lo = dst + R * 32;
-  for (int idx = pk_tid(); idx < R * 32; idx += pk_nt()) {
+  dst += 2 * R * 32;
+  if (!pk_mine(e)) return;
+  for (int idx = threadIdx.x; idx < R * 32; idx += blockDim.x) {
     const int r = idx >> 5, k = idx & 31;
     const float v = get(r, k);
     const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);          // the 19 bits the tensor core reads (nsb_tc.cuh)
     const int o = ((r >> 3) * 8 + (k >> 2)) * 32 + (r & 7) * 4 + (k & 3);
     hi[o] = h; lo[o] = v - h;
   }
-  dst += 2 * R * 32;
 }
 template <int LV>
-__device__ void pack_operands_level(float* __restrict__ img /* packed image of this level: raw part already written */) {
+__device__ void pack_operands_level(float* __restrict__ img /* packed image of this level: raw part already written */, int& e) {
   using D = Dec<LV>;
   const float* W = img;
   constexpr int PH = D::PH;
   const int o_wh[5] = {0, D::o_W1, D::o_W2, D::o_W3H, D::o_W4};
   // forward
   float* dst = img + op_fwd_offset(LV);
-  for (int i = pk_tid(); i < kHdrFloats; i += pk_nt()) {
+  if (pk_mine(e)) for (int i = threadIdx.x; i < kHdrFloats; i += blockDim.x) {
     float v = 0.0f;
     if (i < 160) v = W[D::o_b + i];
     else if (i < 320) v = D::XYZ ? W[D::o_bc + (i - 160)] : 0.0f;
@@ -112,34 +115,35 @@ __device__ void pack_operands_level(float* __restrict__ img /* packed image of t
   dst += kHdrFloats;
   if (D::XYZ)
     for (int h = 0; h < D::CD / 32; h++)
-      emit_tile(dst, 160, [&](int r, int k) { return W[D::o_WC + r * D::PC + 32 * h + k]; });          // row r = 32 i + o
+      emit_tile(dst, e, 160, [&](int r, int k) { return W[D::o_WC + r * D::PC + 32 * h + k]; });          // row r = 32 i + o
   for (int b = 0; b < op_nblk(LV); b++)
-    emit_tile(dst, 64, [&](int r, int k) { return W[(r < 32 ? D::o_W0 : D::o_W3E) + (r & 31) * D::PF + 32 * b + k]; });
-  for (int i = 1; i < 5; i++) emit_tile(dst, 32, [&](int r, int k) { return W[o_wh[i] + r * PH + k]; });
+    emit_tile(dst, e, 64, [&](int r, int k) { return W[(r < 32 ? D::o_W0 : D::o_W3E) + (r & 31) * D::PF + 32 * b + k]; });
+  for (int i = 1; i < 5; i++) emit_tile(dst, e, 32, [&](int r, int k) { return W[o_wh[i] + r * PH + k]; });
   // backward (transposed operands)
   dst = img + op_bwd_offset(LV);
   for (int i = 4; i >= 0; i--) {
-    if (D::XYZ) emit_tile(dst, D::CD, [&](int c, int k) { return W[D::o_WC + (i * 32 + k) * D::PC + c]; });
-    if (i >= 1) emit_tile(dst, 32, [&](int j, int k) { return W[o_wh[i] + k * PH + j]; });
-    if (i == 3 || i == 0) emit_tile(dst, D::FIRSTP, [&](int f, int k) { return W[(i == 0 ? D::o_W0 : D::o_W3E) + k * D::PF + f]; });
+    if (D::XYZ) emit_tile(dst, e, D::CD, [&](int c, int k) { return W[D::o_WC + (i * 32 + k) * D::PC + c]; });
+    if (i >= 1) emit_tile(dst, e, 32, [&](int j, int k) { return W[o_wh[i] + k * PH + j]; });
+    if (i == 3 || i == 0) emit_tile(dst, e, D::FIRSTP, [&](int f, int k) { return W[(i == 0 ? D::o_W0 : D::o_W3E) + k * D::PF + f]; });
   }
 }
 // ---- v2 operand images: units for the tile kernels (layout: nsb_common.cuh op2_*) -------------------------------------------------
 // hi | lo of a [R x KW] canonical tile ([row/8][k/4][row%8][k%4]) whose element (row, k) is get(row, k)
 template <typename F>
-__device__ __forceinline__ void emit_unit(float*& dst, int R, int KW, F&& get) {
+__device__ __forceinline__ void emit_unit(float*& dst, int& e, int R, int KW, F&& get) {
   float* hi = dst; float* lo = dst + R * KW;
-  for (int idx = pk_tid(); idx < R * KW; idx += pk_nt()) {
+  dst += 2 * R * KW;
+  if (!pk_mine(e)) return;
+  for (int idx = threadIdx.x; idx < R * KW; idx += blockDim.x) {
     const int r = idx / KW, k = idx - r * KW;
     const float v = get(r, k);
     const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
     const int o = ((r >> 3) * (KW >> 2) + (k >> 2)) * 32 + (r & 7) * 4 + (k & 3);
     hi[o] = h; lo[o] = v - h;
   }
-  dst += 2 * R * KW;
 }
 template <int LV>
-__device__ void pack_units_level(float* __restrict__ img) {
+__device__ void pack_units_level(float* __restrict__ img, int& e) {
   using D = Dec<LV>;
   const float* W = img;
   constexpr int PH = D::PH;
@@ -147,37 +151,38 @@ __device__ void pack_units_level(float* __restrict__ img) {
   float* dst = img + op2_fwd_offset(LV);
   if (D::XYZ)
     for (int u = 0; u < D::CD / 8; u++)
-      emit_unit(dst, 160, 8, [&](int r, int k) { return W[D::o_WC + r * D::PC + 8 * u + k]; });
+      emit_unit(dst, e, 160, 8, [&](int r, int k) { return W[D::o_WC + r * D::PC + 8 * u + k]; });
   for (int b = 0; b < op_nblk(LV); b++)
     for (int h = 0; h < 2; h++)
-      emit_unit(dst, 64, 16, [&](int r, int k) { return W[(r < 32 ? D::o_W0 : D::o_W3E) + (r & 31) * D::PF + 32 * b + 16 * h + k]; });
-  for (int i = 1; i < 5; i++) emit_unit(dst, 32, 32, [&](int r, int k) { return W[o_wh[i] + r * PH + k]; });
+      emit_unit(dst, e, 64, 16, [&](int r, int k) { return W[(r < 32 ? D::o_W0 : D::o_W3E) + (r & 31) * D::PF + 32 * b + 16 * h + k]; });
+  for (int i = 1; i < 5; i++) emit_unit(dst, e, 32, 32, [&](int r, int k) { return W[o_wh[i] + r * PH + k]; });
   dst = img + op2_bwd_offset(LV);
   for (int i = 4; i >= 0; i--) {
     if (D::XYZ)
       for (int c2 = 0; c2 < D::CD / 32; c2++)
-        emit_unit(dst, 32, 32, [&](int c, int k) { return W[D::o_WC + (i * 32 + k) * D::PC + 32 * c2 + c]; });
-    if (i >= 1) emit_unit(dst, 32, 32, [&](int j, int k) { return W[o_wh[i] + k * PH + j]; });
+        emit_unit(dst, e, 32, 32, [&](int c, int k) { return W[D::o_WC + (i * 32 + k) * D::PC + 32 * c2 + c]; });
+    if (i >= 1) emit_unit(dst, e, 32, 32, [&](int j, int k) { return W[o_wh[i] + k * PH + j]; });
     if (i == 3 || i == 0)
       for (int fb = 0; fb < D::FIRSTP / 32; fb++)
-        emit_unit(dst, 32, 32, [&](int f, int k) { return W[(i == 0 ? D::o_W0 : D::o_W3E) + k * D::PF + 32 * fb + f]; });
+        emit_unit(dst, e, 32, 32, [&](int f, int k) { return W[(i == 0 ? D::o_W0 : D::o_W3E) + k * D::PF + 32 * fb + f]; });
   }
 }
 // ---- v3 forward image: FP16 hi | lo units (layout: nsb_common.cuh op3_*) ----------------------------------------------------------------
 template <typename F>
-__device__ __forceinline__ void emit_unit_h16(__half*& dst, int R, int KW, F&& get) {
+__device__ __forceinline__ void emit_unit_h16(__half*& dst, int& e, int R, int KW, F&& get) {
   __half* hi = dst; __half* lo = dst + R * KW;
-  for (int idx = pk_tid(); idx < R * KW; idx += pk_nt()) {
+  dst += 2 * R * KW;
+  if (!pk_mine(e)) return;
+  for (int idx = threadIdx.x; idx < R * KW; idx += blockDim.x) {
     const int r = idx / KW, k = idx - r * KW;
     const float v = get(r, k);
     const __half h = __float2half_rn(v);
     const int o = ((r >> 3) * (KW >> 3) + (k >> 3)) * 64 + (r & 7) * 8 + (k & 7);
     hi[o] = h; lo[o] = __float2half_rn(v - __half2float(h));
   }
-  dst += 2 * R * KW;
 }
 template <int LV>
-__device__ void pack_units_h16_level(float* __restrict__ img) {
+__device__ void pack_units_h16_level(float* __restrict__ img, int& e) {
   using D = Dec<LV>;
   const float* W = img;
   constexpr int PH = D::PH;
@@ -185,31 +190,20 @@ __device__ void pack_units_h16_level(float* __restrict__ img) {
   __half* dst = reinterpret_cast<__half*>(img + op3_fwd_offset(LV));
   if (D::XYZ)
     for (int u = 0; u < D::CD / 16; u++)
-      emit_unit_h16(dst, 160, 16, [&](int r, int k) { return W[D::o_WC + r * D::PC + 16 * u + k]; });
+      emit_unit_h16(dst, e, 160, 16, [&](int r, int k) { return W[D::o_WC + r * D::PC + 16 * u + k]; });
   for (int b = 0; b < op_nblk(LV); b++)
-    emit_unit_h16(dst, 64, 32, [&](int r, int k) { return W[(r < 32 ? D::o_W0 : D::o_W3E) + (r & 31) * D::PF + 32 * b + k]; });
-  for (int i = 1; i < 5; i++) emit_unit_h16(dst, 32, 32, [&](int r, int k) { return W[o_wh[i] + r * PH + k]; });
+    emit_unit_h16(dst, e, 64, 32, [&](int r, int k) { return W[(r < 32 ? D::o_W0 : D::o_W3E) + (r & 31) * D::PF + 32 * b + k]; });
+  for (int i = 1; i < 5; i++) emit_unit_h16(dst, e, 32, 32, [&](int r, int k) { return W[o_wh[i] + r * PH + k]; });
 }
 __global__ void pack_operands_kernel(const __grid_constant__ PackArgs A) {
   const int lv = blockIdx.x;
   if (!A.present[lv]) return;
+  int e = 0;                                                      // piece counter (pk_mine)
   switch (lv) {
-    case 0: pack_operands_level<0>(A.packed[0]); break;
-    case 1: pack_operands_level<1>(A.packed[1]); break;
-    case 2: pack_operands_level<2>(A.packed[2]); break;
-    default: pack_operands_level<3>(A.packed[3]); break;
-  }
-  switch (lv) {
-    case 0: pack_units_level<0>(A.packed[0]); break;
-    case 1: pack_units_level<1>(A.packed[1]); break;
-    case 2: pack_units_level<2>(A.packed[2]); break;
-    default: pack_units_level<3>(A.packed[3]); break;
-  }
-  switch (lv) {
-    case 0: pack_units_h16_level<0>(A.packed[0]); break;
-    case 1: pack_units_h16_level<1>(A.packed[1]); break;
-    case 2: pack_units_h16_level<2>(A.packed[2]); break;
-    default: pack_units_h16_level<3>(A.packed[3]); break;
+    case 0: pack_operands_level<0>(A.packed[0], e); pack_units_level<0>(A.packed[0], e); pack_units_h16_level<0>(A.packed[0], e); break;
+    case 1: pack_operands_level<1>(A.packed[1], e); pack_units_level<1>(A.packed[1], e); pack_units_h16_level<1>(A.packed[1], e); break;
+    case 2: pack_operands_level<2>(A.packed[2], e); pack_units_level<2>(A.packed[2], e); pack_units_h16_level<2>(A.packed[2], e); break;
+    default: pack_operands_level<3>(A.packed[3], e); pack_units_level<3>(A.packed[3], e); pack_units_h16_level<3>(A.packed[3], e); break;
   }
 }
 
@@ -509,6 +503,42 @@ __global__ void adam_flat_kernel(const AdamTable T, const float* __restrict__ gr
     }
 }
 
+// the mapper's whole optimiser step in ONE launch: CTAs [blk0[g], blk0[g+1]) update voxel group g, the last 32 CTAs the decoder
+struct MapperAdamArgs {
+  nsb_grid g[4]; const int32_t* slots[4]; const float* grad[4]; float* em[4]; float* ev[4]; AdamScalars a[4]; int blk0[5]; int n_groups;
+  AdamTable T; const float* dgrad; float* dem; float* dev; AdamScalars da; int dec_blocks;
+};
+__global__ void adam_mapper_kernel(const __grid_constant__ MapperAdamArgs A) {
+  const int b = blockIdx.x;
+  if (b >= A.blk0[A.n_groups]) {                                   // decoder (adam_flat_kernel)
+    const int bd = b - A.blk0[A.n_groups];
+    for (int t = 0; t < A.T.count; t++)
+      for (int i = bd * blockDim.x + threadIdx.x; i < A.T.n[t]; i += A.dec_blocks * blockDim.x) {
+        const int f = A.T.off[t] + i;
+        float m = A.dem[f], v = A.dev[f];
+        A.T.param[t][i] = adam_update(A.T.param[t][i], A.dgrad[f], m, v, A.da);
+        A.dem[f] = m; A.dev[f] = v;
+      }
+    return;
+  }
+  int q = 0;
+  while (q + 1 < A.n_groups && b >= A.blk0[q + 1]) q++;
+  const nsb_grid& g = A.g[q];
+  const int nb = A.blk0[q + 1] - A.blk0[q], bq = b - A.blk0[q];
+  const long long n = (long long)g.D * g.H * g.W;
+  const int lane = threadIdx.x & 31;
+  for (long long vx = (long long)bq * (blockDim.x >> 5) + (threadIdx.x >> 5); vx < n; vx += (long long)nb * (blockDim.x >> 5)) {      // (adam_masked_kernel)
+    const int s = __ldg(A.slots[q] + vx);
+    if (s < 0) continue;
+    const int w = (int)(vx % g.W), h = (int)((vx / g.W) % g.H), d = (int)(vx / ((long long)g.W * g.H));
+    float* cell = const_cast<float*>(g.data) + d * g.stride_d + h * g.stride_h + w * g.stride_w + lane * g.stride_c;
+    const long long i = (long long)s * 32 + lane;
+    float m = A.em[q][i], v = A.ev[q][i];
+    *cell = adam_update(*cell, A.grad[q][i], m, v, A.a[q]);
+    A.em[q][i] = m; A.ev[q][i] = v;
+  }
+}
+
 // d c2w of every keyframe block (one CTA per frame)
 __global__ void pose_grad_frames_kernel(const float* __restrict__ dirs, const float* __restrict__ dro, const float* __restrict__ drd,
                                         const int32_t* __restrict__ offs, float* __restrict__ out) {
@@ -612,11 +642,8 @@ extern "C" int nsb_adam_masked_voxels(const nsb_grid* grid, const int32_t* slot_
   adam_masked_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*grid, slot_map, grad, exp_avg, exp_avg_sq, a);
   return check_cuda(cudaGetLastError(), "adam_masked_voxels launch");
 }
-extern "C" int nsb_adam_decoder(int level, const nsb_decoder_params* p, const float* grad_flat, float* exp_avg, float* exp_avg_sq,
-                                double lr, double beta1, double beta2, double eps, int step, void* stream) {
-  if (level < 0 || level > 3 || !p || !grad_flat || !exp_avg || !exp_avg_sq) { set_error("adam_decoder: bad arguments"); return NSB_ERR_ARG; }
-  AdamScalars a; int rc = adam_scalars(lr, beta1, beta2, eps, step, &a); if (rc) return rc;
-  AdamTable T; memset(&T, 0, sizeof(T));
+static int adam_table(int level, const nsb_decoder_params* p, AdamTable* Tp) {
+  AdamTable& T = *Tp; memset(&T, 0, sizeof(T));
   auto add = [&](const float* ptr, int kind, int layer, int n) { T.param[T.count] = const_cast<float*>(ptr); T.off[T.count] = (int)flat_offset(level, kind, layer); T.n[T.count] = n; T.count++; };
   const bool xyz = level != 0;
   const int cd = level == 2 ? 64 : 32, no = level == 3 ? 4 : 1;
@@ -628,8 +655,42 @@ extern "C" int nsb_adam_decoder(int level, const nsb_decoder_params* p, const fl
   for (int i = 0; i < 5; i++) { add(p->W[i], 1, i, kHid * dec_in(level, i)); add(p->b[i], 2, i, kHid); }
   if (xyz) for (int i = 0; i < 5; i++) { add(p->Wc[i], 3, i, kHid * cd); add(p->bc[i], 4, i, kHid); }
   add(p->Wo, 5, 0, no * kHid); add(p->bo, 6, 0, no);
+  return NSB_OK;
+}
+extern "C" int nsb_adam_decoder(int level, const nsb_decoder_params* p, const float* grad_flat, float* exp_avg, float* exp_avg_sq,
+                                double lr, double beta1, double beta2, double eps, int step, void* stream) {
+  if (level < 0 || level > 3 || !p || !grad_flat || !exp_avg || !exp_avg_sq) { set_error("adam_decoder: bad arguments"); return NSB_ERR_ARG; }
+  AdamScalars a; int rc = adam_scalars(lr, beta1, beta2, eps, step, &a); if (rc) return rc;
+  AdamTable T; if ((rc = adam_table(level, p, &T))) return rc;
   adam_flat_kernel<<<32, 256, 0, (cudaStream_t)stream>>>(T, grad_flat, exp_avg, exp_avg_sq, a);
   return check_cuda(cudaGetLastError(), "adam_decoder launch");
+}
+extern "C" int nsb_adam_mapper_step(const nsb_adam_voxel_group* groups, int n_groups, int dec_level, const nsb_decoder_params* dec_params,
+                                    const float* dec_grad_flat, float* dec_exp_avg, float* dec_exp_avg_sq, double dec_lr, int dec_step,
+                                    double beta1, double beta2, double eps, void* stream) {
+  if (n_groups < 0 || n_groups > 4 || (n_groups > 0 && !groups)) { set_error("adam_mapper_step: 0..4 voxel groups"); return NSB_ERR_ARG; }
+  MapperAdamArgs A; memset(&A, 0, sizeof(A));
+  A.n_groups = n_groups;
+  int rc;
+  for (int q = 0; q < n_groups; q++) {
+    const nsb_adam_voxel_group& G = groups[q];
+    if (!G.grid.data || !G.slot_map || !G.grad || !G.exp_avg || !G.exp_avg_sq || G.grid.D < 1 || G.grid.H < 1 || G.grid.W < 1) {
+      set_error("adam_mapper_step: bad voxel group %d", q); return NSB_ERR_ARG; }
+    if ((rc = adam_scalars(G.lr, beta1, beta2, eps, G.step, &A.a[q]))) return rc;
+    A.g[q] = G.grid; A.slots[q] = G.slot_map; A.grad[q] = G.grad; A.em[q] = G.exp_avg; A.ev[q] = G.exp_avg_sq;
+    const long long n = (long long)G.grid.D * G.grid.H * G.grid.W;
+    A.blk0[q + 1] = A.blk0[q] + (int)((n + 7) / 8 < 148 * 8 ? (n + 7) / 8 : 148 * 8);
+  }
+  if (dec_level >= 0) {
+    if (dec_level > 3 || !dec_params || !dec_grad_flat || !dec_exp_avg || !dec_exp_avg_sq) { set_error("adam_mapper_step: bad decoder arguments"); return NSB_ERR_ARG; }
+    if ((rc = adam_scalars(dec_lr, beta1, beta2, eps, dec_step, &A.da))) return rc;
+    if ((rc = adam_table(dec_level, dec_params, &A.T))) return rc;
+    A.dgrad = dec_grad_flat; A.dem = dec_exp_avg; A.dev = dec_exp_avg_sq; A.dec_blocks = 32;
+  }
+  const int blocks = A.blk0[n_groups] + A.dec_blocks;
+  if (blocks == 0) return NSB_OK;
+  adam_mapper_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(A);
+  return check_cuda(cudaGetLastError(), "adam_mapper_step launch");
 }
 
 // ---- bundle-adjustment window: poses <-> rays (Mapper.py:346-363, :437-467, :521-540; common.py:74-89, :137-176) --------------------------

@@ -94,10 +94,7 @@ class FusedMappingLoop:
         ctx = self._context(ro.shape[0], stage, dev)
         loss = ctx.run(self.c, self.dec, ro, rd, gd, gc, w_color=self.w_color)
         ctx.finish_packed(dirs, offs)
-        for key in ctx.grad_grids:
-            self.adam.step_voxels(key, self.c[key], self.masked[key], ctx.d_grid[key], lr[key[5:]])
-        if stage == "color":
-            self.adam.step_decoder("color", self.dec, ctx.d_flat["color"], lr["decoders"], renderer=self.r)
+        self._optimiser_step(ctx, stage, lr)
         b = self.ba
         b["step"] += 1
         _lib.check(L.nsb_adam_poses(_VP(b["cams"].data_ptr()), _VP(b["cam_row"].data_ptr()), F, _VP(ctx.d_frames.data_ptr()), _VP(b["m"].data_ptr()),
@@ -123,11 +120,15 @@ class FusedMappingLoop:
         (Mapper.py:412-416).  Returns the loss tensor (device, float64)."""
         ctx = self._context(rays_o.shape[0], stage, rays_o.device)
         loss = ctx.run(self.c, self.dec, rays_o, rays_d, gt_depth, gt_color, w_color=self.w_color)
-        for key in ctx.grad_grids:                              # param groups whose parameters received a gradient (Adam skips the others)
-            self.adam.step_voxels(key, self.c[key], self.masked[key], ctx.d_grid[key], lr[key[5:]])
-        if stage == "color":
-            self.adam.step_decoder("color", self.dec, ctx.d_flat["color"], lr["decoders"], renderer=self.r)
+        self._optimiser_step(ctx, stage, lr)
         return loss
+
+    def _optimiser_step(self, ctx, stage, lr):
+        """optimizer.step() (Mapper.py:504) for the param groups whose parameters received a gradient (Adam skips the others): the selected
+        voxels of the stage's grids and, in stage 'color', the colour decoder -- one launch (optim.FusedMapperAdam.step_all)."""
+        vox = [(key, self.c[key], self.masked[key], ctx.d_grid[key], lr[key[5:]]) for key in ctx.grad_grids]
+        dec = ("color", self.dec, ctx.d_flat["color"], lr["decoders"]) if stage == "color" else None
+        self.adam.step_all(vox, dec, renderer=self.r)
 
 
 def tensor_from_c2w(c2w):

@@ -59,6 +59,44 @@ class FusedMapperAdam:
                                                      _VP(st["v"].data_ptr()), float(lr), self.betas[0], self.betas[1], self.eps, st["step"], _stream()),
                    "nsb_adam_masked_voxels")
 
+    def step_all(self, voxel_items, decoder_item=None, renderer=None):
+        """The mapper's whole optimizer.step() (Mapper.py:504) in ONE launch.  voxel_items: [(key, grid, masked, grad, lr)] (at most four, as
+        step_voxels); decoder_item: (level_name, decoders, grad_flat, lr) or None (as step_decoder)."""
+        items = [it for it in voxel_items if it[2].count > 0]
+        if len(items) > 4:
+            raise RuntimeError("nice_slam_b200: at most four voxel groups per fused optimiser step")
+        groups = (_lib.AdamVoxelGroup * max(len(items), 1))()
+        for q, (key, grid, masked, grad, lr) in enumerate(items):
+            st = self._st(key, masked.count * 32, grid.device)
+            st["step"] += 1
+            g = groups[q]
+            g.grid = grid_struct(grid.detach())
+            g.slot_map, g.grad, g.exp_avg, g.exp_avg_sq = masked.slot_map.data_ptr(), grad.data_ptr(), st["m"].data_ptr(), st["v"].data_ptr()
+            g.lr, g.step = float(lr), st["step"]
+        li, dp, gf, dm, dv, dlr, dstep = -1, None, None, None, None, 0.0, 0
+        if decoder_item is not None:
+            level_name, decoders, grad_flat, dlr = decoder_item
+            li = LEVELS.index(level_name)
+            st = self._st("dec_" + level_name, grad_flat.numel(), grad_flat.device)
+            st["step"] += 1
+            dstep = st["step"]
+            dp = C.byref(self._decoder_struct(decoders, level_name))
+            gf, dm, dv = _VP(grad_flat.data_ptr()), _VP(st["m"].data_ptr()), _VP(st["v"].data_ptr())
+        _lib.check(_lib.lib().nsb_adam_mapper_step(groups, len(items), li, dp, gf, dm, dv, float(dlr), dstep,
+                                                   self.betas[0], self.betas[1], self.eps, _stream()), "nsb_adam_mapper_step")
+        if decoder_item is not None and renderer is not None:
+            renderer.invalidate_decoders((decoder_item[0],))
+
+    def _decoder_struct(self, decoders, level_name):
+        """nsb_decoder_params of a decoder, cached on the storage pointers of its parameters (building it walks ~20 tensors)."""
+        p = named_params(decoders, level_name)
+        key = tuple(t.data_ptr() for t in p.values())
+        hit = self.state.get(("dp", level_name))
+        if hit is None or hit[0] != key:
+            hit = (key, decoder_params_struct(decoders, level_name))
+            self.state[("dp", level_name)] = hit
+        return hit[1]
+
     def step_decoder(self, level_name, decoders, grad_flat, lr, renderer=None):
         """Updates the decoder's parameter tensors in place; pass the FusedRenderer so that its packed-weight cache is invalidated (raw
         pointer writes do not bump the tensors' version counters)."""

@@ -59,8 +59,8 @@ def test_struct_sizes_match_the_header():
     prog = r'''
 #include <stdio.h>
 #include "nice_slam_b200.h"
-int main(){ printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(nsb_grid), sizeof(nsb_decoder_params), sizeof(nsb_render_inputs),
-                   sizeof(nsb_forward_outputs), sizeof(nsb_backward_args), sizeof(nsb_iteration_buffers), sizeof(nsb_peers)); return 0; }
+int main(){ printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(nsb_grid), sizeof(nsb_decoder_params), sizeof(nsb_render_inputs),
+                   sizeof(nsb_forward_outputs), sizeof(nsb_backward_args), sizeof(nsb_iteration_buffers), sizeof(nsb_peers), sizeof(nsb_adam_voxel_group)); return 0; }
 '''
     with tempfile.TemporaryDirectory() as td:
         src = os.path.join(td, "s.c")
@@ -69,7 +69,7 @@ int main(){ printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(nsb_grid), sizeof(nsb
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     mine = [C.sizeof(x) for x in (_lib.Grid, _lib.DecoderParams, _lib.RenderInputs, _lib.ForwardOutputs, _lib.BackwardArgs, _lib.IterationBuffers,
-                                   _lib.Peers)]
+                                   _lib.Peers, _lib.AdamVoxelGroup)]
     assert sizes == mine
 
 
