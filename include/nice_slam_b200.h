@@ -311,6 +311,16 @@ int nsb_eval_points(const nsb_render_inputs* in, const double* points, int n_poi
  * PyTorch on these 12 numbers. */
 int nsb_pose_grad(const float* dirs, const float* d_rays_o, const float* d_rays_d, int n, double* d_c2w, void* stream);
 
+/* ---- per-iteration host blocks ----
+ * The reference moves every batch tensor with its own `.to(device)` and reads the loss with `.item()` (src/Tracker.py:94-105,124-131,
+ * src/Mapper.py:439-462,505-507).  Here the inputs of an iteration are ONE pinned host block and its results ONE block (see
+ * nice_slam_b200/steps.py); nsb_copy_block moves such a block with the SMs (one 16-byte word per thread, all in flight: one PCIe round
+ * trip) instead of a copy-engine transfer -- inside a CUDA graph that is a kernel node between kernel nodes.  Either pointer may be device
+ * memory or the device view of page-locked host memory (nsb_host_device_pointer: NULL + nsb_last_error() if the block is not page-locked);
+ * both must be 16-byte aligned.  Ordinary stream semantics: the copy is complete when the stream reaches the next operation. */
+void* nsb_host_device_pointer(void* pinned_host);
+int nsb_copy_block(void* dst, const void* src, size_t bytes, void* stream);
+
 /* ---- one optimisation iteration = batch max -> forward -> loss seeds -> backward, enqueued by ONE call ----
  * (what Tracker.optimize_cam_in_batch, src/Tracker.py:106-125, and one joint_iter of Mapper.optimize_map,
  * src/Mapper.py:482-503, do around the optimiser step).  All buffers are caller-owned device memory. */

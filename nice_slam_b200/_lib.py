@@ -90,6 +90,8 @@ SYMBOLS = {
     "nsb_mapping_iteration": (C.c_int, [C.POINTER(RenderInputs), C.POINTER(IterationBuffers), _P, _P, C.c_double, C.POINTER(BackwardArgs), _P]),
     "nsb_mapping_seeds": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_double, C.c_int, _P, _P, _P, _P]),
     "nsb_tracking_seeds_workspace": (C.c_size_t, [C.c_int]),
+    "nsb_host_device_pointer": (C.c_void_p, [_P]),
+    "nsb_copy_block": (C.c_int, [_P, _P, C.c_size_t, _P]),
     "nsb_eval_points": (C.c_int, [C.POINTER(RenderInputs), _P, C.c_int, _P, _P]),
     "nsb_voxel_slots_workspace": (C.c_size_t, [C.c_longlong]),
     "nsb_voxel_slots": (C.c_int, [_P, C.c_longlong, _P, _P, _P, C.c_size_t, _P]),

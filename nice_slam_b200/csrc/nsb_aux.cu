@@ -578,6 +578,32 @@ static int make_peers(const nsb_peers* p, PeerX* px) {
 int nsb::make_peerx(const nsb_peers* p, PeerX* px) { return make_peers(p, px); }
 extern "C" size_t nsb_peer_buffer_bytes(int max_rays) { return max_rays < 1 ? 0 : peer_buffer_bytes(max_rays); }
 
+// ------------------------------------------------------------------------------------------------ small host <-> device blocks, copied by the SMs
+// The per-iteration inputs of a tracking iteration are ~10 KB and its results ~5 KB (steps.IterationContext blocks).  As copy-engine nodes of a CUDA
+// graph each of them costs a DMA launch + engine <-> SM synchronisation; one CTA whose threads each move one 16-byte word over the mapped view of the
+// pinned host block has every word in flight at once: one PCIe round trip.  Either side may be device memory or mapped pinned host memory.
+__global__ void __launch_bounds__(1024) block_copy_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n16, size_t tail_off, int tail) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) __stwt(dst + i, __ldcv(src + i));
+  if (blockIdx.x == 0 && (int)threadIdx.x < tail)
+    reinterpret_cast<unsigned char*>(dst)[tail_off + threadIdx.x] = reinterpret_cast<const volatile unsigned char*>(src)[tail_off + threadIdx.x];
+  __threadfence_system();
+}
+extern "C" void* nsb_host_device_pointer(void* pinned_host) {
+  void* d = nullptr;
+  if (!pinned_host) { set_error("host_device_pointer: NULL"); return nullptr; }
+  if (check_cuda(cudaHostGetDevicePointer(&d, pinned_host, 0), "cudaHostGetDevicePointer (is the block page-locked?)")) return nullptr;
+  return d;
+}
+extern "C" int nsb_copy_block(void* dst, const void* src, size_t bytes, void* stream) {
+  if (bytes == 0) return NSB_OK;
+  if (!dst || !src || (((uintptr_t)dst | (uintptr_t)src) & 15)) { set_error("copy_block: pointers must be non-NULL and 16-byte aligned"); return NSB_ERR_ARG; }
+  const size_t n16 = bytes >> 4;
+  const int tail = (int)(bytes & 15);
+  const int grid = (int)((n16 + 1023) / 1024 < 1 ? 1 : ((n16 + 1023) / 1024 > 64 ? 64 : (n16 + 1023) / 1024));
+  block_copy_kernel<<<grid, 1024, 0, (cudaStream_t)stream>>>(static_cast<uint4*>(dst), static_cast<const uint4*>(src), n16, n16 << 4, tail);
+  return check_cuda(cudaGetLastError(), "copy_block launch");
+}
+
 extern "C" int nsb_pose_grad(const float* dirs, const float* d_rays_o, const float* d_rays_d, int n, double* d_c2w, void* stream) {
   if (n < 0 || !d_c2w || (n > 0 && (!dirs || !d_rays_o || !d_rays_d))) { set_error("pose_grad: bad arguments"); return NSB_ERR_ARG; }
   pose_grad_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(dirs, d_rays_o, d_rays_d, n, d_c2w, nullptr, no_peers());

@@ -207,10 +207,14 @@ class ShardedTrackingIteration:
         x = self.ctx
 
         def body():
-            if host_io:
+            if host_io == "sm":                                    # the blocks moved by nsb_copy_block kernels over the mapped host views
+                x.copy_in_sm()
+            elif host_io:
                 x.d_in.copy_(x.h_in, non_blocking=True)
             self.enqueue()
-            if host_io:
+            if host_io == "sm":
+                x.copy_out_sm(x.h_pose13, self.packed)
+            elif host_io:
                 x.h_pose13.copy_(self.packed, non_blocking=True)
         try:
             cur = torch.cuda.current_stream()

@@ -231,15 +231,20 @@ class IterationContext:
         """Capture one whole iteration into a CUDA graph (launch-bound small batches: one graph launch instead of
         4-6 kernel launches + Python glue).  Inputs are read from the context-owned block (load_device_inputs) or,
         with host_io, copied from the pinned staging block inside the graph; results stay in the context's buffers
-        (and, with host_io, are copied to the pinned read-back block inside the graph).
+        (and, with host_io, are copied to the pinned read-back block inside the graph).  host_io = True: copy-engine transfers
+        (cudaMemcpyAsync nodes); host_io = "sm": the same two blocks moved by nsb_copy_block kernels over the mapped host views.
         Re-capture after anything that changes pointers (grids re-created) or the decoders' packed image."""
         ro, rd, gd, gc = self.device_views()
 
         def body():
-            if host_io:
+            if host_io == "sm":
+                self.copy_in_sm()                                          # same two blocks, moved by one CTA each over the mapped host views
+            elif host_io:
                 self.d_in.copy_(self.h_in, non_blocking=True)             # one H2D copy: rays, sensor depth and colour
             self.run(c, decoders, ro, rd, gd, gc, dirs=dirs, **kw)     # d c2w comes out of the backward kernel
-            if host_io:
+            if host_io == "sm":
+                self.copy_out_sm()
+            elif host_io:
                 self.h_res.copy_(self.d_res, non_blocking=True)           # one D2H copy: ray gradients, loss, pose gradient
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
@@ -252,6 +257,28 @@ class IterationContext:
         with torch.cuda.graph(g):
             body()
         return g
+
+    def _mapped(self, t):
+        """Device view of a pinned host tensor (nsb_host_device_pointer); resolved once, outside any graph capture."""
+        key = t.data_ptr()
+        m = getattr(self, "_mapped_ptrs", None)
+        if m is None:
+            m = self._mapped_ptrs = {}
+        if key not in m:
+            p = _lib.lib().nsb_host_device_pointer(_VP(key))
+            if not p:
+                raise RuntimeError("nice_slam_b200: " + _lib.lib().nsb_last_error().decode())
+            m[key] = p
+        return m[key]
+
+    def copy_in_sm(self):
+        """h_in (pinned) -> d_in by nsb_copy_block on the current stream."""
+        _lib.check(_lib.lib().nsb_copy_block(_VP(self.d_in.data_ptr()), _VP(self._mapped(self.h_in)), self.d_in.numel(), _stream()), "nsb_copy_block")
+
+    def copy_out_sm(self, dst=None, src=None):
+        """d_res -> h_res (pinned) by nsb_copy_block on the current stream (dst / src: another pinned / device pair of equal size)."""
+        dst, src = (self.h_res, self.d_res) if dst is None else (dst, src)
+        _lib.check(_lib.lib().nsb_copy_block(_VP(self._mapped(dst)), _VP(src.data_ptr()), src.numel() * src.element_size(), _stream()), "nsb_copy_block")
 
     def stage_host_inputs(self, rays_o, rays_d, gt_depth, gt_color):
         """Fill the pinned host block from CPU tensors (outside the timed region of a benchmark)."""

@@ -397,6 +397,15 @@ def test_fused_tracking_iteration_matches_oracle(n_rays):
     ctx.stage_host_inputs(ro, rd, gd, gc.double())
     loss, d_rays = ctx.run_host(c, dec)
     check(loss, d_rays[0], d_rays[1], ctx.pose_grad(dirs_d))
+    # the end-to-end graph forms: copy-engine transfers and nsb_copy_block kernels deliver the same result block to pinned host memory
+    blocks = []
+    for mode in (True, "sm"):
+        ge = ctx.build_graph(c, dec, dirs=dirs_d, host_io=mode)
+        ctx.d_in.zero_(); ctx.h_res.zero_()
+        ge.replay(); torch.cuda.synchronize()
+        check(ctx.h_loss[0], ctx.h_out.view(2, n_rays, 3)[0], ctx.h_out.view(2, n_rays, 3)[1], ctx.h_pose)
+        blocks.append(ctx.h_res.clone())
+    assert torch.equal(blocks[0], blocks[1])
     # split-phase sharded iteration without a process group == the fused one
     sh = ShardedTrackingIteration(ctx)
     packed = sh.run(c, dec, *dev_in[:2], dirs_d, *dev_in[2:]).clone()
@@ -832,3 +841,29 @@ def test_fused_mapping_loop_against_five_real_mapper_iterations():
     for k, v in case["color_decoder"].items():
         close = (mine[k].detach().cpu() - v).abs() <= 1e-3 * (1 + v.abs())
         assert float(close.float().mean()) > 0.99, (k, float(close.float().mean()))
+
+
+@pytest.mark.parametrize("nbytes", [16, 104, 4904, 10400, 70000, 3 << 20])
+def test_copy_block_moves_pinned_host_blocks_both_ways(nbytes):
+    """nsb_copy_block (SM copy over the mapped view of page-locked host memory): host -> device -> host round trip, bytes preserved,
+    neighbours untouched; a misaligned pointer is refused."""
+    import ctypes as C
+    from nice_slam_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(nbytes)
+    src = torch.randint(0, 256, (nbytes,), dtype=torch.uint8, generator=g).pin_memory()
+    back = torch.zeros(nbytes + 32, dtype=torch.uint8).pin_memory()
+    dev = torch.zeros(nbytes + 32, dtype=torch.uint8, device=DEV)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    hs, hb = L.nsb_host_device_pointer(C.c_void_p(src.data_ptr())), L.nsb_host_device_pointer(C.c_void_p(back.data_ptr()))
+    assert hs and hb
+    _lib.check(L.nsb_copy_block(C.c_void_p(dev.data_ptr() + 16), C.c_void_p(hs), nbytes, st), "nsb_copy_block")
+    _lib.check(L.nsb_copy_block(C.c_void_p(hb + 16), C.c_void_p(dev.data_ptr() + 16), nbytes, st), "nsb_copy_block")
+    torch.cuda.synchronize()
+    assert torch.equal(dev[16: 16 + nbytes].cpu(), src)
+    assert torch.equal(back[16: 16 + nbytes], src)
+    assert int(dev[:16].sum()) == 0 and int(dev[16 + nbytes:].sum()) == 0 and int(back[:16].sum()) == 0 and int(back[16 + nbytes:].sum()) == 0
+    assert L.nsb_copy_block(C.c_void_p(dev.data_ptr() + 4), C.c_void_p(hs), 16, st) != 0          # misaligned destination
+    pageable = torch.zeros(64, dtype=torch.uint8)
+    if not L.nsb_host_device_pointer(C.c_void_p(pageable.data_ptr())):      # (a system with pageable-memory access may accept it)
+        assert b"page-locked" in L.nsb_last_error()
