@@ -502,7 +502,7 @@ def run_native(args):
         # both end-to-end forms deliver the same bits to the pinned result block
         ctx.h_res.zero_(); step_e2e(); want_res = ctx.h_res.clone()
         ctx.h_res.zero_(); step_e2e_sm()
-        assert torch.equal(ctx.h_res, want_res), "nsb_copy_block end-to-end form differs from the copy-engine form"
+        sm_ok = torch.equal(ctx.h_res, want_res)
     else:
         # N > 1: split-phase iteration with the three NCCL exchanges; captured into one CUDA graph per rank when possible
         ctx.load_device_inputs(ro, rd, gd, gc)
@@ -555,6 +555,12 @@ def run_native(args):
                 sharded.enqueue()
                 ctx.copy_out_sm(ctx.h_pose13, sharded.packed)
             torch.cuda.current_stream().synchronize()
+        # both end-to-end forms deliver the same [loss | d c2w] to pinned host memory
+        ctx.h_pose13.zero_(); step_e2e(); want13 = ctx.h_pose13.clone()
+        ctx.h_pose13.zero_(); step_e2e_sm()
+        okf = torch.tensor([1.0 if torch.equal(ctx.h_pose13, want13) else 0.0], device=dev)
+        dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+        sm_ok = bool(okf.item() > 0.5)                             # (a mismatch disqualifies the form instead of killing the multi-rank job)
 
     def timed(fn, steps, warmup, flush_l2):
         for _ in range(warmup):
@@ -602,6 +608,9 @@ def run_native(args):
     warm_ms, _, _ = timed(step_dev, args.steps, 3, False)                 # L2-warm (production steady state), reported as extra
     e2e_dma_ms, _, _ = timed(step_e2e, args.steps, 3, True)
     e2e_sm_ms, _, _ = timed(step_e2e_sm, args.steps, 3, True)
+    if not sm_ok:
+        print("[bench] WARNING: the SM-copy end-to-end form delivered a different result block than the copy-engine form; not used", file=sys.stderr)
+        e2e_sm_ms = float("inf")
     # the public end-to-end call offers both transports for its two host blocks; the line reports the faster one and keeps the other in `extra`
     # (all ranks take the same decision: the times are already max-reduced over the ranks)
     e2e_ms, e2e_copies = (e2e_sm_ms, "sm") if e2e_sm_ms < e2e_dma_ms else (e2e_dma_ms, "dma")
@@ -645,9 +654,9 @@ def run_native(args):
             "e2e": {"value": rays / (e2e_ms / args.steps * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": ctx.h2d_bytes,
                     "d2h_bytes_per_step": ctx.d2h_bytes if sharded is None else 13 * 8, "ms_per_step": e2e_ms / args.steps,
                     "copies": ("one pinned input block -> device and one result block -> pinned host per step, inside the graph, moved by " +
-                               ("nsb_copy_block kernels (SM loads / stores over the mapped host views)" if e2e_copies == "sm"
+                               ("the SMs over the mapped host views (input block: one nsb_copy_block kernel; result block: stored by the backward's last CTA)" if e2e_copies == "sm"
                                 else "copy-engine transfers (cudaMemcpyAsync nodes)")),
-                    "ms_per_step_copy_engine": e2e_dma_ms / args.steps, "ms_per_step_sm_copies": e2e_sm_ms / args.steps},
+                    "ms_per_step_copy_engine": e2e_dma_ms / args.steps, "ms_per_step_sm_copies": e2e_sm_ms / args.steps if sm_ok else None},
             "gpu_launches": (2 if sharded is None else (2 if sharded.fused else (5 if sharded.peers is not None else 6))) * args.steps,
             "extra": {"l2_warm_ms_per_step": warm_ms / args.steps, "l2_warm_rays_per_s": rays / (warm_ms / args.steps * 1e-3),
                       "mapping_sharded_masked": map_sharded, "mapping_other_scenes": scenes, "fwd_f16_option": f16_opt}}

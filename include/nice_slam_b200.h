@@ -171,6 +171,9 @@ typedef struct {
   double* d_c2w;
   int* pose_counter;
   const float* acts;             /* nsb_forward_outputs.acts of the same forward, or NULL */
+  void* result_dst;              /* optional (needs pose_dirs): once d_c2w is written, the same last CTA copies result_bytes bytes from result_src */
+  const void* result_src;        /* to result_dst -- e.g. the block [d_rays_o | d_rays_d | loss | d c2w] to the device view of pinned host memory   */
+  size_t result_bytes;           /* (nsb_host_device_pointer): the iteration's read-back without a copy node.  Both pointers 16-byte aligned.        */
 } nsb_backward_args;
 
 size_t nsb_backward_workspace_bytes(void);

@@ -761,6 +761,20 @@ __device__ __forceinline__ bool fused_pose_grad(const KParams& P, int n_writers,
     for (int w = 0; w < nw; w++) v += s_pose[w * 12 + threadIdx.x];
     P.bw.d_c2w[threadIdx.x] = v;
   }
+  if (P.bw.result_dst != nullptr) {
+    // read-back without a copy node: this CTA is the last writer of everything the caller wants back (ray gradients by the completing CTAs --
+    // fenced above --, the loss by the forward launch, d c2w just now), so it stores the result block to its destination (the mapped view of a
+    // pinned host block) itself.
+    __syncthreads();
+    const uint4* src = static_cast<const uint4*>(P.bw.result_src);
+    uint4* dst = static_cast<uint4*>(P.bw.result_dst);
+    const size_t n16 = P.bw.result_bytes >> 4;
+    for (size_t i = threadIdx.x; i < n16; i += blockDim.x) __stwt(dst + i, __ldcg(src + i));
+    const int tail = (int)(P.bw.result_bytes & 15);
+    if ((int)threadIdx.x < tail)
+      reinterpret_cast<unsigned char*>(dst)[(n16 << 4) + threadIdx.x] = __ldcg(reinterpret_cast<const unsigned char*>(src) + (n16 << 4) + threadIdx.x);
+    __threadfence_system();
+  }
   return true;                                                   // this CTA was the last one: d_c2w is complete (written by threads 0..11)
 }
 
@@ -1233,6 +1247,12 @@ int nsb::render_backward_tail(const nsb_render_inputs* in, const nsb_backward_ar
   const bool want_pose = bw->pose_dirs != nullptr;
   if (want_pose && (!bw->d_c2w || !bw->pose_counter || !bw->d_rays_o || !bw->d_rays_d)) {
     set_error("pose_dirs given without d_c2w / pose_counter / d_rays_o / d_rays_d"); return NSB_ERR_ARG; }
+  if (bw->result_dst != nullptr) {
+    if (!want_pose) { set_error("result_dst needs pose_dirs (the block is stored by the CTA that produces d c2w)"); return NSB_ERR_ARG; }
+    if (tail != nullptr && tail->px.world > 1) { set_error("result_dst is not supported by the sharded backward tail"); return NSB_ERR_ARG; }
+    if (!bw->result_src || ((reinterpret_cast<uintptr_t>(bw->result_dst) | reinterpret_cast<uintptr_t>(bw->result_src)) & 15)) {
+      set_error("result_dst / result_src must be non-NULL and 16-byte aligned"); return NSB_ERR_ARG; }
+  }
   K.bw.pose_dirs = nullptr;                                        // fused only into the LAST launch that writes ray gradients (below)
   for (int l = 0; l < 4; l++) {
     if (bw->slot_map[l] != nullptr && bw->d_grid[l] != nullptr && (reinterpret_cast<uintptr_t>(bw->d_grid[l]) & 15) != 0) {
@@ -1341,7 +1361,10 @@ int nsb::render_backward_tail(const nsb_render_inputs* in, const nsb_backward_ar
   render_bwd_kernel<<<grid, warps * 32, smem, st>>>(K);
   if ((rc = check_cuda(cudaGetLastError(), "render_bwd_kernel launch"))) return rc;
   if (any_w && (rc = launch_unpack_grads(K.d_packed, bw->d_flat, st))) return rc;
-  if (want_pose) return nsb_pose_grad(bw->pose_dirs, bw->d_rays_o, bw->d_rays_d, in->n_rays, bw->d_c2w, stream);   // FP32 path: separate launch
+  if (want_pose) {                                                 // FP32 path: separate launches
+    if ((rc = nsb_pose_grad(bw->pose_dirs, bw->d_rays_o, bw->d_rays_d, in->n_rays, bw->d_c2w, stream))) return rc;
+    if (bw->result_dst != nullptr) return nsb_copy_block(bw->result_dst, bw->result_src, bw->result_bytes, stream);
+  }
   return NSB_OK;
 }
 

@@ -718,16 +718,7 @@ __device__ __forceinline__ void epi_backward(const KParams& P, const TileSmem& t
     for (int o = 0; o < 4; o++) v = fmaf(hdr[336 + o * 32 + kCW * cg + j], g_out[o], v);       // rows >= NO are zero
     g[j] = v;
   }
-  float xr[kCW];                                                 // WG: the layer input H_{i-1} of this row, requested one step ahead of its use
-  auto load_acts = [&](int layer) {                              // (the asm fences of the chain keep the loads where they are written: issued here, they are
-#pragma unroll                                                   //  in flight under the gather / the chain's publish + issue instead of in front of a group)
-    for (int k = 0; k < kKQ; k++) {
-      const float4 v = acts_row != nullptr ? __ldcg(reinterpret_cast<const float4*>(acts_row + layer * 32 + 4 * k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      xr[4 * k] = v.x; xr[4 * k + 1] = v.y; xr[4 * k + 2] = v.z; xr[4 * k + 3] = v.w;
-    }
-  };
   if constexpr (WG) {
-    load_acts(4);                                                // H_4 for the output layer's group
     // grid features of this point -> registers (gathered once through the B tile)
     gather_tile_mn(P.in.grid[lv], w->b, G.xn, warp, lane);
     __syncthreads();
@@ -738,7 +729,13 @@ __device__ __forceinline__ void epi_backward(const KParams& P, const TileSmem& t
 #pragma unroll
     for (int j = 0; j < kCW; j++) go[j] = (cg == 0 && j < 4) ? g_out[j] : 0.0f;
     put_mn16(w->du, row, cg, go);
-    put_mn16(w->b, row, cg, xr);
+    float h4[kCW];
+#pragma unroll
+    for (int k = 0; k < kKQ; k++) {
+      const float4 v = acts_row != nullptr ? __ldcg(reinterpret_cast<const float4*>(acts_row + 4 * 32 + 4 * k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      h4[4 * k] = v.x; h4[4 * k + 1] = v.y; h4[4 * k + 2] = v.z; h4[4 * k + 3] = v.w;
+    }
+    put_mn16(w->b, row, cg, h4);
     wg_group(*w, tmem, 0, w->dpk + DW::o_WO, DW::PH, 4);
     if (cg == 0) {
       const float sb = warp_colsum16(go, lane);
@@ -750,7 +747,6 @@ __device__ __forceinline__ void epi_backward(const KParams& P, const TileSmem& t
   for (int i = 4; i >= 0; i--) {
     const uint32_t m = i == 4 ? m4 : (((i & 2) ? m23 : m01) >> (16 * (i & 1))) & 0xffffu;
     if constexpr (WG) {
-      if (i >= 1) load_acts(i - 1);
       float du[kCW];
 #pragma unroll
       for (int j = 0; j < kCW; j++) du[j] = (m >> j) & 1u ? g[j] : 0.0f;
@@ -773,7 +769,13 @@ __device__ __forceinline__ void epi_backward(const KParams& P, const TileSmem& t
     if (threadIdx.x < 32) issue_bwd_layer(I, t, tmem, lv, i);
     NSB_PH(23);
     if constexpr (WG) {                                          // weight gradients of layer i (the chain's MMAs run meanwhile)
-      if (i >= 1) {                                              // hidden input H_{i-1} (requested at the top of this layer step)
+      if (i >= 1) {                                              // hidden input H_{i-1}
+        float xr[kCW];
+#pragma unroll
+        for (int k = 0; k < kKQ; k++) {
+          const float4 v = acts_row != nullptr ? __ldcg(reinterpret_cast<const float4*>(acts_row + (i - 1) * 32 + 4 * k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          xr[4 * k] = v.x; xr[4 * k + 1] = v.y; xr[4 * k + 2] = v.z; xr[4 * k + 3] = v.w;
+        }
         put_mn16(w->b, row, cg, xr);
         const int o_wh = i == 1 ? DW::o_W1 : i == 2 ? DW::o_W2 : i == 3 ? DW::o_W3H : DW::o_W4;
         wg_group(*w, tmem, 0, w->dpk + o_wh, DW::PH, 32);

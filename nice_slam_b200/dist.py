@@ -147,7 +147,9 @@ class ShardedTrackingIteration:
         self._p = dict(call=call, grids=grids, lin=(t_u, t_s), inp=inp, fo=fo, bw=bw, dirs=dirs, gd=gd, gc=gc,
                        w_color=w_color, hd=int(handle_dynamic), uc=int(use_color), ggd=global_gt_depth)
 
-    def enqueue(self):
+    def enqueue(self, out13_ptr=None):
+        """out13_ptr (fused two-launch form only): device-visible address that receives [loss | d c2w] instead of self.packed -- e.g. the mapped
+        view of a pinned host block, so that the summing CTA's 13 stores are the read-back."""
         import ctypes as C
         from . import _lib
         from .renderer import _VP, _stream
@@ -168,7 +170,7 @@ class ShardedTrackingIteration:
                     _lib.check(L.nsb_batch_max_depth(_VP(p["ggd"].data_ptr()), p["ggd"].numel(), _VP(x.depth_max.data_ptr()), st), "nsb_batch_max_depth")
                     inp.depth_max = x.depth_max.data_ptr()
             _lib.check(L.nsb_tracking_iteration_peers(C.byref(inp), C.byref(x.buf), _VP(p["gc"].data_ptr()), p["w_color"], p["hd"], p["uc"], C.byref(bw),
-                                                      C.byref(self.peers.struct), _VP(self.packed.data_ptr()), st), "nsb_tracking_iteration_peers")
+                                                      C.byref(self.peers.struct), _VP(out13_ptr or self.packed.data_ptr()), st), "nsb_tracking_iteration_peers")
             return self.packed
         if self.peers is not None:
             # five kernels, no collective launch: the three exchanges happen inside batch_max / seeds / pose_grad over peer memory
@@ -211,10 +213,11 @@ class ShardedTrackingIteration:
                 x.copy_in_sm()
             elif host_io:
                 x.d_in.copy_(x.h_in, non_blocking=True)
-            self.enqueue()
-            if host_io == "sm":
+            push = host_io == "sm" and self.peers is not None and self.fused       # the summing CTA stores [loss | d c2w] to pinned memory itself
+            self.enqueue(out13_ptr=x._mapped(x.h_pose13) if push else None)
+            if host_io == "sm" and not push:
                 x.copy_out_sm(x.h_pose13, self.packed)
-            elif host_io:
+            elif host_io and not push:
                 x.h_pose13.copy_(self.packed, non_blocking=True)
         try:
             cur = torch.cuda.current_stream()

@@ -156,10 +156,11 @@ class IterationContext:
                        "nsb_pose_grad_frames")
         return self.packed
 
-    def run(self, c, decoders, rays_o, rays_d, gt_depth, gt_color, w_color=None, handle_dynamic=True, use_color=True, dirs=None):
+    def run(self, c, decoders, rays_o, rays_d, gt_depth, gt_color, w_color=None, handle_dynamic=True, use_color=True, dirs=None, result_to_host=False):
         """Enqueue one iteration on the current stream (inputs already on the device).  Results stay on the device:
         self.loss, self.depth/var/rgb, self.d_rays_o/d, self.d_grid[key], self.d_flat[level]; with `dirs` (camera-frame ray directions
-        [N,3]) also self.d_c2w, produced by the backward kernel itself."""
+        [N,3]) also self.d_c2w, produced by the backward kernel itself.  result_to_host (needs dirs): the CTA that produces d c2w also stores
+        the result block [d_rays_o | d_rays_d | loss | d c2w] into the pinned host block self.h_res (nsb_backward_args.result_dst)."""
         L = _lib.lib()
         n = self._check_inputs(rays_o, rays_d, gt_depth, gt_color)
         call, grids, _ = self.r._call(c, decoders, self.stage, gt_depth if self.render_with_depth else None, self.dev)
@@ -169,6 +170,10 @@ class IterationContext:
         if dirs is not None:
             _require_cuda(dirs, "dirs")
             bw.pose_dirs, bw.d_c2w, bw.pose_counter = dirs.data_ptr(), self.d_c2w.data_ptr(), self.pose_counter.data_ptr()
+        if result_to_host:
+            if dirs is None or self.h_res is None:
+                raise RuntimeError("nice_slam_b200: result_to_host needs dirs and a context with host staging")
+            bw.result_dst, bw.result_src, bw.result_bytes = self._mapped(self.h_res), self.d_res.data_ptr(), self.d_res.numel()
         if self.kind == "track":
             w = 0.5 if w_color is None else w_color
             _lib.check(L.nsb_tracking_iteration(C.byref(inp), C.byref(self.buf), _VP(gt_color.data_ptr()), w, int(handle_dynamic),
@@ -232,7 +237,8 @@ class IterationContext:
         4-6 kernel launches + Python glue).  Inputs are read from the context-owned block (load_device_inputs) or,
         with host_io, copied from the pinned staging block inside the graph; results stay in the context's buffers
         (and, with host_io, are copied to the pinned read-back block inside the graph).  host_io = True: copy-engine transfers
-        (cudaMemcpyAsync nodes); host_io = "sm": the same two blocks moved by nsb_copy_block kernels over the mapped host views.
+        (cudaMemcpyAsync nodes); host_io = "sm": the input block moved by an nsb_copy_block kernel over the mapped host view, the result block
+        stored to pinned memory by the backward's last CTA (with dirs; by a second nsb_copy_block otherwise).
         Re-capture after anything that changes pointers (grids re-created) or the decoders' packed image."""
         ro, rd, gd, gc = self.device_views()
 
@@ -241,8 +247,9 @@ class IterationContext:
                 self.copy_in_sm()                                          # same two blocks, moved by one CTA each over the mapped host views
             elif host_io:
                 self.d_in.copy_(self.h_in, non_blocking=True)             # one H2D copy: rays, sensor depth and colour
-            self.run(c, decoders, ro, rd, gd, gc, dirs=dirs, **kw)     # d c2w comes out of the backward kernel
-            if host_io == "sm":
+            push = host_io == "sm" and dirs is not None               # the backward's last CTA stores the result block to pinned memory itself
+            self.run(c, decoders, ro, rd, gd, gc, dirs=dirs, result_to_host=push, **kw)     # d c2w comes out of the backward kernel
+            if host_io == "sm" and not push:
                 self.copy_out_sm()
             elif host_io:
                 self.h_res.copy_(self.d_res, non_blocking=True)           # one D2H copy: ray gradients, loss, pose gradient
