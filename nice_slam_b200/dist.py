@@ -208,16 +208,18 @@ class ShardedTrackingIteration:
         """CUDA graph of enqueue() (and, with host_io, of the pinned-host copies around it); None if capture fails."""
         x = self.ctx
 
+        sm = host_io in ("sm", "sm_push")
+
         def body():
-            if host_io == "sm":                                    # the blocks moved by nsb_copy_block kernels over the mapped host views
+            if sm:                                                 # the blocks moved by nsb_copy_block launches over the mapped host views
                 x.copy_in_sm()
             elif host_io:
                 x.d_in.copy_(x.h_in, non_blocking=True)
-            push = host_io == "sm" and self.peers is not None and self.fused       # the summing CTA stores [loss | d c2w] to pinned memory itself
+            push = host_io == "sm_push" and self.peers is not None and self.fused       # the summing CTA stores [loss | d c2w] to pinned memory itself
             self.enqueue(out13_ptr=x._mapped(x.h_pose13) if push else None)
-            if host_io == "sm" and not push:
+            if sm and not push:
                 x.copy_out_sm(x.h_pose13, self.packed)
-            elif host_io and not push:
+            elif host_io and not sm:
                 x.h_pose13.copy_(self.packed, non_blocking=True)
         try:
             cur = torch.cuda.current_stream()

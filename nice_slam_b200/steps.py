@@ -237,21 +237,23 @@ class IterationContext:
         4-6 kernel launches + Python glue).  Inputs are read from the context-owned block (load_device_inputs) or,
         with host_io, copied from the pinned staging block inside the graph; results stay in the context's buffers
         (and, with host_io, are copied to the pinned read-back block inside the graph).  host_io = True: copy-engine transfers
-        (cudaMemcpyAsync nodes); host_io = "sm": the input block moved by an nsb_copy_block kernel over the mapped host view, the result block
-        stored to pinned memory by the backward's last CTA (with dirs; by a second nsb_copy_block otherwise).
+        (cudaMemcpyAsync nodes); host_io = "sm": both blocks moved by nsb_copy_block launches over the mapped host views; host_io = "sm_push": the
+        input block as for "sm", the result block stored to pinned memory by the backward's last CTA (needs dirs; else as "sm").
         Re-capture after anything that changes pointers (grids re-created) or the decoders' packed image."""
         ro, rd, gd, gc = self.device_views()
 
+        sm = host_io in ("sm", "sm_push")
+
         def body():
-            if host_io == "sm":
-                self.copy_in_sm()                                          # same two blocks, moved by one CTA each over the mapped host views
+            if sm:
+                self.copy_in_sm()                                          # the input block moved by one nsb_copy_block launch over the mapped host view
             elif host_io:
                 self.d_in.copy_(self.h_in, non_blocking=True)             # one H2D copy: rays, sensor depth and colour
-            push = host_io == "sm" and dirs is not None               # the backward's last CTA stores the result block to pinned memory itself
+            push = host_io == "sm_push" and dirs is not None          # the backward's last CTA stores the result block to pinned memory itself
             self.run(c, decoders, ro, rd, gd, gc, dirs=dirs, result_to_host=push, **kw)     # d c2w comes out of the backward kernel
-            if host_io == "sm" and not push:
+            if sm and not push:
                 self.copy_out_sm()
-            elif host_io:
+            elif host_io and not sm:
                 self.h_res.copy_(self.d_res, non_blocking=True)           # one D2H copy: ray gradients, loss, pose gradient
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()

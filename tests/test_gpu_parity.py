@@ -397,15 +397,15 @@ def test_fused_tracking_iteration_matches_oracle(n_rays):
     ctx.stage_host_inputs(ro, rd, gd, gc.double())
     loss, d_rays = ctx.run_host(c, dec)
     check(loss, d_rays[0], d_rays[1], ctx.pose_grad(dirs_d))
-    # the end-to-end graph forms: copy-engine transfers and nsb_copy_block kernels deliver the same result block to pinned host memory
+    # the end-to-end graph forms: copy-engine transfers, nsb_copy_block kernels and the backward's own store deliver the same result block to pinned host memory
     blocks = []
-    for mode in (True, "sm"):
+    for mode in (True, "sm", "sm_push"):
         ge = ctx.build_graph(c, dec, dirs=dirs_d, host_io=mode)
         ctx.d_in.zero_(); ctx.h_res.zero_()
         ge.replay(); torch.cuda.synchronize()
         check(ctx.h_loss[0], ctx.h_out.view(2, n_rays, 3)[0], ctx.h_out.view(2, n_rays, 3)[1], ctx.h_pose)
         blocks.append(ctx.h_res.clone())
-    assert torch.equal(blocks[0], blocks[1])
+    assert torch.equal(blocks[0], blocks[1]) and torch.equal(blocks[0], blocks[2])
     # split-phase sharded iteration without a process group == the fused one
     sh = ShardedTrackingIteration(ctx)
     packed = sh.run(c, dec, *dev_in[:2], dirs_d, *dev_in[2:]).clone()

@@ -1,5 +1,6 @@
 #!/bin/bash
-# late-round-2 validation on one GPU: smoke(), the GPU suite, the full bench line, the launch list of one mapping iteration
+# late-round-2 validation on one GPU: smoke(), the GPU suite, the full bench line [, the launch list of one mapping iteration]
+#   tools/gpu_r02_late.sh <tag> [ncu]
 tag=${1:-r02late}
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
@@ -15,6 +16,7 @@ print([(x["scene"], round(x["ms_per_step"],3)) for x in d["extra"]["mapping_othe
 print("cpu", d["cpu_baseline"])
 PYEOF
 tail -3 gpurun_out/${tag}_bench.err
+if [ "$2" = "ncu" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${tag}_map_launches.csv python tools/map_launches.py 996 > gpurun_out/${tag}_map_launches.log 2>&1
 python - <<PYEOF
 import csv
@@ -24,3 +26,4 @@ seq=[(r[ki].split("(")[0], float(r[vi])) for r in rows[1:]]
 idx=[i for i,(k,_) in enumerate(seq) if "render_fwd" in k]
 for k,v in seq[idx[-1]:]: print("%-60s %10.1f us" % (k[:60], v/1000 if v>1000 else v))
 PYEOF
+fi
