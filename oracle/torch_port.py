@@ -4,10 +4,10 @@ render-and-backprop hot path.
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
 this file.  The product path (nice_slam_b200/) never does; it fails loudly without its CUDA library.
 
-Parity status: PINNED.  tests/test_oracle_vs_reference.py runs this port side by side with the
-unmodified reference imported from /root/reference (tests/ref_harness.py) and requires bit-identical
-z_vals / outputs / gradients on CPU; tests/golden/*.pt hold outputs of the real reference generated by
-tests/make_golden.py, and this port is re-checked against them wherever /root/reference is absent.
+Parity status: PINNED.  tests/make_golden.py runs this port side by side with the unmodified reference
+imported from /root/reference (shims in tests/ref_harness.py) and asserts bit-identical z_vals / outputs /
+gradients on CPU for every fixture it writes; tests/golden/*.pt hold those outputs of the real reference,
+and tests/test_oracle_golden.py re-checks this port against them wherever /root/reference is absent.
 
 The reference is pure Python over PyTorch; the arithmetic of grid_sample / Linear / sort / cumprod /
 autograd lives in the third-party PyTorch wheel (reference pins pytorch=1.11.0, environment.yaml:81;
