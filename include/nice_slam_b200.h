@@ -79,7 +79,8 @@ size_t nsb_packed_decoder_floats(int level);
 int nsb_version(void);
 const char* nsb_last_error(void);
 /* Process-wide options.  "mlp_backend": 0 = auto (default: tcgen05 tile kernels), 1 = FP32-FMA decoders, 2 = tcgen05 round-1 ray-group
- * kernels, 3 = tcgen05 tile kernels (3xTF32, two CTAs per SM). */
+ * kernels, 3 = tcgen05 tile kernels (3xTF32, two CTAs per SM).  "split_model": 1 (default) = a tile's decoders are spread over CTAs only while
+ * that beats one CTA per tile by wave efficiency, 0 = always for batches of <= 262144 points.  "wgrad_tc", "fwd_f16", "pdl", "small_rays": DESIGN.md. */
 int nsb_set_option(const char* key, int value);
 
 /* Diagnostic: resident CTAs per SM of the tile-centric tensor-core kernels (2 = the design point: two tiles in flight per SM). */

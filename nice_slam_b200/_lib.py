@@ -149,6 +149,9 @@ def lib():
         f16 = os.environ.get("NSB_FWD_F16")                  # 1 = forward decoders with FP16 hi|lo operands (kind::f16) instead of 3xTF32
         if f16 is not None:
             h.nsb_set_option(b"fwd_f16", int(f16))
+        sm = os.environ.get("NSB_SPLIT_MODEL")               # 0 = per-decoder items for every batch of <= 262144 points (default: by wave efficiency)
+        if sm is not None:
+            h.nsb_set_option(b"split_model", int(sm))
         _LIB = h
     return _LIB
 

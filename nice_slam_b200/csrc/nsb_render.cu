@@ -1016,6 +1016,7 @@ static void choose_config(int n_items, int S, int rows, bool bwd, int wbytes, in
   *smem = smem_layout(wbytes, max_pts, r, w, rows, bwd, nullptr, nullptr);
 }
 
+static int g_split_model = 1;      // tile kernels: per-decoder items only while they beat all-decoder items by wave efficiency (0: split whenever N*S <= kSplitMaxPts)
 static int g_pdl = 0;              // iteration entry points: the backward launch as a programmatic dependent of the forward launch
 static int g_fwd_f16 = 0;          // tile-kernel forward with FP16 hi|lo operands (kind::f16, K = 16 per MMA) instead of 3xTF32; see nsb_tile.cuh mma_unit_h
 static int g_wgrad_tc = 1;         // decoder weight gradients on the tensor cores when the forward kept the layer outputs (0: FP32-FMA pass)
@@ -1053,6 +1054,15 @@ static bool tile_ws_plan(void* ws, size_t bytes, int N, int S, int n_dec, bool b
   if (!ws || (reinterpret_cast<uintptr_t>(ws) & 15)) return false;
   bytes &= ~size_t(15);
   int split = ((long long)N * S <= kSplitMaxPts && n_dec > 1) ? n_dec : 1;
+  if (split > 1 && g_split_model) {
+    // Splitting a tile's decoders over CTAs buys parallelism for batches that do not fill the GPU, at the price of one prologue / ray-completion
+    // pass per decoder: measured on the configs[4] sweep, a per-decoder item sustains ~0.81x (three decoders) of the throughput of the same work
+    // inside all-decoder items.  Once the tiles alone fill the resident slots (two CTAs per SM), compare the two forms by their wave efficiency.
+    const long long tiles = tile_count((long long)N * S), slots = 2ll * sm_count();
+    auto wave_eff = [&](long long items) { const long long waves = (items + slots - 1) / slots; return (double)items / (double)(waves * slots); };
+    const double eff_one = wave_eff(tiles), eff_split = wave_eff(tiles * n_dec) * (1.0 - 0.095 * (n_dec - 1));
+    if (tiles >= slots && eff_one >= eff_split) split = 1;
+  }
   if (bytes < tile_ws_need(N, S, split, bwd)) split = 1;
   if (bytes < tile_ws_need(N, S, split, bwd)) return false;
   out->split = split;
@@ -1145,6 +1155,7 @@ extern "C" int nsb_set_option(const char* key, int value) {
   if (key && !strcmp(key, "wgrad_tc")) { g_wgrad_tc = value != 0; return NSB_OK; }
   if (key && !strcmp(key, "fwd_f16")) { g_fwd_f16 = value != 0; return NSB_OK; }
   if (key && !strcmp(key, "pdl")) { g_pdl = value != 0; return NSB_OK; }
+  if (key && !strcmp(key, "split_model")) { g_split_model = value != 0; return NSB_OK; }
   if (key && !strcmp(key, "small_rays")) { if (value < 0) { set_error("small_rays must be >= 0"); return NSB_ERR_ARG; } g_small_rays = value; return NSB_OK; }
   if (key && !strcmp(key, "mlp_backend")) { if (value < 0 || value > 3) { set_error("mlp_backend must be 0 (auto = tile kernels), 1 (FP32-FMA), 2 (tcgen05, round-1 ray-group kernels) or 3 (tcgen05 tile kernels)"); return NSB_ERR_ARG; } g_mlp_backend = value; return NSB_OK; }
   set_error("unknown option %s", key ? key : "(null)"); return NSB_ERR_ARG;

@@ -867,3 +867,32 @@ def test_copy_block_moves_pinned_host_blocks_both_ways(nbytes):
     pageable = torch.zeros(64, dtype=torch.uint8)
     if not L.nsb_host_device_pointer(C.c_void_p(pageable.data_ptr())):      # (a system with pageable-memory access may accept it)
         assert b"page-locked" in L.nsb_last_error()
+
+
+@pytest.mark.parametrize("stage,n_rays", [("color", 4096), ("fine", 2500)])
+def test_item_split_policy_does_not_change_the_bits(stage, n_rays):
+    """Medium batches: one CTA per tile (all decoders) vs one CTA per (tile, decoder) -- the dispatch picks by wave efficiency (option
+    split_model); both forms evaluate the same arithmetic: outputs bit-identical, ray gradients equal up to the order of their float64 partial sums."""
+    from nice_slam_b200 import _lib
+    L = _lib.lib()
+    sc = su.load_scenes()["room0"]
+    grids, dec_state = su.make_grids(sc, "soft"), su.load_decoders("soft")
+    renderer, c, dec = make_renderer(sc, grids, dec_state, DEV)
+    ro, rd, gd, gc = su.make_rays(sc, n_rays, seed=4242)
+    ro, rd, gd = ro.to(DEV), rd.to(DEV), gd.to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    s1 = torch.randn(n_rays, dtype=torch.float64, device=DEV, generator=g); s2 = torch.randn(n_rays, 3, device=DEV, generator=g)
+    res = []
+    try:
+        for model in (1, 0):
+            assert L.nsb_set_option(b"split_model", model) == 0
+            r1 = ro.clone().requires_grad_(True); r2 = rd.clone().requires_grad_(True)
+            d, u, col = renderer.render_batch_ray(c, dec, r2, r1, DEV, stage, gt_depth=gd)
+            ga = torch.autograd.grad((d * s1).sum() + (col * s2).sum() + u.sum(), (r1, r2))
+            res.append((d.detach(), u.detach(), col.detach(), ga[0], ga[1]))
+    finally:
+        L.nsb_set_option(b"split_model", 1)
+    for a, b in zip(res[0][:3], res[1][:3]):
+        assert torch.equal(a, b)
+    for a, b in zip(res[0][3:], res[1][3:]):        # per-ray sums: float64 partial sums added in a different order before the cast to float32
+        assert rel(a, b) < 1e-6
