@@ -212,15 +212,36 @@ def extra_workloads(sc, renderer, c, dec, dev, flush, peak):
         torch.cuda.synchronize()
         return sum(a.elapsed_time(b) for a, b in evs) / steps
 
+    def graphed(fn):
+        """(callable, how): fn captured into a CUDA graph -- these iterations are 2-8 launches of 0.05-0.6 ms each, and with stream launches a slow
+        or busy host makes them enqueue-bound (r02ae: 0.87 instead of 0.63 ms for the same mapping iteration) -- or fn itself if capture fails."""
+        try:
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                fn(); fn()
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            g.replay(); torch.cuda.synchronize()
+            return g.replay, "CUDA graph replay"
+        except Exception as e:                                     # noqa: BLE001
+            torch.cuda.synchronize()
+            return fn, "stream launches (graph capture failed: %s)" % type(e).__name__
+
     out = {}
     n = 996
     ro, rd, dirs, gd, gc = [t.to(dev) for t in make_batch(sc, n, 101)]
     ctx = IterationContext(renderer, n, "color", dev, kind="map", grad_grids=("grid_middle", "grid_fine", "grid_color"), grad_decoders=("color",))
     gcf = gc.float()
-    ms = time_steps(lambda: ctx.run(c, dec, ro, rd, gd, gcf), 100)
+    step, how = graphed(lambda: ctx.run(c, dec, ro, rd, gd, gcf))
+    ms = time_steps(step, 100)
     bpr = 48 * 3 * 1024 * 2
     out["mapping_configs1"] = {"workload": "room0 mapping iteration, 996 rays x 48, stage color, dense voxel grads (middle+fine+color) + colour-decoder grads",
-                               "ms_per_step": ms, "rays_per_s": n / (ms * 1e-3), "algorithmic_bytes_per_ray": bpr,
+                               "launch": how, "ms_per_step": ms, "rays_per_s": n / (ms * 1e-3), "algorithmic_bytes_per_ray": bpr,
                                "hbm_frac": n * bpr / (ms * 1e-3) / 1e9 / peak}
     # the same iteration inside the native mapper loop: frustum-selected voxels (on-GPU mask of a synthetic frame), compact gradients,
     # fused Adam in place on the grids + on the colour decoder (nice_slam_b200/mapping.py) -- what one joint_iter of Mapper.optimize_map costs
@@ -254,8 +275,9 @@ def extra_workloads(sc, renderer, c, dec, dev, flush, peak):
         for nn, steps in ((256, 100), (1024, 100), (4096, 40), (16384, 12), (65536, 5)):
             ro, rd, dirs, gd, gc = [t.to(dev) for t in make_batch(sc, nn, 200 + nn)]
             cx = IterationContext(rr, nn, "color", dev, kind="track", host_staging=False)
-            ms = time_steps(lambda: cx.run(c, dec, ro, rd, gd, gc), steps)
-            sweep.append({"rays": nn, "samples": S, "ms_per_step": ms, "rays_per_s": nn / (ms * 1e-3),
+            step, how = graphed(lambda: cx.run(c, dec, ro, rd, gd, gc))
+            ms = time_steps(step, steps)
+            sweep.append({"rays": nn, "samples": S, "launch": how, "ms_per_step": ms, "rays_per_s": nn / (ms * 1e-3),
                           "hbm_frac": nn * S * 3 * 1024 / (ms * 1e-3) / 1e9 / peak})
             del cx
     out["sweep_tracking_iteration"] = sweep
