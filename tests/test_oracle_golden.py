@@ -292,3 +292,36 @@ def test_keyframe_overlap_oracle_matches_real_mapper():
     # the reference draws its pixels with the torch RNG first; only the numpy stream matters for the permutation
     rng = np.random.RandomState(case["numpy_seed"])
     assert [int(x) for x in kf.select(per, case["k"], rng)] == case["selected"]
+
+
+@pytest.mark.parametrize("stage,n_samples,n_surface,n_rays", [("color", 5, 3, 37), ("fine", 32, 16, 1), ("middle", 16, 16, 61),
+                                                              ("color", 80, 16, 9), ("coarse", 32, 16, 23), ("color", 32, 0, 19)])
+def test_the_two_oracles_agree_on_ragged_shapes(stage, n_samples, n_surface, n_rays):
+    """Shapes the reference fixtures do not hold (other sample counts, a single ray, no near-surface samples, some zero sensor depths):
+    the C restatement against the torch port -- z_vals bit-exact, outputs and gradients at the path's tolerance.  (The torch port is the one
+    pinned bit for bit to the reference; this keeps the C oracle, which smoke() and the GPU tests use at these shapes, honest.)"""
+    sc = su.load_scenes()["room0"]
+    grids, dec, bound = su.make_grids(sc, "soft"), su.load_decoders("soft"), su.scene_bound(sc)
+    ro, rd, gd, _ = su.make_rays(sc, n_rays, seed=1000 + n_rays)
+    gd = gd.clone()
+    gd[::5] = 0.0                                                        # rays without a sensor depth (Renderer.py:133-149)
+    with_depth = stage != "coarse" and n_surface > 0
+    gt = gd if with_depth else None
+    g = torch.Generator().manual_seed(n_samples)
+    s_d = torch.randn(n_rays, dtype=torch.float64, generator=g)
+    s_v = torch.randn(n_rays, dtype=torch.float64, generator=g)
+    s_c = torch.randn(n_rays, 3, generator=g)
+    r_o = ro.clone().requires_grad_(True); r_d = rd.clone().requires_grad_(True)
+    gg = {k: v.clone().requires_grad_(k[5:] in LV[stage]) for k, v in grids.items()}
+    d, u, c, aux = tp.render_batch_ray(gg, dec, r_d, r_o, stage, gt, bound, n_samples=n_samples, n_surface=n_surface, return_aux=True)
+    ((d * s_d).sum() + (u * s_v).sum() + (c * s_c).sum()).backward()
+    scene = co.Scene(grids, dec, bound, coarse_enlarge=sc["coarse_bound_enlarge"], n_samples=n_samples, n_surface=n_surface)
+    f = scene.forward(stage, ro, rd, gt)
+    assert np.array_equal(f["z_vals"], aux["z_vals"].numpy())
+    assert rel(f["depth"], d.detach()) < TOL and rel(f["var"], u.detach()) < TOL
+    if stage == "color":
+        assert rel(f["rgb"], c.detach()) < TOL
+    b = scene.backward(stage, ro, rd, gt, s_d, s_v, s_c, grad_grids=["grid_" + x for x in LV[stage]], grad_decoders=[])
+    assert rel(b["d_rays_o"], r_o.grad) < TOL and rel(b["d_rays_d"], r_d.grad) < TOL
+    for x in LV[stage]:
+        assert rel(b["d_grid_" + x], gg["grid_" + x].grad) < TOL, x
