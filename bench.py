@@ -12,8 +12,11 @@ reduction.  N > 1: the global batch of 200*N rays is ray-sharded (weak scaling) 
 batch-global ops require (depth maxima MAX, residual all-gather for the median, SUM of loss + pose gradient) over NCCL.
 The Adam step on the 7 pose numbers stays in PyTorch and is outside the timed region of both arms.
 
-`value` : rays/s with inputs resident in HBM; `e2e`: same through IterationContext.run_host (pinned host inputs, H2D and D2H
-inside the timed region).  --impl reference times the reference algorithm's CPU path (oracle port, PyTorch CPU, all host
+`value` : rays/s with inputs resident in HBM; `e2e`: the same iteration through IterationContext.build_graph(host_io=...): pinned host
+inputs -> device, iteration, loss + ray / pose gradients -> pinned host, all inside the timed region, followed by a stream synchronize (the
+caller reads the result).  The two host blocks can travel as copy-engine nodes ("dma"), as nsb_copy_block kernels over the mapped pinned
+memory ("sm"), or with the result stored by the backward's last CTA ("sm_push"); all three are timed, checked to deliver identical bytes, and
+the fastest is reported (`e2e.ms_per_step_by_transport` keeps the three figures).  --impl reference times the reference algorithm's CPU path (oracle port, PyTorch CPU, all host
 threads) on the same batch.  Every timed quantity uses CUDA events on the launching stream, max over ranks.
 """
 import argparse
