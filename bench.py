@@ -130,6 +130,16 @@ def make_batch(sc, n, seed):
     return ro[sel].contiguous(), rd[sel].contiguous(), dirs[sel].contiguous(), gd[sel].contiguous(), gc[sel].contiguous()
 
 
+def workload_config(world):
+    """`config` of BOTH arms: the reference arm times the reference's CPU implementation on this arm's configuration, so the two lines carry
+    the same dict; what is specific to a run (launch form, exchange back-end, the reference arm's bounded sample) sits next to it (`run`)."""
+    return {"workload": WORKLOAD, "rays_per_step": RAYS_PER_GPU * world,
+            "l2": "flushed between steps on the GPU (256 MiB memset outside the event pair)",
+            "batch": "every step replays the same synthetic ray batch (fixed seed); grids and decoders are not updated between steps",
+            "parallelism": "ray-sharded x%d" % world,
+            "timing": "GPU arm: sum of per-step CUDA-event pairs, max over ranks; reference arm: wall clock around the timed steps on the host"}
+
+
 # ------------------------------------------------------------------------------------------------ reference arm (CPU)
 def cpu_iteration_fn(sc, batch):
     """One tracking iteration of the reference algorithm on the host CPUs (oracle port = same torch ops as the reference)."""
@@ -190,7 +200,8 @@ def run_reference(args):
     value = n_rays / (ms * 1e-3)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": WORKLOAD, "device": "host CPU", "rays_per_step": n_rays},
+            "data": "synthetic", "config": workload_config(args.gpus),
+            "run": {"device": "host CPU", "rays_per_timed_step": n_rays},
             "cpu_baseline": {"value": value, "unit": "rays/s", "cores": best[1], "kind": "port",
                              "sample": "%d tracking iterations on %d of the 200 rays per step (oracle/torch_port.py, PyTorch CPU, %d threads of %d cores)"
                                        % (args.steps, n_rays, best[1], os.cpu_count() or 1)},
@@ -678,11 +689,9 @@ def run_native(args):
     peak, peak_src = peaks()
     line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rays_per_step": rays, "l2": "flushed between steps (256 MiB memset outside the event pair)",
-                       "batch": "every step replays the same synthetic ray batch (fixed seed); grids and decoders are not updated between steps",
-                       "launch": "CUDA graph replay (one graph per iteration)" if (sharded is None or use_graph) else "stream launches + NCCL",
-                       "parallelism": "ray-sharded x%d" % world, "exchange": exchange if sharded is not None else "none (single GPU)",
-                       "timing": "sum of per-step CUDA-event pairs, max over ranks"},
+            "config": workload_config(world),
+            "run": {"launch": "CUDA graph replay (one graph per iteration)" if (sharded is None or use_graph) else "stream launches + NCCL",
+                    "exchange": exchange if sharded is not None else "none (single GPU)"},
             "clocks": clocks,
             "e2e": {"value": rays / (e2e_ms / args.steps * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": ctx.h2d_bytes,
                     "d2h_bytes_per_step": ctx.d2h_bytes if sharded is None else 13 * 8, "ms_per_step": e2e_ms / args.steps,

@@ -16,7 +16,7 @@ for k in ${SKIP1:+} $([ -n "$SKIP1" ] || echo 1) $n; do
 import json
 try:
     d=json.loads(open("gpurun_out/${tag}_bench_n$k.json").read().strip().splitlines()[-1])
-    print("N=$k ms/step", round(d["ms_per_step"],5), "rays/s", round(d["value"]), "e2e", round(d["e2e"]["ms_per_step"],5), "launches", d["gpu_launches"], d["config"]["exchange"])
+    print("N=$k ms/step", round(d["ms_per_step"],5), "rays/s", round(d["value"]), "e2e", round(d["e2e"]["ms_per_step"],5), "launches", d["gpu_launches"], d["run"]["exchange"])
     m=d["extra"]["mapping_sharded_masked"]; print("  sharded mapping:", round(m["ms_per_step"],4), "collectives", m["collectives_per_step"], m["launch"])
     print("  scenes:", [(x["scene"], round(x["ms_per_step"],3), x["collectives_per_step"]) for x in d["extra"]["mapping_other_scenes"]])
 except Exception as e:
